@@ -1,0 +1,92 @@
+"""ctypes binding of libmcedm_b200.so (the C ABI declared in include/mcedm_b200.h).
+
+The library is built in-tree by ``mcedm_b200.build``.  There is no fallback: if the shared object is
+missing, or a call fails, a RuntimeError is raised with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmcedm_b200.so")
+
+_vp = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_d = C.c_double
+_ip = C.POINTER(C.c_int)
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> argtypes; every function returns int (0 = ok) unless listed in _RESTYPES
+_PROTOTYPES = {
+    "mcedm_abi_version": [],
+    "mcedm_check_watchdog": [_vp],
+    "mcedm_conv_igemm": [_vpp, _i, _ip, _ip, _ip, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp],
+    "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
+    "mcedm_conv_direct_ref": [_vpp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+}
+_RESTYPES = {"mcedm_last_error": C.c_char_p}
+
+_lib = None
+
+
+class McedmError(RuntimeError):
+    pass
+
+
+def exported_names():
+    """Every symbol include/mcedm_b200.h declares (used by the CPU-side ABI test)."""
+    return sorted(list(_PROTOTYPES) + list(_RESTYPES))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise McedmError(
+                f"{LIB_PATH} is missing: build it with `python -m mcedm_b200.build` "
+                "(there is no CPU or PyTorch fallback for the sm_100a kernels)")
+        l = C.CDLL(LIB_PATH)
+        for name, args in _PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        for name, res in _RESTYPES.items():
+            fn = getattr(l, name)
+            fn.argtypes = []
+            fn.restype = res
+        if l.mcedm_abi_version() != 1:
+            raise McedmError("libmcedm_b200.so ABI version mismatch; rebuild with `python -m mcedm_b200.build`")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mcedm_last_error()
+        raise McedmError(f"{what or 'mcedm call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def int_array(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def ptr_array(tensors):
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check_watchdog():
+    check(lib().mcedm_check_watchdog(stream_ptr()), "watchdog")

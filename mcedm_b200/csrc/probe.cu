@@ -1,0 +1,148 @@
+// Bring-up / checker kernels. NOT on the product path:
+//   * mcedm_probe_umma      — one-CTA tcgen05 experiment used by tests/ to pin down UMMA descriptor
+//                             behaviour on real sm_100a silicon (row-shifted K-major A tiles with the
+//                             descriptor base_offset field; MN-major B tiles), which decides what the
+//                             fast kernels may rely on.
+//   * mcedm_conv_direct_ref — plain CUDA-core direct convolution with the same segment semantics as
+//                             mcedm_conv_igemm, used by the GPU tests as an on-device cross-check.
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+#include <cuda_bf16.h>
+
+namespace mcedm {
+
+// A: [a_rows x 64] bf16 row-major (a_rows <= 256), loaded by one TMA box into a 1024-aligned SW128 tile.
+// Bm: [64 x 64] bf16 row-major. b_mn_major == 0: Bm is [N][K] (K-major);  == 1: Bm is [K][N] (MN-major).
+// D[128 x 64] = A[row_shift : row_shift+128, :] * B^T, using an A descriptor whose start address is
+// advanced by row_shift*128 bytes and whose base_offset field is `base_offset`.
+__global__ void __launch_bounds__(128, 1)
+probe_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int a_rows,
+                  int row_shift, int base_offset, int b_mn_major, float* out, unsigned int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;                 // up to 256 rows * 128 B = 32 KB
+  uint8_t* b_smem = smem + 32768;         // 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 8192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], (uint32_t)(a_rows * 128 + 8192));
+    tma_load_2d(a_smem, &tm_a, &bars[0], 0, 0);
+    tma_load_2d(b_smem, &tm_b, &bars[0], 0, 0);
+    mbar_wait(&bars[0], 0, err, 0x900);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, b_mn_major);
+    const uint32_t a_base = smem_u32(a_smem) + row_shift * 128;
+    const uint32_t b_base = smem_u32(b_smem);
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t ad = umma_desc_k_sw128(a_base + k * 32, (uint32_t)base_offset);
+      const uint64_t bd = b_mn_major ? umma_desc_mn_sw128(b_base + k * 2048, 8192) : umma_desc_k_sw128(b_base + k * 32);
+      umma_f16(tmem_base, ad, bd, idesc, (uint32_t)(k != 0));
+    }
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0, err, 0x901);
+  tc_fence_after();
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+__global__ void conv_direct_ref_kernel(const __nv_bfloat16* s0, const __nv_bfloat16* s1, const __nv_bfloat16* s2,
+                                       const __nv_bfloat16* s3, const int* seg, int n_seg,
+                                       const __nv_bfloat16* w, const float* bias, int B, int H, int W, int N,
+                                       float* out, const float* res, int res_mode) {
+  const long long total = (long long)B * H * W * N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % N);
+  const long long pix = idx / N;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int b = (int)(pix / ((long long)W * H));
+  const __nv_bfloat16* srcs[4] = {s0, s1, s2, s3};
+  float acc = bias ? bias[n] : 0.f;
+  for (int s = 0; s < n_seg; ++s) {
+    const int yy = y + seg[3 * s + 1], xx = x + seg[3 * s + 2];
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const __nv_bfloat16* a = srcs[seg[3 * s]] + (((long long)b * H + yy) * W + xx) * 64;
+    const __nv_bfloat16* wr = w + ((long long)s * N + n) * 64;
+    float part = 0.f;
+    for (int c = 0; c < 64; ++c) part += __bfloat162float(a[c]) * __bfloat162float(wr[c]);
+    acc += part;
+  }
+  if (res_mode == 1) {
+    acc += res[pix * N + n];
+  } else if (res_mode == 2) {
+    acc += res[(((long long)b * (H / 2) + y / 2) * (W / 2) + x / 2) * N + n];
+  } else if (res_mode == 3) {
+    const long long Ws = 2 * W;
+    const float* r0 = res + (((long long)b * 2 * H + 2 * y) * Ws + 2 * x) * N + n;
+    acc += 0.25f * ((r0[0] + r0[N]) + (r0[Ws * N] + r0[Ws * N + N]));
+  }
+  out[idx] = acc;
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int row_shift, int base_offset,
+                                int b_mn_major, float* out, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(a_rows >= 128 && a_rows <= 256 && row_shift >= 0 && row_shift + 128 <= a_rows,
+                "probe_umma: bad a_rows/row_shift");
+  CUtensorMap tm_a, tm_b;
+  int rc = make_tmap_rows64_bf16(&tm_a, a, a_rows, a_rows);
+  if (rc) return rc;
+  rc = make_tmap_rows64_bf16(&tm_b, bm, 64, 64);
+  if (rc) return rc;
+  unsigned int* err = watchdog_ptr();
+  MCEDM_REQUIRE(err != nullptr, "probe_umma: no watchdog word");
+  const int smem = 1024 + 32768 + 8192 + 64;
+  MCEDM_CUDA(cudaFuncSetAttribute(probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_umma_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_a, tm_b, a_rows, row_shift,
+                                                                               base_offset, b_mn_major, out, err);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_conv_direct_ref(const void* const* src, int n_src, const int* seg_dev, int n_seg,
+                                     const void* w_packed, const float* bias, int B, int H, int W, int N, float* out,
+                                     const float* res, int res_mode, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n_src >= 1 && n_src <= 4, "conv_direct_ref: n_src");
+  const __nv_bfloat16* s[4];
+  for (int i = 0; i < 4; ++i) s[i] = reinterpret_cast<const __nv_bfloat16*>(src[i < n_src ? i : 0]);
+  const long long total = (long long)B * H * W * N;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  conv_direct_ref_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      s[0], s[1], s[2], s[3], seg_dev, n_seg, reinterpret_cast<const __nv_bfloat16*>(w_packed), bias, B, H, W, N, out,
+      res, res_mode);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,34 @@
+// Host-side runtime shared by the launchers: error reporting, the device watchdog word,
+// SM count and TMA tensor-map construction (cuTensorMapEncodeTiled through the runtime's
+// driver entry point, so the library does not link libcuda directly).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mcedm {
+
+// Records `msg` as the library's last error (thread-local) and returns `code`.
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define MCEDM_CUDA(x)                                                   \
+  do {                                                                  \
+    cudaError_t _e = (x);                                               \
+    if (_e != cudaSuccess) return ::mcedm::cuda_fail(_e, #x);           \
+  } while (0)
+#define MCEDM_REQUIRE(cond, ...)                                        \
+  do {                                                                  \
+    if (!(cond)) return ::mcedm::fail(-1, __VA_ARGS__);                 \
+  } while (0)
+
+// Device word the bounded mbarrier waits write on timeout (see ptx.cuh). Allocated on first use.
+unsigned int* watchdog_ptr();
+int num_sms();
+
+// NHWC bf16 activation tensor [B, H, W, C] viewed by TMA as (C, W, H, B), box (64, box_w, box_h, 1),
+// SWIZZLE_128B, zero fill outside the tensor (this is what implements the conv's zero padding).
+int make_tmap_nhwc_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int box_w, int box_h);
+// Row-major bf16 matrix [rows, 64] (packed weights), box (64, box_rows), SWIZZLE_128B.
+int make_tmap_rows64_bf16(CUtensorMap* out, const void* ptr, long long rows, int box_rows);
+
+}  // namespace mcedm
