@@ -63,6 +63,75 @@ MCEDM_API int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg
                      int out_bf16, const float* res, int res_mode, float* stats_partial, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* K2  GroupNorm statistics / fused GroupNorm + scale-shift + SiLU + resample                     */
+/*     (models/adm_blocks.py:86-97 GroupNorm; :161, :163-166, :175, :403 call sites)              */
+/* -------------------------------------------------------------------------------------------- */
+/* partial[t][g][0..1] = (sum, sum of squares) over pixel tile t (128 pixels) and group g (4 channels)
+ * of an fp32 [n_pixels, 64] tensor.  Same format conv_igemm/conv_in emit from their epilogues. */
+MCEDM_API int mcedm_gn_stats(const float* x, long long n_pixels, float* partial, void* stream);
+/*
+ * out = act( GroupNorm(x) * (1 + scale) + shift ), optionally resampled, written as bf16 NHWC.
+ *   x            fp32 NHWC [B,Hin,Win,64]; partial = its tile statistics [B*Hin*Win/128][16][2]
+ *   gamma, beta  fp32 [64] (slice of the GroupNorm affine for these 64 channels)
+ *   scale_shift  NULL, or fp32 with scale[c] at [b*emb_batch_stride + c] and shift[c] at
+ *                [b*emb_batch_stride + emb_shift_offset + c]  (affine(emb).chunk(2), adm_blocks.py:163-165;
+ *                emb_batch_stride = 0 broadcasts one embedding over the batch, as in sampling)
+ *   act          0 identity (norm2), 1 SiLU
+ *   resample     0 none | 1 nearest x2 (out is [B,2Hin,2Win,64]) | 2 2x2 mean (out is [B,Hin/2,Win/2,64]);
+ *                this is the resampling Conv2d applies before its 3x3 filter (adm_blocks.py:73-77)
+ *   out_raw_bf16 NULL, or receives bf16(x) (operand of the block's 1x1 skip projection)
+ */
+MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
+                             const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int act,
+                             int resample, int B, int Hin, int Win, void* out_bf16, void* out_raw_bf16, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */
+/* -------------------------------------------------------------------------------------------- */
+/* qkv bf16 [B,L,192] = (q|k|v) x 64 channels; out bf16 [B,L,64]; softmax(q.k/8) in fp32. L % 128 == 0. */
+MCEDM_API int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* embedding MLP, first conv, output head                                                        */
+/* -------------------------------------------------------------------------------------------- */
+/* emb = silu(L1(silu(L0([cos|sin](c_noise x freqs)))))  (adm_blocks.py:185-199, :367-379), then
+ * out[a][b][0:128] = aff_w[a] @ emb[b] + aff_b[a] for the n_aff blocks (adm_blocks.py:163).
+ * freqs fp32 [32]; w0,w1 fp32 [64,64]; aff_w fp32 [n_aff,128,64]; emb_out NULL or [Bemb,64]. */
+MCEDM_API int mcedm_emb_mlp(const float* c_noise, const float* freqs, const float* w0, const float* b0,
+                            const float* w1, const float* b1, const float* aff_w, const float* aff_b, int n_aff,
+                            int Bemb, float* emb_out, float* out, void* stream);
+/* 3x3 conv of cat([cond, x]) (NCHW fp32, Cc + Cx <= 8 channels) -> fp32 NHWC [B,H,W,64] + tile statistics
+ * (adm_blocks.py:319-340 cat_conditioning, :384-385). w fp32 [64, Cc+Cx, 3, 3] in the reference layout. */
+MCEDM_API int mcedm_conv_in(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
+                            int B, int H, int W, float* out, float* stats_partial, void* stream);
+/* dst NCHW fp32 [B,Cout,H,W] = first Cout channels of src NHWC fp32 [B,H,W,Cs] (out_conv result, :403). */
+MCEDM_API int mcedm_head_to_nchw(const float* src, int Cs, int Cout, int B, int H, int W, float* dst, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* K4/K5  EDM preconditioning and stochastic-Heun sampler updates with mask blending              */
+/*        (models/mcedm.py:199-211, :443-461, :570-638)                                           */
+/* -------------------------------------------------------------------------------------------- */
+/* All tensors NCHW; state fp64, network I/O fp32, mask fp32 (1 = missing/generated, 0 = observed). */
+/* x = cond[:, :C]*(1-mask) + (noise*t0)*mask                                   (mcedm.py:590-597) */
+MCEDM_API int mcedm_edm_init(const float* noise, const float* cond, int Ccond, const float* mask, double t0, int B,
+                             int C, int H, int W, double* x, void* stream);
+/* x_hat = x_cur + coef*eps*mask ; x_in = c_in*float(x_hat)       coef = sqrt(t_hat^2-t_cur^2)*S_noise (:608) */
+MCEDM_API int mcedm_edm_churn(const double* x_cur, const double* eps, const float* mask, double coef, float c_in,
+                              long long total, double* x_hat, float* x_in, void* stream);
+/* D = c_skip*float(x_hat)+c_out*F ; d_cur = (x_hat-D)/t_hat ; x_next = x_hat+(t_next-t_hat)*d_cur*mask ;
+ * x_in = c_in_next*float(x_next) (x_in, D_out may be NULL)                                 (:612-618) */
+MCEDM_API int mcedm_edm_euler(const double* x_hat, const float* F, const float* mask, double t_hat, double t_next,
+                              float c_skip, float c_out, float c_in_next, long long total, double* d_cur,
+                              double* x_next, float* x_in, float* D_out, void* stream);
+/* second-order correction                                                                  (:621-628) */
+MCEDM_API int mcedm_edm_correct(const double* x_hat, const double* x_e, const float* F2, const double* d_cur,
+                                const float* mask, double t_hat, double t_next, float c_skip, float c_out,
+                                long long total, double* x_next, float* D_out, void* stream);
+/* D[b] = c_skip[b*stride]*x[b] + c_out[b*stride]*F[b]   (mcedm.py:210, :460); chw = elements per sample */
+MCEDM_API int mcedm_edm_precond_out(const float* x, const float* F, const float* c_skip, const float* c_out,
+                                    int coef_stride, int B, long long chw, float* D, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* bring-up / checker kernels (tests only; not on the product path)                              */
 /* -------------------------------------------------------------------------------------------- */
 MCEDM_API int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int row_shift, int base_offset, int b_mn_major,
@@ -71,6 +140,8 @@ MCEDM_API int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int ro
 MCEDM_API int mcedm_conv_direct_ref(const void* const* src, int n_src, const int* seg_dev, int n_seg, const void* w_packed,
                           const float* bias, int B, int H, int W, int N, float* out, const float* res, int res_mode,
                           void* stream);
+/* fp32 CUDA-core attention on the same bf16 qkv (out fp32 [B,L,64]) */
+MCEDM_API int mcedm_attention_ref(const void* qkv_bf16, int B, int L, float* out_f32, void* stream);
 
 #ifdef __cplusplus
 }

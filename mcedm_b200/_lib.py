@@ -23,6 +23,18 @@ _PROTOTYPES = {
     "mcedm_abi_version": [],
     "mcedm_check_watchdog": [_vp],
     "mcedm_conv_igemm": [_vpp, _i, _ip, _ip, _ip, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp],
+    "mcedm_gn_stats": [_vp, C.c_longlong, _vp, _vp],
+    "mcedm_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mcedm_attention": [_vp, _i, _i, _vp, _vp],
+    "mcedm_attention_ref": [_vp, _i, _i, _vp, _vp],
+    "mcedm_emb_mlp": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "mcedm_conv_in": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "mcedm_head_to_nchw": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "mcedm_edm_init": [_vp, _vp, _i, _vp, _d, _i, _i, _i, _i, _vp, _vp],
+    "mcedm_edm_churn": [_vp, _vp, _vp, _d, _f, C.c_longlong, _vp, _vp, _vp],
+    "mcedm_edm_euler": [_vp, _vp, _vp, _d, _d, _f, _f, _f, C.c_longlong, _vp, _vp, _vp, _vp, _vp],
+    "mcedm_edm_correct": [_vp, _vp, _vp, _vp, _vp, _d, _d, _f, _f, C.c_longlong, _vp, _vp, _vp],
+    "mcedm_edm_precond_out": [_vp, _vp, _vp, _vp, _i, _i, C.c_longlong, _vp, _vp],
     "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
     "mcedm_conv_direct_ref": [_vpp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
 }

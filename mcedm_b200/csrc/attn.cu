@@ -1,0 +1,299 @@
+// K3 — fused single-head self-attention at the low-resolution U-Net levels on tcgen05.
+//
+// Replaces AttentionOp.forward + the value einsum of UNetBlock.forward
+// (models/adm_blocks.py:103-109, :176-178):
+//     w = softmax_j( sum_c q[c,i] * k[c,j] / sqrt(64) )   (fp32),   a[c,i] = sum_j w[i,j] * v[c,j]
+// for one head of 64 channels over L = H*W tokens (L = 1024 at 32x32).  The reference materialises
+// the L x L weight matrix in HBM (4 MB per sample per block); here it never leaves the SM.
+//
+// Input : qkv bf16 [B, L, 192] = (q | k | v) blocks of 64 channels, written by the qkv 1x1 conv
+//         (conv_igemm with N = 192; the reference's per-channel q/k/v interleave,
+//         adm_blocks.py:175-176, is undone by permuting the weight rows once at pack time).
+// Output: a bf16 [B, L, 64] (operand of the proj 1x1 conv).
+//
+// One CTA = 128 queries of one sample. Two passes over the keys in blocks of 128:
+//   pass 1: S = Q K^T on tensor cores -> TMEM; softmax warps keep a running (max, sum) per row;
+//   pass 2: S again, P = exp2((S - max) * log2e/8) -> bf16 -> swizzled smem, O += P V on tensor cores.
+// The second QK^T costs 50 % more MMA work but removes every accumulator rescale; the kernel is
+// bound by the exp/convert work of the 4 softmax warps, not by the tensor pipe.
+//   warp 0 : TMA producer (Q once; K blocks in pass 1; K and V blocks in pass 2; 3-stage ring)
+//   warp 1 : MMA issuer (S double-buffered in TMEM so softmax of block j overlaps QK^T of block j+1)
+//   warps 2-5 : softmax / epilogue, one query row per thread (TMEM lane == row: no shuffles needed)
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+#include <cuda_bf16.h>
+
+namespace mcedm {
+
+constexpr int kKvStages = 3;
+constexpr int kTile = 16384;  // 128 rows x 128 B
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(192, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out, unsigned int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                                  // 16 KB
+  uint8_t* kv_smem = q_smem + kTile;                       // stages x (K 16 KB | V 16 KB)
+  uint8_t* p_smem = kv_smem + kKvStages * 2 * kTile;       // 2 buffers x 32 KB (2 atoms of 64 keys)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * 2 * kTile);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* o_full = bars + 1;        // 1
+  uint64_t* s_full = bars + 2;        // 2
+  uint64_t* s_empty = bars + 4;       // 2
+  uint64_t* p_full = bars + 6;        // 2
+  uint64_t* p_empty = bars + 8;       // 2
+  uint64_t* kv_full = bars + 10;      // stages
+  uint64_t* kv_empty = bars + 10 + kKvStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kKvStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = L / 128;
+  const int b = blockIdx.x / nblk;
+  const int q0 = (blockIdx.x - b * nblk) * 128;
+  const int n_it = 2 * nblk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_qkv);
+    mbar_init(q_full, 1);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTile);
+      tma_load_4d(q_smem, &tm_qkv, q_full, 0, q0, 0, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int pass = it / nblk, j = it - pass * nblk;
+        const uint32_t s = it % kKvStages, n = it / kKvStages;
+        mbar_wait(&kv_empty[s], (n & 1u) ^ 1u, err, 0x1100 + s);
+        mbar_expect_tx(&kv_full[s], pass ? 2 * kTile : kTile);
+        tma_load_4d(kv_smem + s * 2 * kTile, &tm_qkv, &kv_full[s], 64, j * 128, 0, b);
+        if (pass) tma_load_4d(kv_smem + s * 2 * kTile + kTile, &tm_qkv, &kv_full[s], 128, j * 128, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B = V, MN-major
+      mbar_wait(q_full, 0, err, 0x1200);
+      tc_fence_after();
+      const uint32_t q_base = smem_u32(q_smem);
+      for (int it = 0; it <= n_it; ++it) {
+        if (it < n_it) {
+          const int pass = it / nblk;
+          const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
+          const uint32_t s = it % kKvStages, n = it / kKvStages;
+          mbar_wait(&s_empty[sb], (ns & 1u) ^ 1u, err, 0x1300 + sb);
+          mbar_wait(&kv_full[s], n & 1u, err, 0x1400 + s);
+          tc_fence_after();
+          const uint32_t k_base = smem_u32(kv_smem + s * 2 * kTile);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + sb * 128, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32),
+                     idesc_s, (uint32_t)(k != 0));
+          umma_commit(&s_full[sb]);
+          if (pass == 0) umma_commit(&kv_empty[s]);
+        }
+        if (it >= nblk + 1) {
+          const int jp = it - 1 - nblk;                    // P V of the previous pass-2 block
+          const uint32_t pb = jp & 1u, np = (uint32_t)jp >> 1;
+          const uint32_t sp = (it - 1) % kKvStages;
+          mbar_wait(&p_full[pb], np & 1u, err, 0x1500 + pb);
+          tc_fence_after();
+          const uint32_t p_base = smem_u32(p_smem + pb * 2 * kTile);
+          const uint32_t v_base = smem_u32(kv_smem + sp * 2 * kTile + kTile);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_f16(tmem_o, umma_desc_k_sw128(p_base + (kk >> 2) * kTile + (kk & 3) * 32),
+                     umma_desc_mn_sw128(v_base + kk * 2048, 8192), idesc_o, (uint32_t)((jp | kk) != 0));
+          umma_commit(&p_empty[pb]);
+          umma_commit(&kv_empty[sp]);
+        }
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float c1 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+    float m = -INFINITY, l = 0.f;
+    // ---------------- pass 1: running max / sum ----------------
+    for (int it = 0; it < nblk; ++it) {
+      const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
+      mbar_wait(&s_full[sb], ns & 1u, err, 0x1600 + sb);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
+        tmem_wait_ld();
+        float cm = __uint_as_float(v[0]);
+#pragma unroll
+        for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+        const float mn = fmaxf(m, cm);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += ex2((__uint_as_float(v[i]) - mn) * c1);
+        l = l * ex2((m - mn) * c1) + acc;
+        m = mn;
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[sb]);
+    }
+    const float mc = m * c1;
+    // ---------------- pass 2: P = exp2(S*c1 - m*c1) -> bf16 -> smem ----------------
+    for (int j = 0; j < nblk; ++j) {
+      const int it = nblk + j;
+      const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
+      const uint32_t pb = j & 1u, np = (uint32_t)j >> 1;
+      mbar_wait(&s_full[sb], ns & 1u, err, 0x1700 + sb);
+      mbar_wait(&p_empty[pb], (np & 1u) ^ 1u, err, 0x1800 + pb);
+      tc_fence_after();
+      uint8_t* prow = p_smem + pb * 2 * kTile + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
+        tmem_wait_ld();
+        uint8_t* atom_row = prow + (c >> 1) * kTile;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 o;
+          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[u * 8 + 2 * e]), c1, -mc));
+            const float p1 = ex2(fmaf(__uint_as_float(v[u * 8 + 2 * e + 1]), c1, -mc));
+            op[e] = pack_bf16x2(p0, p1);
+          }
+          const int unit = ((c & 1) * 4 + u) ^ (row & 7);
+          *reinterpret_cast<uint4*>(atom_row + unit * 16) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[sb]);
+      fence_proxy_async_smem();     // generic-proxy P writes -> visible to the UMMA (async proxy) reads
+      mbar_arrive(&p_full[pb]);
+    }
+    // ---------------- epilogue: O / l -> bf16 ----------------
+    mbar_wait(o_full, 0, err, 0x1900);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    __nv_bfloat16* orow = out + ((long long)b * L + q0 + row) * 64;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_o + lane_addr + c * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[u * 8 + 0]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l);
+        o.y = pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l);
+        o.z = pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l);
+        o.w = pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// CUDA-core fp32 checker (tests only): one warp per query.
+__global__ void attn_ref_kernel(const __nv_bfloat16* __restrict__ qkv, int L, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (qi >= L) return;
+  const __nv_bfloat16* base = qkv + (long long)b * L * 192;
+  float qv[64];
+  for (int c = 0; c < 64; ++c) qv[c] = __bfloat162float(base[(long long)qi * 192 + c]);
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) {
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s += qv[c] * __bfloat162float(base[(long long)j * 192 + 64 + c]);
+    m = fmaxf(m, s * 0.125f);
+  }
+  for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float l = 0.f, acc[64];
+  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s += qv[c] * __bfloat162float(base[(long long)j * 192 + 64 + c]);
+    const float p = expf(s * 0.125f - m);
+    l += p;
+    for (int c = 0; c < 64; ++c) acc[c] += p * __bfloat162float(base[(long long)j * 192 + 128 + c]);
+  }
+  for (int off = 16; off; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+  for (int c = 0; c < 64; ++c) {
+    float a = acc[c];
+    for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) out[((long long)b * L + qi) * 64 + c] = a / l;
+  }
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && L >= 128 && L % 128 == 0, "attention: L=%d must be a positive multiple of 128", L);
+  CUtensorMap tm;
+  int rc = make_tmap_nhwc_bf16(&tm, qkv_bf16, B, 1, L, 192, 128, 1);
+  if (rc) return rc;
+  unsigned int* err = watchdog_ptr();
+  MCEDM_REQUIRE(err != nullptr, "attention: no watchdog word");
+  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  attn_kernel<<<B * (L / 128), 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), err);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_attention_ref(const void* qkv_bf16, int B, int L, float* out_f32, void* stream) {
+  using namespace mcedm;
+  dim3 grid((L + 3) / 4, B);
+  attn_ref_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), L, out_f32);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}

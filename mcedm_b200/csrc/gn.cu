@@ -1,0 +1,239 @@
+// K2 — GroupNorm statistics and fused GroupNorm-apply + adaptive scale/shift + SiLU + resample.
+//
+// Replaces, per UNetBlock (models/adm_blocks.py:159-181):
+//   silu(norm0(x))                                   :161  (+ the up/down resample conv0 performs
+//                                                          before its 3x3 filter, :73-77)
+//   silu(addcmul(shift, norm1(x), scale + 1))        :163-166
+//   norm2(x)                                         :175
+// and silu(out_norm(x)) (:403).  GroupNorm itself is models/adm_blocks.py:86-97: groups of 4
+// consecutive channels, biased variance over 4*H*W values, eps 1e-5, per-channel affine.
+//
+// All kernels are HBM-bound streaming kernels (fp32 in -> bf16 out, 6 B per element): 128-bit
+// loads/stores, one pass.  Statistics arrive as per-128-pixel-tile partial sums (sum, sum of
+// squares per group) that the conv epilogue already produced (conv_igemm.cu); they are folded in
+// fp64 in a fixed order here, so results are run-to-run deterministic.
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+namespace mcedm {
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone partial statistics (used for tensors not produced by conv_igemm, and by tests)
+// x: fp32 [n_tiles*128, 64]; out: [n_tiles][16][2]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ out) {
+  const long long tile = blockIdx.x;
+  const int unit = threadIdx.x & 15;      // 4-channel group
+  const int r0 = threadIdx.x >> 4;        // 0..15
+  const float4* xp = reinterpret_cast<const float4*>(x + tile * 128 * 64);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = xp[(r0 + 16 * i) * 16 + unit];
+    s1 += (a.x + a.y) + (a.z + a.w);
+    s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+  }
+  // lanes l and l^16 of a warp share `unit`
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  __shared__ float sm[8][16][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 16) {
+    sm[warp][lane][0] = s1;
+    sm[warp][lane][1] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][g][k];
+    out[tile * 32 + threadIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply
+// ---------------------------------------------------------------------------------------------
+struct GnApplyParams {
+  const float* x;            // fp32 NHWC [B, Hin, Win, 64]
+  const float* partial;      // [B*tiles_per_img][16][2]
+  int tiles_per_img;         // Hin*Win/128
+  const float* gamma;        // [64]
+  const float* beta;         // [64]
+  const float* scale_shift;  // nullptr or [Bemb][2*C_emb]: scale at +c, shift at +C_emb+c
+  int emb_batch_stride;      // 0 when one embedding row is broadcast over the batch
+  int emb_shift_offset;      // distance (floats) from scale[c] to shift[c]
+  float eps;
+  int act;                   // 0 identity, 1 SiLU
+  int resample;              // 0 same, 1 nearest x2 up (out is 2Hin x 2Win), 2 2x2 mean (out is Hin/2 x Win/2)
+  int Hin, Win;
+  void* out;                 // bf16 NHWC at the output resolution
+  void* out_raw;             // nullptr or bf16 NHWC copy of x itself (same resolution only)
+  int pix_per_cta;           // INPUT pixels per CTA for resample 0/1, OUTPUT pixels per CTA for resample 2
+};
+
+__device__ __forceinline__ float4 gn_act4(float4 v, const float4 a, const float4 b, int act) {
+  v.x = fmaf(v.x, a.x, b.x);
+  v.y = fmaf(v.y, a.y, b.y);
+  v.z = fmaf(v.z, a.z, b.z);
+  v.w = fmaf(v.w, a.w, b.w);
+  if (act) {
+    v.x = silu_f(v.x);
+    v.y = silu_f(v.y);
+    v.z = silu_f(v.z);
+    v.w = silu_f(v.w);
+  }
+  return v;
+}
+__device__ __forceinline__ uint4 pack8(const float4 lo, const float4 hi) {
+  uint4 o;
+  o.x = pack_bf16x2(lo.x, lo.y);
+  o.y = pack_bf16x2(lo.z, lo.w);
+  o.z = pack_bf16x2(hi.x, hi.y);
+  o.w = pack_bf16x2(hi.z, hi.w);
+  return o;
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  __shared__ float sA[64], sB[64];
+  __shared__ float sMean[16], sRstd[16];
+  const int b = blockIdx.y;
+  {
+    // fold the per-tile partial sums of image b: 16 threads per group, fixed order, fp64
+    const int g = threadIdx.x >> 4, j = threadIdx.x & 15;
+    double s1 = 0.0, s2 = 0.0;
+    const float* pp = p.partial + (long long)b * p.tiles_per_img * 32 + g * 2;
+    for (int t = j; t < p.tiles_per_img; t += 16) {
+      s1 += (double)pp[t * 32];
+      s2 += (double)pp[t * 32 + 1];
+    }
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (j == 0) {
+      const double cnt = 4.0 * (double)p.Hin * (double)p.Win;
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      sMean[g] = (float)mean;
+      sRstd[g] = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float a = sRstd[c >> 2] * p.gamma[c];
+    float bb = p.beta[c] - sMean[c >> 2] * a;
+    if (p.scale_shift) {
+      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
+      const float sc = 1.0f + ss[c];
+      a *= sc;
+      bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
+    }
+    sA[c] = a;
+    sB[c] = bb;
+  }
+  __syncthreads();
+  const int c8 = threadIdx.x & 7;          // 8-channel slice
+  const int ps = threadIdx.x >> 3;         // 0..31
+  const float4 a_lo = *reinterpret_cast<const float4*>(&sA[c8 * 8]);
+  const float4 a_hi = *reinterpret_cast<const float4*>(&sA[c8 * 8 + 4]);
+  const float4 b_lo = *reinterpret_cast<const float4*>(&sB[c8 * 8]);
+  const float4 b_hi = *reinterpret_cast<const float4*>(&sB[c8 * 8 + 4]);
+  const long long in_img = (long long)b * p.Hin * p.Win;
+  const int pix0 = blockIdx.x * p.pix_per_cta;
+  uint4* out = reinterpret_cast<uint4*>(p.out);
+
+  if (p.resample == 0) {
+    for (int i = ps; i < p.pix_per_cta; i += 32) {
+      const long long pix = in_img + pix0 + i;
+      const float4* xp = reinterpret_cast<const float4*>(p.x + pix * 64 + c8 * 8);
+      const float4 lo = xp[0], hi = xp[1];
+      if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo, hi);
+      out[pix * 8 + c8] = pack8(gn_act4(lo, a_lo, b_lo, p.act), gn_act4(hi, a_hi, b_hi, p.act));
+    }
+  } else if (p.resample == 1) {
+    const int Wo = p.Win * 2;
+    const long long out_img = (long long)b * p.Hin * p.Win * 4;
+    for (int i = ps; i < p.pix_per_cta; i += 32) {
+      const int ip = pix0 + i;
+      const int y = ip / p.Win, x = ip - y * p.Win;
+      const float4* xp = reinterpret_cast<const float4*>(p.x + (in_img + ip) * 64 + c8 * 8);
+      const uint4 v = pack8(gn_act4(xp[0], a_lo, b_lo, p.act), gn_act4(xp[1], a_hi, b_hi, p.act));
+      const long long o00 = out_img + (long long)(2 * y) * Wo + 2 * x;
+      out[o00 * 8 + c8] = v;
+      out[(o00 + 1) * 8 + c8] = v;
+      out[(o00 + Wo) * 8 + c8] = v;
+      out[(o00 + Wo + 1) * 8 + c8] = v;
+    }
+  } else {
+    const int Wo = p.Win >> 1, Ho = p.Hin >> 1;
+    const long long out_img = (long long)b * Ho * Wo;
+    for (int i = ps; i < p.pix_per_cta; i += 32) {
+      const int op = pix0 + i;
+      const int y = op / Wo, x = op - y * Wo;
+      const float* base = p.x + (in_img + (long long)(2 * y) * p.Win + 2 * x) * 64 + c8 * 8;
+      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4* xp = reinterpret_cast<const float4*>(base + ((k >> 1) * p.Win + (k & 1)) * 64);
+        const float4 l = gn_act4(xp[0], a_lo, b_lo, p.act), h = gn_act4(xp[1], a_hi, b_hi, p.act);
+        lo.x += l.x; lo.y += l.y; lo.z += l.z; lo.w += l.w;
+        hi.x += h.x; hi.y += h.y; hi.z += h.z; hi.w += h.w;
+      }
+      lo.x *= 0.25f; lo.y *= 0.25f; lo.z *= 0.25f; lo.w *= 0.25f;
+      hi.x *= 0.25f; hi.y *= 0.25f; hi.z *= 0.25f; hi.w *= 0.25f;
+      out[(out_img + op) * 8 + c8] = pack8(lo, hi);
+    }
+  }
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_gn_stats(const float* x, long long n_pixels, float* partial, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n_pixels > 0 && n_pixels % 128 == 0, "gn_stats: pixel count %lld must be a multiple of 128", n_pixels);
+  gn_stats_kernel<<<(unsigned)(n_pixels / 128), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, partial);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
+                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
+                              int act, int resample, int B, int Hin, int Win, void* out_bf16, void* out_raw_bf16,
+                              void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply: Hin*Win=%d must be a multiple of 128", Hin * Win);
+  MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: resample=%d", resample);
+  MCEDM_REQUIRE(resample == 0 || out_raw_bf16 == nullptr, "gn_apply: raw copy only without resampling");
+  MCEDM_REQUIRE(resample != 2 || (Hin % 2 == 0 && Win % 2 == 0), "gn_apply: 2x2 mean needs even H, W");
+  GnApplyParams p;
+  p.x = x;
+  p.partial = partial;
+  p.tiles_per_img = Hin * Win / 128;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.scale_shift = scale_shift;
+  p.emb_batch_stride = emb_batch_stride;
+  p.emb_shift_offset = emb_shift_offset;
+  p.eps = eps;
+  p.act = act;
+  p.resample = resample;
+  p.Hin = Hin;
+  p.Win = Win;
+  p.out = out_bf16;
+  p.out_raw = out_raw_bf16;
+  const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
+  int per = 256;
+  while (per > 32 && (work % per) != 0) per >>= 1;
+  MCEDM_REQUIRE(work % per == 0, "gn_apply: cannot tile %d pixels", work);
+  p.pix_per_cta = per;
+  dim3 grid(work / per, B);
+  gn_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}

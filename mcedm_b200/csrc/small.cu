@@ -1,0 +1,185 @@
+// Small kernels around the U-Net trunk:
+//   * emb_mlp      — noise embedding + all per-block `affine` projections in one launch
+//                    (models/adm_blocks.py:185-199 PositionalEmbedding, :367-379 map_layer0/1,
+//                     :163 affine(emb) of every UNetBlock).
+//   * conv_in      — first 3x3 conv on cat([cond, x]) (models/adm_blocks.py:319-340, :384-385):
+//                    NCHW fp32 in (<= 8 channels) -> NHWC fp32 64-channel out + GroupNorm partials.
+//                    fp32 CUDA-core math: K = 9*Cin <= 72 is far too small for the tensor cores and
+//                    the layer is bound by its 256 B/pixel store.
+//   * head_to_nchw — picks the first Cout channels of the padded NHWC out_conv result -> NCHW F_x.
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+namespace mcedm {
+
+// ------------------------------------------- emb MLP -------------------------------------------
+// grid = Bemb, block = 128
+__global__ void __launch_bounds__(128)
+emb_mlp_kernel(const float* __restrict__ c_noise, const float* __restrict__ freqs, const float* __restrict__ w0,
+               const float* __restrict__ b0, const float* __restrict__ w1, const float* __restrict__ b1,
+               const float* __restrict__ aff_w, const float* __restrict__ aff_b, int n_aff, int Bemb,
+               float* __restrict__ emb_out, float* __restrict__ out) {
+  __shared__ float e[64], h0[64], h1[64];
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (t < 32) {
+    const float ang = c_noise[b] * freqs[t];
+    e[t] = cosf(ang);
+    e[t + 32] = sinf(ang);
+  }
+  __syncthreads();
+  if (t < 64) {
+    float acc = 0.f;
+    for (int k = 0; k < 64; ++k) acc = fmaf(e[k], w0[t * 64 + k], acc);
+    h0[t] = silu_f(acc + b0[t]);
+  }
+  __syncthreads();
+  if (t < 64) {
+    float acc = 0.f;
+    for (int k = 0; k < 64; ++k) acc = fmaf(h0[k], w1[t * 64 + k], acc);
+    const float v = silu_f(acc + b1[t]);
+    h1[t] = v;
+    if (emb_out) emb_out[b * 64 + t] = v;
+  }
+  __syncthreads();
+  for (int a = 0; a < n_aff; ++a) {
+    const float* w = aff_w + ((long long)a * 128 + t) * 64;
+    float acc = 0.f;
+    for (int k = 0; k < 64; ++k) acc = fmaf(h1[k], w[k], acc);
+    out[((long long)a * Bemb + b) * 128 + t] = acc + aff_b[a * 128 + t];
+  }
+}
+
+// ------------------------------------------- conv_in -------------------------------------------
+// One CTA = one 128-pixel tile (128/W image rows); warp = one pixel at a time, lane = 2 output channels.
+constexpr int kMaxCin = 8;
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x, int Cx, const float* __restrict__ cond, int Cc,
+               const float* __restrict__ w, const float* __restrict__ bias, int H, int W,
+               float* __restrict__ out, float* __restrict__ stats) {
+  extern __shared__ float patch[];  // [Cin][rows+2][W+2]
+  constexpr int Cin = CIN;
+  const int rows = 128 / W;
+  const int tiles_per_img = H * W / 128;
+  const int tile = blockIdx.x;
+  const int b = tile / tiles_per_img;
+  const int y0 = (tile - b * tiles_per_img) * rows;
+  const int PW = W + 2, PH = rows + 2;
+  for (int i = threadIdx.x; i < Cin * PH * PW; i += 256) {
+    const int c = i / (PH * PW);
+    const int r = (i - c * PH * PW) / PW;
+    const int xx = i - c * PH * PW - r * PW;
+    const int gy = y0 + r - 1, gx = xx - 1;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      v = (c < Cc) ? cond[(((long long)b * Cc + c) * H + gy) * W + gx]
+                   : x[(((long long)b * Cx + (c - Cc)) * H + gy) * W + gx];
+    }
+    patch[i] = v;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // weights of this lane's 2 output channels: w[co][ci][ky][kx]
+  float w0[CIN * 9], w1[CIN * 9];
+#pragma unroll
+  for (int i = 0; i < CIN * 9; ++i) {
+    w0[i] = w[(2 * lane) * Cin * 9 + i];
+    w1[i] = w[(2 * lane + 1) * Cin * 9 + i];
+  }
+  const float bz0 = bias ? bias[2 * lane] : 0.f, bz1 = bias ? bias[2 * lane + 1] : 0.f;
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  for (int pi = warp; pi < 128; pi += 8) {
+    const int r = pi / W, xx = pi - r * W;
+    float a0 = bz0, a1 = bz1;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = patch[(c * PH + r + ky) * PW + xx + kx];
+          a0 = fmaf(v, w0[c * 9 + ky * 3 + kx], a0);
+          a1 = fmaf(v, w1[c * 9 + ky * 3 + kx], a1);
+        }
+    }
+    const long long pix = (long long)tile * 128 + pi;
+    *reinterpret_cast<float2*>(out + pix * 64 + 2 * lane) = make_float2(a0, a1);
+    s1 += a0 + a1;
+    s2 += a0 * a0 + a1 * a1;
+  }
+  if (stats) {
+    // group of 4 channels = lanes (2g, 2g+1)
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    __shared__ float sm[8][16][2];
+    if ((lane & 1) == 0) {
+      sm[warp][lane >> 1][0] = s1;
+      sm[warp][lane >> 1][1] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) t += sm[ww][g][k];
+      stats[(long long)tile * 32 + threadIdx.x] = t;
+    }
+  }
+}
+
+// ----------------------------------------- head_to_nchw ----------------------------------------
+__global__ void head_to_nchw_kernel(const float* __restrict__ src, int Cs, int Cout, long long HW, long long total,
+                                    float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*Cout*HW (NCHW order)
+  if (i >= total) return;
+  const long long pix = i % HW;
+  const int c = (int)((i / HW) % Cout);
+  const long long b = i / (HW * Cout);
+  dst[i] = src[(b * HW + pix) * Cs + c];
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_emb_mlp(const float* c_noise, const float* freqs, const float* w0, const float* b0,
+                             const float* w1, const float* b1, const float* aff_w, const float* aff_b, int n_aff,
+                             int Bemb, float* emb_out, float* out, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(Bemb >= 1 && n_aff >= 0, "emb_mlp: bad sizes");
+  emb_mlp_kernel<<<Bemb, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c_noise, freqs, w0, b0, w1, b1, aff_w,
+                                                                            aff_b, n_aff, Bemb, emb_out, out);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_conv_in(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
+                             int B, int H, int W, float* out, float* stats_partial, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(Cx >= 1 && Cc >= 0 && Cx + Cc <= kMaxCin, "conv_in: %d+%d input channels exceed %d", Cx, Cc, kMaxCin);
+  MCEDM_REQUIRE(Cc == 0 || cond != nullptr, "conv_in: cond channels without a cond tensor");
+  MCEDM_REQUIRE(W >= 8 && W <= 128 && 128 % W == 0 && (H * W) % 128 == 0, "conv_in: W=%d H=%d unsupported", W, H);
+  const int rows = 128 / W;
+  const int smem = (Cx + Cc) * (rows + 2) * (W + 2) * (int)sizeof(float);
+  const unsigned grid = (unsigned)(B * (H * W / 128));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define MCEDM_CONV_IN_CASE(C) \
+  case C: conv_in_kernel<C><<<grid, 256, smem, st>>>(x, Cx, cond, Cc, w, bias, H, W, out, stats_partial); break;
+  switch (Cx + Cc) {
+    MCEDM_CONV_IN_CASE(1) MCEDM_CONV_IN_CASE(2) MCEDM_CONV_IN_CASE(3) MCEDM_CONV_IN_CASE(4)
+    MCEDM_CONV_IN_CASE(5) MCEDM_CONV_IN_CASE(6) MCEDM_CONV_IN_CASE(7) MCEDM_CONV_IN_CASE(8)
+  }
+#undef MCEDM_CONV_IN_CASE
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_head_to_nchw(const float* src, int Cs, int Cout, int B, int H, int W, float* dst, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(Cout >= 1 && Cout <= Cs, "head_to_nchw: Cout=%d Cs=%d", Cout, Cs);
+  const long long HW = (long long)H * W, total = HW * Cout * B;
+  head_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, Cs, Cout, HW, total, dst);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}

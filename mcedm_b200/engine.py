@@ -1,0 +1,284 @@
+"""Launch plan of the B200-native ADM U-Net forward pass.
+
+`UNetEngine` turns a `DhariwalUNet` parameter container into (a) packed device weights in the layouts
+the sm_100a kernels want and (b) a fixed sequence of C-ABI launches per forward call
+(include/mcedm_b200.h).  It follows DhariwalUNet.forward / UNetBlock.forward of the reference
+(models/adm_blocks.py:364-404, :159-181) with these fusions:
+
+  * every tensor in the trunk is a 64-channel NHWC tensor; the decoder's channel concat
+    (adm_blocks.py:401) never materialises — conv0 of those blocks reads two sources;
+  * GroupNorm statistics come out of the producing conv's epilogue (per-tile partial sums);
+  * GroupNorm-apply + (1+scale)/shift + SiLU + the 2x up/down resampling of conv0 is ONE pass that
+    writes the bf16 tensor-core operand;
+  * bias, residual add (identity / 2x2-mean / nearest-x2 skip) and the 1x1 skip projection of the
+    128->64 blocks are folded into conv1's implicit GEMM (extra K segments on the raw input);
+  * q/k/v de-interleave is a one-time weight-row permutation; softmax(QK^T)V never leaves the SM.
+
+HBM layout: fp32 NHWC for the residual stream and conv0 outputs, bf16 NHWC for every tensor-core
+operand.  Workspaces are torch tensors owned by this object, keyed by batch size.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+
+_SEG9 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+
+
+def pack_conv3x3(weight: torch.Tensor, n_out_pad: Optional[int] = None) -> torch.Tensor:
+    """[Cout, 64*n_src, k, k] fp32 -> bf16 [n_src*k*k][Cout(_pad)][64], segment order (source, ky, kx)."""
+    cout, cin, k, _ = weight.shape
+    n_src = cin // 64
+    w = weight.detach().reshape(cout, n_src, 64, k, k).permute(1, 3, 4, 0, 2).reshape(n_src * k * k, cout, 64)
+    if n_out_pad is not None and n_out_pad > cout:
+        w = torch.cat([w, w.new_zeros(w.shape[0], n_out_pad - cout, 64)], dim=1)
+    return w.to(torch.bfloat16).contiguous()
+
+
+class _Block:
+    """Packed weights + static description of one UNetBlock."""
+
+    def __init__(self, name: str, mod, aff_index: int):
+        self.name = name
+        self.mod = mod
+        self.n_src = mod.in_channels // 64
+        self.up, self.down = mod.up, mod.down
+        self.attn = bool(mod.num_heads)
+        self.aff_index = aff_index
+        self.skip_conv = mod.skip is not None and mod.skip.weight is not None
+        if mod.num_heads not in (0, 1):
+            raise NotImplementedError("attention kernel handles one 64-channel head")
+        if not mod.adaptive_scale:
+            raise NotImplementedError("adaptive_scale=False has no kernel")
+
+    def pack(self):
+        m = self.mod
+        self.w0 = pack_conv3x3(m.conv0.weight)
+        self.b0 = m.conv0.bias.detach().float().contiguous()
+        w1 = pack_conv3x3(m.conv1.weight)
+        b1 = m.conv1.bias.detach().float()
+        if self.skip_conv:
+            w1 = torch.cat([w1, pack_conv3x3(m.skip.weight)], dim=0).contiguous()
+            b1 = b1 + m.skip.bias.detach().float()
+        self.w1, self.b1 = w1, b1.contiguous()
+        self.g0, self.be0 = m.norm0.weight.detach().float().contiguous(), m.norm0.bias.detach().float().contiguous()
+        self.g1, self.be1 = m.norm1.weight.detach().float().contiguous(), m.norm1.bias.detach().float().contiguous()
+        if self.attn:
+            # reference channel order is (c*3 + {q,k,v}) (adm_blocks.py:175-176) -> blocked (q | k | v)
+            perm = torch.arange(192, device=m.qkv.weight.device).reshape(64, 3).t().reshape(-1)
+            self.wqkv = m.qkv.weight.detach()[perm].reshape(1, 192, 64).to(torch.bfloat16).contiguous()
+            self.bqkv = m.qkv.bias.detach().float()[perm].contiguous()
+            self.wproj = m.proj.weight.detach().reshape(1, 64, 64).to(torch.bfloat16).contiguous()
+            self.bproj = m.proj.bias.detach().float().contiguous()
+            self.g2 = m.norm2.weight.detach().float().contiguous()
+            self.be2 = m.norm2.bias.detach().float().contiguous()
+
+
+class UNetEngine:
+    def __init__(self, unet):
+        self.unet = unet
+        self.lib = L.lib()
+        self.blocks_enc: List[_Block] = []
+        self.blocks_dec: List[_Block] = []
+        aff = 0
+        self.conv_in_name = None
+        self._attn_levels = set()
+        level = 0
+        for name, mod in unet.enc.items():
+            if name.endswith("_conv"):
+                self.conv_in_name = name
+            else:
+                if mod.down:
+                    level += 1
+                self.blocks_enc.append(_Block("enc." + name, mod, aff))
+                if mod.num_heads:
+                    self._attn_levels.add(level)
+                aff += 1
+        for name, mod in unet.dec.items():
+            if mod.up:
+                level -= 1
+            self.blocks_dec.append(_Block("dec." + name, mod, aff))
+            if mod.num_heads:
+                self._attn_levels.add(level)
+            aff += 1
+        self.n_aff = aff
+        self._packed_key = None
+        self._ws: Dict[tuple, dict] = {}
+
+    # ------------------------------------------------------------------ weights
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
+
+    def pack(self, force: bool = False):
+        key = self._param_key()
+        if not force and key == self._packed_key:
+            return
+        u = self.unet
+        dev = u.out_conv.weight.device
+        if dev.type != "cuda":
+            raise L.McedmError("mcedm_b200.DhariwalUNet parameters must live on a CUDA (sm_100) device; "
+                               "there is no CPU path")
+        with torch.no_grad():
+            for b in self.blocks_enc + self.blocks_dec:
+                b.pack()
+            cin = u.enc[self.conv_in_name]
+            self.w_in = cin.weight.detach().float().contiguous()
+            self.b_in = cin.bias.detach().float().contiguous()
+            self.w_out = pack_conv3x3(u.out_conv.weight, n_out_pad=16)
+            self.b_out = torch.cat([u.out_conv.bias.detach().float(),
+                                    torch.zeros(16 - u.out_channels, device=dev)]).contiguous()
+            self.g_out = u.out_norm.weight.detach().float().contiguous()
+            self.be_out = u.out_norm.bias.detach().float().contiguous()
+            self.freqs = u.map_noise.frequencies(torch.float32).to(dev).contiguous()
+            self.w_m0, self.b_m0 = u.map_layer0.weight.detach().float().contiguous(), \
+                u.map_layer0.bias.detach().float().contiguous()
+            self.w_m1, self.b_m1 = u.map_layer1.weight.detach().float().contiguous(), \
+                u.map_layer1.bias.detach().float().contiguous()
+            blocks = self.blocks_enc + self.blocks_dec
+            self.aff_w = torch.stack([b.mod.affine.weight.detach().float() for b in blocks]).contiguous()
+            self.aff_b = torch.stack([b.mod.affine.bias.detach().float() for b in blocks]).contiguous()
+        self._packed_key = key
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B: int, H: int, W: int, dev) -> dict:
+        key = (B, H, W, dev.index)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        f32 = dict(device=dev, dtype=torch.float32)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        ws = {}
+        # residual-stream tensors are allocated per block output on first use (see _tensor)
+        ws["pool"] = {}
+        ws["h"] = torch.empty(B * H * W * 64, **f32)            # conv0 output (largest resolution)
+        ws["h_st"] = torch.empty(B * H * W // 128 * 32, **f32)
+        ws["a"] = [torch.empty(B * H * W * 64, **bf) for _ in range(2)]   # normalised operands (2 sources)
+        ws["raw"] = [torch.empty(B * H * W * 64, **bf) for _ in range(2)]  # raw bf16 copies for 1x1 skips
+        ws["a1"] = torch.empty(B * H * W * 64, **bf)
+        att_pix = max([B * (H >> lv) * (W >> lv) for lv in self._attn_levels] or [128])
+        ws["qkv"] = torch.empty(att_pix * 192, **bf)
+        ws["att"] = torch.empty(att_pix * 64, **bf)
+        ws["o16"] = torch.empty(B * H * W * 16, **f32)
+        ws["ss"] = torch.empty(self.n_aff * B * 128, **f32)
+        ws["F"] = torch.empty(B, self.unet.out_channels, H, W, **f32)
+        self._ws[key] = ws
+        return ws
+
+    @staticmethod
+    def _tensor(ws, name: str, B: int, H: int, W: int, dev):
+        t = ws["pool"].get(name)
+        if t is None:
+            t = (torch.empty(B, H, W, 64, device=dev, dtype=torch.float32),
+                 torch.empty(B * H * W // 128, 16, 2, device=dev, dtype=torch.float32))
+            ws["pool"][name] = t
+        return t
+
+    # ------------------------------------------------------------------ launches
+    def _conv(self, srcs, segs, w, bias, B, H, W, N, out, out_bf16, res, res_mode, stats, st):
+        L.check(self.lib.mcedm_conv_igemm(
+            L.ptr_array(srcs), len(srcs), L.int_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
+            L.int_array([s[2] for s in segs]), len(segs), L.ptr(w), L.ptr(bias), B, H, W, N, L.ptr(out), out_bf16,
+            L.ptr(res), res_mode, L.ptr(stats), st), "conv_igemm")
+
+    def _gn_apply(self, x, stats, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out, raw, st, eps=1e-5):
+        L.check(self.lib.mcedm_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ss), ss_stride, 64,
+                                        eps, act, resample, B, Hin, Win, L.ptr(out), L.ptr(raw), st), "gn_apply")
+
+    def _run_block(self, blk: _Block, inputs, B, H_in, W_in, ws, emb_stride, st, dev):
+        """inputs: list of (fp32 NHWC tensor, stats) at resolution H_in x W_in. Returns (out, stats, H, W)."""
+        if blk.up:
+            H, W, rs, res_mode = H_in * 2, W_in * 2, 1, 2
+        elif blk.down:
+            H, W, rs, res_mode = H_in // 2, W_in // 2, 2, 3
+        else:
+            H, W, rs, res_mode = H_in, W_in, 0, 1
+        eps = blk.mod.norm0.eps
+        a_srcs, raw_srcs = [], []
+        for i, (x, x_st) in enumerate(inputs):
+            raw = ws["raw"][i] if blk.skip_conv else None
+            self._gn_apply(x, x_st, blk.g0[64 * i:64 * (i + 1)], blk.be0[64 * i:64 * (i + 1)], None, 0, 1, rs, B,
+                           H_in, W_in, ws["a"][i], raw, st, eps)
+            a_srcs.append(ws["a"][i])
+            if blk.skip_conv:
+                raw_srcs.append(raw)
+        segs0 = [(i, dy, dx) for i in range(len(inputs)) for (dy, dx) in _SEG9]
+        self._conv(a_srcs, segs0, blk.w0, blk.b0, B, H, W, 64, ws["h"], 0, None, 0, ws["h_st"], st)
+        ss = ws["ss"][blk.aff_index * self._ss_rows * 128:]
+        self._gn_apply(ws["h"], ws["h_st"], blk.g1, blk.be1, ss, emb_stride, 1, 0, B, H, W, ws["a1"], None, st, eps)
+        out, out_st = self._tensor(ws, blk.name, B, H, W, dev)
+        segs1 = [(0, dy, dx) for (dy, dx) in _SEG9]
+        srcs1 = [ws["a1"]]
+        if blk.skip_conv:
+            segs1 += [(1 + i, 0, 0) for i in range(len(raw_srcs))]
+            srcs1 += raw_srcs
+            self._conv(srcs1, segs1, blk.w1, blk.b1, B, H, W, 64, out, 0, None, 0, out_st, st)
+        else:
+            self._conv(srcs1, segs1, blk.w1, blk.b1, B, H, W, 64, out, 0, inputs[0][0], res_mode, out_st, st)
+        if blk.attn:
+            self._gn_apply(out, out_st, blk.g2, blk.be2, None, 0, 0, 0, B, H, W, ws["a1"], None, st, eps)
+            self._conv([ws["a1"]], [(0, 0, 0)], blk.wqkv, blk.bqkv, B, H, W, 192, ws["qkv"], 1, None, 0, None, st)
+            L.check(self.lib.mcedm_attention(L.ptr(ws["qkv"]), B, H * W, L.ptr(ws["att"]), st), "attention")
+            out2, out2_st = self._tensor(ws, blk.name + ".attn", B, H, W, dev)
+            self._conv([ws["att"]], [(0, 0, 0)], blk.wproj, blk.bproj, B, H, W, 64, out2, 0, out, 1, out2_st, st)
+            out, out_st = out2, out2_st
+        return out, out_st, H, W
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, noise_labels: torch.Tensor, cond: Optional[torch.Tensor]) -> torch.Tensor:
+        u = self.unet
+        if not x.is_cuda:
+            raise L.McedmError("DhariwalUNet.forward needs CUDA tensors: the sm_100a kernels have no CPU fallback")
+        if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != u.x_channels:
+            raise ValueError(f"x must be fp32 [B,{u.x_channels},H,W], got {x.dtype} {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H * W % 128 != 0 or W > 128 or 128 % W != 0:
+            raise ValueError(f"unsupported field size {H}x{W} (needs W | 128 and 128 | H*W)")
+        dev = x.device
+        self.pack()
+        x = x.contiguous()
+        if u.cond_channels > 0:
+            if cond is None:
+                cond = torch.zeros(B, u.cond_channels, H, W, device=dev, dtype=torch.float32)
+            if cond.shape != (B, u.cond_channels, H, W) or cond.dtype != torch.float32:
+                raise ValueError(f"cond must be fp32 [B,{u.cond_channels},H,W], got {cond.dtype} {tuple(cond.shape)}")
+            cond = cond.contiguous()
+        else:
+            cond = None
+        nl = noise_labels.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if nl.numel() not in (1, B):
+            raise ValueError(f"noise_labels must have 1 or B={B} entries, got {nl.numel()}")
+        ws = self._workspace(B, H, W, dev)
+        st = L.stream_ptr()
+        lib = self.lib
+        Bemb = nl.numel()
+        self._ss_rows = Bemb
+        emb_stride = 128 if Bemb == B and B > 1 else 0
+        L.check(lib.mcedm_emb_mlp(L.ptr(nl), L.ptr(self.freqs), L.ptr(self.w_m0), L.ptr(self.b_m0), L.ptr(self.w_m1),
+                                  L.ptr(self.b_m1), L.ptr(self.aff_w), L.ptr(self.aff_b), self.n_aff, Bemb, None,
+                                  L.ptr(ws["ss"]), st), "emb_mlp")
+        t0, t0_st = self._tensor(ws, "conv_in", B, H, W, dev)
+        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in),
+                                  L.ptr(self.b_in), B, H, W, L.ptr(t0), L.ptr(t0_st), st), "conv_in")
+        cur, cur_st, ch, cw = t0, t0_st, H, W
+        skips = [(t0, t0_st)]
+        for blk in self.blocks_enc:
+            cur, cur_st, ch, cw = self._run_block(blk, [(cur, cur_st)], B, ch, cw, ws, emb_stride, st, dev)
+            skips.append((cur, cur_st))
+        for blk in self.blocks_dec:
+            inputs = [(cur, cur_st)]
+            if blk.n_src == 2:
+                inputs.append(skips.pop())
+            cur, cur_st, ch, cw = self._run_block(blk, inputs, B, ch, cw, ws, emb_stride, st, dev)
+        # out_conv(silu(out_norm(x)))  (adm_blocks.py:403), N padded to 16 for the tensor cores
+        self._gn_apply(cur, cur_st, self.g_out, self.be_out, None, 0, 1, 0, B, H, W, ws["a1"], None, st,
+                       u.out_norm.eps)
+        self._conv([ws["a1"]], [(0, dy, dx) for (dy, dx) in _SEG9], self.w_out, self.b_out, B, H, W, 16, ws["o16"], 0,
+                   None, 0, None, st)
+        out = torch.empty(B, u.out_channels, H, W, device=dev, dtype=torch.float32)
+        L.check(lib.mcedm_head_to_nchw(L.ptr(ws["o16"]), 16, u.out_channels, B, H, W, L.ptr(out), st), "head_to_nchw")
+        return out
