@@ -127,6 +127,9 @@ MCEDM_API int mcedm_edm_euler(const double* x_hat, const float* F, const float* 
 MCEDM_API int mcedm_edm_correct(const double* x_hat, const double* x_e, const float* F2, const double* d_cur,
                                 const float* mask, double t_hat, double t_next, float c_skip, float c_out,
                                 long long total, double* x_next, float* D_out, void* stream);
+/* x_in[b] = c_in[b*stride] * x[b]                                       (mcedm.py:208, :454) */
+MCEDM_API int mcedm_edm_precond_in(const float* x, const float* c_in, int coef_stride, int B, long long chw,
+                                   float* x_in, void* stream);
 /* D[b] = c_skip[b*stride]*x[b] + c_out[b*stride]*F[b]   (mcedm.py:210, :460); chw = elements per sample */
 MCEDM_API int mcedm_edm_precond_out(const float* x, const float* F, const float* c_skip, const float* c_out,
                                     int coef_stride, int B, long long chw, float* D, void* stream);

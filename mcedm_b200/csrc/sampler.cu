@@ -88,6 +88,14 @@ __global__ void edm_precond_out_kernel(const float* __restrict__ x, const float*
   D[i] = __fadd_rn(__fmul_rn(c_skip[b * coef_stride], x[i]), __fmul_rn(c_out[b * coef_stride], F[i]));
 }
 
+// x_in = c_in[b] * x  (network input scaling, models/mcedm.py:208, :454)
+__global__ void edm_precond_in_kernel(const float* __restrict__ x, const float* __restrict__ c_in, int coef_stride,
+                                      long long chw, long long total, float* __restrict__ x_in) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  x_in[i] = __fmul_rn(c_in[(i / chw) * coef_stride], x[i]);
+}
+
 static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
 }  // namespace mcedm
@@ -138,6 +146,16 @@ extern "C" int mcedm_edm_precond_out(const float* x, const float* F, const float
   const long long total = (long long)B * chw;
   edm_precond_out_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, F, c_skip, c_out, coef_stride, chw, total, D);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_precond_in(const float* x, const float* c_in, int coef_stride, int B, long long chw,
+                                    float* x_in, void* stream) {
+  using namespace mcedm;
+  const long long total = (long long)B * chw;
+  edm_precond_in_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, c_in, coef_stride,
+                                                                                               chw, total, x_in);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/mcedm_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mcedm_b200.h")).read()
+    return sorted(set(re.findall(r"MCEDM_API\s+(?:const\s+)?\w+\*?\s+(mcedm_\w+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from mcedm_b200 import build
+
+    return build.build()
+
+
+def test_header_declares_the_hot_path_entry_points():
+    names = _declared()
+    for must in ("mcedm_conv_igemm", "mcedm_gn_apply", "mcedm_attention", "mcedm_edm_churn", "mcedm_edm_euler",
+                 "mcedm_edm_correct", "mcedm_emb_mlp", "mcedm_conv_in"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in include/mcedm_b200.h but not exported"
+    lib.mcedm_abi_version.restype = ctypes.c_int
+    assert lib.mcedm_abi_version() == 1
+
+
+def test_python_binding_covers_the_header(libpath):
+    from mcedm_b200 import _lib
+
+    assert sorted(_lib.exported_names()) == _declared()
+    _lib.lib()
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions(libpath):
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", libpath], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass   # tcgen05.mma, TMA, tcgen05.ld
+    assert "HMMA." not in sass                                            # no legacy mma.sync path
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mcedm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r"#.*", "", txt).replace("edm_oracle", "oracle") or \
+                    not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f"{f} imports the oracle"
+
+
+def test_cuda_path_fails_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from common import stress_unet
+
+    net, _, _ = stress_unet()
+    with pytest.raises(Exception):
+        net(torch.zeros(1, 2, 128, 128), torch.tensor([0.1]), torch.zeros(1, 2, 128, 128))

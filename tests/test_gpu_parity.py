@@ -1,0 +1,266 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI / the reference-shaped
+Python surface, against the CPU oracle and the fixtures generated from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): per-step denoiser output within 1e-2 relative (bf16 tensor-core
+operands, fp32 accumulation); integer / mask / indexing work bit-exact; fp64 sampler updates bit-exact
+given the same network output.
+"""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from common import NoiseFeed, fixture_state, golden, stress_module, stress_unet
+from mcedm_b200.utils import rel_l2
+from oracle import edm_oracle as O
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mcedm_b200 import _lib
+
+    _lib.lib()
+    return _lib
+
+
+# ----------------------------------------------------------------------------------------------- K1
+def _pack(w, n_src):
+    cout, cin, k, _ = w.shape
+    segs, mats = [], []
+    for i in range(n_src):
+        for ky in range(k):
+            for kx in range(k):
+                segs.append((i, ky - k // 2, kx - k // 2))
+                mats.append(w[:, 64 * i:64 * (i + 1), ky, kx])
+    return torch.stack(mats, 0), segs
+
+
+@pytest.mark.parametrize("B,H,W,n_src,k,N,res_mode,out_bf16", [
+    (2, 128, 128, 1, 3, 64, 1, 0), (2, 128, 128, 2, 3, 64, 0, 0), (3, 64, 64, 1, 3, 64, 2, 0),
+    (2, 64, 64, 1, 3, 64, 3, 0), (5, 32, 32, 2, 3, 64, 1, 0), (3, 32, 32, 1, 1, 192, 0, 1),
+    (2, 64, 64, 1, 3, 128, 0, 0), (2, 128, 128, 1, 3, 16, 0, 0), (1, 16, 16, 1, 3, 64, 0, 0)])
+def test_conv_igemm_matches_fp32_conv(L, dev, B, H, W, n_src, k, N, res_mode, out_bf16):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(B * 1000 + H + N)
+    srcs = [torch.randn(B, H, W, 64, generator=g).to(dev).to(torch.bfloat16).contiguous() for _ in range(n_src)]
+    w = (torch.randn(N, 64 * n_src, k, k, generator=g) / (64 * n_src * k * k) ** 0.5).to(dev)
+    wp, segs = _pack(w, n_src)
+    wp = wp.to(torch.bfloat16).contiguous()
+    bias = torch.randn(N, generator=g).to(dev)
+    res = {0: None, 1: (B, H, W, N), 2: (B, H // 2, W // 2, N), 3: (B, 2 * H, 2 * W, N)}[res_mode]
+    res = torch.randn(*res, generator=g).to(dev) if res else None
+    out = torch.full((B, H, W, N), float("nan"), device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    st = torch.full((B * H * W // 128, N // 4, 2), float("nan"), device=dev)
+    L.check(lib.mcedm_conv_igemm(L.ptr_array(srcs), n_src, L.int_array([s[0] for s in segs]),
+                                 L.int_array([s[1] for s in segs]), L.int_array([s[2] for s in segs]), len(segs),
+                                 L.ptr(wp), L.ptr(bias), B, H, W, N, L.ptr(out), out_bf16, L.ptr(res), res_mode,
+                                 L.ptr(st), L.stream_ptr()), "conv_igemm")
+    L.check_watchdog()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = torch.cat([s.float() for s in srcs], -1).permute(0, 3, 1, 2)
+    wq = torch.cat([wp[i * k * k:(i + 1) * k * k].float() for i in range(n_src)], 2)
+    wq = wq.reshape(k, k, N, 64 * n_src).permute(2, 3, 0, 1).contiguous()
+    ref = F.conv2d(x.double(), wq.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
+    if res_mode == 1:
+        ref = ref + res
+    elif res_mode == 2:
+        ref = ref + res.repeat_interleave(2, 1).repeat_interleave(2, 2)
+    elif res_mode == 3:
+        ref = ref + F.avg_pool2d(res.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), ref) < (4e-3 if out_bf16 else 2e-6)
+    if not out_bf16:
+        v = out.reshape(-1, 128, N // 4, 4)
+        assert torch.allclose(st[..., 0], v.sum(dim=(1, 3)), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(st[..., 1], (v * v).sum(dim=(1, 3)), rtol=1e-4, atol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("B,H,W,rs,act,use_ss", [(2, 128, 128, 0, 1, True), (3, 32, 32, 1, 1, False),
+                                                 (2, 64, 64, 2, 1, False), (2, 32, 32, 0, 0, False)])
+def test_gn_apply_matches_group_norm(L, dev, B, H, W, rs, act, use_ss):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(H + rs)
+    x = (torch.randn(B, H, W, 64, generator=g) * 2 + 0.5).to(dev)
+    gamma, beta = torch.randn(64, generator=g).to(dev), torch.randn(64, generator=g).to(dev)
+    ss = (torch.randn(B, 128, generator=g) * 0.3).to(dev)
+    st = torch.empty(B * H * W // 128, 16, 2, device=dev)
+    L.check(lib.mcedm_gn_stats(L.ptr(x), B * H * W, L.ptr(st), L.stream_ptr()))
+    Ho, Wo = (2 * H, 2 * W) if rs == 1 else (H // 2, W // 2) if rs == 2 else (H, W)
+    out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
+    L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64,
+                               1e-5, act, rs, B, H, W, L.ptr(out), None, L.stream_ptr()))
+    y = F.group_norm(x.permute(0, 3, 1, 2), 16, gamma, beta, 1e-5)
+    if use_ss:
+        y = torch.addcmul(ss[:, 64:, None, None], y, ss[:, :64, None, None] + 1)
+    y = F.silu(y) if act else y
+    y = y.repeat_interleave(2, 2).repeat_interleave(2, 3) if rs == 1 else F.avg_pool2d(y, 2) if rs == 2 else y
+    assert rel_l2(out.float(), y.permute(0, 2, 3, 1)) < 4e-3      # one bf16 rounding of the output
+
+
+# ----------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("B,Lq,scale", [(2, 1024, 1.0), (3, 256, 3.0), (1, 1024, 6.0)])
+def test_attention_matches_fp32_softmax(L, dev, B, Lq, scale):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(Lq)
+    qkv = (torch.randn(B, Lq, 192, generator=g) * scale).to(dev).to(torch.bfloat16)
+    out = torch.full((B, Lq, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), L.stream_ptr()), "attention")
+    L.check_watchdog()
+    q, k, v = qkv.double().split(64, dim=2)
+    ref = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=2) @ v
+    assert rel_l2(out.float(), ref) < 5e-3                         # bf16 P and bf16 output rounding
+    chk = torch.empty(B, Lq, 64, device=dev)
+    L.check(lib.mcedm_attention_ref(L.ptr(qkv), B, Lq, L.ptr(chk), L.stream_ptr()))
+    assert rel_l2(chk, ref) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- K5
+def test_sampler_updates_bit_exact_against_torch_fp64(L, dev):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 2, 128, 128
+    noise = torch.randn(B, C, H, W, generator=g)
+    cond = torch.randn(B, C, H, W, generator=g)
+    mask = (torch.rand(B, C, H, W, generator=g) > 0.5).float()
+    eps = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    F1, F2 = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    t_cur, t_next = torch.tensor(63.788, dtype=torch.float64), torch.tensor(56.7995, dtype=torch.float64)
+    t_hat = t_cur + 0.3 * t_cur
+    # torch (CPU, fp64/fp32) restatement of mcedm.py:594-628
+    x0 = cond * (1 - mask) + (noise.double() * t_cur) * mask
+    x_hat = x0 + (t_hat ** 2 - t_cur ** 2).sqrt() * 1 * eps * mask
+
+    def D_of(xt, sig, Fx):
+        cs, co, _, _ = O.precond_coeffs(sig)
+        return cs * xt.float() + co * Fx
+
+    d1 = D_of(x_hat, t_hat, F1)
+    d_cur = (x_hat - d1.double()) / t_hat
+    x_e = x_hat + (t_next - t_hat) * d_cur * mask
+    d2 = D_of(x_e, t_next, F2)
+    x_new = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * (x_e - d2.double()) / t_next) * mask
+    # kernels
+    from mcedm_b200.mcedm import precond_scalars
+
+    # keep the device copies alive: L.ptr() only carries the address
+    noise_d, cond_d, mask_d, eps_d, F1_d, F2_d = [t.to(dev).contiguous() for t in (noise, cond, mask, eps, F1, F2)]
+    n = noise.numel()
+    xg = torch.empty(B, C, H, W, device=dev, dtype=torch.float64)
+    s = L.stream_ptr()
+    L.check(lib.mcedm_edm_init(L.ptr(noise_d), L.ptr(cond_d), C, L.ptr(mask_d), float(t_cur), B, C, H, W, L.ptr(xg), s))
+    assert torch.equal(xg.cpu(), x0)
+    xh, xin = torch.empty_like(xg), torch.empty(B, C, H, W, device=dev)
+    cs, co, ci, _ = precond_scalars(float(t_hat))
+    cs2, co2, ci2, _ = precond_scalars(float(t_next))
+    coef = float((t_hat ** 2 - t_cur ** 2).sqrt())
+    L.check(lib.mcedm_edm_churn(L.ptr(xg), L.ptr(eps_d), L.ptr(mask_d), coef, ci, n, L.ptr(xh), L.ptr(xin), s))
+    assert torch.equal(xh.cpu(), x_hat)
+    assert torch.equal(xin.cpu(), O.precond_coeffs(t_hat)[2].reshape(()) * x_hat.float())
+    dc, xe, Db = torch.empty_like(xg), torch.empty_like(xg), torch.empty_like(xin)
+    L.check(lib.mcedm_edm_euler(L.ptr(xh), L.ptr(F1_d), L.ptr(mask_d), float(t_hat), float(t_next), cs, co, ci2, n,
+                                L.ptr(dc), L.ptr(xe), L.ptr(xin), L.ptr(Db), s))
+    assert torch.equal(Db.cpu(), d1) and torch.equal(dc.cpu(), d_cur) and torch.equal(xe.cpu(), x_e)
+    xn = torch.empty_like(xg)
+    L.check(lib.mcedm_edm_correct(L.ptr(xh), L.ptr(xe), L.ptr(F2_d), L.ptr(dc), L.ptr(mask_d), float(t_hat),
+                                  float(t_next), cs2, co2, n, L.ptr(xn), L.ptr(Db), s))
+    assert torch.equal(Db.cpu(), d2) and torch.equal(xn.cpu(), x_new)
+    keep = mask == 0
+    assert torch.equal(xn.cpu()[keep], cond.double()[keep])        # observed entries untouched, bit for bit
+
+
+# ----------------------------------------------------------------------------------------------- network
+def test_unet_forward_within_bf16_bar_of_reference(dev):
+    g = golden("unet_forward.pt")
+    net, cfg, _ = stress_unet()
+    net = net.to(dev)
+    for case in g["cases"]:
+        y = net(case["x"].to(dev), case["noise_labels"].to(dev), case["cond"].to(dev))
+        assert y.shape == case["out"].shape and y.dtype == torch.float32
+        assert rel_l2(y, case["out"]) < BF16_TOL
+    # batch independence: a sample's output does not depend on its neighbours (GroupNorm / attention are per sample)
+    c0 = g["cases"][1]
+    y2 = net(c0["x"].to(dev), c0["noise_labels"].to(dev), c0["cond"].to(dev))
+    y1 = net(c0["x"][1:].to(dev), c0["noise_labels"][1:].to(dev), c0["cond"][1:].to(dev))
+    assert torch.equal(y2[1:], y1)
+
+
+def test_cond_edm_network_within_bf16_bar(dev):
+    g = golden("cond_edm_forward.pt")
+    net, _, _ = stress_unet("config_adm_edm_res32_cond_h")
+    net = net.to(dev)
+    y = net(g["x"].to(dev), g["noise_labels"].to(dev), g["cond"].to(dev))
+    assert rel_l2(y, g["out"]) < BF16_TOL
+
+
+def test_get_denoised_within_bf16_bar(dev):
+    g = golden("denoise.pt")
+    pl, _ = stress_module()
+    pl = pl.to(dev)
+    for case in g["cases"]:
+        d, f = pl.get_denoised(pl.ema_model, case["xt"].to(dev), torch.tensor(case["sigma"], dtype=torch.float64),
+                               cond=case["cond"].to(dev), w=0.0)
+        assert rel_l2(d, case["D"]) < BF16_TOL and rel_l2(f, case["F"]) < BF16_TOL
+
+
+def test_sample_edm_trajectory_parity_with_injected_noise(dev):
+    g = golden("trajectory.pt")
+    pl, cfg = stress_module()
+    pl = pl.to(dev)
+    state, _, _, _ = fixture_state()
+    for tr in g["trajs"]:
+        feed = NoiseFeed(tr["seed"])
+        pl._noise_hook = feed.hook
+        pl._trace = []
+        mask = tr["mask"].to(dev)
+        cond_in = pl.get_cond_in(state.to(dev), mask, None, None).permute(0, 3, 1, 2).contiguous()
+        mask_c = mask.permute(0, 3, 1, 2).contiguous()
+        hu = feed.draw(mask_c)
+        sp = copy.deepcopy(cfg.diff_sampler)
+        sp.timesteps = tr["steps"]
+        xs = pl.sample_edm(hu, cond_in, mask_c, sp, return_last=True, guide_dx=False)
+        assert feed.calls == tr["calls"], "RNG draws differ from the reference in shape / dtype / order"
+        assert len(pl._trace) == len(tr["denoised"])
+        for (i, which, sigma, d), ref in zip(pl._trace, tr["denoised"]):
+            assert abs(sigma - ref["sigma"]) <= 1e-6 * max(1.0, ref["sigma"])
+            assert rel_l2(d, ref["D"]) < BF16_TOL, f"step {i}.{which} sigma {sigma}"
+        assert xs.dtype == torch.float64 and tuple(xs.shape) == tuple(tr["xs"].shape)
+        known = tr["mask"] == 0
+        assert torch.equal(xs[:, -1].cpu()[known], state.double()[known])   # bit-identical observed entries
+        assert rel_l2(xs, tr["xs"]) < 5e-2
+    pl._noise_hook = pl._trace = None
+
+
+def test_full_trajectory_rmse_within_2pct_of_reference(dev):
+    g = golden("trajectory_full.pt")
+    pl, cfg = stress_module()
+    pl = pl.to(dev)
+    state, h, u, _ = fixture_state()
+    from mcedm_b200 import data as D
+
+    mask = D.sample_mask(h[0], u[0], False)[g["mask_name"]].unsqueeze(0)
+    feed = NoiseFeed(g["seed"])
+    pl._noise_hook = feed.hook
+    cond_in = pl.get_cond_in(state.to(dev), mask.to(dev), None, None).permute(0, 3, 1, 2).contiguous()
+    mask_c = mask.permute(0, 3, 1, 2).contiguous().to(dev)
+    hu = feed.draw(mask_c)
+    xs = pl.sample_edm(hu, cond_in, mask_c, copy.deepcopy(cfg.diff_sampler), return_last=True)
+    pl._noise_hook = None
+    assert len(feed.calls) == g["n_calls"]
+    rmse = torch.sqrt((((xs[:, -1].cpu() - state) * mask) ** 2).sum() / mask.sum())
+    assert abs(float(rmse) - float(g["rmse"])) <= 0.02 * float(g["rmse"])
+
+
+def test_no_cpu_fallback(dev):
+    net, _, _ = stress_unet()
+    with pytest.raises(Exception):
+        net(torch.zeros(1, 2, 128, 128), torch.tensor([0.1]), torch.zeros(1, 2, 128, 128))

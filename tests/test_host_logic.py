@@ -1,0 +1,122 @@
+"""CPU: host-side logic — config composition, module surface / checkpoint keys, schedule and scalars,
+synthetic data contract, and the multi-process sharding paths on gloo (world_size 2)."""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+from common import hparams, stress_module
+from mcedm_b200 import data as D
+from mcedm_b200.config import AttrDict, compose
+from oracle import edm_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_compose_applies_reference_style_overrides():
+    cfg = compose("config_adm_edm_mcedm_res32", ["datamodule.batch_size=16", "diff_sampler.n_samples=1",
+                                                 "system=swe_per"])
+    assert cfg.datamodule.batch_size == 16 and cfg.diff_sampler.n_samples == 1 and cfg.system == "swe_per"
+    m = cfg.model.hparams.model
+    assert (m.ch, list(m.ch_mult), m.resolution, list(m.attn_resolutions)) == (64, [1, 1, 1], 128, [32])
+    assert not hasattr(m, "node_type") and m.get("node_type", 7) == 7     # OmegaConf-like missing-key semantics
+    assert float(cfg.model.hparams.sampler.S_max) == float("inf")
+
+
+def test_module_surface_and_checkpoint_keys():
+    pl, cfg = stress_module()
+    sd = pl.state_dict()
+    assert len(sd) == 412
+    for k in ("model.map_layer0.weight", "model.enc.128x128_conv.weight", "model.dec.32x32_block0.qkv.weight",
+              "model.dec.128x128_block1.skip.weight", "model.out_conv.weight", "ema_model.ma_model.out_conv.weight",
+              "normalizer_input.subtract", "normalizer_target.divide", "model.enc.64x64_down.conv0.resample_filter"):
+        assert k in sd, k
+    assert tuple(sd["model.dec.32x32_block0.qkv.weight"].shape) == (192, 64, 1, 1)
+    assert tuple(sd["model.out_conv.weight"].shape) == (2, 64, 3, 3)
+    opt = pl.configure_optimizers()["optimizer"]
+    assert isinstance(opt, torch.optim.Adam) and sum(p.numel() for g in opt.param_groups for p in g["params"]) == 1587010
+    for name in ("model_precond", "forward", "get_denoised", "sample_edm", "training_step", "validation_step",
+                 "test_step", "get_cond_in", "get_loss_weight", "round_sigma", "set_test_sampler_params"):
+        assert callable(getattr(pl, name))
+
+
+def test_ema_update_matches_reference_rule():
+    pl, _ = stress_module()
+    before = copy.deepcopy(pl.ema_model.ma_model.state_dict())
+    with torch.no_grad():
+        for p in pl.model.parameters():
+            p.add_(0.01)
+    pl.ema_model.update(pl.model)
+    for (k, v), p in zip(pl.ema_model.ma_model.named_parameters(), pl.model.parameters()):
+        assert torch.allclose(v, before[k] * 0.999 + 0.001 * p, rtol=0, atol=1e-7)
+
+
+def test_schedule_and_precond_scalars_match_oracle():
+    from mcedm_b200.mcedm import precond_scalars
+
+    pl, cfg = stress_module()
+    t = pl.edm_time_steps(cfg.diff_sampler)
+    ref = O.edm_schedule(50, 0.002, 80, 7)
+    assert len(t) == 51 and t[-1] == 0.0 and t == ref.tolist()
+    assert abs(t[0] - 80.0) < 1e-9 and abs(t[1] - 71.5010) < 1e-3 and abs(t[49] - 0.002) < 1e-12
+    for sigma in (80.0, 104.0, 1.3, 0.0026, 0.002):
+        cs, co, ci, cn = precond_scalars(sigma)
+        r = [float(v.reshape(())) for v in O.precond_coeffs(torch.tensor(sigma, dtype=torch.float64))]
+        assert (cs, co, ci) == (r[0], r[1], r[2])
+        assert abs(cn - r[3]) <= 2e-7 * max(1.0, abs(r[3]))
+
+
+def test_synthetic_batches_have_the_reference_contract():
+    h, tg, xg, u, m = D.make_batch("swe_per", 3, "train", seed=1)
+    assert h.shape == u.shape == (3, 128, 128, 1) and m.shape == (3, 128, 128, 2) and tg.shape == (3, 128, 128, 1)
+    assert 0.99 <= float(h.min()) and float(h.max()) <= 2.01 and float(u.abs().max()) < 1.0
+    assert set(m.unique().tolist()) <= {0.0, 1.0}
+    # each item misses exactly one whole variable
+    assert all(float(m[i, ..., 0].mean()) + float(m[i, ..., 1].mean()) == 1.0 for i in range(3))
+    _, _, _, _, md = D.make_batch("swe", 2, "eval")
+    assert set(md) == {"u", "h"} and float(md["u"][..., 1].min()) == 1.0 and float(md["u"][..., 0].max()) == 0.0
+    a, ud = D.darcy_fields(2)
+    assert set(np.unique(a).tolist()) <= {np.float32(0.1), np.float32(1.0)} and ud.min() >= 0
+    dm = D.SyntheticMaskDatamodule(system="swe_per", n_train=8, n_test=4, batch_size=4)
+    dm.setup("fit")
+    st = dm.get_norm_stats()
+    assert tuple(st["input_mean"].shape) == (1,)
+    b = next(iter(dm.train_dataloader()))
+    assert len(b) == 5 and b[4].shape == (4, 128, 128, 2)
+    bt = next(iter(dm.test_dataloader()))
+    assert isinstance(bt[4], dict) and bt[4]["h"].shape == (4, 128, 128, 2)
+
+
+def test_unsupported_reference_options_raise():
+    from mcedm_b200.mcedm import PlMcedm
+
+    hp = copy.deepcopy(hparams().model.hparams)
+    hp.model.dx_cond = True
+    try:
+        PlMcedm(hp)
+        raise AssertionError("dx_cond must raise")
+    except NotImplementedError:
+        pass
+    hp = copy.deepcopy(hparams().model.hparams)
+    hp.optimization.optimizer = "Lion"
+    pl = PlMcedm(hp)
+    try:
+        pl.configure_optimizers()
+        raise AssertionError("unknown optimizer must raise")
+    except NotImplementedError:
+        pass
+
+
+def test_two_rank_gloo_sharding_and_gradient_allreduce():
+    """world_size 2 on CPU: row sharding + gather reproduces the single-process order; flat all-reduce averages."""
+    script = os.path.join(ROOT, "tests", "dist_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2"], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "OK" in outs[0]

@@ -1,0 +1,118 @@
+"""CPU: the oracle (oracle/edm_oracle.py) against fixtures produced by the unmodified reference."""
+import torch
+
+from common import NoiseFeed, fixture_state, golden, hparams, stress_unet
+from mcedm_b200 import data as D
+from mcedm_b200.utils import rel_l2, state_hash
+from oracle import edm_oracle as O
+
+
+def _sd_cfg(config="config_adm_edm_mcedm_res32"):
+    net, cfg, init_hash = stress_unet(config)
+    return {k: v.detach() for k, v in net.state_dict().items()}, dict(cfg.model.hparams.model), cfg, init_hash
+
+
+def test_init_and_stress_weights_match_reference():
+    g = golden("unet_forward.pt")
+    sd, _, _, init_hash = _sd_cfg()
+    assert init_hash == g["init_hash"], "seeded initialisation differs from the reference's"
+    assert state_hash(sd) == g["stress_hash"]
+    assert sum(v.numel() for k, v in sd.items() if "resample_filter" not in k) == g["n_params"] == 1587010
+
+
+def test_oracle_unet_forward_matches_reference():
+    g = golden("unet_forward.pt")
+    sd, mcfg, _, _ = _sd_cfg()
+    for case in g["cases"]:
+        with torch.no_grad():
+            y = O.unet_forward(sd, mcfg, case["x"], case["noise_labels"], case["cond"])
+        assert rel_l2(y, case["out"]) < 1e-6
+        assert case["out"].abs().max() > 0.5, "fixture must not be the vacuous zero-output network"
+
+
+def test_oracle_cond_edm_network_matches_reference():
+    g = golden("cond_edm_forward.pt")
+    sd, mcfg, _, init_hash = _sd_cfg("config_adm_edm_res32_cond_h")
+    assert init_hash == g["init_hash"] and state_hash(sd) == g["stress_hash"]
+    with torch.no_grad():
+        y = O.unet_forward(sd, mcfg, g["x"], g["noise_labels"], g["cond"])
+    assert y.shape == (2, 1, 128, 128) and rel_l2(y, g["out"]) < 1e-6
+
+
+def test_oracle_denoise_matches_reference():
+    g = golden("denoise.pt")
+    sd, mcfg, _, _ = _sd_cfg()
+    for case in g["cases"]:
+        with torch.no_grad():
+            d, f = O.denoise(sd, mcfg, case["xt"], torch.tensor(case["sigma"], dtype=torch.float64), case["cond"])
+        assert rel_l2(d, case["D"]) < 1e-6 and rel_l2(f, case["F"]) < 1e-6
+
+
+def test_oracle_trajectory_matches_reference():
+    g = golden("trajectory.pt")
+    sd, mcfg, cfg, _ = _sd_cfg()
+    state, _, _, _ = fixture_state()
+    for tr in g["trajs"]:
+        assert torch.equal(tr["state"], state), "synthetic field generator drifted from the fixture"
+        feed = NoiseFeed(tr["seed"])
+        mask = tr["mask"]
+        cond_in = O.get_cond_in(state, mask, feed.draw(state)).permute(0, 3, 1, 2).contiguous()
+        mask_c = mask.permute(0, 3, 1, 2).contiguous()
+        hu_arg = feed.draw(mask_c)          # the caller's draw passed as `hu` (mcedm.py:373); only its shape is used
+        hu_noise = feed.draw(hu_arg)        # the sampler's own initial noise (mcedm.py:576)
+        sp = dict(cfg.diff_sampler)
+        sp["timesteps"] = tr["steps"]
+        rec = []
+        with torch.no_grad():
+            xs = O.sample_edm(sd, mcfg, hu_noise, cond_in, mask_c, sp, lambda i, x: feed.draw(x), record=rec)
+        assert feed.calls == tr["calls"], "RNG call sequence (shapes/dtypes/order) differs from the reference"
+        assert len(rec) == len(tr["denoised"])
+        for (i, which, sigma, d), ref in zip(rec, tr["denoised"]):
+            assert abs(sigma - ref["sigma"]) <= 1e-6 * max(1.0, abs(ref["sigma"]))
+            assert rel_l2(d, ref["D"]) < 1e-5
+        assert xs.dtype == torch.float64 and xs.shape == tr["xs"].shape
+        assert rel_l2(xs, tr["xs"]) < 1e-6
+        # observed entries (mask == 0) keep their clean value bit-exactly through the trajectory
+        known = mask == 0
+        assert torch.equal(xs[:, -1][known], state.double()[known])
+
+
+def test_oracle_training_loss_matches_reference():
+    g = golden("train_step.pt")
+    sd, mcfg, _, _ = _sd_cfg()
+    B = g["mask"].shape[0]
+    state, _, _, _ = fixture_state(n=B, seed=g["seed_fields"])
+    feed = NoiseFeed(g["noise_seed"])
+    mask = g["mask"]
+    cond = O.get_cond_in(state, mask, feed.draw(state)).permute(0, 3, 1, 2).contiguous()
+    x = state.permute(0, 3, 1, 2).contiguous()
+    noise = feed.draw(x)
+    torch.manual_seed(g["cpu_seed"])
+    sigma = (torch.randn([B, 1, 1, 1]) * 1.2 - 1.2).exp()
+    with torch.no_grad():
+        loss, _ = O.training_loss(sd, mcfg, x, sigma, noise, cond, mask.permute(0, 3, 1, 2).contiguous())
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+def test_mask_generators_bit_identical():
+    g = golden("masks.pt")
+    _, h, u, _ = fixture_state()
+    torch.manual_seed(g["train_seed"])
+    mine = torch.stack([D.sample_mask(h[0], u[0], True) for _ in range(8)])
+    assert torch.equal(mine.to(torch.uint8), g["train_masks"])
+    torch.manual_seed(g["train_seed"])
+    coins = [float(torch.rand(1)) for _ in range(8)]
+    orc = torch.stack([O.train_mask(h[0], u[0], c) for c in coins])
+    assert torch.equal(orc.to(torch.uint8), g["train_masks"])
+    torch.manual_seed(g["time_seed"])
+    mine_t = torch.stack([D.sample_time_mask(h[0], u[0], True) for _ in range(8)])
+    assert torch.equal(mine_t.to(torch.uint8), g["time_train"])
+    ev = D.sample_mask(h[0], u[0], False)
+    assert torch.equal(ev["u"].to(torch.uint8), g["eval_u"]) and torch.equal(ev["h"].to(torch.uint8), g["eval_h"])
+    oe = O.eval_masks(h[0], u[0])
+    assert torch.equal(oe["u"].to(torch.uint8), g["eval_u"]) and torch.equal(oe["h"].to(torch.uint8), g["eval_h"])
+    te = D.sample_time_mask(h[0], u[0], False, add_time_masks=True)
+    ot = O.time_eval_masks(h[0], u[0])
+    for k in ("hu", "u", "h"):
+        assert torch.equal(te[k].to(torch.uint8), g["time_eval"][k])
+        assert torch.equal(ot[k].to(torch.uint8), g["time_eval"][k])
