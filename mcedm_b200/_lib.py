@@ -42,6 +42,9 @@ _PROTOTYPES = {
 _RESTYPES = {"mcedm_last_error": C.c_char_p}
 
 _lib = None
+# number of kernel launches issued through the C ABI by this process (every successful call below launches
+# exactly one kernel; graph replays are added by the engine); bench.py reports it as gpu_launches
+LAUNCHES = [0]
 
 
 class McedmError(RuntimeError):
@@ -76,6 +79,7 @@ def lib():
 
 
 def check(rc: int, what: str = ""):
+    LAUNCHES[0] += 1
     if rc != 0:
         msg = lib().mcedm_last_error()
         raise McedmError(f"{what or 'mcedm call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
@@ -103,3 +107,4 @@ def stream_ptr():
 
 def check_watchdog():
     check(lib().mcedm_check_watchdog(stream_ptr()), "watchdog")
+    LAUNCHES[0] -= 1

@@ -230,9 +230,17 @@ def test_sample_edm_trajectory_parity_with_injected_noise(dev):
         xs = pl.sample_edm(hu, cond_in, mask_c, sp, return_last=True, guide_dx=False)
         assert feed.calls == tr["calls"], "RNG draws differ from the reference in shape / dtype / order"
         assert len(pl._trace) == len(tr["denoised"])
-        for (i, which, sigma, d), ref in zip(pl._trace, tr["denoised"]):
+        sd = {k: v.detach().cpu() for k, v in pl.ema_model.ma_model.state_dict().items()}
+        mcfg = dict(cfg.model.hparams.model)
+        for (i, which, sigma, d, xt), ref in zip(pl._trace, tr["denoised"]):
             assert abs(sigma - ref["sigma"]) <= 1e-6 * max(1.0, ref["sigma"])
-            assert rel_l2(d, ref["D"]) < BF16_TOL, f"step {i}.{which} sigma {sigma}"
+            # per-step denoiser parity on the SAME input: the oracle (pinned to the reference) evaluated on the
+            # state this path actually fed to the network
+            with torch.no_grad():
+                d_or, _ = O.denoise(sd, mcfg, xt.cpu(), torch.tensor(sigma, dtype=torch.float64), cond_in.cpu())
+            assert rel_l2(d, d_or) < BF16_TOL, f"step {i}.{which} sigma {sigma}"
+            # and against the reference's own trajectory (inputs differ by the accumulated bf16 deviations)
+            assert rel_l2(d, ref["D"]) < 3e-2, f"step {i}.{which} sigma {sigma} (trajectory)"
         assert xs.dtype == torch.float64 and tuple(xs.shape) == tuple(tr["xs"].shape)
         known = tr["mask"] == 0
         assert torch.equal(xs[:, -1].cpu()[known], state.double()[known])   # bit-identical observed entries
