@@ -62,6 +62,34 @@ MCEDM_API int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg
                      int n_seg, const void* w_packed, const float* bias, int B, int H, int W, int N, void* out,
                      int out_bf16, const float* res, int res_mode, float* stats_partial, void* stream);
 
+/*
+ * Row-resident variant of mcedm_conv_igemm for W == 128 (one tile = one image row): every input row is
+ * fetched once (TMA box with a 1-pixel zero halo) and reused by its 9 taps through row-shifted UMMA
+ * descriptors.  Same weight packing: w_packed = bf16 [9*n_halo + n_ctr][N][64], segment order
+ * (halo source, ky, kx) then the centre sources.
+ *   halo_src[i] : n_halo (1..2) bf16 NHWC [B,H,128,64] tensors convolved 3x3
+ *   ctr_src[i]  : n_ctr (0..2) bf16 NHWC tensors entering with the centre tap only (1x1 skip projection)
+ *   N           : 16 or 64; res_mode 0 | 1 | 2 as in mcedm_conv_igemm; out may alias res when res_mode == 1.
+ *   stats_partial: NULL or fp32 [B*H][4][N/4][2]: one (sum, sum of squares) record per image row and
+ *                 32-pixel quarter of it (no cross-warp reduction in the epilogue).
+ */
+MCEDM_API int mcedm_conv_rows(const void* const* halo_src, int n_halo, const void* const* ctr_src, int n_ctr,
+                              const void* w_packed, const float* bias, int B, int H, int N, void* out, int out_bf16,
+                              const float* res, int res_mode, float* stats_partial, void* stream);
+
+/*
+ * Narrow-level (W <= 64) variant: the bf16 operand is a zero-padded flat pixel sequence (written by
+ * mcedm_gn_apply with out_pitch/out_blk), position(b,y,x) = b*blk + (y+1)*pitch + x, so every filter tap
+ * is a constant row offset and each 16 KB chunk of the input is fetched once.
+ *   mcedm_flat_geometry: pitch = W + 8, block_positions = roundup((H+2)*pitch, 128)
+ *   src_flat  bf16 [B*block_positions, 64]; w_packed bf16 [9][64][64]; out fp32 NHWC [B,H,W,64] (dense)
+ *   res_mode  0 | 1 | 2 | 3 as in mcedm_conv_igemm; out may alias res when res_mode == 1
+ *   stats_partial NULL or fp32 [B*block_positions/128][4][16][2]
+ */
+MCEDM_API int mcedm_flat_geometry(int H, int W, int* pitch, int* block_positions);
+MCEDM_API int mcedm_conv_flat(const void* src_flat, const void* w_packed, const float* bias, int B, int H, int W, int N,
+                              float* out, const float* res, int res_mode, float* stats_partial, void* stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* K2  GroupNorm statistics / fused GroupNorm + scale-shift + SiLU + resample                     */
 /*     (models/adm_blocks.py:86-97 GroupNorm; :161, :163-166, :175, :403 call sites)              */
@@ -71,7 +99,9 @@ MCEDM_API int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg
 MCEDM_API int mcedm_gn_stats(const float* x, long long n_pixels, float* partial, void* stream);
 /*
  * out = act( GroupNorm(x) * (1 + scale) + shift ), optionally resampled, written as bf16 NHWC.
- *   x            fp32 NHWC [B,Hin,Win,64]; partial = its tile statistics [B*Hin*Win/128][16][2]
+ *   x            fp32 NHWC [B,Hin,Win,64]; partial = its statistics records [B*parts_per_img][16][2]
+ *                (parts_per_img = 0 means Hin*Win/128, the mcedm_conv_igemm / mcedm_gn_stats format;
+ *                mcedm_conv_rows emits 4 records per image row: parts_per_img = 4*Hin)
  *   gamma, beta  fp32 [64] (slice of the GroupNorm affine for these 64 channels)
  *   scale_shift  NULL, or fp32 with scale[c] at [b*emb_batch_stride + c] and shift[c] at
  *                [b*emb_batch_stride + emb_shift_offset + c]  (affine(emb).chunk(2), adm_blocks.py:163-165;
@@ -79,11 +109,15 @@ MCEDM_API int mcedm_gn_stats(const float* x, long long n_pixels, float* partial,
  *   act          0 identity (norm2), 1 SiLU
  *   resample     0 none | 1 nearest x2 (out is [B,2Hin,2Win,64]) | 2 2x2 mean (out is [B,Hin/2,Win/2,64]);
  *                this is the resampling Conv2d applies before its 3x3 filter (adm_blocks.py:73-77)
- *   out_raw_bf16 NULL, or receives bf16(x) (operand of the block's 1x1 skip projection)
+ *   out_pitch, out_blk  0, 0: out is dense NHWC; otherwise out is the zero-padded flat layout consumed by
+ *                mcedm_conv_flat (values from mcedm_flat_geometry at the OUTPUT resolution); only data
+ *                positions are written, the padding must have been zeroed once by the owner of the buffer
+ *   out_raw_bf16 NULL, or receives bf16(x) in dense NHWC (operand of the block's 1x1 skip projection)
  */
 MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int act,
-                             int resample, int B, int Hin, int Win, void* out_bf16, void* out_raw_bf16, void* stream);
+                             int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch, int out_blk,
+                             void* out_bf16, void* out_raw_bf16, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */

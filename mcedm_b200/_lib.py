@@ -23,8 +23,11 @@ _PROTOTYPES = {
     "mcedm_abi_version": [],
     "mcedm_check_watchdog": [_vp],
     "mcedm_conv_igemm": [_vpp, _i, _ip, _ip, _ip, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp],
+    "mcedm_conv_rows": [_vpp, _i, _vpp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mcedm_gn_stats": [_vp, C.c_longlong, _vp, _vp],
-    "mcedm_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mcedm_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mcedm_flat_geometry": [_i, _i, _ip, _ip],
+    "mcedm_conv_flat": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
     "mcedm_attention": [_vp, _i, _i, _vp, _vp],
     "mcedm_attention_ref": [_vp, _i, _i, _vp, _vp],
     "mcedm_emb_mlp": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],

@@ -1,0 +1,395 @@
+// K1b — 3x3 convolution for 128-pixel-wide images: implicit GEMM on tcgen05 with ROW-RESIDENT input.
+//
+// Same math and same packed-weight layout as conv_igemm.cu (models/adm_blocks.py:65-81 Conv2d.forward,
+// fused residual :171 and 1x1 skip :150-151), specialised for the level that carries 68 % of the
+// network's FLOPs (W = 128, one output tile = one image row).  conv_igemm fetches one 16 KB A tile per
+// filter tap (9 L2->SMEM loads per tile) and measured L2-bandwidth bound at ~330 TFLOP/s; here every
+// input row is fetched ONCE:
+//
+//   * a CTA owns a contiguous range of output rows (balanced over the grid: one wave, no tail);
+//   * input row y of a source is one TMA box (64 ch, 130 px, 1, 1) at x = -1: 130 x 128 B with the
+//     left/right zero padding supplied by TMA out-of-bounds fill, kept in a ring of row slots;
+//   * the tap (dy, dx) of output row y is the SAME slot (input row y+dy) addressed through a UMMA
+//     descriptor whose start address is advanced by (dx+1) * 128 B — SWIZZLE_128B is a function of the
+//     absolute shared-memory address, so a row-shifted view of a swizzled tile is still a valid
+//     K-major operand (pinned on silicon by tests/test_gpu_parity.py::test_umma_row_shifted_descriptor);
+//   * each input row is used by 3 output rows x 3 dx taps = 9 segments before its slot is recycled:
+//     L2->SMEM traffic drops from 147 KB to ~17 KB per tile.
+//   * optional "centre" sources (the raw bf16 block input of the 1x1 skip projection) are plain
+//     128 x 128 B tiles loaded once per output row.
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-9 epilogue: two warps per
+// TMEM lane quarter, each draining one 32-column half of the tile (4-deep TMEM accumulator ring; the
+// residual tile is prefetched before the accumulator is waited for; GroupNorm partial sums are written
+// per (tile, lane quarter) so the epilogue warps never synchronise with each other).
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+#include <cuda_bf16.h>
+
+namespace mcedm {
+
+constexpr int kHaloRows = 130;
+constexpr int kHaloBytes = 17 * 1024;          // 130 x 128 B = 16640, padded to a 1024 multiple
+constexpr int kHaloTx = kHaloRows * 128;
+constexpr int kCtrBytes = 16 * 1024;
+
+struct RowsParams {
+  int n_halo;            // 1..2 sources with 9 taps each
+  int n_ctr;             // 0..2 centre-tap sources
+  int n_slots;           // halo ring depth (input rows)
+  int n_cslots;          // centre ring depth (output rows)
+  int H;                 // image height; W == 128
+  long long total_rows;  // B * H
+  const float* bias;
+  void* out;
+  int out_bf16;
+  const float* res;
+  int res_mode;          // 0 none, 1 same resolution, 2 nearest-x2 upsample of res
+  float* stats;          // [total_rows][4 lane quarters][N/4][2]
+  unsigned int* err;
+};
+
+template <int N>
+struct RowsCfg {
+  static constexpr int CH = (N >= 32) ? 32 : 16;
+  static constexpr int NCH = N / CH;
+  static constexpr int U = CH / 4;
+  static constexpr int W_SEG_BYTES = N * 128;
+  static constexpr int EPI_WARPS = 4 * NCH;                 // one warp per (lane quarter, column chunk)
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
+  static constexpr int ACC_BUFS = 4;
+  static constexpr int TMEM_COLS = (ACC_BUFS * N <= 32) ? 32 : (ACC_BUFS * N <= 64) ? 64 : (ACC_BUFS * N <= 128) ? 128 : 256;
+};
+
+// UMMA descriptor = constant high word | (address >> 4): the issuing thread only does 32-bit adds
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t addr) {
+  constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 | version 1 | SWIZZLE_128B
+  const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | (1u << 16);         // start address | LBO = 1
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+template <int N>
+__global__ void __launch_bounds__(RowsCfg<N>::THREADS, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_h0,
+                 const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_c0,
+                 const __grid_constant__ CUtensorMap tm_c1, const RowsParams p) {
+  using Cfg = RowsCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_seg = p.n_halo * 9 + p.n_ctr;
+  const int slot_bytes = p.n_halo * kHaloBytes;
+  const int cslot_bytes = p.n_ctr * kCtrBytes;
+  uint8_t* w_smem = smem;
+  uint8_t* h_smem = w_smem + n_seg * Cfg::W_SEG_BYTES;
+  uint8_t* c_smem = h_smem + p.n_slots * slot_bytes;
+  uint8_t* stage_smem = c_smem + p.n_cslots * cslot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + Cfg::STAGE_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* acc_full = bars + 1;                     // ACC_BUFS
+  uint64_t* acc_empty = acc_full + Cfg::ACC_BUFS;    // ACC_BUFS
+  uint64_t* h_full = acc_empty + Cfg::ACC_BUFS;      // n_slots
+  uint64_t* h_empty = h_full + p.n_slots;
+  uint64_t* c_full = h_empty + p.n_slots;   // n_cslots
+  uint64_t* c_empty = c_full + p.n_cslots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + p.n_cslots);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // balanced contiguous row range of this CTA
+  const long long r_begin = p.total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = p.total_rows * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_w);
+    prefetch_tmap(&tm_h0);
+    mbar_init(w_full, 1);
+    for (int i = 0; i < Cfg::ACC_BUFS; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 32 * Cfg::EPI_WARPS);
+    }
+    for (int i = 0; i < p.n_slots; ++i) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&h_empty[i], 1);
+    }
+    for (int i = 0; i < p.n_cslots; ++i) {
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)(n_seg * Cfg::W_SEG_BYTES));
+      for (int s = 0; s < n_seg; ++s) tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * N);
+      uint32_t hl = 0, cl = 0;   // halo rows / centre tiles loaded so far
+      long long r = r_begin;
+      while (r < r_end) {
+        const int b = (int)(r / p.H);
+        const int y0 = (int)(r - (long long)b * p.H);
+        const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+        for (int k = 0; k < R + 2; ++k) {
+          const uint32_t slot = hl % (uint32_t)p.n_slots, ph = (hl / (uint32_t)p.n_slots) & 1u;
+          mbar_wait(&h_empty[slot], ph ^ 1u, p.err, 0x2100 + slot);
+          mbar_expect_tx(&h_full[slot], (uint32_t)(p.n_halo * kHaloTx));
+          tma_load_4d(h_smem + slot * slot_bytes, &tm_h0, &h_full[slot], 0, -1, y0 - 1 + k, b);
+          if (p.n_halo > 1)
+            tma_load_4d(h_smem + slot * slot_bytes + kHaloBytes, &tm_h1, &h_full[slot], 0, -1, y0 - 1 + k, b);
+          ++hl;
+          if (p.n_ctr > 0 && k >= 2) {
+            const uint32_t cs = cl % (uint32_t)p.n_cslots, cph = (cl / (uint32_t)p.n_cslots) & 1u;
+            mbar_wait(&c_empty[cs], cph ^ 1u, p.err, 0x2200 + cs);
+            mbar_expect_tx(&c_full[cs], (uint32_t)(p.n_ctr * kCtrBytes));
+            tma_load_4d(c_smem + cs * cslot_bytes, &tm_c0, &c_full[cs], 0, 0, y0 + k - 2, b);
+            if (p.n_ctr > 1) tma_load_4d(c_smem + cs * cslot_bytes + kCtrBytes, &tm_c1, &c_full[cs], 0, 0, y0 + k - 2, b);
+            ++cl;
+          }
+        }
+        r += R;
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+      mbar_wait(w_full, 0, p.err, 0x2300);
+      tc_fence_after();
+      const uint32_t w_base = smem_u32(w_smem);
+      const uint32_t h_base = smem_u32(h_smem);
+      const uint32_t c_base = smem_u32(c_smem);
+      uint32_t hbase = 0;      // global index of the current segment's first halo row
+      uint32_t waited = 0;     // halo rows [0, waited) are known to have landed
+      uint32_t cc = 0, tcount = 0;
+      long long r = r_begin;
+      while (r < r_end) {
+        const int b = (int)(r / p.H);
+        const int y0 = (int)(r - (long long)b * p.H);
+        const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+        for (int j = 0; j < R; ++j, ++tcount) {
+          const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
+          mbar_wait(&acc_empty[buf], aph ^ 1u, p.err, 0x2400 + buf);
+          while (waited < hbase + j + 3) {
+            const uint32_t slot = waited % (uint32_t)p.n_slots, ph = (waited / (uint32_t)p.n_slots) & 1u;
+            mbar_wait(&h_full[slot], ph, p.err, 0x2500 + slot);
+            ++waited;
+          }
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * N;
+          uint32_t first = 1;
+          for (int s = 0; s < p.n_halo; ++s) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t slot = (hbase + j + ky) % (uint32_t)p.n_slots;
+              const uint32_t row_base = h_base + slot * slot_bytes + s * kHaloBytes;
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint32_t a_base = row_base + kx * 128;     // (dx + 1) pixel rows into the halo'd row
+                const uint32_t b_base = w_base + (s * 9 + ky * 3 + kx) * Cfg::W_SEG_BYTES;
+#pragma unroll
+                const uint64_t ad = desc_from_lo(a_base), bd = desc_from_lo(b_base);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {   // +32 B along K = +2 in the (address >> 4) field
+                  umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first ? 0u : 1u);
+                  first = 0;
+                }
+              }
+            }
+          }
+          if (p.n_ctr > 0) {
+            const uint32_t cs = cc % (uint32_t)p.n_cslots, cph = (cc / (uint32_t)p.n_cslots) & 1u;
+            mbar_wait(&c_full[cs], cph, p.err, 0x2600 + cs);
+            tc_fence_after();
+            for (int s = 0; s < p.n_ctr; ++s) {
+              const uint32_t a_base = c_base + cs * cslot_bytes + s * kCtrBytes;
+              const uint32_t b_base = w_base + (p.n_halo * 9 + s) * Cfg::W_SEG_BYTES;
+              const uint64_t ad = desc_from_lo(a_base), bd = desc_from_lo(b_base);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+            }
+            umma_commit(&c_empty[cs]);
+            ++cc;
+          }
+          // input row (hbase + j) has no further user; the last output row also frees the two rows below it
+          umma_commit(&h_empty[(hbase + j) % (uint32_t)p.n_slots]);
+          if (j == R - 1) {
+            umma_commit(&h_empty[(hbase + j + 1) % (uint32_t)p.n_slots]);
+            umma_commit(&h_empty[(hbase + j + 2) % (uint32_t)p.n_slots]);
+          }
+          umma_commit(&acc_full[buf]);
+        }
+        hbase += R + 2;
+        r += R;
+      }
+    }
+  } else {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int ew = warp - 2;                // 0 .. EPI_WARPS-1
+    const int ch = ew >> 2;                 // column chunk drained by this warp
+    uint8_t* my_stage = stage_smem + ew * (32 * Cfg::CH * 4);
+    const int unit = lane % Cfg::U;
+    const int row_in_it = lane / Cfg::U;
+    constexpr int ROWS_PER_IT = 32 / Cfg::U;
+    const int c0 = ch * Cfg::CH + unit * 4;
+    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bz = *reinterpret_cast<const float4*>(p.bias + c0);
+    uint32_t tcount = 0;
+    for (long long r = r_begin; r < r_end; ++r, ++tcount) {
+      const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
+      const long long pix0 = r * 128 + q * 32;
+      // residual prefetch (independent of the accumulator)
+      float4 rr[Cfg::U];
+      if (p.res_mode == 1) {
+#pragma unroll
+        for (int itr = 0; itr < Cfg::U; ++itr)
+          rr[itr] = *reinterpret_cast<const float4*>(p.res + (pix0 + itr * ROWS_PER_IT + row_in_it) * N + c0);
+      } else if (p.res_mode == 2) {
+        const int bimg = (int)(r / p.H);
+        const int y = (int)(r - (long long)bimg * p.H);
+        const float* rrow = p.res + ((long long)bimg * (p.H >> 1) + (y >> 1)) * 64 * N + c0;
+#pragma unroll
+        for (int itr = 0; itr < Cfg::U; ++itr)
+          rr[itr] = *reinterpret_cast<const float4*>(rrow + ((q * 32 + itr * ROWS_PER_IT + row_in_it) >> 1) * N);
+      }
+      mbar_wait(&acc_full[buf], aph, p.err, 0x2700 + buf);
+      tc_fence_after();
+      uint32_t v[Cfg::CH];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * N + ch * Cfg::CH;
+      if constexpr (Cfg::CH == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+#pragma unroll
+      for (int j = 0; j < Cfg::U; ++j) {
+        const int pj = j ^ (lane & (Cfg::U - 1));
+        *reinterpret_cast<uint4*>(my_stage + lane * (Cfg::CH * 4) + pj * 16) =
+            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      __syncwarp();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int itr = 0; itr < Cfg::U; ++itr) {
+        const int row = itr * ROWS_PER_IT + row_in_it;
+        const int pu = unit ^ (row & (Cfg::U - 1));
+        float4 a = *reinterpret_cast<const float4*>(my_stage + row * (Cfg::CH * 4) + pu * 16);
+        a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
+        if (p.res_mode != 0) {
+          a.x += rr[itr].x; a.y += rr[itr].y; a.z += rr[itr].z; a.w += rr[itr].w;
+        }
+        s1 += (a.x + a.y) + (a.z + a.w);
+        s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+        const long long pix = pix0 + row;
+        if (p.out_bf16) {
+          uint2 o;
+          o.x = pack_bf16x2(a.x, a.y);
+          o.y = pack_bf16x2(a.z, a.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * N + c0) = o;
+        } else {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * N + c0) = a;
+        }
+      }
+      if (p.stats) {
+        // lanes sharing `unit` hold the same 4-channel group; partial = (tile, lane quarter, group)
+#pragma unroll
+        for (int off = Cfg::U; off < 32; off <<= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+        if (lane < Cfg::U)
+          *reinterpret_cast<float2*>(p.stats + ((r * 4 + q) * (N / 4) + ch * Cfg::U + lane) * 2) = make_float2(s1, s2);
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int N>
+static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const CUtensorMap* tm_c, RowsParams p,
+                       cudaStream_t stream) {
+  using Cfg = RowsCfg<N>;
+  const int n_seg = p.n_halo * 9 + p.n_ctr;
+  const int fixed = 1024 + n_seg * Cfg::W_SEG_BYTES + Cfg::STAGE_BYTES + 512;
+  const int slot_bytes = p.n_halo * kHaloBytes;
+  p.n_cslots = p.n_ctr ? 2 : 0;
+  int avail = 232448 - fixed - p.n_cslots * p.n_ctr * kCtrBytes;
+  int slots = avail / slot_bytes;
+  if (slots < 4 && p.n_ctr) {            // trade the centre double-buffer for halo depth
+    p.n_cslots = 1;
+    avail = 232448 - fixed - p.n_cslots * p.n_ctr * kCtrBytes;
+    slots = avail / slot_bytes;
+  }
+  if (slots > 8) slots = 8;
+  MCEDM_REQUIRE(slots >= 3, "conv_rows: %d halo sources + %d centre sources with N=%d do not fit in shared memory",
+                p.n_halo, p.n_ctr, N);
+  p.n_slots = slots;
+  const int smem = fixed + slots * slot_bytes + p.n_cslots * p.n_ctr * kCtrBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  long long grid = p.total_rows < num_sms() ? p.total_rows : num_sms();
+  conv_rows_kernel<N><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_conv_rows(const void* const* halo_src, int n_halo, const void* const* ctr_src, int n_ctr,
+                               const void* w_packed, const float* bias, int B, int H, int N, void* out, int out_bf16,
+                               const float* res, int res_mode, float* stats_partial, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n_halo >= 1 && n_halo <= 2 && n_ctr >= 0 && n_ctr <= 2, "conv_rows: n_halo=%d n_ctr=%d", n_halo, n_ctr);
+  MCEDM_REQUIRE(B >= 1 && H >= 1, "conv_rows: bad B/H");
+  MCEDM_REQUIRE(res_mode >= 0 && res_mode <= 2 && (res_mode == 0 || res != nullptr), "conv_rows: bad residual mode");
+  MCEDM_REQUIRE(res_mode != 2 || H % 2 == 0, "conv_rows: upsampled residual needs even H");
+  RowsParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_halo = n_halo;
+  p.n_ctr = n_ctr;
+  p.H = H;
+  p.total_rows = (long long)B * H;
+  p.bias = bias;
+  p.out = out;
+  p.out_bf16 = out_bf16;
+  p.res = res;
+  p.res_mode = res_mode;
+  p.stats = stats_partial;
+  p.err = watchdog_ptr();
+  MCEDM_REQUIRE(p.err != nullptr, "conv_rows: cannot allocate the watchdog word");
+  CUtensorMap tm_w, tm_h[2], tm_c[2];
+  int rc = make_tmap_rows64_bf16(&tm_w, w_packed, (long long)(n_halo * 9 + n_ctr) * N, N);
+  if (rc) return rc;
+  for (int i = 0; i < 2; ++i) {
+    rc = make_tmap_nhwc_bf16(&tm_h[i], halo_src[i < n_halo ? i : 0], B, H, 128, 64, kHaloRows, 1);
+    if (rc) return rc;
+    rc = make_tmap_nhwc_bf16(&tm_c[i], n_ctr ? ctr_src[i < n_ctr ? i : 0] : halo_src[0], B, H, 128, 64, 128, 1);
+    if (rc) return rc;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (N) {
+    case 16: return launch_rows<16>(tm_w, tm_h, tm_c, p, st);
+    case 64: return launch_rows<64>(tm_w, tm_h, tm_c, p, st);
+    default: return fail(-1, "conv_rows: N=%d unsupported (16, 64)", N);
+  }
+}

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 struct GnApplyParams {
   const float* x;            // fp32 NHWC [B, Hin, Win, 64]
   const float* partial;      // [B*tiles_per_img][16][2]
-  int tiles_per_img;         // Hin*Win/128
+  int tiles_per_img;         // partial-sum records per image (Hin*Win/128, or 4x that from conv_rows)
   const float* gamma;        // [64]
   const float* beta;         // [64]
   const float* scale_shift;  // nullptr or [Bemb][2*C_emb]: scale at +c, shift at +C_emb+c
@@ -72,7 +72,15 @@ struct GnApplyParams {
   void* out;                 // bf16 NHWC at the output resolution
   void* out_raw;             // nullptr or bf16 NHWC copy of x itself (same resolution only)
   int pix_per_cta;           // INPUT pixels per CTA for resample 0/1, OUTPUT pixels per CTA for resample 2
+  int out_pitch;             // 0: dense NHWC output; > 0: padded flat layout of conv_flat.cu (row pitch)
+  int out_blk;               // positions per image block of the padded layout
 };
+
+// pixel index of output (b, y, x) in the dense NHWC layout or in the padded flat layout
+__device__ __forceinline__ long long gn_out_index(const GnApplyParams& p, int b, int y, int x, int Ho, int Wo) {
+  if (p.out_pitch > 0) return (long long)b * p.out_blk + (long long)(y + 1) * p.out_pitch + x;
+  return ((long long)b * Ho + y) * Wo + x;
+}
 
 __device__ __forceinline__ float4 gn_act4(float4 v, const float4 a, const float4 b, int act) {
   v.x = fmaf(v.x, a.x, b.x);
@@ -101,13 +109,26 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   __shared__ float sMean[16], sRstd[16];
   const int b = blockIdx.y;
   {
-    // fold the per-tile partial sums of image b: 16 threads per group, fixed order, fp64
+    // fold the partial-sum records of image b: 16 threads per group, fixed order, fp64.
+    // Loads are issued 8 at a time before any add so the L2 latency is paid once per batch, not per record.
     const int g = threadIdx.x >> 4, j = threadIdx.x & 15;
     double s1 = 0.0, s2 = 0.0;
-    const float* pp = p.partial + (long long)b * p.tiles_per_img * 32 + g * 2;
-    for (int t = j; t < p.tiles_per_img; t += 16) {
-      s1 += (double)pp[t * 32];
-      s2 += (double)pp[t * 32 + 1];
+    const float2* pp = reinterpret_cast<const float2*>(p.partial + (long long)b * p.tiles_per_img * 32 + g * 2);
+    int t = j;
+    for (; t + 7 * 16 < p.tiles_per_img; t += 8 * 16) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = pp[(t + k * 16) * 16];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s1 += (double)v[k].x;
+        s2 += (double)v[k].y;
+      }
+    }
+    for (; t < p.tiles_per_img; t += 16) {
+      const float2 v = pp[t * 16];
+      s1 += (double)v.x;
+      s2 += (double)v.y;
     }
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) {
@@ -150,29 +171,34 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
 
   if (p.resample == 0) {
     for (int i = ps; i < p.pix_per_cta; i += 32) {
-      const long long pix = in_img + pix0 + i;
+      const int ip = pix0 + i;
+      const long long pix = in_img + ip;
       const float4* xp = reinterpret_cast<const float4*>(p.x + pix * 64 + c8 * 8);
       const float4 lo = xp[0], hi = xp[1];
       if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo, hi);
-      out[pix * 8 + c8] = pack8(gn_act4(lo, a_lo, b_lo, p.act), gn_act4(hi, a_hi, b_hi, p.act));
+      long long opix = pix;
+      if (p.out_pitch > 0) {
+        const int y = ip / p.Win;
+        opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
+      }
+      out[opix * 8 + c8] = pack8(gn_act4(lo, a_lo, b_lo, p.act), gn_act4(hi, a_hi, b_hi, p.act));
     }
   } else if (p.resample == 1) {
-    const int Wo = p.Win * 2;
-    const long long out_img = (long long)b * p.Hin * p.Win * 4;
+    const int Wo = p.Win * 2, Ho = p.Hin * 2;
+    const long long rstride = p.out_pitch > 0 ? p.out_pitch : Wo;
     for (int i = ps; i < p.pix_per_cta; i += 32) {
       const int ip = pix0 + i;
       const int y = ip / p.Win, x = ip - y * p.Win;
       const float4* xp = reinterpret_cast<const float4*>(p.x + (in_img + ip) * 64 + c8 * 8);
       const uint4 v = pack8(gn_act4(xp[0], a_lo, b_lo, p.act), gn_act4(xp[1], a_hi, b_hi, p.act));
-      const long long o00 = out_img + (long long)(2 * y) * Wo + 2 * x;
+      const long long o00 = gn_out_index(p, b, 2 * y, 2 * x, Ho, Wo);
       out[o00 * 8 + c8] = v;
       out[(o00 + 1) * 8 + c8] = v;
-      out[(o00 + Wo) * 8 + c8] = v;
-      out[(o00 + Wo + 1) * 8 + c8] = v;
+      out[(o00 + rstride) * 8 + c8] = v;
+      out[(o00 + rstride + 1) * 8 + c8] = v;
     }
   } else {
     const int Wo = p.Win >> 1, Ho = p.Hin >> 1;
-    const long long out_img = (long long)b * Ho * Wo;
     for (int i = ps; i < p.pix_per_cta; i += 32) {
       const int op = pix0 + i;
       const int y = op / Wo, x = op - y * Wo;
@@ -187,7 +213,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       }
       lo.x *= 0.25f; lo.y *= 0.25f; lo.z *= 0.25f; lo.w *= 0.25f;
       hi.x *= 0.25f; hi.y *= 0.25f; hi.z *= 0.25f; hi.w *= 0.25f;
-      out[(out_img + op) * 8 + c8] = pack8(lo, hi);
+      out[gn_out_index(p, b, y, x, Ho, Wo) * 8 + c8] = pack8(lo, hi);
     }
   }
 }
@@ -204,8 +230,8 @@ extern "C" int mcedm_gn_stats(const float* x, long long n_pixels, float* partial
 
 extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
                               const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
-                              int act, int resample, int B, int Hin, int Win, void* out_bf16, void* out_raw_bf16,
-                              void* stream) {
+                              int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
+                              int out_blk, void* out_bf16, void* out_raw_bf16, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply: Hin*Win=%d must be a multiple of 128", Hin * Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: resample=%d", resample);
@@ -214,7 +240,7 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   GnApplyParams p;
   p.x = x;
   p.partial = partial;
-  p.tiles_per_img = Hin * Win / 128;
+  p.tiles_per_img = parts_per_img > 0 ? parts_per_img : Hin * Win / 128;
   p.gamma = gamma;
   p.beta = beta;
   p.scale_shift = scale_shift;
@@ -227,8 +253,13 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   p.Win = Win;
   p.out = out_bf16;
   p.out_raw = out_raw_bf16;
+  p.out_pitch = out_pitch;
+  p.out_blk = out_blk;
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
-  int per = 256;
+  // few, fat CTAs amortise the statistics prologue; keep >= ~4 CTAs per SM when the batch allows it
+  int per = 2048;
+  while (per > 32 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
+  if (per < 32) per = 32;
   while (per > 32 && (work % per) != 0) per >>= 1;
   MCEDM_REQUIRE(work % per == 0, "gn_apply: cannot tile %d pixels", work);
   p.pix_per_cta = per;

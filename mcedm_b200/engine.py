@@ -107,6 +107,8 @@ class UNetEngine:
             aff += 1
         self.n_aff = aff
         self._packed_key = None
+        self.use_rows = True     # row-resident conv kernel (conv_rows.cu) for the 128-pixel-wide level
+        self.use_flat = True     # padded-flat conv kernel (conv_flat.cu) for the narrower levels
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
 
@@ -156,7 +158,7 @@ class UNetEngine:
         # residual-stream tensors are allocated per block output on first use (see _tensor)
         ws["pool"] = {}
         ws["h"] = torch.empty(B * H * W * 64, **f32)            # conv0 output (largest resolution)
-        ws["h_st"] = torch.empty(B * H * W // 128 * 32, **f32)
+        ws["h_st"] = torch.empty(B * (H * W // 128 + H // 4 + 8) * 4 * 32, **f32)
         ws["a"] = [torch.empty(B * H * W * 64, **bf) for _ in range(2)]   # normalised operands (2 sources)
         ws["raw"] = [torch.empty(B * H * W * 64, **bf) for _ in range(2)]  # raw bf16 copies for 1x1 skips
         ws["a1"] = torch.empty(B * H * W * 64, **bf)
@@ -171,10 +173,12 @@ class UNetEngine:
 
     @staticmethod
     def _tensor(ws, name: str, B: int, H: int, W: int, dev):
+        """(fp32 NHWC tensor, GroupNorm partial-sum records) of a named activation; the record buffer holds
+        up to 4 records per 128-pixel tile (the conv_rows format)."""
         t = ws["pool"].get(name)
         if t is None:
             t = (torch.empty(B, H, W, 64, device=dev, dtype=torch.float32),
-                 torch.empty(B * H * W // 128, 16, 2, device=dev, dtype=torch.float32))
+                 torch.empty(B * (H * W // 128 + H // 4 + 8) * 4, 16, 2, device=dev, dtype=torch.float32))
             ws["pool"][name] = t
         return t
 
@@ -185,12 +189,75 @@ class UNetEngine:
             L.int_array([s[2] for s in segs]), len(segs), L.ptr(w), L.ptr(bias), B, H, W, N, L.ptr(out), out_bf16,
             L.ptr(res), res_mode, L.ptr(stats), st), "conv_igemm")
 
-    def _gn_apply(self, x, stats, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out, raw, st, eps=1e-5):
+    def _flat_geom(self, H, W):
+        pitch, blk = C.c_int(0), C.c_int(0)
+        L.check(self.lib.mcedm_flat_geometry(H, W, C.byref(pitch), C.byref(blk)), "flat_geometry")
+        L.LAUNCHES[0] -= 1
+        return pitch.value, blk.value
+
+    def _flat_buffers(self, ws, B, H, W, dev):
+        """Zero-padded flat bf16 operand buffers of one level: (two conv0 sources, conv1 source, pitch, blk).
+        Allocated zeroed once; the kernels only ever write data positions, so the padding stays zero."""
+        key = ("flat", H, W)
+        fb = ws["pool"].get(key)
+        if fb is None:
+            pitch, blk = self._flat_geom(H, W)
+            mk = lambda: torch.zeros(B * blk * 64, device=dev, dtype=torch.bfloat16)  # noqa: E731
+            fb = ([mk(), mk()], mk(), pitch, blk)
+            ws["pool"][key] = fb
+        return fb
+
+    def _conv_flat(self, src, w, bias, B, H, W, out, res, res_mode, stats, st):
+        L.check(self.lib.mcedm_conv_flat(L.ptr(src), L.ptr(w), L.ptr(bias), B, H, W, 64, L.ptr(out), L.ptr(res),
+                                         res_mode, L.ptr(stats), st), "conv_flat")
+
+    def _conv3x3(self, halo, ctr, w, bias, B, H, W, N, out, res, res_mode, stats, st, flat=None):
+        if flat is not None:
+            pitch, blk = flat
+            parts = 4 * (blk // 128)
+            if len(halo) == 2:
+                # split K over the two sources, second pass accumulates in place (see the W == 128 case)
+                self._conv_flat(halo[0], w[:9], None, B, H, W, out, None, 0, None, st)
+                self._conv_flat(halo[1], w[9:18], bias, B, H, W, out, out, 1, stats, st)
+                return parts
+            if ctr:
+                # 3x3 part on the padded operand, then the 1x1 skip projection of the raw (dense) block input
+                self._conv_flat(halo[0], w[:9], bias, B, H, W, out, None, 0, None, st)
+                self._conv(list(ctr), [(i, 0, 0) for i in range(len(ctr))], w[9:], None, B, H, W, N, out, 0, out, 1,
+                           stats, st)
+                return H * W // 128
+            self._conv_flat(halo[0], w, bias, B, H, W, out, res, res_mode, stats, st)
+            return parts
+        """3x3 conv of the concatenated `halo` sources (+ 1x1 of the `ctr` sources) -> fp32 out (+ stats).
+        Returns the number of statistics records per image written to `stats`."""
+        if W == 128 and self.use_rows and res_mode in (0, 1, 2) and N in (16, 64):
+            if len(halo) == 1:
+                L.check(self.lib.mcedm_conv_rows(L.ptr_array(halo), 1, L.ptr_array(ctr) if ctr else None, len(ctr),
+                                                 L.ptr(w), L.ptr(bias), B, H, N, L.ptr(out), 0, L.ptr(res), res_mode,
+                                                 L.ptr(stats), st), "conv_rows")
+                return 4 * H
+            if len(halo) == 2 and not ctr and res_mode == 0:
+                # K = 1152 weights (144 KB) cannot stay resident next to the row ring: split K over the two
+                # sources; the second pass accumulates onto the first pass's fp32 result in place.
+                L.check(self.lib.mcedm_conv_rows(L.ptr_array(halo[:1]), 1, None, 0, L.ptr(w[:9]), None, B, H, N,
+                                                 L.ptr(out), 0, None, 0, None, st), "conv_rows")
+                L.check(self.lib.mcedm_conv_rows(L.ptr_array(halo[1:]), 1, None, 0, L.ptr(w[9:]), L.ptr(bias), B, H, N,
+                                                 L.ptr(out), 0, L.ptr(out), 1, L.ptr(stats), st), "conv_rows")
+                return 4 * H
+        segs = [(i, dy, dx) for i in range(len(halo)) for (dy, dx) in _SEG9]
+        segs += [(len(halo) + i, 0, 0) for i in range(len(ctr))]
+        self._conv(list(halo) + list(ctr), segs, w, bias, B, H, W, N, out, 0, res, res_mode, stats, st)
+        return H * W // 128
+
+    def _gn_apply(self, x, stats, parts, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out, raw, st,
+                  eps=1e-5, flat=None):
+        pitch, blk = flat if flat is not None else (0, 0)
         L.check(self.lib.mcedm_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ss), ss_stride, 64,
-                                        eps, act, resample, B, Hin, Win, L.ptr(out), L.ptr(raw), st), "gn_apply")
+                                        eps, act, resample, B, Hin, Win, parts, pitch, blk, L.ptr(out), L.ptr(raw),
+                                        st), "gn_apply")
 
     def _run_block(self, blk: _Block, inputs, B, H_in, W_in, ws, emb_stride, st, dev):
-        """inputs: list of (fp32 NHWC tensor, stats) at resolution H_in x W_in. Returns (out, stats, H, W)."""
+        """inputs: list of (fp32 NHWC tensor, stats, parts) at H_in x W_in. Returns ((out, stats, parts), H, W)."""
         if blk.up:
             H, W, rs, res_mode = H_in * 2, W_in * 2, 1, 2
         elif blk.down:
@@ -198,35 +265,37 @@ class UNetEngine:
         else:
             H, W, rs, res_mode = H_in, W_in, 0, 1
         eps = blk.mod.norm0.eps
+        flat = None
+        a_bufs, a1_buf = ws["a"], ws["a1"]
+        if self.use_flat and W <= 64:
+            a_bufs, a1_buf, pitch, fblk = self._flat_buffers(ws, B, H, W, dev)
+            flat = (pitch, fblk)
         a_srcs, raw_srcs = [], []
-        for i, (x, x_st) in enumerate(inputs):
+        for i, (x, x_st, x_parts) in enumerate(inputs):
             raw = ws["raw"][i] if blk.skip_conv else None
-            self._gn_apply(x, x_st, blk.g0[64 * i:64 * (i + 1)], blk.be0[64 * i:64 * (i + 1)], None, 0, 1, rs, B,
-                           H_in, W_in, ws["a"][i], raw, st, eps)
-            a_srcs.append(ws["a"][i])
+            self._gn_apply(x, x_st, x_parts, blk.g0[64 * i:64 * (i + 1)], blk.be0[64 * i:64 * (i + 1)], None, 0, 1, rs,
+                           B, H_in, W_in, a_bufs[i], raw, st, eps, flat=flat)
+            a_srcs.append(a_bufs[i])
             if blk.skip_conv:
                 raw_srcs.append(raw)
-        segs0 = [(i, dy, dx) for i in range(len(inputs)) for (dy, dx) in _SEG9]
-        self._conv(a_srcs, segs0, blk.w0, blk.b0, B, H, W, 64, ws["h"], 0, None, 0, ws["h_st"], st)
+        h_parts = self._conv3x3(a_srcs, [], blk.w0, blk.b0, B, H, W, 64, ws["h"], None, 0, ws["h_st"], st, flat=flat)
         ss = ws["ss"][blk.aff_index * self._ss_rows * 128:]
-        self._gn_apply(ws["h"], ws["h_st"], blk.g1, blk.be1, ss, emb_stride, 1, 0, B, H, W, ws["a1"], None, st, eps)
+        self._gn_apply(ws["h"], ws["h_st"], h_parts, blk.g1, blk.be1, ss, emb_stride, 1, 0, B, H, W, a1_buf, None, st,
+                       eps, flat=flat)
         out, out_st = self._tensor(ws, blk.name, B, H, W, dev)
-        segs1 = [(0, dy, dx) for (dy, dx) in _SEG9]
-        srcs1 = [ws["a1"]]
         if blk.skip_conv:
-            segs1 += [(1 + i, 0, 0) for i in range(len(raw_srcs))]
-            srcs1 += raw_srcs
-            self._conv(srcs1, segs1, blk.w1, blk.b1, B, H, W, 64, out, 0, None, 0, out_st, st)
+            parts = self._conv3x3([a1_buf], raw_srcs, blk.w1, blk.b1, B, H, W, 64, out, None, 0, out_st, st, flat=flat)
         else:
-            self._conv(srcs1, segs1, blk.w1, blk.b1, B, H, W, 64, out, 0, inputs[0][0], res_mode, out_st, st)
+            parts = self._conv3x3([a1_buf], [], blk.w1, blk.b1, B, H, W, 64, out, inputs[0][0], res_mode, out_st, st,
+                                  flat=flat)
         if blk.attn:
-            self._gn_apply(out, out_st, blk.g2, blk.be2, None, 0, 0, 0, B, H, W, ws["a1"], None, st, eps)
+            self._gn_apply(out, out_st, parts, blk.g2, blk.be2, None, 0, 0, 0, B, H, W, ws["a1"], None, st, eps)
             self._conv([ws["a1"]], [(0, 0, 0)], blk.wqkv, blk.bqkv, B, H, W, 192, ws["qkv"], 1, None, 0, None, st)
             L.check(self.lib.mcedm_attention(L.ptr(ws["qkv"]), B, H * W, L.ptr(ws["att"]), st), "attention")
             out2, out2_st = self._tensor(ws, blk.name + ".attn", B, H, W, dev)
             self._conv([ws["att"]], [(0, 0, 0)], blk.wproj, blk.bproj, B, H, W, 64, out2, 0, out, 1, out2_st, st)
-            out, out_st = out2, out2_st
-        return out, out_st, H, W
+            out, out_st, parts = out2, out2_st, H * W // 128
+        return (out, out_st, parts), H, W
 
     # ------------------------------------------------------------------ forward
     def _check_inputs(self, x, noise_labels, cond):
@@ -271,21 +340,20 @@ class UNetEngine:
         t0, t0_st = self._tensor(ws, "conv_in", B, H, W, dev)
         L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in),
                                   L.ptr(self.b_in), B, H, W, L.ptr(t0), L.ptr(t0_st), st), "conv_in")
-        cur, cur_st, ch, cw = t0, t0_st, H, W
-        skips = [(t0, t0_st)]
+        cur, ch, cw = (t0, t0_st, H * W // 128), H, W
+        skips = [cur]
         for blk in self.blocks_enc:
-            cur, cur_st, ch, cw = self._run_block(blk, [(cur, cur_st)], B, ch, cw, ws, emb_stride, st, dev)
-            skips.append((cur, cur_st))
+            cur, ch, cw = self._run_block(blk, [cur], B, ch, cw, ws, emb_stride, st, dev)
+            skips.append(cur)
         for blk in self.blocks_dec:
-            inputs = [(cur, cur_st)]
+            inputs = [cur]
             if blk.n_src == 2:
                 inputs.append(skips.pop())
-            cur, cur_st, ch, cw = self._run_block(blk, inputs, B, ch, cw, ws, emb_stride, st, dev)
+            cur, ch, cw = self._run_block(blk, inputs, B, ch, cw, ws, emb_stride, st, dev)
         # out_conv(silu(out_norm(x)))  (adm_blocks.py:403), N padded to 16 for the tensor cores
-        self._gn_apply(cur, cur_st, self.g_out, self.be_out, None, 0, 1, 0, B, H, W, ws["a1"], None, st,
+        self._gn_apply(cur[0], cur[1], cur[2], self.g_out, self.be_out, None, 0, 1, 0, B, H, W, ws["a1"], None, st,
                        u.out_norm.eps)
-        self._conv([ws["a1"]], [(0, dy, dx) for (dy, dx) in _SEG9], self.w_out, self.b_out, B, H, W, 16, ws["o16"], 0,
-                   None, 0, None, st)
+        self._conv3x3([ws["a1"]], [], self.w_out, self.b_out, B, H, W, 16, ws["o16"], None, 0, None, st)
         L.check(lib.mcedm_head_to_nchw(L.ptr(ws["o16"]), 16, u.out_channels, B, H, W, L.ptr(out), st), "head_to_nchw")
         return out
 
@@ -336,24 +404,26 @@ class UNetEngine:
         out = torch.empty(x.shape[0], self.unet.out_channels, x.shape[2], x.shape[3], device=x.device)
         self._launch_all(x, nl, cond, out)
         rec_all = []
-        orig = self._conv
+        orig = self._conv3x3
 
         for _ in range(repeats):
             rec = []
 
-            def timed(srcs, segs, w, bias, B, H, W, N, o, o_bf16, res, res_mode, stats, st):
+            def timed(halo, ctr, w, bias, B, H, W, N, o, res, res_mode, stats, st, flat=None):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_seg = 9 * len(halo) + len(ctr)
                 e0.record()
-                orig(srcs, segs, w, bias, B, H, W, N, o, o_bf16, res, res_mode, stats, st)
+                parts = orig(halo, ctr, w, bias, B, H, W, N, o, res, res_mode, stats, st, flat=flat)
                 e1.record()
-                rec.append(dict(N=N, n_seg=len(segs), pixels=B * H * W, H=H, flops=2.0 * B * H * W * N * 64 * len(segs),
+                rec.append(dict(N=N, n_seg=n_seg, pixels=B * H * W, H=H, flops=2.0 * B * H * W * N * 64 * n_seg,
                                 ev=(e0, e1)))
+                return parts
 
-            self._conv = timed
+            self._conv3x3 = timed
             try:
                 self._launch_all(x, nl, cond, out)
             finally:
-                self._conv = orig
+                del self._conv3x3
             torch.cuda.synchronize()
             rec_all.append(rec)
         res = []

@@ -84,6 +84,81 @@ def test_conv_igemm_matches_fp32_conv(L, dev, B, H, W, n_src, k, N, res_mode, ou
         assert torch.allclose(st[..., 1], (v * v).sum(dim=(1, 3)), rtol=1e-4, atol=1e-3)
 
 
+def _to_flat(x_bhwc, pitch, blk):
+    B, H, W, C = x_bhwc.shape
+    flat = torch.zeros(B * blk, C, device=x_bhwc.device, dtype=x_bhwc.dtype)
+    idx = (torch.arange(B, device=x_bhwc.device)[:, None, None] * blk
+           + (torch.arange(H, device=x_bhwc.device)[None, :, None] + 1) * pitch
+           + torch.arange(W, device=x_bhwc.device)[None, None, :])
+    flat[idx.reshape(-1)] = x_bhwc.reshape(-1, C)
+    return flat
+
+
+@pytest.mark.parametrize("B,H,W,res_mode", [(3, 64, 64, 1), (2, 64, 64, 2), (2, 32, 32, 3), (5, 32, 32, 0),
+                                             (40, 64, 64, 1), (2, 16, 16, 1)])
+def test_conv_flat_and_conv_rows_match_conv_igemm_bitwise(L, dev, B, H, W, res_mode):
+    """The row-resident (W=128) and padded-flat (W<=64) kernels issue the same MMAs in the same order as
+    conv_igemm, so their results must be bit-identical to it (which is itself checked against fp64 above)."""
+    import ctypes as C
+
+    from mcedm_b200.engine import pack_conv3x3
+
+    lib = L.lib()
+    g = torch.Generator().manual_seed(H * 7 + res_mode)
+    N = 64
+
+    def run(Wc, Hc, flat):
+        a = torch.randn(B, Hc, Wc, 64, generator=g).to(dev).to(torch.bfloat16).contiguous()
+        w = pack_conv3x3((torch.randn(N, 64, 3, 3, generator=g) / 24).to(dev))
+        bias = torch.randn(N, generator=g).to(dev)
+        rshape = {0: None, 1: (B, Hc, Wc, N), 2: (B, Hc // 2, Wc // 2, N), 3: (B, 2 * Hc, 2 * Wc, N)}[res_mode]
+        res = torch.randn(*rshape, generator=g).to(dev) if rshape else None
+        segs = [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+        ref = torch.full((B, Hc, Wc, N), float("nan"), device=dev)
+        st_ref = torch.empty(B * Hc * Wc // 128, 16, 2, device=dev)
+        L.check(lib.mcedm_conv_igemm(L.ptr_array([a]), 1, L.int_array([s[0] for s in segs]),
+                                     L.int_array([s[1] for s in segs]), L.int_array([s[2] for s in segs]), 9, L.ptr(w),
+                                     L.ptr(bias), B, Hc, Wc, N, L.ptr(ref), 0, L.ptr(res), res_mode, L.ptr(st_ref),
+                                     L.stream_ptr()))
+        out = torch.full((B, Hc, Wc, N), float("nan"), device=dev)
+        if flat:
+            pitch, blk = C.c_int(0), C.c_int(0)
+            L.check(lib.mcedm_flat_geometry(Hc, Wc, C.byref(pitch), C.byref(blk)))
+            af = _to_flat(a, pitch.value, blk.value)
+            st = torch.zeros(B * blk.value // 128, 4, 16, 2, device=dev)
+            L.check(lib.mcedm_conv_flat(L.ptr(af), L.ptr(w), L.ptr(bias), B, Hc, Wc, N, L.ptr(out), L.ptr(res), res_mode,
+                                        L.ptr(st), L.stream_ptr()), "conv_flat")
+        else:
+            st = torch.zeros(B * Hc, 4, 16, 2, device=dev)
+            L.check(lib.mcedm_conv_rows(L.ptr_array([a]), 1, None, 0, L.ptr(w), L.ptr(bias), B, Hc, N, L.ptr(out), 0,
+                                        L.ptr(res), res_mode, L.ptr(st), L.stream_ptr()), "conv_rows")
+        L.check_watchdog()
+        assert torch.equal(out, ref)
+        tot, tot_ref = st.reshape(B, -1, 16, 2).sum(1), st_ref.reshape(B, -1, 16, 2).sum(1)
+        assert torch.allclose(tot, tot_ref, rtol=1e-5, atol=1e-2)
+
+    run(W, H, flat=True)
+    if res_mode != 3:
+        run(128, H, flat=False)
+
+
+def test_umma_row_shifted_descriptor(L, dev):
+    """Pins the hardware behaviour conv_rows / conv_flat rely on: a SWIZZLE_128B K-major operand addressed
+    through a descriptor whose start is advanced by whole 128-byte rows (base_offset field 0) reads the
+    row-shifted tile; and an MN-major B operand (attention's V) is consumed as stored."""
+    lib = L.lib()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(144, 64, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    bm = torch.randn(64, 64, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    for b_mn in (0, 1):
+        for shift in (0, 1, 2, 7, 9, 16):
+            out = torch.full((128, 64), float("nan"), device=dev)
+            L.check(lib.mcedm_probe_umma(L.ptr(a), 144, L.ptr(bm), shift, 0, b_mn, L.ptr(out), L.stream_ptr()))
+            L.check_watchdog()
+            ref = a[shift:shift + 128].float() @ (bm.float() if b_mn else bm.float().t())
+            assert (out - ref).abs().max().item() < 1e-4
+
+
 # ----------------------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("B,H,W,rs,act,use_ss", [(2, 128, 128, 0, 1, True), (3, 32, 32, 1, 1, False),
                                                  (2, 64, 64, 2, 1, False), (2, 32, 32, 0, 0, False)])
@@ -98,7 +173,7 @@ def test_gn_apply_matches_group_norm(L, dev, B, H, W, rs, act, use_ss):
     Ho, Wo = (2 * H, 2 * W) if rs == 1 else (H // 2, W // 2) if rs == 2 else (H, W)
     out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
     L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64,
-                               1e-5, act, rs, B, H, W, L.ptr(out), None, L.stream_ptr()))
+                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, L.stream_ptr()))
     y = F.group_norm(x.permute(0, 3, 1, 2), 16, gamma, beta, 1e-5)
     if use_ss:
         y = torch.addcmul(ss[:, 64:, None, None], y, ss[:, :64, None, None] + 1)
