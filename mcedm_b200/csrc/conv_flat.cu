@@ -235,7 +235,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int pu = unit ^ (row & 7);
         float4 a = *reinterpret_cast<const float4*>(my_stage + row * 128 + pu * 16);
         if (opix[itr] >= 0) {
-          a.x += bz.x + rr[itr].x; a.y += bz.y + rr[itr].y; a.z += bz.z + rr[itr].z; a.w += bz.w + rr[itr].w;
+          a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
+          a.x += rr[itr].x; a.y += rr[itr].y; a.z += rr[itr].z; a.w += rr[itr].w;
           s1 += (a.x + a.y) + (a.z + a.w);
           s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
           *reinterpret_cast<float4*>(p.out + opix[itr] * N + c0) = a;

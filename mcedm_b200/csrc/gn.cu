@@ -170,18 +170,31 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   uint4* out = reinterpret_cast<uint4*>(p.out);
 
   if (p.resample == 0) {
-    for (int i = ps; i < p.pix_per_cta; i += 32) {
-      const int ip = pix0 + i;
-      const long long pix = in_img + ip;
-      const float4* xp = reinterpret_cast<const float4*>(p.x + pix * 64 + c8 * 8);
-      const float4 lo = xp[0], hi = xp[1];
-      if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo, hi);
-      long long opix = pix;
-      if (p.out_pitch > 0) {
-        const int y = ip / p.Win;
-        opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
+    // 4 pixels (8 x 128-bit loads) in flight per thread before any dependent work
+    for (int i = ps; i < p.pix_per_cta; i += 128) {
+      float4 lo[4], hi[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i + 32 * k < p.pix_per_cta) {
+          const float4* xp = reinterpret_cast<const float4*>(p.x + (in_img + pix0 + i + 32 * k) * 64 + c8 * 8);
+          lo[k] = xp[0];
+          hi[k] = xp[1];
+        }
       }
-      out[opix * 8 + c8] = pack8(gn_act4(lo, a_lo, b_lo, p.act), gn_act4(hi, a_hi, b_hi, p.act));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i + 32 * k < p.pix_per_cta) {
+          const int ip = pix0 + i + 32 * k;
+          const long long pix = in_img + ip;
+          if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo[k], hi[k]);
+          long long opix = pix;
+          if (p.out_pitch > 0) {
+            const int y = ip / p.Win;
+            opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
+          }
+          out[opix * 8 + c8] = pack8(gn_act4(lo[k], a_lo, b_lo, p.act), gn_act4(hi[k], a_hi, b_hi, p.act));
+        }
+      }
     }
   } else if (p.resample == 1) {
     const int Wo = p.Win * 2, Ho = p.Hin * 2;

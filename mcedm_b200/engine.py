@@ -221,11 +221,12 @@ class UNetEngine:
                 self._conv_flat(halo[1], w[9:18], bias, B, H, W, out, out, 1, stats, st)
                 return parts
             if ctr:
-                # 3x3 part on the padded operand, then the 1x1 skip projection of the raw (dense) block input
-                self._conv_flat(halo[0], w[:9], bias, B, H, W, out, None, 0, None, st)
-                self._conv(list(ctr), [(i, 0, 0) for i in range(len(ctr))], w[9:], None, B, H, W, N, out, 0, out, 1,
-                           stats, st)
-                return H * W // 128
+                # 1x1 skip projection of the raw (dense) block input first, then the 3x3 part accumulates onto
+                # it in place (conv_flat prefetches its residual; conv_igemm's residual path is the slow one)
+                self._conv(list(ctr), [(i, 0, 0) for i in range(len(ctr))], w[9:], None, B, H, W, N, out, 0, None, 0,
+                           None, st)
+                self._conv_flat(halo[0], w[:9], bias, B, H, W, out, out, 1, stats, st)
+                return parts
             self._conv_flat(halo[0], w, bias, B, H, W, out, res, res_mode, stats, st)
             return parts
         """3x3 conv of the concatenated `halo` sources (+ 1x1 of the `ctr` sources) -> fp32 out (+ stats).
