@@ -100,7 +100,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform control flow; one elected lane issues the tcgen05 instructions
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B = V, MN-major
       mbar_wait(q_full, 0, err, 0x1200);
@@ -114,13 +115,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
           mbar_wait(&s_empty[sb], (ns & 1u) ^ 1u, err, 0x1300 + sb);
           mbar_wait(&kv_full[s], n & 1u, err, 0x1400 + s);
           tc_fence_after();
-          const uint32_t k_base = smem_u32(kv_smem + s * 2 * kTile);
+          const uint64_t qd = umma_desc_k_sw128(q_base);
+          const uint64_t kd = umma_desc_k_sw128(smem_u32(kv_smem + s * 2 * kTile));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + sb * 128, umma_desc_k_sw128(q_base + k * 32), umma_desc_k_sw128(k_base + k * 32),
-                     idesc_s, (uint32_t)(k != 0));
-          umma_commit(&s_full[sb]);
-          if (pass == 0) umma_commit(&kv_empty[s]);
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + sb * 128, qd + 2 * k, kd + 2 * k, idesc_s, (uint32_t)(k != 0));
+            umma_commit(&s_full[sb]);
+            if (pass == 0) umma_commit(&kv_empty[s]);
+          }
+          __syncwarp();
         }
         if (it >= nblk + 1) {
           const int jp = it - 1 - nblk;                    // P V of the previous pass-2 block
@@ -130,15 +133,19 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
           tc_fence_after();
           const uint32_t p_base = smem_u32(p_smem + pb * 2 * kTile);
           const uint32_t v_base = smem_u32(kv_smem + sp * 2 * kTile + kTile);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            umma_f16(tmem_o, umma_desc_k_sw128(p_base + (kk >> 2) * kTile + (kk & 3) * 32),
-                     umma_desc_mn_sw128(v_base + kk * 2048, 8192), idesc_o, (uint32_t)((jp | kk) != 0));
-          umma_commit(&p_empty[pb]);
-          umma_commit(&kv_empty[sp]);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_f16(tmem_o, umma_desc_k_sw128(p_base + (kk >> 2) * kTile + (kk & 3) * 32),
+                       umma_desc_mn_sw128(v_base + kk * 2048, 8192), idesc_o, (uint32_t)((jp | kk) != 0));
+            umma_commit(&p_empty[pb]);
+            umma_commit(&kv_empty[sp]);
+          }
+          __syncwarp();
         }
       }
-      umma_commit(o_full);
+      if (elect_one()) umma_commit(o_full);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -144,7 +144,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, N);
       mbar_wait(w_full, 0, p.err, 0x3200);
       tc_fence_after();
@@ -163,26 +164,29 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const uint32_t d_tmem = tmem_base + buf * N;
         // window = slots (j % S), +1, +2 (mirrors keep them contiguous); the tile itself is the middle chunk
         const uint32_t centre = ring_base + ((uint32_t)j % (uint32_t)S) * kChunkBytes + 128 * 128;
-        uint32_t first = 1;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const uint32_t a_base = centre + (uint32_t)(((ky - 1) * p.P + (kx - 1)) * 128);
-            const uint64_t ad = flat_desc(a_base), bd = flat_desc(w_base + (ky * 3 + kx) * Cfg::W_SEG_BYTES);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first ? 0u : 1u);
-              first = 0;
+            const uint64_t ad = flat_desc(centre + (uint32_t)(((ky - 1) * p.P + (kx - 1)) * 128));
+            const uint64_t bd = flat_desc(w_base + (ky * 3 + kx) * Cfg::W_SEG_BYTES);
+            if (elect_one()) {
+              umma_f16(d_tmem, ad, bd, idesc, (ky | kx) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
             }
           }
         }
-        umma_commit(&c_empty[(uint32_t)j % (uint32_t)S]);        // chunk j has no further user
-        if (j == n_tiles - 1) {
-          umma_commit(&c_empty[(uint32_t)(j + 1) % (uint32_t)S]);
-          umma_commit(&c_empty[(uint32_t)(j + 2) % (uint32_t)S]);
+        if (elect_one()) {
+          umma_commit(&c_empty[(uint32_t)j % (uint32_t)S]);        // chunk j has no further user
+          if (j == n_tiles - 1) {
+            umma_commit(&c_empty[(uint32_t)(j + 1) % (uint32_t)S]);
+            umma_commit(&c_empty[(uint32_t)(j + 2) % (uint32_t)S]);
+          }
+          umma_commit(&acc_full[buf]);
         }
-        umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
   } else {

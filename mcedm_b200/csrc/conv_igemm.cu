@@ -135,7 +135,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
+    // warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
       mbar_wait(w_full, 0, p.err, 0x200);
       tc_fence_after();
@@ -151,17 +152,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
           const uint32_t ph = (it / (uint32_t)p.n_stages) & 1u;
           mbar_wait(&a_full[stage], ph, p.err, 0x400 + stage);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + stage * kATileBytes);
-          const uint32_t b_base = smem_u32(w_smem + s * Cfg::W_SEG_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row
-            umma_f16(d_tmem, umma_desc_k_sw128(a_base + k * 32), umma_desc_k_sw128(b_base + k * 32), idesc,
-                     (uint32_t)((s | k) != 0));
+          const uint64_t ad = umma_desc_k_sw128(smem_u32(a_smem + stage * kATileBytes));
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(w_smem + s * Cfg::W_SEG_BYTES));
+          if (elect_one()) {
+            // advance 16 bf16 (32 B) along K inside the 128-byte swizzle row: +2 in the (address >> 4) field
+            umma_f16(d_tmem, ad, bd, idesc, s != 0 ? 1u : 0u);
+            umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+            umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            umma_commit(&a_empty[stage]);  // smem stage reusable once these MMAs have read it
           }
-          umma_commit(&a_empty[stage]);  // smem stage reusable once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(&acc_full[buf]);     // accumulator complete
+        if (elect_one()) umma_commit(&acc_full[buf]);     // accumulator complete
+        __syncwarp();
       }
     }
   } else {

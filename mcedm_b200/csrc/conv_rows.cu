@@ -162,7 +162,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one
+    // elected lane issues each tcgen05 instruction.  (Running this under `if (lane == 0)` made ptxas
+    // emit an election loop + R2UR moves per MMA: ~4K issue cycles per tile on one thread, which was
+    // the kernel's bottleneck.)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, N);
       mbar_wait(w_full, 0, p.err, 0x2300);
       tc_fence_after();
@@ -187,7 +191,6 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * N;
-          uint32_t first = 1;
           for (int s = 0; s < p.n_halo; ++s) {
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
@@ -195,14 +198,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
               const uint32_t row_base = h_base + slot * slot_bytes + s * kHaloBytes;
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
-                const uint32_t a_base = row_base + kx * 128;     // (dx + 1) pixel rows into the halo'd row
-                const uint32_t b_base = w_base + (s * 9 + ky * 3 + kx) * Cfg::W_SEG_BYTES;
-#pragma unroll
-                const uint64_t ad = desc_from_lo(a_base), bd = desc_from_lo(b_base);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {   // +32 B along K = +2 in the (address >> 4) field
-                  umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first ? 0u : 1u);
-                  first = 0;
+                // (dx + 1) pixel rows into the halo'd row; +32 B along K = +2 in the (address >> 4) field
+                const uint64_t ad = desc_from_lo(row_base + kx * 128);
+                const uint64_t bd = desc_from_lo(w_base + (s * 9 + ky * 3 + kx) * Cfg::W_SEG_BYTES);
+                const uint32_t acc0 = (s | ky | kx) != 0 ? 1u : 0u;
+                if (elect_one()) {
+                  umma_f16(d_tmem, ad, bd, idesc, acc0);
+                  umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                  umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                  umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
                 }
               }
             }
@@ -212,22 +216,26 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             mbar_wait(&c_full[cs], cph, p.err, 0x2600 + cs);
             tc_fence_after();
             for (int s = 0; s < p.n_ctr; ++s) {
-              const uint32_t a_base = c_base + cs * cslot_bytes + s * kCtrBytes;
-              const uint32_t b_base = w_base + (p.n_halo * 9 + s) * Cfg::W_SEG_BYTES;
-              const uint64_t ad = desc_from_lo(a_base), bd = desc_from_lo(b_base);
+              const uint64_t ad = desc_from_lo(c_base + cs * cslot_bytes + s * kCtrBytes);
+              const uint64_t bd = desc_from_lo(w_base + (p.n_halo * 9 + s) * Cfg::W_SEG_BYTES);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+              }
             }
-            umma_commit(&c_empty[cs]);
+            if (elect_one()) umma_commit(&c_empty[cs]);
             ++cc;
           }
-          // input row (hbase + j) has no further user; the last output row also frees the two rows below it
-          umma_commit(&h_empty[(hbase + j) % (uint32_t)p.n_slots]);
-          if (j == R - 1) {
-            umma_commit(&h_empty[(hbase + j + 1) % (uint32_t)p.n_slots]);
-            umma_commit(&h_empty[(hbase + j + 2) % (uint32_t)p.n_slots]);
+          if (elect_one()) {
+            // input row (hbase + j) has no further user; the last output row also frees the two rows below it
+            umma_commit(&h_empty[(hbase + j) % (uint32_t)p.n_slots]);
+            if (j == R - 1) {
+              umma_commit(&h_empty[(hbase + j + 1) % (uint32_t)p.n_slots]);
+              umma_commit(&h_empty[(hbase + j + 2) % (uint32_t)p.n_slots]);
+            }
+            umma_commit(&acc_full[buf]);
           }
-          umma_commit(&acc_full[buf]);
+          __syncwarp();
         }
         hbase += R + 2;
         r += R;
