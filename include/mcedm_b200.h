@@ -113,11 +113,42 @@ MCEDM_API int mcedm_gn_stats(const float* x, long long n_pixels, float* partial,
  *                mcedm_conv_flat (values from mcedm_flat_geometry at the OUTPUT resolution); only data
  *                positions are written, the padding must have been zeroed once by the owner of the buffer
  *   out_raw_bf16 NULL, or receives bf16(x) in dense NHWC (operand of the block's 1x1 skip projection)
+ *   meanrstd_out NULL, or fp32 [B][16][2] receiving (mean, rstd) per group, saved for mcedm_gn_bwd
  */
 MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int act,
                              int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch, int out_blk,
-                             void* out_bf16, void* out_raw_bf16, void* stream);
+                             void* out_bf16, void* out_raw_bf16, float* meanrstd_out, void* stream);
+
+/*
+ * Backward of mcedm_gn_apply (training; autograd of adm_blocks.py:95, :161, :166).  Three launches: per-CTA partial
+ * sums of (du, du*xh) per channel, a per-sample finalize, and the element pass.
+ *   dy            fp32 NHWC gradient w.r.t. the operand gn_apply wrote (at the conv resolution)
+ *   x, meanrstd   saved forward input and its (mean, rstd) records
+ *   red_partial   scratch fp32 [B][mcedm_gn_bwd_ctas_per_img(Hin,Win,B)][64][2];  coef scratch fp32 [B][64][4]
+ *   dgb_partial   out fp32 [B][64][2]: per-sample (d gamma, d beta) contributions (sum over b = the gradient)
+ *   d_scale_shift NULL or out: d scale at [b*dss_batch_stride + c], d shift at [... + emb_shift_offset + c]
+ *   add0/add1     NULL or fp32 tensors added to dx (residual-path gradients); add0_mode 0 same resolution,
+ *                 1 add0 is at 2x resolution (adjoint of a nearest-x2 skip: sum of 4), 2 add0 is at 1/2 resolution
+ *                 (adjoint of a 2x2-mean skip: 0.25 * nearest)
+ *   dx            NULL or out fp32 NHWC [B,Hin,Win,64]; dx_bf16 NULL or bf16 copy (dense, or padded-flat with
+ *                 out_pitch/out_blk); colsum_partial NULL or out fp32 [B*ctas_per_img][64] column sums of dx
+ */
+MCEDM_API int mcedm_gn_bwd_ctas_per_img(int Hin, int Win, int B);
+MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrstd, const float* gamma,
+                           const float* beta, const float* scale_shift, int emb_batch_stride, int emb_shift_offset,
+                           float eps, int act, int resample, int B, int Hin, int Win, float* red_partial, float* coef,
+                           float* dgb_partial, float* d_scale_shift, int dss_batch_stride, const float* add0,
+                           int add0_mode, const float* add1, float* dx, void* dx_bf16, int out_pitch, int out_blk,
+                           float* colsum_partial, void* stream);
+/* out[j] (+)= scale * sum_r in[r*stride_r + j*stride_j]  (ordered fp64 sum; folds per-CTA / per-sample partials) */
+MCEDM_API int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r, int n_cols, long long stride_j,
+                                float* out, int accumulate, float scale, void* stream);
+/* K6: masked weighted EDM loss and dL/dF (mcedm.py:213-239, :278; losses.py:48-53). NCHW fp32, chw elements per
+ * sample; loss = (1/B) * sum(loss_partial[B][ctas_per_sample]); dF may be NULL (forward value only). */
+MCEDM_API int mcedm_edm_loss(const float* F, const float* x_noise, const float* x, const float* mask,
+                             const float* c_skip, const float* c_out, const float* weight, int B, long long chw,
+                             float* dF, float* loss_partial, int ctas_per_sample, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */

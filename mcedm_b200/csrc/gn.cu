@@ -72,6 +72,7 @@ struct GnApplyParams {
   void* out;                 // bf16 NHWC at the output resolution
   void* out_raw;             // nullptr or bf16 NHWC copy of x itself (same resolution only)
   int pix_per_cta;           // INPUT pixels per CTA for resample 0/1, OUTPUT pixels per CTA for resample 2
+  float* meanrstd_out;       // nullptr or [B][16][2] receiving (mean, rstd) per group (saved for the backward)
   int out_pitch;             // 0: dense NHWC output; > 0: padded flat layout of conv_flat.cu (row pitch)
   int out_blk;               // positions per image block of the padded layout
 };
@@ -157,6 +158,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     }
     sA[c] = a;
     sB[c] = bb;
+  } else if (threadIdx.x < 80 && p.meanrstd_out && blockIdx.x == 0) {
+    const int g = threadIdx.x - 64;
+    *reinterpret_cast<float2*>(p.meanrstd_out + ((long long)b * 16 + g) * 2) = make_float2(sMean[g], sRstd[g]);
   }
   __syncthreads();
   const int c8 = threadIdx.x & 7;          // 8-channel slice
@@ -244,7 +248,7 @@ extern "C" int mcedm_gn_stats(const float* x, long long n_pixels, float* partial
 extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
                               const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
                               int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
-                              int out_blk, void* out_bf16, void* out_raw_bf16, void* stream) {
+                              int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply: Hin*Win=%d must be a multiple of 128", Hin * Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: resample=%d", resample);
@@ -268,6 +272,7 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   p.out_raw = out_raw_bf16;
   p.out_pitch = out_pitch;
   p.out_blk = out_blk;
+  p.meanrstd_out = meanrstd_out;
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
   // few, fat CTAs amortise the statistics prologue; keep >= ~4 CTAs per SM when the batch allows it
   int per = 2048;

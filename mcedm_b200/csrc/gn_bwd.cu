@@ -1,0 +1,411 @@
+// K2-bwd / K6 — backward of the fused GroupNorm + (1+scale)/shift + SiLU + resample pass, and the masked
+// mixed-conditioning EDM loss with its gradient.
+//
+// Forward (gn.cu; models/adm_blocks.py:86-97, :161, :163-166):
+//     xh = (x - mu) * rstd          per (sample, group of 4 channels)
+//     u  = (xh * gamma + beta) * (1 + s) + sh          s, sh = affine(emb) halves (0 when absent)
+//     y  = resample(act(u))         act = SiLU | identity; resample = none | nearest x2 | 2x2 mean
+// Backward, given dy (fp32, at the conv resolution):
+//     du = resample^T(dy) * act'(u)
+//     per (sample, channel):  A1 = sum_hw du,  A2 = sum_hw du * xh          (pass 1: gn_bwd_reduce)
+//     d sh = A1,  d s = gamma*A2 + beta*A1,  d beta = sum_b (1+s) A1,  d gamma = sum_b (1+s) A2
+//     dx = rstd * ( gamma (1+s) du - m1 - xh * m2 ),   m1, m2 = group means of gamma(1+s){A1, A2}
+//                                                                         (finalize + pass 2: gn_bwd_apply)
+// Pass 2 also adds up to two residual-path gradients, writes the fp32 total, a bf16 copy in the conv
+// operand layout (dense NHWC or the padded-flat layout of conv_flat.cu) and per-CTA column sums of the
+// total (= the bias gradient of the convolution that produced x).  All reductions are two-stage and
+// ordered: results are deterministic.  Streaming, HBM-bound kernels (128-bit accesses).
+//
+// Loss (models/mcedm.py:213-239, :278; models/losses.py:48-53):
+//     D = c_skip x_noise + c_out F ;  L = (1/B) sum_b w_b sum (m D - m x)^2 ;  dF = c_out (2/B) w_b m (m D - m x)
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+namespace mcedm {
+
+struct GnBwdParams {
+  const float* dy;           // fp32 NHWC [B, Ho, Wo, 64] gradient w.r.t. the operand written by gn_apply
+  const float* x;            // fp32 NHWC [B, Hin, Win, 64] saved input of the GroupNorm
+  const float* meanrstd;     // forward statistics of x saved by gn_apply: [B][16][2] = (mean, rstd)
+  const float* gamma;
+  const float* beta;
+  const float* scale_shift;  // nullptr or scale at [b*stride + c], shift at [b*stride + off + c]
+  int emb_batch_stride, emb_shift_offset;
+  float eps;
+  int act, resample;
+  int B, Hin, Win;
+  int ctas_per_img, pix_per_cta;   // INPUT pixels per CTA
+  float* red_partial;        // pass 1 out: [B][ctas_per_img][64][2]
+  // ---- pass 2 ----
+  const float* coef;         // [B][64][4] = (k1, rstd*m1, rstd*m2, unused) from gn_bwd_finalize
+  const float* add0;         // nullptr or fp32 [B,Hin,Win,64] added to dx (residual-path gradients)
+  const float* add1;
+  int add0_mode;             // how add0 maps onto x: 0 same res, 1 add0 is at 2x res (sum 2x2), 2 add0 at 1/2 res (0.25 * nearest)
+  float* dx;                 // fp32 NHWC total gradient w.r.t. x (may be nullptr)
+  void* dx_bf16;             // nullptr or bf16 copy (operand layout)
+  int out_pitch, out_blk;    // padded-flat layout parameters of dx_bf16 (0 = dense)
+  float* colsum_partial;     // nullptr or [B*ctas_per_img][64]
+};
+
+__device__ __forceinline__ float silu_grad(float u) {
+  const float sg = 1.0f / (1.0f + __expf(-u));
+  return sg * (1.0f + u * (1.0f - sg));
+}
+
+// mean / rstd of (b, g) as saved by the forward gn_apply (meanrstd[b][16][2])
+__device__ __forceinline__ void gn_load_stats(const GnBwdParams& p, int b, float* sMean, float* sRstd) {
+  if (threadIdx.x < 16) {
+    const float2 v = *reinterpret_cast<const float2*>(p.meanrstd + ((long long)b * 16 + threadIdx.x) * 2);
+    sMean[threadIdx.x] = v.x;
+    sRstd[threadIdx.x] = v.y;
+  }
+}
+
+// resample^T(dy) for 4 channels of input pixel (b, y, x)
+__device__ __forceinline__ float4 gather_dy(const GnBwdParams& p, int b, int y, int x, int c) {
+  if (p.resample == 0) {
+    return *reinterpret_cast<const float4*>(p.dy + (((long long)b * p.Hin + y) * p.Win + x) * 64 + c);
+  } else if (p.resample == 1) {   // forward upsampled: each input pixel fed 4 outputs
+    const int Wo = p.Win * 2;
+    const float* d0 = p.dy + (((long long)b * p.Hin * 2 + 2 * y) * Wo + 2 * x) * 64 + c;
+    const float4 a = *reinterpret_cast<const float4*>(d0), bq = *reinterpret_cast<const float4*>(d0 + 64);
+    const float4 cq = *reinterpret_cast<const float4*>(d0 + (long long)Wo * 64);
+    const float4 dq = *reinterpret_cast<const float4*>(d0 + (long long)Wo * 64 + 64);
+    return make_float4((a.x + bq.x) + (cq.x + dq.x), (a.y + bq.y) + (cq.y + dq.y), (a.z + bq.z) + (cq.z + dq.z),
+                       (a.w + bq.w) + (cq.w + dq.w));
+  } else {                        // forward 2x2 mean: each input pixel fed one output with weight 1/4
+    const float4 a = *reinterpret_cast<const float4*>(
+        p.dy + (((long long)b * (p.Hin >> 1) + (y >> 1)) * (p.Win >> 1) + (x >> 1)) * 64 + c);
+    return make_float4(0.25f * a.x, 0.25f * a.y, 0.25f * a.z, 0.25f * a.w);
+  }
+}
+
+struct ChanCoef {   // per-channel forward coefficients held in registers for 4 channels
+  float4 a, bb, k;  // u = x*a + bb ;  xh = x*rs - mr (rs, mr are per group: same for the 4 channels)
+};
+
+// block = 256 threads: 16 channel-quads x 16 pixel lanes
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p) {
+  __shared__ float sMean[16], sRstd[16];
+  __shared__ float sA[64], sB[64];
+  __shared__ float red[16][64][2];
+  const int b = blockIdx.y;
+  gn_load_stats(p, b, sMean, sRstd);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float a = sRstd[c >> 2] * p.gamma[c];
+    float bb = p.beta[c] - sMean[c >> 2] * a;
+    if (p.scale_shift) {
+      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
+      const float sc = 1.0f + ss[c];
+      a *= sc;
+      bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
+    }
+    sA[c] = a;
+    sB[c] = bb;
+  }
+  __syncthreads();
+  const int cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int c = cq * 4;
+  const float4 a4 = *reinterpret_cast<const float4*>(&sA[c]);
+  const float4 b4 = *reinterpret_cast<const float4*>(&sB[c]);
+  const float rs = sRstd[cq], mr = sMean[cq] * sRstd[cq];
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  const int pix0 = blockIdx.x * p.pix_per_cta;
+  for (int i = pl; i < p.pix_per_cta; i += 16) {
+    const int ip = pix0 + i;
+    const int y = ip / p.Win, x = ip - y * p.Win;
+    const float4 xv = *reinterpret_cast<const float4*>(p.x + (((long long)b * p.Hin + y) * p.Win + x) * 64 + c);
+    float4 d = gather_dy(p, b, y, x, c);
+    if (p.act) {
+      d.x *= silu_grad(fmaf(xv.x, a4.x, b4.x));
+      d.y *= silu_grad(fmaf(xv.y, a4.y, b4.y));
+      d.z *= silu_grad(fmaf(xv.z, a4.z, b4.z));
+      d.w *= silu_grad(fmaf(xv.w, a4.w, b4.w));
+    }
+    s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+    s2.x += d.x * fmaf(xv.x, rs, -mr);
+    s2.y += d.y * fmaf(xv.y, rs, -mr);
+    s2.z += d.z * fmaf(xv.z, rs, -mr);
+    s2.w += d.w * fmaf(xv.w, rs, -mr);
+  }
+  red[pl][c + 0][0] = s1.x; red[pl][c + 0][1] = s2.x;
+  red[pl][c + 1][0] = s1.y; red[pl][c + 1][1] = s2.y;
+  red[pl][c + 2][0] = s1.z; red[pl][c + 2][1] = s2.z;
+  red[pl][c + 3][0] = s1.w; red[pl][c + 3][1] = s2.w;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += red[r][cc][k];
+    p.red_partial[(((long long)b * p.ctas_per_img + blockIdx.x) * 64 + cc) * 2 + k] = t;
+  }
+}
+
+// grid = B, block = 64 (one thread per channel).  Folds the pass-1 partials, writes the pass-2 coefficients and
+// the parameter-gradient contributions of sample b: (d gamma, d beta) rows ([B][64][2], summed over b by
+// mcedm_reduce_rows) and d(scale | shift).
+__global__ void __launch_bounds__(64)
+gn_bwd_finalize_kernel(const float* __restrict__ red_partial, int ctas_per_img, const float* __restrict__ meanrstd,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* __restrict__ scale_shift, int emb_batch_stride, int emb_shift_offset, int Hin,
+                       int Win, float* __restrict__ coef, float* __restrict__ dgb_partial,
+                       float* __restrict__ d_scale_shift, int dss_batch_stride) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  __shared__ float sG1[64], sG2[64];
+  const float rstd = meanrstd[((long long)b * 16 + (c >> 2)) * 2 + 1];
+  const float cnt = 4.0f * (float)Hin * (float)Win;
+  double a1 = 0.0, a2 = 0.0;
+  const float2* rp = reinterpret_cast<const float2*>(red_partial + ((long long)b * ctas_per_img * 64 + c) * 2);
+  int t = 0;
+  for (; t + 8 <= ctas_per_img; t += 8) {
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = rp[(t + k) * 64];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a1 += (double)v[k].x;
+      a2 += (double)v[k].y;
+    }
+  }
+  for (; t < ctas_per_img; ++t) {
+    const float2 v = rp[t * 64];
+    a1 += (double)v.x;
+    a2 += (double)v.y;
+  }
+  float sc = 1.0f;
+  if (scale_shift) sc = 1.0f + scale_shift[(long long)b * emb_batch_stride + c];
+  const float g = gamma[c], be = beta[c];
+  const float A1 = (float)a1, A2 = (float)a2;
+  const float k1 = g * sc;                      // d xh = k1 * du
+  sG1[c] = k1 * A1;
+  sG2[c] = k1 * A2;
+  __syncthreads();
+  const int g0 = c & ~3;
+  const float m1 = ((sG1[g0] + sG1[g0 + 1]) + (sG1[g0 + 2] + sG1[g0 + 3])) / cnt;
+  const float m2 = ((sG2[g0] + sG2[g0 + 1]) + (sG2[g0 + 2] + sG2[g0 + 3])) / cnt;
+  float* co = coef + ((long long)b * 64 + c) * 4;
+  co[0] = rstd * k1;
+  co[1] = rstd * m1;
+  co[2] = rstd * m2;
+  co[3] = 0.f;
+  dgb_partial[((long long)b * 64 + c) * 2 + 0] = sc * A2;     // d gamma contribution of sample b
+  dgb_partial[((long long)b * 64 + c) * 2 + 1] = sc * A1;     // d beta
+  if (d_scale_shift) {
+    d_scale_shift[(long long)b * dss_batch_stride + c] = g * A2 + be * A1;                  // d scale
+    d_scale_shift[(long long)b * dss_batch_stride + emb_shift_offset + c] = A1;             // d shift
+  }
+}
+
+__device__ __forceinline__ float4 gather_add(const float* add, int mode, int b, int y, int x, int H, int W, int c) {
+  if (mode == 0) {
+    return *reinterpret_cast<const float4*>(add + (((long long)b * H + y) * W + x) * 64 + c);
+  } else if (mode == 1) {   // add is at 2x resolution (the block downsampled its skip path): 0.25 * sum of 4... no:
+    // forward skip = 2x2 mean of x  ->  d x = 0.25 * g(y/2, x/2); handled by mode 2. mode 1: forward skip =
+    // nearest-x2 upsample of x -> d x = sum of the 4 outputs
+    const int Wo = W * 2;
+    const float* d0 = add + (((long long)b * H * 2 + 2 * y) * Wo + 2 * x) * 64 + c;
+    const float4 a = *reinterpret_cast<const float4*>(d0), bq = *reinterpret_cast<const float4*>(d0 + 64);
+    const float4 cq = *reinterpret_cast<const float4*>(d0 + (long long)Wo * 64);
+    const float4 dq = *reinterpret_cast<const float4*>(d0 + (long long)Wo * 64 + 64);
+    return make_float4((a.x + bq.x) + (cq.x + dq.x), (a.y + bq.y) + (cq.y + dq.y), (a.z + bq.z) + (cq.z + dq.z),
+                       (a.w + bq.w) + (cq.w + dq.w));
+  } else {
+    const float4 a =
+        *reinterpret_cast<const float4*>(add + (((long long)b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * 64 + c);
+    return make_float4(0.25f * a.x, 0.25f * a.y, 0.25f * a.z, 0.25f * a.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) {
+  __shared__ float sMean[16], sRstd[16];
+  __shared__ float sA[64], sB[64];
+  __shared__ float red[16][64];
+  const int b = blockIdx.y;
+  gn_load_stats(p, b, sMean, sRstd);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float a = sRstd[c >> 2] * p.gamma[c];
+    float bb = p.beta[c] - sMean[c >> 2] * a;
+    if (p.scale_shift) {
+      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
+      const float sc = 1.0f + ss[c];
+      a *= sc;
+      bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
+    }
+    sA[c] = a;
+    sB[c] = bb;
+  }
+  __syncthreads();
+  const int cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
+  const int c = cq * 4;
+  const float4 a4 = *reinterpret_cast<const float4*>(&sA[c]);
+  const float4 b4 = *reinterpret_cast<const float4*>(&sB[c]);
+  const float rs = sRstd[cq], mr = sMean[cq] * sRstd[cq];
+  const float4* cf = reinterpret_cast<const float4*>(p.coef + ((long long)b * 64 + c) * 4);
+  const float4 k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];   // (k1, rm1, rm2, -) per channel
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int pix0 = blockIdx.x * p.pix_per_cta;
+  for (int i = pl; i < p.pix_per_cta; i += 16) {
+    const int ip = pix0 + i;
+    const int y = ip / p.Win, x = ip - y * p.Win;
+    const long long pix = ((long long)b * p.Hin + y) * p.Win + x;
+    const float4 xv = *reinterpret_cast<const float4*>(p.x + pix * 64 + c);
+    float4 d = gather_dy(p, b, y, x, c);
+    if (p.act) {
+      d.x *= silu_grad(fmaf(xv.x, a4.x, b4.x));
+      d.y *= silu_grad(fmaf(xv.y, a4.y, b4.y));
+      d.z *= silu_grad(fmaf(xv.z, a4.z, b4.z));
+      d.w *= silu_grad(fmaf(xv.w, a4.w, b4.w));
+    }
+    float4 o;
+    o.x = k0.x * d.x - k0.y - fmaf(xv.x, rs, -mr) * k0.z;
+    o.y = k1.x * d.y - k1.y - fmaf(xv.y, rs, -mr) * k1.z;
+    o.z = k2.x * d.z - k2.y - fmaf(xv.z, rs, -mr) * k2.z;
+    o.w = k3.x * d.w - k3.y - fmaf(xv.w, rs, -mr) * k3.z;
+    if (p.add0) {
+      const float4 r = gather_add(p.add0, p.add0_mode, b, y, x, p.Hin, p.Win, c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    if (p.add1) {
+      const float4 r = *reinterpret_cast<const float4*>(p.add1 + pix * 64 + c);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+    if (p.dx) *reinterpret_cast<float4*>(p.dx + pix * 64 + c) = o;
+    if (p.dx_bf16) {
+      long long opix = pix;
+      if (p.out_pitch > 0) opix = (long long)b * p.out_blk + (long long)(y + 1) * p.out_pitch + x;
+      uint2 ob;
+      ob.x = pack_bf16x2(o.x, o.y);
+      ob.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dx_bf16) + opix * 64 + c) = ob;
+    }
+  }
+  if (p.colsum_partial) {
+    red[pl][c + 0] = cs.x; red[pl][c + 1] = cs.y; red[pl][c + 2] = cs.z; red[pl][c + 3] = cs.w;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) t += red[r][threadIdx.x];
+      p.colsum_partial[((long long)b * p.ctas_per_img + blockIdx.x) * 64 + threadIdx.x] = t;
+    }
+  }
+}
+
+// out[j] (+)= sum_r in[r*stride_r + j*stride_j + offset], ordered, one thread per j (small reductions of partials)
+__global__ void reduce_rows_kernel(const float* __restrict__ in, int n_rows, long long stride_r, int n_cols,
+                                   long long stride_j, float* __restrict__ out, int accumulate, float scale) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cols) return;
+  double t = 0.0;
+  for (int r = 0; r < n_rows; ++r) t += (double)in[r * stride_r + j * stride_j];
+  const float v = (float)t * scale;
+  out[j] = accumulate ? out[j] + v : v;
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// grid = (ctas_per_sample, B); NCHW fp32 tensors with chw elements per sample
+__global__ void __launch_bounds__(256)
+edm_loss_kernel(const float* __restrict__ F, const float* __restrict__ x_noise, const float* __restrict__ x,
+                const float* __restrict__ mask, const float* __restrict__ c_skip, const float* __restrict__ c_out,
+                const float* __restrict__ weight, long long chw, int B, float* __restrict__ dF,
+                float* __restrict__ loss_partial) {
+  const int b = blockIdx.y;
+  const float cs = c_skip[b], co = c_out[b], w = weight[b];
+  const float gscale = 2.0f * w / (float)B;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < chw; i += (long long)gridDim.x * 256) {
+    const long long k = (long long)b * chw + i;
+    const float m = mask ? mask[k] : 1.0f;
+    const float D = __fadd_rn(__fmul_rn(cs, x_noise[k]), __fmul_rn(co, F[k]));
+    const float diff = __fsub_rn(__fmul_rn(D, m), __fmul_rn(x[k], m));
+    acc += w * diff * diff;
+    if (dF) dF[k] = co * gscale * m * diff;
+  }
+  __shared__ float sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_partial[(long long)b * gridDim.x + blockIdx.x] = sm[0];
+}
+
+static int pick_pix_per_cta(int work, int B) {
+  int per = 2048;
+  while (per > 16 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
+  if (per < 16) per = 16;
+  while (per > 16 && (work % per) != 0) per >>= 1;
+  return per;
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_gn_bwd_ctas_per_img(int Hin, int Win, int B) {
+  const int work = Hin * Win;
+  return work / mcedm::pick_pix_per_cta(work, B);
+}
+
+extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrstd, const float* gamma, const float* beta, const float* scale_shift, int emb_batch_stride,
+                            int emb_shift_offset, float eps, int act, int resample, int B, int Hin, int Win,
+                            float* red_partial, float* coef, float* dgb_partial, float* d_scale_shift,
+                            int dss_batch_stride, const float* add0, int add0_mode, const float* add1, float* dx,
+                            void* dx_bf16, int out_pitch, int out_blk, float* colsum_partial, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 16 == 0, "gn_bwd: bad shape");
+  MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_bwd: resample=%d", resample);
+  GnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.dy = dy; p.x = x; p.meanrstd = meanrstd;
+  p.gamma = gamma; p.beta = beta; p.scale_shift = scale_shift;
+  p.emb_batch_stride = emb_batch_stride; p.emb_shift_offset = emb_shift_offset;
+  p.eps = eps; p.act = act; p.resample = resample;
+  p.B = B; p.Hin = Hin; p.Win = Win;
+  const int work = Hin * Win;
+  p.pix_per_cta = pick_pix_per_cta(work, B);
+  p.ctas_per_img = work / p.pix_per_cta;
+  p.red_partial = red_partial;
+  p.coef = coef;
+  p.add0 = add0; p.add0_mode = add0_mode; p.add1 = add1;
+  p.dx = dx; p.dx_bf16 = dx_bf16; p.out_pitch = out_pitch; p.out_blk = out_blk;
+  p.colsum_partial = colsum_partial;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(p.ctas_per_img, B);
+  gn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
+  gn_bwd_finalize_kernel<<<B, 64, 0, st>>>(red_partial, p.ctas_per_img, meanrstd, gamma, beta, scale_shift,
+                                            emb_batch_stride, emb_shift_offset, Hin, Win, coef, dgb_partial,
+                                            d_scale_shift, dss_batch_stride);
+  MCEDM_CUDA(cudaGetLastError());
+  gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r, int n_cols, long long stride_j,
+                                 float* out, int accumulate, float scale, void* stream) {
+  using namespace mcedm;
+  reduce_rows_kernel<<<(n_cols + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, n_rows, stride_r, n_cols, stride_j, out, accumulate, scale);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_loss(const float* F, const float* x_noise, const float* x, const float* mask,
+                              const float* c_skip, const float* c_out, const float* weight, int B, long long chw,
+                              float* dF, float* loss_partial, int ctas_per_sample, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && ctas_per_sample >= 1, "edm_loss: bad sizes");
+  dim3 grid(ctas_per_sample, B);
+  edm_loss_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(F, x_noise, x, mask, c_skip, c_out, weight,
+                                                                            chw, B, dF, loss_partial);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}

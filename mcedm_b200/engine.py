@@ -251,11 +251,11 @@ class UNetEngine:
         return H * W // 128
 
     def _gn_apply(self, x, stats, parts, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out, raw, st,
-                  eps=1e-5, flat=None):
+                  eps=1e-5, flat=None, meanrstd=None):
         pitch, blk = flat if flat is not None else (0, 0)
         L.check(self.lib.mcedm_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ss), ss_stride, 64,
                                         eps, act, resample, B, Hin, Win, parts, pitch, blk, L.ptr(out), L.ptr(raw),
-                                        st), "gn_apply")
+                                        L.ptr(meanrstd), st), "gn_apply")
 
     def _run_block(self, blk: _Block, inputs, B, H_in, W_in, ws, emb_stride, st, dev):
         """inputs: list of (fp32 NHWC tensor, stats, parts) at H_in x W_in. Returns ((out, stats, parts), H, W)."""
