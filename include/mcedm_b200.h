@@ -151,6 +151,25 @@ MCEDM_API int mcedm_edm_loss(const float* F, const float* x_noise, const float* 
                              float* dF, float* loss_partial, int ctas_per_sample, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* K1w  convolution weight gradient on tcgen05 (autograd of models/adm_blocks.py:65-81)           */
+/* -------------------------------------------------------------------------------------------- */
+/*
+ * partial[cta][tap][co][ci] = sum over the CTA's image rows of dy[b,y,x,co] * a[b,y+ky-1,x+kx-1,ci]
+ *   dy, a      bf16 pixel tensors, each a 64-channel block (c_off) of a tensor with c_total channels, in
+ *              layout 0 (dense NHWC [B,H,W,c_total]) or 1 (padded-flat of mcedm_flat_geometry, W <= 64)
+ *   taps       9 (3x3, tap = ky*3+kx) or 1 (1x1 convolutions: qkv, proj, skip)
+ *   partial    fp32 [mcedm_wgrad_ctas(B,H,W)][taps][64][64]
+ * mcedm_wgrad_reduce folds the partials in a fixed order (fp64) into the reference weight layout:
+ *   dw[(co*co_mul + co_add)][ci_off + ci][tap] (+)= sum_cta partial[cta][tap][co][ci],  dw = [Cout][cin_total][k][k]
+ * W % 16 == 0, 16 <= W <= 128.
+ */
+MCEDM_API int mcedm_wgrad_ctas(int B, int H, int W);
+MCEDM_API int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
+                               int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, void* stream);
+MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
+                                 int co_mul, int co_add, int accumulate, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */
 /* -------------------------------------------------------------------------------------------- */
 /* qkv bf16 [B,L,192] = (q|k|v) x 64 channels; out bf16 [B,L,64]; softmax(q.k/8) in fp32. L % 128 == 0. */

@@ -31,6 +31,9 @@ _PROTOTYPES = {
                      _vp, _vp, _i, _i, _vp, _vp],
     "mcedm_reduce_rows": [_vp, _i, C.c_longlong, _i, C.c_longlong, _vp, _i, _f, _vp],
     "mcedm_edm_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, _i, _vp],
+    "mcedm_wgrad_ctas": [_i, _i, _i],
+    "mcedm_conv_wgrad": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "mcedm_flat_geometry": [_i, _i, _ip, _ip],
     "mcedm_conv_flat": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
     "mcedm_attention": [_vp, _i, _i, _vp, _vp],

@@ -1,0 +1,332 @@
+// K1w — weight gradient of the 3x3 / 1x1 convolutions on tcgen05 (training backward of
+// models/adm_blocks.py:65-81 Conv2d.forward as autograd differentiates it):
+//
+//     dW[co][ci][ky][kx] = sum_{b,y,x} dy[b,y,x,co] * a[b, y+ky-1, x+kx-1, ci]          (a zero outside the image)
+//
+// i.e. a [64 x 64] GEMM per filter tap whose contraction index is the PIXEL.  In NHWC both operands have
+// the channel contiguous and the pixel strided, so both are MN-major UMMA operands: one pixel = one
+// 128-byte shared-memory row, a K=16 MMA step = 16 consecutive pixels of one image row.
+//
+//   * B operand  = a   : image row y' as one TMA box (64 ch, W+2 px from x=-1): the kx shift is a UMMA
+//                        descriptor start address advanced by kx*128 B (SWIZZLE_128B is a function of the
+//                        absolute shared-memory address, same trick as conv_rows.cu), zero columns come
+//                        from TMA out-of-bounds fill (dense layout) or stored zeros (padded-flat layout);
+//   * A operand  = dy  : the ky shift is moved onto dy:  dW[ky] = sum_{y'} dy[y'-(ky-1)]^T a[y'].  dy rows
+//                        live in a ring of image-row slots with two mirror slots (rows y'-1, y', y'+1 are
+//                        always contiguous), so TWO taps are stacked into one M=128 MMA: the two
+//                        64-channel M atoms are one slot (= LBO) apart.  Pair A = (ky=1 | ky=0) starts at
+//                        row y', pair B = (ky=2 | duplicate) starts at row y'-1.
+//   * 6 accumulators (pair x kx) of [128 x 64] fp32 stay in TMEM for the CTA's whole row range; one
+//     epilogue at the end writes the CTA's partial dW, folded in fixed order by wgrad_reduce_kernel
+//     (deterministic, no atomics).
+//
+// Layout codes for dy / a:  0 = dense NHWC [B,H,W,C];  1 = the padded-flat layout of conv_flat.cu
+// (position(b,y,x) = b*blk + (y+1)*pitch + x, padding zeroed once by the buffer's owner).
+#include "ptx.cuh"
+#include "runtime.cuh"
+#include "../../include/mcedm_b200.h"
+
+#include <cuda_bf16.h>
+
+namespace mcedm {
+
+struct WgradParams {
+  int H, W;
+  long long total_rows;    // B * H
+  int taps;                // 9 or 1
+  int dy_row_off, a_row_off;   // stored row = image row + off (1 for the padded-flat layout)
+  int dy_coff, a_coff;     // first channel of the 64-channel block inside the tensor
+  int n_slots;             // dy ring depth S (physical S + 2)
+  int n_aslots;
+  int dy_slot_bytes;       // W * 128
+  int a_slot_bytes;        // (W + 2) * 128 rounded up to 1024
+  float* partial;          // [gridDim.x][taps][64][64]
+  unsigned int* err;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_a,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.n_slots, SA = p.n_aslots;
+  uint8_t* dy_smem = smem;                                           // (S + 2) slots
+  uint8_t* a_smem = dy_smem + (S + 2) * p.dy_slot_bytes;             // SA slots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + SA * p.a_slot_bytes);
+  uint64_t* acc_full = bars;
+  uint64_t* dy_full = bars + 1;
+  uint64_t* dy_empty = dy_full + S;
+  uint64_t* a_full = dy_empty + S;
+  uint64_t* a_empty = a_full + SA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + SA);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r_begin = p.total_rows * blockIdx.x / gridDim.x;
+  const long long r_end = p.total_rows * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_dy);
+    prefetch_tmap(&tm_a);
+    mbar_init(acc_full, 1);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&dy_full[i], 1);
+      mbar_init(&dy_empty[i], 1);
+    }
+    for (int i = 0; i < SA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t hl = 0, al = 0;
+      long long r = r_begin;
+      while (r < r_end) {
+        const int b = (int)(r / p.H);
+        const int y0 = (int)(r - (long long)b * p.H);
+        const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+        for (int k = 0; k < R + 2; ++k) {
+          // dy row y0 - 1 + k (rows -1 and H are zero: out-of-bounds fill or stored padding)
+          const uint32_t slot = hl % (uint32_t)S, ph = (hl / (uint32_t)S) & 1u;
+          mbar_wait(&dy_empty[slot], ph ^ 1u, p.err, 0x4100 + slot);
+          const bool mirror = slot < 2 && hl >= (uint32_t)S;
+          mbar_expect_tx(&dy_full[slot], (uint32_t)(mirror ? 2 * p.dy_slot_bytes : p.dy_slot_bytes));
+          tma_load_4d(dy_smem + slot * p.dy_slot_bytes, &tm_dy, &dy_full[slot], p.dy_coff, 0,
+                      y0 - 1 + k + p.dy_row_off, b);
+          if (mirror)
+            tma_load_4d(dy_smem + (S + slot) * p.dy_slot_bytes, &tm_dy, &dy_full[slot], p.dy_coff, 0,
+                        y0 - 1 + k + p.dy_row_off, b);
+          ++hl;
+          if (k >= 2) {
+            // a row y0 + k - 2 with a one-pixel halo on both sides
+            const uint32_t as = al % (uint32_t)SA, aph = (al / (uint32_t)SA) & 1u;
+            mbar_wait(&a_empty[as], aph ^ 1u, p.err, 0x4200 + as);
+            mbar_expect_tx(&a_full[as], (uint32_t)((p.W + 2) * 128));
+            tma_load_4d(a_smem + as * p.a_slot_bytes, &tm_a, &a_full[as], p.a_coff, -1, y0 + k - 2 + p.a_row_off, b);
+            ++al;
+          }
+        }
+        r += R;
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);    // A and B both MN-major
+    const uint32_t dy_base = smem_u32(dy_smem);
+    const uint32_t a_base = smem_u32(a_smem);
+    const uint32_t lbo = (uint32_t)p.dy_slot_bytes;
+    const int kblocks = p.W >> 4;
+    uint32_t hbase = 0, waited = 0, ac = 0;
+    uint32_t first = 1;
+    long long r = r_begin;
+    while (r < r_end) {
+      const int b = (int)(r / p.H);
+      const int y0 = (int)(r - (long long)b * p.H);
+      const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+      for (int j = 0; j < R; ++j) {
+        while (waited < hbase + j + 3) {
+          const uint32_t slot = waited % (uint32_t)S, ph = (waited / (uint32_t)S) & 1u;
+          mbar_wait(&dy_full[slot], ph, p.err, 0x4300 + slot);
+          ++waited;
+        }
+        const uint32_t as = ac % (uint32_t)SA, aph = (ac / (uint32_t)SA) & 1u;
+        mbar_wait(&a_full[as], aph, p.err, 0x4400 + as);
+        tc_fence_after();
+        // window slots w, w+1, w+2 hold dy rows y'-1, y', y'+1 (mirrors keep them contiguous)
+        const uint32_t w0 = dy_base + ((hbase + j) % (uint32_t)S) * lbo;
+        const uint32_t arow = a_base + as * (uint32_t)p.a_slot_bytes;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const uint64_t adA = umma_desc_mn_sw128(w0 + lbo + kb * 2048, lbo);    // (ky=1 | ky=0)
+          const uint64_t adB = umma_desc_mn_sw128(w0 + kb * 2048, lbo);          // (ky=2 | duplicate)
+          const uint32_t acc = first ? 0u : 1u;
+          if (p.taps == 9) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t bd = umma_desc_mn_sw128(arow + (kb * 16 + kx) * 128, 8192);
+              if (elect_one()) {
+                umma_f16(tmem_base + kx * 64, adA, bd, idesc, acc);
+                umma_f16(tmem_base + (3 + kx) * 64, adB, bd, idesc, acc);
+              }
+            }
+          } else {
+            const uint64_t bd = umma_desc_mn_sw128(arow + (kb * 16 + 1) * 128, 8192);
+            if (elect_one()) umma_f16(tmem_base + 64, adA, bd, idesc, acc);
+          }
+          first = 0;
+        }
+        if (elect_one()) {
+          umma_commit(&a_empty[as]);
+          umma_commit(&dy_empty[(hbase + j) % (uint32_t)S]);
+          if (j == R - 1) {
+            umma_commit(&dy_empty[(hbase + j + 1) % (uint32_t)S]);
+            umma_commit(&dy_empty[(hbase + j + 2) % (uint32_t)S]);
+          }
+        }
+        __syncwarp();
+        ++ac;
+      }
+      hbase += R + 2;
+      r += R;
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;            // accumulator row: co = m & 63, upper half = second tap of the pair
+    const int co = m & 63;
+    mbar_wait(acc_full, 0, p.err, 0x4500);
+    tc_fence_after();
+    float* base = p.partial + (long long)blockIdx.x * p.taps * 4096;
+    const bool has_work = r_end > r_begin;
+    for (int i = 0; i < 6; ++i) {
+      const int pair = i / 3, kx = i - pair * 3;
+      int tap;
+      if (p.taps == 9) {
+        const int ky = (pair == 0) ? (m < 64 ? 1 : 0) : (m < 64 ? 2 : -1);
+        tap = ky < 0 ? -1 : ky * 3 + kx;
+      } else {
+        tap = (i == 1 && m < 64) ? 0 : -1;
+      }
+      if (p.taps == 1 && i != 1) continue;       // warp-uniform
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + i * 64 + c * 32, v);
+        tmem_wait_ld();
+        if (tap >= 0) {
+          float4* dst = reinterpret_cast<float4*>(base + ((long long)tap * 64 + co) * 64 + c * 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 o;
+            o.x = has_work ? __uint_as_float(v[4 * u + 0]) : 0.f;
+            o.y = has_work ? __uint_as_float(v[4 * u + 1]) : 0.f;
+            o.z = has_work ? __uint_as_float(v[4 * u + 2]) : 0.f;
+            o.w = has_work ? __uint_as_float(v[4 * u + 3]) : 0.f;
+            dst[u] = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw[(co*co_mul + co_add)][ci_off + ci][tap] (+)= sum_cta partial[cta][tap][co][ci]   (fp64 ordered sum)
+// dw is the reference weight layout [Cout][cin_total][k][k] flattened, k*k = taps.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int taps, float* __restrict__ dw, int cin_total,
+                    int ci_off, int co_mul, int co_add, int accumulate) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;        // (tap, co, ci), ci fastest
+  if (idx >= taps * 4096) return;
+  const int ci = idx & 63, co = (idx >> 6) & 63, tap = idx >> 12;
+  double t = 0.0;
+  int c = 0;
+  for (; c + 4 <= n_ctas; c += 4) {
+    const float v0 = partial[(long long)(c + 0) * taps * 4096 + idx];
+    const float v1 = partial[(long long)(c + 1) * taps * 4096 + idx];
+    const float v2 = partial[(long long)(c + 2) * taps * 4096 + idx];
+    const float v3 = partial[(long long)(c + 3) * taps * 4096 + idx];
+    t += (double)v0;
+    t += (double)v1;
+    t += (double)v2;
+    t += (double)v3;
+  }
+  for (; c < n_ctas; ++c) t += (double)partial[(long long)c * taps * 4096 + idx];
+  float* o = dw + ((long long)(co * co_mul + co_add) * cin_total + ci_off + ci) * taps + tap;
+  *o = accumulate ? *o + (float)t : (float)t;
+}
+
+static int wgrad_grid(int B, int H, int W) {
+  long long g = (long long)B * H * W / 1024;
+  if (g < 1) g = 1;
+  if (g > num_sms()) g = num_sms();
+  if (g > (long long)B * H) g = (long long)B * H;
+  return (int)g;
+}
+
+static int make_pix_tmap(CUtensorMap* tm, const void* ptr, int layout, int c_total, int B, int H, int W, int box_w,
+                         int* row_off) {
+  if (layout == 0) {
+    *row_off = 0;
+    return make_tmap_pix_bf16(tm, ptr, c_total, W, H, B, (long long)H * W, box_w);
+  }
+  int P = 0, blk = 0;
+  int rc = mcedm_flat_geometry(H, W, &P, &blk);
+  if (rc) return rc;
+  *row_off = 1;
+  return make_tmap_pix_bf16(tm, ptr, c_total, P, H + 2, B, blk, box_w);
+}
+
+}  // namespace mcedm
+
+extern "C" int mcedm_wgrad_ctas(int B, int H, int W) { return mcedm::wgrad_grid(B, H, W); }
+
+extern "C" int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
+                                int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial,
+                                void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && H >= 1 && W >= 16 && W <= 128 && W % 16 == 0, "conv_wgrad: unsupported W=%d", W);
+  MCEDM_REQUIRE(taps == 9 || taps == 1, "conv_wgrad: taps=%d (9 or 1)", taps);
+  MCEDM_REQUIRE(dy_ctotal % 64 == 0 && a_ctotal % 64 == 0 && dy_coff % 64 == 0 && a_coff % 64 == 0 &&
+                    dy_coff < dy_ctotal && a_coff < a_ctotal,
+                "conv_wgrad: bad channel block");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = H;
+  p.W = W;
+  p.total_rows = (long long)B * H;
+  p.taps = taps;
+  p.dy_coff = dy_coff;
+  p.a_coff = a_coff;
+  p.dy_slot_bytes = W * 128;
+  p.a_slot_bytes = ((W + 2) * 128 + 1023) / 1024 * 1024;
+  p.n_slots = 4;
+  p.n_aslots = 3;
+  p.partial = partial;
+  p.err = watchdog_ptr();
+  MCEDM_REQUIRE(p.err != nullptr, "conv_wgrad: cannot allocate the watchdog word");
+  CUtensorMap tm_dy, tm_a;
+  int rc = make_pix_tmap(&tm_dy, dy, dy_layout, dy_ctotal, B, H, W, W, &p.dy_row_off);
+  if (rc) return rc;
+  rc = make_pix_tmap(&tm_a, a, a_layout, a_ctotal, B, H, W, W + 2, &p.a_row_off);
+  if (rc) return rc;
+  const int smem = 1024 + (p.n_slots + 2) * p.dy_slot_bytes + p.n_aslots * p.a_slot_bytes + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  const int grid = wgrad_grid(B, H, W);
+  conv_wgrad_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_dy, tm_a, p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
+                                  int co_mul, int co_add, int accumulate, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n_ctas >= 1 && (taps == 9 || taps == 1), "wgrad_reduce: bad sizes");
+  const int n = taps * 4096;
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, n_ctas, taps, dw, cin_total, ci_off, co_mul, co_add, accumulate);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -88,6 +88,23 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W, 
   return 0;
 }
 
+int make_tmap_pix_bf16(CUtensorMap* out, const void* ptr, int c_total, int pitch, int rows, int B,
+                       long long img_stride, int box_w) {
+  EncodeTiledFn fn = encode_fn();
+  MCEDM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  MCEDM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA source must be 16-byte aligned");
+  MCEDM_REQUIRE(c_total % 64 == 0 && box_w >= 1 && box_w <= 256, "bad pixel tensor-map (C=%d box_w=%d)", c_total, box_w);
+  cuuint64_t dims[4] = {(cuuint64_t)c_total, (cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)c_total * 2, (cuuint64_t)pitch * c_total * 2, (cuuint64_t)img_stride * c_total * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MCEDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(pix %dx%dx%dx%d) failed: %d", B, rows, pitch, c_total, (int)r);
+  return 0;
+}
+
 int make_tmap_rows64_bf16(CUtensorMap* out, const void* ptr, long long rows, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   MCEDM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");

@@ -28,6 +28,11 @@ int num_sms();
 // NHWC bf16 activation tensor [B, H, W, C] viewed by TMA as (C, W, H, B), box (64, box_w, box_h, 1),
 // SWIZZLE_128B, zero fill outside the tensor (this is what implements the conv's zero padding).
 int make_tmap_nhwc_bf16(CUtensorMap* out, const void* ptr, int B, int H, int W, int C, int box_w, int box_h);
+// Pixel-sequence view used by the backward kernels: bf16 [B][rows][pitch][c_total] with images img_stride
+// pixels apart (dense NHWC: pitch = W, rows = H, img_stride = H*W; padded-flat: pitch = P, rows = H + 2,
+// img_stride = blk).  TMA dims (c_total, pitch, rows, B), box (64, box_w, 1, 1), SWIZZLE_128B, zero fill.
+int make_tmap_pix_bf16(CUtensorMap* out, const void* ptr, int c_total, int pitch, int rows, int B,
+                       long long img_stride, int box_w);
 // Row-major bf16 matrix [rows, 64] (packed weights), box (64, box_rows), SWIZZLE_128B.
 int make_tmap_rows64_bf16(CUtensorMap* out, const void* ptr, long long rows, int box_rows);
 

@@ -1,0 +1,204 @@
+"""GPU parity tests of the training (backward) kernels, called through the C ABI, against torch autograd in
+fp64/fp32 on the same inputs (run with -m gpu on a B200).
+
+Tolerances: tensor-core kernels take bf16 operands and accumulate in fp32, so weight / data gradients are
+compared against an fp64 reference computed FROM THE SAME bf16-rounded operands (then the only difference is
+accumulation order: 1e-4); element-wise backward kernels (GroupNorm, loss) are fp32: 1e-5 .. 1e-4.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mcedm_b200.utils import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mcedm_b200 import _lib
+
+    _lib.lib()
+    return _lib
+
+
+def flat_geom(L, H, W):
+    pitch, blk = C.c_int(0), C.c_int(0)
+    L.check(L.lib().mcedm_flat_geometry(H, W, C.byref(pitch), C.byref(blk)))
+    return pitch.value, blk.value
+
+
+def to_flat(L, x):
+    """dense bf16 NHWC [B,H,W,C] -> the zero-padded flat layout of conv_flat.cu"""
+    B, H, W, Cc = x.shape
+    P, blk = flat_geom(L, H, W)
+    f = torch.zeros(B, blk, Cc, device=x.device, dtype=x.dtype)
+    f[:, P:P + H * P].view(B, H, P, Cc)[:, :, :W] = x
+    return f.reshape(B * blk, Cc).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- K1w
+@pytest.mark.parametrize("B,H,W,taps,dy_layout,a_layout,ctot", [
+    (2, 128, 128, 9, 0, 0, 64), (3, 64, 64, 9, 1, 1, 64), (5, 32, 32, 9, 1, 1, 64), (2, 16, 16, 9, 1, 1, 64),
+    (40, 128, 128, 9, 0, 0, 64), (3, 32, 32, 1, 0, 0, 192), (2, 64, 64, 1, 1, 0, 64), (2, 128, 128, 1, 0, 0, 64)])
+def test_conv_wgrad_matches_autograd(L, dev, B, H, W, taps, dy_layout, a_layout, ctot):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(B * 100 + H + taps)
+    dy = torch.randn(B, H, W, ctot, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    a = torch.randn(B, H, W, 64, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    coff = ctot - 64
+    dy_buf = to_flat(L, dy) if dy_layout else dy
+    a_buf = to_flat(L, a) if a_layout else a
+    n = lib.mcedm_wgrad_ctas(B, H, W)
+    partial = torch.full((n, taps, 64, 64), float("nan"), device=dev)
+    L.check(lib.mcedm_conv_wgrad(L.ptr(dy_buf), dy_layout, ctot, coff, L.ptr(a_buf), a_layout, 64, 0, B, H, W, taps,
+                                 L.ptr(partial), L.stream_ptr()), "conv_wgrad")
+    L.check_watchdog()
+    k = 3 if taps == 9 else 1
+    dw = torch.full((64, 128, k, k), 7.0, device=dev)
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 128, 64, 1, 0, 0, L.stream_ptr()))
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 128, 0, 1, 0, 1, L.stream_ptr()))
+    w = torch.zeros(64, 64, k, k, device=dev, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(a.double().permute(0, 3, 1, 2), w, padding=k // 2)
+    y.backward(dy[..., coff:].double().permute(0, 3, 1, 2))
+    assert rel_l2(dw[:, 64:], w.grad) < 1e-4
+    assert rel_l2(dw[:, :64] - 7.0, w.grad) < 1e-3
+    # q/k/v row interleave of the qkv projection: co_mul = 3
+    dq = torch.zeros(192, 64, k, k, device=dev)
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dq), 64, 0, 3, 1, 0, L.stream_ptr()))
+    assert rel_l2(dq[1::3], w.grad) < 1e-4 and dq[0::3].abs().max() == 0
+
+
+# ----------------------------------------------------------------------------------------------- dgrad
+def pack_dgrad(w):
+    """[Cout=64, Cin=64, 3, 3] -> packed weights of the data-gradient conv: bf16 [9][ci][co], taps flipped."""
+    return w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 64, 64).to(torch.bfloat16).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 128, 128), (3, 64, 64), (4, 32, 32)])
+def test_conv_dgrad_through_forward_kernels(L, dev, B, H, W):
+    """dx = conv(dy, flipped/transposed weights): the forward kernels ARE the data-gradient kernels."""
+    lib = L.lib()
+    g = torch.Generator().manual_seed(H)
+    dy = torch.randn(B, H, W, 64, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev).to(torch.bfloat16).float()
+    wp = pack_dgrad(w)
+    out = torch.full((B, H, W, 64), float("nan"), device=dev)
+    if W == 128:
+        srcs = (C.c_void_p * 1)(dy.data_ptr())
+        L.check(lib.mcedm_conv_rows(srcs, 1, None, 0, L.ptr(wp), None, B, H, 64, L.ptr(out), 0, None, 0, None,
+                                    L.stream_ptr()), "conv_rows")
+    else:
+        L.check(lib.mcedm_conv_flat(L.ptr(to_flat(L, dy)), L.ptr(wp), None, B, H, W, 64, L.ptr(out), None, 0, None,
+                                    L.stream_ptr()), "conv_flat")
+    L.check_watchdog()
+    a = torch.zeros(B, 64, H, W, device=dev, dtype=torch.float64, requires_grad=True)
+    F.conv2d(a, w.double(), padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    assert rel_l2(out, a.grad.permute(0, 2, 3, 1)) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- K2 bwd
+@pytest.mark.parametrize("B,H,W,rs,act,use_ss,add0_mode,use_add1,flat", [
+    (2, 128, 128, 0, 1, True, None, False, False), (3, 32, 32, 1, 1, False, 0, True, True),
+    (2, 64, 64, 2, 1, False, 1, False, True), (2, 32, 32, 0, 0, False, 0, False, True),
+    (2, 64, 64, 0, 1, True, 2, True, False)])
+def test_gn_bwd_matches_autograd(L, dev, B, H, W, rs, act, use_ss, add0_mode, use_add1, flat):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(H * 7 + rs)
+    x = (torch.randn(B, H, W, 64, generator=g) * 2 + 0.5).to(dev)
+    gamma, beta = torch.randn(64, generator=g).to(dev), torch.randn(64, generator=g).to(dev)
+    ss = (torch.randn(B, 128, generator=g) * 0.3).to(dev)
+    st = torch.empty(B * H * W // 128, 16, 2, device=dev)
+    L.check(lib.mcedm_gn_stats(L.ptr(x), B * H * W, L.ptr(st), L.stream_ptr()))
+    Ho, Wo = (2 * H, 2 * W) if rs == 1 else (H // 2, W // 2) if rs == 2 else (H, W)
+    out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
+    mr = torch.empty(B, 16, 2, device=dev)
+    L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64,
+                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, L.ptr(mr), L.stream_ptr()))
+    dy = torch.randn(B, Ho, Wo, 64, generator=g).to(dev)
+    add0 = None
+    if add0_mode is not None:
+        shp = {0: (B, H, W, 64), 1: (B, 2 * H, 2 * W, 64), 2: (B, H // 2, W // 2, 64)}[add0_mode]
+        add0 = torch.randn(*shp, generator=g).to(dev)
+    add1 = torch.randn(B, H, W, 64, generator=g).to(dev) if use_add1 else None
+    n_cta = lib.mcedm_gn_bwd_ctas_per_img(H, W, B)
+    red = torch.empty(B, n_cta, 64, 2, device=dev)
+    coef = torch.empty(B, 64, 4, device=dev)
+    dgb = torch.empty(B, 64, 2, device=dev)
+    dss = torch.zeros(B, 128, device=dev)
+    dx = torch.empty(B, H, W, 64, device=dev)
+    P, blk = flat_geom(L, H, W) if flat else (0, 0)
+    dxb = torch.zeros(B * blk, 64, device=dev, dtype=torch.bfloat16) if flat else \
+        torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16)
+    cs = torch.empty(B * n_cta, 64, device=dev)
+    L.check(lib.mcedm_gn_bwd(L.ptr(dy), L.ptr(x), L.ptr(mr), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None,
+                             128, 64, 1e-5, act, rs, B, H, W, L.ptr(red), L.ptr(coef), L.ptr(dgb),
+                             L.ptr(dss) if use_ss else None, 128, L.ptr(add0), add0_mode or 0, L.ptr(add1), L.ptr(dx),
+                             L.ptr(dxb), P, blk, L.ptr(cs), L.stream_ptr()), "gn_bwd")
+    # fp64 autograd reference
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    gd, bd, sd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True), ss.double().requires_grad_(True)
+    y = F.group_norm(xd, 16, gd, bd, 1e-5)
+    if use_ss:
+        y = torch.addcmul(sd[:, 64:, None, None], y, sd[:, :64, None, None] + 1)
+    y = F.silu(y) if act else y
+    y = y.repeat_interleave(2, 2).repeat_interleave(2, 3) if rs == 1 else F.avg_pool2d(y, 2) if rs == 2 else y
+    y.backward(dy.double().permute(0, 3, 1, 2))
+    ref = xd.grad.permute(0, 2, 3, 1)
+    if add0 is not None:
+        a0 = add0.double().permute(0, 3, 1, 2)
+        a0 = F.avg_pool2d(a0, 2) * 4 if add0_mode == 1 else \
+            0.25 * a0.repeat_interleave(2, 2).repeat_interleave(2, 3) if add0_mode == 2 else a0
+        ref = ref + a0.permute(0, 2, 3, 1)
+    if add1 is not None:
+        ref = ref + add1.double()
+    assert rel_l2(dx, ref) < 2e-5
+    dense = dxb.view(B, blk, 64)[:, P:P + H * P].reshape(B, H, P, 64)[:, :, :W] if flat else dxb
+    assert rel_l2(dense.float(), ref) < 4e-3
+    if flat:   # the padding of the flat layout must stay zero
+        assert dxb.float().abs().sum().item() == pytest.approx(dense.float().abs().sum().item(), rel=1e-6)
+    assert rel_l2(dgb[:, :, 0].sum(0), gd.grad) < 2e-5 and rel_l2(dgb[:, :, 1].sum(0), bd.grad) < 2e-5
+    if use_ss:
+        assert rel_l2(dss, sd.grad) < 2e-5
+    assert rel_l2(cs.view(B, n_cta, 64).sum((0, 1)), ref.sum((0, 1, 2))) < 1e-4
+
+
+def test_reduce_rows(L, dev):
+    x = torch.randn(37, 5, 64, device=dev)
+    out = torch.ones(64, device=dev)
+    L.check(L.lib().mcedm_reduce_rows(L.ptr(x[:, 2]), 37, 5 * 64, 64, 1, L.ptr(out), 1, 0.5, L.stream_ptr()))
+    assert torch.allclose(out, 1 + 0.5 * x[:, 2].double().sum(0).float(), atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------- K6
+def test_edm_loss_and_gradient(L, dev):
+    from oracle import edm_oracle as O
+
+    B, chw = 5, 2 * 128 * 128
+    g = torch.Generator().manual_seed(3)
+    Fx = torch.randn(B, 2, 128, 128, generator=g).to(dev)
+    x = torch.randn(B, 2, 128, 128, generator=g).to(dev)
+    mask = (torch.rand(B, 2, 128, 128, generator=g) > 0.5).float().to(dev)
+    sigma = (torch.randn(B, 1, 1, 1, generator=g) * 1.2 - 1.2).exp().to(dev)
+    x_noise = x + mask * torch.randn(B, 2, 128, 128, generator=g).to(dev) * sigma
+    c_skip, c_out, _, _ = O.precond_coeffs(sigma)
+    w = O.loss_weight(sigma)
+    Fd = Fx.double().requires_grad_(True)
+    D = c_skip.double() * x_noise.double() + c_out.double() * Fd
+    ref = torch.mean(torch.sum(w.double() * (D * mask - x.double() * mask) ** 2, dim=(1, 2, 3)))
+    ref.backward()
+    n_cta = 8
+    dF = torch.empty_like(Fx)
+    part = torch.empty(B, n_cta, device=dev)
+    L.check(L.lib().mcedm_edm_loss(L.ptr(Fx), L.ptr(x_noise), L.ptr(x), L.ptr(mask), L.ptr(c_skip.reshape(-1).contiguous()),
+                                   L.ptr(c_out.reshape(-1).contiguous()), L.ptr(w.reshape(-1).contiguous()), B, chw,
+                                   L.ptr(dF), L.ptr(part), n_cta, L.stream_ptr()), "edm_loss")
+    assert abs(part.double().sum().item() / B - ref.item()) < 1e-5 * abs(ref.item())
+    assert rel_l2(dF, Fd.grad) < 1e-5
