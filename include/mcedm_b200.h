@@ -172,8 +172,18 @@ MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, flo
 /* -------------------------------------------------------------------------------------------- */
 /* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */
 /* -------------------------------------------------------------------------------------------- */
-/* qkv bf16 [B,L,192] = (q|k|v) x 64 channels; out bf16 [B,L,64]; softmax(q.k/8) in fp32. L % 128 == 0. */
-MCEDM_API int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, void* stream);
+/* qkv bf16 [B,L,192] = (q|k|v) x 64 channels; out bf16 [B,L,64]; softmax(q.k/8) in fp32. L % 128 == 0.
+ * lse_out NULL, or fp32 [B,L] receiving the base-2 log-sum-exp of each row (saved for mcedm_attention_bwd). */
+MCEDM_API int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, void* stream);
+/*
+ * Backward of mcedm_attention (autograd of adm_blocks.py:103-118 AttentionOp + the einsum at :178):
+ *   given d_out bf16 [B,L,64] (gradient w.r.t. out), the saved qkv / out / lse, writes dq, dk, dv bf16 [B,L,64].
+ *   dvec  scratch fp32 [B,L]  (D_i = sum_c d_out[i,c] * out[i,c])
+ * Two tcgen05 kernels (one CTA per 128 queries for dq, one CTA per 128 keys for dk/dv) recompute
+ * P = exp2(S*log2e/8 - lse) tile by tile; the L x L matrices never reach HBM.
+ */
+MCEDM_API int mcedm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
+                                  int B, int L, float* dvec, void* dq_bf16, void* dk_bf16, void* dv_bf16, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* embedding MLP, first conv, output head                                                        */

@@ -36,7 +36,8 @@ _PROTOTYPES = {
     "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "mcedm_flat_geometry": [_i, _i, _ip, _ip],
     "mcedm_conv_flat": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
-    "mcedm_attention": [_vp, _i, _i, _vp, _vp],
+    "mcedm_attention": [_vp, _i, _i, _vp, _vp, _vp],
+    "mcedm_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_attention_ref": [_vp, _i, _i, _vp, _vp],
     "mcedm_emb_mlp": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "mcedm_conv_in": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],

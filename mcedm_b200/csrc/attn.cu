@@ -37,7 +37,8 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(192, 1)
-attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out, unsigned int* err) {
+attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out,
+            float* __restrict__ lse_out, unsigned int* err) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                                  // 16 KB
@@ -215,6 +216,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     mbar_wait(o_full, 0, err, 0x1900);
     tc_fence_after();
     const float inv_l = 1.0f / l;
+    // saved for the backward: P[i][j] = exp2(S[i][j] * c1 - lse2[i])
+    if (lse_out) lse_out[(long long)b * L + q0 + row] = mc + log2f(l);
     __nv_bfloat16* orow = out + ((long long)b * L + q0 + row) * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
@@ -276,7 +279,7 @@ __global__ void attn_ref_kernel(const __nv_bfloat16* __restrict__ qkv, int L, fl
 
 }  // namespace mcedm
 
-extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, void* stream) {
+extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && L >= 128 && L % 128 == 0, "attention: L=%d must be a positive multiple of 128", L);
   CUtensorMap tm;
@@ -291,7 +294,7 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
     attr_set = true;
   }
   attn_kernel<<<B * (L / 128), 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), err);
+      tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, err);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -292,7 +292,7 @@ class UNetEngine:
         if blk.attn:
             self._gn_apply(out, out_st, parts, blk.g2, blk.be2, None, 0, 0, 0, B, H, W, ws["a1"], None, st, eps)
             self._conv([ws["a1"]], [(0, 0, 0)], blk.wqkv, blk.bqkv, B, H, W, 192, ws["qkv"], 1, None, 0, None, st)
-            L.check(self.lib.mcedm_attention(L.ptr(ws["qkv"]), B, H * W, L.ptr(ws["att"]), st), "attention")
+            L.check(self.lib.mcedm_attention(L.ptr(ws["qkv"]), B, H * W, L.ptr(ws["att"]), None, st), "attention")
             out2, out2_st = self._tensor(ws, blk.name + ".attn", B, H, W, dev)
             self._conv([ws["att"]], [(0, 0, 0)], blk.wproj, blk.bproj, B, H, W, 64, out2, 0, out, 1, out2_st, st)
             out, out_st, parts = out2, out2_st, H * W // 128

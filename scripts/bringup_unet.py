@@ -61,7 +61,7 @@ def test_attn():
     for (B, Lq, scale) in [(2, 1024, 1.0), (3, 256, 3.0), (1, 1024, 6.0)]:
         qkv = (torch.randn(B, Lq, 192, generator=g) * scale).to(dev).to(torch.bfloat16)
         out = torch.full((B, Lq, 64), float("nan"), device=dev, dtype=torch.bfloat16)
-        L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), L.stream_ptr()), "attn")
+        L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), None, L.stream_ptr()), "attn")
         try:
             L.check_watchdog()
             wd = ""

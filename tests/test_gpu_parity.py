@@ -189,7 +189,7 @@ def test_attention_matches_fp32_softmax(L, dev, B, Lq, scale):
     g = torch.Generator().manual_seed(Lq)
     qkv = (torch.randn(B, Lq, 192, generator=g) * scale).to(dev).to(torch.bfloat16)
     out = torch.full((B, Lq, 64), float("nan"), device=dev, dtype=torch.bfloat16)
-    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), L.stream_ptr()), "attention")
+    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), None, L.stream_ptr()), "attention")
     L.check_watchdog()
     q, k, v = qkv.double().split(64, dim=2)
     ref = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=2) @ v

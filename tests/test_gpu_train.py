@@ -202,3 +202,30 @@ def test_edm_loss_and_gradient(L, dev):
                                    L.ptr(dF), L.ptr(part), n_cta, L.stream_ptr()), "edm_loss")
     assert abs(part.double().sum().item() / B - ref.item()) < 1e-5 * abs(ref.item())
     assert rel_l2(dF, Fd.grad) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- K3 bwd
+@pytest.mark.parametrize("B,Lq,scale", [(2, 1024, 1.0), (3, 256, 2.0), (1, 1024, 4.0)])
+def test_attention_bwd_matches_autograd(L, dev, B, Lq, scale):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(Lq + 1)
+    qkv = (torch.randn(B, Lq, 192, generator=g) * scale).to(dev).to(torch.bfloat16)
+    d_out = torch.randn(B, Lq, 64, generator=g).to(dev).to(torch.bfloat16)
+    out = torch.empty(B, Lq, 64, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, Lq, device=dev)
+    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), L.ptr(lse), L.stream_ptr()), "attention")
+    dvec = torch.empty(B, Lq, device=dev)
+    dq, dk, dv = (torch.full((B, Lq, 64), float("nan"), device=dev, dtype=torch.bfloat16) for _ in range(3))
+    L.check(lib.mcedm_attention_bwd(L.ptr(qkv), L.ptr(out), L.ptr(d_out), L.ptr(lse), B, Lq, L.ptr(dvec), L.ptr(dq),
+                                    L.ptr(dk), L.ptr(dv), L.stream_ptr()), "attention_bwd")
+    L.check_watchdog()
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.split(64, dim=2)
+    s = q @ k.transpose(1, 2) / 8.0
+    ref = torch.softmax(s, dim=2) @ v
+    ref.backward(d_out.double())
+    assert rel_l2(lse, torch.logsumexp(s, dim=2) * 1.4426950408889634) < 1e-5
+    rq, rk, rv = x.grad.split(64, dim=2)
+    assert rel_l2(dv.float(), rv) < 8e-3        # bf16 P, bf16 output
+    assert rel_l2(dq.float(), rq) < 1.5e-2      # bf16 dS (difference of nearly equal terms), bf16 output
+    assert rel_l2(dk.float(), rk) < 1.5e-2
