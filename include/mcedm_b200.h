@@ -132,7 +132,8 @@ MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* 
  *                 1 add0 is at 2x resolution (adjoint of a nearest-x2 skip: sum of 4), 2 add0 is at 1/2 resolution
  *                 (adjoint of a 2x2-mean skip: 0.25 * nearest)
  *   dx            NULL or out fp32 NHWC [B,Hin,Win,64]; dx_bf16 NULL or bf16 copy (dense, or padded-flat with
- *                 out_pitch/out_blk); colsum_partial NULL or out fp32 [B*ctas_per_img][64] column sums of dx
+ *                 out_pitch/out_blk); dx_bf16_dense NULL or a second, always dense bf16 copy (operand of the 1x1
+ *                 convolutions); colsum_partial NULL or out fp32 [B*ctas_per_img][64] column sums of dx
  */
 MCEDM_API int mcedm_gn_bwd_ctas_per_img(int Hin, int Win, int B);
 MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrstd, const float* gamma,
@@ -140,15 +141,18 @@ MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrst
                            float eps, int act, int resample, int B, int Hin, int Win, float* red_partial, float* coef,
                            float* dgb_partial, float* d_scale_shift, int dss_batch_stride, const float* add0,
                            int add0_mode, const float* add1, float* dx, void* dx_bf16, int out_pitch, int out_blk,
-                           float* colsum_partial, void* stream);
+                           void* dx_bf16_dense, float* colsum_partial, void* stream);
 /* out[j] (+)= scale * sum_r in[r*stride_r + j*stride_j]  (ordered fp64 sum; folds per-CTA / per-sample partials) */
 MCEDM_API int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r, int n_cols, long long stride_j,
                                 float* out, int accumulate, float scale, void* stream);
 /* K6: masked weighted EDM loss and dL/dF (mcedm.py:213-239, :278; losses.py:48-53). NCHW fp32, chw elements per
- * sample; loss = (1/B) * sum(loss_partial[B][ctas_per_sample]); dF may be NULL (forward value only). */
+ * sample; loss = (1/B) * sum(loss_partial[B][ctas_per_sample]); dF may be NULL (forward value only).
+ * dF_pad_bf16 NULL, or bf16 NHWC [B, hw, 64] whose first chw/hw channels receive dL/dF (the other channels must
+ * have been zeroed by the owner): the tensor-core operand of out_conv's weight / data gradient. */
 MCEDM_API int mcedm_edm_loss(const float* F, const float* x_noise, const float* x, const float* mask,
                              const float* c_skip, const float* c_out, const float* weight, int B, long long chw,
-                             float* dF, float* loss_partial, int ctas_per_sample, void* stream);
+                             float* dF, void* dF_pad_bf16, long long hw, float* loss_partial, int ctas_per_sample,
+                             void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K1w  convolution weight gradient on tcgen05 (autograd of models/adm_blocks.py:65-81)           */
@@ -161,13 +165,14 @@ MCEDM_API int mcedm_edm_loss(const float* F, const float* x_noise, const float* 
  *   partial    fp32 [mcedm_wgrad_ctas(B,H,W)][taps][64][64]
  * mcedm_wgrad_reduce folds the partials in a fixed order (fp64) into the reference weight layout:
  *   dw[(co*co_mul + co_add)][ci_off + ci][tap] (+)= sum_cta partial[cta][tap][co][ci],  dw = [Cout][cin_total][k][k]
+ *   for co < co_count, ci < ci_count (out_conv has 2 real output channels, the first conv 4 real inputs)
  * W % 16 == 0, 16 <= W <= 128.
  */
 MCEDM_API int mcedm_wgrad_ctas(int B, int H, int W);
 MCEDM_API int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
                                int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, void* stream);
 MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
-                                 int co_mul, int co_add, int accumulate, void* stream);
+                                 int co_mul, int co_add, int co_count, int ci_count, int accumulate, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */
@@ -227,6 +232,36 @@ MCEDM_API int mcedm_edm_precond_in(const float* x, const float* c_in, int coef_s
 /* D[b] = c_skip[b*stride]*x[b] + c_out[b*stride]*F[b]   (mcedm.py:210, :460); chw = elements per sample */
 MCEDM_API int mcedm_edm_precond_out(const float* x, const float* F, const float* c_skip, const float* c_out,
                                     int coef_stride, int B, long long chw, float* D, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* training-side small kernels (train_small.cu)                                                  */
+/* -------------------------------------------------------------------------------------------- */
+/* x_noise = x + mask*noise*sigma[b] ; x_in = c_in[b]*x_noise   (mcedm.py:216, :208); mask may be NULL */
+MCEDM_API int mcedm_edm_noise_in(const float* x, const float* noise, const float* mask, const float* sigma,
+                                 const float* c_in, int B, long long chw, float* x_noise, float* x_in, void* stream);
+/* channels [c_dst0, c_dst0+Ca+Cb) of a 64-channel bf16 NHWC tensor <- cat(a, b) (NCHW fp32; b may be NULL, Cb = 0) */
+MCEDM_API int mcedm_nchw_to_nhwc_pad(const float* a, int Ca, const float* b, int Cb, int B, int H, int W,
+                                     void* dst_bf16, int c_dst0, void* stream);
+/* partial[cta][64] = column sums over the CTA's pixel range of channels [c_off, c_off+64) of bf16 [pixels, C] */
+MCEDM_API int mcedm_colsum_bf16(const void* x_bf16, long long pixels, int C, int c_off, float* partial, int n_ctas,
+                                void* stream);
+/* backward of mcedm_emb_mlp: dss fp32 [n_aff][B][128] = gradient of every block's (scale | shift);
+ * vec_scratch fp32 [B][320]; outputs in the reference parameter shapes (affine [n_aff][128][64] / [n_aff][128],
+ * map_layer1, map_layer0 [64][64] / [64]) */
+MCEDM_API int mcedm_emb_mlp_bwd(const float* c_noise, const float* freqs, const float* w0, const float* b0,
+                                const float* w1, const float* b1, const float* aff_w, const float* dss, int n_aff, int B,
+                                float* vec_scratch, float* d_aff_w, float* d_aff_b, float* d_w1, float* d_b1,
+                                float* d_w0, float* d_b0, void* stream);
+/* partial[i] = sum of squares of the i-th grid-stride slice of g (fp64); n_partial CTAs */
+MCEDM_API int mcedm_sumsq_partial(const float* g, long long n, double* partial, int n_partial, void* stream);
+/* torch.optim.Adam step on flat fp32 buffers (mcedm.py:141) with gradient-norm clipping folded in
+ * (trainer_ddim.yaml:8-9: coef = min(1, max_norm / (grad_scale*||g|| + 1e-6)); norm_partial NULL = no clipping);
+ * grad_scale multiplies g first (1/world_size after a sum all-reduce); norm_out NULL or receives the norm. */
+MCEDM_API int mcedm_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, const double* norm_partial,
+                              int n_partial, float max_norm, float grad_scale, float* norm_out, void* stream);
+/* ema = ema*beta + (1-beta)*p   (ddim_blocks.py:48-56) */
+MCEDM_API int mcedm_ema_update(float* ema, const float* p, long long n, float beta, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* bring-up / checker kernels (tests only; not on the product path)                              */

@@ -28,12 +28,19 @@ _PROTOTYPES = {
     "mcedm_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mcedm_gn_bwd_ctas_per_img": [_i, _i, _i],
     "mcedm_gn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp,
-                     _vp, _vp, _i, _i, _vp, _vp],
+                     _vp, _vp, _i, _i, _vp, _vp, _vp],
     "mcedm_reduce_rows": [_vp, _i, C.c_longlong, _i, C.c_longlong, _vp, _i, _f, _vp],
-    "mcedm_edm_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, _i, _vp],
+    "mcedm_edm_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _i, _vp],
+    "mcedm_edm_noise_in": [_vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, _vp],
+    "mcedm_nchw_to_nhwc_pad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "mcedm_colsum_bf16": [_vp, C.c_longlong, _i, _i, _vp, _i, _vp],
+    "mcedm_emb_mlp_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mcedm_sumsq_partial": [_vp, C.c_longlong, _vp, _i, _vp],
+    "mcedm_adam_step": [_vp, _vp, _vp, _vp, C.c_longlong, _f, _f, _f, _f, _f, _i, _vp, _i, _f, _f, _vp, _vp],
+    "mcedm_ema_update": [_vp, _vp, C.c_longlong, _f, _vp],
     "mcedm_wgrad_ctas": [_i, _i, _i],
     "mcedm_conv_wgrad": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
-    "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mcedm_flat_geometry": [_i, _i, _ip, _ip],
     "mcedm_conv_flat": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
     "mcedm_attention": [_vp, _i, _i, _vp, _vp, _vp],

@@ -233,10 +233,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
 // dw is the reference weight layout [Cout][cin_total][k][k] flattened, k*k = taps.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int taps, float* __restrict__ dw, int cin_total,
-                    int ci_off, int co_mul, int co_add, int accumulate) {
+                    int ci_off, int co_mul, int co_add, int co_count, int ci_count, int accumulate) {
   const int idx = blockIdx.x * 256 + threadIdx.x;        // (tap, co, ci), ci fastest
   if (idx >= taps * 4096) return;
   const int ci = idx & 63, co = (idx >> 6) & 63, tap = idx >> 12;
+  if (co >= co_count || ci >= ci_count) return;
   double t = 0.0;
   int c = 0;
   for (; c + 4 <= n_ctas; c += 4) {
@@ -321,12 +322,13 @@ extern "C" int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, in
 }
 
 extern "C" int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
-                                  int co_mul, int co_add, int accumulate, void* stream) {
+                                  int co_mul, int co_add, int co_count, int ci_count, int accumulate, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(n_ctas >= 1 && (taps == 9 || taps == 1), "wgrad_reduce: bad sizes");
+  MCEDM_REQUIRE(co_count >= 1 && co_count <= 64 && ci_count >= 1 && ci_count <= 64, "wgrad_reduce: bad channel counts");
   const int n = taps * 4096;
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partial, n_ctas, taps, dw, cin_total, ci_off, co_mul, co_add, accumulate);
+      partial, n_ctas, taps, dw, cin_total, ci_off, co_mul, co_add, co_count, ci_count, accumulate);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

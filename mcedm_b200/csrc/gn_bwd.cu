@@ -45,6 +45,7 @@ struct GnBwdParams {
   float* dx;                 // fp32 NHWC total gradient w.r.t. x (may be nullptr)
   void* dx_bf16;             // nullptr or bf16 copy (operand layout)
   int out_pitch, out_blk;    // padded-flat layout parameters of dx_bf16 (0 = dense)
+  void* dx_bf16_dense;       // nullptr or a second, always dense NHWC bf16 copy (operand of the 1x1 convolutions)
   float* colsum_partial;     // nullptr or [B*ctas_per_img][64]
 };
 
@@ -285,6 +286,12 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) 
       ob.y = pack_bf16x2(o.z, o.w);
       *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dx_bf16) + opix * 64 + c) = ob;
     }
+    if (p.dx_bf16_dense) {
+      uint2 ob;
+      ob.x = pack_bf16x2(o.x, o.y);
+      ob.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.dx_bf16_dense) + pix * 64 + c) = ob;
+    }
   }
   if (p.colsum_partial) {
     red[pl][c + 0] = cs.x; red[pl][c + 1] = cs.y; red[pl][c + 2] = cs.z; red[pl][c + 3] = cs.w;
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(256)
 edm_loss_kernel(const float* __restrict__ F, const float* __restrict__ x_noise, const float* __restrict__ x,
                 const float* __restrict__ mask, const float* __restrict__ c_skip, const float* __restrict__ c_out,
                 const float* __restrict__ weight, long long chw, int B, float* __restrict__ dF,
-                float* __restrict__ loss_partial) {
+                uint16_t* __restrict__ dF_pad, long long hw, float* __restrict__ loss_partial) {
   const int b = blockIdx.y;
   const float cs = c_skip[b], co = c_out[b], w = weight[b];
   const float gscale = 2.0f * w / (float)B;
@@ -326,7 +333,12 @@ edm_loss_kernel(const float* __restrict__ F, const float* __restrict__ x_noise, 
     const float D = __fadd_rn(__fmul_rn(cs, x_noise[k]), __fmul_rn(co, F[k]));
     const float diff = __fsub_rn(__fmul_rn(D, m), __fmul_rn(x[k], m));
     acc += w * diff * diff;
-    if (dF) dF[k] = co * gscale * m * diff;
+    const float gF = co * gscale * m * diff;
+    if (dF) dF[k] = gF;
+    if (dF_pad) {   // channel c of pixel (b, i % hw) in a 64-channel bf16 NHWC tensor
+      const long long c = i / hw;
+      dF_pad[((long long)b * hw + (i - c * hw)) * 64 + c] = (uint16_t)(pack_bf16x2(gF, 0.f) & 0xffffu);
+    }
   }
   __shared__ float sm[256];
   sm[threadIdx.x] = acc;
@@ -357,7 +369,8 @@ extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrs
                             int emb_shift_offset, float eps, int act, int resample, int B, int Hin, int Win,
                             float* red_partial, float* coef, float* dgb_partial, float* d_scale_shift,
                             int dss_batch_stride, const float* add0, int add0_mode, const float* add1, float* dx,
-                            void* dx_bf16, int out_pitch, int out_blk, float* colsum_partial, void* stream) {
+                            void* dx_bf16, int out_pitch, int out_blk, void* dx_bf16_dense, float* colsum_partial,
+                            void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 16 == 0, "gn_bwd: bad shape");
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_bwd: resample=%d", resample);
@@ -375,6 +388,7 @@ extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrs
   p.coef = coef;
   p.add0 = add0; p.add0_mode = add0_mode; p.add1 = add1;
   p.dx = dx; p.dx_bf16 = dx_bf16; p.out_pitch = out_pitch; p.out_blk = out_blk;
+  p.dx_bf16_dense = dx_bf16_dense;
   p.colsum_partial = colsum_partial;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.ctas_per_img, B);
@@ -400,12 +414,16 @@ extern "C" int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r
 
 extern "C" int mcedm_edm_loss(const float* F, const float* x_noise, const float* x, const float* mask,
                               const float* c_skip, const float* c_out, const float* weight, int B, long long chw,
-                              float* dF, float* loss_partial, int ctas_per_sample, void* stream) {
+                              float* dF, void* dF_pad_bf16, long long hw, float* loss_partial, int ctas_per_sample,
+                              void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && ctas_per_sample >= 1, "edm_loss: bad sizes");
+  MCEDM_REQUIRE(dF_pad_bf16 == nullptr || (hw >= 1 && chw % hw == 0 && chw / hw <= 64), "edm_loss: bad padded output");
   dim3 grid(ctas_per_sample, B);
   edm_loss_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(F, x_noise, x, mask, c_skip, c_out, weight,
-                                                                            chw, B, dF, loss_partial);
+                                                                            chw, B, dF,
+                                                                            reinterpret_cast<uint16_t*>(dF_pad_bf16), hw,
+                                                                            loss_partial);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

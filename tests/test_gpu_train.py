@@ -63,8 +63,8 @@ def test_conv_wgrad_matches_autograd(L, dev, B, H, W, taps, dy_layout, a_layout,
     L.check_watchdog()
     k = 3 if taps == 9 else 1
     dw = torch.full((64, 128, k, k), 7.0, device=dev)
-    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 128, 64, 1, 0, 0, L.stream_ptr()))
-    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 128, 0, 1, 0, 1, L.stream_ptr()))
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 128, 64, 1, 0, 64, 64, 0, L.stream_ptr()))
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 128, 0, 1, 0, 64, 64, 1, L.stream_ptr()))
     w = torch.zeros(64, 64, k, k, device=dev, dtype=torch.float64, requires_grad=True)
     y = F.conv2d(a.double().permute(0, 3, 1, 2), w, padding=k // 2)
     y.backward(dy[..., coff:].double().permute(0, 3, 1, 2))
@@ -72,8 +72,12 @@ def test_conv_wgrad_matches_autograd(L, dev, B, H, W, taps, dy_layout, a_layout,
     assert rel_l2(dw[:, :64] - 7.0, w.grad) < 1e-3
     # q/k/v row interleave of the qkv projection: co_mul = 3
     dq = torch.zeros(192, 64, k, k, device=dev)
-    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dq), 64, 0, 3, 1, 0, L.stream_ptr()))
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dq), 64, 0, 3, 1, 64, 64, 0, L.stream_ptr()))
     assert rel_l2(dq[1::3], w.grad) < 1e-4 and dq[0::3].abs().max() == 0
+    # channel-count limits (out_conv: 2 real outputs; first conv: 4 real inputs)
+    dsm = torch.zeros(2, 4, k, k, device=dev)
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dsm), 4, 0, 1, 0, 2, 4, 0, L.stream_ptr()))
+    assert rel_l2(dsm, w.grad[:2, :4]) < 1e-4
 
 
 # ----------------------------------------------------------------------------------------------- dgrad
@@ -138,10 +142,11 @@ def test_gn_bwd_matches_autograd(L, dev, B, H, W, rs, act, use_ss, add0_mode, us
     dxb = torch.zeros(B * blk, 64, device=dev, dtype=torch.bfloat16) if flat else \
         torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16)
     cs = torch.empty(B * n_cta, 64, device=dev)
+    dxd = torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16)
     L.check(lib.mcedm_gn_bwd(L.ptr(dy), L.ptr(x), L.ptr(mr), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None,
                              128, 64, 1e-5, act, rs, B, H, W, L.ptr(red), L.ptr(coef), L.ptr(dgb),
                              L.ptr(dss) if use_ss else None, 128, L.ptr(add0), add0_mode or 0, L.ptr(add1), L.ptr(dx),
-                             L.ptr(dxb), P, blk, L.ptr(cs), L.stream_ptr()), "gn_bwd")
+                             L.ptr(dxb), P, blk, L.ptr(dxd), L.ptr(cs), L.stream_ptr()), "gn_bwd")
     # fp64 autograd reference
     xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
     gd, bd, sd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True), ss.double().requires_grad_(True)
@@ -161,7 +166,7 @@ def test_gn_bwd_matches_autograd(L, dev, B, H, W, rs, act, use_ss, add0_mode, us
         ref = ref + add1.double()
     assert rel_l2(dx, ref) < 2e-5
     dense = dxb.view(B, blk, 64)[:, P:P + H * P].reshape(B, H, P, 64)[:, :, :W] if flat else dxb
-    assert rel_l2(dense.float(), ref) < 4e-3
+    assert rel_l2(dense.float(), ref) < 4e-3 and torch.equal(dense, dxd)
     if flat:   # the padding of the flat layout must stay zero
         assert dxb.float().abs().sum().item() == pytest.approx(dense.float().abs().sum().item(), rel=1e-6)
     assert rel_l2(dgb[:, :, 0].sum(0), gd.grad) < 2e-5 and rel_l2(dgb[:, :, 1].sum(0), bd.grad) < 2e-5
@@ -197,11 +202,13 @@ def test_edm_loss_and_gradient(L, dev):
     n_cta = 8
     dF = torch.empty_like(Fx)
     part = torch.empty(B, n_cta, device=dev)
+    pad = torch.zeros(B, 128, 128, 64, device=dev, dtype=torch.bfloat16)
     L.check(L.lib().mcedm_edm_loss(L.ptr(Fx), L.ptr(x_noise), L.ptr(x), L.ptr(mask), L.ptr(c_skip.reshape(-1).contiguous()),
                                    L.ptr(c_out.reshape(-1).contiguous()), L.ptr(w.reshape(-1).contiguous()), B, chw,
-                                   L.ptr(dF), L.ptr(part), n_cta, L.stream_ptr()), "edm_loss")
+                                   L.ptr(dF), L.ptr(pad), 128 * 128, L.ptr(part), n_cta, L.stream_ptr()), "edm_loss")
     assert abs(part.double().sum().item() / B - ref.item()) < 1e-5 * abs(ref.item())
     assert rel_l2(dF, Fd.grad) < 1e-5
+    assert torch.equal(pad[..., :2].permute(0, 3, 1, 2), dF.to(torch.bfloat16)) and pad[..., 2:].abs().max() == 0
 
 
 # ----------------------------------------------------------------------------------------------- K3 bwd
@@ -229,3 +236,82 @@ def test_attention_bwd_matches_autograd(L, dev, B, Lq, scale):
     assert rel_l2(dv.float(), rv) < 8e-3        # bf16 P, bf16 output
     assert rel_l2(dq.float(), rq) < 1.5e-2      # bf16 dS (difference of nearly equal terms), bf16 output
     assert rel_l2(dk.float(), rk) < 1.5e-2
+
+
+# ----------------------------------------------------------------------------------------------- small kernels
+def test_noise_in_pad_colsum(L, dev):
+    lib = L.lib()
+    B, H, W = 3, 32, 64
+    g = torch.Generator().manual_seed(5)
+    x, noise = torch.randn(B, 2, H, W, generator=g).to(dev), torch.randn(B, 2, H, W, generator=g).to(dev)
+    mask = (torch.rand(B, 2, H, W, generator=g) > 0.5).float().to(dev)
+    sigma, c_in = torch.rand(B, generator=g).to(dev) + 0.1, torch.rand(B, generator=g).to(dev)
+    xn, xi = torch.empty_like(x), torch.empty_like(x)
+    L.check(lib.mcedm_edm_noise_in(L.ptr(x), L.ptr(noise), L.ptr(mask), L.ptr(sigma), L.ptr(c_in), B, 2 * H * W,
+                                   L.ptr(xn), L.ptr(xi), L.stream_ptr()))
+    ref = x + mask * noise * sigma.view(B, 1, 1, 1)
+    assert torch.equal(xn, ref) and torch.equal(xi, c_in.view(B, 1, 1, 1) * ref)
+    pad = torch.zeros(B, H, W, 64, device=dev, dtype=torch.bfloat16)
+    L.check(lib.mcedm_nchw_to_nhwc_pad(L.ptr(x), 2, L.ptr(noise), 2, B, H, W, L.ptr(pad), 0, L.stream_ptr()))
+    assert torch.equal(pad[..., :4].permute(0, 3, 1, 2), torch.cat([x, noise], 1).to(torch.bfloat16))
+    assert pad[..., 4:].abs().max() == 0
+    t = torch.randn(B * H * W, 192, generator=g).to(dev).to(torch.bfloat16)
+    part = torch.empty(37, 64, device=dev)
+    L.check(lib.mcedm_colsum_bf16(L.ptr(t), B * H * W, 192, 64, L.ptr(part), 37, L.stream_ptr()))
+    assert rel_l2(part.sum(0), t[:, 64:128].double().sum(0)) < 1e-5
+
+
+def test_emb_mlp_bwd_matches_autograd(L, dev):
+    lib = L.lib()
+    B, n_aff = 6, 15
+    g = torch.Generator().manual_seed(9)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)  # noqa: E731
+    c_noise, freqs = r(B) * 0.5, torch.rand(32, generator=g).to(dev)
+    w0, b0, w1, b1 = r(64, 64) / 8, r(64) * 0.1, r(64, 64) / 8, r(64) * 0.1
+    aff_w, aff_b, dss = r(n_aff, 128, 64) / 8, r(n_aff, 128) * 0.1, r(n_aff, B, 128)
+    out = torch.empty(n_aff, B, 128, device=dev)
+    L.check(lib.mcedm_emb_mlp(L.ptr(c_noise), L.ptr(freqs), L.ptr(w0), L.ptr(b0), L.ptr(w1), L.ptr(b1), L.ptr(aff_w),
+                              L.ptr(aff_b), n_aff, B, None, L.ptr(out), L.stream_ptr()))
+    P = [t.double().requires_grad_(True) for t in (w0, b0, w1, b1, aff_w, aff_b)]
+    ang = c_noise.double()[:, None] * freqs.double()[None]
+    e = torch.cat([ang.cos(), ang.sin()], 1)
+    h1 = F.silu(F.silu(e @ P[0].t() + P[1]) @ P[2].t() + P[3])
+    ref = torch.einsum("bk,atk->abt", h1, P[4]) + P[5][:, None]
+    assert rel_l2(out, ref) < 1e-5
+    ref.backward(dss.double())
+    vec = torch.empty(B, 320, device=dev)
+    G = [torch.full_like(t, float("nan")) for t in (aff_w, aff_b, w1, b1, w0, b0)]
+    L.check(lib.mcedm_emb_mlp_bwd(L.ptr(c_noise), L.ptr(freqs), L.ptr(w0), L.ptr(b0), L.ptr(w1), L.ptr(b1), L.ptr(aff_w),
+                                  L.ptr(dss), n_aff, B, L.ptr(vec), *[L.ptr(t) for t in G], L.stream_ptr()))
+    for got, want in zip(G, (P[4], P[5], P[2], P[3], P[0], P[1])):
+        assert rel_l2(got, want.grad) < 1e-5
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_adam_ema_clip_match_torch(L, dev, clip):
+    lib = L.lib()
+    n = 100003
+    g = torch.Generator().manual_seed(11)
+    p0 = torch.randn(n, generator=g).to(dev)
+    p = p0.clone()
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    m, v, ema = torch.zeros(n, device=dev), torch.zeros(n, device=dev), p0.clone()
+    ema_ref = p0.clone()
+    part = torch.empty(64, device=dev, dtype=torch.float64)
+    nrm = torch.zeros(1, device=dev)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g).to(dev) * (0.01 if step == 2 else 1.0)
+        ref.grad = grad.clone()
+        if clip:
+            tn = torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        ema_ref = ema_ref * 0.9 + (1 - 0.9) * ref.detach()
+        L.check(lib.mcedm_sumsq_partial(L.ptr(grad), n, L.ptr(part), 64, L.stream_ptr()))
+        L.check(lib.mcedm_adam_step(L.ptr(p), L.ptr(grad), L.ptr(m), L.ptr(v), n, 2e-2, 0.9, 0.999, 1e-8, 0.0, step,
+                                    L.ptr(part) if clip else None, 64, 1.0, 1.0, L.ptr(nrm), L.stream_ptr()))
+        L.check(lib.mcedm_ema_update(L.ptr(ema), L.ptr(p), n, 0.9, L.stream_ptr()))
+        if clip:
+            assert abs(nrm.item() - tn.item()) < 1e-4 * tn.item()
+        assert rel_l2(p - p0, ref.detach() - p0) < 1e-5
+        assert rel_l2(ema - p0, ema_ref - p0) < 1e-4
