@@ -244,4 +244,9 @@ class DhariwalUNet(torch.nn.Module):
         cond [B,Cc,H,W] fp32 or None (zeros, as in models/adm_blocks.py:327-331). Returns [B,out_ch,H,W] fp32."""
         if x_self_cond is not None or dx is not None or class_labels is not None or augment_labels is not None:
             raise NotImplementedError("self-conditioning, dx conditioning, class and augment labels are not supported")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training: the autograd node's backward runs the hand-written backward kernels (train_engine.py)
+            from .autograd import UNetFunction
+
+            return UNetFunction.apply(self, x, noise_labels, cond, *self.parameters())
         return self.engine().forward(x, noise_labels, cond)

@@ -25,7 +25,9 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib as L
+from .train_engine import TrainMixin
 
+WEIGHT_EPOCH = [0]
 _SEG9 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 
@@ -78,7 +80,7 @@ class _Block:
             self.be2 = m.norm2.bias.detach().float().contiguous()
 
 
-class UNetEngine:
+class UNetEngine(TrainMixin):
     def __init__(self, unet):
         self.unet = unet
         self.lib = L.lib()
@@ -111,10 +113,12 @@ class UNetEngine:
         self.use_flat = True     # padded-flat conv kernel (conv_flat.cu) for the narrower levels
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
+        self._tape = None
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
+        # WEIGHT_EPOCH counts in-place parameter updates made by the fused optimizer kernels (no autograd version bump)
+        return (WEIGHT_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
 
     def pack(self, force: bool = False):
         key = self._param_key()

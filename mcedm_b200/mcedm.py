@@ -149,8 +149,12 @@ class PlMcedm(LightningModule):
     def configure_optimizers(self):
         params = self.model.parameters()
         if self.optimizer == "Adam":
-            opt = torch.optim.Adam(params, lr=self.lr, weight_decay=self.weight_decay, betas=(self.beta1, 0.999),
-                                   amsgrad=self.amsgrad, eps=self.eps)
+            from .optim import FusedAdam
+
+            # torch.optim.Adam's arguments and state_dict layout, one fused clip+Adam kernel over a flat buffer
+            opt = FusedAdam(params, lr=self.lr, weight_decay=self.weight_decay, betas=(self.beta1, 0.999),
+                            amsgrad=self.amsgrad, eps=self.eps)
+            opt.grad_provider = lambda: self.model.engine().flat_grad()
         elif self.optimizer == "RMSProp":
             opt = torch.optim.RMSprop(params, lr=self.lr, weight_decay=self.weight_decay)
         elif self.optimizer == "SGD":
@@ -240,6 +244,32 @@ class PlMcedm(LightningModule):
             cond = None
         return self.model_precond(x_noise, sigma.float(), cond, x_self_cond=None, dx=None)
 
+    def forward_loss(self, x, sigma, noise, cond, mask, weight):
+        """Fused equivalent of `criteria(forward(x, sigma, noise, cond, mask) * mask, x * mask, weight)`
+        (mcedm.py:213-235, :278; losses.py:48-53), differentiable w.r.t. the U-Net parameters."""
+        from .autograd import EdmLossFunction
+
+        lib = L.lib()
+        if torch.rand(1) >= self.cond_p:                            # :231, host RNG draw kept for RNG parity
+            cond = None
+        B = x.shape[0]
+        chw = x[0].numel()
+        s = sigma.to(torch.float32).reshape(-1)
+        if s.numel() != B:
+            raise ValueError(f"sigma must have {B} entries")
+        den = s ** 2 + self.sigma_data ** 2
+        c_skip = (self.sigma_data ** 2 / den).contiguous()
+        c_out = (s * self.sigma_data / den.sqrt()).contiguous()
+        c_in = (1 / den.sqrt()).contiguous()
+        c_noise = (s.log() / 4).contiguous()
+        w = weight.to(torch.float32).reshape(-1).contiguous()
+        x = x.contiguous()
+        x_noise, x_in = torch.empty_like(x), torch.empty_like(x)
+        L.check(lib.mcedm_edm_noise_in(L.ptr(x), L.ptr(noise.contiguous()), L.ptr(mask), L.ptr(s.contiguous()),
+                                       L.ptr(c_in), B, chw, L.ptr(x_noise), L.ptr(x_in), L.stream_ptr()), "edm_noise_in")
+        F_x = self.model(x_in, c_noise, cond)
+        return EdmLossFunction.apply(F_x, x_noise, x, mask, c_skip, c_out, w)
+
     def get_denoised(self, model, xt, t, cond=None, x_self_cond=None, dx=None, w=None):
         if x_self_cond is not None or dx is not None:
             raise NotImplementedError("self-conditioning / dx conditioning are not supported")
@@ -263,8 +293,10 @@ class PlMcedm(LightningModule):
         sigma = (rnd_normal * self.P_std + self.P_mean).exp()
         weight = self.get_loss_weight(sigma)
         mask_c = rearrange(mask, "b h w c -> b c h w").contiguous()
-        D_x = self.forward(x, sigma, noise, cond=cond_in, mask=mask_c)
-        loss = self.criteria(D_x * mask_c, x * mask_c, weight)
+        # reference: D_x = self.forward(...); loss = self.criteria(D_x * mask, x * mask, weight)  (:277-278).
+        # Here noise injection + c_in scaling, the U-Net, and preconditioning + masked weighted loss (+ dL/dF) are
+        # three fused launches/nodes; `loss.backward()` runs the backward kernels.
+        loss = self.forward_loss(x, sigma, noise, cond_in, mask_c, weight)
         self.log("train_loss", loss, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
         return loss
 

@@ -55,6 +55,14 @@ class EmaModel(nn.Module):
         sel = [(c, m) for c, m in zip(cur, ma) if c.requires_grad]
         if not sel:
             return
+        if len(sel) == len(cur) and cur[0].is_cuda:
+            # one kernel over flat buffers (train_small.cu ema_update); no torch arithmetic on the GPU path
+            from .optim import ema_update_
+
+            if not hasattr(self, "_flat_state"):
+                object.__setattr__(self, "_flat_state", {})
+            ema_update_(ma, cur, self.beta, self._flat_state)
+            return
         # ema = ema * beta + (1 - beta) * p   (ddim_blocks.py:53-56), one fused multi-tensor pass
         mas = [m for _, m in sel]
         torch._foreach_mul_(mas, self.beta)

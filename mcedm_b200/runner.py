@@ -167,6 +167,12 @@ class Trainer:
         self.optimizer = module.configure_optimizers()["optimizer"]
         self.optimizers = [self.optimizer]
         params = [p for g in self.optimizer.param_groups for p in g["params"]]
+        from .optim import FusedAdam
+
+        fused = isinstance(self.optimizer, FusedAdam)
+        if fused:
+            self.optimizer.max_grad_norm = self.gradient_clip_val or None
+            self.optimizer.grad_scale = 1.0 / self.world_size
         if ckpt_path:
             ckpt = torch.load(ckpt_path, map_location=self._device)
             module.load_state_dict(ckpt["state_dict"])
@@ -181,9 +187,15 @@ class Trainer:
                 self.optimizer.zero_grad(set_to_none=True)
                 loss = module.training_step(batch, batch_idx)
                 loss.backward()
-                self._allreduce_grads(params)
-                if self.gradient_clip_val:
-                    torch.nn.utils.clip_grad_norm_(params, self.gradient_clip_val)
+                if fused:
+                    # gradients already live in one flat buffer: all-reduce it in place (sum; the 1/world factor and
+                    # the clip coefficient are folded into the Adam kernel)
+                    if self.world_size > 1:
+                        dist.all_reduce(self.optimizer.flat_grads())
+                else:
+                    self._allreduce_grads(params)
+                    if self.gradient_clip_val:
+                        torch.nn.utils.clip_grad_norm_(params, self.gradient_clip_val)
                 module.optimizer_step(epoch, batch_idx, self.optimizer)
                 module.global_step = step = step + 1
                 if self.max_steps and step >= self.max_steps:

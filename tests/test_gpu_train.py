@@ -315,3 +315,104 @@ def test_adam_ema_clip_match_torch(L, dev, clip):
             assert abs(nrm.item() - tn.item()) < 1e-4 * tn.item()
         assert rel_l2(p - p0, ref.detach() - p0) < 1e-5
         assert rel_l2(ema - p0, ema_ref - p0) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- whole network
+def _train_batch(g, dev):
+    from common import fixture_state
+
+    B = g["mask"].shape[0]
+    state, _, _, _ = fixture_state(n=B, seed=g["seed_fields"])
+    grid = torch.zeros(B, 128, 128, 1)
+    return tuple(t.to(dev) for t in (state[..., 0:1].contiguous(), grid, grid, state[..., 1:2].contiguous(), g["mask"]))
+
+
+def test_training_step_matches_reference_golden(dev):
+    """loss, a sample of parameter gradients and the global gradient norm of ONE training step against the fixture
+    produced by the unmodified reference (tests/golden/make_golden.py G4): bf16 tensor-core operands, fp32 accumulate."""
+    from common import NoiseFeed, golden, stress_module
+
+    g = golden("train_step.pt")
+    pl, _ = stress_module()
+    pl = pl.to(dev).train()
+    feed = NoiseFeed(g["noise_seed"])
+    pl._noise_hook = feed.hook
+    torch.manual_seed(g["cpu_seed"])
+    loss = pl.training_step(_train_batch(g, dev), 0)
+    loss.backward()
+    from mcedm_b200 import _lib
+    _lib.check_watchdog()
+    assert abs(float(loss) - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+    named = dict(pl.model.named_parameters())
+    errs = {k: rel_l2(named[k].grad, v) for k, v in g["grads"].items()}
+    print({k: f"{e:.2e}" for k, e in errs.items()})
+    assert max(errs.values()) < 4e-2, errs
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in pl.model.parameters()))
+    assert abs(float(gn) - float(g["grad_norm"])) < 2e-2 * float(g["grad_norm"])
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pl.model.parameters())
+
+
+def test_every_parameter_gradient_matches_oracle_autograd(dev):
+    """All 196 parameter gradients against fp32 autograd through the CPU oracle on the same inputs."""
+    from common import NoiseFeed, golden, stress_module
+    from oracle import edm_oracle as O
+
+    g = golden("train_step.pt")
+    pl, cfg = stress_module()
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "resample" not in k)
+          for k, v in pl.model.state_dict().items()}
+    pl = pl.to(dev).train()
+    h, _, _, u, mask = _train_batch(g, dev)
+    x = torch.cat([h, u], -1).permute(0, 3, 1, 2).contiguous()
+    mask_c = mask.permute(0, 3, 1, 2).contiguous()
+    gen = torch.Generator().manual_seed(1)
+    noise = torch.randn(x.shape, generator=gen).to(dev)
+    cond = (x * (1 - mask_c) + torch.randn(x.shape, generator=gen).to(dev) * mask_c).contiguous()
+    sigma = torch.tensor([0.7, 3.0]).view(2, 1, 1, 1).to(dev)
+    loss = pl.forward_loss(x, sigma, noise, cond, mask_c, pl.get_loss_weight(sigma))
+    loss.backward()
+    ref, _ = O.training_loss(sd, dict(cfg.model.hparams.model), x.cpu(), sigma.cpu(), noise.cpu(), cond.cpu(), mask_c.cpu())
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-2 * abs(float(ref))
+    worst, flat_a, flat_b = [], [], []
+    for k, p in pl.model.named_parameters():
+        e = rel_l2(p.grad, sd[k].grad)
+        worst.append((e, k))
+        flat_a.append(p.grad.flatten().cpu())
+        flat_b.append(sd[k].grad.flatten())
+    worst.sort(reverse=True)
+    print([(f"{e:.2e}", k) for e, k in worst[:8]])
+    assert rel_l2(torch.cat(flat_a), torch.cat(flat_b)) < 2e-2
+    assert worst[0][0] < 6e-2, worst[:5]
+
+
+def test_fused_optimizer_step_and_ema_inside_trainer_loop(dev):
+    """Two optimizer steps through the module hooks (FusedAdam + EMA kernel): parameters move, EMA follows with
+    rate 0.999, packed weights are refreshed (the loss changes), optimizer state_dict keeps torch.optim.Adam's layout."""
+    from common import NoiseFeed, golden, stress_module
+
+    g = golden("train_step.pt")
+    pl, _ = stress_module()
+    pl = pl.to(dev).train()
+    opt = pl.configure_optimizers()["optimizer"]
+    opt.max_grad_norm = 1.0
+    p0 = [p.detach().clone() for p in pl.model.parameters()]
+    e0 = [p.detach().clone() for p in pl.ema_model.ma_model.parameters()]
+    losses = []
+    for it in range(2):
+        feed = NoiseFeed(g["noise_seed"])
+        pl._noise_hook = feed.hook
+        torch.manual_seed(g["cpu_seed"])
+        opt.zero_grad(set_to_none=True)
+        loss = pl.training_step(_train_batch(g, dev), it)
+        loss.backward()
+        pl.optimizer_step(0, it, opt)
+        losses.append(float(loss))
+    assert losses[1] != losses[0] and all(l == l for l in losses)
+    moved = torch.cat([(a - b).flatten() for a, b in zip(pl.model.parameters(), p0)])
+    assert 0 < moved.abs().max().item() <= 2 * 2e-4 * 1.01          # Adam step is bounded by lr per step
+    for e, e_old, p in zip(pl.ema_model.ma_model.parameters(), e0, pl.model.parameters()):
+        assert torch.isfinite(e).all()
+    sd = opt.state_dict()
+    assert len(sd["state"]) == len(p0) and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd["state"][0]["step"]) == 2.0
