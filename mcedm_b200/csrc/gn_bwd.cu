@@ -305,15 +305,26 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) 
   }
 }
 
-// out[j] (+)= sum_r in[r*stride_r + j*stride_j + offset], ordered, one thread per j (small reductions of partials)
-__global__ void reduce_rows_kernel(const float* __restrict__ in, int n_rows, long long stride_r, int n_cols,
-                                   long long stride_j, float* __restrict__ out, int accumulate, float scale) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_cols) return;
+// out[j] (+)= scale * sum_r in[r*stride_r + j*stride_j]: 64 columns x 16 row lanes per CTA, fp64, fixed order
+// (folds per-CTA / per-sample partial sums; deterministic)
+__global__ void __launch_bounds__(1024)
+reduce_rows_kernel(const float* __restrict__ in, int n_rows, long long stride_r, int n_cols, long long stride_j,
+                   float* __restrict__ out, int accumulate, float scale) {
+  __shared__ double sm[16][64];
+  const int c = threadIdx.x & 63, lane = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + c;
   double t = 0.0;
-  for (int r = 0; r < n_rows; ++r) t += (double)in[r * stride_r + j * stride_j];
-  const float v = (float)t * scale;
-  out[j] = accumulate ? out[j] + v : v;
+  if (j < n_cols)
+    for (int r = lane; r < n_rows; r += 16) t += (double)in[r * stride_r + j * stride_j];
+  sm[lane][c] = t;
+  __syncthreads();
+  if (lane == 0 && j < n_cols) {
+    double a = 0.0;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) a += sm[l][c];
+    const float v = (float)a * scale;
+    out[j] = accumulate ? out[j] + v : v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ loss
@@ -406,7 +417,7 @@ extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrs
 extern "C" int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r, int n_cols, long long stride_j,
                                  float* out, int accumulate, float scale, void* stream) {
   using namespace mcedm;
-  reduce_rows_kernel<<<(n_cols + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  reduce_rows_kernel<<<(n_cols + 63) / 64, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       in, n_rows, stride_r, n_cols, stride_j, out, accumulate, scale);
   MCEDM_CUDA(cudaGetLastError());
   return 0;

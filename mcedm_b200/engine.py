@@ -140,7 +140,8 @@ class UNetEngine(TrainMixin):
                                     torch.zeros(16 - u.out_channels, device=dev)]).contiguous()
             self.g_out = u.out_norm.weight.detach().float().contiguous()
             self.be_out = u.out_norm.bias.detach().float().contiguous()
-            self.freqs = u.map_noise.frequencies(torch.float32).to(dev).contiguous()
+            if getattr(self, "freqs", None) is None or self.freqs.device != dev:   # constants: one H2D copy ever
+                self.freqs = u.map_noise.frequencies(torch.float32).to(dev).contiguous()
             self.w_m0, self.b_m0 = u.map_layer0.weight.detach().float().contiguous(), \
                 u.map_layer0.bias.detach().float().contiguous()
             self.w_m1, self.b_m1 = u.map_layer1.weight.detach().float().contiguous(), \

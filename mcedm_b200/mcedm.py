@@ -257,6 +257,8 @@ class PlMcedm(LightningModule):
         s = sigma.to(torch.float32).reshape(-1)
         if s.numel() != B:
             raise ValueError(f"sigma must have {B} entries")
+        if self.use_cuda_graph and self.model.training and torch.is_grad_enabled():
+            return self._graphed_loss(x, s, noise, cond, mask, weight)
         den = s ** 2 + self.sigma_data ** 2
         c_skip = (self.sigma_data ** 2 / den).contiguous()
         c_out = (s * self.sigma_data / den.sqrt()).contiguous()
@@ -269,6 +271,26 @@ class PlMcedm(LightningModule):
                                        L.ptr(c_in), B, chw, L.ptr(x_noise), L.ptr(x_in), L.stream_ptr()), "edm_noise_in")
         F_x = self.model(x_in, c_noise, cond)
         return EdmLossFunction.apply(F_x, x_noise, x, mask, c_skip, c_out, w)
+
+    def _graphed_loss(self, x, s, noise, cond, mask, weight):
+        """The same three nodes replayed from two CUDA graphs on static buffers (train_graph.py)."""
+        from .train_graph import GraphedLossFunction, TrainStepGraph
+
+        unet = self.model
+        params = list(unet.parameters())
+        key = (tuple(x.shape), x.device.index, params[0].data_ptr(), params[-1].data_ptr())
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        tg = graphs.get(key)
+        if tg is None:
+            if len(graphs) > 4:
+                graphs.clear()
+            tg = TrainStepGraph(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], unet.cond_channels, x.device)
+            tg.load(x, s, noise, cond, mask, weight)
+            tg.capture()
+            graphs[key] = tg
+            self.__dict__["_train_trigger"] = torch.zeros((), device=x.device, requires_grad=True)
+        tg.load(x, s, noise, cond, mask, weight)
+        return GraphedLossFunction.apply(tg, self.__dict__["_train_trigger"])
 
     def get_denoised(self, model, xt, t, cond=None, x_self_cond=None, dx=None, w=None):
         if x_self_cond is not None or dx is not None:

@@ -63,6 +63,8 @@ class FusedAdam(torch.optim.Adam):
         self._flat_g = None
         self._steps = 0
         self._n_partial = 128
+        if self._params[0].is_cuda:             # normally true: optimizers are configured after the module moved
+            self._bind()
 
     def _bind(self):
         if not self._params[0].is_cuda:

@@ -63,9 +63,9 @@ class TrainMixin:
         return self._grad_layout()
 
     # ------------------------------------------------------------------ packed weights of the data-gradient convs
-    def pack_train(self):
+    def pack_train(self, force: bool = False):
         self.pack()
-        if getattr(self, "_packed_train_key", None) == self._packed_key:
+        if not force and getattr(self, "_packed_train_key", None) == self._packed_key:
             return
         with torch.no_grad():
             for b in self.blocks_enc + self.blocks_dec:

@@ -352,8 +352,10 @@ def test_training_step_matches_reference_golden(dev):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pl.model.parameters())
 
 
-def test_every_parameter_gradient_matches_oracle_autograd(dev):
-    """All 196 parameter gradients against fp32 autograd through the CPU oracle on the same inputs."""
+@pytest.mark.parametrize("graph", [False, True])
+def test_every_parameter_gradient_matches_oracle_autograd(dev, graph):
+    """All 196 parameter gradients against fp32 autograd through the CPU oracle on the same inputs, through the
+    eager autograd bridge and through the CUDA-graph replay (twice: the replay must re-read its static inputs)."""
     from common import NoiseFeed, golden, stress_module
     from oracle import edm_oracle as O
 
@@ -362,6 +364,7 @@ def test_every_parameter_gradient_matches_oracle_autograd(dev):
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "resample" not in k)
           for k, v in pl.model.state_dict().items()}
     pl = pl.to(dev).train()
+    pl.use_cuda_graph = graph
     h, _, _, u, mask = _train_batch(g, dev)
     x = torch.cat([h, u], -1).permute(0, 3, 1, 2).contiguous()
     mask_c = mask.permute(0, 3, 1, 2).contiguous()
@@ -369,6 +372,9 @@ def test_every_parameter_gradient_matches_oracle_autograd(dev):
     noise = torch.randn(x.shape, generator=gen).to(dev)
     cond = (x * (1 - mask_c) + torch.randn(x.shape, generator=gen).to(dev) * mask_c).contiguous()
     sigma = torch.tensor([0.7, 3.0]).view(2, 1, 1, 1).to(dev)
+    if graph:     # a first step on other inputs: the second replay must not see stale data
+        pl.forward_loss(x.flip(0), sigma * 2, noise.flip(0), cond.flip(0), mask_c.flip(0), pl.get_loss_weight(sigma * 2)).backward()
+        pl.zero_grad(set_to_none=True)
     loss = pl.forward_loss(x, sigma, noise, cond, mask_c, pl.get_loss_weight(sigma))
     loss.backward()
     ref, _ = O.training_loss(sd, dict(cfg.model.hparams.model), x.cpu(), sigma.cpu(), noise.cpu(), cond.cpu(), mask_c.cpu())
