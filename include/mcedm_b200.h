@@ -114,11 +114,14 @@ MCEDM_API int mcedm_gn_stats(const float* x, long long n_pixels, float* partial,
  *                positions are written, the padding must have been zeroed once by the owner of the buffer
  *   out_raw_bf16 NULL, or receives bf16(x) in dense NHWC (operand of the block's 1x1 skip projection)
  *   meanrstd_out NULL, or fp32 [B][16][2] receiving (mean, rstd) per group, saved for mcedm_gn_bwd
+ *   coef_scratch fp32 [B][128] scratch: per-channel (a | b) of y = act(a*x + b), written by the finalize launch
+ *                and read by the streaming launch (two launches per call)
  */
 MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int act,
                              int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch, int out_blk,
-                             void* out_bf16, void* out_raw_bf16, float* meanrstd_out, void* stream);
+                             void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
+                             void* stream);
 
 /*
  * Backward of mcedm_gn_apply (training; autograd of adm_blocks.py:95, :161, :166).  Three launches: per-CTA partial

@@ -25,7 +25,7 @@ _PROTOTYPES = {
     "mcedm_conv_igemm": [_vpp, _i, _ip, _ip, _ip, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mcedm_conv_rows": [_vpp, _i, _vpp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp],
     "mcedm_gn_stats": [_vp, C.c_longlong, _vp, _vp],
-    "mcedm_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mcedm_gn_apply": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_gn_bwd_ctas_per_img": [_i, _i, _i],
     "mcedm_gn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp,
                      _vp, _vp, _i, _i, _vp, _vp, _vp],

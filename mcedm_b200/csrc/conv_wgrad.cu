@@ -256,7 +256,7 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int taps, flo
 }
 
 static int wgrad_grid(int B, int H, int W) {
-  long long g = (long long)B * H * W / 1024;
+  long long g = (long long)B * H * W / 512;
   if (g < 1) g = 1;
   if (g > num_sms()) g = num_sms();
   if (g > (long long)B * H) g = (long long)B * H;
@@ -299,8 +299,14 @@ extern "C" int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, in
   p.a_coff = a_coff;
   p.dy_slot_bytes = W * 128;
   p.a_slot_bytes = ((W + 2) * 128 + 1023) / 1024 * 1024;
-  p.n_slots = 4;
-  p.n_aslots = 3;
+  // ring depths: ~64 KB of dy rows and ~48 KB of a rows in flight (narrow levels have 2-4 KB rows: the
+  // producer has to run many rows ahead of the MMA issuer to hide the TMA round trip)
+  p.n_slots = 65536 / p.dy_slot_bytes;
+  if (p.n_slots < 4) p.n_slots = 4;
+  if (p.n_slots > 16) p.n_slots = 16;
+  p.n_aslots = 49152 / p.a_slot_bytes;
+  if (p.n_aslots < 3) p.n_aslots = 3;
+  if (p.n_aslots > 12) p.n_aslots = 12;
   p.partial = partial;
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "conv_wgrad: cannot allocate the watchdog word");

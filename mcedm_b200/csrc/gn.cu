@@ -73,6 +73,7 @@ struct GnApplyParams {
   void* out_raw;             // nullptr or bf16 NHWC copy of x itself (same resolution only)
   int pix_per_cta;           // INPUT pixels per CTA for resample 0/1, OUTPUT pixels per CTA for resample 2
   float* meanrstd_out;       // nullptr or [B][16][2] receiving (mean, rstd) per group (saved for the backward)
+  float* coef;               // [B][128]: per-channel (a | b) with y = act(a*x + b); written by gn_finalize_kernel
   int out_pitch;             // 0: dense NHWC output; > 0: padded flat layout of conv_flat.cu (row pitch)
   int out_blk;               // positions per image block of the padded layout
 };
@@ -105,10 +106,11 @@ __device__ __forceinline__ uint4 pack8(const float4 lo, const float4 hi) {
   return o;
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
-  __shared__ float sA[64], sB[64];
+// grid = B: folds the partial-sum records of image b (fixed order, fp64) into per-channel coefficients.
+// Done once per GroupNorm instead of once per streaming CTA, so the apply pass below is a pure stream.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnApplyParams p) {
   __shared__ float sMean[16], sRstd[16];
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;
   {
     // fold the partial-sum records of image b: 16 threads per group, fixed order, fp64.
     // Loads are issued 8 at a time before any add so the L2 latency is paid once per batch, not per record.
@@ -156,19 +158,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       a *= sc;
       bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
     }
-    sA[c] = a;
-    sB[c] = bb;
-  } else if (threadIdx.x < 80 && p.meanrstd_out && blockIdx.x == 0) {
+    p.coef[(long long)b * 128 + c] = a;
+    p.coef[(long long)b * 128 + 64 + c] = bb;
+  } else if (threadIdx.x < 80 && p.meanrstd_out) {
     const int g = threadIdx.x - 64;
     *reinterpret_cast<float2*>(p.meanrstd_out + ((long long)b * 16 + g) * 2) = make_float2(sMean[g], sRstd[g]);
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  const int b = blockIdx.y;
   const int c8 = threadIdx.x & 7;          // 8-channel slice
   const int ps = threadIdx.x >> 3;         // 0..31
-  const float4 a_lo = *reinterpret_cast<const float4*>(&sA[c8 * 8]);
-  const float4 a_hi = *reinterpret_cast<const float4*>(&sA[c8 * 8 + 4]);
-  const float4 b_lo = *reinterpret_cast<const float4*>(&sB[c8 * 8]);
-  const float4 b_hi = *reinterpret_cast<const float4*>(&sB[c8 * 8 + 4]);
+  const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)b * 128 + c8 * 8);
+  const float4 a_lo = __ldg(cf), a_hi = __ldg(cf + 1), b_lo = __ldg(cf + 16), b_hi = __ldg(cf + 17);
   const long long in_img = (long long)b * p.Hin * p.Win;
   const int pix0 = blockIdx.x * p.pix_per_cta;
   uint4* out = reinterpret_cast<uint4*>(p.out);
@@ -248,7 +251,8 @@ extern "C" int mcedm_gn_stats(const float* x, long long n_pixels, float* partial
 extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
                               const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
                               int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
-                              int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, void* stream) {
+                              int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
+                              void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply: Hin*Win=%d must be a multiple of 128", Hin * Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: resample=%d", resample);
@@ -273,15 +277,19 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   p.out_pitch = out_pitch;
   p.out_blk = out_blk;
   p.meanrstd_out = meanrstd_out;
+  p.coef = coef_scratch;
+  MCEDM_REQUIRE(coef_scratch != nullptr, "gn_apply: coef_scratch (fp32 [B][128]) is required");
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
-  // few, fat CTAs amortise the statistics prologue; keep >= ~4 CTAs per SM when the batch allows it
-  int per = 2048;
+  // streaming CTAs of <= 512 pixels (~200 KB of traffic each); keep >= ~4 CTAs per SM when the batch allows it
+  int per = 512;
   while (per > 32 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
   if (per < 32) per = 32;
   while (per > 32 && (work % per) != 0) per >>= 1;
   MCEDM_REQUIRE(work % per == 0, "gn_apply: cannot tile %d pixels", work);
   p.pix_per_cta = per;
   dim3 grid(work / per, B);
+  gn_finalize_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
   gn_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;

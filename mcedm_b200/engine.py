@@ -114,6 +114,7 @@ class UNetEngine(TrainMixin):
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self._tape = None
+        self._gn_coef: Dict[tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -258,9 +259,13 @@ class UNetEngine(TrainMixin):
     def _gn_apply(self, x, stats, parts, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out, raw, st,
                   eps=1e-5, flat=None, meanrstd=None):
         pitch, blk = flat if flat is not None else (0, 0)
+        coef = self._gn_coef.get((B, x.device.index))
+        if coef is None:
+            coef = self._gn_coef[(B, x.device.index)] = torch.empty(B, 128, device=x.device, dtype=torch.float32)
         L.check(self.lib.mcedm_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ss), ss_stride, 64,
                                         eps, act, resample, B, Hin, Win, parts, pitch, blk, L.ptr(out), L.ptr(raw),
-                                        L.ptr(meanrstd), st), "gn_apply")
+                                        L.ptr(meanrstd), L.ptr(coef), st), "gn_apply")
+        L.LAUNCHES[0] += 1      # finalize + streaming pass
 
     def _run_block(self, blk: _Block, inputs, B, H_in, W_in, ws, emb_stride, st, dev):
         """inputs: list of (fp32 NHWC tensor, stats, parts) at H_in x W_in. Returns ((out, stats, parts), H, W)."""

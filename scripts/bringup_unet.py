@@ -38,7 +38,7 @@ def test_gn():
         out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
         raw = torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16) if rs == 0 else None
         L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128,
-                                   64, 1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), L.ptr(raw), None, L.stream_ptr()))
+                                   64, 1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), L.ptr(raw), None, L.ptr(torch.empty(B, 128, device=dev)), L.stream_ptr()))
         xn = x.permute(0, 3, 1, 2)
         y = F.group_norm(xn, 16, gamma, beta, 1e-5)
         if use_ss:

@@ -173,7 +173,7 @@ def test_gn_apply_matches_group_norm(L, dev, B, H, W, rs, act, use_ss):
     Ho, Wo = (2 * H, 2 * W) if rs == 1 else (H // 2, W // 2) if rs == 2 else (H, W)
     out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
     L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64,
-                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, None, L.stream_ptr()))
+                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, None, L.ptr(torch.empty(B, 128, device=dev)), L.stream_ptr()))
     y = F.group_norm(x.permute(0, 3, 1, 2), 16, gamma, beta, 1e-5)
     if use_ss:
         y = torch.addcmul(ss[:, 64:, None, None], y, ss[:, :64, None, None] + 1)

@@ -125,7 +125,7 @@ def test_gn_bwd_matches_autograd(L, dev, B, H, W, rs, act, use_ss, add0_mode, us
     out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
     mr = torch.empty(B, 16, 2, device=dev)
     L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64,
-                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, L.ptr(mr), L.stream_ptr()))
+                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, L.ptr(mr), L.ptr(torch.empty(B, 128, device=dev)), L.stream_ptr()))
     dy = torch.randn(B, Ho, Wo, 64, generator=g).to(dev)
     add0 = None
     if add0_mode is not None:
