@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--cpu-baseline-fields", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=32, help="training samples per GPU per step (config 3: 256 / 8)")
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-train", action="store_true", help="skip the training-throughput measurement")
     return ap.parse_args()
 
 
@@ -130,6 +133,40 @@ def cpu_sample_fields(n_fields, timesteps, seed=0):
     with torch.no_grad():
         O.sample_edm(sd, dict(cfg.model.hparams.model), noise, cond, mask_c, sp,
                      lambda i, x: torch.randn(x.shape, dtype=x.dtype, generator=g))
+    return time.perf_counter() - t0, threads
+
+
+def cpu_train_step(batch, seed=0):
+    """Times one reference-algorithm training step (loss + backward through the oracle, fp32 autograd) on all host
+    cores. Returns (seconds, threads)."""
+    import torch
+
+    from mcedm_b200 import data as D
+    from mcedm_b200.adm_blocks import DhariwalUNet
+    from mcedm_b200.config import compose
+    from mcedm_b200.utils import randomize_zero_init
+    from oracle import edm_oracle as O
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = compose("config_adm_edm_mcedm_res32")
+    torch.manual_seed(1)
+    net = DhariwalUNet(copy.deepcopy(cfg.model.hparams))
+    randomize_zero_init(net, 2)
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and "resample" not in k)
+          for k, v in net.state_dict().items()}
+    h, tg, xg, u, mask = D.make_batch("swe_per", batch, "train", seed=seed)
+    st = D.field_stats("swe_per", 16)
+    state = torch.cat([(h - st["input_mean"]) / st["input_std"], (u - st["target_mean"]) / st["target_std"]], -1)
+    g = torch.Generator().manual_seed(seed)
+    x = state.permute(0, 3, 1, 2).contiguous()
+    mask_c = mask.permute(0, 3, 1, 2).contiguous()
+    cond = O.get_cond_in(state, mask, torch.randn(state.shape, generator=g)).permute(0, 3, 1, 2).contiguous()
+    noise = torch.randn(x.shape, generator=g)
+    sigma = (torch.randn([batch, 1, 1, 1], generator=g) * 1.2 - 1.2).exp()
+    t0 = time.perf_counter()
+    loss, _ = O.training_loss(sd, dict(cfg.model.hparams.model), x, sigma, noise, cond, mask_c)
+    loss.backward()
     return time.perf_counter() - t0, threads
 
 
@@ -257,18 +294,42 @@ def run_b200(args):
         pk = peaks()
         unet = pl.ema_model.ma_model
         x = torch.randn(chunk, 2, 128, 128, device=dev)
-        prof = unet.engine().profile_convs(x, torch.tensor([0.1], device=dev), cond_all[:chunk])
-        dom = [p for p in prof if p["N"] == 64 and p["n_seg"] >= 9]
+        prof_all = unet.engine().profile_convs(x, torch.tensor([0.1], device=dev), cond_all[:chunk], with_gn=True)
+        prof = [p for p in prof_all if p["kind"] == "conv"]
+        gn = [p for p in prof_all if p["kind"] == "gn"]
+        dom = [p for p in prof if p["N"] == 64 and p["n_seg"] >= 9 and p["H"] == 128]
         fl, t = sum(p["flops"] for p in dom), sum(p["ms"] for p in dom)
         conv_ms_all = sum(p["ms"] for p in prof)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")    # dram bytes per launch from an `ncu --set full` capture
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("conv_rows_kernel<64>")
         achieved = fl / (t * 1e-3) / 1e12
         roof = dict(bound="tensor", achieved=achieved, peak=pk["tensor_sustained"], unit="TFLOP/s",
-                    frac=achieved / pk["tensor_sustained"], traffic=None, kernel="conv_igemm_kernel<64> (3x3, 9-18 K segments)",
+                    frac=achieved / pk["tensor_sustained"], traffic=traffic,
+                    kernel="conv_rows_kernel<64> (3x3 implicit GEMM at 128x128, 64->64 channels per launch; 68 % of the FLOPs)",
                     launches_per_eval=len(dom), flops_per_eval=fl, ms_per_eval=t, conv_share_of_eval_ms=conv_ms_all,
                     peak_source=pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                    other_kernels=[
+                        dict(kernel="conv_flat_kernel<64> (3x3 at 64x64 / 32x32)", bound="tensor", unit="TFLOP/s",
+                             achieved=sum(p["flops"] for p in prof if p["N"] == 64 and p["n_seg"] >= 9 and p["H"] < 128) /
+                             max(1e-9, sum(p["ms"] for p in prof if p["N"] == 64 and p["n_seg"] >= 9 and p["H"] < 128)) / 1e9,
+                             peak=pk["tensor_sustained"]),
+                        dict(kernel="gn_finalize_kernel + gn_apply_kernel (GroupNorm+scale/shift+SiLU -> bf16 operand)",
+                             bound="hbm", unit="GB/s", achieved=sum(p["bytes"] for p in gn) / max(1e-9, sum(p["ms"] for p in gn)) / 1e6,
+                             peak=pk["hbm"], ms_per_eval=sum(p["ms"] for p in gn), launches_per_eval=2 * len(gn))],
                     end_to_end_tflops=value * EVALS_PER_FIELD * FLOPS_PER_EVAL * (args.timesteps * 2 - 1) / 99 / 1e12 / world)
+    train = None
+    if not args.no_train:
+        train = measure_training(args, cfg, dev, rank, world, barrier)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
+        if train is not None:
+            dt, threads = cpu_train_step(2)
+            train["cpu_baseline"] = dict(value=2 / dt, unit="samples/s", cores=threads, kind="port",
+                                         sample="one training step (loss + backward) of 2 samples through the oracle "
+                                                f"port of the reference algorithm, torch CPU fp32 autograd, {threads} threads")
         dt, threads = cpu_sample_fields(args.cpu_baseline_fields, args.timesteps)
         cpu = dict(value=args.cpu_baseline_fields / dt, unit="fields/s", cores=threads, kind="port",
                    sample=f"{args.cpu_baseline_fields} field x {args.timesteps} Heun steps of the same workload "
@@ -276,8 +337,11 @@ def run_b200(args):
     if rank == 0:
         line = dict(metric="edm_sampled_fields_per_sec", value=value, unit="fields/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload="mcedm edm_sampler Heun sampling, n_samples=1024 of 128x128 SWE fields per GPU "
+                    vs_baseline=None, dtype="fp16" if pl.ema_model.ma_model.engine().infer_fmt else "bf16", data="synthetic",
+                    config=dict(operands="16-bit tensor-core operands (fp16 for inference: 11 significand bits, per-step "
+                                         "denoiser error 1.3e-3 vs the reference; bf16 selectable: 1.0e-2), fp32 accumulation, "
+                                         "fp32 residual stream, fp64 sampler state",
+                                workload="mcedm edm_sampler Heun sampling, n_samples=1024 of 128x128 SWE fields per GPU "
                                          "(BASELINE configs[1])", fields_per_gpu=rows, micro_batch=chunk,
                                 timesteps=args.timesteps, net_evals_per_field=2 * args.timesteps - 1,
                                 weights="random init (seed 1) + randomised zero-init tensors (seed 2)",
@@ -287,11 +351,83 @@ def run_b200(args):
                     clocks=clk,
                     e2e=dict(value=e2e_value, unit="fields/s", h2d_bytes_per_step=int(2 * rows * 2 * 128 * 128 * 4),
                              d2h_bytes_per_step=int(rows * 2 * 128 * 128 * 8), ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu)
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train=train)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_training(args, cfg, dev, rank, world, barrier):
+    """U-Net train samples/s (BASELINE metric, second half; configs[2]: masked mixed-conditioning EDM training, bf16
+    tensor-core operands, data-parallel): every rank runs `--train-batch` samples per step through
+    PlMcedm.training_step -> loss.backward() -> [NCCL all-reduce of the flat gradient] -> fused clip+Adam -> EMA."""
+    import torch
+    import torch.distributed as dist
+
+    from mcedm_b200 import _lib as L
+    from mcedm_b200 import data as D
+    from mcedm_b200.mcedm import PlMcedm
+    from mcedm_b200.utils import randomize_zero_init
+
+    B = args.train_batch
+    torch.manual_seed(1)
+    pl = PlMcedm(copy.deepcopy(cfg.model.hparams))
+    randomize_zero_init(pl.model, 2)
+    pl = pl.to(dev).train()
+    opt = pl.configure_optimizers()["optimizer"]
+    opt.max_grad_norm = 1.0
+    opt.grad_scale = 1.0 / world
+    st = D.field_stats("swe_per", 16)
+    pl.normalizer_input.set_stats(st["input_mean"].to(dev), st["input_std"].to(dev))
+    pl.normalizer_target.set_stats(st["target_mean"].to(dev), st["target_std"].to(dev))
+    host = [t.pin_memory() for t in D.make_batch("swe_per", B, "train", seed=17 + rank)]
+    resident = tuple(t.to(dev) for t in host)
+
+    def step(e2e):
+        batch = tuple(t.to(dev, non_blocking=True) for t in host) if e2e else resident
+        opt.zero_grad(set_to_none=True)
+        loss = pl.training_step(batch, 0)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(opt.flat_grads())
+        pl.optimizer_step(0, 0, opt)
+        return loss
+
+    def timed(e2e, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = step(e2e)
+            if e2e:
+                loss.item()                                  # device -> host read of the step's loss
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(5):
+        step(False)
+    n0 = L.LAUNCHES[0]
+    ms = timed(False, args.train_steps)
+    launches = L.LAUNCHES[0] - n0
+    ms_e2e = timed(True, args.train_steps)
+    L.check_watchdog()
+    per = ms / args.train_steps
+    bytes_in = sum(t.numel() * t.element_size() for t in host)
+    return dict(metric="unet_train_samples_per_sec", value=B * world * args.train_steps / (ms / 1e3), unit="samples/s",
+                ms_per_step=per, batch_per_gpu=B, global_batch=B * world, steps=args.train_steps, dtype="bf16",
+                tflops_per_gpu=56.305e9 * B / per / 1e9,
+                e2e=dict(value=B * world * args.train_steps / (ms_e2e / 1e3), unit="samples/s",
+                         h2d_bytes_per_step=bytes_in, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.train_steps),
+                gpu_launches=launches,
+                config=dict(workload="masked mixed-conditioning EDM training step (BASELINE configs[2]): forward + loss + "
+                                     "backward + grad all-reduce + clip + Adam + EMA", optimizer="Adam lr 2e-4, clip 1.0, EMA 0.999",
+                            parallelism=f"data-parallel over {world} GPU(s), one NCCL all-reduce of the flat fp32 gradient",
+                            cuda_graph=True))
 
 
 if __name__ == "__main__":

@@ -15,6 +15,10 @@
  *       bf16 NHWC  = tensor-core operands (normalised + activated tensors);
  *   - the public tensors of the reference API (x, cond, mask, D_x, sampler state) stay NCHW,
  *     fp32 (sampler state fp64), exactly as models/mcedm.py passes them.
+ *   - op_fmt selects the format of every 16-bit tensor-core operand of a call (activations, packed weights and a
+ *     16-bit output): 0 = bf16, 1 = fp16 (same layouts, same tensor throughput; names keep the `_bf16` suffix).
+ *     Training uses bf16 throughout (gradients need its range); inference may use fp16, whose 11 significand bits
+ *     cut the operand-rounding error of the network output ~8x (activations are normalised, weights are O(1)).
  *   - there is NO CPU implementation behind any of these: without an sm_100 device they fail.
  */
 #ifndef MCEDM_B200_H
@@ -60,7 +64,7 @@ MCEDM_API int mcedm_check_watchdog(void* stream);
  */
 MCEDM_API int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg_src, const int* seg_dy, const int* seg_dx,
                      int n_seg, const void* w_packed, const float* bias, int B, int H, int W, int N, void* out,
-                     int out_bf16, const float* res, int res_mode, float* stats_partial, void* stream);
+                     int out_bf16, const float* res, int res_mode, float* stats_partial, int op_fmt, void* stream);
 
 /*
  * Row-resident variant of mcedm_conv_igemm for W == 128 (one tile = one image row): every input row is
@@ -75,7 +79,7 @@ MCEDM_API int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg
  */
 MCEDM_API int mcedm_conv_rows(const void* const* halo_src, int n_halo, const void* const* ctr_src, int n_ctr,
                               const void* w_packed, const float* bias, int B, int H, int N, void* out, int out_bf16,
-                              const float* res, int res_mode, float* stats_partial, void* stream);
+                              const float* res, int res_mode, float* stats_partial, int op_fmt, void* stream);
 
 /*
  * Narrow-level (W <= 64) variant: the bf16 operand is a zero-padded flat pixel sequence (written by
@@ -88,7 +92,8 @@ MCEDM_API int mcedm_conv_rows(const void* const* halo_src, int n_halo, const voi
  */
 MCEDM_API int mcedm_flat_geometry(int H, int W, int* pitch, int* block_positions);
 MCEDM_API int mcedm_conv_flat(const void* src_flat, const void* w_packed, const float* bias, int B, int H, int W, int N,
-                              float* out, const float* res, int res_mode, float* stats_partial, void* stream);
+                              float* out, const float* res, int res_mode, float* stats_partial, int op_fmt,
+                              void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K2  GroupNorm statistics / fused GroupNorm + scale-shift + SiLU + resample                     */
@@ -121,7 +126,7 @@ MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* 
                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int act,
                              int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch, int out_blk,
                              void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
-                             void* stream);
+                             int op_fmt, void* stream);
 
 /*
  * Backward of mcedm_gn_apply (training; autograd of adm_blocks.py:95, :161, :166).  Three launches: per-CTA partial
@@ -182,7 +187,8 @@ MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, flo
 /* -------------------------------------------------------------------------------------------- */
 /* qkv bf16 [B,L,192] = (q|k|v) x 64 channels; out bf16 [B,L,64]; softmax(q.k/8) in fp32. L % 128 == 0.
  * lse_out NULL, or fp32 [B,L] receiving the base-2 log-sum-exp of each row (saved for mcedm_attention_bwd). */
-MCEDM_API int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, void* stream);
+MCEDM_API int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, int op_fmt,
+                              void* stream);
 /*
  * Backward of mcedm_attention (autograd of adm_blocks.py:103-118 AttentionOp + the einsum at :178):
  *   given d_out bf16 [B,L,64] (gradient w.r.t. out), the saved qkv / out / lse, writes dq, dk, dv bf16 [B,L,64].

@@ -12,8 +12,9 @@
 // Output: a bf16 [B, L, 64] (operand of the proj 1x1 conv).
 //
 // One CTA = 128 queries of one sample. Two passes over the keys in blocks of 128:
-//   pass 1: S = Q K^T on tensor cores -> TMEM; softmax warps keep a running (max, sum) per row;
-//   pass 2: S again, P = exp2((S - max) * log2e/8) -> bf16 -> swizzled smem, O += P V on tensor cores.
+//   pass 1: S = Q K^T on tensor cores -> TMEM; softmax warps keep the running row maximum (no exponentials);
+//   pass 2: S again, P = exp2((S - max) * log2e/8) -> bf16 -> swizzled smem, O += P V on tensor cores; the row
+//           sum is accumulated in fp32 from the same exponentials.
 // The second QK^T costs 50 % more MMA work but removes every accumulator rescale; the kernel is
 // bound by the exp/convert work of the 4 softmax warps, not by the tensor pipe.
 //   warp 0 : TMA producer (Q once; K blocks in pass 1; K and V blocks in pass 2; 3-stage ring)
@@ -38,7 +39,7 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(192, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out,
-            float* __restrict__ lse_out, unsigned int* err) {
+            float* __restrict__ lse_out, int fmt, unsigned int* err) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                                  // 16 KB
@@ -103,8 +104,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   } else if (warp == 1) {
     // warp-uniform control flow; one elected lane issues the tcgen05 instructions
     {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);   // B = V, MN-major
+      const uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, fmt);
+      const uint32_t idesc_o = umma_idesc_16(128, 64, 0, 1, fmt);    // B = V, MN-major
       mbar_wait(q_full, 0, err, 0x1200);
       tc_fence_after();
       const uint32_t q_base = smem_u32(q_smem);
@@ -154,7 +155,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c1 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
     float m = -INFINITY, l = 0.f;
-    // ---------------- pass 1: running max / sum ----------------
+    // ---------------- pass 1: row maximum only (the row sum is accumulated from the pass-2 exponentials) -----
     for (int it = 0; it < nblk; ++it) {
       const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
       mbar_wait(&s_full[sb], ns & 1u, err, 0x1600 + sb);
@@ -164,15 +165,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
         tmem_wait_ld();
-        float cm = __uint_as_float(v[0]);
+        float cm0 = __uint_as_float(v[0]), cm1 = __uint_as_float(v[1]);
 #pragma unroll
-        for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
-        const float mn = fmaxf(m, cm);
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc += ex2((__uint_as_float(v[i]) - mn) * c1);
-        l = l * ex2((m - mn) * c1) + acc;
-        m = mn;
+        for (int i = 2; i < 32; i += 2) {
+          cm0 = fmaxf(cm0, __uint_as_float(v[i]));
+          cm1 = fmaxf(cm1, __uint_as_float(v[i + 1]));
+        }
+        m = fmaxf(m, fmaxf(cm0, cm1));
       }
       tc_fence_before();
       mbar_arrive(&s_empty[sb]);
@@ -201,7 +200,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
           for (int e = 0; e < 4; ++e) {
             const float p0 = ex2(fmaf(__uint_as_float(v[u * 8 + 2 * e]), c1, -mc));
             const float p1 = ex2(fmaf(__uint_as_float(v[u * 8 + 2 * e + 1]), c1, -mc));
-            op[e] = pack_bf16x2(p0, p1);
+            op[e] = pack_op2(p0, p1, fmt);
+            // normalise by what the P V product actually sums (the rounded weights)
+            if (fmt) {
+              const float2 r = unpack_f16x2(op[e]);
+              l += r.x + r.y;
+            } else {
+              l += bf16_lo(op[e]) + bf16_hi(op[e]);
+            }
           }
           const int unit = ((c & 1) * 4 + u) ^ (row & 7);
           *reinterpret_cast<uint4*>(atom_row + unit * 16) = o;
@@ -227,10 +233,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[u * 8 + 0]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l);
-        o.y = pack_bf16x2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l);
-        o.z = pack_bf16x2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l);
-        o.w = pack_bf16x2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l);
+        o.x = pack_op2(__uint_as_float(v[u * 8 + 0]) * inv_l, __uint_as_float(v[u * 8 + 1]) * inv_l, fmt);
+        o.y = pack_op2(__uint_as_float(v[u * 8 + 2]) * inv_l, __uint_as_float(v[u * 8 + 3]) * inv_l, fmt);
+        o.z = pack_op2(__uint_as_float(v[u * 8 + 4]) * inv_l, __uint_as_float(v[u * 8 + 5]) * inv_l, fmt);
+        o.w = pack_op2(__uint_as_float(v[u * 8 + 6]) * inv_l, __uint_as_float(v[u * 8 + 7]) * inv_l, fmt);
         *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = o;
       }
     }
@@ -279,7 +285,8 @@ __global__ void attn_ref_kernel(const __nv_bfloat16* __restrict__ qkv, int L, fl
 
 }  // namespace mcedm
 
-extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, void* stream) {
+extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, int op_fmt,
+                               void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && L >= 128 && L % 128 == 0, "attention: L=%d must be a positive multiple of 128", L);
   CUtensorMap tm;
@@ -294,7 +301,7 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
     attr_set = true;
   }
   attn_kernel<<<B * (L / 128), 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, err);
+      tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0, err);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -38,6 +38,7 @@ struct FlatParams {
   const float* res;
   int res_mode;            // 0 none, 1 same res, 2 nearest-x2 of [B,H/2,W/2,N], 3 2x2 mean of [B,2H,2W,N]
   float* stats;            // [total_tiles][4][N/4][2]
+  int fmt;                 // 16-bit operand format: 0 bf16, 1 fp16
   unsigned int* err;
 };
 
@@ -146,7 +147,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // ====================================== MMA issuer ======================================
     // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+      const uint32_t idesc = umma_idesc_16(128, N, 0, 0, p.fmt);
       mbar_wait(w_full, 0, p.err, 0x3200);
       tc_fence_after();
       const uint32_t w_base = smem_u32(w_smem);
@@ -279,7 +280,8 @@ extern "C" int mcedm_flat_geometry(int H, int W, int* pitch, int* block_position
 }
 
 extern "C" int mcedm_conv_flat(const void* src_flat, const void* w_packed, const float* bias, int B, int H, int W, int N,
-                               float* out, const float* res, int res_mode, float* stats_partial, void* stream) {
+                               float* out, const float* res, int res_mode, float* stats_partial, int op_fmt,
+                               void* stream) {
   using namespace mcedm;
   int P = 0, blk = 0;
   int rc = mcedm_flat_geometry(H, W, &P, &blk);
@@ -298,6 +300,7 @@ extern "C" int mcedm_conv_flat(const void* src_flat, const void* w_packed, const
   p.res = res;
   p.res_mode = res_mode;
   p.stats = stats_partial;
+  p.fmt = op_fmt ? 1 : 0;
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "conv_flat: cannot allocate the watchdog word");
   MCEDM_REQUIRE((long long)B * blk < (1LL << 31), "conv_flat: tensor too large for 32-bit TMA coordinates");

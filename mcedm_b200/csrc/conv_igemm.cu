@@ -45,6 +45,7 @@ struct ConvParams {
   const float* bias;      // [N] or nullptr
   void* out;              // [pixels, N] fp32 or bf16
   int out_bf16;
+  int fmt;               // 16-bit operand format (inputs, weights and a 16-bit output): 0 bf16, 1 fp16
   const float* res;       // residual, fp32 NHWC with N channels (resolution per res_mode)
   int res_mode;           // 0 none, 1 same resolution, 2 nearest-x2 upsample of res, 3 2x2 mean of res
   float* stats;           // [n_tiles][N/4][2] (sum, sum of squares of the stored values) or nullptr
@@ -137,7 +138,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     // ====================================== MMA issuer ======================================
     // warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
+      const uint32_t idesc = umma_idesc_16(kTileM, N, 0, 0, p.fmt);
       mbar_wait(w_full, 0, p.err, 0x200);
       tc_fence_after();
       uint32_t it = 0, tcount = 0;
@@ -243,8 +244,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
           s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
           if (p.out_bf16) {
             uint2 o;
-            o.x = pack_bf16x2(a.x, a.y);
-            o.y = pack_bf16x2(a.z, a.w);
+            o.x = pack_op2(a.x, a.y, p.fmt);
+            o.y = pack_op2(a.z, a.w, p.fmt);
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * N + c0) = o;
           } else {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * N + c0) = a;
@@ -312,7 +313,7 @@ static int launch_conv(const CUtensorMap& tm_w, const CUtensorMap* tm_a, const C
 extern "C" int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg_src, const int* seg_dy,
                                 const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
                                 int W, int N, void* out, int out_bf16, const float* res, int res_mode,
-                                float* stats_partial, void* stream) {
+                                float* stats_partial, int op_fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(n_src >= 1 && n_src <= 4, "conv_igemm: n_src=%d not in 1..4", n_src);
   MCEDM_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, "conv_igemm: n_seg=%d not in 1..%d", n_seg, kMaxSeg);
@@ -340,6 +341,7 @@ extern "C" int mcedm_conv_igemm(const void* const* src, int n_src, const int* se
   p.bias = bias;
   p.out = out;
   p.out_bf16 = out_bf16;
+  p.fmt = op_fmt ? 1 : 0;
   p.res = res;
   p.res_mode = res_mode;
   p.stats = stats_partial;

@@ -45,6 +45,7 @@ struct RowsParams {
   const float* bias;
   void* out;
   int out_bf16;
+  int fmt;               // 16-bit operand format: 0 bf16, 1 fp16
   const float* res;
   int res_mode;          // 0 none, 1 same resolution, 2 nearest-x2 upsample of res
   float* stats;          // [total_rows][4 lane quarters][N/4][2]
@@ -167,7 +168,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // emit an election loop + R2UR moves per MMA: ~4K issue cycles per tile on one thread, which was
     // the kernel's bottleneck.)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+      const uint32_t idesc = umma_idesc_16(128, N, 0, 0, p.fmt);
       mbar_wait(w_full, 0, p.err, 0x2300);
       tc_fence_after();
       const uint32_t w_base = smem_u32(w_smem);
@@ -301,8 +302,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const long long pix = pix0 + row;
         if (p.out_bf16) {
           uint2 o;
-          o.x = pack_bf16x2(a.x, a.y);
-          o.y = pack_bf16x2(a.z, a.w);
+          o.x = pack_op2(a.x, a.y, p.fmt);
+          o.y = pack_op2(a.z, a.w, p.fmt);
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * N + c0) = o;
         } else {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * N + c0) = a;
@@ -365,7 +366,7 @@ static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const C
 
 extern "C" int mcedm_conv_rows(const void* const* halo_src, int n_halo, const void* const* ctr_src, int n_ctr,
                                const void* w_packed, const float* bias, int B, int H, int N, void* out, int out_bf16,
-                               const float* res, int res_mode, float* stats_partial, void* stream) {
+                               const float* res, int res_mode, float* stats_partial, int op_fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(n_halo >= 1 && n_halo <= 2 && n_ctr >= 0 && n_ctr <= 2, "conv_rows: n_halo=%d n_ctr=%d", n_halo, n_ctr);
   MCEDM_REQUIRE(B >= 1 && H >= 1, "conv_rows: bad B/H");
@@ -380,6 +381,7 @@ extern "C" int mcedm_conv_rows(const void* const* halo_src, int n_halo, const vo
   p.bias = bias;
   p.out = out;
   p.out_bf16 = out_bf16;
+  p.fmt = op_fmt ? 1 : 0;
   p.res = res;
   p.res_mode = res_mode;
   p.stats = stats_partial;

@@ -73,6 +73,7 @@ struct GnApplyParams {
   void* out_raw;             // nullptr or bf16 NHWC copy of x itself (same resolution only)
   int pix_per_cta;           // INPUT pixels per CTA for resample 0/1, OUTPUT pixels per CTA for resample 2
   float* meanrstd_out;       // nullptr or [B][16][2] receiving (mean, rstd) per group (saved for the backward)
+  int fmt;                   // output operand format: 0 bf16, 1 fp16
   float* coef;               // [B][128]: per-channel (a | b) with y = act(a*x + b); written by gn_finalize_kernel
   int out_pitch;             // 0: dense NHWC output; > 0: padded flat layout of conv_flat.cu (row pitch)
   int out_blk;               // positions per image block of the padded layout
@@ -97,12 +98,12 @@ __device__ __forceinline__ float4 gn_act4(float4 v, const float4 a, const float4
   }
   return v;
 }
-__device__ __forceinline__ uint4 pack8(const float4 lo, const float4 hi) {
+__device__ __forceinline__ uint4 pack8(const float4 lo, const float4 hi, int fmt) {
   uint4 o;
-  o.x = pack_bf16x2(lo.x, lo.y);
-  o.y = pack_bf16x2(lo.z, lo.w);
-  o.z = pack_bf16x2(hi.x, hi.y);
-  o.w = pack_bf16x2(hi.z, hi.w);
+  o.x = pack_op2(lo.x, lo.y, fmt);
+  o.y = pack_op2(lo.z, lo.w, fmt);
+  o.z = pack_op2(hi.x, hi.y, fmt);
+  o.w = pack_op2(hi.z, hi.w, fmt);
   return o;
 }
 
@@ -193,13 +194,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
         if (i + 32 * k < p.pix_per_cta) {
           const int ip = pix0 + i + 32 * k;
           const long long pix = in_img + ip;
-          if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo[k], hi[k]);
+          if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo[k], hi[k], p.fmt);
           long long opix = pix;
           if (p.out_pitch > 0) {
             const int y = ip / p.Win;
             opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
           }
-          out[opix * 8 + c8] = pack8(gn_act4(lo[k], a_lo, b_lo, p.act), gn_act4(hi[k], a_hi, b_hi, p.act));
+          out[opix * 8 + c8] = pack8(gn_act4(lo[k], a_lo, b_lo, p.act), gn_act4(hi[k], a_hi, b_hi, p.act), p.fmt);
         }
       }
     }
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       const int ip = pix0 + i;
       const int y = ip / p.Win, x = ip - y * p.Win;
       const float4* xp = reinterpret_cast<const float4*>(p.x + (in_img + ip) * 64 + c8 * 8);
-      const uint4 v = pack8(gn_act4(xp[0], a_lo, b_lo, p.act), gn_act4(xp[1], a_hi, b_hi, p.act));
+      const uint4 v = pack8(gn_act4(xp[0], a_lo, b_lo, p.act), gn_act4(xp[1], a_hi, b_hi, p.act), p.fmt);
       const long long o00 = gn_out_index(p, b, 2 * y, 2 * x, Ho, Wo);
       out[o00 * 8 + c8] = v;
       out[(o00 + 1) * 8 + c8] = v;
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       }
       lo.x *= 0.25f; lo.y *= 0.25f; lo.z *= 0.25f; lo.w *= 0.25f;
       hi.x *= 0.25f; hi.y *= 0.25f; hi.z *= 0.25f; hi.w *= 0.25f;
-      out[gn_out_index(p, b, y, x, Ho, Wo) * 8 + c8] = pack8(lo, hi);
+      out[gn_out_index(p, b, y, x, Ho, Wo) * 8 + c8] = pack8(lo, hi, p.fmt);
     }
   }
 }
@@ -252,7 +253,7 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
                               const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
                               int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
                               int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
-                              void* stream) {
+                              int op_fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply: Hin*Win=%d must be a multiple of 128", Hin * Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: resample=%d", resample);
@@ -278,6 +279,7 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   p.out_blk = out_blk;
   p.meanrstd_out = meanrstd_out;
   p.coef = coef_scratch;
+  p.fmt = op_fmt ? 1 : 0;
   MCEDM_REQUIRE(coef_scratch != nullptr, "gn_apply: coef_scratch (fp32 [B][128]) is required");
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
   // streaming CTAs of <= 512 pixels (~200 KB of traffic each); keep >= ~4 CTAs per SM when the batch allows it

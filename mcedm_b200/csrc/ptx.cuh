@@ -190,6 +190,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// Operand format of the 16-bit tensor-core operands: 0 = bf16 (training: gradients need the range), 1 = fp16
+// (inference: activations are normalised and weights are O(1), and fp16's 11 significand bits cut the
+// operand-rounding error of the network output ~8x at the same tensor throughput).  Same instruction kind.
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int fmt) {
+  const uint32_t f = fmt ? 0u : 1u;       // descriptor format code: 0 = f16, 1 = bf16
+  return (1u << 4) | (f << 7) | (f << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// (kind::f16 requires A and B to share one 16-bit format: a bf16 x fp16 mix raises an illegal-instruction fault
+// on sm_100a — tried, to keep the weights at 11 significand bits.)
 
 // -------------------------------------- misc numerics -----------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
@@ -198,6 +209,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi, int fmt) {
+  return fmt ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n"
+      : "=f"(lo), "=f"(hi) : "r"(v));
+  return make_float2(lo, hi);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }

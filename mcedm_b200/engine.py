@@ -31,14 +31,14 @@ WEIGHT_EPOCH = [0]
 _SEG9 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 
-def pack_conv3x3(weight: torch.Tensor, n_out_pad: Optional[int] = None) -> torch.Tensor:
-    """[Cout, 64*n_src, k, k] fp32 -> bf16 [n_src*k*k][Cout(_pad)][64], segment order (source, ky, kx)."""
+def pack_conv3x3(weight: torch.Tensor, n_out_pad: Optional[int] = None, dtype=torch.bfloat16) -> torch.Tensor:
+    """[Cout, 64*n_src, k, k] fp32 -> 16-bit [n_src*k*k][Cout(_pad)][64], segment order (source, ky, kx)."""
     cout, cin, k, _ = weight.shape
     n_src = cin // 64
     w = weight.detach().reshape(cout, n_src, 64, k, k).permute(1, 3, 4, 0, 2).reshape(n_src * k * k, cout, 64)
     if n_out_pad is not None and n_out_pad > cout:
         w = torch.cat([w, w.new_zeros(w.shape[0], n_out_pad - cout, 64)], dim=1)
-    return w.to(torch.bfloat16).contiguous()
+    return w.to(dtype).contiguous()
 
 
 class _Block:
@@ -57,14 +57,14 @@ class _Block:
         if not mod.adaptive_scale:
             raise NotImplementedError("adaptive_scale=False has no kernel")
 
-    def pack(self):
+    def pack(self, dtype=torch.bfloat16):
         m = self.mod
-        self.w0 = pack_conv3x3(m.conv0.weight)
+        self.w0 = pack_conv3x3(m.conv0.weight, dtype=dtype)
         self.b0 = m.conv0.bias.detach().float().contiguous()
-        w1 = pack_conv3x3(m.conv1.weight)
+        w1 = pack_conv3x3(m.conv1.weight, dtype=dtype)
         b1 = m.conv1.bias.detach().float()
         if self.skip_conv:
-            w1 = torch.cat([w1, pack_conv3x3(m.skip.weight)], dim=0).contiguous()
+            w1 = torch.cat([w1, pack_conv3x3(m.skip.weight, dtype=dtype)], dim=0).contiguous()
             b1 = b1 + m.skip.bias.detach().float()
         self.w1, self.b1 = w1, b1.contiguous()
         self.g0, self.be0 = m.norm0.weight.detach().float().contiguous(), m.norm0.bias.detach().float().contiguous()
@@ -72,9 +72,9 @@ class _Block:
         if self.attn:
             # reference channel order is (c*3 + {q,k,v}) (adm_blocks.py:175-176) -> blocked (q | k | v)
             perm = torch.arange(192, device=m.qkv.weight.device).reshape(64, 3).t().reshape(-1)
-            self.wqkv = m.qkv.weight.detach()[perm].reshape(1, 192, 64).to(torch.bfloat16).contiguous()
+            self.wqkv = m.qkv.weight.detach()[perm].reshape(1, 192, 64).to(dtype).contiguous()
             self.bqkv = m.qkv.bias.detach().float()[perm].contiguous()
-            self.wproj = m.proj.weight.detach().reshape(1, 64, 64).to(torch.bfloat16).contiguous()
+            self.wproj = m.proj.weight.detach().reshape(1, 64, 64).to(dtype).contiguous()
             self.bproj = m.proj.bias.detach().float().contiguous()
             self.g2 = m.norm2.weight.detach().float().contiguous()
             self.be2 = m.norm2.bias.detach().float().contiguous()
@@ -114,12 +114,17 @@ class UNetEngine(TrainMixin):
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, tuple] = {}
         self._tape = None
+        # format of the 16-bit tensor-core operands (include/mcedm_b200.h `op_fmt`): inference defaults to fp16
+        # (11 significand bits: ~8x smaller operand-rounding error than bf16, same throughput; activations are
+        # normalised and weights O(1), so the narrower range is safe); training always runs bf16.
+        self.infer_fmt = 1
+        self._fmt = 1
         self._gn_coef: Dict[tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
         # WEIGHT_EPOCH counts in-place parameter updates made by the fused optimizer kernels (no autograd version bump)
-        return (WEIGHT_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
+        return (WEIGHT_EPOCH[0], self._fmt) + tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
 
     def pack(self, force: bool = False):
         key = self._param_key()
@@ -130,13 +135,14 @@ class UNetEngine(TrainMixin):
         if dev.type != "cuda":
             raise L.McedmError("mcedm_b200.DhariwalUNet parameters must live on a CUDA (sm_100) device; "
                                "there is no CPU path")
+        dt = torch.float16 if self._fmt else torch.bfloat16
         with torch.no_grad():
             for b in self.blocks_enc + self.blocks_dec:
-                b.pack()
+                b.pack(dt)
             cin = u.enc[self.conv_in_name]
             self.w_in = cin.weight.detach().float().contiguous()
             self.b_in = cin.bias.detach().float().contiguous()
-            self.w_out = pack_conv3x3(u.out_conv.weight, n_out_pad=16)
+            self.w_out = pack_conv3x3(u.out_conv.weight, n_out_pad=16, dtype=dt)
             self.b_out = torch.cat([u.out_conv.bias.detach().float(),
                                     torch.zeros(16 - u.out_channels, device=dev)]).contiguous()
             self.g_out = u.out_norm.weight.detach().float().contiguous()
@@ -193,7 +199,7 @@ class UNetEngine(TrainMixin):
         L.check(self.lib.mcedm_conv_igemm(
             L.ptr_array(srcs), len(srcs), L.int_array([s[0] for s in segs]), L.int_array([s[1] for s in segs]),
             L.int_array([s[2] for s in segs]), len(segs), L.ptr(w), L.ptr(bias), B, H, W, N, L.ptr(out), out_bf16,
-            L.ptr(res), res_mode, L.ptr(stats), st), "conv_igemm")
+            L.ptr(res), res_mode, L.ptr(stats), self._fmt, st), "conv_igemm")
 
     def _flat_geom(self, H, W):
         pitch, blk = C.c_int(0), C.c_int(0)
@@ -215,7 +221,7 @@ class UNetEngine(TrainMixin):
 
     def _conv_flat(self, src, w, bias, B, H, W, out, res, res_mode, stats, st):
         L.check(self.lib.mcedm_conv_flat(L.ptr(src), L.ptr(w), L.ptr(bias), B, H, W, 64, L.ptr(out), L.ptr(res),
-                                         res_mode, L.ptr(stats), st), "conv_flat")
+                                         res_mode, L.ptr(stats), self._fmt, st), "conv_flat")
 
     def _conv3x3(self, halo, ctr, w, bias, B, H, W, N, out, res, res_mode, stats, st, flat=None):
         if flat is not None:
@@ -241,15 +247,15 @@ class UNetEngine(TrainMixin):
             if len(halo) == 1:
                 L.check(self.lib.mcedm_conv_rows(L.ptr_array(halo), 1, L.ptr_array(ctr) if ctr else None, len(ctr),
                                                  L.ptr(w), L.ptr(bias), B, H, N, L.ptr(out), 0, L.ptr(res), res_mode,
-                                                 L.ptr(stats), st), "conv_rows")
+                                                 L.ptr(stats), self._fmt, st), "conv_rows")
                 return 4 * H
             if len(halo) == 2 and not ctr and res_mode == 0:
                 # K = 1152 weights (144 KB) cannot stay resident next to the row ring: split K over the two
                 # sources; the second pass accumulates onto the first pass's fp32 result in place.
                 L.check(self.lib.mcedm_conv_rows(L.ptr_array(halo[:1]), 1, None, 0, L.ptr(w[:9]), None, B, H, N,
-                                                 L.ptr(out), 0, None, 0, None, st), "conv_rows")
+                                                 L.ptr(out), 0, None, 0, None, self._fmt, st), "conv_rows")
                 L.check(self.lib.mcedm_conv_rows(L.ptr_array(halo[1:]), 1, None, 0, L.ptr(w[9:]), L.ptr(bias), B, H, N,
-                                                 L.ptr(out), 0, L.ptr(out), 1, L.ptr(stats), st), "conv_rows")
+                                                 L.ptr(out), 0, L.ptr(out), 1, L.ptr(stats), self._fmt, st), "conv_rows")
                 return 4 * H
         segs = [(i, dy, dx) for i in range(len(halo)) for (dy, dx) in _SEG9]
         segs += [(len(halo) + i, 0, 0) for i in range(len(ctr))]
@@ -264,7 +270,7 @@ class UNetEngine(TrainMixin):
             coef = self._gn_coef[(B, x.device.index)] = torch.empty(B, 128, device=x.device, dtype=torch.float32)
         L.check(self.lib.mcedm_gn_apply(L.ptr(x), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ss), ss_stride, 64,
                                         eps, act, resample, B, Hin, Win, parts, pitch, blk, L.ptr(out), L.ptr(raw),
-                                        L.ptr(meanrstd), L.ptr(coef), st), "gn_apply")
+                                        L.ptr(meanrstd), L.ptr(coef), self._fmt, st), "gn_apply")
         L.LAUNCHES[0] += 1      # finalize + streaming pass
 
     def _run_block(self, blk: _Block, inputs, B, H_in, W_in, ws, emb_stride, st, dev):
@@ -302,7 +308,7 @@ class UNetEngine(TrainMixin):
         if blk.attn:
             self._gn_apply(out, out_st, parts, blk.g2, blk.be2, None, 0, 0, 0, B, H, W, ws["a1"], None, st, eps)
             self._conv([ws["a1"]], [(0, 0, 0)], blk.wqkv, blk.bqkv, B, H, W, 192, ws["qkv"], 1, None, 0, None, st)
-            L.check(self.lib.mcedm_attention(L.ptr(ws["qkv"]), B, H * W, L.ptr(ws["att"]), None, st), "attention")
+            L.check(self.lib.mcedm_attention(L.ptr(ws["qkv"]), B, H * W, L.ptr(ws["att"]), None, self._fmt, st), "attention")
             out2, out2_st = self._tensor(ws, blk.name + ".attn", B, H, W, dev)
             self._conv([ws["att"]], [(0, 0, 0)], blk.wproj, blk.bproj, B, H, W, 64, out2, 0, out, 1, out2_st, st)
             out, out_st, parts = out2, out2_st, H * W // 128
@@ -371,6 +377,7 @@ class UNetEngine(TrainMixin):
     @torch.no_grad()
     def forward(self, x: torch.Tensor, noise_labels: torch.Tensor, cond: Optional[torch.Tensor]) -> torch.Tensor:
         x, nl, cond = self._check_inputs(x, noise_labels, cond)
+        self._fmt = self.infer_fmt
         self.pack()
         B, _, H, W = x.shape
         out = torch.empty(B, self.unet.out_channels, H, W, device=x.device, dtype=torch.float32)
@@ -407,15 +414,17 @@ class UNetEngine(TrainMixin):
 
     # ------------------------------------------------------------------ per-kernel timing (bench roofline)
     @torch.no_grad()
-    def profile_convs(self, x, noise_labels, cond, repeats: int = 3):
-        """CUDA-event time of every conv_igemm launch of one forward pass (on the launching stream).
-        Returns a list of dicts: N, n_seg, pixels, flops, ms (mean over `repeats`)."""
+    def profile_convs(self, x, noise_labels, cond, repeats: int = 3, with_gn: bool = False):
+        """CUDA-event time of every 3x3-conv launch (and, with_gn, every GroupNorm pass) of one forward pass, on the
+        launching stream.  Returns a list of dicts (kind 'conv': N, n_seg, pixels, H, flops, ms; kind 'gn': bytes, ms),
+        ms = mean over `repeats`."""
         x, nl, cond = self._check_inputs(x, noise_labels, cond)
+        self._fmt = self.infer_fmt
         self.pack()
         out = torch.empty(x.shape[0], self.unet.out_channels, x.shape[2], x.shape[3], device=x.device)
         self._launch_all(x, nl, cond, out)
         rec_all = []
-        orig = self._conv3x3
+        orig, orig_gn = self._conv3x3, self._gn_apply
 
         for _ in range(repeats):
             rec = []
@@ -426,19 +435,37 @@ class UNetEngine(TrainMixin):
                 e0.record()
                 parts = orig(halo, ctr, w, bias, B, H, W, N, o, res, res_mode, stats, st, flat=flat)
                 e1.record()
-                rec.append(dict(N=N, n_seg=n_seg, pixels=B * H * W, H=H, flops=2.0 * B * H * W * N * 64 * n_seg,
-                                ev=(e0, e1)))
+                rec.append(dict(kind="conv", N=N, n_seg=n_seg, pixels=B * H * W, H=H, res_mode=res_mode,
+                                flops=2.0 * B * H * W * N * 64 * n_seg, ev=(e0, e1)))
                 return parts
 
+            def timed_gn(x_, stats, parts, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out_, raw, st,
+                         eps=1e-5, flat=None, meanrstd=None):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                orig_gn(x_, stats, parts, gamma, beta, ss, ss_stride, act, resample, B, Hin, Win, out_, raw, st, eps,
+                        flat=flat, meanrstd=meanrstd)
+                e1.record()
+                n_in = B * Hin * Win * 64
+                n_out = n_in * 4 if resample == 1 else n_in // 4 if resample == 2 else n_in
+                rec.append(dict(kind="gn", H=Hin, resample=resample,
+                                bytes=4.0 * n_in + 2.0 * n_out + (2.0 * n_in if raw is not None else 0.0), ev=(e0, e1)))
+
             self._conv3x3 = timed
+            if with_gn:
+                self._gn_apply = timed_gn
             try:
                 self._launch_all(x, nl, cond, out)
             finally:
                 del self._conv3x3
+                if with_gn:
+                    del self._gn_apply
             torch.cuda.synchronize()
             rec_all.append(rec)
         res = []
         for i, r in enumerate(rec_all[0]):
             ms = sum(rr[i]["ev"][0].elapsed_time(rr[i]["ev"][1]) for rr in rec_all) / len(rec_all)
-            res.append(dict(N=r["N"], n_seg=r["n_seg"], pixels=r["pixels"], H=r["H"], flops=r["flops"], ms=ms))
+            d = {k: v for k, v in r.items() if k != "ev"}
+            d["ms"] = ms
+            res.append(d)
         return res

@@ -64,6 +64,7 @@ class TrainMixin:
 
     # ------------------------------------------------------------------ packed weights of the data-gradient convs
     def pack_train(self, force: bool = False):
+        self._fmt = 0                     # training runs bf16 operands throughout (gradients need the range)
         self.pack()
         if not force and getattr(self, "_packed_train_key", None) == self._packed_key:
             return
@@ -156,7 +157,7 @@ class TrainMixin:
             lse = self._t(tw, (blk.name, "lse"), (B, H * W), torch.float32)
             self._gn_apply(out, out_st, parts, blk.g2, blk.be2, None, 0, 0, 0, B, H, W, a2, None, st, eps, meanrstd=mr2)
             self._conv([a2], [(0, 0, 0)], blk.wqkv, blk.bqkv, B, H, W, 192, qkv, 1, None, 0, None, st)
-            L.check(self.lib.mcedm_attention(L.ptr(qkv), B, H * W, L.ptr(att), L.ptr(lse), st), "attention")
+            L.check(self.lib.mcedm_attention(L.ptr(qkv), B, H * W, L.ptr(att), L.ptr(lse), 0, st), "attention")
             out2, out2_st = self._act(tw, blk.name + ".attn", B, H, W)
             self._conv([att], [(0, 0, 0)], blk.wproj, blk.bproj, B, H, W, 64, out2, 0, out, 1, out2_st, st)
             rec["final_name"] = blk.name + ".attn"
@@ -166,6 +167,7 @@ class TrainMixin:
     def forward_train(self, x: torch.Tensor, noise_labels: torch.Tensor, cond: Optional[torch.Tensor]) -> torch.Tensor:
         """Forward pass that keeps what `backward` needs. Returns F_x [B,out_ch,H,W] fp32 (a fresh tensor)."""
         x, nl, cond = self._check_inputs(x, noise_labels, cond)
+        self._fmt = 0
         u = self.unet
         B, _, H, W = x.shape
         if (W >> 2) % 16 != 0:
@@ -287,6 +289,7 @@ class TrainMixin:
         T = self._tape
         if T is None:
             raise L.McedmError("backward() without a preceding forward_train()")
+        self._fmt = 0
         u, lib = self.unet, self.lib
         B, H, W, tw, tape = T["B"], T["H"], T["W"], T["tw"], T["tape"]
         dev = tw["dev"]

@@ -43,6 +43,7 @@ class TrainStepGraph:
     def _fwd(self):
         pl, lib, st = self.pl, L.lib(), L.stream_ptr()
         eng = pl.model.engine()
+        eng._fmt = 0
         eng.pack(force=True)
         eng.pack_train(force=True)
         B = self.x.shape[0]

@@ -11,5 +11,5 @@ w = pack_conv3x3(torch.randn(N, 64, 3, 3, device=dev) / 24)
 bias = torch.randn(N, device=dev); res = torch.randn(B, H, 128, N, device=dev)
 out = torch.empty(B, H, 128, N, device=dev); st = torch.empty(B * H, 4, 16, 2, device=dev)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
-    L.check(lib.mcedm_conv_rows(L.ptr_array([a]), 1, None, 0, L.ptr(w), L.ptr(bias), B, H, N, L.ptr(out), 0, L.ptr(res), 1, L.ptr(st), L.stream_ptr()))
+    L.check(lib.mcedm_conv_rows(L.ptr_array([a]), 1, None, 0, L.ptr(w), L.ptr(bias), B, H, N, L.ptr(out), 0, L.ptr(res), 1, L.ptr(st), 0, L.stream_ptr()))
 torch.cuda.synchronize(); print("ok")

@@ -98,10 +98,10 @@ def test_conv_dgrad_through_forward_kernels(L, dev, B, H, W):
     if W == 128:
         srcs = (C.c_void_p * 1)(dy.data_ptr())
         L.check(lib.mcedm_conv_rows(srcs, 1, None, 0, L.ptr(wp), None, B, H, 64, L.ptr(out), 0, None, 0, None,
-                                    L.stream_ptr()), "conv_rows")
+                                    0, L.stream_ptr()), "conv_rows")
     else:
         L.check(lib.mcedm_conv_flat(L.ptr(to_flat(L, dy)), L.ptr(wp), None, B, H, W, 64, L.ptr(out), None, 0, None,
-                                    L.stream_ptr()), "conv_flat")
+                                    0, L.stream_ptr()), "conv_flat")
     L.check_watchdog()
     a = torch.zeros(B, 64, H, W, device=dev, dtype=torch.float64, requires_grad=True)
     F.conv2d(a, w.double(), padding=1).backward(dy.double().permute(0, 3, 1, 2))
@@ -125,7 +125,7 @@ def test_gn_bwd_matches_autograd(L, dev, B, H, W, rs, act, use_ss, add0_mode, us
     out = torch.empty(B, Ho, Wo, 64, device=dev, dtype=torch.bfloat16)
     mr = torch.empty(B, 16, 2, device=dev)
     L.check(lib.mcedm_gn_apply(L.ptr(x), L.ptr(st), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64,
-                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, L.ptr(mr), L.ptr(torch.empty(B, 128, device=dev)), L.stream_ptr()))
+                               1e-5, act, rs, B, H, W, 0, 0, 0, L.ptr(out), None, L.ptr(mr), L.ptr(torch.empty(B, 128, device=dev)), 0, L.stream_ptr()))
     dy = torch.randn(B, Ho, Wo, 64, generator=g).to(dev)
     add0 = None
     if add0_mode is not None:
@@ -220,7 +220,7 @@ def test_attention_bwd_matches_autograd(L, dev, B, Lq, scale):
     d_out = torch.randn(B, Lq, 64, generator=g).to(dev).to(torch.bfloat16)
     out = torch.empty(B, Lq, 64, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, Lq, device=dev)
-    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), L.ptr(lse), L.stream_ptr()), "attention")
+    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), L.ptr(lse), 0, L.stream_ptr()), "attention")
     dvec = torch.empty(B, Lq, device=dev)
     dq, dk, dv = (torch.full((B, Lq, 64), float("nan"), device=dev, dtype=torch.bfloat16) for _ in range(3))
     L.check(lib.mcedm_attention_bwd(L.ptr(qkv), L.ptr(out), L.ptr(d_out), L.ptr(lse), B, Lq, L.ptr(dvec), L.ptr(dq),
@@ -231,7 +231,8 @@ def test_attention_bwd_matches_autograd(L, dev, B, Lq, scale):
     s = q @ k.transpose(1, 2) / 8.0
     ref = torch.softmax(s, dim=2) @ v
     ref.backward(d_out.double())
-    assert rel_l2(lse, torch.logsumexp(s, dim=2) * 1.4426950408889634) < 1e-5
+    # the row sum is taken over the ROUNDED weights (what P V actually sums): lse is exact to ~2^-9 / sqrt(L)
+    assert rel_l2(lse, torch.logsumexp(s, dim=2) * 1.4426950408889634) < 1e-4
     rq, rk, rv = x.grad.split(64, dim=2)
     assert rel_l2(dv.float(), rv) < 8e-3        # bf16 P, bf16 output
     assert rel_l2(dq.float(), rq) < 1.5e-2      # bf16 dS (difference of nearly equal terms), bf16 output
