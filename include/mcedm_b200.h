@@ -96,6 +96,66 @@ MCEDM_API int mcedm_conv_flat(const void* src_flat, const void* w_packed, const 
                               void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* K1f  GroupNorm-fused convolutions with 16-bit activations (inference path)                     */
+/*      (adm_blocks.py:161 / :166 / :403 silu(norm(x)[*(1+scale)+shift]) folded into Conv2d.forward :65-81)  */
+/* -------------------------------------------------------------------------------------------- */
+/*
+ * Inference keeps every activation of the trunk in HBM as a RAW 16-bit tensor (op_fmt: fp16 by default) plus the
+ * GroupNorm partial sums its producer emitted.  The consumer conv normalises on the fly: mcedm_gn_coef folds the
+ * partial sums of a tensor into per-(sample, channel) coefficients (a | b), and the *_fused convs apply
+ * y = silu(a*x + b) to each input row / chunk in shared memory right after its TMA load (transform warps), so the
+ * normalised operand never exists in HBM.  Zero padding is preserved (padding pixels are not transformed).
+ *
+ * mcedm_conv_rows_fused (W == 128):
+ *   halo_src[i], halo_coef[i]  n_halo (1..2) raw 16-bit NHWC [B,H,128,64] tensors and their fp32 [B][128] coefficients
+ *   ctr_src[i]                 n_ctr (0..2) raw 16-bit tensors entering with the centre tap only, NOT transformed
+ *                              (1x1 skip projection of the raw block input, adm_blocks.py:150-151)
+ *   w_packed                   16-bit [9*n_halo + n_ctr][n_total][64]; this launch computes output channels
+ *                              [n_off, n_off + N) of n_total (N = 16 | 32 | 64): a 128-channel conv0 runs as two N = 32
+ *                              launches whose 72 KB of weights stay resident
+ *   bias fp32 [n_total] | NULL; out [B,H,128,n_total] 16-bit (out_16 = 1) or fp32 (0)
+ *   res16, res_mode            0 none | 1 16-bit [B,H,128,n_total] | 2 16-bit half-resolution tensor, nearest-x2:
+ *                              dense [B,H/2,64,n_total] (res_pitch = 0) or padded-flat (res_pitch, res_blk)
+ *   halo_coef == NULL (or all entries NULL): the halo sources are already-normalised operands (no transform);
+ *   likewise coef == NULL in mcedm_conv_flat_fused (the conv0 of an up/down block reads mcedm_gn_apply16 output)
+ *   stats_partial              NULL or fp32 [B*H][4][n_total/4][2] (this launch fills groups n_off/4 ...)
+ * mcedm_conv_flat_fused (W <= 64): src/out/res in the padded-flat layout of mcedm_flat_geometry
+ *   out_flat   16-bit [B*blk][64] (out_f32 = 0) or fp32 [B*blk][64] (out_f32 = 1, K-split partial); only data
+ *              positions are written (padding must have been zeroed once by the owner)
+ *   res        res_mode 1: same-resolution padded-flat, 16-bit or fp32 (res_f32 = 1);
+ *              2: 16-bit at half resolution, 3: 16-bit at double resolution (2x2 mean); for 2/3 the residual tensor's
+ *              own layout is given by res_pitch/res_blk (0,0 = dense NHWC, e.g. the 128-wide level)
+ *   stats_partial  NULL or fp32 [B*blk/128][4][16][2]
+ * mcedm_conv_igemm16: mcedm_conv_igemm with a 16-bit output and a prefetched 16-bit residual (res_mode 0 | 1);
+ *   io_pitch/io_blk > 0 place out and res in the padded-flat layout (sources stay dense).
+ * mcedm_gn_apply16: stand-alone apply for the places that still need a materialised operand (2x resampling in front
+ *   of conv0, norm2 in front of the qkv projection): x16 raw 16-bit, dense (in_pitch = 0) or padded-flat; coef from
+ *   mcedm_gn_coef; act / resample / out_pitch / out_blk as in mcedm_gn_apply.
+ * mcedm_conv_in16: mcedm_conv_in writing a 16-bit NHWC tensor.
+ */
+MCEDM_API int mcedm_gn_coef(const float* partial, int parts_per_img, const float* gamma, const float* beta,
+                            const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int B,
+                            int Hin, int Win, float* coef_out, float* meanrstd_out, void* stream);
+MCEDM_API int mcedm_gn_apply16(const void* x16, int in_pitch, int in_blk, const float* coef, int act, int resample,
+                               int B, int Hin, int Win, int out_pitch, int out_blk, void* out16, int op_fmt,
+                               void* stream);
+MCEDM_API int mcedm_conv_rows_fused(const void* const* halo_src, const float* const* halo_coef, int n_halo,
+                                    const void* const* ctr_src, int n_ctr, const void* w_packed, const float* bias,
+                                    int B, int H, int N, int n_off, int n_total, void* out, int out_16,
+                                    const void* res16, int res_mode, int res_pitch, int res_blk,
+                                    float* stats_partial, int op_fmt, void* stream);
+MCEDM_API int mcedm_conv_flat_fused(const void* src_flat16, const float* coef, const void* w_packed, const float* bias,
+                                    int B, int H, int W, int N, void* out_flat, int out_f32, const void* res,
+                                    int res_mode, int res_f32, int res_pitch, int res_blk, float* stats_partial,
+                                    int op_fmt, void* stream);
+MCEDM_API int mcedm_conv_igemm16(const void* const* src, int n_src, const int* seg_src, const int* seg_dy,
+                                 const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
+                                 int W, int N, void* out16, const void* res16, int res_mode, int io_pitch, int io_blk,
+                                 float* stats_partial, int op_fmt, void* stream);
+MCEDM_API int mcedm_conv_in16(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
+                              int B, int H, int W, void* out16, float* stats_partial, int op_fmt, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* K2  GroupNorm statistics / fused GroupNorm + scale-shift + SiLU + resample                     */
 /*     (models/adm_blocks.py:86-97 GroupNorm; :161, :163-166, :175, :403 call sites)              */
 /* -------------------------------------------------------------------------------------------- */

@@ -191,7 +191,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
         tmem_wait_ld();
-        uint8_t* atom_row = prow + (c >> 1) * kTile;
+        const uint32_t atom_row = smem_u32(prow) + (c >> 1) * kTile;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 o;
@@ -210,7 +210,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
             }
           }
           const int unit = ((c & 1) * 4 + u) ^ (row & 7);
-          *reinterpret_cast<uint4*>(atom_row + unit * 16) = o;
+          sts128(atom_row + unit * 16, o);
         }
       }
       tc_fence_before();

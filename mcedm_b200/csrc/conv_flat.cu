@@ -18,6 +18,13 @@
 //
 // Warp roles / epilogue exactly as conv_rows.cu (8 epilogue warps, 4-deep TMEM accumulator ring,
 // per-(tile, lane quarter) GroupNorm partial sums).
+//
+// FUSED variant (inference, mcedm_conv_flat_fused): as in conv_rows.cu, the source is the RAW 16-bit activation in
+// the padded flat layout and four transform warps apply y = silu(a[b,c]*x + b[b,c]) (GroupNorm + scale/shift + SiLU,
+// coefficients from mcedm_gn_coef) to every data position of a chunk in shared memory before its first MMA; padding
+// positions are skipped so their zeros survive.  Output and residual are padded-flat too (output position == tile
+// row position, so the epilogue stores are trivially coalesced): 16-bit, or fp32 for the K-split partial sum of the
+// 128-channel decoder convs (pass 1 writes an fp32 partial, pass 2 adds it as its residual).
 #include "ptx.cuh"
 #include "runtime.cuh"
 #include "../../include/mcedm_b200.h"
@@ -40,16 +47,22 @@ struct FlatParams {
   float* stats;            // [total_tiles][4][N/4][2]
   int fmt;                 // 16-bit operand format: 0 bf16, 1 fp16
   unsigned int* err;
+  // ---- FUSED variant only
+  const float* coef;       // fp32 [B][128] = (a | b) of y = silu(a*x + b)
+  int out_f32;             // out is fp32 padded-flat [B*blk][N] (K-split partial) instead of 16-bit padded-flat
+  int res_f32;             // res (mode 1 only) is fp32 padded-flat
+  int res_pitch, res_blk;  // layout of the 16-bit residual tensor at ITS resolution: 0,0 dense NHWC, else padded-flat
 };
 
-template <int N>
+template <int N, bool FUSED>
 struct FlatCfg {
   static constexpr int CH = 32;
   static constexpr int NCH = N / CH;
   static constexpr int U = 8;
   static constexpr int W_SEG_BYTES = N * 128;
   static constexpr int EPI_WARPS = 4 * NCH;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int XF_WARPS = FUSED ? 4 : 0;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
   static constexpr int ACC_BUFS = 4;
   static constexpr int TMEM_COLS = (ACC_BUFS * N <= 256) ? 256 : 512;
@@ -79,11 +92,59 @@ __device__ __forceinline__ float4 flat_residual(const FlatParams& p, int N, int 
   }
 }
 
-template <int N>
-__global__ void __launch_bounds__(FlatCfg<N>::THREADS, 1)
+__device__ __forceinline__ float4 flat_unpack4(uint2 v, int fmt) {
+  if (fmt) {
+    const float2 lo = unpack_f16x2(v.x), hi = unpack_f16x2(v.y);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+}
+// pixel index of (b, y, x) in a 16-bit tensor of height Hs / width Ws that is dense (pitch 0) or padded-flat
+__device__ __forceinline__ long long flat_index(int pitch, int blk, int b, int y, int x, int Hs, int Ws) {
+  if (pitch > 0) return (long long)b * blk + (long long)(y + 1) * pitch + x;
+  return ((long long)b * Hs + y) * Ws + x;
+}
+// residual of the fused variant: 16-bit (any mode) or fp32 padded-flat (mode 1, the K-split partial sum)
+__device__ __forceinline__ float4 flat_residual16(const FlatParams& p, int N, int b, int y, int x, int c0, long long pos) {
+  const uint16_t* r16 = reinterpret_cast<const uint16_t*>(p.res);
+  if (p.res_mode == 1) {
+    if (p.res_f32) return *reinterpret_cast<const float4*>(p.res + pos * N + c0);
+    return flat_unpack4(*reinterpret_cast<const uint2*>(r16 + pos * N + c0), p.fmt);
+  } else if (p.res_mode == 2) {
+    const long long i = flat_index(p.res_pitch, p.res_blk, b, y >> 1, x >> 1, p.H >> 1, p.W >> 1);
+    return flat_unpack4(*reinterpret_cast<const uint2*>(r16 + i * N + c0), p.fmt);
+  } else {
+    const int Hs = p.H << 1, Ws = p.W << 1;
+    const long long i00 = flat_index(p.res_pitch, p.res_blk, b, 2 * y, 2 * x, Hs, Ws);
+    const long long rs = p.res_pitch > 0 ? p.res_pitch : Ws;
+    const float4 r00 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + i00 * N + c0), p.fmt);
+    const float4 r01 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + 1) * N + c0), p.fmt);
+    const float4 r10 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + rs) * N + c0), p.fmt);
+    const float4 r11 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + rs + 1) * N + c0), p.fmt);
+    return make_float4(0.25f * ((r00.x + r01.x) + (r10.x + r11.x)), 0.25f * ((r00.y + r01.y) + (r10.y + r11.y)),
+                       0.25f * ((r00.z + r01.z) + (r10.z + r11.z)), 0.25f * ((r00.w + r01.w) + (r10.w + r11.w)));
+  }
+}
+// 2 raw 16-bit values -> silu(a*x + b) (same arithmetic as conv_rows.cu xf_pair)
+__device__ __forceinline__ uint32_t flat_xf_pair(uint32_t v, float a0, float b0, float a1, float b1, int fmt) {
+  float x0, x1;
+  if (fmt) {
+    const float2 f = unpack_f16x2(v);
+    x0 = f.x;
+    x1 = f.y;
+  } else {
+    x0 = bf16_lo(v);
+    x1 = bf16_hi(v);
+  }
+  // the coefficients arrive pre-halved: h = (a*x + b) / 2, silu(a*x + b) = h * (1 + tanh(h))
+  return pack_op2(silu_from_half_arg(fmaf(x0, a0, b0)), silu_from_half_arg(fmaf(x1, a1, b1)), fmt);
+}
+
+template <int N, bool FUSED>
+__global__ void __launch_bounds__(FlatCfg<N, FUSED>::THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a,
                  const FlatParams p) {
-  using Cfg = FlatCfg<N>;
+  using Cfg = FlatCfg<N, FUSED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.n_slots;
@@ -96,7 +157,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   uint64_t* acc_empty = acc_full + Cfg::ACC_BUFS;
   uint64_t* c_full = acc_empty + Cfg::ACC_BUFS;                 // S
   uint64_t* c_empty = c_full + S;                               // S
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + S);
+  uint64_t* c_ready = c_empty + S;                              // S (FUSED: chunk transformed, visible to the MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_ready + S);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +177,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     for (int i = 0; i < S; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 1);
+      mbar_init(&c_ready[i], FUSED ? 32 * Cfg::XF_WARPS : 1);
     }
     fence_barrier_init();
   }
@@ -158,7 +221,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         mbar_wait(&acc_empty[buf], aph ^ 1u, p.err, 0x3300 + buf);
         while (waited < j + 3) {
           const uint32_t slot = (uint32_t)waited % (uint32_t)S, ph = ((uint32_t)waited / (uint32_t)S) & 1u;
-          mbar_wait(&c_full[slot], ph, p.err, 0x3400 + slot);
+          mbar_wait(FUSED ? &c_ready[slot] : &c_full[slot], ph, p.err, 0x3400 + slot);
           ++waited;
         }
         tc_fence_after();
@@ -190,17 +253,40 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         __syncwarp();
       }
     }
-  } else {
+  } else if (!FUSED || warp < 2 + Cfg::EPI_WARPS) {
     // ======================================= epilogue =======================================
     const int q = warp & 3;
     const int ew = warp - 2;
     const int ch = ew >> 2;
-    uint8_t* my_stage = stage_smem + ew * (32 * Cfg::CH * 4);
+    const uint32_t my_stage = smem_u32(stage_smem) + ew * (32 * Cfg::CH * 4);
     const int unit = lane & 7;
     const int row_in_it = lane >> 3;
     const int c0 = ch * Cfg::CH + unit * 4;
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bz = *reinterpret_cast<const float4*>(p.bias + c0);
+    // FUSED, 16-bit residual at the same or half resolution (the common cases): the residual of tile j+1 is requested
+    // before tile j is processed (raw register double buffer), otherwise every tile pays the DRAM latency in full.
+    const bool pre = FUSED && ((p.res_mode == 1 && !p.res_f32) || p.res_mode == 2);
+    uint2 rh_n[8];
+    auto prefetch = [&](int j) {
+      const long long tile = t_begin + j;
+      const int b = (int)(tile / p.tiles_per_img);
+      const int pos0 = (int)(tile - (long long)b * p.tiles_per_img) * 128 + q * 32;
+      const uint16_t* r16 = reinterpret_cast<const uint16_t*>(p.res);
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        const int pos = pos0 + itr * 4 + row_in_it;
+        const int row = pos / p.P;
+        const int x = pos - row * p.P;
+        rh_n[itr] = make_uint2(0u, 0u);
+        if ((row >= 1) && (row <= p.H) && (x < p.W)) {
+          const long long i = p.res_mode == 1 ? tile * 128 + q * 32 + itr * 4 + row_in_it
+                                              : flat_index(p.res_pitch, p.res_blk, b, (row - 1) >> 1, x >> 1, p.H >> 1, p.W >> 1);
+          rh_n[itr] = *reinterpret_cast<const uint2*>(r16 + i * N + c0);
+        }
+      }
+    };
+    if (pre && n_tiles > 0) prefetch(0);
     for (int j = 0; j < n_tiles; ++j) {
       const long long tile = t_begin + j;
       const uint32_t buf = (uint32_t)j % Cfg::ACC_BUFS, aph = ((uint32_t)j / Cfg::ACC_BUFS) & 1u;
@@ -215,10 +301,19 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int row = pos / p.P;
         const int x = pos - row * p.P;
         const bool valid = (row >= 1) && (row <= p.H) && (x < p.W);
-        opix[itr] = valid ? (((long long)b * p.H + (row - 1)) * p.W + x) : -1;
-        rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && p.res_mode != 0) rr[itr] = flat_residual(p, N, b, row - 1, x, c0);
+        if constexpr (FUSED) {
+          const long long gpos = tile * 128 + q * 32 + itr * 4 + row_in_it;    // padded-flat output position
+          opix[itr] = valid ? gpos : -1;
+          rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pre) rr[itr] = flat_unpack4(rh_n[itr], p.fmt);
+          else if (valid && p.res_mode != 0) rr[itr] = flat_residual16(p, N, b, row - 1, x, c0, gpos);
+        } else {
+          opix[itr] = valid ? (((long long)b * p.H + (row - 1)) * p.W + x) : -1;
+          rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && p.res_mode != 0) rr[itr] = flat_residual(p, N, b, row - 1, x, c0);
+        }
       }
+      if (pre && j + 1 < n_tiles) prefetch(j + 1);
       mbar_wait(&acc_full[buf], aph, p.err, 0x3500 + buf);
       tc_fence_after();
       uint32_t v[32];
@@ -229,8 +324,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int pj = jj ^ (lane & 7);
-        *reinterpret_cast<uint4*>(my_stage + lane * 128 + pj * 16) =
-            make_uint4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+        sts128(my_stage + lane * 128 + pj * 16, make_uint4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]));
       }
       __syncwarp();
       float s1 = 0.f, s2 = 0.f;
@@ -238,13 +332,20 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       for (int itr = 0; itr < 8; ++itr) {
         const int row = itr * 4 + row_in_it;
         const int pu = unit ^ (row & 7);
-        float4 a = *reinterpret_cast<const float4*>(my_stage + row * 128 + pu * 16);
+        float4 a = lds128f(my_stage + row * 128 + pu * 16);
         if (opix[itr] >= 0) {
           a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
           a.x += rr[itr].x; a.y += rr[itr].y; a.z += rr[itr].z; a.w += rr[itr].w;
           s1 += (a.x + a.y) + (a.z + a.w);
           s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
-          *reinterpret_cast<float4*>(p.out + opix[itr] * N + c0) = a;
+          if (FUSED && !p.out_f32) {
+            uint2 o;
+            o.x = pack_op2(a.x, a.y, p.fmt);
+            o.y = pack_op2(a.z, a.w, p.fmt);
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + opix[itr] * N + c0) = o;
+          } else {
+            *reinterpret_cast<float4*>(p.out + opix[itr] * N + c0) = a;
+          }
         }
       }
       if (p.stats) {
@@ -257,6 +358,71 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           *reinterpret_cast<float2*>(p.stats + ((tile * 4 + q) * (N / 4) + ch * 8 + lane) * 2) = make_float2(s1, s2);
       }
       __syncwarp();
+    }
+  } else {
+    // ============================ GroupNorm + SiLU transform (FUSED) ============================
+    // thread t owns the logical 16-byte chunk jc = t & 7 (channels 8jc .. 8jc+7) of positions (t >> 3) + 16 i of every
+    // 128-position chunk; physical 16-byte slot = jc ^ (position & 7) (SWIZZLE_128B, 1 KB-aligned chunk slots).
+    const int t = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    const int jc = t & 7;
+    const int prow = t >> 3;
+    int cur_b = -1;
+    float ca[8], cb[8];
+    for (int k = 0; k < n_tiles + 2; ++k) {
+      const uint32_t slot = (uint32_t)k % (uint32_t)S, ph = ((uint32_t)k / (uint32_t)S) & 1u;
+      mbar_wait(&c_full[slot], ph, p.err, 0x3600 + slot);
+      const long long g = t_begin - 1 + k;                 // global chunk; outside the tensor = TMA zero fill
+      if (g >= 0 && g < p.total_tiles && p.coef != nullptr) {
+        const int b = (int)(g / p.tiles_per_img);
+        const int base_pos = (int)(g - (long long)b * p.tiles_per_img) * 128;
+        if (b != cur_b) {
+          cur_b = b;
+          const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)b * 128 + jc * 8);
+          const float4 a0 = __ldg(cf), a1 = __ldg(cf + 1), b0 = __ldg(cf + 16), b1 = __ldg(cf + 17);
+          ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+          cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ca[e] *= 0.5f;
+            cb[e] *= 0.5f;
+          }
+        }
+        const uint32_t base = smem_u32(ring) + slot * kChunkBytes;
+        const bool mirror = slot < 2 && k >= S;
+        uint4 v[8];
+        bool ok[8];
+        // (row, column) of this thread's first position; the next ones are 16 positions apart (P >= 24 > 16: at most
+        // one row wrap per step), so one division per chunk instead of eight
+        int row = (base_pos + prow) / p.P;
+        int x = (base_pos + prow) - row * p.P;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pi = prow + 16 * i;
+          ok[i] = (row >= 1) && (row <= p.H) && (x < p.W);
+          v[i] = lds128(base + pi * 128 + ((jc ^ (pi & 7)) << 4));
+          x += 16;
+          if (x >= p.P) {
+            x -= p.P;
+            ++row;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int pi = prow + 16 * i;
+          if (ok[i]) {
+            uint4 o;
+            o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], p.fmt);
+            o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], p.fmt);
+            o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], p.fmt);
+            o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], p.fmt);
+            const int off = pi * 128 + ((jc ^ (pi & 7)) << 4);
+            sts128(base + off, o);
+            if (mirror) sts128(base + S * kChunkBytes + off, o);
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      mbar_arrive(&c_ready[slot]);
     }
   }
 
@@ -278,6 +444,37 @@ extern "C" int mcedm_flat_geometry(int H, int W, int* pitch, int* block_position
   *block_positions = ((H + 2) * P + 127) / 128 * 128;
   return 0;
 }
+
+namespace mcedm {
+template <bool FUSED>
+static int launch_flat(FlatParams p, const void* src_flat, const void* w_packed, int B, int blk, cudaStream_t st) {
+  using Cfg = FlatCfg<64, FUSED>;
+  const int N = 64;
+  p.err = watchdog_ptr();
+  MCEDM_REQUIRE(p.err != nullptr, "conv_flat: cannot allocate the watchdog word");
+  MCEDM_REQUIRE((long long)B * blk < (1LL << 31), "conv_flat: tensor too large for 32-bit TMA coordinates");
+  const int fixed = 1024 + 9 * Cfg::W_SEG_BYTES + Cfg::STAGE_BYTES + 768;
+  int slots = (232448 - fixed) / kChunkBytes - 2;
+  if (slots > 6) slots = 6;
+  MCEDM_REQUIRE(slots >= 3, "conv_flat: shared memory budget");
+  p.n_slots = slots;
+  const int smem = fixed + (slots + 2) * kChunkBytes;
+  CUtensorMap tm_w, tm_a;
+  int rc = make_tmap_rows64_bf16(&tm_w, w_packed, 9LL * N, N);
+  if (rc) return rc;
+  rc = make_tmap_rows64_bf16(&tm_a, src_flat, (long long)B * blk, 128);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_flat_kernel<64, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv_flat_kernel<64, FUSED><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(tm_w, tm_a, p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace mcedm
 
 extern "C" int mcedm_conv_flat(const void* src_flat, const void* w_packed, const float* bias, int B, int H, int W, int N,
                                float* out, const float* res, int res_mode, float* stats_partial, int op_fmt,
@@ -301,28 +498,37 @@ extern "C" int mcedm_conv_flat(const void* src_flat, const void* w_packed, const
   p.res_mode = res_mode;
   p.stats = stats_partial;
   p.fmt = op_fmt ? 1 : 0;
-  p.err = watchdog_ptr();
-  MCEDM_REQUIRE(p.err != nullptr, "conv_flat: cannot allocate the watchdog word");
-  MCEDM_REQUIRE((long long)B * blk < (1LL << 31), "conv_flat: tensor too large for 32-bit TMA coordinates");
-  using Cfg = FlatCfg<64>;
-  const int fixed = 1024 + 9 * Cfg::W_SEG_BYTES + Cfg::STAGE_BYTES + 512;
-  int slots = (232448 - fixed) / kChunkBytes - 2;
-  if (slots > 6) slots = 6;
-  MCEDM_REQUIRE(slots >= 3, "conv_flat: shared memory budget");
-  p.n_slots = slots;
-  const int smem = fixed + (slots + 2) * kChunkBytes;
-  CUtensorMap tm_w, tm_a;
-  rc = make_tmap_rows64_bf16(&tm_w, w_packed, 9LL * N, N);
+  return launch_flat<false>(p, src_flat, w_packed, B, blk, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mcedm_conv_flat_fused(const void* src_flat16, const float* coef, const void* w_packed, const float* bias,
+                                     int B, int H, int W, int N, void* out_flat, int out_f32, const void* res,
+                                     int res_mode, int res_f32, int res_pitch, int res_blk, float* stats_partial,
+                                     int op_fmt, void* stream) {
+  using namespace mcedm;
+  int P = 0, blk = 0;
+  int rc = mcedm_flat_geometry(H, W, &P, &blk);
   if (rc) return rc;
-  rc = make_tmap_rows64_bf16(&tm_a, src_flat, (long long)B * blk, 128);
-  if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MCEDM_CUDA(cudaFuncSetAttribute(conv_flat_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
-  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_flat_kernel<64><<<(unsigned)grid, Cfg::THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_w, tm_a, p);
-  MCEDM_CUDA(cudaGetLastError());
-  return 0;
+  MCEDM_REQUIRE(N == 64, "conv_flat_fused: N=%d unsupported (64)", N);
+  MCEDM_REQUIRE(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || res != nullptr), "conv_flat_fused: bad residual mode");
+  MCEDM_REQUIRE(!res_f32 || res_mode == 1, "conv_flat_fused: an fp32 residual must be same-resolution padded-flat");
+  FlatParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = H;
+  p.W = W;
+  p.P = P;
+  p.tiles_per_img = blk / 128;
+  p.total_tiles = (long long)B * p.tiles_per_img;
+  p.bias = bias;
+  p.out = reinterpret_cast<float*>(out_flat);
+  p.out_f32 = out_f32 ? 1 : 0;
+  p.res = reinterpret_cast<const float*>(res);
+  p.res_mode = res_mode;
+  p.res_f32 = res_f32 ? 1 : 0;
+  p.res_pitch = res_pitch;
+  p.res_blk = res_blk;
+  p.stats = stats_partial;
+  p.fmt = op_fmt ? 1 : 0;
+  p.coef = coef;
+  return launch_flat<true>(p, src_flat16, w_packed, B, blk, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -50,6 +50,9 @@ struct ConvParams {
   int res_mode;           // 0 none, 1 same resolution, 2 nearest-x2 upsample of res, 3 2x2 mean of res
   float* stats;           // [n_tiles][N/4][2] (sum, sum of squares of the stored values) or nullptr
   unsigned int* err;
+  // ---- 16-bit I/O variant (mcedm_conv_igemm16, inference)
+  int res16;              // residual (res_mode 1) is 16-bit in the operand format and is prefetched
+  int io_pitch, io_blk;   // > 0: out and res are padded-flat (conv_flat.cu layout) instead of dense NHWC
 };
 
 template <int N>
@@ -173,7 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     // ======================================= epilogue =======================================
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int ew = warp - 2;             // staging slot
-    uint8_t* my_stage = stage_smem + ew * (32 * Cfg::CH * 4);
+    const uint32_t my_stage = smem_u32(stage_smem) + ew * (32 * Cfg::CH * 4);
     const int unit = lane % Cfg::U;
     const int row_in_it = lane / Cfg::U;
     constexpr int ROWS_PER_IT = 32 / Cfg::U;
@@ -182,11 +185,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
       const uint32_t aph = (tcount >> 1) & 1u;
+      const long long pix0 = (long long)tile * kTileM + q * 32;
+      // output / residual pixel index of this lane's rows (dense, or padded-flat for the 16-bit I/O variant)
+      long long opix[Cfg::U];
+#pragma unroll
+      for (int itr = 0; itr < Cfg::U; ++itr) {
+        const long long pix = pix0 + itr * ROWS_PER_IT + row_in_it;
+        opix[itr] = pix;
+        if (p.io_pitch > 0) {
+          const int b = (int)(pix / HW);
+          const int rem = (int)(pix - (long long)b * HW);
+          const int y = rem / p.W;
+          opix[itr] = (long long)b * p.io_blk + (long long)(y + 1) * p.io_pitch + (rem - y * p.W);
+        }
+      }
+      // 16-bit residual prefetch (independent of the accumulator); N <= 64 only
+      constexpr int NPRE = (N <= 64) ? Cfg::NCH : 1;
+      uint2 rh[NPRE][Cfg::U];
+      if (N <= 64 && p.res16 && p.res_mode == 1) {
+#pragma unroll
+        for (int ch = 0; ch < NPRE; ++ch)
+#pragma unroll
+          for (int itr = 0; itr < Cfg::U; ++itr)
+            rh[ch][itr] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res) + opix[itr] * N +
+                                                          ch * Cfg::CH + unit * 4);
+      }
       mbar_wait(&acc_full[buf], aph, p.err, 0x500 + buf);
       tc_fence_after();
       float* my_stat = stat_smem + ((tcount & 1u) * 4 + ew) * (N / 4) * 2;
-      const long long pix0 = (long long)tile * kTileM + q * 32;
-#pragma unroll 1
+      constexpr int kChUnroll = (N <= 64) ? Cfg::NCH : 1;
+#pragma unroll kChUnroll
       for (int ch = 0; ch < Cfg::NCH; ++ch) {
         uint32_t v[Cfg::CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_STRIDE + ch * Cfg::CH;
@@ -200,8 +228,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
 #pragma unroll
         for (int j = 0; j < Cfg::U; ++j) {
           const int pj = j ^ (lane & (Cfg::U - 1));
-          *reinterpret_cast<uint4*>(my_stage + lane * (Cfg::CH * 4) + pj * 16) =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          sts128(my_stage + lane * (Cfg::CH * 4) + pj * 16, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
         __syncwarp();
         const int c0 = ch * Cfg::CH + unit * 4;
@@ -212,12 +239,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
         for (int itr = 0; itr < Cfg::U; ++itr) {
           const int row = itr * ROWS_PER_IT + row_in_it;
           const int pu = unit ^ (row & (Cfg::U - 1));
-          float4 a = *reinterpret_cast<const float4*>(my_stage + row * (Cfg::CH * 4) + pu * 16);
+          float4 a = lds128f(my_stage + row * (Cfg::CH * 4) + pu * 16);
           a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
           const long long pix = pix0 + row;
           if (p.res_mode == 1) {
-            const float4 r = *reinterpret_cast<const float4*>(p.res + pix * N + c0);
-            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            if (N <= 64 && p.res16) {
+              const uint2 hv = rh[N <= 64 ? ch : 0][itr];
+              float2 lo, hi;
+              if (p.fmt) {
+                lo = unpack_f16x2(hv.x);
+                hi = unpack_f16x2(hv.y);
+              } else {
+                lo = make_float2(bf16_lo(hv.x), bf16_hi(hv.x));
+                hi = make_float2(bf16_lo(hv.y), bf16_hi(hv.y));
+              }
+              a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
+            } else {
+              const float4 r = *reinterpret_cast<const float4*>(p.res + pix * N + c0);
+              a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            }
           } else if (p.res_mode != 0) {
             const int b = (int)(pix / HW);
             const int rem = (int)(pix - (long long)b * HW);
@@ -246,9 +286,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
             uint2 o;
             o.x = pack_op2(a.x, a.y, p.fmt);
             o.y = pack_op2(a.z, a.w, p.fmt);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * N + c0) = o;
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix[itr] * N + c0) = o;
           } else {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * N + c0) = a;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix[itr] * N + c0) = a;
           }
         }
         if (p.stats) {
@@ -310,11 +350,13 @@ static int launch_conv(const CUtensorMap& tm_w, const CUtensorMap* tm_a, const C
 
 }  // namespace mcedm
 
-extern "C" int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg_src, const int* seg_dy,
-                                const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
-                                int W, int N, void* out, int out_bf16, const float* res, int res_mode,
-                                float* stats_partial, int op_fmt, void* stream) {
+static int conv_igemm_impl(const void* const* src, int n_src, const int* seg_src, const int* seg_dy,
+                           const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
+                           int W, int N, void* out, int out_bf16, const float* res, int res_mode,
+                           float* stats_partial, int op_fmt, int res16, int io_pitch, int io_blk, void* stream) {
   using namespace mcedm;
+  MCEDM_REQUIRE(!res16 || (res_mode == 1 && N <= 64), "conv_igemm16: a 16-bit residual needs res_mode 1 and N <= 64");
+  MCEDM_REQUIRE(io_pitch == 0 || (io_pitch >= W && io_blk >= (H + 2) * io_pitch), "conv_igemm16: bad padded-flat geometry");
   MCEDM_REQUIRE(n_src >= 1 && n_src <= 4, "conv_igemm: n_src=%d not in 1..4", n_src);
   MCEDM_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, "conv_igemm: n_seg=%d not in 1..%d", n_seg, kMaxSeg);
   MCEDM_REQUIRE(W >= 8 && W <= 128 && (128 % W) == 0, "conv_igemm: W=%d must divide 128", W);
@@ -345,6 +387,9 @@ extern "C" int mcedm_conv_igemm(const void* const* src, int n_src, const int* se
   p.res = res;
   p.res_mode = res_mode;
   p.stats = stats_partial;
+  p.res16 = res16 ? 1 : 0;
+  p.io_pitch = io_pitch;
+  p.io_blk = io_blk;
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "conv_igemm: cannot allocate the watchdog word (no CUDA device?)");
 
@@ -364,4 +409,21 @@ extern "C" int mcedm_conv_igemm(const void* const* src, int n_src, const int* se
     case 192: return launch_conv<192>(tm_w, tm_a, p, st);
     default: return fail(-1, "conv_igemm: N=%d unsupported (16, 64, 128, 192)", N);
   }
+}
+
+extern "C" int mcedm_conv_igemm(const void* const* src, int n_src, const int* seg_src, const int* seg_dy,
+                                const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
+                                int W, int N, void* out, int out_bf16, const float* res, int res_mode,
+                                float* stats_partial, int op_fmt, void* stream) {
+  return conv_igemm_impl(src, n_src, seg_src, seg_dy, seg_dx, n_seg, w_packed, bias, B, H, W, N, out, out_bf16, res,
+                         res_mode, stats_partial, op_fmt, 0, 0, 0, stream);
+}
+
+extern "C" int mcedm_conv_igemm16(const void* const* src, int n_src, const int* seg_src, const int* seg_dy,
+                                  const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
+                                  int W, int N, void* out16, const void* res16, int res_mode, int io_pitch, int io_blk,
+                                  float* stats_partial, int op_fmt, void* stream) {
+  return conv_igemm_impl(src, n_src, seg_src, seg_dy, seg_dx, n_seg, w_packed, bias, B, H, W, N, out16, 1,
+                         reinterpret_cast<const float*>(res16), res_mode, stats_partial, op_fmt, res_mode == 1, io_pitch,
+                         io_blk, stream);
 }

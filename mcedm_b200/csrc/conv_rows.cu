@@ -22,6 +22,17 @@
 // TMEM lane quarter, each draining one 32-column half of the tile (4-deep TMEM accumulator ring; the
 // residual tile is prefetched before the accumulator is waited for; GroupNorm partial sums are written
 // per (tile, lane quarter) so the epilogue warps never synchronise with each other).
+//
+// FUSED variant (inference, mcedm_conv_rows_fused): the halo sources are RAW 16-bit activations (the residual stream
+// or a conv0 output exactly as the producing conv stored it) and the GroupNorm + (1+scale)/shift + SiLU of
+// adm_blocks.py:161/:166/:403 is applied IN SHARED MEMORY by four extra "transform" warps between the TMA load of a
+// row and its first MMA: y = silu(a[b,c]*x + b[b,c]) with per-(sample, channel) coefficients from mcedm_gn_coef.
+// The normalised operand therefore never exists in HBM (the separate gn_apply pass read 4 B and wrote 2 B per element
+// per conv).  The transform rewrites each 16-byte chunk in place (same swizzled address), skips the two zero-padding
+// pixel columns and the out-of-image rows (their zeros must stay zeros), then fence.proxy.async + mbarrier-arrives on
+// h_ready[slot], which is what the MMA warp waits for in this variant.  Output, residual and the centre sources are
+// 16-bit too; an output-channel window (n_off, n_total) lets a 128-channel conv run as two N=32 passes whose weights
+// (72 KB each) stay resident.
 #include "ptx.cuh"
 #include "runtime.cuh"
 #include "../../include/mcedm_b200.h"
@@ -48,18 +59,24 @@ struct RowsParams {
   int fmt;               // 16-bit operand format: 0 bf16, 1 fp16
   const float* res;
   int res_mode;          // 0 none, 1 same resolution, 2 nearest-x2 upsample of res
-  float* stats;          // [total_rows][4 lane quarters][N/4][2]
+  float* stats;          // [total_rows][4 lane quarters][n_total/4][2]
   unsigned int* err;
+  int n_off;             // first output channel of this launch inside the n_total-channel out / res / stats rows
+  int n_total;           // channels per pixel of out / res (== N unless an output-channel window is used)
+  int w_rows;            // rows per segment of the packed weight matrix (== n_total)
+  const float* coef[2];  // FUSED: per halo source, fp32 [B][128] = (a | b) of y = silu(a*x + b); NULL = no transform
+  int res_pitch, res_blk; // FUSED, res_mode 2: the half-resolution residual is padded-flat (0,0: dense NHWC)
 };
 
-template <int N>
+template <int N, bool FUSED>
 struct RowsCfg {
   static constexpr int CH = (N >= 32) ? 32 : 16;
   static constexpr int NCH = N / CH;
   static constexpr int U = CH / 4;
   static constexpr int W_SEG_BYTES = N * 128;
   static constexpr int EPI_WARPS = 4 * NCH;                 // one warp per (lane quarter, column chunk)
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int XF_WARPS = FUSED ? 4 : 0;            // GroupNorm+SiLU transform warps (after the epilogue warps)
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
   static constexpr int ACC_BUFS = 4;
   static constexpr int TMEM_COLS = (ACC_BUFS * N <= 32) ? 32 : (ACC_BUFS * N <= 64) ? 64 : (ACC_BUFS * N <= 128) ? 128 : 256;
@@ -72,12 +89,27 @@ __device__ __forceinline__ uint64_t desc_from_lo(uint32_t addr) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-template <int N>
-__global__ void __launch_bounds__(RowsCfg<N>::THREADS, 1)
+// 8 raw 16-bit values -> silu(a*x + b) -> 8 16-bit values (fp32 math; e^-v through one ex2 and one rcp)
+__device__ __forceinline__ uint32_t xf_pair(uint32_t v, float a0, float b0, float a1, float b1, int fmt) {
+  float x0, x1;
+  if (fmt) {
+    const float2 f = unpack_f16x2(v);
+    x0 = f.x;
+    x1 = f.y;
+  } else {
+    x0 = bf16_lo(v);
+    x1 = bf16_hi(v);
+  }
+  // the coefficients arrive pre-halved: h = (a*x + b) / 2, silu(a*x + b) = h * (1 + tanh(h))
+  return pack_op2(silu_from_half_arg(fmaf(x0, a0, b0)), silu_from_half_arg(fmaf(x1, a1, b1)), fmt);
+}
+
+template <int N, bool FUSED>
+__global__ void __launch_bounds__(RowsCfg<N, FUSED>::THREADS, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_h0,
                  const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_c0,
                  const __grid_constant__ CUtensorMap tm_c1, const RowsParams p) {
-  using Cfg = RowsCfg<N>;
+  using Cfg = RowsCfg<N, FUSED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_seg = p.n_halo * 9 + p.n_ctr;
@@ -95,7 +127,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   uint64_t* h_empty = h_full + p.n_slots;
   uint64_t* c_full = h_empty + p.n_slots;   // n_cslots
   uint64_t* c_empty = c_full + p.n_cslots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + p.n_cslots);
+  uint64_t* h_ready = c_empty + p.n_cslots;   // n_slots (FUSED: row transformed and visible to the async proxy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + p.n_slots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,6 +147,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     for (int i = 0; i < p.n_slots; ++i) {
       mbar_init(&h_full[i], 1);
       mbar_init(&h_empty[i], 1);
+      mbar_init(&h_ready[i], 32 * Cfg::XF_WARPS + (FUSED ? 0 : 1));
     }
     for (int i = 0; i < p.n_cslots; ++i) {
       mbar_init(&c_full[i], 1);
@@ -134,7 +168,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       mbar_expect_tx(w_full, (uint32_t)(n_seg * Cfg::W_SEG_BYTES));
-      for (int s = 0; s < n_seg; ++s) tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * N);
+      for (int s = 0; s < n_seg; ++s)
+        tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * p.w_rows + p.n_off);
       uint32_t hl = 0, cl = 0;   // halo rows / centre tiles loaded so far
       long long r = r_begin;
       while (r < r_end) {
@@ -187,7 +222,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           mbar_wait(&acc_empty[buf], aph ^ 1u, p.err, 0x2400 + buf);
           while (waited < hbase + j + 3) {
             const uint32_t slot = waited % (uint32_t)p.n_slots, ph = (waited / (uint32_t)p.n_slots) & 1u;
-            mbar_wait(&h_full[slot], ph, p.err, 0x2500 + slot);
+            mbar_wait(FUSED ? &h_ready[slot] : &h_full[slot], ph, p.err, 0x2500 + slot);
             ++waited;
           }
           tc_fence_after();
@@ -242,36 +277,60 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         r += R;
       }
     }
-  } else {
+  } else if (!FUSED || warp < 2 + Cfg::EPI_WARPS) {
     // ======================================= epilogue =======================================
     const int q = warp & 3;                 // TMEM lane quarter
     const int ew = warp - 2;                // 0 .. EPI_WARPS-1
     const int ch = ew >> 2;                 // column chunk drained by this warp
-    uint8_t* my_stage = stage_smem + ew * (32 * Cfg::CH * 4);
+    const uint32_t my_stage = smem_u32(stage_smem) + ew * (32 * Cfg::CH * 4);
     const int unit = lane % Cfg::U;
     const int row_in_it = lane / Cfg::U;
     constexpr int ROWS_PER_IT = 32 / Cfg::U;
-    const int c0 = ch * Cfg::CH + unit * 4;
+    const int c0 = ch * Cfg::CH + unit * 4;          // column inside this launch's N-wide window
+    const int NT = p.n_total;                        // channels per pixel of out / res
+    const int cg = p.n_off + c0;                     // column inside the out / res rows
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias) bz = *reinterpret_cast<const float4*>(p.bias + c0);
+    if (p.bias) bz = *reinterpret_cast<const float4*>(p.bias + cg);
+    const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.res);
+    // The residual of tile r+1 is requested before tile r is processed (register double buffer): with all epilogue
+    // warps on the same tile, a load issued at the top of its own tile would expose the full DRAM latency per tile.
+    float4 rr_n[FUSED ? 1 : Cfg::U];      // fp32 residual (training / unfused path)
+    uint2 rh_n[FUSED ? Cfg::U : 1];       // 16-bit residual (fused path)
+    auto load_res = [&](long long r) {
+      const long long pix0 = r * 128 + q * 32;
+      if (p.res_mode == 1) {
+#pragma unroll
+        for (int itr = 0; itr < Cfg::U; ++itr) {
+          const long long o = (pix0 + itr * ROWS_PER_IT + row_in_it) * NT + cg;
+          if constexpr (FUSED) rh_n[itr] = *reinterpret_cast<const uint2*>(res16 + o);
+          else rr_n[itr] = *reinterpret_cast<const float4*>(p.res + o);
+        }
+      } else if (p.res_mode == 2) {
+        const int bimg = (int)(r / p.H);
+        const int y = (int)(r - (long long)bimg * p.H);
+        const long long rrow = (FUSED && p.res_pitch > 0)
+                                   ? ((long long)bimg * p.res_blk + (long long)((y >> 1) + 1) * p.res_pitch) * NT + cg
+                                   : ((long long)bimg * (p.H >> 1) + (y >> 1)) * 64 * NT + cg;
+#pragma unroll
+        for (int itr = 0; itr < Cfg::U; ++itr) {
+          const long long o = rrow + ((q * 32 + itr * ROWS_PER_IT + row_in_it) >> 1) * NT;
+          if constexpr (FUSED) rh_n[itr] = *reinterpret_cast<const uint2*>(res16 + o);
+          else rr_n[itr] = *reinterpret_cast<const float4*>(p.res + o);
+        }
+      }
+    };
+    if (r_begin < r_end) load_res(r_begin);
     uint32_t tcount = 0;
     for (long long r = r_begin; r < r_end; ++r, ++tcount) {
       const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
       const long long pix0 = r * 128 + q * 32;
-      // residual prefetch (independent of the accumulator)
-      float4 rr[Cfg::U];
-      if (p.res_mode == 1) {
+      float4 rr[FUSED ? 1 : Cfg::U];
+      uint2 rh[FUSED ? Cfg::U : 1];
 #pragma unroll
-        for (int itr = 0; itr < Cfg::U; ++itr)
-          rr[itr] = *reinterpret_cast<const float4*>(p.res + (pix0 + itr * ROWS_PER_IT + row_in_it) * N + c0);
-      } else if (p.res_mode == 2) {
-        const int bimg = (int)(r / p.H);
-        const int y = (int)(r - (long long)bimg * p.H);
-        const float* rrow = p.res + ((long long)bimg * (p.H >> 1) + (y >> 1)) * 64 * N + c0;
+      for (int itr = 0; itr < (FUSED ? 1 : Cfg::U); ++itr) rr[itr] = rr_n[itr];
 #pragma unroll
-        for (int itr = 0; itr < Cfg::U; ++itr)
-          rr[itr] = *reinterpret_cast<const float4*>(rrow + ((q * 32 + itr * ROWS_PER_IT + row_in_it) >> 1) * N);
-      }
+      for (int itr = 0; itr < (FUSED ? Cfg::U : 1); ++itr) rh[itr] = rh_n[itr];
+      if (r + 1 < r_end) load_res(r + 1);
       mbar_wait(&acc_full[buf], aph, p.err, 0x2700 + buf);
       tc_fence_after();
       uint32_t v[Cfg::CH];
@@ -283,8 +342,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
       for (int j = 0; j < Cfg::U; ++j) {
         const int pj = j ^ (lane & (Cfg::U - 1));
-        *reinterpret_cast<uint4*>(my_stage + lane * (Cfg::CH * 4) + pj * 16) =
-            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        sts128(my_stage + lane * (Cfg::CH * 4) + pj * 16, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       }
       __syncwarp();
       float s1 = 0.f, s2 = 0.f;
@@ -292,10 +350,22 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       for (int itr = 0; itr < Cfg::U; ++itr) {
         const int row = itr * ROWS_PER_IT + row_in_it;
         const int pu = unit ^ (row & (Cfg::U - 1));
-        float4 a = *reinterpret_cast<const float4*>(my_stage + row * (Cfg::CH * 4) + pu * 16);
+        float4 a = lds128f(my_stage + row * (Cfg::CH * 4) + pu * 16);
         a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
         if (p.res_mode != 0) {
-          a.x += rr[itr].x; a.y += rr[itr].y; a.z += rr[itr].z; a.w += rr[itr].w;
+          if constexpr (FUSED) {
+            float2 lo, hi;
+            if (p.fmt) {
+              lo = unpack_f16x2(rh[itr].x);
+              hi = unpack_f16x2(rh[itr].y);
+            } else {
+              lo = make_float2(bf16_lo(rh[itr].x), bf16_hi(rh[itr].x));
+              hi = make_float2(bf16_lo(rh[itr].y), bf16_hi(rh[itr].y));
+            }
+            a.x += lo.x; a.y += lo.y; a.z += hi.x; a.w += hi.y;
+          } else {
+            a.x += rr[itr].x; a.y += rr[itr].y; a.z += rr[itr].z; a.w += rr[itr].w;
+          }
         }
         s1 += (a.x + a.y) + (a.z + a.w);
         s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
@@ -304,9 +374,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           uint2 o;
           o.x = pack_op2(a.x, a.y, p.fmt);
           o.y = pack_op2(a.z, a.w, p.fmt);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * N + c0) = o;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * NT + cg) = o;
         } else {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * N + c0) = a;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * NT + cg) = a;
         }
       }
       if (p.stats) {
@@ -317,9 +387,72 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           s2 += __shfl_xor_sync(0xffffffffu, s2, off);
         }
         if (lane < Cfg::U)
-          *reinterpret_cast<float2*>(p.stats + ((r * 4 + q) * (N / 4) + ch * Cfg::U + lane) * 2) = make_float2(s1, s2);
+          *reinterpret_cast<float2*>(p.stats + ((r * 4 + q) * (NT / 4) + (cg >> 2)) * 2) = make_float2(s1, s2);
       }
       __syncwarp();
+    }
+  } else {
+    // ============================ GroupNorm + SiLU transform (FUSED) ============================
+    // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
+    // halo row; the chunk's physical position follows SWIZZLE_128B: chunk ^ (pixel row & 7) (slots are 1 KB aligned).
+    const int t = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    const int j = t & 7;
+    const int prow = t >> 3;                // 0 .. 15
+    uint32_t hl = 0;
+    long long r = r_begin;
+    while (r < r_end) {
+      const int b = (int)(r / p.H);
+      const int y0 = (int)(r - (long long)b * p.H);
+      const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+      float ca[2][8], cb[2][8];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (s < p.n_halo && p.coef[0] != nullptr) {
+          const float4* cf = reinterpret_cast<const float4*>(p.coef[s] + (long long)b * 128 + j * 8);
+          const float4 a0 = __ldg(cf), a1 = __ldg(cf + 1), b0 = __ldg(cf + 16), b1 = __ldg(cf + 17);
+          ca[s][0] = a0.x; ca[s][1] = a0.y; ca[s][2] = a0.z; ca[s][3] = a0.w;
+          ca[s][4] = a1.x; ca[s][5] = a1.y; ca[s][6] = a1.z; ca[s][7] = a1.w;
+          cb[s][0] = b0.x; cb[s][1] = b0.y; cb[s][2] = b0.z; cb[s][3] = b0.w;
+          cb[s][4] = b1.x; cb[s][5] = b1.y; cb[s][6] = b1.z; cb[s][7] = b1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            ca[s][e] *= 0.5f;
+            cb[s][e] *= 0.5f;
+          }
+        }
+      }
+      for (int k = 0; k < R + 2; ++k, ++hl) {
+        const uint32_t slot = hl % (uint32_t)p.n_slots, ph = (hl / (uint32_t)p.n_slots) & 1u;
+        mbar_wait(&h_full[slot], ph, p.err, 0x2800 + slot);
+        const int y = y0 - 1 + k;
+        if (y >= 0 && y < p.H && p.coef[0] != nullptr) {   // out-of-image rows are TMA zero fill and must stay zero
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s < p.n_halo) {
+              const uint32_t base = smem_u32(h_smem) + slot * slot_bytes + s * kHaloBytes;
+              uint4 v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int px = 1 + prow + 16 * i;
+                v[i] = lds128(base + px * 128 + ((j ^ (px & 7)) << 4));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int px = 1 + prow + 16 * i;
+                uint4 o;
+                o.x = xf_pair(v[i].x, ca[s][0], cb[s][0], ca[s][1], cb[s][1], p.fmt);
+                o.y = xf_pair(v[i].y, ca[s][2], cb[s][2], ca[s][3], cb[s][3], p.fmt);
+                o.z = xf_pair(v[i].z, ca[s][4], cb[s][4], ca[s][5], cb[s][5], p.fmt);
+                o.w = xf_pair(v[i].w, ca[s][6], cb[s][6], ca[s][7], cb[s][7], p.fmt);
+                sts128(base + px * 128 + ((j ^ (px & 7)) << 4), o);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+        }
+        mbar_arrive(&h_ready[slot]);
+      }
+      r += R;
     }
   }
 
@@ -331,34 +464,59 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   }
 }
 
-template <int N>
+template <int N, bool FUSED>
 static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const CUtensorMap* tm_c, RowsParams p,
                        cudaStream_t stream) {
-  using Cfg = RowsCfg<N>;
+  using Cfg = RowsCfg<N, FUSED>;
   const int n_seg = p.n_halo * 9 + p.n_ctr;
   const int fixed = 1024 + n_seg * Cfg::W_SEG_BYTES + Cfg::STAGE_BYTES + 512;
   const int slot_bytes = p.n_halo * kHaloBytes;
   p.n_cslots = p.n_ctr ? 2 : 0;
   int avail = 232448 - fixed - p.n_cslots * p.n_ctr * kCtrBytes;
   int slots = avail / slot_bytes;
-  if (slots < 4 && p.n_ctr) {            // trade the centre double-buffer for halo depth
+  if (slots < (FUSED ? 5 : 4) && p.n_ctr) {            // trade the centre double-buffer for halo depth
     p.n_cslots = 1;
     avail = 232448 - fixed - p.n_cslots * p.n_ctr * kCtrBytes;
     slots = avail / slot_bytes;
   }
   if (slots > 8) slots = 8;
-  MCEDM_REQUIRE(slots >= 3, "conv_rows: %d halo sources + %d centre sources with N=%d do not fit in shared memory",
-                p.n_halo, p.n_ctr, N);
+  MCEDM_REQUIRE(slots >= (FUSED ? 4 : 3),
+                "conv_rows: %d halo sources + %d centre sources with N=%d do not fit in shared memory", p.n_halo,
+                p.n_ctr, N);
   p.n_slots = slots;
   const int smem = fixed + slots * slot_bytes + p.n_cslots * p.n_ctr * kCtrBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   long long grid = p.total_rows < num_sms() ? p.total_rows : num_sms();
-  conv_rows_kernel<N><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
+  conv_rows_kernel<N, FUSED><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
   MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int rows_common(RowsParams& p, CUtensorMap& tm_w, CUtensorMap* tm_h, CUtensorMap* tm_c,
+                       const void* const* halo_src, int n_halo, const void* const* ctr_src, int n_ctr,
+                       const void* w_packed, int B, int H, int N) {
+  MCEDM_REQUIRE(n_halo >= 1 && n_halo <= 2 && n_ctr >= 0 && n_ctr <= 2, "conv_rows: n_halo=%d n_ctr=%d", n_halo, n_ctr);
+  MCEDM_REQUIRE(B >= 1 && H >= 1, "conv_rows: bad B/H");
+  MCEDM_REQUIRE(p.res_mode >= 0 && p.res_mode <= 2 && (p.res_mode == 0 || p.res != nullptr), "conv_rows: bad residual mode");
+  MCEDM_REQUIRE(p.res_mode != 2 || H % 2 == 0, "conv_rows: upsampled residual needs even H");
+  p.n_halo = n_halo;
+  p.n_ctr = n_ctr;
+  p.H = H;
+  p.total_rows = (long long)B * H;
+  p.err = watchdog_ptr();
+  MCEDM_REQUIRE(p.err != nullptr, "conv_rows: cannot allocate the watchdog word");
+  int rc = make_tmap_rows64_bf16(&tm_w, w_packed, (long long)(n_halo * 9 + n_ctr) * p.w_rows, N);
+  if (rc) return rc;
+  for (int i = 0; i < 2; ++i) {
+    rc = make_tmap_nhwc_bf16(&tm_h[i], halo_src[i < n_halo ? i : 0], B, H, 128, 64, kHaloRows, 1);
+    if (rc) return rc;
+    rc = make_tmap_nhwc_bf16(&tm_c[i], n_ctr ? ctr_src[i < n_ctr ? i : 0] : halo_src[0], B, H, 128, 64, 128, 1);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -368,16 +526,8 @@ extern "C" int mcedm_conv_rows(const void* const* halo_src, int n_halo, const vo
                                const void* w_packed, const float* bias, int B, int H, int N, void* out, int out_bf16,
                                const float* res, int res_mode, float* stats_partial, int op_fmt, void* stream) {
   using namespace mcedm;
-  MCEDM_REQUIRE(n_halo >= 1 && n_halo <= 2 && n_ctr >= 0 && n_ctr <= 2, "conv_rows: n_halo=%d n_ctr=%d", n_halo, n_ctr);
-  MCEDM_REQUIRE(B >= 1 && H >= 1, "conv_rows: bad B/H");
-  MCEDM_REQUIRE(res_mode >= 0 && res_mode <= 2 && (res_mode == 0 || res != nullptr), "conv_rows: bad residual mode");
-  MCEDM_REQUIRE(res_mode != 2 || H % 2 == 0, "conv_rows: upsampled residual needs even H");
   RowsParams p;
   memset(&p, 0, sizeof(p));
-  p.n_halo = n_halo;
-  p.n_ctr = n_ctr;
-  p.H = H;
-  p.total_rows = (long long)B * H;
   p.bias = bias;
   p.out = out;
   p.out_bf16 = out_bf16;
@@ -385,21 +535,54 @@ extern "C" int mcedm_conv_rows(const void* const* halo_src, int n_halo, const vo
   p.res = res;
   p.res_mode = res_mode;
   p.stats = stats_partial;
-  p.err = watchdog_ptr();
-  MCEDM_REQUIRE(p.err != nullptr, "conv_rows: cannot allocate the watchdog word");
+  p.n_off = 0;
+  p.n_total = N;
+  p.w_rows = N;
   CUtensorMap tm_w, tm_h[2], tm_c[2];
-  int rc = make_tmap_rows64_bf16(&tm_w, w_packed, (long long)(n_halo * 9 + n_ctr) * N, N);
+  int rc = rows_common(p, tm_w, tm_h, tm_c, halo_src, n_halo, ctr_src, n_ctr, w_packed, B, H, N);
   if (rc) return rc;
-  for (int i = 0; i < 2; ++i) {
-    rc = make_tmap_nhwc_bf16(&tm_h[i], halo_src[i < n_halo ? i : 0], B, H, 128, 64, kHaloRows, 1);
-    if (rc) return rc;
-    rc = make_tmap_nhwc_bf16(&tm_c[i], n_ctr ? ctr_src[i < n_ctr ? i : 0] : halo_src[0], B, H, 128, 64, 128, 1);
-    if (rc) return rc;
-  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (N) {
-    case 16: return launch_rows<16>(tm_w, tm_h, tm_c, p, st);
-    case 64: return launch_rows<64>(tm_w, tm_h, tm_c, p, st);
+    case 16: return launch_rows<16, false>(tm_w, tm_h, tm_c, p, st);
+    case 64: return launch_rows<64, false>(tm_w, tm_h, tm_c, p, st);
     default: return fail(-1, "conv_rows: N=%d unsupported (16, 64)", N);
+  }
+}
+
+extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* const* halo_coef, int n_halo,
+                                     const void* const* ctr_src, int n_ctr, const void* w_packed, const float* bias,
+                                     int B, int H, int N, int n_off, int n_total, void* out, int out_16,
+                                     const void* res16, int res_mode, int res_pitch, int res_blk,
+                                     float* stats_partial, int op_fmt, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n_total >= N && n_off >= 0 && n_off + N <= n_total && n_off % 4 == 0 && n_total % 4 == 0,
+                "conv_rows_fused: bad output window (N=%d n_off=%d n_total=%d)", N, n_off, n_total);
+  RowsParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.out = out;
+  p.out_bf16 = out_16;
+  p.fmt = op_fmt ? 1 : 0;
+  p.res = reinterpret_cast<const float*>(res16);
+  p.res_mode = res_mode;
+  p.stats = stats_partial;
+  p.n_off = n_off;
+  p.n_total = n_total;
+  p.w_rows = n_total;
+  p.res_pitch = res_pitch;
+  p.res_blk = res_blk;
+  for (int i = 0; i < n_halo && i < 2; ++i) {
+    p.coef[i] = halo_coef ? halo_coef[i] : nullptr;      // all NULL: the sources are already-normalised operands
+    MCEDM_REQUIRE((p.coef[i] != nullptr) == (p.coef[0] != nullptr), "conv_rows_fused: coefficients for all sources or none");
+  }
+  CUtensorMap tm_w, tm_h[2], tm_c[2];
+  int rc = rows_common(p, tm_w, tm_h, tm_c, halo_src, n_halo, ctr_src, n_ctr, w_packed, B, H, N);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (N) {
+    case 16: return launch_rows<16, true>(tm_w, tm_h, tm_c, p, st);
+    case 32: return launch_rows<32, true>(tm_w, tm_h, tm_c, p, st);
+    case 64: return launch_rows<64, true>(tm_w, tm_h, tm_c, p, st);
+    default: return fail(-1, "conv_rows_fused: N=%d unsupported (16, 32, 64)", N);
   }
 }

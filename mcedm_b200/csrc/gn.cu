@@ -77,6 +77,8 @@ struct GnApplyParams {
   float* coef;               // [B][128]: per-channel (a | b) with y = act(a*x + b); written by gn_finalize_kernel
   int out_pitch;             // 0: dense NHWC output; > 0: padded flat layout of conv_flat.cu (row pitch)
   int out_blk;               // positions per image block of the padded layout
+  int x16;                   // x is a 16-bit NHWC tensor in the operand format (inference: raw activations are 16-bit)
+  int in_pitch, in_blk;      // x16 only: x itself is in the padded flat layout (0: dense)
 };
 
 // pixel index of output (b, y, x) in the dense NHWC layout or in the padded flat layout
@@ -167,6 +169,35 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnApplyParams p)
   }
 }
 
+// 8 consecutive channels of input pixel `pix` (dense index inside the whole tensor) as two float4
+template <bool X16>
+__device__ __forceinline__ void gn_load8(const GnApplyParams& p, long long pix, int c8, float4& lo, float4& hi) {
+  if constexpr (X16) {
+    const uint4 v = reinterpret_cast<const uint4*>(p.x)[pix * 8 + c8];
+    if (p.fmt) {
+      const float2 a = unpack_f16x2(v.x), b = unpack_f16x2(v.y), c = unpack_f16x2(v.z), d = unpack_f16x2(v.w);
+      lo = make_float4(a.x, a.y, b.x, b.y);
+      hi = make_float4(c.x, c.y, d.x, d.y);
+    } else {
+      lo = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+      hi = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+    }
+  } else {
+    const float4* xp = reinterpret_cast<const float4*>(p.x + pix * 64 + c8 * 8);
+    lo = xp[0];
+    hi = xp[1];
+  }
+}
+// dense pixel index (b, y, x) of the INPUT tensor, or its padded-flat position when the 16-bit input is flat
+__device__ __forceinline__ long long gn_in_index(const GnApplyParams& p, int b, int ip) {
+  if (p.in_pitch > 0) {
+    const int y = ip / p.Win;
+    return (long long)b * p.in_blk + (long long)(y + 1) * p.in_pitch + (ip - y * p.Win);
+  }
+  return (long long)b * p.Hin * p.Win + ip;
+}
+
+template <bool X16>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   const int b = blockIdx.y;
   const int c8 = threadIdx.x & 7;          // 8-channel slice
@@ -183,11 +214,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       float4 lo[4], hi[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (i + 32 * k < p.pix_per_cta) {
-          const float4* xp = reinterpret_cast<const float4*>(p.x + (in_img + pix0 + i + 32 * k) * 64 + c8 * 8);
-          lo[k] = xp[0];
-          hi[k] = xp[1];
-        }
+        if (i + 32 * k < p.pix_per_cta) gn_load8<X16>(p, gn_in_index(p, b, pix0 + i + 32 * k), c8, lo[k], hi[k]);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -210,8 +237,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     for (int i = ps; i < p.pix_per_cta; i += 32) {
       const int ip = pix0 + i;
       const int y = ip / p.Win, x = ip - y * p.Win;
-      const float4* xp = reinterpret_cast<const float4*>(p.x + (in_img + ip) * 64 + c8 * 8);
-      const uint4 v = pack8(gn_act4(xp[0], a_lo, b_lo, p.act), gn_act4(xp[1], a_hi, b_hi, p.act), p.fmt);
+      float4 xl, xh;
+      gn_load8<X16>(p, gn_in_index(p, b, ip), c8, xl, xh);
+      const uint4 v = pack8(gn_act4(xl, a_lo, b_lo, p.act), gn_act4(xh, a_hi, b_hi, p.act), p.fmt);
       const long long o00 = gn_out_index(p, b, 2 * y, 2 * x, Ho, Wo);
       out[o00 * 8 + c8] = v;
       out[(o00 + 1) * 8 + c8] = v;
@@ -223,12 +251,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     for (int i = ps; i < p.pix_per_cta; i += 32) {
       const int op = pix0 + i;
       const int y = op / Wo, x = op - y * Wo;
-      const float* base = p.x + (in_img + (long long)(2 * y) * p.Win + 2 * x) * 64 + c8 * 8;
       float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4* xp = reinterpret_cast<const float4*>(base + ((k >> 1) * p.Win + (k & 1)) * 64);
-        const float4 l = gn_act4(xp[0], a_lo, b_lo, p.act), h = gn_act4(xp[1], a_hi, b_hi, p.act);
+        float4 xl, xh;
+        gn_load8<X16>(p, gn_in_index(p, b, (2 * y + (k >> 1)) * p.Win + 2 * x + (k & 1)), c8, xl, xh);
+        const float4 l = gn_act4(xl, a_lo, b_lo, p.act), h = gn_act4(xh, a_hi, b_hi, p.act);
         lo.x += l.x; lo.y += l.y; lo.z += l.z; lo.w += l.w;
         hi.x += h.x; hi.y += h.y; hi.z += h.z; hi.w += h.w;
       }
@@ -280,6 +308,9 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   p.meanrstd_out = meanrstd_out;
   p.coef = coef_scratch;
   p.fmt = op_fmt ? 1 : 0;
+  p.x16 = 0;
+  p.in_pitch = 0;
+  p.in_blk = 0;
   MCEDM_REQUIRE(coef_scratch != nullptr, "gn_apply: coef_scratch (fp32 [B][128]) is required");
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
   // streaming CTAs of <= 512 pixels (~200 KB of traffic each); keep >= ~4 CTAs per SM when the batch allows it
@@ -292,7 +323,67 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   dim3 grid(work / per, B);
   gn_finalize_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   MCEDM_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  gn_apply_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_gn_coef(const float* partial, int parts_per_img, const float* gamma, const float* beta,
+                             const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int B,
+                             int Hin, int Win, float* coef_out, float* meanrstd_out, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && parts_per_img >= 1 && coef_out != nullptr, "gn_coef: bad arguments");
+  GnApplyParams p;
+  memset(&p, 0, sizeof(p));
+  p.partial = partial;
+  p.tiles_per_img = parts_per_img;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.scale_shift = scale_shift;
+  p.emb_batch_stride = emb_batch_stride;
+  p.emb_shift_offset = emb_shift_offset;
+  p.eps = eps;
+  p.Hin = Hin;
+  p.Win = Win;
+  p.meanrstd_out = meanrstd_out;
+  p.coef = coef_out;
+  gn_finalize_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_gn_apply16(const void* x16, int in_pitch, int in_blk, const float* coef, int act, int resample,
+                                int B, int Hin, int Win, int out_pitch, int out_blk, void* out16, int op_fmt,
+                                void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply16: Hin*Win=%d must be a multiple of 128", Hin * Win);
+  MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply16: resample=%d", resample);
+  MCEDM_REQUIRE(resample != 2 || (Hin % 2 == 0 && Win % 2 == 0), "gn_apply16: 2x2 mean needs even H, W");
+  MCEDM_REQUIRE(coef != nullptr, "gn_apply16: coefficients (mcedm_gn_coef) are required");
+  GnApplyParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = reinterpret_cast<const float*>(x16);
+  p.x16 = 1;
+  p.in_pitch = in_pitch;
+  p.in_blk = in_blk;
+  p.act = act;
+  p.resample = resample;
+  p.Hin = Hin;
+  p.Win = Win;
+  p.out = out16;
+  p.out_pitch = out_pitch;
+  p.out_blk = out_blk;
+  p.coef = const_cast<float*>(coef);
+  p.fmt = op_fmt ? 1 : 0;
+  const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);
+  int per = 512;
+  while (per > 32 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
+  if (per < 32) per = 32;
+  while (per > 32 && (work % per) != 0) per >>= 1;
+  MCEDM_REQUIRE(work % per == 0, "gn_apply16: cannot tile %d pixels", work);
+  p.pix_per_cta = per;
+  dim3 grid(work / per, B);
+  gn_apply_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

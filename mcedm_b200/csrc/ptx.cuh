@@ -22,6 +22,24 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Explicit shared-space 128-bit accesses.  Pointers derived from the 1 KB-aligned dynamic shared-memory base go
+// through a uintptr_t round trip, after which nvcc no longer knows their address space and emits GENERIC LD/ST
+// (L1TEX path, long-scoreboard latency) instead of LDS/STS — measured as the top stall of the conv epilogues.
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  const uint4 v = lds128(saddr);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
 // ------------------------------------------ mbarrier ------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -205,6 +223,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int a_mn_majo
 // -------------------------------------- misc numerics -----------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
+// silu(2h) = h * (1 + tanh(h)) with ONE special-function op (MUFU.TANH, max relative error 2^-11 on tanh) instead of
+// ex2 + rcp: the in-shared-memory GroupNorm+SiLU transform of the fused convs is instruction-bound.
+__device__ __forceinline__ float silu_from_half_arg(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -212,7 +238,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  // satfinite: a value beyond the fp16 range (65504) clamps instead of becoming inf (16-bit activation storage)
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ uint32_t pack_op2(float lo, float hi, int fmt) {

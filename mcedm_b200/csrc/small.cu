@@ -61,7 +61,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ x, int Cx, const float* __restrict__ cond, int Cc,
                const float* __restrict__ w, const float* __restrict__ bias, int H, int W, int n_tiles,
-               float* __restrict__ out, float* __restrict__ stats) {
+               float* __restrict__ out, float* __restrict__ stats, int out16, int fmt) {
   extern __shared__ float patch[];  // [Cin][rows+2][W+8]; image column xx lives at index xx + 4
   __shared__ float sm[8][16][2];
   const int rows = 128 / W;
@@ -119,7 +119,8 @@ conv_in_kernel(const float* __restrict__ x, int Cx, const float* __restrict__ co
       const long long pix = (long long)tile * 128 + r * W + x0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        *reinterpret_cast<float2*>(out + (pix + j) * 64 + 2 * lane) = make_float2(a0[j], a1[j]);
+        if (out16) reinterpret_cast<uint32_t*>(out)[(pix + j) * 32 + lane] = pack_op2(a0[j], a1[j], fmt);
+        else *reinterpret_cast<float2*>(out + (pix + j) * 64 + 2 * lane) = make_float2(a0[j], a1[j]);
         s1 += a0[j] + a1[j];
         s2 += a0[j] * a0[j] + a1[j] * a1[j];
       }
@@ -168,8 +169,8 @@ extern "C" int mcedm_emb_mlp(const float* c_noise, const float* freqs, const flo
   return 0;
 }
 
-extern "C" int mcedm_conv_in(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
-                             int B, int H, int W, float* out, float* stats_partial, void* stream) {
+static int conv_in_impl(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
+                        int B, int H, int W, float* out, float* stats_partial, int out16, int fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(Cx >= 1 && Cc >= 0 && Cx + Cc <= kMaxCin, "conv_in: %d+%d input channels exceed %d", Cx, Cc, kMaxCin);
   MCEDM_REQUIRE(Cc == 0 || cond != nullptr, "conv_in: cond channels without a cond tensor");
@@ -180,7 +181,7 @@ extern "C" int mcedm_conv_in(const float* x, int Cx, const float* cond, int Cc, 
   const unsigned grid = (unsigned)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define MCEDM_CONV_IN_CASE(C) \
-  case C: conv_in_kernel<C><<<grid, 256, smem, st>>>(x, Cx, cond, Cc, w, bias, H, W, n_tiles, out, stats_partial); break;
+  case C: conv_in_kernel<C><<<grid, 256, smem, st>>>(x, Cx, cond, Cc, w, bias, H, W, n_tiles, out, stats_partial, out16, fmt); break;
   switch (Cx + Cc) {
     MCEDM_CONV_IN_CASE(1) MCEDM_CONV_IN_CASE(2) MCEDM_CONV_IN_CASE(3) MCEDM_CONV_IN_CASE(4)
     MCEDM_CONV_IN_CASE(5) MCEDM_CONV_IN_CASE(6) MCEDM_CONV_IN_CASE(7) MCEDM_CONV_IN_CASE(8)
@@ -188,6 +189,17 @@ extern "C" int mcedm_conv_in(const float* x, int Cx, const float* cond, int Cc, 
 #undef MCEDM_CONV_IN_CASE
   MCEDM_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mcedm_conv_in(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
+                             int B, int H, int W, float* out, float* stats_partial, void* stream) {
+  return conv_in_impl(x, Cx, cond, Cc, w, bias, B, H, W, out, stats_partial, 0, 0, stream);
+}
+
+extern "C" int mcedm_conv_in16(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
+                               int B, int H, int W, void* out16, float* stats_partial, int op_fmt, void* stream) {
+  return conv_in_impl(x, Cx, cond, Cc, w, bias, B, H, W, reinterpret_cast<float*>(out16), stats_partial, 1,
+                      op_fmt ? 1 : 0, stream);
 }
 
 extern "C" int mcedm_head_to_nchw(const float* src, int Cs, int Cout, int B, int H, int W, float* dst, void* stream) {

@@ -20,11 +20,13 @@ operand.  Workspaces are torch tensors owned by this object, keyed by batch size
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
 
 from . import _lib as L
+from .fused_engine import FusedMixin
 from .train_engine import TrainMixin
 
 WEIGHT_EPOCH = [0]
@@ -80,7 +82,7 @@ class _Block:
             self.be2 = m.norm2.bias.detach().float().contiguous()
 
 
-class UNetEngine(TrainMixin):
+class UNetEngine(TrainMixin, FusedMixin):
     def __init__(self, unet):
         self.unet = unet
         self.lib = L.lib()
@@ -119,6 +121,9 @@ class UNetEngine(TrainMixin):
         # normalised and weights O(1), so the narrower range is safe); training always runs bf16.
         self.infer_fmt = 1
         self._fmt = 1
+        # inference plan: True = GroupNorm fused into the convs + 16-bit activations (fused_engine.py);
+        # False = the unfused fp32-stream plan below (what training's forward uses)
+        self.fused = os.environ.get("MCEDM_FUSED", "1") != "0"
         self._gn_coef: Dict[tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ weights
@@ -342,6 +347,8 @@ class UNetEngine(TrainMixin):
     def _launch_all(self, x, nl, cond, out):
         """The launch sequence of one forward pass; no allocation, no host sync (CUDA-graph capturable
         once the workspace for this batch size exists)."""
+        if self.fused and self._fmt == 1 and x.shape[-1] == 128:      # bf16 storage would miss the 1e-2 bar
+            return self._launch_all_fused(x, nl, cond, out)
         u = self.unet
         B, _, H, W = x.shape
         dev = x.device
@@ -394,7 +401,7 @@ class UNetEngine(TrainMixin):
         if not use_graph:
             return self._launch_all(x, nl, cond, out)
         key = (x.data_ptr(), nl.data_ptr(), 0 if cond is None else cond.data_ptr(), out.data_ptr(), tuple(x.shape),
-               self._packed_key)
+               self._packed_key, self.fused)
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) > 8:

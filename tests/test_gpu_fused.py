@@ -1,0 +1,277 @@
+"""GPU tests of the GroupNorm-fused 16-bit inference kernels (include/mcedm_b200.h, section K1f) against a plain
+PyTorch fp64 reference of the same op on the same 16-bit-rounded inputs:
+
+    operand = silu(a[b,c] * x + b[b,c])  rounded to the operand format   (adm_blocks.py:161 / :166 after GroupNorm)
+    out     = conv3x3(operand) + bias (+ residual)                        (adm_blocks.py:65-81, :171)
+
+Tolerance: the kernel rounds the transformed operand to 16 bits exactly like the reference below does, evaluates
+SiLU with ex2/rcp approximations (a few ulp of fp32) and accumulates in fp32; the 16-bit output rounding dominates:
+rel-L2 < 6e-4 for fp16 outputs (2^-12 rounding ~ 1.4e-4 rms), < 2e-5 for fp32 outputs.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mcedm_b200.engine import pack_conv3x3
+from mcedm_b200.utils import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mcedm_b200 import _lib
+
+    _lib.lib()
+    return _lib
+
+
+def _dt(fmt):
+    return torch.float16 if fmt else torch.bfloat16
+
+
+def _coef(B, g, dev):
+    a = (0.5 + torch.rand(B, 64, generator=g)).to(dev)
+    b = (0.5 * torch.randn(B, 64, generator=g)).to(dev)
+    return torch.cat([a, b], 1).contiguous()
+
+
+def _operand(x16, coef, fmt):
+    """fp64 reference of the transform, rounded to the operand format like the kernel's shared-memory rewrite."""
+    a = coef[:, None, None, :64]
+    b = coef[:, None, None, 64:]
+    v = x16.float() * a + b            # fp32 fma in the kernel; fp32 here (same rounding up to fma contraction)
+    y = v.double() * torch.sigmoid(v.double())
+    return y.to(_dt(fmt)).double()
+
+
+def _conv_ref(ops, w, bias):
+    x = torch.cat(ops, -1).permute(0, 3, 1, 2)
+    return F.conv2d(x, w.double(), None if bias is None else bias.double(), padding=w.shape[-1] // 2).permute(0, 2, 3, 1)
+
+
+def _geom(L, H, W):
+    pitch, blk = C.c_int(0), C.c_int(0)
+    L.check(L.lib().mcedm_flat_geometry(H, W, C.byref(pitch), C.byref(blk)))
+    return pitch.value, blk.value
+
+
+def _to_flat(x_bhwc, pitch, blk):
+    B, H, W, Cn = x_bhwc.shape
+    flat = torch.zeros(B * blk, Cn, device=x_bhwc.device, dtype=x_bhwc.dtype)
+    flat[_flat_idx(B, H, W, pitch, blk, x_bhwc.device)] = x_bhwc.reshape(-1, Cn)
+    return flat
+
+
+def _flat_idx(B, H, W, pitch, blk, dev):
+    idx = (torch.arange(B, device=dev)[:, None, None] * blk + (torch.arange(H, device=dev)[None, :, None] + 1) * pitch
+           + torch.arange(W, device=dev)[None, None, :])
+    return idx.reshape(-1)
+
+
+def _from_flat(flat, B, H, W, pitch, blk):
+    return flat[_flat_idx(B, H, W, pitch, blk, flat.device)].reshape(B, H, W, -1)
+
+
+# --------------------------------------------------------------------------------------- conv_rows_fused
+@pytest.mark.parametrize("B,H,n_halo,n_ctr,N,res_mode,fmt,out16", [
+    (2, 128, 1, 0, 64, 0, 1, 1), (3, 128, 1, 0, 64, 1, 1, 1), (2, 128, 1, 0, 64, 2, 1, 1), (2, 128, 2, 0, 32, 0, 1, 1),
+    (2, 128, 1, 2, 64, 0, 1, 1), (2, 128, 1, 0, 16, 0, 1, 0), (5, 24, 1, 0, 64, 1, 0, 1), (150, 4, 1, 0, 64, 1, 1, 1)])
+def test_conv_rows_fused_matches_reference(L, dev, B, H, n_halo, n_ctr, N, res_mode, fmt, out16):
+    lib = L.lib()
+    dt = _dt(fmt)
+    g = torch.Generator().manual_seed(B * 131 + H + N + res_mode)
+    n_total = 64 if N == 32 else N
+    halos = [torch.randn(B, H, 128, 64, generator=g).to(dev).to(dt).contiguous() for _ in range(n_halo)]
+    coefs = [_coef(B, g, dev) for _ in range(n_halo)]
+    ctrs = [torch.randn(B, H, 128, 64, generator=g).to(dev).to(dt).contiguous() for _ in range(n_ctr)]
+    w3 = (torch.randn(n_total, 64 * n_halo, 3, 3, generator=g) / (576 * n_halo) ** 0.5).to(dev)
+    wp = pack_conv3x3(w3, dtype=dt)
+    w1 = None
+    if n_ctr:
+        w1 = (torch.randn(n_total, 64 * n_ctr, 1, 1, generator=g) / (64 * n_ctr) ** 0.5).to(dev)
+        wp = torch.cat([wp, pack_conv3x3(w1, dtype=dt)], 0).contiguous()
+    bias = torch.randn(n_total, generator=g).to(dev)
+    rshape = {0: None, 1: (B, H, 128, n_total), 2: (B, H // 2, 64, n_total)}[res_mode]
+    res = torch.randn(*rshape, generator=g).to(dev).to(dt).contiguous() if rshape else None
+    out = torch.full((B, H, 128, n_total), float("nan"), device=dev, dtype=dt if out16 else torch.float32)
+    st = torch.full((B * H, 4, n_total // 4, 2), float("nan"), device=dev)
+    coef_ptrs = (C.c_void_p * n_halo)(*[c.data_ptr() for c in coefs])
+    for n_off in range(0, n_total, N):
+        L.check(lib.mcedm_conv_rows_fused(L.ptr_array(halos), coef_ptrs, n_halo, L.ptr_array(ctrs) if ctrs else None,
+                                          n_ctr, L.ptr(wp), L.ptr(bias), B, H, N, n_off, n_total, L.ptr(out), out16,
+                                          L.ptr(res), res_mode, 0, 0, L.ptr(st), fmt, L.stream_ptr()), "conv_rows_fused")
+    L.check_watchdog()
+    # reference on the same rounded weights
+    wq = wp.double()
+    w3q = wq[:9 * n_halo].reshape(n_halo, 3, 3, n_total, 64).permute(3, 0, 4, 1, 2).reshape(n_total, 64 * n_halo, 3, 3)
+    ref = _conv_ref([_operand(h, c, fmt) for h, c in zip(halos, coefs)], w3q, bias)
+    if n_ctr:
+        w1q = wq[9 * n_halo:].reshape(n_ctr, n_total, 64).permute(1, 0, 2).reshape(n_total, 64 * n_ctr, 1, 1)
+        ref = ref + _conv_ref([c.double() for c in ctrs], w1q, None)
+    if res_mode == 1:
+        ref = ref + res.double()
+    elif res_mode == 2:
+        ref = ref + res.double().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    tol = (6e-4 if fmt else 4e-3) if out16 else 4e-4   # fp32 out: the tanh-approx SiLU moves ~1 operand ulp
+    assert rel_l2(out.double(), ref) < tol
+    v = ref.reshape(B, H * 128, n_total // 4, 4)
+    tot = st.reshape(B, -1, n_total // 4, 2).double().sum(1)
+    assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+    assert torch.allclose(tot[..., 1], (v * v).sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+
+
+# --------------------------------------------------------------------------------------- conv_flat_fused
+@pytest.mark.parametrize("B,H,W,res_mode,res_layout,out_f32,fmt", [
+    (3, 64, 64, 0, "flat", 0, 1), (3, 64, 64, 1, "flat", 0, 1), (2, 64, 64, 3, "dense", 0, 1), (2, 32, 32, 3, "flat", 0, 1),
+    (2, 64, 64, 2, "flat", 0, 1), (5, 32, 32, 1, "f32", 0, 1), (5, 32, 32, 0, "flat", 1, 1), (40, 32, 32, 1, "flat", 0, 0),
+    (2, 16, 16, 1, "flat", 0, 1)])
+def test_conv_flat_fused_matches_reference(L, dev, B, H, W, res_mode, res_layout, out_f32, fmt):
+    lib = L.lib()
+    dt = _dt(fmt)
+    g = torch.Generator().manual_seed(B * 17 + H + res_mode * 5 + out_f32)
+    pitch, blk = _geom(L, H, W)
+    x = torch.randn(B, H, W, 64, generator=g).to(dev).to(dt)
+    coef = _coef(B, g, dev)
+    w3 = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
+    wp = pack_conv3x3(w3, dtype=dt)
+    bias = torch.randn(64, generator=g).to(dev)
+    res = res_dev = None
+    rp, rb, res_f32 = 0, 0, 0
+    if res_mode == 1:
+        if res_layout == "f32":
+            res = torch.randn(B, H, W, 64, generator=g).to(dev)
+            res_f32 = 1
+        else:
+            res = torch.randn(B, H, W, 64, generator=g).to(dev).to(dt)
+        res_dev = _to_flat(res, pitch, blk)
+    elif res_mode == 2:
+        res = torch.randn(B, H // 2, W // 2, 64, generator=g).to(dev).to(dt)
+        rp, rb = _geom(L, H // 2, W // 2)
+        res_dev = _to_flat(res, rp, rb)
+    elif res_mode == 3:
+        res = torch.randn(B, 2 * H, 2 * W, 64, generator=g).to(dev).to(dt)
+        if res_layout == "dense":
+            res_dev = res.contiguous()
+        else:
+            rp, rb = _geom(L, 2 * H, 2 * W)
+            res_dev = _to_flat(res, rp, rb)
+    out = torch.zeros(B * blk, 64, device=dev, dtype=torch.float32 if out_f32 else dt)
+    st = torch.zeros(B * blk // 128, 4, 16, 2, device=dev)
+    L.check(lib.mcedm_conv_flat_fused(L.ptr(_to_flat(x, pitch, blk)), L.ptr(coef), L.ptr(wp), L.ptr(bias), B, H, W, 64,
+                                      L.ptr(out), out_f32, L.ptr(res_dev), res_mode, res_f32, rp, rb, L.ptr(st), fmt,
+                                      L.stream_ptr()), "conv_flat_fused")
+    L.check_watchdog()
+    wq = wp.double().reshape(3, 3, 64, 64).permute(2, 3, 0, 1)
+    ref = _conv_ref([_operand(x, coef, fmt)], wq, bias)
+    if res_mode == 1:
+        ref = ref + res.double()
+    elif res_mode == 2:
+        ref = ref + res.double().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    elif res_mode == 3:
+        ref = ref + F.avg_pool2d(res.double().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    got = _from_flat(out, B, H, W, pitch, blk).double()
+    assert rel_l2(got, ref) < (2e-5 if out_f32 else (6e-4 if fmt else 4e-3))
+    # padding positions of the output are never written
+    mask = torch.ones(B * blk, dtype=torch.bool, device=dev)
+    mask[_flat_idx(B, H, W, pitch, blk, dev)] = False
+    assert float(out[mask].abs().max()) == 0.0
+    v = ref.reshape(B, H * W, 16, 4)
+    tot = st.reshape(B, -1, 16, 2).double().sum(1)
+    assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+    assert torch.allclose(tot[..., 1], (v * v).sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+
+
+# --------------------------------------------------------------------------------------- gn_coef + gn_apply16
+@pytest.mark.parametrize("B,H,W,rs,act,in_flat,out_flat,fmt", [
+    (2, 128, 128, 0, 1, False, False, 1), (2, 128, 128, 2, 1, False, True, 1), (3, 64, 64, 1, 1, True, False, 1),
+    (3, 64, 64, 2, 1, True, True, 1), (2, 32, 32, 0, 0, True, False, 1), (2, 32, 32, 1, 1, True, True, 0)])
+def test_gn_coef_and_apply16_match_group_norm(L, dev, B, H, W, rs, act, in_flat, out_flat, fmt):
+    lib = L.lib()
+    dt = _dt(fmt)
+    g = torch.Generator().manual_seed(H + rs * 3 + act)
+    x = (torch.randn(B, H, W, 64, generator=g) * 1.7 + 0.3).to(dev).to(dt)
+    gamma = (1 + 0.2 * torch.randn(64, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(64, generator=g)).to(dev)
+    ss = (0.3 * torch.randn(B, 128, generator=g)).to(dev)
+    # statistics from the stand-alone kernel on the fp32 copy of the values
+    part = torch.empty(B * H * W // 128, 16, 2, device=dev)
+    L.check(lib.mcedm_gn_stats(L.ptr(x.float().contiguous()), B * H * W, L.ptr(part), L.stream_ptr()))
+    coef = torch.empty(B, 128, device=dev)
+    L.check(lib.mcedm_gn_coef(L.ptr(part), H * W // 128, L.ptr(gamma), L.ptr(beta), L.ptr(ss), 128, 64, 1e-5, B, H, W,
+                              L.ptr(coef), None, L.stream_ptr()), "gn_coef")
+    ip, ib = _geom(L, H, W) if in_flat else (0, 0)
+    xin = _to_flat(x, ip, ib) if in_flat else x.contiguous()
+    Ho, Wo = {0: (H, W), 1: (2 * H, 2 * W), 2: (H // 2, W // 2)}[rs]
+    op, ob = _geom(L, Ho, Wo) if out_flat else (0, 0)
+    out = torch.zeros(B * ob, 64, device=dev, dtype=dt) if out_flat else torch.empty(B, Ho, Wo, 64, device=dev, dtype=dt)
+    L.check(lib.mcedm_gn_apply16(L.ptr(xin), ip, ib, L.ptr(coef), act, rs, B, H, W, op, ob, L.ptr(out), fmt,
+                                 L.stream_ptr()), "gn_apply16")
+    L.check_watchdog()
+    xn = F.group_norm(x.double().permute(0, 3, 1, 2), 16, gamma.double(), beta.double(), 1e-5)
+    xn = xn * (1 + ss[:, :64].double()[:, :, None, None]) + ss[:, 64:].double()[:, :, None, None]
+    if act:
+        xn = F.silu(xn)
+    if rs == 1:
+        xn = xn.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    elif rs == 2:
+        xn = F.avg_pool2d(xn, 2)
+    ref = xn.permute(0, 2, 3, 1)
+    got = _from_flat(out, B, Ho, Wo, op, ob) if out_flat else out
+    assert rel_l2(got.double(), ref) < (6e-4 if fmt else 4e-3)
+
+
+# --------------------------------------------------------------------------------------- conv_igemm16 / conv_in16
+@pytest.mark.parametrize("B,H,W,res,flat", [(3, 32, 32, True, True), (2, 32, 32, False, False), (2, 64, 64, True, False)])
+def test_conv_igemm16_flat_output_and_16bit_residual(L, dev, B, H, W, res, flat):
+    lib = L.lib()
+    dt = torch.float16
+    g = torch.Generator().manual_seed(H + B)
+    a = torch.randn(B, H, W, 64, generator=g).to(dev).to(dt).contiguous()
+    w = (torch.randn(64, 64, 1, 1, generator=g) / 8).to(dev)
+    wp = pack_conv3x3(w, dtype=dt)
+    bias = torch.randn(64, generator=g).to(dev)
+    pitch, blk = _geom(L, H, W) if flat else (0, 0)
+    r = torch.randn(B, H, W, 64, generator=g).to(dev).to(dt) if res else None
+    r_dev = None if r is None else (_to_flat(r, pitch, blk) if flat else r.contiguous())
+    out = torch.zeros(B * blk, 64, device=dev, dtype=dt) if flat else torch.empty(B, H, W, 64, device=dev, dtype=dt)
+    st = torch.empty(B * H * W // 128, 16, 2, device=dev)
+    L.check(lib.mcedm_conv_igemm16(L.ptr_array([a]), 1, L.int_array([0]), L.int_array([0]), L.int_array([0]), 1, L.ptr(wp),
+                                   L.ptr(bias), B, H, W, 64, L.ptr(out), L.ptr(r_dev), 1 if res else 0, pitch, blk,
+                                   L.ptr(st), 1, L.stream_ptr()), "conv_igemm16")
+    L.check_watchdog()
+    ref = _conv_ref([a.double()], wp.double().reshape(64, 64, 1, 1), bias)
+    if res:
+        ref = ref + r.double()
+    got = _from_flat(out, B, H, W, pitch, blk) if flat else out
+    assert rel_l2(got.double(), ref) < 6e-4
+    v = ref.reshape(B, H * W, 16, 4)
+    tot = st.reshape(B, -1, 16, 2).double().sum(1)
+    assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=1.0)
+
+
+def test_conv_in16_matches_fp32_conv(L, dev):
+    lib = L.lib()
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 3, 128, 128
+    x = torch.randn(B, 2, H, W, generator=g).to(dev)
+    c = torch.randn(B, 2, H, W, generator=g).to(dev)
+    w = (torch.randn(64, 4, 3, 3, generator=g) / 6).to(dev)
+    bias = torch.randn(64, generator=g).to(dev)
+    out = torch.empty(B, H, W, 64, device=dev, dtype=torch.float16)
+    st = torch.empty(B * H * W // 128, 16, 2, device=dev)
+    L.check(lib.mcedm_conv_in16(L.ptr(x), 2, L.ptr(c), 2, L.ptr(w), L.ptr(bias), B, H, W, L.ptr(out), L.ptr(st), 1,
+                                L.stream_ptr()), "conv_in16")
+    L.check_watchdog()
+    ref = F.conv2d(torch.cat([c, x], 1).double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(out.double(), ref) < 6e-4
+    v = ref.reshape(B, H * W, 16, 4)
+    tot = st.reshape(B, -1, 16, 2).double().sum(1)
+    assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=1.0)
