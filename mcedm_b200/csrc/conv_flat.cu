@@ -209,48 +209,57 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
+    // lean issue loop (see conv_rows.cu): wrap-around ring counters, one election per tile, immediate offsets
     {
       const uint32_t idesc = umma_idesc_16(128, N, 0, 0, p.fmt);
       mbar_wait(w_full, 0, p.err, 0x3200);
       tc_fence_after();
-      const uint32_t w_base = smem_u32(w_smem);
-      const uint32_t ring_base = smem_u32(ring);
+      const uint32_t w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);
+      const uint32_t ring_lo = (smem_u32(ring) >> 4) | (1u << 16);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+      // tap (ky, kx) = row offset ((ky-1)*P + (kx-1)) * 128 B from the centre chunk, in 16-byte units
+      int tap_off[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_off[t] = ((t / 3 - 1) * p.P + (t % 3 - 1)) * 8;
+      uint32_t slot = 0, wslot = 0, wph = 0;
       int waited = 0;
       for (int j = 0; j < n_tiles; ++j) {
         const uint32_t buf = (uint32_t)j % Cfg::ACC_BUFS, aph = ((uint32_t)j / Cfg::ACC_BUFS) & 1u;
         mbar_wait(&acc_empty[buf], aph ^ 1u, p.err, 0x3300 + buf);
         while (waited < j + 3) {
-          const uint32_t slot = (uint32_t)waited % (uint32_t)S, ph = ((uint32_t)waited / (uint32_t)S) & 1u;
-          mbar_wait(FUSED ? &c_ready[slot] : &c_full[slot], ph, p.err, 0x3400 + slot);
+          mbar_wait(FUSED ? &c_ready[wslot] : &c_full[wslot], wph, p.err, 0x3400 + wslot);
           ++waited;
+          if (++wslot == (uint32_t)S) {
+            wslot = 0;
+            wph ^= 1u;
+          }
         }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * N;
-        // window = slots (j % S), +1, +2 (mirrors keep them contiguous); the tile itself is the middle chunk
-        const uint32_t centre = ring_base + ((uint32_t)j % (uint32_t)S) * kChunkBytes + 128 * 128;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint64_t ad = flat_desc(centre + (uint32_t)(((ky - 1) * p.P + (kx - 1)) * 128));
-            const uint64_t bd = flat_desc(w_base + (ky * 3 + kx) * Cfg::W_SEG_BYTES);
-            if (elect_one()) {
-              umma_f16(d_tmem, ad, bd, idesc, (ky | kx) != 0 ? 1u : 0u);
-              umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-              umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-              umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-            }
-          }
-        }
+        // window = slots slot, +1, +2 (mirrors keep them contiguous); the tile itself is the middle chunk
+        const uint32_t centre = ring_lo + (slot + 1) * (kChunkBytes >> 4);
+        const uint32_t s1 = (slot + 1 == (uint32_t)S) ? 0u : slot + 1;
+        const uint32_t s2 = (s1 + 1 == (uint32_t)S) ? 0u : s1 + 1;
         if (elect_one()) {
-          umma_commit(&c_empty[(uint32_t)j % (uint32_t)S]);        // chunk j has no further user
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint64_t ad = desc(centre + (uint32_t)tap_off[t]);
+            const uint64_t bd = desc(w_lo + t * (Cfg::W_SEG_BYTES >> 4));
+            umma_f16(d_tmem, ad, bd, idesc, t != 0 ? 1u : 0u);
+            umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+            umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+          }
+          umma_commit(&c_empty[slot]);        // chunk j has no further user
           if (j == n_tiles - 1) {
-            umma_commit(&c_empty[(uint32_t)(j + 1) % (uint32_t)S]);
-            umma_commit(&c_empty[(uint32_t)(j + 2) % (uint32_t)S]);
+            umma_commit(&c_empty[s1]);
+            umma_commit(&c_empty[s2]);
           }
           umma_commit(&acc_full[buf]);
         }
         __syncwarp();
+        slot = s1;
       }
     }
   } else if (!FUSED || warp < 2 + Cfg::EPI_WARPS) {
@@ -273,11 +282,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       const int b = (int)(tile / p.tiles_per_img);
       const int pos0 = (int)(tile - (long long)b * p.tiles_per_img) * 128 + q * 32;
       const uint16_t* r16 = reinterpret_cast<const uint16_t*>(p.res);
+      int row = (pos0 + row_in_it) / p.P;            // one division per tile; the lane's rows are 4 positions apart
+      int x = (pos0 + row_in_it) - row * p.P;
 #pragma unroll
-      for (int itr = 0; itr < 8; ++itr) {
-        const int pos = pos0 + itr * 4 + row_in_it;
-        const int row = pos / p.P;
-        const int x = pos - row * p.P;
+      for (int itr = 0; itr < 8; ++itr, x += 4) {
+        if (x >= p.P) {
+          x -= p.P;
+          ++row;
+        }
         rh_n[itr] = make_uint2(0u, 0u);
         if ((row >= 1) && (row <= p.H) && (x < p.W)) {
           const long long i = p.res_mode == 1 ? tile * 128 + q * 32 + itr * 4 + row_in_it
@@ -295,11 +307,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       // decode this lane's 8 rows (position -> image row / column; padding rows are dropped)
       long long opix[8];
       float4 rr[8];
+      int row = (pos0 + row_in_it) / p.P;            // one division per tile; the lane's rows are 4 positions apart
+      int x = (pos0 + row_in_it) - row * p.P;
 #pragma unroll
-      for (int itr = 0; itr < 8; ++itr) {
-        const int pos = pos0 + itr * 4 + row_in_it;
-        const int row = pos / p.P;
-        const int x = pos - row * p.P;
+      for (int itr = 0; itr < 8; ++itr, x += 4) {
+        if (x >= p.P) {
+          x -= p.P;
+          ++row;
+        }
         const bool valid = (row >= 1) && (row <= p.H) && (x < p.W);
         if constexpr (FUSED) {
           const long long gpos = tile * 128 + q * 32 + itr * 4 + row_in_it;    // padded-flat output position

@@ -70,7 +70,7 @@ struct RowsParams {
 
 template <int N, bool FUSED>
 struct RowsCfg {
-  static constexpr int CH = (N >= 32) ? 32 : 16;
+  static constexpr int CH = (N >= 32) ? 32 : 16;        // (16 epilogue warps of 16 columns were tried: no gain)
   static constexpr int NCH = N / CH;
   static constexpr int U = CH / 4;
   static constexpr int W_SEG_BYTES = N * 128;
@@ -202,78 +202,101 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // elected lane issues each tcgen05 instruction.  (Running this under `if (lane == 0)` made ptxas
     // emit an election loop + R2UR moves per MMA: ~4K issue cycles per tile on one thread, which was
     // the kernel's bottleneck.)
+    // Kept lean on purpose: this single warp's instruction stream paces the tensor pipe.  Ring positions are
+    // wrap-around counters (no integer division), the three input rows' descriptor words are formed once per tile,
+    // and ONE elected lane issues the tile's 36 tcgen05.mma back to back with immediate descriptor offsets
+    // (the previous per-tap election + per-tap address arithmetic cost ~510 instructions per tile, which measured
+    // as the limiter: tensor pipe 35 % active with every other role waiting).
     {
       const uint32_t idesc = umma_idesc_16(128, N, 0, 0, p.fmt);
       mbar_wait(w_full, 0, p.err, 0x2300);
       tc_fence_after();
-      const uint32_t w_base = smem_u32(w_smem);
-      const uint32_t h_base = smem_u32(h_smem);
-      const uint32_t c_base = smem_u32(c_smem);
-      uint32_t hbase = 0;      // global index of the current segment's first halo row
-      uint32_t waited = 0;     // halo rows [0, waited) are known to have landed
-      uint32_t cc = 0, tcount = 0;
+      const uint32_t ns = (uint32_t)p.n_slots;
+      const uint32_t w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);          // descriptor low words: address >> 4 | LBO
+      const uint32_t h_lo = (smem_u32(h_smem) >> 4) | (1u << 16);
+      const uint32_t c_lo = (smem_u32(c_smem) >> 4) | (1u << 16);
+      const uint32_t slot16 = (uint32_t)slot_bytes >> 4;
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 | version 1 | SWIZZLE_128B
+      auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+      uint32_t s0 = 0;                      // ring slot of the current tile's first input row
+      uint32_t wslot = 0, wph = 0;          // next ring slot to wait for and its phase
+      uint32_t waited = 0, need = 3;        // rows known to have landed / rows the current tile needs
+      uint32_t cs = 0, cph = 0, tcount = 0;
       long long r = r_begin;
       while (r < r_end) {
         const int b = (int)(r / p.H);
         const int y0 = (int)(r - (long long)b * p.H);
         const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
-        for (int j = 0; j < R; ++j, ++tcount) {
+        for (int j = 0; j < R; ++j, ++tcount, ++need) {
           const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
           mbar_wait(&acc_empty[buf], aph ^ 1u, p.err, 0x2400 + buf);
-          while (waited < hbase + j + 3) {
-            const uint32_t slot = waited % (uint32_t)p.n_slots, ph = (waited / (uint32_t)p.n_slots) & 1u;
-            mbar_wait(FUSED ? &h_ready[slot] : &h_full[slot], ph, p.err, 0x2500 + slot);
+          while (waited < need) {
+            mbar_wait(FUSED ? &h_ready[wslot] : &h_full[wslot], wph, p.err, 0x2500 + wslot);
             ++waited;
+            if (++wslot == ns) {
+              wslot = 0;
+              wph ^= 1u;
+            }
           }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * N;
-          for (int s = 0; s < p.n_halo; ++s) {
+          const uint32_t s1 = (s0 + 1 == ns) ? 0u : s0 + 1;
+          const uint32_t s2 = (s1 + 1 == ns) ? 0u : s1 + 1;
+          const uint32_t a_lo[3] = {h_lo + s0 * slot16, h_lo + s1 * slot16, h_lo + s2 * slot16};
+          if (elect_one()) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const uint32_t slot = (hbase + j + ky) % (uint32_t)p.n_slots;
-              const uint32_t row_base = h_base + slot * slot_bytes + s * kHaloBytes;
+            for (int s = 0; s < 2; ++s) {
+              if (s < p.n_halo) {
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                // (dx + 1) pixel rows into the halo'd row; +32 B along K = +2 in the (address >> 4) field
-                const uint64_t ad = desc_from_lo(row_base + kx * 128);
-                const uint64_t bd = desc_from_lo(w_base + (s * 9 + ky * 3 + kx) * Cfg::W_SEG_BYTES);
-                const uint32_t acc0 = (s | ky | kx) != 0 ? 1u : 0u;
-                if (elect_one()) {
-                  umma_f16(d_tmem, ad, bd, idesc, acc0);
-                  umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                  umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                  umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                  for (int kx = 0; kx < 3; ++kx) {
+                    // (dx + 1) pixel rows into the halo'd row = +8 in the (address >> 4) field; +32 B along K = +2
+                    const uint64_t ad = desc(a_lo[ky] + s * (kHaloBytes >> 4) + kx * 8);
+                    const uint64_t bd = desc(w_lo + (s * 9 + ky * 3 + kx) * (Cfg::W_SEG_BYTES >> 4));
+                    umma_f16(d_tmem, ad, bd, idesc, (s | ky | kx) != 0 ? 1u : 0u);
+                    umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                    umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                    umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                  }
                 }
               }
             }
           }
           if (p.n_ctr > 0) {
-            const uint32_t cs = cc % (uint32_t)p.n_cslots, cph = (cc / (uint32_t)p.n_cslots) & 1u;
+            // centre tiles last: their (single-buffered) slot is the one most likely to be late
             mbar_wait(&c_full[cs], cph, p.err, 0x2600 + cs);
             tc_fence_after();
-            for (int s = 0; s < p.n_ctr; ++s) {
-              const uint64_t ad = desc_from_lo(c_base + cs * cslot_bytes + s * kCtrBytes);
-              const uint64_t bd = desc_from_lo(w_base + (p.n_halo * 9 + s) * Cfg::W_SEG_BYTES);
-              if (elect_one()) {
+          }
+          if (elect_one()) {
+            if (p.n_ctr > 0) {
+              for (int s = 0; s < p.n_ctr; ++s) {
+                const uint64_t ad = desc(c_lo + ((cs * (uint32_t)cslot_bytes + s * kCtrBytes) >> 4));
+                const uint64_t bd = desc(w_lo + (p.n_halo * 9 + s) * (Cfg::W_SEG_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
               }
+              umma_commit(&c_empty[cs]);
             }
-            if (elect_one()) umma_commit(&c_empty[cs]);
-            ++cc;
-          }
-          if (elect_one()) {
-            // input row (hbase + j) has no further user; the last output row also frees the two rows below it
-            umma_commit(&h_empty[(hbase + j) % (uint32_t)p.n_slots]);
+            // input row s0 has no further user; the last output row of a segment also frees the two rows below it
+            umma_commit(&h_empty[s0]);
             if (j == R - 1) {
-              umma_commit(&h_empty[(hbase + j + 1) % (uint32_t)p.n_slots]);
-              umma_commit(&h_empty[(hbase + j + 2) % (uint32_t)p.n_slots]);
+              umma_commit(&h_empty[s1]);
+              umma_commit(&h_empty[s2]);
             }
             umma_commit(&acc_full[buf]);
           }
           __syncwarp();
+          s0 = s1;
+          if (p.n_ctr > 0 && ++cs == (uint32_t)p.n_cslots) {
+            cs = 0;
+            cph ^= 1u;
+          }
         }
-        hbase += R + 2;
+        // the next segment starts two rows further on (its own top halo row and the one above it)
+        s0 = (s0 + 1 == ns) ? 0u : s0 + 1;
+        s0 = (s0 + 1 == ns) ? 0u : s0 + 1;
+        need += 2;
         r += R;
       }
     }

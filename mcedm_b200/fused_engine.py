@@ -101,12 +101,16 @@ class FusedMixin:
             cptr = None if coefs is None else (C.c_void_p * len(coefs))(*[c.data_ptr() for c in coefs])
             hal = L.ptr_array([s.t for s in srcs])
             if len(srcs) == 2:
-                # 128-channel conv0: two N = 32 passes (output-channel window) so the 72 KB of weights stay resident
+                # 128-channel conv0 (K = 1152: 144 KB of weights do not fit next to the row ring): K-split over the two
+                # sources.  Pass 1 leaves its partial sum in `out` (16-bit), pass 2 adds it as an in-place residual.
+                # (Two N = 32 output-channel passes with both sources resident were measured 40 % slower: the ring
+                # shrinks to 4 two-source slots and every row is transformed twice.)
                 assert not ctr and res is None
-                for n_off in (0, 32):
-                    L.check(self.lib.mcedm_conv_rows_fused(hal, cptr, 2, None, 0, L.ptr(w), L.ptr(bias), B, H, 32, n_off, 64,
-                                                           L.ptr(out.t), 1, None, 0, 0, 0, L.ptr(out.st) if stats else None,
-                                                           self._fmt, st), "conv_rows_fused")
+                for i in (0, 1):
+                    L.check(self.lib.mcedm_conv_rows_fused(
+                        L.ptr_array([srcs[i].t]), (C.c_void_p * 1)(coefs[i].data_ptr()), 1, None, 0, L.ptr(w[9 * i:9 * i + 9]),
+                        L.ptr(bias) if i else None, B, H, 64, 0, 64, L.ptr(out.t), 1, L.ptr(out.t) if i else None, i, 0, 0,
+                        L.ptr(out.st) if (stats and i) else None, self._fmt, st), "conv_rows_fused")
             else:
                 cs = L.ptr_array([c.t for c in ctr]) if ctr else None
                 L.check(self.lib.mcedm_conv_rows_fused(hal, cptr, 1, cs, len(ctr) if ctr else 0, L.ptr(w), L.ptr(bias), B, H,
@@ -119,14 +123,13 @@ class FusedMixin:
         pitch, blk = out.flat
         lib = self.lib
         if len(srcs) == 2:
-            # 128-channel conv0: K-split, pass 1 leaves an fp32 padded-flat partial that pass 2 adds as its residual
+            # 128-channel conv0: K-split as above (16-bit partial in `out`, added in place by pass 2)
             assert not ctr and res is None
-            tmp = self._fbuf(ws, f"ksplit.{H}", (B * blk, 64), torch.float32, out.t.device)
-            L.check(lib.mcedm_conv_flat_fused(L.ptr(srcs[0].t), L.ptr(coefs[0]), L.ptr(w[:9]), None, B, H, W, 64, L.ptr(tmp), 1,
-                                              None, 0, 0, 0, 0, None, self._fmt, st), "conv_flat_fused")
-            L.check(lib.mcedm_conv_flat_fused(L.ptr(srcs[1].t), L.ptr(coefs[1]), L.ptr(w[9:18]), L.ptr(bias), B, H, W, 64,
-                                              L.ptr(out.t), 0, L.ptr(tmp), 1, 1, 0, 0, L.ptr(out.st) if stats else None,
-                                              self._fmt, st), "conv_flat_fused")
+            for i in (0, 1):
+                L.check(lib.mcedm_conv_flat_fused(L.ptr(srcs[i].t), L.ptr(coefs[i]), L.ptr(w[9 * i:9 * i + 9]),
+                                                  L.ptr(bias) if i else None, B, H, W, 64, L.ptr(out.t), 0,
+                                                  L.ptr(out.t) if i else None, i, 0, 0, 0,
+                                                  L.ptr(out.st) if (stats and i) else None, self._fmt, st), "conv_flat_fused")
         else:
             res_t = res.t if res is not None else None
             if ctr:
