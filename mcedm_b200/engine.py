@@ -421,6 +421,100 @@ class UNetEngine(TrainMixin, FusedMixin):
 
     # ------------------------------------------------------------------ per-kernel timing (bench roofline)
     @torch.no_grad()
+    def profile_kernels(self, x, noise_labels, cond, repeats: int = 3):
+        """CUDA-event time of every C-ABI launch of one forward pass (current plan), on the launching stream.
+        Returns a list of dicts {name, ms, flops, bytes} in launch order; ms = mean over `repeats`.  flops / bytes are
+        the ALGORITHMIC figures of the launch (what DESIGN.md section 4 states per kernel), derived from its arguments."""
+        x, nl, cond = self._check_inputs(x, noise_labels, cond)
+        self._fmt = self.infer_fmt
+        self.pack()
+        out = torch.empty(x.shape[0], self.unet.out_channels, x.shape[2], x.shape[3], device=x.device)
+        self._launch_all(x, nl, cond, out)
+        real = self.lib
+        runs = []
+
+        def v(a):
+            return a.value if hasattr(a, "value") else a
+
+        def work(name, a):
+            """(flops, bytes) of a launch from its C-ABI arguments (positions per include/mcedm_b200.h)."""
+            if name == "mcedm_conv_rows_fused":
+                n_halo, n_ctr, B, H, N, n_total, res_mode = v(a[2]), v(a[4]), v(a[7]), v(a[8]), v(a[9]), v(a[11]), v(a[15])
+                px = B * H * 128
+                out_b = 2 if v(a[13]) else 4
+                return (2.0 * px * N * 64 * (9 * n_halo + n_ctr),
+                        px * 64 * 2.0 * (n_halo + n_ctr) + px * N * out_b + (px * N * 2.0 * (1 if res_mode == 1 else 0.25)
+                                                                             if res_mode else 0.0))
+            if name == "mcedm_conv_flat_fused":
+                B, H, W, res_mode = v(a[4]), v(a[5]), v(a[6]), v(a[11])
+                px = B * H * W
+                return 2.0 * px * 64 * 576, px * 64 * 2.0 * (2 + {0: 0, 1: 1, 2: 0.25, 3: 4}[res_mode])
+            if name == "mcedm_conv_rows":
+                n_halo, n_ctr, B, H, N, res_mode = v(a[1]), v(a[3]), v(a[6]), v(a[7]), v(a[8]), v(a[12])
+                px = B * H * 128
+                return (2.0 * px * N * 64 * (9 * n_halo + n_ctr),
+                        px * 64 * 2.0 * (n_halo + n_ctr) + px * N * 4.0 * (1 + (1 if res_mode == 1 else 0.25 if res_mode else 0)))
+            if name == "mcedm_conv_flat":
+                B, H, W, res_mode = v(a[3]), v(a[4]), v(a[5]), v(a[9])
+                px = B * H * W
+                return 2.0 * px * 64 * 576, px * 64 * (2.0 + 4.0 * (1 + {0: 0, 1: 1, 2: 0.25, 3: 4}[res_mode]))
+            if name in ("mcedm_conv_igemm", "mcedm_conv_igemm16"):
+                n_src, n_seg, B, H, W, N = v(a[1]), v(a[5]), v(a[8]), v(a[9]), v(a[10]), v(a[11])
+                px = B * H * W
+                return 2.0 * px * N * 64 * n_seg, px * 64 * 2.0 * n_src + px * N * 2.0
+            if name == "mcedm_attention":
+                B, Lq = v(a[1]), v(a[2])
+                return 4.0 * B * Lq * Lq * 64, B * Lq * (192 + 64) * 2.0
+            if name == "mcedm_gn_apply16":
+                rs, B, H, W = v(a[5]), v(a[6]), v(a[7]), v(a[8])
+                n_in = B * H * W * 64
+                return 0.0, 2.0 * n_in + 2.0 * (n_in * 4 if rs == 1 else n_in // 4 if rs == 2 else n_in)
+            if name == "mcedm_gn_apply":
+                rs, B, H, W = v(a[9]), v(a[10]), v(a[11]), v(a[12])
+                n_in = B * H * W * 64
+                return 0.0, 4.0 * n_in + 2.0 * (n_in * 4 if rs == 1 else n_in // 4 if rs == 2 else n_in)
+            if name in ("mcedm_conv_in", "mcedm_conv_in16"):
+                cin, B, H, W = v(a[1]) + v(a[3]), v(a[6]), v(a[7]), v(a[8])
+                px = B * H * W
+                return 2.0 * px * 64 * 9 * cin, px * (cin * 4.0 + 64 * (2.0 if name.endswith("16") else 4.0))
+            return 0.0, 0.0
+
+        class _Proxy:
+            def __init__(self, rec):
+                self.rec = rec
+
+            def __getattr__(self, name):
+                fn = getattr(real, name)
+                if not name.startswith("mcedm_") or name in ("mcedm_flat_geometry", "mcedm_last_error"):
+                    return fn
+
+                def call(*a):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = fn(*a)
+                    e1.record()
+                    fl, by = work(name, a)
+                    self.rec.append(dict(name=name[6:], flops=fl, bytes=by, ev=(e0, e1)))
+                    return rc
+                return call
+
+        try:
+            for _ in range(repeats):
+                rec = []
+                self.lib = _Proxy(rec)
+                self._launch_all(x, nl, cond, out)
+                torch.cuda.synchronize()
+                runs.append(rec)
+        finally:
+            self.lib = real
+        res = []
+        for i, r in enumerate(runs[0]):
+            ms = sum(rr[i]["ev"][0].elapsed_time(rr[i]["ev"][1]) for rr in runs) / len(runs)
+            res.append(dict(name=r["name"], flops=r["flops"], bytes=r["bytes"], ms=ms))
+        return res
+
+    # (legacy per-conv timing of the unfused plan)
+    @torch.no_grad()
     def profile_convs(self, x, noise_labels, cond, repeats: int = 3, with_gn: bool = False):
         """CUDA-event time of every 3x3-conv launch (and, with_gn, every GroupNorm pass) of one forward pass, on the
         launching stream.  Returns a list of dicts (kind 'conv': N, n_seg, pixels, H, flops, ms; kind 'gn': bytes, ms),
