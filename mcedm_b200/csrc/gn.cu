@@ -87,16 +87,25 @@ __device__ __forceinline__ long long gn_out_index(const GnApplyParams& p, int b,
   return ((long long)b * Ho + y) * Wo + x;
 }
 
+// FAST (the 16-bit inference instantiation): SiLU through one MUFU.TANH instead of ex2 + rcp, as in the fused convs
+template <bool FAST = false>
 __device__ __forceinline__ float4 gn_act4(float4 v, const float4 a, const float4 b, int act) {
   v.x = fmaf(v.x, a.x, b.x);
   v.y = fmaf(v.y, a.y, b.y);
   v.z = fmaf(v.z, a.z, b.z);
   v.w = fmaf(v.w, a.w, b.w);
   if (act) {
-    v.x = silu_f(v.x);
-    v.y = silu_f(v.y);
-    v.z = silu_f(v.z);
-    v.w = silu_f(v.w);
+    if constexpr (FAST) {
+      v.x = silu_from_half_arg(0.5f * v.x);
+      v.y = silu_from_half_arg(0.5f * v.y);
+      v.z = silu_from_half_arg(0.5f * v.z);
+      v.w = silu_from_half_arg(0.5f * v.w);
+    } else {
+      v.x = silu_f(v.x);
+      v.y = silu_f(v.y);
+      v.z = silu_f(v.z);
+      v.w = silu_f(v.w);
+    }
   }
   return v;
 }
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
             const int y = ip / p.Win;
             opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
           }
-          out[opix * 8 + c8] = pack8(gn_act4(lo[k], a_lo, b_lo, p.act), gn_act4(hi[k], a_hi, b_hi, p.act), p.fmt);
+          out[opix * 8 + c8] = pack8(gn_act4<X16>(lo[k], a_lo, b_lo, p.act), gn_act4<X16>(hi[k], a_hi, b_hi, p.act), p.fmt);
         }
       }
     }
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       const int y = ip / p.Win, x = ip - y * p.Win;
       float4 xl, xh;
       gn_load8<X16>(p, gn_in_index(p, b, ip), c8, xl, xh);
-      const uint4 v = pack8(gn_act4(xl, a_lo, b_lo, p.act), gn_act4(xh, a_hi, b_hi, p.act), p.fmt);
+      const uint4 v = pack8(gn_act4<X16>(xl, a_lo, b_lo, p.act), gn_act4<X16>(xh, a_hi, b_hi, p.act), p.fmt);
       const long long o00 = gn_out_index(p, b, 2 * y, 2 * x, Ho, Wo);
       out[o00 * 8 + c8] = v;
       out[(o00 + 1) * 8 + c8] = v;
@@ -248,21 +257,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     }
   } else {
     const int Wo = p.Win >> 1, Ho = p.Hin >> 1;
-    for (int i = ps; i < p.pix_per_cta; i += 32) {
-      const int op = pix0 + i;
-      const int y = op / Wo, x = op - y * Wo;
-      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    // two output pixels (8 loads) in flight per thread before any dependent work
+    for (int i = ps; i < p.pix_per_cta; i += 64) {
+      float4 xl[2][4], xh[2][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float4 xl, xh;
-        gn_load8<X16>(p, gn_in_index(p, b, (2 * y + (k >> 1)) * p.Win + 2 * x + (k & 1)), c8, xl, xh);
-        const float4 l = gn_act4(xl, a_lo, b_lo, p.act), h = gn_act4(xh, a_hi, b_hi, p.act);
-        lo.x += l.x; lo.y += l.y; lo.z += l.z; lo.w += l.w;
-        hi.x += h.x; hi.y += h.y; hi.z += h.z; hi.w += h.w;
+      for (int u = 0; u < 2; ++u) {
+        const int op = pix0 + i + 32 * u;
+        const int y = op / Wo, x = op - y * Wo;
+        if (i + 32 * u < p.pix_per_cta) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            gn_load8<X16>(p, gn_in_index(p, b, (2 * y + (k >> 1)) * p.Win + 2 * x + (k & 1)), c8, xl[u][k], xh[u][k]);
+        }
       }
-      lo.x *= 0.25f; lo.y *= 0.25f; lo.z *= 0.25f; lo.w *= 0.25f;
-      hi.x *= 0.25f; hi.y *= 0.25f; hi.z *= 0.25f; hi.w *= 0.25f;
-      out[gn_out_index(p, b, y, x, Ho, Wo) * 8 + c8] = pack8(lo, hi, p.fmt);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (i + 32 * u < p.pix_per_cta) {
+          const int op = pix0 + i + 32 * u;
+          const int y = op / Wo, x = op - y * Wo;
+          float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 l = gn_act4<X16>(xl[u][k], a_lo, b_lo, p.act), h = gn_act4<X16>(xh[u][k], a_hi, b_hi, p.act);
+            lo.x += l.x; lo.y += l.y; lo.z += l.z; lo.w += l.w;
+            hi.x += h.x; hi.y += h.y; hi.z += h.z; hi.w += h.w;
+          }
+          lo.x *= 0.25f; lo.y *= 0.25f; lo.z *= 0.25f; lo.w *= 0.25f;
+          hi.x *= 0.25f; hi.y *= 0.25f; hi.z *= 0.25f; hi.w *= 0.25f;
+          out[gn_out_index(p, b, y, x, Ho, Wo) * 8 + c8] = pack8(lo, hi, p.fmt);
+        }
+      }
     }
   }
 }

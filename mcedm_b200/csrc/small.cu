@@ -14,39 +14,51 @@
 namespace mcedm {
 
 // ------------------------------------------- emb MLP -------------------------------------------
-// grid = Bemb, block = 128
+// grid = (Bemb, n_aff), block = 128 (4 warps).  Every CTA recomputes the 64-wide embedding of its sample (two 64x64
+// mat-vecs) and then applies ONE block's affine (128x64); mat-vec rows are spread over the warps with coalesced
+// weight reads and a shuffle reduction.  (One CTA per sample doing all 16 affines serially with one strided weight
+// row per thread took 80 us per evaluation in the sampling loop, where Bemb = 1.)
+__device__ __forceinline__ float warp_dot64(const float* __restrict__ w_row, const float* x, int lane) {
+  float acc = fmaf(w_row[lane], x[lane], w_row[lane + 32] * x[lane + 32]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  return acc;
+}
+
 __global__ void __launch_bounds__(128)
 emb_mlp_kernel(const float* __restrict__ c_noise, const float* __restrict__ freqs, const float* __restrict__ w0,
                const float* __restrict__ b0, const float* __restrict__ w1, const float* __restrict__ b1,
                const float* __restrict__ aff_w, const float* __restrict__ aff_b, int n_aff, int Bemb,
                float* __restrict__ emb_out, float* __restrict__ out) {
   __shared__ float e[64], h0[64], h1[64];
-  const int b = blockIdx.x, t = threadIdx.x;
+  const int b = blockIdx.x, a = blockIdx.y, t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   if (t < 32) {
     const float ang = c_noise[b] * freqs[t];
     e[t] = cosf(ang);
     e[t + 32] = sinf(ang);
   }
   __syncthreads();
-  if (t < 64) {
-    float acc = 0.f;
-    for (int k = 0; k < 64; ++k) acc = fmaf(e[k], w0[t * 64 + k], acc);
-    h0[t] = silu_f(acc + b0[t]);
+  for (int r = warp; r < 64; r += 4) {
+    const float acc = warp_dot64(w0 + r * 64, e, lane);
+    if (lane == 0) h0[r] = silu_f(acc + b0[r]);
   }
   __syncthreads();
-  if (t < 64) {
-    float acc = 0.f;
-    for (int k = 0; k < 64; ++k) acc = fmaf(h0[k], w1[t * 64 + k], acc);
-    const float v = silu_f(acc + b1[t]);
-    h1[t] = v;
-    if (emb_out) emb_out[b * 64 + t] = v;
+  for (int r = warp; r < 64; r += 4) {
+    const float acc = warp_dot64(w1 + r * 64, h0, lane);
+    if (lane == 0) {
+      const float v = silu_f(acc + b1[r]);
+      h1[r] = v;
+      if (emb_out && a == 0) emb_out[b * 64 + r] = v;
+    }
   }
   __syncthreads();
-  for (int a = 0; a < n_aff; ++a) {
-    const float* w = aff_w + ((long long)a * 128 + t) * 64;
-    float acc = 0.f;
-    for (int k = 0; k < 64; ++k) acc = fmaf(h1[k], w[k], acc);
-    out[((long long)a * Bemb + b) * 128 + t] = acc + aff_b[a * 128 + t];
+  if (a < n_aff) {
+    const float* w = aff_w + (long long)a * 128 * 64;
+    for (int r = warp; r < 128; r += 4) {
+      const float acc = warp_dot64(w + r * 64, h1, lane);
+      if (lane == 0) out[((long long)a * Bemb + b) * 128 + r] = acc + aff_b[a * 128 + r];
+    }
   }
 }
 
@@ -163,7 +175,7 @@ extern "C" int mcedm_emb_mlp(const float* c_noise, const float* freqs, const flo
                              int Bemb, float* emb_out, float* out, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(Bemb >= 1 && n_aff >= 0, "emb_mlp: bad sizes");
-  emb_mlp_kernel<<<Bemb, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c_noise, freqs, w0, b0, w1, b1, aff_w,
+  emb_mlp_kernel<<<dim3(Bemb, n_aff > 0 ? n_aff : 1), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c_noise, freqs, w0, b0, w1, b1, aff_w,
                                                                             aff_b, n_aff, Bemb, emb_out, out);
   MCEDM_CUDA(cudaGetLastError());
   return 0;

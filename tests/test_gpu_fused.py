@@ -275,3 +275,4 @@ def test_conv_in16_matches_fp32_conv(L, dev):
     v = ref.reshape(B, H * W, 16, 4)
     tot = st.reshape(B, -1, 16, 2).double().sum(1)
     assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=1.0)
+
