@@ -335,6 +335,12 @@ MCEDM_API int mcedm_ema_update(float* ema, const float* p, long long n, float be
 /* -------------------------------------------------------------------------------------------- */
 /* bring-up / checker kernels (tests only; not on the product path)                              */
 /* -------------------------------------------------------------------------------------------- */
+/* tensor-pipe + shared-memory operand-fetch ceiling: every SM issues n_tiles x 36 tcgen05.mma (M=128, N, K=16, the conv
+ * kernels' descriptor pattern) and nothing else; cycles_per_cta[sm] = clock64 ticks (DEVICE int64 [#SMs]). */
+MCEDM_API int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_cta, void* stream);
+/* bring-up: per-CTA cycles spent in each role's barrier waits by the last fused conv_rows launch run with MCEDM_DBG=32
+ * (HOST int64 [160][8]: h_empty, acc_empty, h_ready, acc_full, h_full waits; epilogue, MMA, producer role totals) */
+MCEDM_API int mcedm_debug_rows(long long* host_out);
 MCEDM_API int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int row_shift, int base_offset, int b_mn_major,
                      float* out, void* stream);
 /* seg_dev: DEVICE int array [n_seg][3] = (src, dy, dx). Same math as mcedm_conv_igemm on CUDA cores. */

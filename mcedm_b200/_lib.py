@@ -62,6 +62,8 @@ _PROTOTYPES = {
     "mcedm_edm_correct": [_vp, _vp, _vp, _vp, _vp, _d, _d, _f, _f, C.c_longlong, _vp, _vp, _vp],
     "mcedm_edm_precond_in": [_vp, _vp, _i, _i, C.c_longlong, _vp, _vp],
     "mcedm_edm_precond_out": [_vp, _vp, _vp, _vp, _i, _i, C.c_longlong, _vp, _vp],
+    "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
+    "mcedm_debug_rows": [_vp],
     "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
     "mcedm_conv_direct_ref": [_vpp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
 }

@@ -19,7 +19,10 @@
 // bound by the exp/convert work of the 4 softmax warps, not by the tensor pipe.
 //   warp 0 : TMA producer (Q once; K blocks in pass 1; K and V blocks in pass 2; 3-stage ring)
 //   warp 1 : MMA issuer (S double-buffered in TMEM so softmax of block j overlaps QK^T of block j+1)
-//   warps 2-5 : softmax / epilogue, one query row per thread (TMEM lane == row: no shuffles needed)
+//   warps 2-9 : softmax / epilogue: two warps per TMEM lane quarter, each owning one 64-key half of every S block of
+//               its 32 query rows (TMEM lane == row: no shuffles); the halves' row maxima / row sums meet once per
+//               pass through shared memory.  (With 4 softmax warps = one per scheduler, the dependent
+//               ld -> ex2 -> cvt -> st chain had nothing to overlap with and set the kernel's pace.)
 #include "ptx.cuh"
 #include "runtime.cuh"
 #include "../../include/mcedm_b200.h"
@@ -37,7 +40,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out,
             float* __restrict__ lse_out, int fmt, unsigned int* err) {
   extern __shared__ uint8_t smem_raw[];
@@ -55,6 +58,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   uint64_t* kv_full = bars + 10;      // stages
   uint64_t* kv_empty = bars + 10 + kKvStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kKvStages);
+  float* xch_m = reinterpret_cast<float*>(p_smem + 2 * 2 * kTile + 256);   // [2 halves][128 rows] partial row maxima
+  float* xch_l = xch_m + 256;                                              // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = L / 128;
@@ -68,8 +73,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     mbar_init(o_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&s_empty[i], 8);                              // one arrival per softmax warp
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_empty[i], 1);
     }
     for (int i = 0; i < kKvStages; ++i) {
@@ -151,6 +156,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     }
   } else {
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;          // which 64-key half of every S block this warp owns
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c1 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
@@ -161,7 +167,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       mbar_wait(&s_full[sb], ns & 1u, err, 0x1600 + sb);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * hsel; c < 2 * hsel + 2; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
         tmem_wait_ld();
@@ -174,8 +180,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
         m = fmaxf(m, fmaxf(cm0, cm1));
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[sb]);
+      mbar_arrive_warp(&s_empty[sb]);
     }
+    // the two halves of a row exchange their partial maxima
+    xch_m[hsel * 128 + row] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(xch_m[row], xch_m[128 + row]);
     const float mc = m * c1;
     // ---------------- pass 2: P = exp2(S*c1 - m*c1) -> bf16 -> smem ----------------
     for (int j = 0; j < nblk; ++j) {
@@ -187,7 +197,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       tc_fence_after();
       uint8_t* prow = p_smem + pb * 2 * kTile + row * 128;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * hsel; c < 2 * hsel + 2; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
         tmem_wait_ld();
@@ -214,19 +224,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
         }
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[sb]);
+      mbar_arrive_warp(&s_empty[sb]);
       fence_proxy_async_smem();     // generic-proxy P writes -> visible to the UMMA (async proxy) reads
-      mbar_arrive(&p_full[pb]);
+      mbar_arrive_warp(&p_full[pb]);
     }
     // ---------------- epilogue: O / l -> bf16 ----------------
+    xch_l[hsel * 128 + row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l = xch_l[row] + xch_l[128 + row];
     mbar_wait(o_full, 0, err, 0x1900);
     tc_fence_after();
     const float inv_l = 1.0f / l;
     // saved for the backward: P[i][j] = exp2(S[i][j] * c1 - lse2[i])
-    if (lse_out) lse_out[(long long)b * L + q0 + row] = mc + log2f(l);
+    if (lse_out && hsel == 0) lse_out[(long long)b * L + q0 + row] = mc + log2f(l);
     __nv_bfloat16* orow = out + ((long long)b * L + q0 + row) * 64;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    for (int c = hsel; c < hsel + 1; ++c) {
       uint32_t v[32];
       tmem_ld_x32(tmem_o + lane_addr + c * 32, v);
       tmem_wait_ld();
@@ -294,13 +307,13 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
   if (rc) return rc;
   unsigned int* err = watchdog_ptr();
   MCEDM_REQUIRE(err != nullptr, "attention: no watchdog word");
-  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 256;
+  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 256 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
     MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  attn_kernel<<<B * (L / 128), 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  attn_kernel<<<B * (L / 128), 320, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0, err);
   MCEDM_CUDA(cudaGetLastError());
   return 0;

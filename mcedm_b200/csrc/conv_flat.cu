@@ -172,12 +172,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     mbar_init(w_full, 1);
     for (int i = 0; i < Cfg::ACC_BUFS; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 32 * Cfg::EPI_WARPS);
+      mbar_init(&acc_empty[i], Cfg::EPI_WARPS);              // one arrival per warp
     }
     for (int i = 0; i < S; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 1);
-      mbar_init(&c_ready[i], FUSED ? 32 * Cfg::XF_WARPS : 1);
+      mbar_init(&c_ready[i], FUSED ? Cfg::XF_WARPS : 1);
     }
     fence_barrier_init();
   }
@@ -318,7 +318,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * N + ch * Cfg::CH, v);
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        mbar_arrive_warp(&acc_empty[buf]);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int pj = jj ^ (lane & 7);
@@ -420,7 +420,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * N + ch * Cfg::CH, v);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
+      mbar_arrive_warp(&acc_empty[buf]);
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const int pj = jj ^ (lane & 7);
@@ -523,7 +523,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
         fence_proxy_async_smem();
       }
-      mbar_arrive(&c_ready[slot]);
+      mbar_arrive_warp(&c_ready[slot]);
     }
   }
 

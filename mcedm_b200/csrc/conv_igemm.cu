@@ -100,7 +100,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 4);                           // one arrival per epilogue warp
     }
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&a_full[i], 1);
@@ -222,7 +222,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
         tmem_wait_ld();
         if (ch == Cfg::NCH - 1) {
           tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);  // all of this thread's TMEM reads of this buffer are done
+          mbar_arrive_warp(&acc_empty[buf]);  // all of this warp's TMEM reads of this buffer are done
         }
         // registers (one pixel row per thread) -> swizzled staging rows
 #pragma unroll

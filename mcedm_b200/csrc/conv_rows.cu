@@ -38,6 +38,7 @@
 #include "../../include/mcedm_b200.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace mcedm {
 
@@ -65,6 +66,7 @@ struct RowsParams {
   int n_total;           // channels per pixel of out / res (== N unless an output-channel window is used)
   int w_rows;            // rows per segment of the packed weight matrix (== n_total)
   const float* coef[2];  // FUSED: per halo source, fp32 [B][128] = (a | b) of y = silu(a*x + b); NULL = no transform
+  int dbg;               // bring-up instrumentation (MCEDM_DBG): 32 time every role's barrier waits, 64 time MMA issue / commits
   int res_pitch, res_blk; // FUSED, res_mode 2: the half-resolution residual is padded-flat (0,0: dense NHWC)
 };
 
@@ -78,9 +80,26 @@ struct RowsCfg {
   static constexpr int XF_WARPS = FUSED ? 4 : 0;            // GroupNorm+SiLU transform warps (after the epilogue warps)
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
-  static constexpr int ACC_BUFS = 4;
-  static constexpr int TMEM_COLS = (ACC_BUFS * N <= 32) ? 32 : (ACC_BUFS * N <= 64) ? 64 : (ACC_BUFS * N <= 128) ? 128 : 256;
+  // STACK (fused N = 64): the three vertical taps of a filter column are stacked into ONE N = 192 MMA per input row
+  // (see the MMA issuer); eight 64-column accumulators then rotate through all 512 TMEM columns.
+  static constexpr bool STACK = FUSED && N == 64;
+  static constexpr int ACC_BUFS = STACK ? 8 : 4;
+  static constexpr int TMEM_COLS = (ACC_BUFS * N <= 32) ? 32 : (ACC_BUFS * N <= 64) ? 64 : (ACC_BUFS * N <= 128) ? 128
+                                   : (ACC_BUFS * N <= 256) ? 256 : 512;
 };
+
+// bring-up instrumentation (MCEDM_DBG & 32): cycles each role spends inside its barrier waits, per CTA
+__device__ long long g_rows_dbg[160][8];
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, unsigned int* err, uint32_t tag, long long& acc,
+                                           bool on) {
+  if (!on) {
+    mbar_wait(bar, parity, err, tag);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err, tag);
+  acc += clock64() - t0;
+}
 
 // UMMA descriptor = constant high word | (address >> 4): the issuing thread only does 32-bit adds
 __device__ __forceinline__ uint64_t desc_from_lo(uint32_t addr) {
@@ -142,12 +161,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     mbar_init(w_full, 1);
     for (int i = 0; i < Cfg::ACC_BUFS; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 32 * Cfg::EPI_WARPS);
+      mbar_init(&acc_empty[i], Cfg::EPI_WARPS);              // one arrival per warp
     }
     for (int i = 0; i < p.n_slots; ++i) {
       mbar_init(&h_full[i], 1);
       mbar_init(&h_empty[i], 1);
-      mbar_init(&h_ready[i], 32 * Cfg::XF_WARPS + (FUSED ? 0 : 1));
+      mbar_init(&h_ready[i], Cfg::XF_WARPS + (FUSED ? 0 : 1));
     }
     for (int i = 0; i < p.n_cslots; ++i) {
       mbar_init(&c_full[i], 1);
@@ -168,9 +187,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       mbar_expect_tx(w_full, (uint32_t)(n_seg * Cfg::W_SEG_BYTES));
-      for (int s = 0; s < n_seg; ++s)
-        tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * p.w_rows + p.n_off);
+      for (int s = 0; s < n_seg; ++s) {
+        // STACK keeps the taps of one filter column contiguous: slot (kx*3 + ky) holds tap (ky, kx)
+        const int slot = (Cfg::STACK && s < 9) ? (s % 3) * 3 + s / 3 : s;
+        tma_load_2d(w_smem + slot * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * p.w_rows + p.n_off);
+      }
       uint32_t hl = 0, cl = 0;   // halo rows / centre tiles loaded so far
+      long long dbg_w0 = 0;
+      const long long dbg_t0 = clock64();
       long long r = r_begin;
       while (r < r_end) {
         const int b = (int)(r / p.H);
@@ -178,7 +202,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
         for (int k = 0; k < R + 2; ++k) {
           const uint32_t slot = hl % (uint32_t)p.n_slots, ph = (hl / (uint32_t)p.n_slots) & 1u;
-          mbar_wait(&h_empty[slot], ph ^ 1u, p.err, 0x2100 + slot);
+          timed_wait(&h_empty[slot], ph ^ 1u, p.err, 0x2100 + slot, dbg_w0, (p.dbg & 32) != 0);
           mbar_expect_tx(&h_full[slot], (uint32_t)(p.n_halo * kHaloTx));
           tma_load_4d(h_smem + slot * slot_bytes, &tm_h0, &h_full[slot], 0, -1, y0 - 1 + k, b);
           if (p.n_halo > 1)
@@ -195,6 +219,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
         r += R;
       }
+      if (p.dbg & 32) {
+        g_rows_dbg[blockIdx.x][0] = dbg_w0;
+        g_rows_dbg[blockIdx.x][7] = clock64() - dbg_t0;
+      }
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
@@ -202,6 +230,148 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // elected lane issues each tcgen05 instruction.  (Running this under `if (lane == 0)` made ptxas
     // emit an election loop + R2UR moves per MMA: ~4K issue cycles per tile on one thread, which was
     // the kernel's bottleneck.)
+    if constexpr (Cfg::STACK) {
+      // ---------------------------------------------------------------------------------------------------------
+      // ky-stacked issue (N = 192).  With N = 64 every MMA re-reads its 4 KB A tile for 2 KB of weights and the pure
+      // issue loop tops out at 1865 cycles per tile against 1152 of tensor time (scripts/probe_mma_rate.py: shared-
+      // memory operand fetch); N = 128..192 runs at 96 % of the pipe.  So the loop is turned inside out: instead of
+      // "output row <- 3 input rows x 3 taps" it is "input row k -> the three output rows k, k-1, k-2 it feeds", ONE
+      // MMA per (kx, K step) with the weights of ky = 0, 1, 2 stacked as 192 B-rows.  Its 192 accumulator columns are
+      // the 64-column accumulators of those three output rows, laid out in DESCENDING tile order around the 512 TMEM
+      // columns so that they are adjacent; 12 MMAs per row instead of 36, A traffic cut 3x.  Splits: the very first
+      // MMA into a fresh accumulator must not accumulate (single flag per instruction -> ky = 0 goes alone on
+      // (kx, ks) = (0, 0)); a window that wraps past column 511 is issued in two pieces; segment edges drop the
+      // sub-blocks whose output row is outside the CTA's range.
+      // ---------------------------------------------------------------------------------------------------------
+      const uint32_t idesc1 = umma_idesc_16(128, 64, 0, 0, p.fmt), idesc2 = umma_idesc_16(128, 128, 0, 0, p.fmt),
+                     idesc3 = umma_idesc_16(128, 192, 0, 0, p.fmt);
+      mbar_wait(w_full, 0, p.err, 0x2300);
+      tc_fence_after();
+      const uint32_t ns = (uint32_t)p.n_slots;
+      const uint32_t w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);
+      const uint32_t h_lo = (smem_u32(h_smem) >> 4) | (1u << 16);
+      const uint32_t c_lo = (smem_u32(c_smem) >> 4) | (1u << 16);
+      const uint32_t slot16 = (uint32_t)slot_bytes >> 4;
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
+      uint32_t hs = 0, hph = 0;             // ring slot / phase of the next input row
+      uint32_t cs = 0, cph = 0;
+      uint32_t t0 = 0;                      // tile counter of the current segment's first output row
+      long long dbg_w1 = 0, dbg_w2 = 0;
+      const long long dbg_t0 = clock64();
+      long long r = r_begin;
+      while (r < r_end) {
+        const int b = (int)(r / p.H);
+        const int y0 = (int)(r - (long long)b * p.H);
+        const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+        for (int k = 0; k < R + 2; ++k) {
+          if (k < R) {                      // output row k receives its first contribution from this input row
+            const uint32_t tn = t0 + (uint32_t)k;
+            timed_wait(&acc_empty[tn & 7u], ((tn >> 3) & 1u) ^ 1u, p.err, 0x2400 + (tn & 7u), dbg_w1, (p.dbg & 32) != 0);
+          }
+          timed_wait(&h_ready[hs], hph, p.err, 0x2500 + hs, dbg_w2, (p.dbg & 32) != 0);
+          const bool ctr_now = p.n_ctr > 0 && k >= 2;      // centre tiles of output row k-2, just before it completes
+          if (ctr_now) mbar_wait(&c_full[cs], cph, p.err, 0x2600 + cs);
+          tc_fence_after();
+          const uint32_t a_row = h_lo + hs * slot16;
+          const int kyA = k - (R - 1) > 0 ? k - (R - 1) : 0;   // output row k - ky must lie in [0, R)
+          const int kyB = k < 2 ? k : 2;
+          // Straight-line issue: every descriptor word below is (a value formed once per row in warp-uniform code) +
+          // (a compile-time constant), so the elected lane executes little more than the tcgen05.mma themselves.
+          // (A first version computed windows / splits inside the elected branch: ~165 cycles of dependent scalar
+          // code per MMA, 2000 cycles per row before a single MMA was issued.)
+          const uint32_t blk0 = (8u - ((t0 + (uint32_t)(k - kyA)) & 7u)) & 7u;      // accumulator block of B-row kyA
+          const int nky = kyB - kyA + 1;
+          const int split = (int)(8u - blk0) < nky ? (int)(8u - blk0) : nky;        // B-rows before the window wraps
+          const uint32_t d0 = tmem_base + blk0 * 64u;                                // first piece
+          const uint32_t d1 = tmem_base + ((blk0 + (uint32_t)split) & 7u) * 64u;     // piece after the wrap / after ky = 0
+          const uint32_t wrow = w_lo + (uint32_t)kyA * (Cfg::W_SEG_BYTES >> 4);
+          const bool fresh = kyA == 0;        // output row k starts here: its very first MMA must not accumulate
+          const long long dbg_c0 = (p.dbg & 64) ? clock64() : 0;
+          if (nky == 3 && split == 3) {
+            // interior row, contiguous window: N = 64 (fresh) + N = 128, then 11 x N = 192
+            if (elect_one()) {
+              umma_f16(d0, desc(a_row), desc(wrow), idesc1, 0u);
+              umma_f16(d0 + 64u, desc(a_row), desc(wrow + (Cfg::W_SEG_BYTES >> 4)), idesc2, 1u);
+#pragma unroll
+              for (int i = 1; i < 12; ++i) {
+                const int kx = i >> 2, ks = i & 3;
+                umma_f16(d0, desc(a_row + kx * 8 + ks * 2), desc(wrow + kx * 3 * (Cfg::W_SEG_BYTES >> 4) + ks * 2), idesc3, 1u);
+              }
+            }
+          } else {
+            // edge rows (fewer B-rows) and wrapped windows: pieces [kyA, kyA+split) at d0 and [kyA+split, kyB] at d1;
+            // a fresh accumulator additionally takes ky = 0 alone on the first MMA
+            const int n0 = split, n1 = nky - split;
+            const uint32_t i0 = n0 == 1 ? idesc1 : n0 == 2 ? idesc2 : idesc3;
+            const uint32_t i1 = n1 == 1 ? idesc1 : idesc2;
+            const uint32_t w1 = wrow + (uint32_t)n0 * (Cfg::W_SEG_BYTES >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < 12; ++i) {
+                const int kx = i >> 2, ks = i & 3;
+                const uint64_t ad = desc(a_row + kx * 8 + ks * 2);
+                const uint32_t wo = kx * 3 * (Cfg::W_SEG_BYTES >> 4) + ks * 2;
+                if (i == 0 && fresh && n0 > 1) {
+                  // split the first piece: ky = 0 fresh, the rest of it accumulating
+                  umma_f16(d0, ad, desc(wrow), idesc1, 0u);
+                  umma_f16(d0 + 64u, ad, desc(wrow + (Cfg::W_SEG_BYTES >> 4)), n0 == 2 ? idesc1 : idesc2, 1u);
+                } else {
+                  umma_f16(d0, ad, desc(wrow + wo), i0, (i == 0 && fresh) ? 0u : 1u);
+                }
+                if (n1 > 0) umma_f16(d1, ad, desc(w1 + wo), i1, 1u);
+              }
+            }
+          }
+          const long long dbg_c1 = (p.dbg & 64) ? clock64() : 0;
+          if (elect_one()) {
+            umma_commit(&h_empty[hs]);                       // an input row is consumed entirely by its own step
+            if (k >= 2) {
+              const uint32_t td = t0 + (uint32_t)(k - 2);    // output row k-2 is complete after this step
+              if (ctr_now) {
+                const uint32_t blk = (8u - (td & 7u)) & 7u;
+                for (int s = 0; s < p.n_ctr; ++s) {
+                  const uint64_t ad = desc(c_lo + ((cs * (uint32_t)cslot_bytes + s * kCtrBytes) >> 4));
+                  const uint64_t bd = desc(w_lo + (9 + s) * (Cfg::W_SEG_BYTES >> 4));
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_base + blk * 64u, ad + 2 * ks, bd + 2 * ks, idesc1, 1u);
+                }
+                umma_commit(&c_empty[cs]);
+              }
+              umma_commit(&acc_full[td & 7u]);
+            }
+          }
+          if (p.dbg & 64) {
+            const long long dbg_c2 = clock64();
+            dbg_w1 += dbg_c1 - dbg_c0;                       // MMA issue
+            dbg_w2 += dbg_c2 - dbg_c1;                       // commits
+          }
+          __syncwarp();
+          if (++hs == ns) {
+            hs = 0;
+            hph ^= 1u;
+          }
+          if (ctr_now && ++cs == (uint32_t)p.n_cslots) {
+            cs = 0;
+            cph ^= 1u;
+          }
+        }
+        t0 += (uint32_t)R;
+        r += R;
+      }
+      if (p.dbg & 64) {                                      // only the elected lane measured: take the warp maximum
+        for (int off = 16; off; off >>= 1) {
+          const long long o1 = __shfl_xor_sync(0xffffffffu, dbg_w1, off), o2 = __shfl_xor_sync(0xffffffffu, dbg_w2, off);
+          dbg_w1 = o1 > dbg_w1 ? o1 : dbg_w1;
+          dbg_w2 = o2 > dbg_w2 ? o2 : dbg_w2;
+        }
+      }
+      if ((p.dbg & 96) && lane == 0) {
+        g_rows_dbg[blockIdx.x][1] = dbg_w1;
+        g_rows_dbg[blockIdx.x][2] = dbg_w2;
+        g_rows_dbg[blockIdx.x][6] = clock64() - dbg_t0;
+      }
+    } else
     // Kept lean on purpose: this single warp's instruction stream paces the tensor pipe.  Ring positions are
     // wrap-around counters (no integer division), the three input rows' descriptor words are formed once per tile,
     // and ONE elected lane issues the tile's 36 tcgen05.mma back to back with immediate descriptor offsets
@@ -343,6 +513,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
     };
     if (r_begin < r_end) load_res(r_begin);
+    long long dbg_w3 = 0;
+    const long long dbg_t0 = clock64();
     uint32_t tcount = 0;
     for (long long r = r_begin; r < r_end; ++r, ++tcount) {
       const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
@@ -354,14 +526,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
       for (int itr = 0; itr < (FUSED ? Cfg::U : 1); ++itr) rh[itr] = rh_n[itr];
       if (r + 1 < r_end) load_res(r + 1);
-      mbar_wait(&acc_full[buf], aph, p.err, 0x2700 + buf);
+      timed_wait(&acc_full[buf], aph, p.err, 0x2700 + buf, dbg_w3, (p.dbg & 32) != 0);
       tc_fence_after();
       uint32_t v[Cfg::CH];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * N + ch * Cfg::CH;
+      const uint32_t acc_col = Cfg::STACK ? ((8u - buf) & 7u) * 64u : buf * N;     // STACK: descending tile order
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + ch * Cfg::CH;
       if constexpr (Cfg::CH == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
+      mbar_arrive_warp(&acc_empty[buf]);
 #pragma unroll
       for (int j = 0; j < Cfg::U; ++j) {
         const int pj = j ^ (lane & (Cfg::U - 1));
@@ -414,6 +587,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
       __syncwarp();
     }
+    if ((p.dbg & 32) && warp == 2 && lane == 0) {
+      g_rows_dbg[blockIdx.x][3] = dbg_w3;
+      g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
+    }
   } else {
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
@@ -422,6 +599,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int j = t & 7;
     const int prow = t >> 3;                // 0 .. 15
     uint32_t hl = 0;
+    long long dbg_w4 = 0;
     long long r = r_begin;
     while (r < r_end) {
       const int b = (int)(r / p.H);
@@ -446,7 +624,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
       for (int k = 0; k < R + 2; ++k, ++hl) {
         const uint32_t slot = hl % (uint32_t)p.n_slots, ph = (hl / (uint32_t)p.n_slots) & 1u;
-        mbar_wait(&h_full[slot], ph, p.err, 0x2800 + slot);
+        timed_wait(&h_full[slot], ph, p.err, 0x2800 + slot, dbg_w4, (p.dbg & 32) != 0);
         const int y = y0 - 1 + k;
         if (y >= 0 && y < p.H && p.coef[0] != nullptr) {   // out-of-image rows are TMA zero fill and must stay zero
 #pragma unroll
@@ -473,10 +651,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
           fence_proxy_async_smem();
         }
-        mbar_arrive(&h_ready[slot]);
+        mbar_arrive_warp(&h_ready[slot]);
       }
       r += R;
     }
+    if ((p.dbg & 32) && t == 0) g_rows_dbg[blockIdx.x][4] = dbg_w4;
   }
 
   tc_fence_before();
@@ -594,6 +773,7 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
   p.w_rows = n_total;
   p.res_pitch = res_pitch;
   p.res_blk = res_blk;
+  if (const char* e = getenv("MCEDM_DBG")) p.dbg = atoi(e);
   for (int i = 0; i < n_halo && i < 2; ++i) {
     p.coef[i] = halo_coef ? halo_coef[i] : nullptr;      // all NULL: the sources are already-normalised operands
     MCEDM_REQUIRE((p.coef[i] != nullptr) == (p.coef[0] != nullptr), "conv_rows_fused: coefficients for all sources or none");
@@ -602,10 +782,18 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
   int rc = rows_common(p, tm_w, tm_h, tm_c, halo_src, n_halo, ctr_src, n_ctr, w_packed, B, H, N);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MCEDM_REQUIRE(N != 64 || n_halo == 1, "conv_rows_fused: N = 64 takes one halo source (K-split 128-channel convs)");
   switch (N) {
     case 16: return launch_rows<16, true>(tm_w, tm_h, tm_c, p, st);
     case 32: return launch_rows<32, true>(tm_w, tm_h, tm_c, p, st);
     case 64: return launch_rows<64, true>(tm_w, tm_h, tm_c, p, st);
     default: return fail(-1, "conv_rows_fused: N=%d unsupported (16, 32, 64)", N);
   }
+}
+
+extern "C" int mcedm_debug_rows(long long* host_out) {
+  using namespace mcedm;
+  MCEDM_CUDA(cudaDeviceSynchronize());
+  MCEDM_CUDA(cudaMemcpyFromSymbol(host_out, g_rows_dbg, sizeof(long long) * 160 * 8));
+  return 0;
 }

@@ -110,6 +110,97 @@ __global__ void conv_direct_ref_kernel(const __nv_bfloat16* s0, const __nv_bfloa
 
 }  // namespace mcedm
 
+namespace mcedm {
+// Pure issue-rate probe: one CTA per SM issues `n_tiles` x 36 tcgen05.mma (M = 128, N, K = 16, both operands in
+// shared memory with the conv kernels' descriptor pattern: 9 row-shifted A views x 4 K steps, 9 weight segments) and
+// nothing else - no TMA, no epilogue, uninitialised operands.  cycles[cta] = clock64 ticks for the whole loop.  This
+// is the tensor-pipe + shared-memory operand-fetch ceiling the conv kernels are measured against.
+template <int N>
+__global__ void __launch_bounds__(64, 1) probe_mma_rate_kernel(int n_tiles, long long* cycles, unsigned int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_smem = smem;                          // 9 x N x 128 B
+  uint8_t* a_smem = smem + 9 * N * 128;            // 3 input rows of 17 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + 3 * 17408);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 1) {
+    const uint32_t idesc = umma_idesc_16(128, N, 0, 0, 1);
+    const uint32_t w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);
+    const uint32_t a_lo = (smem_u32(a_smem) >> 4) | (1u << 16);
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kHi) << 32) | lo; };
+    const long long t0 = clock64();
+    for (int t = 0; t < n_tiles; ++t) {
+      const uint32_t buf = (uint32_t)t & 3u;
+      if (t >= 4) mbar_wait(&bars[buf], (((uint32_t)t >> 2) - 1u) & 1u, err, 0x910 + buf);   // accumulator's previous use done
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint64_t ad = desc(a_lo + ky * (17408 >> 4) + kx * 8);
+            const uint64_t bd = desc(w_lo + (ky * 3 + kx) * (N * 128 >> 4));
+            umma_f16(tmem_base + buf * N, ad, bd, idesc, (ky | kx) != 0 ? 1u : 0u);
+            umma_f16(tmem_base + buf * N, ad + 2, bd + 2, idesc, 1u);
+            umma_f16(tmem_base + buf * N, ad + 4, bd + 4, idesc, 1u);
+            umma_f16(tmem_base + buf * N, ad + 6, bd + 6, idesc, 1u);
+          }
+        }
+        umma_commit(&bars[buf]);
+      }
+      __syncwarp();
+    }
+    // drain: wait for the last use of every accumulator buffer
+    for (int t = (n_tiles > 4 ? n_tiles - 4 : 0); t < n_tiles; ++t)
+      mbar_wait(&bars[t & 3], ((uint32_t)t >> 2) & 1u, err, 0x920 + (t & 3));
+    const long long t1 = clock64();
+    if (elect_one()) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+}  // namespace mcedm
+
+extern "C" int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_cta, void* stream) {
+  using namespace mcedm;
+  unsigned int* err = watchdog_ptr();
+  MCEDM_REQUIRE(err != nullptr, "probe_mma_rate: no watchdog word");
+  MCEDM_REQUIRE(n_tiles >= 1 && (N == 64 || N == 128 || N == 256), "probe_mma_rate: N in {64,128,256}");
+  const int smem = 1024 + 9 * N * 128 + 3 * 17408 + 256;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N == 64) {
+    MCEDM_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_mma_rate_kernel<64><<<num_sms(), 64, smem, st>>>(n_tiles, cycles_per_cta, err);
+  } else if (N == 128) {
+    MCEDM_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_mma_rate_kernel<128><<<num_sms(), 64, smem, st>>>(n_tiles, cycles_per_cta, err);
+  } else {
+    MCEDM_REQUIRE(smem <= 232448, "probe_mma_rate: N=256 weights do not fit");
+    MCEDM_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_mma_rate_kernel<256><<<num_sms(), 64, smem, st>>>(n_tiles, cycles_per_cta, err);
+  }
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int row_shift, int base_offset,
                                 int b_mn_major, float* out, void* stream) {
   using namespace mcedm;
