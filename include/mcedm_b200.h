@@ -85,7 +85,7 @@ MCEDM_API int mcedm_conv_rows(const void* const* halo_src, int n_halo, const voi
  * Narrow-level (W <= 64) variant: the bf16 operand is a zero-padded flat pixel sequence (written by
  * mcedm_gn_apply with out_pitch/out_blk), position(b,y,x) = b*blk + (y+1)*pitch + x, so every filter tap
  * is a constant row offset and each 16 KB chunk of the input is fetched once.
- *   mcedm_flat_geometry: pitch = W + 8, block_positions = roundup((H+2)*pitch, 128)
+ *   mcedm_flat_geometry: pitch = W + 1 (16 <= W <= 64), block_positions = roundup((H+2)*pitch, 128)
  *   src_flat  bf16 [B*block_positions, 64]; w_packed bf16 [9][64][64]; out fp32 NHWC [B,H,W,64] (dense)
  *   res_mode  0 | 1 | 2 | 3 as in mcedm_conv_igemm; out may alias res when res_mode == 1
  *   stats_partial NULL or fp32 [B*block_positions/128][4][16][2]

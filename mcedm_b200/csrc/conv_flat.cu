@@ -6,15 +6,15 @@
 // several image rows; with a dense layout a +-1 pixel shift would leak across row ends.  The bf16
 // operand is therefore stored by the producing GroupNorm pass (gn.cu) in a padded layout:
 //
-//     image block (blk positions, a multiple of 128):  [P zeros][row 0: W px | 8 zeros][row 1 ...] ... [zeros]
-//     P = W + 8 = row pitch;  position(b, y, x) = b*blk + (y+1)*P + x
+//     image block (blk positions, a multiple of 128):  [P zeros][row 0: W px | 1 zero][row 1 ...] ... [zeros]
+//     P = W + 1 = row pitch;  position(b, y, x) = b*blk + (y+1)*P + x
 //
 // so the whole tensor is ONE flat sequence of 128-byte pixels in which the filter tap (dy, dx) is the
 // constant offset dy*P + dx and every out-of-image neighbour is a stored zero.  A tile = 128
 // consecutive positions; its 9 A operands are row-shifted UMMA descriptors into a ring of 128-position
 // chunks (chunk t-1, t, t+1 are adjacent in the ring; two mirror slots keep them adjacent across the
 // wrap).  Each chunk is one 16 KB TMA load and serves 3 tiles x 9 taps.  Rows that fall on padding
-// (11 % at 64x64, 27 % at 32x32) are computed and dropped by the epilogue.
+// (6 % at 64x64, 12 % at 32x32; a pitch of W + 8 used to cost 19 % / 37 %) are computed and dropped by the epilogue.
 //
 // Warp roles / epilogue exactly as conv_rows.cu (8 epilogue warps, 4-deep TMEM accumulator ring,
 // per-(tile, lane quarter) GroupNorm partial sums).
@@ -492,7 +492,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const bool mirror = slot < 2 && k >= S;
         uint4 v[8];
         bool ok[8];
-        // (row, column) of this thread's first position; the next ones are 16 positions apart (P >= 24 > 16: at most
+        // (row, column) of this thread's first position; the next ones are 16 positions apart (P >= 17 > 16: at most
         // one row wrap per step), so one division per chunk instead of eight
         int row = (base_pos + prow) / p.P;
         int x = (base_pos + prow) - row * p.P;
@@ -539,8 +539,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 
 extern "C" int mcedm_flat_geometry(int H, int W, int* pitch, int* block_positions) {
   using namespace mcedm;
-  MCEDM_REQUIRE(W >= 8 && W <= 64 && H >= 1, "flat layout supports 8 <= W <= 64 (W=%d)", W);
-  const int P = W + 8;
+  MCEDM_REQUIRE(W >= 16 && W <= 64 && H >= 1, "flat layout supports 16 <= W <= 64 (W=%d)", W);
+  const int P = W + 1;     // one shared zero column between image rows is all the 3x3 taps need
   *pitch = P;
   *block_positions = ((H + 2) * P + 127) / 128 * 128;
   return 0;
