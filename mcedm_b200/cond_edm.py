@@ -1,0 +1,175 @@
+"""Drop-in host mirror of the reference's single-task EDM module `PlCondEdm` (models/ddim.py:1608-1773, on top of
+`PlCondDdim` :1054-1606): the baseline of BASELINE config 5 (`config_adm_edm_res32_cond_h`) — `u` is denoised, `h`
+(or the Darcy permeability `a`) is the condition, there is no mask.
+
+Same EDM mathematics as `PlMcedm`, so the class reuses its kernel path unchanged:
+  * the network + preconditioning (`model_precond`, `get_denoised`) are `PlMcedm._precond_apply`;
+  * the sampler `sample_edm(h, u_noise, sparams)` (ddim.py:1532-1601: plain stochastic Heun) is the masked sampler core
+    with an all-ones mask — `x*1`, `+ known*0` and `*mask` are exact in floating point, so it is the same arithmetic
+    (checked against the reference fixture by tests/test_gpu_parity.py::test_cond_edm_sampler_and_training_step);
+  * `training_step` is the fused noise-injection / U-Net / loss(+dL/dF) path with `mask=None` (loss over every pixel,
+    ddim.py:1723).
+What is NOT mirrored (SURVEY §8f "next"): the PDE residual metric, the correlation / min-max-scaled metrics, `dx_cond`,
+`guide_dx`, self-conditioning, `node_type`, and the DDIM sampler (`sample`, `sample_with_repeat` raise, as in the reference).
+"""
+from __future__ import annotations
+
+import torch
+from einops import rearrange
+
+from .mcedm import PlMcedm
+
+
+class PlCondEdm(PlMcedm):
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        m = hparams.model
+        # probability of keeping the conditioning during training (PlCondDdim.__init__, ddim.py:1058-1059)
+        self.cond_p = m.cond_p if hasattr(m, "cond_p") else 0.8
+        self.node_type = m.node_type if hasattr(m, "node_type") else False
+        if self.node_type:
+            raise NotImplementedError("node_type conditioning is not on the hot path")
+        if getattr(m, "self_cond", False):
+            raise NotImplementedError("self-conditioning is not supported")
+        self.mae_criterion = torch.nn.L1Loss()                       # PlDdim.__init__, ddim.py:75
+        self.h_ch = m.cond_channels if m.cond_channels else 1
+        self.u_ch = m.out_ch
+        self.log_lr = False
+
+    # ---------------------------------------------------------------- configuration helpers
+    def get_inp_stats_shape(self, hparams):                           # ddim.py:1061-1064
+        ch = hparams.model.in_channels
+        return (ch,) if ch > 1 else ()
+
+    def get_tar_stats_shape(self, hparams):                           # ddim.py:1066-1069
+        ch = hparams.model.out_ch
+        return (ch,) if ch > 1 else ()
+
+    @staticmethod
+    def get_edm_sampler_params():                                     # ddim.py:1620-1645
+        from .config import AttrDict
+
+        return AttrDict(name="edm", type="edm", timesteps=50, sigma_min=0.002, sigma_max=80, rho=7, S_churn=15.0, S_min=0,
+                        S_max="inf", S_noise=1, n_samples=5, n_repeat=2, n_time_h=128, n_time_u=0, return_last=True,
+                        select_by_pde=False, use_gt_pde_select=True, guide_dx=False, w=0.0, plot_scaled=False)
+
+    def set_test_sampler_params(self, params):                        # ddim.py:1647-1652
+        if params.type != "edm":
+            print("Model with EDM preconditioning supports only EDM sampler ")
+            params = self.get_edm_sampler_params()
+        self.test_sparams = params
+
+    def inverse_data_transform_u(self, u):                            # ddim.py:1071-1079
+        if self.rescaled:
+            u = (u + 1.0) / 2.0
+        if self.normalization == "min_max":
+            u = torch.clamp(u, 0.0, 1.0)
+        return self.normalizer_target(u, inverse=True)
+
+    def get_cond_in(self, h, u, dx, dt):                              # ddim.py:1081-1116 (node_type False)
+        cond_ch = self.model.cond_channels
+        if cond_ch == self.h_ch:
+            return h
+        if cond_ch == self.h_ch + self.u_ch:
+            return torch.cat([h, u[:, 0:1].repeat(1, u.shape[1], 1, 1)], dim=-1)
+        if cond_ch == self.h_ch + 2:
+            return torch.cat([h, dt, dx], dim=-1)
+        if cond_ch == self.h_ch + self.u_ch + 2:
+            return torch.cat([h, u[:, 0:1].repeat(1, u.shape[1], 1, 1), dt, dx], dim=-1)
+        raise TypeError(f"Number of conditional channels {cond_ch} should be changed to match the known states "
+                        f"channels {self.h_ch}")                      # the reference raises a str here (a TypeError)
+
+    # ---------------------------------------------------------------- training
+    def forward(self, x, sigma, noise, cond=None):                    # ddim.py:1668-1694 -> (D_x, x0_t)
+        x_noise = x + noise * sigma
+        if torch.rand(1) >= self.cond_p:                              # host RNG draw kept for RNG parity (:1684)
+            cond = None
+        d = self.model_precond(x_noise, sigma.float(), cond)
+        return d, d
+
+    def training_step(self, train_batch, batch_idx):                  # ddim.py:1700-1737
+        h_unnorm, dx, dt, u_unnorm = train_batch
+        self.h_ch = h_ch = h_unnorm.shape[-1]
+        self.u_ch = u_ch = u_unnorm.shape[-1]
+        x = self.data_transform(h_unnorm, u_unnorm)
+        h, u = x[..., 0:h_ch], x[..., h_ch:h_ch + u_ch]
+        cond_in = rearrange(self.get_cond_in(h, u, dx, dt), "b h w c -> b c h w").contiguous()
+        u = rearrange(u, "b h w c -> b c h w").contiguous()
+        noise = self._randn_like("noise", u)
+        rnd_normal = torch.randn([u.shape[0], 1, 1, 1]).type_as(u)    # CPU RNG, as :1714-1715
+        sigma = (rnd_normal * self.P_std + self.P_mean).exp()
+        weight = self.get_loss_weight(sigma)
+        # reference: D_x, _ = self.forward(u, sigma, noise, cond=cond_in); loss = self.criteria(D_x, u, weight).
+        # Fused here exactly as in PlMcedm.training_step, with no mask (the cond_p coin is drawn inside forward_loss).
+        loss = self.forward_loss(u, sigma, noise, cond_in, None, weight)
+        self.log("train_loss", loss, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+        if self.pde_loss_lambda > 0.0:
+            raise NotImplementedError("the PDE residual loss term is outside the hot path (SURVEY §8f)")
+        return loss
+
+    # ---------------------------------------------------------------- sampling
+    def sample(self, h, u_noise, sparams, return_last=True, guide_dx=False):
+        raise NotImplementedError("Only EDM sampler is supported for the model with EDM pre-conditioning")
+
+    def sample_with_repeat(self, h, u, sparams, return_last=True, guide_dx=False):
+        raise NotImplementedError("Only EDM sampler is supported for the model with EDM pre-conditioning")
+
+    @torch.no_grad()
+    def sample_edm(self, h, u_noise, sparams, return_last=True, guide_dx=False):   # ddim.py:1532-1601
+        """h: condition b h w c; u_noise: the caller's N(0,1) draw b h w c. Returns xs [b, t, h, w, c] float64."""
+        if guide_dx:
+            raise NotImplementedError("guide_dx (PDE guidance) has no sm_100a kernel yet (SURVEY §8f)")
+        w = sparams.w
+        if not (w is None or abs(w) < 0.001):
+            raise NotImplementedError("classifier-free guidance (w != 0) is not supported")
+        if not u_noise.is_cuda:
+            from . import _lib as L
+
+            raise L.McedmError("sample_edm needs CUDA tensors: the sm_100a kernels have no CPU fallback")
+        cond = rearrange(h, "b h w c -> b c h w").contiguous().float()
+        noise = rearrange(u_noise, "b h w c -> b c h w").contiguous()
+        return self._sample_core(noise, cond, torch.ones_like(noise, dtype=torch.float32), sparams, return_last)
+
+    # ---------------------------------------------------------------- evaluation steps (MAE metrics; see module docstring)
+    def validation_step(self, val_batch, batch_idx):                  # ddim.py:1154-1217
+        if (self.current_epoch + 1) % 100 != 0 and self.current_epoch != 0:
+            return {"epoch": self.current_epoch}
+        h_unnorm, dx, dt, u_unnorm = val_batch
+        self.h_ch = h_ch = h_unnorm.shape[-1]
+        self.u_ch = u_ch = u_unnorm.shape[-1]
+        state_gt = self.data_transform(h_unnorm, u_unnorm)
+        h, u = state_gt[..., :h_ch], state_gt[..., h_ch:u_ch + h_ch]
+        u_noise = self._randn_like("val_noise", u)
+        if self.sparams.type != "edm":
+            raise TypeError("Non EDM sampler is not supported for the model")
+        xs = self.sample_edm(self.get_cond_in(h, u, dx, dt), u_noise, self.sparams, return_last=True,
+                             guide_dx=self.sparams.guide_dx)
+        u_last = xs[:, -1, :, :, :u_ch]
+        loss_u = self.mae_criterion(u_last, u)
+        loss_u_un = self.mae_criterion(self.inverse_data_transform_u(u_last), u_unnorm)
+        self.log("val_mae_u", loss_u, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+        self.log("val_mae_u_un", loss_u_un, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+        return {"epoch": self.current_epoch, "loss": loss_u, "loss_u_un": loss_u_un, "traj": xs[:, -1].unsqueeze(dim=1),
+                "gt": state_gt[..., h_ch:u_ch + h_ch]}
+
+    def test_step(self, test_batch, test_idx):                        # ddim.py:1219-1319
+        h_unnorm, dx, dt, u_unnorm = test_batch
+        self.h_ch = h_ch = h_unnorm.shape[-1]
+        self.u_ch = u_ch = u_unnorm.shape[-1]
+        state_gt = self.data_transform(h_unnorm, u_unnorm)
+        h, u = state_gt[..., :h_ch], state_gt[..., h_ch:u_ch + h_ch]
+        n_samples = self.test_sparams.n_samples
+        cond_in_rep = self.get_cond_in(h, u, dx, dt).repeat(n_samples, 1, 1, 1)
+        u_noise = self._randn_like("test_noise", u.repeat(n_samples, 1, 1, 1))
+        if self.test_sparams.type != "edm":
+            raise TypeError("Non EDM sampler is not supported for the model")
+        xs = self.sample_edm(cond_in_rep, u_noise, self.test_sparams, return_last=self.test_sparams.return_last,
+                             guide_dx=self.test_sparams.guide_dx)
+        xs_mean = torch.mean(rearrange(xs, "(n b) t h w c -> n b t h w c", n=n_samples), dim=0)
+        u_last = xs_mean[:, -1, :, :, :u_ch]
+        loss_u = self.mae_criterion(u_last, u)
+        loss_u_un = self.mae_criterion(self.inverse_data_transform_u(u_last), u_unnorm)
+        self.log("test_mae_u", loss_u, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+        self.log("test_mae_u_un", loss_u_un, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+        traj = rearrange(xs[:, -1], "(n b) h w c -> b h w n c", n=n_samples).unsqueeze(dim=1)
+        return {"loss": loss_u, "loss_u_un": loss_u_un, "traj": traj, "gt": state_gt[..., h_ch:u_ch + h_ch]}

@@ -510,16 +510,16 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int pi = prow + 16 * i;
-          if (ok[i]) {
-            uint4 o;
-            o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], p.fmt);
-            o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], p.fmt);
-            o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], p.fmt);
-            o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], p.fmt);
-            const int off = pi * 128 + ((jc ^ (pi & 7)) << 4);
-            sts128(base + off, o);
-            if (mirror) sts128(base + S * kChunkBytes + off, o);
-          }
+          // branch-free (lanes of a warp sit on different positions): padding positions hold zeros and get them back
+          uint4 o;
+          o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], p.fmt);
+          o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], p.fmt);
+          o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], p.fmt);
+          o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], p.fmt);
+          if (!ok[i]) o = v[i];
+          const int off = pi * 128 + ((jc ^ (pi & 7)) << 4);
+          sts128(base + off, o);
+          if (mirror) sts128(base + S * kChunkBytes + off, o);
         }
         fence_proxy_async_smem();
       }

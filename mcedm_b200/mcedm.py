@@ -421,10 +421,17 @@ class PlMcedm(LightningModule):
             raise NotImplementedError("classifier-free guidance (w != 0) is not supported")
         if not hu.is_cuda:
             raise L.McedmError("sample_edm needs CUDA tensors: the sm_100a kernels have no CPU fallback")
+        hu_noise = self._randn_like("init", hu)                     # :576
+        return self._sample_core(hu_noise, cond, hu_mask, sparams, return_last)
+
+    @torch.no_grad()
+    def _sample_core(self, hu_noise, cond, hu_mask, sparams, return_last=True):
+        """Stochastic Heun with mask blending on the kernels, given the initial N(0,1) draw `hu_noise` [B,C,H,W]
+        (shared with PlCondEdm, whose sampler takes the draw from its caller and uses an all-ones mask)."""
+        hu = hu_noise
         lib = L.lib()
         model = self.ema_model if self.ema_model is not None else self.model
         unet = self._unet_of(model)
-        hu_noise = self._randn_like("init", hu)                     # :576
         t_steps = self.edm_time_steps(sparams)
         num_steps = sparams.timesteps
         B, C, H, W = hu.shape

@@ -264,6 +264,44 @@ def sample_edm(sd, model_cfg, hu_noise: Tensor, cond: Tensor, hu_mask: Tensor, s
     return torch.stack(xs, dim=0).permute(1, 0, 3, 4, 2)             # 't b c h w -> b t h w c'
 
 
+def cond_sample_edm(sd, model_cfg, u_noise: Tensor, h_cond: Tensor, sparams,
+                    step_noise: Callable[[int, Tensor], Tensor], return_last: bool = True,
+                    record: Optional[list] = None) -> Tensor:
+    """PlCondDdim.sample_edm as PlCondEdm uses it (models/ddim.py:1532-1601; config 5): plain stochastic Heun, NO
+    mask, the condition is h.  Guidance off (guide_dx False => the `- 5 * dx / t_hat` terms are exact zeros; w = 0;
+    no self-conditioning).  u_noise fp32 [B,C,H,W] is the caller's draw (the sampler does not draw its own initial
+    noise, unlike PlMcedm); h_cond [B,Cc,H,W].  Returns xs [B, T, H, W, C] fp64."""
+    num_steps = int(sparams["timesteps"])
+    t_steps = edm_schedule(num_steps, sparams["sigma_min"], sparams["sigma_max"], sparams["rho"])
+    x_next = u_noise.to(torch.float64) * t_steps[0]                   # :1555
+    xs = [x_next]
+    s_min, s_max = sparams["S_min"], float(sparams["S_max"])
+    for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
+        x_cur = x_next
+        gamma = min(sparams["S_churn"] / num_steps, np.sqrt(2) - 1) if s_min <= t_cur <= s_max else 0
+        t_hat = t_cur + gamma * t_cur
+        x_hat = x_cur + (t_hat ** 2 - t_cur ** 2).sqrt() * sparams["S_noise"] * step_noise(i, x_cur)   # :1566
+        d1, _ = denoise(sd, model_cfg, x_hat, t_hat, h_cond)
+        if record is not None:
+            record.append((i, 0, float(t_hat), d1))
+        d_cur = (x_hat - d1.to(torch.float64)) / t_hat                # :1576-1578 with dx = 0
+        x_next = x_hat + (t_next - t_hat) * d_cur
+        if i < num_steps - 1:
+            d2, _ = denoise(sd, model_cfg, x_next, t_next, h_cond)
+            if record is not None:
+                record.append((i, 1, float(t_next), d2))
+            d_prime = (x_next - d2.to(torch.float64)) / t_next
+            x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
+        xs = [x_next] if return_last else xs + [x_next]
+    return torch.stack(xs, dim=0).permute(1, 0, 3, 4, 2)
+
+
+def cond_training_loss(sd, model_cfg, u: Tensor, sigma: Tensor, noise: Tensor, h_cond: Optional[Tensor]):
+    """PlCondEdm.forward + NoiseEstimationLoss (models/ddim.py:1668-1694, :1723; losses.py:48-53): x_noise = u + noise*sigma,
+    loss over every pixel, the condition h is not scaled (and is None when the cond_p coin drops it)."""
+    return training_loss(sd, model_cfg, u, sigma, noise, h_cond, None)
+
+
 # ------------------------------------------------------------------------------------------------
 # mask generators (datamodules/h5_dataset.py), mask == 1 -> missing / to be generated
 # ------------------------------------------------------------------------------------------------

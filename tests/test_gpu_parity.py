@@ -11,7 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from common import NoiseFeed, fixture_state, golden, stress_module, stress_unet
+from common import NoiseFeed, fixture_state, golden, hparams, stress_module, stress_unet
 from mcedm_b200.utils import rel_l2
 from oracle import edm_oracle as O
 
@@ -347,6 +347,67 @@ def test_cond_edm_network_within_bf16_bar(dev):
     net = net.to(dev)
     y = net(g["x"].to(dev), g["noise_labels"].to(dev), g["cond"].to(dev))
     assert rel_l2(y, g["out"]) < BF16_TOL
+
+
+def test_cond_edm_sampler_and_training_step(dev):
+    """Config 5 (`PlCondEdm`, config_adm_edm_res32_cond_h on Darcy-shaped fields): the kernel path behind the reference's
+    single-task surface against the fixture produced by the unmodified reference (tests/golden/make_golden_cond.py):
+    same RNG call sequence, per-evaluation D_x within the bar on the SAME input (teacher-forced through the oracle),
+    final sample close, and the training-step loss."""
+    from mcedm_b200 import data as D
+    from mcedm_b200.cond_edm import PlCondEdm
+    from mcedm_b200.utils import randomize_zero_init
+
+    g = golden("cond_edm_path.pt")
+    cfg = hparams("config_adm_edm_res32_cond_h")
+    torch.manual_seed(1)
+    pl = PlCondEdm(copy.deepcopy(cfg.model.hparams))
+    randomize_zero_init(pl.model, 2)
+    pl.ema_model.ma_model.load_state_dict(pl.model.state_dict())
+    sd = {k: v.detach().clone() for k, v in pl.model.state_dict().items()}
+    mcfg = dict(cfg.model.hparams.model)
+    pl = pl.to(dev)
+    st = g["stats"]
+    pl.normalizer_input.set_stats(st["input_mean"].to(dev), st["input_std"].to(dev))
+    pl.normalizer_target.set_stats(st["target_mean"].to(dev), st["target_std"].to(dev))
+    a, u = D._FIELDS["darcy"](2, 128, first_seed=g["field_seed"])
+    a, u = torch.from_numpy(a).to(dev), torch.from_numpy(u).to(dev)
+    # ---- sampling (eval / no_grad, as Lightning runs test_step)
+    pl.eval()
+    state = pl.data_transform(a[:1], u[:1])
+    h_n, u_n = state[..., :1], state[..., 1:2]
+    feed = NoiseFeed(g["sample"]["seed"])
+    pl._noise_hook = feed.hook
+    pl._trace = []
+    sp = copy.deepcopy(cfg.diff_sampler)
+    sp.timesteps = g["sample"]["steps"]
+    u_noise = feed.draw(u_n)
+    xs = pl.sample_edm(pl.get_cond_in(h_n, u_n, None, None), u_noise, sp, return_last=True, guide_dx=False)
+    assert [tuple(c) for c in feed.calls] == [tuple(c) for c in g["sample"]["calls"]]
+    assert xs.shape == (1, 1, 128, 128, 1) and xs.dtype == torch.float64
+    assert len(pl._trace) == len(g["sample"]["denoised"])
+    cond_c = h_n.permute(0, 3, 1, 2).contiguous().cpu()
+    for (i, which, sigma, d, xt), ref in zip(pl._trace, g["sample"]["denoised"]):
+        assert abs(sigma - ref["sigma"]) <= 1e-6 * max(1.0, ref["sigma"])
+        with torch.no_grad():
+            d_or, _ = O.denoise(sd, mcfg, xt.cpu(), torch.tensor(sigma, dtype=torch.float64), cond_c)
+        assert rel_l2(d, d_or) < BF16_TOL
+    # 5 chained evaluations on adversarial weights: the trajectories stay close (not a per-step bar)
+    assert rel_l2(xs, g["sample"]["xs"]) < 5e-2
+    pl._noise_hook, pl._trace = None, None
+    # ---- training step (bf16 training plan; loss within 1e-2 like test_training_step_matches_reference_golden)
+    pl.train()
+    pl.cond_p = 1.0
+    nf = NoiseFeed(g["train"]["noise_seed"])
+    pl._noise_hook = nf.hook
+    torch.manual_seed(g["train"]["cpu_seed"])
+    grid = torch.zeros(2, 128, 128, 1, device=dev)
+    loss = pl.training_step((a, grid, grid, u), 0)
+    assert abs(float(loss) - float(g["train"]["loss"])) < 1e-2 * abs(float(g["train"]["loss"]))
+    loss.backward()
+    gflat = pl.model.engine().flat_grad()
+    gnorm = float(torch.sqrt((gflat.double() ** 2).sum()))
+    assert abs(gnorm - float(g["train"]["grad_norm"])) < 3e-2 * float(g["train"]["grad_norm"])
 
 
 def test_get_denoised_within_bf16_bar(dev):

@@ -120,3 +120,33 @@ def test_two_rank_gloo_sharding_and_gradient_allreduce():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "OK" in outs[0]
+
+
+def test_cond_edm_module_surface():
+    """PlCondEdm (config 5) keeps the reference constructor / method surface and the PlCondDdim conditioning variants."""
+    import copy
+
+    from mcedm_b200.cond_edm import PlCondEdm
+    from mcedm_b200.config import compose
+
+    cfg = compose("config_adm_edm_res32_cond_h")
+    pl = PlCondEdm(copy.deepcopy(cfg.model.hparams))
+    for name in ("training_step", "validation_step", "test_step", "sample_edm", "get_denoised", "model_precond", "forward",
+                 "get_cond_in", "set_test_sampler_params", "get_edm_sampler_params", "inverse_data_transform_u",
+                 "configure_optimizers", "optimizer_step", "round_sigma"):
+        assert callable(getattr(pl, name))
+    assert pl.model.x_channels == 1 and pl.model.cond_channels == 1 and pl.model.out_channels == 1
+    assert pl.normalizer_input.subtract.shape == () and pl.normalizer_target.divide.shape == ()   # scalar stats
+    h, u = torch.randn(2, 8, 8, 1), torch.randn(2, 8, 8, 1)
+    pl.h_ch = pl.u_ch = 1
+    assert torch.equal(pl.get_cond_in(h, u, None, None), h)
+    sp = pl.get_edm_sampler_params()
+    assert sp.type == "edm" and sp.n_samples == 5 and float(sp.S_max) == float("inf")
+    pl.set_test_sampler_params(compose("config_adm_edm_res32_cond_h").diff_sampler)
+    assert pl.test_sparams.type == "edm"
+    for fn in (pl.sample, pl.sample_with_repeat):
+        try:
+            fn(None, None, None)
+            raise AssertionError("DDIM samplers must raise")
+        except NotImplementedError:
+            pass

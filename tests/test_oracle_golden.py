@@ -116,3 +116,44 @@ def test_mask_generators_bit_identical():
     for k in ("hu", "u", "h"):
         assert torch.equal(te[k].to(torch.uint8), g["time_eval"][k])
         assert torch.equal(ot[k].to(torch.uint8), g["time_eval"][k])
+
+
+def test_oracle_cond_edm_path_matches_reference():
+    """Config 5 (PlCondEdm: u denoised, h as condition, no mask): the oracle's unmasked sampler and loss against the
+    fixture produced by the unmodified reference (tests/golden/make_golden_cond.py)."""
+    import copy
+
+    from mcedm_b200 import data as D
+    from oracle import edm_oracle as O
+
+    g = golden("cond_edm_path.pt")
+    net, cfg, _ = stress_unet("config_adm_edm_res32_cond_h")
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    mcfg = dict(cfg.model.hparams.model)
+    a, u = D._FIELDS["darcy"](2, 128, first_seed=g["field_seed"])
+    a, u = torch.from_numpy(a), torch.from_numpy(u)
+    st = g["stats"]
+    h_n = ((a - st["input_mean"]) / st["input_std"]).permute(0, 3, 1, 2).contiguous()
+    u_n = ((u - st["target_mean"]) / st["target_std"]).permute(0, 3, 1, 2).contiguous()
+    # ---- sampler: same draws in the same order (u_noise fp32 b h w c, then one fp64 draw per step)
+    feed = NoiseFeed(g["sample"]["seed"])
+    u_noise = feed.draw(torch.empty(1, 128, 128, 1)).permute(0, 3, 1, 2).contiguous()
+    sp = dict(copy.deepcopy(cfg.diff_sampler))
+    sp["timesteps"] = g["sample"]["steps"]
+    rec = []
+    with torch.no_grad():
+        xs = O.cond_sample_edm(sd, mcfg, u_noise, h_n[:1], sp, lambda i, x: feed.draw(x), record=rec)
+    assert [tuple(c) for c in feed.calls] == [tuple(c) for c in g["sample"]["calls"]]
+    assert len(rec) == len(g["sample"]["denoised"])
+    for (i, which, sigma, d), ref in zip(rec, g["sample"]["denoised"]):
+        assert abs(sigma - ref["sigma"]) <= 1e-9 * max(1.0, ref["sigma"])
+        assert rel_l2(d, ref["D"]) < 1e-5
+    assert rel_l2(xs, g["sample"]["xs"]) < 1e-5
+    # ---- training loss: noise = randn_like(u) (NoiseFeed), sigma from the CPU RNG, one cond_p coin (cond_p = 1: kept)
+    nf = NoiseFeed(g["train"]["noise_seed"])
+    noise = nf.draw(u_n)
+    torch.manual_seed(g["train"]["cpu_seed"])
+    sigma = (torch.randn([2, 1, 1, 1]) * 1.2 - 1.2).exp()
+    with torch.no_grad():
+        loss, _ = O.cond_training_loss(sd, mcfg, u_n, sigma, noise, h_n)
+    assert abs(float(loss) - float(g["train"]["loss"])) < 2e-5 * abs(float(g["train"]["loss"]))
