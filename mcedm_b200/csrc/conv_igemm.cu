@@ -61,17 +61,23 @@ struct ConvCfg {
   static constexpr int NCH = N / CH;
   static constexpr int U = CH / 4;                        // 16-byte units per staged row
   static constexpr int W_SEG_BYTES = N * 128;
-  static constexpr int STAGE_BYTES = 4 * 32 * CH * 4;     // per-CTA epilogue staging
+  // epilogue column groups: G x 4 warps, each group drains NCH / G chunks of every tile (with 4 warps for N = 192 the
+  // six chunks per tile made the epilogue the pacer of the 1x1 convs: 50 us for a 12 us memory job)
+  static constexpr int G = (N >= 192) ? 3 : (N >= 64) ? 2 : 1;
+  static constexpr int NLOC = NCH / G;                     // chunks per warp
+  static constexpr int THREADS = 64 + 128 * G;
+  static constexpr int STAGE_BYTES = 4 * G * 32 * CH * 4;  // per-CTA epilogue staging
   static constexpr int STAT_BYTES = 2 * 4 * (N / 4) * 2 * 4;
   static constexpr int ACC_STRIDE = (N == 192) ? 256 : N; // TMEM column stride between the two buffers
   static constexpr int TMEM_COLS = (2 * ACC_STRIDE <= 32) ? 32 : (2 * ACC_STRIDE <= 64) ? 64
                                    : (2 * ACC_STRIDE <= 128) ? 128 : (2 * ACC_STRIDE <= 256) ? 256 : 512;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 template <int N>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(ConvCfg<N>::THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a0,
                   const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_a2,
                   const __grid_constant__ CUtensorMap tm_a3, const ConvParams p) {
@@ -100,7 +106,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);                           // one arrival per epilogue warp
+      mbar_init(&acc_empty[i], 4 * Cfg::G);                  // one arrival per epilogue warp
     }
     for (int i = 0; i < p.n_stages; ++i) {
       mbar_init(&a_full[i], 1);
@@ -176,6 +182,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     // ======================================= epilogue =======================================
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int ew = warp - 2;             // staging slot
+    const int cg = ew >> 2;              // column group: chunks [cg * NLOC, (cg + 1) * NLOC)
     const uint32_t my_stage = smem_u32(stage_smem) + ew * (32 * Cfg::CH * 4);
     const int unit = lane % Cfg::U;
     const int row_in_it = lane / Cfg::U;
@@ -200,27 +207,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
         }
       }
       // 16-bit residual prefetch (independent of the accumulator); N <= 64 only
-      constexpr int NPRE = (N <= 64) ? Cfg::NCH : 1;
+      constexpr int NPRE = (N <= 64) ? Cfg::NLOC : 1;
       uint2 rh[NPRE][Cfg::U];
       if (N <= 64 && p.res16 && p.res_mode == 1) {
 #pragma unroll
-        for (int ch = 0; ch < NPRE; ++ch)
+        for (int lc = 0; lc < NPRE; ++lc)
 #pragma unroll
           for (int itr = 0; itr < Cfg::U; ++itr)
-            rh[ch][itr] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res) + opix[itr] * N +
-                                                          ch * Cfg::CH + unit * 4);
+            rh[lc][itr] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.res) + opix[itr] * N +
+                                                          (cg * Cfg::NLOC + lc) * Cfg::CH + unit * 4);
       }
       mbar_wait(&acc_full[buf], aph, p.err, 0x500 + buf);
       tc_fence_after();
-      float* my_stat = stat_smem + ((tcount & 1u) * 4 + ew) * (N / 4) * 2;
-      constexpr int kChUnroll = (N <= 64) ? Cfg::NCH : 1;
+      float* my_stat = stat_smem + ((tcount & 1u) * 4 + q) * (N / 4) * 2;
+      constexpr int kChUnroll = (N <= 64) ? Cfg::NLOC : 1;
 #pragma unroll kChUnroll
-      for (int ch = 0; ch < Cfg::NCH; ++ch) {
+      for (int lc = 0; lc < Cfg::NLOC; ++lc) {
+        const int ch = cg * Cfg::NLOC + lc;
         uint32_t v[Cfg::CH];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_STRIDE + ch * Cfg::CH;
         if constexpr (Cfg::CH == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
         tmem_wait_ld();
-        if (ch == Cfg::NCH - 1) {
+        if (lc == Cfg::NLOC - 1) {
           tc_fence_before();
           mbar_arrive_warp(&acc_empty[buf]);  // all of this warp's TMEM reads of this buffer are done
         }
@@ -244,7 +252,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
           const long long pix = pix0 + row;
           if (p.res_mode == 1) {
             if (N <= 64 && p.res16) {
-              const uint2 hv = rh[N <= 64 ? ch : 0][itr];
+              const uint2 hv = rh[N <= 64 ? lc : 0][itr];
               float2 lo, hi;
               if (p.fmt) {
                 lo = unpack_f16x2(hv.x);
@@ -306,8 +314,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
         __syncwarp();
       }
       if (p.stats) {
-        epi_bar_sync();
-        const int t = threadIdx.x - 64;  // 0..127
+        epi_bar_sync<128 * Cfg::G>();
+        const int t = threadIdx.x - 64;  // 0 .. 128 G - 1
         if (t < (N / 4) * 2) {
           const float* sb = stat_smem + (tcount & 1u) * 4 * (N / 4) * 2;
           const float tot = (sb[t] + sb[(N / 4) * 2 + t]) + (sb[2 * (N / 4) * 2 + t] + sb[3 * (N / 4) * 2 + t]);
@@ -343,7 +351,7 @@ static int launch_conv(const CUtensorMap& tm_w, const CUtensorMap* tm_a, const C
     attr_smem = 232448;
   }
   int grid = q.n_tiles < num_sms() ? q.n_tiles : num_sms();
-  conv_igemm_kernel<N><<<grid, 192, smem, stream>>>(tm_w, tm_a[0], tm_a[1], tm_a[2], tm_a[3], q);
+  conv_igemm_kernel<N><<<grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_a[0], tm_a[1], tm_a[2], tm_a[3], q);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

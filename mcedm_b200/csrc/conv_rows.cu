@@ -77,7 +77,9 @@ struct RowsCfg {
   static constexpr int U = CH / 4;
   static constexpr int W_SEG_BYTES = N * 128;
   static constexpr int EPI_WARPS = 4 * NCH;                 // one warp per (lane quarter, column chunk)
-  static constexpr int XF_WARPS = FUSED ? 4 : 0;            // GroupNorm+SiLU transform warps (after the epilogue warps)
+  // GroupNorm+SiLU transform warps (after the epilogue warps); the 16-wide head conv has a quarter of the MMA / epilogue
+  // work per row, so there the transform is the pacer and gets eight
+  static constexpr int XF_WARPS = FUSED ? (N == 16 ? 8 : 4) : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
   // STACK (fused N = 64): the three vertical taps of a filter column are stacked into ONE N = 192 MMA per input row
@@ -597,7 +599,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // halo row; the chunk's physical position follows SWIZZLE_128B: chunk ^ (pixel row & 7) (slots are 1 KB aligned).
     const int t = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
     const int j = t & 7;
-    const int prow = t >> 3;                // 0 .. 15
+    const int prow = t >> 3;                // 0 .. XF_ROWS-1
+    constexpr int XF_ROWS = FUSED ? 4 * Cfg::XF_WARPS : 16;   // pixels covered per pass by the transform threads
+    constexpr int XF_IT = 128 / XF_ROWS;
     uint32_t hl = 0;
     long long dbg_w4 = 0;
     long long r = r_begin;
@@ -631,15 +635,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           for (int s = 0; s < 2; ++s) {
             if (s < p.n_halo) {
               const uint32_t base = smem_u32(h_smem) + slot * slot_bytes + s * kHaloBytes;
-              uint4 v[8];
+              uint4 v[XF_IT];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int px = 1 + prow + 16 * i;
+              for (int i = 0; i < XF_IT; ++i) {
+                const int px = 1 + prow + XF_ROWS * i;
                 v[i] = lds128(base + px * 128 + ((j ^ (px & 7)) << 4));
               }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int px = 1 + prow + 16 * i;
+              for (int i = 0; i < XF_IT; ++i) {
+                const int px = 1 + prow + XF_ROWS * i;
                 uint4 o;
                 o.x = xf_pair(v[i].x, ca[s][0], cb[s][0], ca[s][1], cb[s][1], p.fmt);
                 o.y = xf_pair(v[i].y, ca[s][2], cb[s][2], ca[s][3], cb[s][3], p.fmt);
