@@ -156,6 +156,25 @@ MCEDM_API int mcedm_conv_in16(const float* x, int Cx, const float* cond, int Cc,
                               int B, int H, int W, void* out16, float* stats_partial, int op_fmt, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* fp32-accuracy inference mode (per-step denoiser output within 1e-4 of the fp32 reference)      */
+/* -------------------------------------------------------------------------------------------- */
+/*
+ * Every tensor-core operand is split into two fp16 terms (x = hi + lo) and every GEMM is issued three times
+ * (hi*W_hi, lo*W_hi, hi*W_lo) through the regular entry points with in-place fp32 accumulation (res_mode 1, res == out).
+ *   mcedm_gn_apply_split: mcedm_gn_apply writing the operand as a (hi, lo) fp16 pair (and the raw copy likewise);
+ *   mcedm_split16:        fp32 [n] -> (hi, lo) fp16;
+ *   mcedm_attention_f32:  softmax(q k^T / 8) v in fp32 (CUDA cores) on fp32 qkv [B,L,192] -> fp32 [B,L,64]
+ *                         (adm_blocks.py:103-109 computes the softmax in fp32).
+ */
+MCEDM_API int mcedm_gn_apply_split(const float* x, const float* partial, const float* gamma, const float* beta,
+                                   const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
+                                   int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
+                                   int out_blk, void* out_hi, void* out_lo, void* raw_hi, void* raw_lo,
+                                   float* coef_scratch, void* stream);
+MCEDM_API int mcedm_split16(const float* x, long long n, void* hi16, void* lo16, void* stream);
+MCEDM_API int mcedm_attention_f32(const float* qkv_f32, int B, int L, float* out_f32, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* K2  GroupNorm statistics / fused GroupNorm + scale-shift + SiLU + resample                     */
 /*     (models/adm_blocks.py:86-97 GroupNorm; :161, :163-166, :175, :403 call sites)              */
 /* -------------------------------------------------------------------------------------------- */

@@ -77,6 +77,8 @@ struct GnApplyParams {
   float* coef;               // [B][128]: per-channel (a | b) with y = act(a*x + b); written by gn_finalize_kernel
   int out_pitch;             // 0: dense NHWC output; > 0: padded flat layout of conv_flat.cu (row pitch)
   int out_blk;               // positions per image block of the padded layout
+  void* out_lo;              // nullptr, or (fp32-accuracy mode) receives operand - float(rounded operand), same layout as out
+  void* out_raw_lo;          // likewise for the raw copy
   int x16;                   // x is a 16-bit NHWC tensor in the operand format (inference: raw activations are 16-bit)
   int in_pitch, in_blk;      // x16 only: x itself is in the padded flat layout (0: dense)
 };
@@ -115,6 +117,17 @@ __device__ __forceinline__ uint4 pack8(const float4 lo, const float4 hi, int fmt
   o.y = pack_op2(lo.z, lo.w, fmt);
   o.z = pack_op2(hi.x, hi.y, fmt);
   o.w = pack_op2(hi.z, hi.w, fmt);
+  return o;
+}
+
+// second term of the split operand: what the 16-bit rounding of (lo, hi) dropped (fp32-accuracy mode, fp16 only)
+__device__ __forceinline__ uint4 pack8_rem(const float4 lo, const float4 hi, const uint4 r) {
+  const float2 a = unpack_f16x2(r.x), b = unpack_f16x2(r.y), c = unpack_f16x2(r.z), d = unpack_f16x2(r.w);
+  uint4 o;
+  o.x = pack_f16x2(lo.x - a.x, lo.y - a.y);
+  o.y = pack_f16x2(lo.z - b.x, lo.w - b.y);
+  o.z = pack_f16x2(hi.x - c.x, hi.y - c.y);
+  o.w = pack_f16x2(hi.z - d.x, hi.w - d.y);
   return o;
 }
 
@@ -230,13 +243,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
         if (i + 32 * k < p.pix_per_cta) {
           const int ip = pix0 + i + 32 * k;
           const long long pix = in_img + ip;
-          if (p.out_raw) reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = pack8(lo[k], hi[k], p.fmt);
+          if (p.out_raw) {
+            const uint4 rw = pack8(lo[k], hi[k], p.fmt);
+            reinterpret_cast<uint4*>(p.out_raw)[pix * 8 + c8] = rw;
+            if (p.out_raw_lo) reinterpret_cast<uint4*>(p.out_raw_lo)[pix * 8 + c8] = pack8_rem(lo[k], hi[k], rw);
+          }
           long long opix = pix;
           if (p.out_pitch > 0) {
             const int y = ip / p.Win;
             opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
           }
-          out[opix * 8 + c8] = pack8(gn_act4<X16>(lo[k], a_lo, b_lo, p.act), gn_act4<X16>(hi[k], a_hi, b_hi, p.act), p.fmt);
+          const float4 yl = gn_act4<X16>(lo[k], a_lo, b_lo, p.act), yh = gn_act4<X16>(hi[k], a_hi, b_hi, p.act);
+          const uint4 yo = pack8(yl, yh, p.fmt);
+          out[opix * 8 + c8] = yo;
+          if (p.out_lo) reinterpret_cast<uint4*>(p.out_lo)[opix * 8 + c8] = pack8_rem(yl, yh, yo);
         }
       }
     }
@@ -248,12 +268,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       const int y = ip / p.Win, x = ip - y * p.Win;
       float4 xl, xh;
       gn_load8<X16>(p, gn_in_index(p, b, ip), c8, xl, xh);
-      const uint4 v = pack8(gn_act4<X16>(xl, a_lo, b_lo, p.act), gn_act4<X16>(xh, a_hi, b_hi, p.act), p.fmt);
+      const float4 yl = gn_act4<X16>(xl, a_lo, b_lo, p.act), yh = gn_act4<X16>(xh, a_hi, b_hi, p.act);
+      const uint4 v = pack8(yl, yh, p.fmt);
       const long long o00 = gn_out_index(p, b, 2 * y, 2 * x, Ho, Wo);
       out[o00 * 8 + c8] = v;
       out[(o00 + 1) * 8 + c8] = v;
       out[(o00 + rstride) * 8 + c8] = v;
       out[(o00 + rstride + 1) * 8 + c8] = v;
+      if (p.out_lo) {
+        uint4* ol = reinterpret_cast<uint4*>(p.out_lo);
+        const uint4 r = pack8_rem(yl, yh, v);
+        ol[o00 * 8 + c8] = r;
+        ol[(o00 + 1) * 8 + c8] = r;
+        ol[(o00 + rstride) * 8 + c8] = r;
+        ol[(o00 + rstride + 1) * 8 + c8] = r;
+      }
     }
   } else {
     const int Wo = p.Win >> 1, Ho = p.Hin >> 1;
@@ -284,7 +313,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
           }
           lo.x *= 0.25f; lo.y *= 0.25f; lo.z *= 0.25f; lo.w *= 0.25f;
           hi.x *= 0.25f; hi.y *= 0.25f; hi.z *= 0.25f; hi.w *= 0.25f;
-          out[gn_out_index(p, b, y, x, Ho, Wo) * 8 + c8] = pack8(lo, hi, p.fmt);
+          const uint4 yo = pack8(lo, hi, p.fmt);
+          const long long oi = gn_out_index(p, b, y, x, Ho, Wo);
+          out[oi * 8 + c8] = yo;
+          if (p.out_lo) reinterpret_cast<uint4*>(p.out_lo)[oi * 8 + c8] = pack8_rem(lo, hi, yo);
         }
       }
     }
@@ -301,11 +333,11 @@ extern "C" int mcedm_gn_stats(const float* x, long long n_pixels, float* partial
   return 0;
 }
 
-extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
-                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
-                              int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
-                              int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
-                              int op_fmt, void* stream) {
+static int gn_apply_impl(const float* x, const float* partial, const float* gamma, const float* beta,
+                         const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
+                         int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
+                         int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
+                         int op_fmt, void* out_lo, void* out_raw_lo, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply: Hin*Win=%d must be a multiple of 128", Hin * Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply: resample=%d", resample);
@@ -335,6 +367,8 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   p.x16 = 0;
   p.in_pitch = 0;
   p.in_blk = 0;
+  p.out_lo = out_lo;
+  p.out_raw_lo = out_raw_lo;
   MCEDM_REQUIRE(coef_scratch != nullptr, "gn_apply: coef_scratch (fp32 [B][128]) is required");
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
   // streaming CTAs of <= 512 pixels (~200 KB of traffic each); keep >= ~4 CTAs per SM when the batch allows it
@@ -350,6 +384,28 @@ extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float*
   gn_apply_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mcedm_gn_apply(const float* x, const float* partial, const float* gamma, const float* beta,
+                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
+                              int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
+                              int out_blk, void* out_bf16, void* out_raw_bf16, float* meanrstd_out, float* coef_scratch,
+                              int op_fmt, void* stream) {
+  return gn_apply_impl(x, partial, gamma, beta, scale_shift, emb_batch_stride, emb_shift_offset, eps, act, resample, B, Hin,
+                       Win, parts_per_img, out_pitch, out_blk, out_bf16, out_raw_bf16, meanrstd_out, coef_scratch, op_fmt,
+                       nullptr, nullptr, stream);
+}
+
+extern "C" int mcedm_gn_apply_split(const float* x, const float* partial, const float* gamma, const float* beta,
+                                    const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps,
+                                    int act, int resample, int B, int Hin, int Win, int parts_per_img, int out_pitch,
+                                    int out_blk, void* out_hi, void* out_lo, void* raw_hi, void* raw_lo,
+                                    float* coef_scratch, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(out_lo != nullptr && (raw_hi == nullptr) == (raw_lo == nullptr), "gn_apply_split: hi and lo outputs go in pairs");
+  return gn_apply_impl(x, partial, gamma, beta, scale_shift, emb_batch_stride, emb_shift_offset, eps, act, resample, B, Hin,
+                       Win, parts_per_img, out_pitch, out_blk, out_hi, raw_hi, nullptr, coef_scratch, 1, out_lo, raw_lo,
+                       stream);
 }
 
 extern "C" int mcedm_gn_coef(const float* partial, int parts_per_img, const float* gamma, const float* beta,

@@ -27,6 +27,7 @@ import torch
 
 from . import _lib as L
 from .fused_engine import FusedMixin
+from .precise_engine import PreciseMixin
 from .train_engine import TrainMixin
 
 WEIGHT_EPOCH = [0]
@@ -82,7 +83,7 @@ class _Block:
             self.be2 = m.norm2.bias.detach().float().contiguous()
 
 
-class UNetEngine(TrainMixin, FusedMixin):
+class UNetEngine(TrainMixin, FusedMixin, PreciseMixin):
     def __init__(self, unet):
         self.unet = unet
         self.lib = L.lib()
@@ -124,6 +125,8 @@ class UNetEngine(TrainMixin, FusedMixin):
         # inference plan: True = GroupNorm fused into the convs + 16-bit activations (fused_engine.py);
         # False = the unfused fp32-stream plan below (what training's forward uses)
         self.fused = os.environ.get("MCEDM_FUSED", "1") != "0"
+        # "fp16": the plans above (bar 1e-2);  "fp32": split-operand fp32-accuracy plan (bar 1e-4, precise_engine.py)
+        self.precision = "fp16"
         self._gn_coef: Dict[tuple, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ weights
@@ -347,6 +350,10 @@ class UNetEngine(TrainMixin, FusedMixin):
     def _launch_all(self, x, nl, cond, out):
         """The launch sequence of one forward pass; no allocation, no host sync (CUDA-graph capturable
         once the workspace for this batch size exists)."""
+        if self.precision == "fp32":
+            if self._fmt != 1:
+                raise ValueError("the fp32-accuracy plan splits operands into fp16 pairs: infer_fmt must be 1")
+            return self._launch_all_precise(x, nl, cond, out)
         if self.fused and self._fmt == 1 and x.shape[-1] == 128:      # bf16 storage would miss the 1e-2 bar
             return self._launch_all_fused(x, nl, cond, out)
         u = self.unet
@@ -401,7 +408,7 @@ class UNetEngine(TrainMixin, FusedMixin):
         if not use_graph:
             return self._launch_all(x, nl, cond, out)
         key = (x.data_ptr(), nl.data_ptr(), 0 if cond is None else cond.data_ptr(), out.data_ptr(), tuple(x.shape),
-               self._packed_key, self.fused)
+               self._packed_key, self.fused, self.precision)
         entry = self._graphs.get(key)
         if entry is None:
             if len(self._graphs) > 8:

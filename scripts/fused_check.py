@@ -34,6 +34,11 @@ with torch.no_grad():
         eng.fused = fused
         outs[fused] = net(x.to(dev), nl.to(dev), c.to(dev)).cpu()
         L.check_watchdog()
+    eng.fused, eng.precision = True, "fp32"
+    out32 = net(x.to(dev), nl.to(dev), c.to(dev)).cpu()
+    eng.precision = "fp16"
+    L.check_watchdog()
+print(f"fp32-accuracy plan vs oracle {rel_l2(out32, ref):.3e}")
 print(f"unfused vs oracle {rel_l2(outs[False], ref):.3e}   fused vs oracle {rel_l2(outs[True], ref):.3e}   "
       f"fused vs unfused {rel_l2(outs[True], outs[False]):.3e}", flush=True)
 Bt = int(sys.argv[1]) if len(sys.argv) > 1 else 128
@@ -41,8 +46,9 @@ x = torch.randn(Bt, 2, 128, 128, device=dev)
 c = torch.randn(Bt, 2, 128, 128, device=dev)
 nl = torch.tensor([0.3], device=dev)
 out = torch.empty(Bt, 2, 128, 128, device=dev)
-for fused in (False, True):
-    eng.fused = fused
+for fused in (False, True, "fp32"):
+    eng.fused = bool(fused)
+    eng.precision = "fp32" if fused == "fp32" else "fp16"
     eng._fmt = eng.infer_fmt
     eng.forward_static(x, nl, c, out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

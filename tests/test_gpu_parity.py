@@ -494,3 +494,26 @@ def test_no_cpu_fallback(dev):
     net, _, _ = stress_unet()
     with pytest.raises(Exception):
         net(torch.zeros(1, 2, 128, 128), torch.tensor([0.1]), torch.zeros(1, 2, 128, 128))
+
+
+def test_fp32_accuracy_plan_within_1e4(dev):
+    """north_star: per-step denoiser output within 1e-4 relative in fp32.  The split-operand plan (precise_engine.py:
+    (hi, lo) fp16 operand pairs, three accumulating tensor-core launches per GEMM, fp32 attention) against the fixtures of
+    the unmodified fp32 reference: network output F and denoiser output D at sigma in {80, 1.5, 0.05}."""
+    g = golden("denoise.pt")
+    pl, _ = stress_module()
+    pl = pl.to(dev).eval()
+    pl.ema_model.ma_model.engine().precision = "fp32"
+    for case in g["cases"]:
+        with torch.no_grad():
+            d, f = pl.get_denoised(pl.ema_model, case["xt"].to(dev), torch.tensor(case["sigma"], dtype=torch.float64),
+                                   cond=case["cond"].to(dev), w=0.0)
+        assert rel_l2(f, case["F"]) < 1e-4 and rel_l2(d, case["D"]) < 1e-4
+    gf = golden("unet_forward.pt")
+    net, _, _ = stress_unet()
+    net = net.to(dev).eval()
+    net.engine().precision = "fp32"
+    for case in gf["cases"]:
+        with torch.no_grad():
+            y = net(case["x"].to(dev), case["noise_labels"].to(dev), case["cond"].to(dev))
+        assert rel_l2(y, case["out"]) < 1e-4
