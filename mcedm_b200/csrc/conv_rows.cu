@@ -40,6 +40,12 @@
 #include <cuda_bf16.h>
 #include <cstdlib>
 
+// 16 epilogue warps of 16 columns for the fused N = 64 kernel (tried twice: with the lean issue loop it gains 4 % without
+// the transform and loses with it: 22 warps at 80 registers starve the transform warps).  Kept as a build-time knob.
+#ifndef MCEDM_EPI16
+#define MCEDM_EPI16 0
+#endif
+
 namespace mcedm {
 
 constexpr int kHaloRows = 130;
@@ -72,7 +78,7 @@ struct RowsParams {
 
 template <int N, bool FUSED>
 struct RowsCfg {
-  static constexpr int CH = (N >= 32) ? 32 : 16;        // (16 epilogue warps of 16 columns were tried: no gain)
+  static constexpr int CH = (N >= 32 && !(FUSED && N == 64 && MCEDM_EPI16)) ? 32 : 16;
   static constexpr int NCH = N / CH;
   static constexpr int U = CH / 4;
   static constexpr int W_SEG_BYTES = N * 128;
