@@ -152,6 +152,12 @@ MCEDM_API int mcedm_conv_igemm16(const void* const* src, int n_src, const int* s
                                  const int* seg_dx, int n_seg, const void* w_packed, const float* bias, int B, int H,
                                  int W, int N, void* out16, const void* res16, int res_mode, int io_pitch, int io_blk,
                                  float* stats_partial, int op_fmt, void* stream);
+/* The same first conv on the tensor cores (W == 128, Cc + Cx <= 5): builder warps fold the three horizontal taps into
+ * K (k = kx*Cin + c, one K = 16 step per input row), the vertical taps are stacked into N as in mcedm_conv_rows_fused.
+ * w16_packed: 16-bit [3 ky][64 co][64 k], zero beyond k = 3*Cin (engine.pack). Inputs are rounded to 16 bits once. */
+MCEDM_API int mcedm_conv_in_tc16(const float* x, int Cx, const float* cond, int Cc, const void* w16_packed,
+                                 const float* bias, int B, int H, void* out16, float* stats_partial, int op_fmt,
+                                 void* stream);
 MCEDM_API int mcedm_conv_in16(const float* x, int Cx, const float* cond, int Cc, const float* w, const float* bias,
                               int B, int H, int W, void* out16, float* stats_partial, int op_fmt, void* stream);
 

@@ -30,6 +30,7 @@ _PROTOTYPES = {
                               _vp],
     "mcedm_conv_flat_fused": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "mcedm_conv_igemm16": [_vpp, _i, _ip, _ip, _ip, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp],
+    "mcedm_conv_in_tc16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "mcedm_conv_in16": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "mcedm_gn_apply_split": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "mcedm_split16": [_vp, C.c_longlong, _vp, _vp, _vp],

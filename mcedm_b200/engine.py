@@ -150,6 +150,13 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin):
             cin = u.enc[self.conv_in_name]
             self.w_in = cin.weight.detach().float().contiguous()
             self.b_in = cin.bias.detach().float().contiguous()
+            # the same weights for the tensor-core first conv (conv_in_tc.cu): [ky][co][k = kx*Cin + c], zero-padded to 64
+            c_tot = cin.weight.shape[1]
+            if 3 * c_tot <= 15 and cin.weight.shape[0] == 64:
+                wk = cin.weight.detach().float().permute(2, 0, 3, 1).reshape(3, 64, 3 * c_tot)      # ky, co, (kx, c)
+                self.w_in_tc = torch.cat([wk, wk.new_zeros(3, 64, 64 - 3 * c_tot)], 2).to(dt).contiguous()
+            else:
+                self.w_in_tc = None
             self.w_out = pack_conv3x3(u.out_conv.weight, n_out_pad=16, dtype=dt)
             self.b_out = torch.cat([u.out_conv.bias.detach().float(),
                                     torch.zeros(16 - u.out_channels, device=dev)]).contiguous()

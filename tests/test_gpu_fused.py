@@ -276,3 +276,30 @@ def test_conv_in16_matches_fp32_conv(L, dev):
     tot = st.reshape(B, -1, 16, 2).double().sum(1)
     assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=1.0)
 
+
+
+@pytest.mark.parametrize("B,H,Cc,Cx", [(3, 128, 2, 2), (150, 4, 1, 1), (2, 24, 0, 2), (2, 128, 3, 2)])
+def test_conv_in_tc16_matches_fp32_conv(L, dev, B, H, Cc, Cx):
+    """Tensor-core first conv (horizontal taps folded into K, vertical taps stacked into N) against a 3x3 conv of the
+    fp16-rounded inputs and weights; statistics records per (row, lane quarter)."""
+    lib = L.lib()
+    g = torch.Generator().manual_seed(B + H + Cc)
+    Cin = Cc + Cx
+    x = torch.randn(B, Cx, H, 128, generator=g).to(dev)
+    c = torch.randn(B, Cc, H, 128, generator=g).to(dev) if Cc else None
+    w = (torch.randn(64, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(dev)
+    bias = torch.randn(64, generator=g).to(dev)
+    wk = w.permute(2, 0, 3, 1).reshape(3, 64, 3 * Cin)
+    wp = torch.cat([wk, wk.new_zeros(3, 64, 64 - 3 * Cin)], 2).to(torch.float16).contiguous()
+    out = torch.full((B, H, 128, 64), float("nan"), device=dev, dtype=torch.float16)
+    st = torch.full((B * H, 4, 16, 2), float("nan"), device=dev)
+    L.check(lib.mcedm_conv_in_tc16(L.ptr(x), Cx, L.ptr(c), Cc, L.ptr(wp), L.ptr(bias), B, H, L.ptr(out), L.ptr(st), 1,
+                                   L.stream_ptr()), "conv_in_tc16")
+    L.check_watchdog()
+    inp = torch.cat([c, x], 1) if Cc else x
+    ref = F.conv2d(inp.half().double(), w.half().double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(out.double(), ref) < 6e-4
+    v = ref.reshape(B, H * 128, 16, 4)
+    tot = st.reshape(B, -1, 16, 2).double().sum(1)
+    assert torch.allclose(tot[..., 0], v.sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
+    assert torch.allclose(tot[..., 1], (v * v).sum(dim=(1, 3)), rtol=2e-3, atol=2.0)
