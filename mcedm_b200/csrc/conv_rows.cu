@@ -90,7 +90,7 @@ struct RowsCfg {
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
   // STACK (fused N = 64): the three vertical taps of a filter column are stacked into ONE N = 192 MMA per input row
   // (see the MMA issuer); eight 64-column accumulators then rotate through all 512 TMEM columns.
-  static constexpr bool STACK = FUSED && N == 64;
+  static constexpr bool STACK = FUSED && (N == 64 || N == 16);   // N = 16: the head conv, 48 stacked B-rows
   static constexpr int ACC_BUFS = STACK ? 8 : 4;
   static constexpr int TMEM_COLS = (ACC_BUFS * N <= 32) ? 32 : (ACC_BUFS * N <= 64) ? 64 : (ACC_BUFS * N <= 128) ? 128
                                    : (ACC_BUFS * N <= 256) ? 256 : 512;
@@ -251,8 +251,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       // (kx, ks) = (0, 0)); a window that wraps past column 511 is issued in two pieces; segment edges drop the
       // sub-blocks whose output row is outside the CTA's range.
       // ---------------------------------------------------------------------------------------------------------
-      const uint32_t idesc1 = umma_idesc_16(128, 64, 0, 0, p.fmt), idesc2 = umma_idesc_16(128, 128, 0, 0, p.fmt),
-                     idesc3 = umma_idesc_16(128, 192, 0, 0, p.fmt);
+      const uint32_t idesc1 = umma_idesc_16(128, N, 0, 0, p.fmt), idesc2 = umma_idesc_16(128, 2 * N, 0, 0, p.fmt),
+                     idesc3 = umma_idesc_16(128, 3 * N, 0, 0, p.fmt);
       mbar_wait(w_full, 0, p.err, 0x2300);
       tc_fence_after();
       const uint32_t ns = (uint32_t)p.n_slots;
@@ -291,8 +291,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           const uint32_t blk0 = (8u - ((t0 + (uint32_t)(k - kyA)) & 7u)) & 7u;      // accumulator block of B-row kyA
           const int nky = kyB - kyA + 1;
           const int split = (int)(8u - blk0) < nky ? (int)(8u - blk0) : nky;        // B-rows before the window wraps
-          const uint32_t d0 = tmem_base + blk0 * 64u;                                // first piece
-          const uint32_t d1 = tmem_base + ((blk0 + (uint32_t)split) & 7u) * 64u;     // piece after the wrap / after ky = 0
+          const uint32_t d0 = tmem_base + blk0 * (uint32_t)N;                        // first piece
+          const uint32_t d1 = tmem_base + ((blk0 + (uint32_t)split) & 7u) * (uint32_t)N;   // piece after the wrap
           const uint32_t wrow = w_lo + (uint32_t)kyA * (Cfg::W_SEG_BYTES >> 4);
           const bool fresh = kyA == 0;        // output row k starts here: its very first MMA must not accumulate
           const long long dbg_c0 = (p.dbg & 64) ? clock64() : 0;
@@ -300,7 +300,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             // interior row, contiguous window: N = 64 (fresh) + N = 128, then 11 x N = 192
             if (elect_one()) {
               umma_f16(d0, desc(a_row), desc(wrow), idesc1, 0u);
-              umma_f16(d0 + 64u, desc(a_row), desc(wrow + (Cfg::W_SEG_BYTES >> 4)), idesc2, 1u);
+              umma_f16(d0 + (uint32_t)N, desc(a_row), desc(wrow + (Cfg::W_SEG_BYTES >> 4)), idesc2, 1u);
 #pragma unroll
               for (int i = 1; i < 12; ++i) {
                 const int kx = i >> 2, ks = i & 3;
@@ -323,7 +323,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                 if (i == 0 && fresh && n0 > 1) {
                   // split the first piece: ky = 0 fresh, the rest of it accumulating
                   umma_f16(d0, ad, desc(wrow), idesc1, 0u);
-                  umma_f16(d0 + 64u, ad, desc(wrow + (Cfg::W_SEG_BYTES >> 4)), n0 == 2 ? idesc1 : idesc2, 1u);
+                  umma_f16(d0 + (uint32_t)N, ad, desc(wrow + (Cfg::W_SEG_BYTES >> 4)), n0 == 2 ? idesc1 : idesc2, 1u);
                 } else {
                   umma_f16(d0, ad, desc(wrow + wo), i0, (i == 0 && fresh) ? 0u : 1u);
                 }
@@ -342,7 +342,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                   const uint64_t ad = desc(c_lo + ((cs * (uint32_t)cslot_bytes + s * kCtrBytes) >> 4));
                   const uint64_t bd = desc(w_lo + (9 + s) * (Cfg::W_SEG_BYTES >> 4));
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_base + blk * 64u, ad + 2 * ks, bd + 2 * ks, idesc1, 1u);
+                  for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_base + blk * (uint32_t)N, ad + 2 * ks, bd + 2 * ks, idesc1, 1u);
                 }
                 umma_commit(&c_empty[cs]);
               }
@@ -537,7 +537,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       timed_wait(&acc_full[buf], aph, p.err, 0x2700 + buf, dbg_w3, (p.dbg & 32) != 0);
       tc_fence_after();
       uint32_t v[Cfg::CH];
-      const uint32_t acc_col = Cfg::STACK ? ((8u - buf) & 7u) * 64u : buf * N;     // STACK: descending tile order
+      const uint32_t acc_col = Cfg::STACK ? ((8u - buf) & 7u) * (uint32_t)N : buf * N;   // STACK: descending tile order
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + ch * Cfg::CH;
       if constexpr (Cfg::CH == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
       tmem_wait_ld();
@@ -792,7 +792,7 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
   int rc = rows_common(p, tm_w, tm_h, tm_c, halo_src, n_halo, ctr_src, n_ctr, w_packed, B, H, N);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MCEDM_REQUIRE(N != 64 || n_halo == 1, "conv_rows_fused: N = 64 takes one halo source (K-split 128-channel convs)");
+  MCEDM_REQUIRE(N == 32 || n_halo == 1, "conv_rows_fused: N = 16 / 64 take one halo source (K-split 128-channel convs)");
   switch (N) {
     case 16: return launch_rows<16, true>(tm_w, tm_h, tm_c, p, st);
     case 32: return launch_rows<32, true>(tm_w, tm_h, tm_c, p, st);
