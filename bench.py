@@ -307,7 +307,7 @@ def run_b200(args):
         flat, fl_f, by_f, t_f = grp(("conv_flat_fused", "conv_flat"))
         att, fl_a, by_a, t_a = grp(("attention",))
         gn, fl_g, by_g, t_g = grp(("gn_apply16", "gn_apply"))
-        cin, fl_i, by_i, t_i = grp(("conv_in16", "conv_in"))
+        cin, fl_i, by_i, t_i = grp(("conv_in_tc16", "conv_in16", "conv_in"))
         total_ms = sum(p["ms"] for p in prof)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")    # dram bytes per launch from an `ncu --set full` capture
@@ -334,7 +334,7 @@ def run_b200(args):
                         dict(kernel="gn_apply (stand-alone GroupNorm+SiLU+resample passes that remain)", bound="hbm",
                              unit="GB/s", achieved=by_g / max(1e-9, t_g) / 1e6, peak=pk["hbm"], ms_per_eval=t_g,
                              launches_per_eval=len(gn)),
-                        dict(kernel="conv_in (first 3x3 conv on cat([cond, x]), CUDA cores)", bound="hbm", unit="GB/s",
+                        dict(kernel="conv_in_tc (first 3x3 conv on cat([cond, x]), tensor cores, 2 MMAs per input row)", bound="hbm", unit="GB/s",
                              achieved=by_i / max(1e-9, t_i) / 1e6, peak=pk["hbm"], ms_per_eval=t_i,
                              launches_per_eval=len(cin))],
                     end_to_end_tflops=value * EVALS_PER_FIELD * FLOPS_PER_EVAL * (args.timesteps * 2 - 1) / 99 / 1e12 / world)

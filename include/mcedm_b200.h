@@ -144,6 +144,10 @@ MCEDM_API int mcedm_conv_rows_fused(const void* const* halo_src, const float* co
                                     int B, int H, int N, int n_off, int n_total, void* out, int out_16,
                                     const void* res16, int res_mode, int res_pitch, int res_blk,
                                     float* stats_partial, int op_fmt, void* stream);
+/* Output head: out_conv(silu(out_norm(x))) (adm_blocks.py:403) as one launch writing F_x fp32 NCHW [B, c_out, H, 128]
+ * straight from the accumulators (w_packed 16-bit [9][16][64], rows >= c_out zero; bias fp32 [>= c_out]). */
+MCEDM_API int mcedm_conv_head_fused(const void* src16, const float* coef, const void* w_packed, const float* bias, int B,
+                                    int H, int c_out, float* F_nchw, int op_fmt, void* stream);
 MCEDM_API int mcedm_conv_flat_fused(const void* src_flat16, const float* coef, const void* w_packed, const float* bias,
                                     int B, int H, int W, int N, void* out_flat, int out_f32, const void* res,
                                     int res_mode, int res_f32, int res_pitch, int res_blk, float* stats_partial,

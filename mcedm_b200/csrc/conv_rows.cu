@@ -72,6 +72,7 @@ struct RowsParams {
   int n_total;           // channels per pixel of out / res (== N unless an output-channel window is used)
   int w_rows;            // rows per segment of the packed weight matrix (== n_total)
   const float* coef[2];  // FUSED: per halo source, fp32 [B][128] = (a | b) of y = silu(a*x + b); NULL = no transform
+  int nchw_c;            // FUSED N = 16 head: > 0 -> out is fp32 NCHW [B, nchw_c, H, 128] (the network output F_x)
   int dbg;               // bring-up instrumentation (MCEDM_DBG): 32 time every role's barrier waits, 64 time MMA issue / commits
   int res_pitch, res_blk; // FUSED, res_mode 2: the half-resolution residual is padded-flat (0,0: dense NHWC)
 };
@@ -543,6 +544,21 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive_warp(&acc_empty[buf]);
+      if constexpr (FUSED && N == 16) {
+        if (p.nchw_c > 0) {
+          // output head (adm_blocks.py:403): the TMEM layout (lane = pixel) IS the NCHW order along x, so the first
+          // nchw_c accumulator columns go straight to F_x[b, c, y, :] as coalesced 128-byte rows - no staging, no
+          // 16-channel NHWC intermediate, no separate head_to_nchw pass
+          const int bimg = (int)(r / p.H);
+          const int y = (int)(r - (long long)bimg * p.H);
+          float* F = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < p.nchw_c)
+              F[(((long long)bimg * p.nchw_c + c) * p.H + y) * 128 + q * 32 + lane] = __uint_as_float(v[c]) + __ldg(p.bias + c);
+          continue;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < Cfg::U; ++j) {
         const int pj = j ^ (lane & (Cfg::U - 1));
@@ -806,4 +822,26 @@ extern "C" int mcedm_debug_rows(long long* host_out) {
   MCEDM_CUDA(cudaDeviceSynchronize());
   MCEDM_CUDA(cudaMemcpyFromSymbol(host_out, g_rows_dbg, sizeof(long long) * 160 * 8));
   return 0;
+}
+
+extern "C" int mcedm_conv_head_fused(const void* src16, const float* coef, const void* w_packed, const float* bias, int B,
+                                     int H, int c_out, float* F_nchw, int op_fmt, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(c_out >= 1 && c_out <= 16 && coef != nullptr && bias != nullptr, "conv_head_fused: bad arguments");
+  RowsParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias;
+  p.out = F_nchw;
+  p.out_bf16 = 0;
+  p.fmt = op_fmt ? 1 : 0;
+  p.n_total = 16;
+  p.w_rows = 16;
+  p.nchw_c = c_out;
+  p.coef[0] = coef;
+  if (const char* e = getenv("MCEDM_DBG")) p.dbg = atoi(e);
+  CUtensorMap tm_w, tm_h[2], tm_c[2];
+  const void* halo[1] = {src16};
+  int rc = rows_common(p, tm_w, tm_h, tm_c, halo, 1, nullptr, 0, w_packed, B, H, 16);
+  if (rc) return rc;
+  return launch_rows<16, true>(tm_w, tm_h, tm_c, p, reinterpret_cast<cudaStream_t>(stream));
 }

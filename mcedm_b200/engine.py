@@ -459,6 +459,14 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin):
                 return (2.0 * px * N * 64 * (9 * n_halo + n_ctr),
                         px * 64 * 2.0 * (n_halo + n_ctr) + px * N * out_b + (px * N * 2.0 * (1 if res_mode == 1 else 0.25)
                                                                              if res_mode else 0.0))
+            if name == "mcedm_conv_head_fused":
+                B, H, c_out = v(a[4]), v(a[5]), v(a[6])
+                px = B * H * 128
+                return 2.0 * px * 16 * 64 * 9, px * 64 * 2.0 + px * c_out * 4.0
+            if name == "mcedm_conv_in_tc16":
+                cin, B, H = v(a[1]) + v(a[3]), v(a[6]), v(a[7])
+                px = B * H * 128
+                return 2.0 * px * 64 * 9 * cin, px * (cin * 4.0 + 64 * 2.0)
             if name == "mcedm_conv_flat_fused":
                 B, H, W, res_mode = v(a[4]), v(a[5]), v(a[6]), v(a[11])
                 px = B * H * W

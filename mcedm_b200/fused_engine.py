@@ -233,9 +233,6 @@ class FusedMixin:
             cur = self._run_block_fused(blk, inputs, B, ws, emb_stride, st, dev)
         # out_conv(silu(out_norm(x)))  (adm_blocks.py:403): the normalisation rides in the conv like everywhere else
         coef = self._fcoef(ws, "out", cur, self.g_out, self.be_out, None, 0, u.out_norm.eps, B, st)
-        o16 = self._fbuf(ws, "o16", (B, H, W, 16), torch.float32, dev)
-        cptr = (C.c_void_p * 1)(coef.data_ptr())
-        L.check(lib.mcedm_conv_rows_fused(L.ptr_array([cur.t]), cptr, 1, None, 0, L.ptr(self.w_out), L.ptr(self.b_out), B, H,
-                                          16, 0, 16, L.ptr(o16), 0, None, 0, 0, 0, None, self._fmt, st), "conv_rows_fused")
-        L.check(lib.mcedm_head_to_nchw(L.ptr(o16), 16, u.out_channels, B, H, W, L.ptr(out), st), "head_to_nchw")
+        L.check(lib.mcedm_conv_head_fused(L.ptr(cur.t), L.ptr(coef), L.ptr(self.w_out), L.ptr(self.b_out), B, H,
+                                          u.out_channels, L.ptr(out), self._fmt, st), "conv_head_fused")
         return out
