@@ -241,10 +241,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const uint32_t centre = ring_lo + (slot + 1) * (kChunkBytes >> 4);
         const uint32_t s1 = (slot + 1 == (uint32_t)S) ? 0u : slot + 1;
         const uint32_t s2 = (s1 + 1 == (uint32_t)S) ? 0u : s1 + 1;
+        // the nine A descriptor words are formed in warp-uniform code; the elected lane only issues
+        uint32_t al[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) al[t] = centre + (uint32_t)tap_off[t];
         if (elect_one()) {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const uint64_t ad = desc(centre + (uint32_t)tap_off[t]);
+            const uint64_t ad = desc(al[t]);
             const uint64_t bd = desc(w_lo + t * (Cfg::W_SEG_BYTES >> 4));
             umma_f16(d_tmem, ad, bd, idesc, t != 0 ? 1u : 0u);
             umma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
