@@ -138,13 +138,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
           const uint32_t sp = (it - 1) % kKvStages;
           mbar_wait(&p_full[pb], np & 1u, err, 0x1500 + pb);
           tc_fence_after();
-          const uint32_t p_base = smem_u32(p_smem + pb * 2 * kTile);
-          const uint32_t v_base = smem_u32(kv_smem + sp * 2 * kTile + kTile);
+          // descriptor words formed in warp-uniform code, compile-time offsets inside the elected branch
+          const uint64_t pd = umma_desc_k_sw128(smem_u32(p_smem + pb * 2 * kTile));
+          const uint64_t vd = umma_desc_mn_sw128(smem_u32(kv_smem + sp * 2 * kTile + kTile), 8192);
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
-              umma_f16(tmem_o, umma_desc_k_sw128(p_base + (kk >> 2) * kTile + (kk & 3) * 32),
-                       umma_desc_mn_sw128(v_base + kk * 2048, 8192), idesc_o, (uint32_t)((jp | kk) != 0));
+              umma_f16(tmem_o, pd + (uint64_t)(((kk >> 2) * kTile + (kk & 3) * 32) >> 4), vd + (uint64_t)((kk * 2048) >> 4),
+                       idesc_o, (uint32_t)((jp | kk) != 0));
             umma_commit(&p_empty[pb]);
             umma_commit(&kv_empty[sp]);
           }
