@@ -105,22 +105,23 @@ __device__ __forceinline__ long long flat_index(int pitch, int blk, int b, int y
   return ((long long)b * Hs + y) * Ws + x;
 }
 // residual of the fused variant: 16-bit (any mode) or fp32 padded-flat (mode 1, the K-split partial sum)
-__device__ __forceinline__ float4 flat_residual16(const FlatParams& p, int N, int b, int y, int x, int c0, long long pos) {
+__device__ __forceinline__ float4 flat_residual16(const FlatParams& p, int fmt, int N, int b, int y, int x, int c0,
+                                                  long long pos) {
   const uint16_t* r16 = reinterpret_cast<const uint16_t*>(p.res);
   if (p.res_mode == 1) {
     if (p.res_f32) return *reinterpret_cast<const float4*>(p.res + pos * N + c0);
-    return flat_unpack4(*reinterpret_cast<const uint2*>(r16 + pos * N + c0), p.fmt);
+    return flat_unpack4(*reinterpret_cast<const uint2*>(r16 + pos * N + c0), fmt);
   } else if (p.res_mode == 2) {
     const long long i = flat_index(p.res_pitch, p.res_blk, b, y >> 1, x >> 1, p.H >> 1, p.W >> 1);
-    return flat_unpack4(*reinterpret_cast<const uint2*>(r16 + i * N + c0), p.fmt);
+    return flat_unpack4(*reinterpret_cast<const uint2*>(r16 + i * N + c0), fmt);
   } else {
     const int Hs = p.H << 1, Ws = p.W << 1;
     const long long i00 = flat_index(p.res_pitch, p.res_blk, b, 2 * y, 2 * x, Hs, Ws);
     const long long rs = p.res_pitch > 0 ? p.res_pitch : Ws;
-    const float4 r00 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + i00 * N + c0), p.fmt);
-    const float4 r01 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + 1) * N + c0), p.fmt);
-    const float4 r10 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + rs) * N + c0), p.fmt);
-    const float4 r11 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + rs + 1) * N + c0), p.fmt);
+    const float4 r00 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + i00 * N + c0), fmt);
+    const float4 r01 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + 1) * N + c0), fmt);
+    const float4 r10 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + rs) * N + c0), fmt);
+    const float4 r11 = flat_unpack4(*reinterpret_cast<const uint2*>(r16 + (i00 + rs + 1) * N + c0), fmt);
     return make_float4(0.25f * ((r00.x + r01.x) + (r10.x + r11.x)), 0.25f * ((r00.y + r01.y) + (r10.y + r11.y)),
                        0.25f * ((r00.z + r01.z) + (r10.z + r11.z)), 0.25f * ((r00.w + r01.w) + (r10.w + r11.w)));
   }
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(FlatCfg<N, FUSED>::THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a,
                  const FlatParams p) {
   using Cfg = FlatCfg<N, FUSED>;
+  const int fmt = FUSED ? 1 : p.fmt;      // the fused (inference) instantiation is fp16-only: folds at compile time
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.n_slots;
@@ -211,7 +213,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
     // lean issue loop (see conv_rows.cu): wrap-around ring counters, one election per tile, immediate offsets
     {
-      const uint32_t idesc = umma_idesc_16(128, N, 0, 0, p.fmt);
+      const uint32_t idesc = umma_idesc_16(128, N, 0, 0, fmt);
       mbar_wait(w_full, 0, p.err, 0x3200);
       tc_fence_after();
       const uint32_t w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);
@@ -337,7 +339,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           float4 a = lds128f(my_stage + rw * 128 + pu * 16);
           a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
           if (has_res) {
-            const float4 r = flat_unpack4(rh[itr], p.fmt);
+            const float4 r = flat_unpack4(rh[itr], fmt);
             a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
           }
           const float m = (vmask >> itr) & 1u ? 1.0f : 0.0f;
@@ -345,8 +347,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           s1 += (a.x + a.y) + (a.z + a.w);
           s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
           uint2 o;
-          o.x = pack_op2(a.x, a.y, p.fmt);
-          o.y = pack_op2(a.z, a.w, p.fmt);
+          o.x = pack_op2(a.x, a.y, fmt);
+          o.y = pack_op2(a.z, a.w, fmt);
           *reinterpret_cast<uint2*>(o16 + base + itr * 4 * N) = o;
         }
         if (p.stats) {
@@ -409,8 +411,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           const long long gpos = tile * 128 + q * 32 + itr * 4 + row_in_it;    // padded-flat output position
           opix[itr] = valid ? gpos : -1;
           rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pre) rr[itr] = flat_unpack4(rh_n[itr], p.fmt);
-          else if (valid && p.res_mode != 0) rr[itr] = flat_residual16(p, N, b, row - 1, x, c0, gpos);
+          if (pre) rr[itr] = flat_unpack4(rh_n[itr], fmt);
+          else if (valid && p.res_mode != 0) rr[itr] = flat_residual16(p, fmt, N, b, row - 1, x, c0, gpos);
         } else {
           opix[itr] = valid ? (((long long)b * p.H + (row - 1)) * p.W + x) : -1;
           rr[itr] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -444,8 +446,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
           if (FUSED && !p.out_f32) {
             uint2 o;
-            o.x = pack_op2(a.x, a.y, p.fmt);
-            o.y = pack_op2(a.z, a.w, p.fmt);
+            o.x = pack_op2(a.x, a.y, fmt);
+            o.y = pack_op2(a.z, a.w, fmt);
             *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + opix[itr] * N + c0) = o;
           } else {
             *reinterpret_cast<float4*>(p.out + opix[itr] * N + c0) = a;
@@ -516,10 +518,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           const int pi = prow + 16 * i;
           // branch-free (lanes of a warp sit on different positions): padding positions hold zeros and get them back
           uint4 o;
-          o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], p.fmt);
-          o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], p.fmt);
-          o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], p.fmt);
-          o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], p.fmt);
+          o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], fmt);
+          o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], fmt);
+          o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], fmt);
+          o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], fmt);
           if (!ok[i]) o = v[i];
           const int off = pi * 128 + ((jc ^ (pi & 7)) << 4);
           sts128(base + off, o);
@@ -615,6 +617,7 @@ extern "C" int mcedm_conv_flat_fused(const void* src_flat16, const float* coef, 
   int rc = mcedm_flat_geometry(H, W, &P, &blk);
   if (rc) return rc;
   MCEDM_REQUIRE(N == 64, "conv_flat_fused: N=%d unsupported (64)", N);
+  MCEDM_REQUIRE(op_fmt == 1, "conv_flat_fused: the fused inference kernels are fp16-only (op_fmt = 1)");
   MCEDM_REQUIRE(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || res != nullptr), "conv_flat_fused: bad residual mode");
   MCEDM_REQUIRE(!res_f32 || res_mode == 1, "conv_flat_fused: an fp32 residual must be same-resolution padded-flat");
   FlatParams p;

@@ -138,6 +138,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                  const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_c0,
                  const __grid_constant__ CUtensorMap tm_c1, const RowsParams p) {
   using Cfg = RowsCfg<N, FUSED>;
+  // the fused (inference) instantiations are fp16-only (bf16 storage misses the 1e-2 bar): the format folds at compile time
+  const int fmt = FUSED ? 1 : p.fmt;
+  const bool out16 = (FUSED && N == 64) ? true : (p.out_bf16 != 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_seg = p.n_halo * 9 + p.n_ctr;
@@ -252,8 +255,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       // (kx, ks) = (0, 0)); a window that wraps past column 511 is issued in two pieces; segment edges drop the
       // sub-blocks whose output row is outside the CTA's range.
       // ---------------------------------------------------------------------------------------------------------
-      const uint32_t idesc1 = umma_idesc_16(128, N, 0, 0, p.fmt), idesc2 = umma_idesc_16(128, 2 * N, 0, 0, p.fmt),
-                     idesc3 = umma_idesc_16(128, 3 * N, 0, 0, p.fmt);
+      const uint32_t idesc1 = umma_idesc_16(128, N, 0, 0, fmt), idesc2 = umma_idesc_16(128, 2 * N, 0, 0, fmt),
+                     idesc3 = umma_idesc_16(128, 3 * N, 0, 0, fmt);
       mbar_wait(w_full, 0, p.err, 0x2300);
       tc_fence_after();
       const uint32_t ns = (uint32_t)p.n_slots;
@@ -387,7 +390,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // (the previous per-tap election + per-tap address arithmetic cost ~510 instructions per tile, which measured
     // as the limiter: tensor pipe 35 % active with every other role waiting).
     {
-      const uint32_t idesc = umma_idesc_16(128, N, 0, 0, p.fmt);
+      const uint32_t idesc = umma_idesc_16(128, N, 0, 0, fmt);
       mbar_wait(w_full, 0, p.err, 0x2300);
       tc_fence_after();
       const uint32_t ns = (uint32_t)p.n_slots;
@@ -575,7 +578,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         if (p.res_mode != 0) {
           if constexpr (FUSED) {
             float2 lo, hi;
-            if (p.fmt) {
+            if (fmt) {
               lo = unpack_f16x2(rh[itr].x);
               hi = unpack_f16x2(rh[itr].y);
             } else {
@@ -590,10 +593,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         s1 += (a.x + a.y) + (a.z + a.w);
         s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
         const long long pix = pix0 + row;
-        if (p.out_bf16) {
+        if (out16) {
           uint2 o;
-          o.x = pack_op2(a.x, a.y, p.fmt);
-          o.y = pack_op2(a.z, a.w, p.fmt);
+          o.x = pack_op2(a.x, a.y, fmt);
+          o.y = pack_op2(a.z, a.w, fmt);
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * NT + cg) = o;
         } else {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * NT + cg) = a;
@@ -667,10 +670,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
               for (int i = 0; i < XF_IT; ++i) {
                 const int px = 1 + prow + XF_ROWS * i;
                 uint4 o;
-                o.x = xf_pair(v[i].x, ca[s][0], cb[s][0], ca[s][1], cb[s][1], p.fmt);
-                o.y = xf_pair(v[i].y, ca[s][2], cb[s][2], ca[s][3], cb[s][3], p.fmt);
-                o.z = xf_pair(v[i].z, ca[s][4], cb[s][4], ca[s][5], cb[s][5], p.fmt);
-                o.w = xf_pair(v[i].w, ca[s][6], cb[s][6], ca[s][7], cb[s][7], p.fmt);
+                o.x = xf_pair(v[i].x, ca[s][0], cb[s][0], ca[s][1], cb[s][1], fmt);
+                o.y = xf_pair(v[i].y, ca[s][2], cb[s][2], ca[s][3], cb[s][3], fmt);
+                o.z = xf_pair(v[i].z, ca[s][4], cb[s][4], ca[s][5], cb[s][5], fmt);
+                o.w = xf_pair(v[i].w, ca[s][6], cb[s][6], ca[s][7], cb[s][7], fmt);
                 sts128(base + px * 128 + ((j ^ (px & 7)) << 4), o);
               }
             }
@@ -808,6 +811,8 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
   int rc = rows_common(p, tm_w, tm_h, tm_c, halo_src, n_halo, ctr_src, n_ctr, w_packed, B, H, N);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MCEDM_REQUIRE(op_fmt == 1, "conv_rows_fused: the fused inference kernels are fp16-only (op_fmt = 1)");
+  MCEDM_REQUIRE(N != 64 || out_16 == 1, "conv_rows_fused: N = 64 writes 16-bit output");
   MCEDM_REQUIRE(N == 32 || n_halo == 1, "conv_rows_fused: N = 16 / 64 take one halo source (K-split 128-channel convs)");
   switch (N) {
     case 16: return launch_rows<16, true>(tm_w, tm_h, tm_c, p, st);

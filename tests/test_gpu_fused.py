@@ -83,7 +83,7 @@ def _from_flat(flat, B, H, W, pitch, blk):
 # --------------------------------------------------------------------------------------- conv_rows_fused
 @pytest.mark.parametrize("B,H,n_halo,n_ctr,N,res_mode,fmt,out16", [
     (2, 128, 1, 0, 64, 0, 1, 1), (3, 128, 1, 0, 64, 1, 1, 1), (2, 128, 1, 0, 64, 2, 1, 1), (2, 128, 2, 0, 32, 0, 1, 1),
-    (2, 128, 1, 2, 64, 0, 1, 1), (2, 128, 1, 0, 16, 0, 1, 0), (5, 24, 1, 0, 64, 1, 0, 1), (150, 4, 1, 0, 64, 1, 1, 1)])
+    (2, 128, 1, 2, 64, 0, 1, 1), (2, 128, 1, 0, 16, 0, 1, 0), (5, 24, 1, 0, 64, 1, 1, 1), (150, 4, 1, 0, 64, 1, 1, 1)])
 def test_conv_rows_fused_matches_reference(L, dev, B, H, n_halo, n_ctr, N, res_mode, fmt, out16):
     lib = L.lib()
     dt = _dt(fmt)
@@ -131,7 +131,7 @@ def test_conv_rows_fused_matches_reference(L, dev, B, H, n_halo, n_ctr, N, res_m
 # --------------------------------------------------------------------------------------- conv_flat_fused
 @pytest.mark.parametrize("B,H,W,res_mode,res_layout,out_f32,fmt", [
     (3, 64, 64, 0, "flat", 0, 1), (3, 64, 64, 1, "flat", 0, 1), (2, 64, 64, 3, "dense", 0, 1), (2, 32, 32, 3, "flat", 0, 1),
-    (2, 64, 64, 2, "flat", 0, 1), (5, 32, 32, 1, "f32", 0, 1), (5, 32, 32, 0, "flat", 1, 1), (40, 32, 32, 1, "flat", 0, 0),
+    (2, 64, 64, 2, "flat", 0, 1), (5, 32, 32, 1, "f32", 0, 1), (5, 32, 32, 0, "flat", 1, 1), (40, 32, 32, 1, "flat", 0, 1),
     (2, 16, 16, 1, "flat", 0, 1)])
 def test_conv_flat_fused_matches_reference(L, dev, B, H, W, res_mode, res_layout, out_f32, fmt):
     lib = L.lib()
