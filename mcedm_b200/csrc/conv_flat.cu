@@ -141,7 +141,9 @@ __device__ __forceinline__ uint32_t flat_xf_pair(uint32_t v, float a0, float b0,
   return pack_op2(silu_from_half_arg(fmaf(x0, a0, b0)), silu_from_half_arg(fmaf(x1, a1, b1)), fmt);
 }
 
-template <int N, bool FUSED>
+// FM (fused only): epilogue variant folded at compile time: 0 fast path without residual, 1 fast path with a
+// same-resolution 16-bit residual, 2 general path (resampled / fp32 residual, fp32 output); -1 = legacy unfused epilogue
+template <int N, bool FUSED, int FM = -1>
 __global__ void __launch_bounds__(FlatCfg<N, FUSED>::THREADS, 1)
 conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_a,
                  const FlatParams p) {
@@ -283,10 +285,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // evaluation).  Output position == tile row position and the residual tensor has the same padded layout, so the
     // lane needs one base offset per tile and immediate offsets per row; padding rows are stored as zeros (which is
     // what they hold anyway) instead of being branched around, and add nothing to the statistics.
-    if (FUSED && !p.out_f32 && (p.res_mode == 0 || (p.res_mode == 1 && !p.res_f32))) {
+    if constexpr (FUSED && (FM == 0 || FM == 1)) {
       const uint16_t* r16 = reinterpret_cast<const uint16_t*>(p.res);
       uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out);
-      const bool has_res = p.res_mode == 1;
+      constexpr bool has_res = FM == 1;
       uint2 rn[8];
       long long base = ((t_begin * 128) + q * 32 + row_in_it) * N + c0;     // element offset of this lane's first row
       if (has_res && n_tiles > 0) {
@@ -553,7 +555,7 @@ extern "C" int mcedm_flat_geometry(int H, int W, int* pitch, int* block_position
 }
 
 namespace mcedm {
-template <bool FUSED>
+template <bool FUSED, int FM = -1>
 static int launch_flat(FlatParams p, const void* src_flat, const void* w_packed, int B, int blk, cudaStream_t st) {
   using Cfg = FlatCfg<64, FUSED>;
   const int N = 64;
@@ -573,11 +575,11 @@ static int launch_flat(FlatParams p, const void* src_flat, const void* w_packed,
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    MCEDM_CUDA(cudaFuncSetAttribute(conv_flat_kernel<64, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_flat_kernel<64, FUSED, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_flat_kernel<64, FUSED><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(tm_w, tm_a, p);
+  conv_flat_kernel<64, FUSED, FM><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(tm_w, tm_a, p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -638,5 +640,8 @@ extern "C" int mcedm_conv_flat_fused(const void* src_flat16, const float* coef, 
   p.stats = stats_partial;
   p.fmt = op_fmt ? 1 : 0;
   p.coef = coef;
-  return launch_flat<true>(p, src_flat16, w_packed, B, blk, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!p.out_f32 && p.res_mode == 0) return launch_flat<true, 0>(p, src_flat16, w_packed, B, blk, st);
+  if (!p.out_f32 && p.res_mode == 1 && !p.res_f32) return launch_flat<true, 1>(p, src_flat16, w_packed, B, blk, st);
+  return launch_flat<true, 2>(p, src_flat16, w_packed, B, blk, st);
 }

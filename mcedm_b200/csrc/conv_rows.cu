@@ -132,7 +132,8 @@ __device__ __forceinline__ uint32_t xf_pair(uint32_t v, float a0, float b0, floa
   return pack_op2(silu_from_half_arg(fmaf(x0, a0, b0)), silu_from_half_arg(fmaf(x1, a1, b1)), fmt);
 }
 
-template <int N, bool FUSED>
+// RM: residual mode folded at compile time (fused N = 64 instantiations; -1 = runtime p.res_mode)
+template <int N, bool FUSED, int RM = -1>
 __global__ void __launch_bounds__(RowsCfg<N, FUSED>::THREADS, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_h0,
                  const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_c0,
@@ -140,11 +141,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   using Cfg = RowsCfg<N, FUSED>;
   // the fused (inference) instantiations are fp16-only (bf16 storage misses the 1e-2 bar): the format folds at compile time
   const int fmt = FUSED ? 1 : p.fmt;
+  const int res_mode = RM >= 0 ? RM : p.res_mode;
+  // fused N = 16 / 64 take exactly one halo source (128-channel convs are K-split): their source loops fold away
+  const int n_halo = (FUSED && N != 32) ? 1 : p.n_halo;
   const bool out16 = (FUSED && N == 64) ? true : (p.out_bf16 != 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int n_seg = p.n_halo * 9 + p.n_ctr;
-  const int slot_bytes = p.n_halo * kHaloBytes;
+  const int n_seg = n_halo * 9 + p.n_ctr;
+  const int slot_bytes = n_halo * kHaloBytes;
   const int cslot_bytes = p.n_ctr * kCtrBytes;
   uint8_t* w_smem = smem;
   uint8_t* h_smem = w_smem + n_seg * Cfg::W_SEG_BYTES;
@@ -215,9 +219,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         for (int k = 0; k < R + 2; ++k) {
           const uint32_t slot = hl % (uint32_t)p.n_slots, ph = (hl / (uint32_t)p.n_slots) & 1u;
           timed_wait(&h_empty[slot], ph ^ 1u, p.err, 0x2100 + slot, dbg_w0, (p.dbg & 32) != 0);
-          mbar_expect_tx(&h_full[slot], (uint32_t)(p.n_halo * kHaloTx));
+          mbar_expect_tx(&h_full[slot], (uint32_t)(n_halo * kHaloTx));
           tma_load_4d(h_smem + slot * slot_bytes, &tm_h0, &h_full[slot], 0, -1, y0 - 1 + k, b);
-          if (p.n_halo > 1)
+          if (n_halo > 1)
             tma_load_4d(h_smem + slot * slot_bytes + kHaloBytes, &tm_h1, &h_full[slot], 0, -1, y0 - 1 + k, b);
           ++hl;
           if (p.n_ctr > 0 && k >= 2) {
@@ -428,7 +432,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-              if (s < p.n_halo) {
+              if (s < n_halo) {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -454,7 +458,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             if (p.n_ctr > 0) {
               for (int s = 0; s < p.n_ctr; ++s) {
                 const uint64_t ad = desc(c_lo + ((cs * (uint32_t)cslot_bytes + s * kCtrBytes) >> 4));
-                const uint64_t bd = desc(w_lo + (p.n_halo * 9 + s) * (Cfg::W_SEG_BYTES >> 4));
+                const uint64_t bd = desc(w_lo + (n_halo * 9 + s) * (Cfg::W_SEG_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
               }
@@ -503,14 +507,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     uint2 rh_n[FUSED ? Cfg::U : 1];       // 16-bit residual (fused path)
     auto load_res = [&](long long r) {
       const long long pix0 = r * 128 + q * 32;
-      if (p.res_mode == 1) {
+      if (res_mode == 1) {
 #pragma unroll
         for (int itr = 0; itr < Cfg::U; ++itr) {
           const long long o = (pix0 + itr * ROWS_PER_IT + row_in_it) * NT + cg;
           if constexpr (FUSED) rh_n[itr] = *reinterpret_cast<const uint2*>(res16 + o);
           else rr_n[itr] = *reinterpret_cast<const float4*>(p.res + o);
         }
-      } else if (p.res_mode == 2) {
+      } else if (res_mode == 2) {
         const int bimg = (int)(r / p.H);
         const int y = (int)(r - (long long)bimg * p.H);
         const long long rrow = (FUSED && p.res_pitch > 0)
@@ -575,7 +579,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int pu = unit ^ (row & (Cfg::U - 1));
         float4 a = lds128f(my_stage + row * (Cfg::CH * 4) + pu * 16);
         a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
-        if (p.res_mode != 0) {
+        if (res_mode != 0) {
           if constexpr (FUSED) {
             float2 lo, hi;
             if (fmt) {
@@ -637,7 +641,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       float ca[2][8], cb[2][8];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
-        if (s < p.n_halo && p.coef[0] != nullptr) {
+        if (s < n_halo && p.coef[0] != nullptr) {
           const float4* cf = reinterpret_cast<const float4*>(p.coef[s] + (long long)b * 128 + j * 8);
           const float4 a0 = __ldg(cf), a1 = __ldg(cf + 1), b0 = __ldg(cf + 16), b1 = __ldg(cf + 17);
           ca[s][0] = a0.x; ca[s][1] = a0.y; ca[s][2] = a0.z; ca[s][3] = a0.w;
@@ -658,7 +662,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         if (y >= 0 && y < p.H && p.coef[0] != nullptr) {   // out-of-image rows are TMA zero fill and must stay zero
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            if (s < p.n_halo) {
+            if (s < n_halo) {
               const uint32_t base = smem_u32(h_smem) + slot * slot_bytes + s * kHaloBytes;
               uint4 v[XF_IT];
 #pragma unroll
@@ -695,7 +699,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   }
 }
 
-template <int N, bool FUSED>
+template <int N, bool FUSED, int RM = -1>
 static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const CUtensorMap* tm_c, RowsParams p,
                        cudaStream_t stream) {
   using Cfg = RowsCfg<N, FUSED>;
@@ -718,11 +722,11 @@ static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const C
   const int smem = fixed + slots * slot_bytes + p.n_cslots * p.n_ctr * kCtrBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   long long grid = p.total_rows < num_sms() ? p.total_rows : num_sms();
-  conv_rows_kernel<N, FUSED><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
+  conv_rows_kernel<N, FUSED, RM><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }
@@ -817,7 +821,10 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
   switch (N) {
     case 16: return launch_rows<16, true>(tm_w, tm_h, tm_c, p, st);
     case 32: return launch_rows<32, true>(tm_w, tm_h, tm_c, p, st);
-    case 64: return launch_rows<64, true>(tm_w, tm_h, tm_c, p, st);
+    case 64:
+      if (res_mode == 0) return launch_rows<64, true, 0>(tm_w, tm_h, tm_c, p, st);
+      if (res_mode == 1) return launch_rows<64, true, 1>(tm_w, tm_h, tm_c, p, st);
+      return launch_rows<64, true, 2>(tm_w, tm_h, tm_c, p, st);
     default: return fail(-1, "conv_rows_fused: N=%d unsupported (16, 32, 64)", N);
   }
 }
