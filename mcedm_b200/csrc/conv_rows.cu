@@ -42,6 +42,9 @@
 
 // 16 epilogue warps of 16 columns for the fused N = 64 kernel (tried twice: with the lean issue loop it gains 4 % without
 // the transform and loses with it: 22 warps at 80 registers starve the transform warps).  Kept as a build-time knob.
+#ifndef MCEDM_XF8
+#define MCEDM_XF8 0   // 8 transform warps for N = 64: +5 % without residual, -12 % with (96-register cap spills the epilogue)
+#endif
 #ifndef MCEDM_EPI16
 #define MCEDM_EPI16 0
 #endif
@@ -86,7 +89,7 @@ struct RowsCfg {
   static constexpr int EPI_WARPS = 4 * NCH;                 // one warp per (lane quarter, column chunk)
   // GroupNorm+SiLU transform warps (after the epilogue warps); the 16-wide head conv has a quarter of the MMA / epilogue
   // work per row, so there the transform is the pacer and gets eight
-  static constexpr int XF_WARPS = FUSED ? (N == 16 ? 8 : 4) : 0;
+  static constexpr int XF_WARPS = FUSED ? ((N == 16 || (N == 64 && MCEDM_XF8)) ? 8 : 4) : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
   // STACK (fused N = 64): the three vertical taps of a filter column are stacked into ONE N = 192 MMA per input row
