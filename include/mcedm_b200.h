@@ -330,6 +330,51 @@ MCEDM_API int mcedm_edm_precond_in(const float* x, const float* c_in, int coef_s
 /* D[b] = c_skip[b*stride]*x[b] + c_out[b*stride]*F[b]   (mcedm.py:210, :460); chw = elements per sample */
 MCEDM_API int mcedm_edm_precond_out(const float* x, const float* F, const float* c_skip, const float* c_out,
                                     int coef_stride, int B, long long chw, float* D, void* stream);
+/* PDE-guided sampler (PlCondDdim.sample_edm with guide_dx, models/ddim.py:1566-1590):
+ * D = c_skip*float(x) + c_out*F with scalar coefficients (get_denoised, ddim.py:1756-1766) */
+MCEDM_API int mcedm_edm_denoised(const double* x, const float* F, float c_skip, float c_out, long long total, float* D,
+                                 void* stream);
+/* d_cur = (x_hat - D)/t_hat - (5*gdx)/t_hat [float32 term] ; x_next = x_hat + ((t_next-t_hat)*d_cur)*mask ;
+ * x_in = c_in_next*float(x_next) (x_in may be NULL)                                            (ddim.py:1569-1573) */
+MCEDM_API int mcedm_edm_euler_guided(const double* x_hat, const float* D, const float* gdx, const float* mask,
+                                     double t_hat, double t_next, float c_in_next, long long total, double* d_cur,
+                                     double* x_next, float* x_in, void* stream);
+/* d' = (x_e - D2)/t_next - (5*gdx)/t_hat ; x_next = x_hat + ((t_next-t_hat)*(0.5 d_cur + 0.5 d'))*mask  (:1588-1592) */
+MCEDM_API int mcedm_edm_correct_guided(const double* x_hat, const double* x_e, const float* D2, const float* gdx,
+                                       const double* d_cur, const float* mask, double t_hat, double t_next,
+                                       long long total, double* x_next, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* K6: PDE residual of sampled fields and its gradient (pde.cu)                                  */
+/* -------------------------------------------------------------------------------------------- */
+/* A field channel is a "plane": element (b,t,x) at base[b*strides[0] + t*strides[1] + x*strides[2]] (element units),
+ * float32 or float64 (f64 flag), cast to float32 on load.  With apply_norm the un-normalised value is v*div + sub
+ * (Normalizer(inverse=True), models/normalizer.py:26-27); div always supplies the residual scale div^2
+ * (SweFvLoss.get_scaling, models/pde_loss.py:187-197).
+ *
+ * SweFvLoss.calculate_loss (models/pde_loss.py:199-215) as called by PlMcedm.get_pde_loss (models/mcedm.py:468-499)
+ * and PlCondDdim.get_pde_loss (models/ddim.py:1388-1422): one FORCE finite-volume step (pde_loss.py:129-165) of every
+ * row t, compared with row t+1 of gt (gt = NULL: with the un-normalised prediction itself); NaN -> 0.
+ * half_dt = float32(0.5*Tn/T), dx = the float32 grid spacing of gen_x (:104-118).  loss [B,T,X,2] float32 (may be
+ * NULL) is bit-identical to the reference's matrix; row_sums [B*T] float64 workspace; total (may be NULL) receives
+ * the float64 sum of all entries (torch.sum in the reference). */
+MCEDM_API int mcedm_swe_fv_loss(const void* h, int h_f64, const long long* h_strides, const void* u, int u_f64,
+                                const long long* u_strides, int apply_norm, float h_div, float h_sub, float u_div,
+                                float u_sub, const float* gt, int B, int T, int X, float half_dt, float dx, float g,
+                                float* loss, double* row_sums, double* total, void* stream);
+/* SweFvLoss.forward(return_d=True) (models/pde_loss.py:231-242): d mean(loss matrix)/d pred (un-normalised), gt held
+ * constant, NaN -> 0; analytic adjoint instead of autograd.  mode 0: out [B,T,X,2]; 1: out [B,T,X] = channel mean
+ * (PlCondDdim.get_dx_pde with calc_prob, models/ddim.py:1445-1446); 2: channel sum (:1448). */
+MCEDM_API int mcedm_swe_fv_grad(const void* h, int h_f64, const long long* h_strides, const void* u, int u_f64,
+                                const long long* u_strides, int apply_norm, float h_div, float h_sub, float u_div,
+                                float u_sub, const float* gt, int B, int T, int X, float half_dt, float dx, float g,
+                                int mode, float* out, void* stream);
+/* DarcyLoss.calculate_loss + forward's /(t*n) (models/pde_loss.py:30-56, :81-84): a, u planes of [B,S,S];
+ * loss [B,S-4,S-4] float32 (may be NULL), row_sums [B*(S-4)] float64 workspace, total as above. */
+MCEDM_API int mcedm_darcy_loss(const void* a, int a_f64, const long long* a_strides, const void* u, int u_f64,
+                               const long long* u_strides, int apply_norm, float a_div, float a_sub, float u_div,
+                               float u_sub, int B, int S, float D, float* loss, double* row_sums, double* total,
+                               void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* training-side small kernels (train_small.cu)                                                  */

@@ -17,6 +17,7 @@ _f = C.c_float
 _d = C.c_double
 _ip = C.POINTER(C.c_int)
 _vpp = C.POINTER(C.c_void_p)
+_llp = C.POINTER(C.c_longlong)
 
 # name -> argtypes; every function returns int (0 = ok) unless listed in _RESTYPES
 _PROTOTYPES = {
@@ -67,6 +68,13 @@ _PROTOTYPES = {
     "mcedm_edm_correct": [_vp, _vp, _vp, _vp, _vp, _d, _d, _f, _f, C.c_longlong, _vp, _vp, _vp],
     "mcedm_edm_precond_in": [_vp, _vp, _i, _i, C.c_longlong, _vp, _vp],
     "mcedm_edm_precond_out": [_vp, _vp, _vp, _vp, _i, _i, C.c_longlong, _vp, _vp],
+    "mcedm_edm_denoised": [_vp, _vp, _f, _f, C.c_longlong, _vp, _vp],
+    "mcedm_edm_euler_guided": [_vp, _vp, _vp, _vp, _d, _d, _f, C.c_longlong, _vp, _vp, _vp, _vp],
+    "mcedm_edm_correct_guided": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, C.c_longlong, _vp, _vp],
+    "mcedm_swe_fv_loss": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp,
+                          _vp],
+    "mcedm_swe_fv_grad": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp],
+    "mcedm_darcy_loss": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _i, _i, _f, _vp, _vp, _vp, _vp],
     "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
     "mcedm_debug_rows": [_vp],
     "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
@@ -127,6 +135,10 @@ def ptr(t):
 
 def int_array(vals):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def ll_array(vals):
+    return (C.c_longlong * len(vals))(*[int(v) for v in vals])
 
 
 def ptr_array(tensors):

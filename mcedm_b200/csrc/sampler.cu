@@ -96,6 +96,47 @@ __global__ void edm_precond_in_kernel(const float* __restrict__ x, const float* 
   x_in[i] = __fmul_rn(c_in[(i / chw) * coef_stride], x[i]);
 }
 
+// ---- PDE-guided variants (PlCondDdim.sample_edm with guide_dx, models/ddim.py:1566-1590) -------------------------
+// D = c_skip*float(x) + c_out*F, materialised because the guidance gradient is a stencil over D  (ddim.py:1756-1766)
+__global__ void edm_denoised_kernel(const double* __restrict__ x, const float* __restrict__ F, float c_skip, float c_out,
+                                    long long total, float* __restrict__ D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  D[i] = __fadd_rn(__fmul_rn(c_skip, (float)x[i]), __fmul_rn(c_out, F[i]));
+}
+
+// d_cur = (x_hat - double(D))/t_hat - double((5*dx)/float(t_hat)) ; x_next = x_hat + ((t_next - t_hat)*d_cur)*m
+// (`weight * dx / t_hat` is a float32 tensor divided by a 0-dim float64 tensor: evaluated in float32, ddim.py:1571)
+__global__ void edm_euler_guided_kernel(const double* __restrict__ x_hat, const float* __restrict__ D,
+                                        const float* __restrict__ gdx, const float* __restrict__ mask, double t_hat,
+                                        float t_div, double dt, float c_in_next, long long total,
+                                        double* __restrict__ d_cur, double* __restrict__ x_next,
+                                        float* __restrict__ x_in) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double xh = x_hat[i];
+  const float gterm = __fdiv_rn(__fmul_rn(5.0f, gdx[i]), t_div);
+  const double d = __dsub_rn(__ddiv_rn(__dsub_rn(xh, (double)D[i]), t_hat), (double)gterm);
+  const double xn = __dadd_rn(xh, __dmul_rn(__dmul_rn(dt, d), (double)mask[i]));
+  d_cur[i] = d;
+  x_next[i] = xn;
+  if (x_in) x_in[i] = __fmul_rn(c_in_next, (float)xn);
+}
+
+// d' = (x_e - double(D2))/t_next - double((5*dx2)/float(t_hat))   [t_hat, not t_next: ddim.py:1590]
+__global__ void edm_correct_guided_kernel(const double* __restrict__ x_hat, const double* __restrict__ x_e,
+                                          const float* __restrict__ D2, const float* __restrict__ gdx,
+                                          const double* __restrict__ d_cur, const float* __restrict__ mask,
+                                          double t_next, float t_div, double dt, long long total,
+                                          double* __restrict__ x_next) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float gterm = __fdiv_rn(__fmul_rn(5.0f, gdx[i]), t_div);
+  const double dp = __dsub_rn(__ddiv_rn(__dsub_rn(x_e[i], (double)D2[i]), t_next), (double)gterm);
+  const double avg = __dadd_rn(__dmul_rn(0.5, d_cur[i]), __dmul_rn(0.5, dp));
+  x_next[i] = __dadd_rn(x_hat[i], __dmul_rn(__dmul_rn(dt, avg), (double)mask[i]));
+}
+
 static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
 }  // namespace mcedm
@@ -156,6 +197,35 @@ extern "C" int mcedm_edm_precond_in(const float* x, const float* c_in, int coef_
   const long long total = (long long)B * chw;
   edm_precond_in_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, c_in, coef_stride,
                                                                                                chw, total, x_in);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_denoised(const double* x, const float* F, float c_skip, float c_out, long long total, float* D,
+                                  void* stream) {
+  using namespace mcedm;
+  edm_denoised_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, F, c_skip, c_out, total,
+                                                                                             D);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_euler_guided(const double* x_hat, const float* D, const float* gdx, const float* mask,
+                                      double t_hat, double t_next, float c_in_next, long long total, double* d_cur,
+                                      double* x_next, float* x_in, void* stream) {
+  using namespace mcedm;
+  edm_euler_guided_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x_hat, D, gdx, mask, t_hat, (float)t_hat, t_next - t_hat, c_in_next, total, d_cur, x_next, x_in);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_correct_guided(const double* x_hat, const double* x_e, const float* D2, const float* gdx,
+                                        const double* d_cur, const float* mask, double t_hat, double t_next,
+                                        long long total, double* x_next, void* stream) {
+  using namespace mcedm;
+  edm_correct_guided_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x_hat, x_e, D2, gdx, d_cur, mask, t_next, (float)t_hat, t_next - t_hat, total, x_next);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

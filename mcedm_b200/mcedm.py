@@ -38,6 +38,7 @@ from . import _lib as L
 from .adm_blocks import DhariwalUNet
 from .config import AttrDict
 from .nn_misc import EmaModel, MaskedLoss, NoiseEstimationLoss, Normalizer
+from .pde_loss import DarcyLoss, get_pde_loss_function
 from .runner import LightningModule
 
 
@@ -103,9 +104,8 @@ class PlMcedm(LightningModule):
 
         self.criteria = NoiseEstimationLoss()
         self.mae_criterion = MaskedLoss()
-        # PDE residual metric (models/pde_loss.py) is a post-sampling diagnostic outside the hot path
-        self.pde_loss = None
-        self.pde_loss_simulator = None
+        # PDE residual metric / guidance term on the K6 kernels (overridden by set_pde_loss_function, :82-84)
+        self.pde_loss, self.pde_loss_simulator = get_pde_loss_function(system="swe", flip_xy=False)
 
         self.sparams = self.get_sampler_params(hparams)
         self.test_sparams = self.sparams
@@ -123,8 +123,8 @@ class PlMcedm(LightningModule):
         ch = hparams.model.out_ch // 2
         return (ch,) if ch > 1 else ()
 
-    def set_pde_loss_function(self, system, flip_xy):
-        self.pde_system, self.pde_flip_xy = system, flip_xy
+    def set_pde_loss_function(self, system, flip_xy):                 # :100-104
+        self.pde_loss, self.pde_loss_simulator = get_pde_loss_function(system, flip_xy)
 
     @staticmethod
     def get_sampler_params(params):
@@ -347,6 +347,8 @@ class PlMcedm(LightningModule):
                                             mask)
             self.log(f"val_mae_{name}", loss_hu, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             self.log(f"val_mae_{name}_un", loss_hu_un, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+            pde_loss = self.get_pde_loss(xs[:, -1], clamp_loss=False, do_rearrange=False) / len(h_unnorm)   # :325-328
+            self.log(f"val_pde_loss_{name}", pde_loss, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             result_dict[f"loss_{name}"] = loss_hu
             result_dict[f"loss_{name}_un"] = loss_hu_un
             result_dict[f"traj_{name}"] = xs[:, -1].unsqueeze(dim=1)
@@ -393,6 +395,12 @@ class PlMcedm(LightningModule):
                                             mask_loss, loss_dim)
             self.log(f"test_mae_{name}", loss_hu, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             self.log(f"test_mae_{name}_un", loss_hu_un, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+            # PDE residual of every prediction, then of the ground truth (:416-428)
+            n_batch = len(h_unnorm)
+            pde_loss = self.get_pde_loss(xs[:, -1], clamp_loss=False, do_rearrange=False) / n_samples / n_batch
+            self.log(f"test_pde_loss_{name}", pde_loss, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
+            pde_loss_gt = self.get_pde_loss(state_gt, clamp_loss=False, do_rearrange=False) / n_batch
+            self.log("test_pde_loss_gt", pde_loss_gt, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             result_dict[f"loss_{name}"] = loss_hu
             result_dict[f"loss_{name}_un"] = loss_hu_un
             if n_samples < 15:
@@ -400,6 +408,58 @@ class PlMcedm(LightningModule):
                                                         n=n_samples).unsqueeze(dim=1)
                 result_dict[f"gt_{name}"] = state_gt
         return result_dict
+
+    # ---------------------------------------------------------------- PDE residual (K6) and guidance
+    def _pde_planes(self, h, u):
+        """The two [B,T,X] channel planes for the fused kernel: normalised planes + apply_norm=True when the inverse
+        transform is the plain `x*divide + subtract` (normalization 'gauss', not rescaled), otherwise the host-side
+        inverse transform (clamp / rescale, :186-197) and apply_norm=False."""
+        if self.rescaled or self.normalization == "min_max":
+            h, u = self.inverse_data_transform(h.to(torch.float32), u.to(torch.float32))
+            return h, u, False
+        return h, u, True
+
+    def _pde_residual(self, h, u, x_gt_unnorm, noise_level, clamp_loss, reduce, sum_channels=False):
+        h, u, apply_norm = self._pde_planes(h, u)
+        fast = reduce and not clamp_loss and noise_level is None
+        if isinstance(self.pde_loss, DarcyLoss):
+            m, total = self.pde_loss.residual(h, u, self.normalizer_input, self.normalizer_target,
+                                              apply_norm=apply_norm, want_matrix=not fast)
+        else:
+            m, total = self.pde_loss.residual(h, u, self.normalizer_input, self.normalizer_target, gt=x_gt_unnorm,
+                                              apply_norm=apply_norm, want_matrix=not fast)
+        if fast:
+            return total.to(torch.float32)
+        if clamp_loss:
+            m = torch.clamp(m, max=1.0)
+        if sum_channels and m.dim() > 3:
+            m = torch.sum(m, dim=-1)                                 # ddim.py:1408-1411
+        if noise_level is not None:
+            m = m / (noise_level.reshape(-1, 1, 1, 1) + 1.0)
+        return torch.sum(m) if reduce else m
+
+    def get_pde_loss(self, x_denoised, x_gt_unnorm=None, noise_level=None, clamp_loss=True, do_rearrange=True,
+                     reduce=True):
+        """:468-499. x_denoised: normalised (h, u) sample, `b c h w` (do_rearrange) or `b h w c`, any float dtype."""
+        if do_rearrange:
+            x_denoised = rearrange(x_denoised, "b c h w -> b h w c")
+        if self.h_ch != 1 or self.u_ch != 1:
+            raise NotImplementedError("the PDE residual kernels take one h and one u channel")
+        return self._pde_residual(x_denoised[..., 0], x_denoised[..., 1], x_gt_unnorm, noise_level, clamp_loss, reduce)
+
+    def get_dx_pde(self, cond, x_denoised, calc_prob=False):
+        # :501-517 slices the LAST axis of a `b c h w` tensor into "h" and "u" and then fails inside
+        # SweFvLoss.calculate_loss (torch.cat of 4- and 2-channel tensors): the reference raises RuntimeError here.
+        raise NotImplementedError("PlMcedm.get_dx_pde is not runnable in the reference either (models/mcedm.py:504: "
+                                  "channel slices taken on the width axis); PDE guidance is implemented for PlCondEdm")
+
+    def get_dx_input(self, cond, x_denoised):                         # :519-557 (dx_cond is rejected in __init__)
+        return None
+
+    def get_dx_log_prob(self, cond, x_denoised, guide_dx):            # :559-568
+        if guide_dx:
+            return self.get_dx_pde(cond, x_denoised, calc_prob=True)
+        return torch.zeros_like(x_denoised)
 
     # ---------------------------------------------------------------- sampler
     def edm_time_steps(self, sparams):
@@ -415,7 +475,7 @@ class PlMcedm(LightningModule):
     @torch.no_grad()
     def sample_edm(self, hu, cond, hu_mask, sparams, return_last=True, guide_dx=False):
         if guide_dx:
-            raise NotImplementedError("guide_dx (PDE guidance) has no sm_100a kernel yet (SURVEY §8f)")
+            self.get_dx_pde(cond, hu)                                 # raises: see get_dx_pde
         w = sparams.w
         if not (w is None or abs(w) < 0.001):
             raise NotImplementedError("classifier-free guidance (w != 0) is not supported")
@@ -425,9 +485,11 @@ class PlMcedm(LightningModule):
         return self._sample_core(hu_noise, cond, hu_mask, sparams, return_last)
 
     @torch.no_grad()
-    def _sample_core(self, hu_noise, cond, hu_mask, sparams, return_last=True):
+    def _sample_core(self, hu_noise, cond, hu_mask, sparams, return_last=True, guide_fn=None):
         """Stochastic Heun with mask blending on the kernels, given the initial N(0,1) draw `hu_noise` [B,C,H,W]
-        (shared with PlCondEdm, whose sampler takes the draw from its caller and uses an all-ones mask)."""
+        (shared with PlCondEdm, whose sampler takes the draw from its caller and uses an all-ones mask).
+        guide_fn(cond, D fp32 [B,C,H,W]) -> fp32 [B,C,H,W]: the PDE-guidance gradient of PlCondDdim.sample_edm
+        (ddim.py:1569-1571, :1588-1590); the updates then subtract (5*dx)/t_hat from both slopes."""
         hu = hu_noise
         lib = L.lib()
         model = self.ema_model if self.ema_model is not None else self.model
@@ -446,7 +508,7 @@ class PlMcedm(LightningModule):
         x_cur, x_hat, x_e, d_cur = bufs["x_cur"], bufs["x_hat"], bufs["x_e"], bufs["d_cur"]
         x_in, F_buf, nl = bufs["x_in"], bufs["F"], bufs["nl"]
         c_noise_all = []
-        D_buf = torch.empty_like(x_in) if self._trace is not None else None
+        D_buf = torch.empty_like(x_in) if (self._trace is not None or guide_fn is not None) else None
         st = L.stream_ptr()
         L.check(lib.mcedm_edm_init(L.ptr(hu_noise), L.ptr(cond), cond.shape[1], L.ptr(mask), t_steps[0], B, C, H, W,
                                    L.ptr(x_cur), st), "edm_init")
@@ -481,16 +543,32 @@ class PlMcedm(LightningModule):
             c_skip2, c_out2, c_in2, c_noise2 = precond_scalars(t_next) if not last else (0.0, 0.0, 0.0, 0.0)
             # Euler step; on the last step x_e already is the result (t_next = 0, no correction)
             out_e = x_cur if last else x_e
-            L.check(lib.mcedm_edm_euler(L.ptr(x_hat), L.ptr(F1), L.ptr(mask), t_hat, t_next, c_skip, c_out, c_in2,
-                                        total, L.ptr(d_cur), L.ptr(out_e), None if last else L.ptr(x_in),
-                                        L.ptr(D_buf), st), "edm_euler")
+            if guide_fn is None:
+                L.check(lib.mcedm_edm_euler(L.ptr(x_hat), L.ptr(F1), L.ptr(mask), t_hat, t_next, c_skip, c_out, c_in2,
+                                            total, L.ptr(d_cur), L.ptr(out_e), None if last else L.ptr(x_in),
+                                            L.ptr(D_buf), st), "edm_euler")
+            else:
+                L.check(lib.mcedm_edm_denoised(L.ptr(x_hat), L.ptr(F1), c_skip, c_out, total, L.ptr(D_buf), st),
+                        "edm_denoised")
+                gdx = guide_fn(cond, D_buf)
+                L.check(lib.mcedm_edm_euler_guided(L.ptr(x_hat), L.ptr(D_buf), L.ptr(gdx), L.ptr(mask), t_hat, t_next,
+                                                   c_in2, total, L.ptr(d_cur), L.ptr(out_e),
+                                                   None if last else L.ptr(x_in), st), "edm_euler_guided")
             if self._trace is not None:
                 self._trace.append((i, 0, t_hat, D_buf.clone(), x_hat.clone()))
             if not last:
                 F2 = net_eval(2 * i + 1)
-                L.check(lib.mcedm_edm_correct(L.ptr(x_hat), L.ptr(x_e), L.ptr(F2), L.ptr(d_cur), L.ptr(mask), t_hat,
-                                              t_next, c_skip2, c_out2, total, L.ptr(x_cur), L.ptr(D_buf), st),
-                        "edm_correct")
+                if guide_fn is None:
+                    L.check(lib.mcedm_edm_correct(L.ptr(x_hat), L.ptr(x_e), L.ptr(F2), L.ptr(d_cur), L.ptr(mask),
+                                                  t_hat, t_next, c_skip2, c_out2, total, L.ptr(x_cur), L.ptr(D_buf),
+                                                  st), "edm_correct")
+                else:
+                    L.check(lib.mcedm_edm_denoised(L.ptr(x_e), L.ptr(F2), c_skip2, c_out2, total, L.ptr(D_buf), st),
+                            "edm_denoised")
+                    gdx = guide_fn(cond, D_buf)
+                    L.check(lib.mcedm_edm_correct_guided(L.ptr(x_hat), L.ptr(x_e), L.ptr(D_buf), L.ptr(gdx),
+                                                         L.ptr(d_cur), L.ptr(mask), t_hat, t_next, total,
+                                                         L.ptr(x_cur), st), "edm_correct_guided")
                 if self._trace is not None:
                     self._trace.append((i, 1, t_next, D_buf.clone(), x_e.clone()))
             if xs is not None:

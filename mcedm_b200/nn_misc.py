@@ -4,6 +4,7 @@
     EmaModel              models/ddim_blocks.py:38-59
     NoiseEstimationLoss   models/losses.py:39-59   (forward value; the fused fwd+grad kernel is K6)
     MaskedLoss            models/losses.py:62-78   (evaluation metric on the sampled fields)
+    CorrelationLoss       models/losses.py:96-128  (evaluation metric of the single-task modules)
 
 They keep the reference's class names, constructor arguments, buffer names and return values so
 checkpoints and callers are interchangeable.  Everything here is a handful of elementwise torch ops on
@@ -108,3 +109,30 @@ class MaskedLoss(nn.Module):
         diff = pred - target
         total = diff.abs().sum() if self.l1 else (diff * diff).sum()
         return total / torch.sum(mask)
+
+
+class CorrelationLoss(nn.Module):
+    """Pearson correlation per channel between prediction and target, averaged over the batch."""
+
+    def __init__(self, reduction="none"):
+        super().__init__()
+        self.reduction = reduction
+
+    @staticmethod
+    def calculate_correlation(x, y):
+        x_bar = x - torch.mean(x, dim=1, keepdim=True)
+        y_bar = y - torch.mean(y, dim=1, keepdim=True)
+        cov = torch.sum(y_bar * x_bar, dim=1)
+        denominator = torch.sqrt(torch.sum(x_bar * x_bar, dim=1) * torch.sum(y_bar * y_bar, dim=1))
+        denominator = torch.where(denominator == 0, denominator + 1e-7, denominator)
+        return torch.mean(cov / denominator, dim=0)
+
+    def forward(self, pred, target):
+        pred = pred.reshape(pred.shape[0], -1, pred.shape[-1])
+        target = target.reshape(target.shape[0], -1, target.shape[-1])
+        corr = self.calculate_correlation(pred, target)
+        if self.reduction == "mean":
+            return torch.mean(corr)
+        if self.reduction == "sum":
+            return torch.sum(corr)
+        return corr

@@ -266,11 +266,13 @@ def sample_edm(sd, model_cfg, hu_noise: Tensor, cond: Tensor, hu_mask: Tensor, s
 
 def cond_sample_edm(sd, model_cfg, u_noise: Tensor, h_cond: Tensor, sparams,
                     step_noise: Callable[[int, Tensor], Tensor], return_last: bool = True,
-                    record: Optional[list] = None) -> Tensor:
+                    record: Optional[list] = None,
+                    guide: Optional[Callable[[Tensor, Tensor], Tensor]] = None) -> Tensor:
     """PlCondDdim.sample_edm as PlCondEdm uses it (models/ddim.py:1532-1601; config 5): plain stochastic Heun, NO
-    mask, the condition is h.  Guidance off (guide_dx False => the `- 5 * dx / t_hat` terms are exact zeros; w = 0;
-    no self-conditioning).  u_noise fp32 [B,C,H,W] is the caller's draw (the sampler does not draw its own initial
-    noise, unlike PlMcedm); h_cond [B,Cc,H,W].  Returns xs [B, T, H, W, C] fp64."""
+    mask, the condition is h; w = 0; no self-conditioning.  u_noise fp32 [B,C,H,W] is the caller's draw (the sampler
+    does not draw its own initial noise, unlike PlMcedm); h_cond [B,Cc,H,W].  Returns xs [B, T, H, W, C] fp64.
+    guide(h_cond, denoised fp64) -> fp32 [B,1,H,W]: `get_dx_log_prob(h, denoised, guide_dx=True)` (ddim.py:641-650,
+    see oracle/pde_oracle.get_dx_pde_cond); None => guide_dx False (the `- 5 * dx / t_hat` terms are exact zeros)."""
     num_steps = int(sparams["timesteps"])
     t_steps = edm_schedule(num_steps, sparams["sigma_min"], sparams["sigma_max"], sparams["rho"])
     x_next = u_noise.to(torch.float64) * t_steps[0]                   # :1555
@@ -284,13 +286,19 @@ def cond_sample_edm(sd, model_cfg, u_noise: Tensor, h_cond: Tensor, sparams,
         d1, _ = denoise(sd, model_cfg, x_hat, t_hat, h_cond)
         if record is not None:
             record.append((i, 0, float(t_hat), d1))
-        d_cur = (x_hat - d1.to(torch.float64)) / t_hat                # :1576-1578 with dx = 0
+        d1 = d1.to(torch.float64)
+        d_cur = (x_hat - d1) / t_hat                                  # :1569-1571
+        if guide is not None:
+            d_cur = d_cur - 5. * guide(h_cond, d1) / t_hat
         x_next = x_hat + (t_next - t_hat) * d_cur
         if i < num_steps - 1:
             d2, _ = denoise(sd, model_cfg, x_next, t_next, h_cond)
             if record is not None:
                 record.append((i, 1, float(t_next), d2))
-            d_prime = (x_next - d2.to(torch.float64)) / t_next
+            d2 = d2.to(torch.float64)
+            d_prime = (x_next - d2) / t_next                          # :1588-1590 (t_hat under dx, as the reference)
+            if guide is not None:
+                d_prime = d_prime - 5. * guide(h_cond, d2) / t_hat
             x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
         xs = [x_next] if return_last else xs + [x_next]
     return torch.stack(xs, dim=0).permute(1, 0, 3, 4, 2)

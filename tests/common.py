@@ -66,3 +66,12 @@ def fixture_state(system="swe_per", n=1, seed=7):
     st = D.field_stats(system, 16)
     state = torch.cat([(h - st["input_mean"]) / st["input_std"], (u - st["target_mean"]) / st["target_std"]], dim=-1)
     return state, h, u, st
+
+
+def pde_fields(system, n, seed, amp=0.05):
+    """(pred, gt, stats) of tests/golden/make_golden_pde.perturbed_fields: clean synthetic field + seeded perturbation."""
+    h, u = D._FIELDS[system](n, 128, first_seed=seed)
+    gt = torch.cat([torch.from_numpy(h), torch.from_numpy(u)], dim=-1)
+    g = torch.Generator().manual_seed(1000 + seed)
+    pred = gt + amp * torch.randn(gt.shape, generator=g)
+    return pred, gt, D.field_stats(system, 16)
