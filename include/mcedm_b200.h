@@ -405,6 +405,12 @@ MCEDM_API int mcedm_adam_step(float* p, const float* g, float* m, float* v, long
                               int n_partial, float max_norm, float grad_scale, float* norm_out, void* stream);
 /* ema = ema*beta + (1-beta)*p   (ddim_blocks.py:48-56) */
 MCEDM_API int mcedm_ema_update(float* ema, const float* p, long long n, float beta, void* stream);
+/* All packed operand copies of the parameters in one launch (replaces the per-tensor permute / flip / cast passes of
+ * the weight re-pack after every optimizer step; adm_blocks.py:58 casts the weights per call in the reference).
+ * dst16[i] = round16(base[idx_a[i]]) for i < n16 (fmt 0 bf16, 1 fp16; idx -1 = zero padding);
+ * dst32[j] = base[idx_a[n16+j]] (+ base[idx_b[j]] when idx_b[j] >= 0) for j < n32. */
+MCEDM_API int mcedm_pack_gather(const float* base, const long long* idx_a, const long long* idx_b, long long n16,
+                                long long n32, int fmt, void* dst16, float* dst32, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* bring-up / checker kernels (tests only; not on the product path)                              */

@@ -51,6 +51,7 @@ _PROTOTYPES = {
     "mcedm_sumsq_partial": [_vp, C.c_longlong, _vp, _i, _vp],
     "mcedm_adam_step": [_vp, _vp, _vp, _vp, C.c_longlong, _f, _f, _f, _f, _f, _i, _vp, _i, _f, _f, _vp, _vp],
     "mcedm_ema_update": [_vp, _vp, C.c_longlong, _f, _vp],
+    "mcedm_pack_gather": [_vp, _vp, _vp, C.c_longlong, C.c_longlong, _i, _vp, _vp, _vp],
     "mcedm_wgrad_ctas": [_i, _i, _i],
     "mcedm_conv_wgrad": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],

@@ -13,6 +13,7 @@
 #include "../../include/mcedm_b200.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace mcedm {
 
@@ -233,7 +234,41 @@ ema_update_kernel(float* __restrict__ ema, const float* __restrict__ p, long lon
     ema[i] = ema[i] * beta + (1.0f - beta) * p[i];                  // ddim_blocks.py:53-56
 }
 
+// Weight packing in one launch: every tensor-core operand copy of the parameters (forward layout, flipped /
+// transposed data-gradient layout, permuted qkv, padded head) is a gather from the fp32 parameter storage.
+// idx_a[i] = element offset from `base` (or -1: zero padding); entries [0, n16) are rounded to the 16-bit operand
+// format, entries [n16, n16 + n32) stay fp32 and may add a second source (conv1 bias + skip bias).
+__global__ void __launch_bounds__(256)
+pack_gather_kernel(const float* __restrict__ base, const long long* __restrict__ idx_a,
+                   const long long* __restrict__ idx_b, long long n16, long long n32, int fmt,
+                   unsigned short* __restrict__ dst16, float* __restrict__ dst32) {
+  const long long n = n16 + n32;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const long long a = idx_a[i];
+    float v = a >= 0 ? base[a] : 0.0f;
+    if (i < n16) {
+      dst16[i] = fmt ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    } else {
+      const long long b = idx_b[i - n16];
+      if (b >= 0) v = __fadd_rn(v, base[b]);
+      dst32[i - n16] = v;
+    }
+  }
+}
+
 }  // namespace mcedm
+
+extern "C" int mcedm_pack_gather(const float* base, const long long* idx_a, const long long* idx_b, long long n16,
+                                 long long n32, int fmt, void* dst16, float* dst32, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n16 >= 0 && n32 >= 0 && n16 + n32 >= 1 && (fmt == 0 || fmt == 1), "pack_gather: bad sizes");
+  int grid = (int)((n16 + n32 + 255) / 256);
+  if (grid > 8 * num_sms()) grid = 8 * num_sms();
+  pack_gather_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      base, idx_a, idx_b, n16, n32, fmt, reinterpret_cast<unsigned short*>(dst16), dst32);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int mcedm_edm_noise_in(const float* x, const float* noise, const float* mask, const float* sigma,
                                   const float* c_in, int B, long long chw, float* x_noise, float* x_in, void* stream) {

@@ -27,6 +27,7 @@ import torch
 
 from . import _lib as L
 from .fused_engine import FusedMixin
+from .pack_plan import PackMixin
 from .precise_engine import PreciseMixin
 from .train_engine import TrainMixin
 
@@ -83,7 +84,7 @@ class _Block:
             self.be2 = m.norm2.bias.detach().float().contiguous()
 
 
-class UNetEngine(TrainMixin, FusedMixin, PreciseMixin):
+class UNetEngine(TrainMixin, FusedMixin, PreciseMixin, PackMixin):
     def __init__(self, unet):
         self.unet = unet
         self.lib = L.lib()
@@ -144,6 +145,8 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin):
             raise L.McedmError("mcedm_b200.DhariwalUNet parameters must live on a CUDA (sm_100) device; "
                                "there is no CPU path")
         dt = torch.float16 if self._fmt else torch.bfloat16
+        if getattr(self, "_pack_dtype_override", None) is not None:
+            dt = self._pack_dtype_override
         with torch.no_grad():
             for b in self.blocks_enc + self.blocks_dec:
                 b.pack(dt)

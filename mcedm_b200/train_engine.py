@@ -26,18 +26,21 @@ import torch
 from . import _lib as L
 
 
+DGRAD_DTYPE = [torch.bfloat16]       # pack_plan.PackPlan probes the layouts with fp32 "index" weights
+
+
 def pack_dgrad3x3(weight: torch.Tensor) -> torch.Tensor:
     """[Cout, 64, 3, 3] (one 64-channel input slice) -> bf16 [9][ci][co(_pad 64)]: taps flipped, channels swapped."""
     cout = weight.shape[0]
     w = weight.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, 64, cout)
     if cout < 64:
         w = torch.cat([w, w.new_zeros(9, 64, 64 - cout)], dim=2)
-    return w.to(torch.bfloat16).contiguous()
+    return w.to(DGRAD_DTYPE[0]).contiguous()
 
 
 def pack_dgrad1x1(weight2d: torch.Tensor) -> torch.Tensor:
     """[co, ci] -> bf16 [1][ci][co]"""
-    return weight2d.detach().t().reshape(1, weight2d.shape[1], weight2d.shape[0]).to(torch.bfloat16).contiguous()
+    return weight2d.detach().t().reshape(1, weight2d.shape[1], weight2d.shape[0]).to(DGRAD_DTYPE[0]).contiguous()
 
 
 class TrainMixin:

@@ -43,9 +43,7 @@ class TrainStepGraph:
     def _fwd(self):
         pl, lib, st = self.pl, L.lib(), L.stream_ptr()
         eng = pl.model.engine()
-        eng._fmt = 0
-        eng.pack(force=True)
-        eng.pack_train(force=True)
+        eng.pack_fused()                   # every operand copy of the parameters: one gather launch (pack_plan.py)
         B = self.x.shape[0]
         chw = self.x[0].numel()
         s = self.sigma

@@ -423,3 +423,45 @@ def test_fused_optimizer_step_and_ema_inside_trainer_loop(dev):
     sd = opt.state_dict()
     assert len(sd["state"]) == len(p0) and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     assert float(sd["state"][0]["step"]) == 2.0
+
+
+def test_pack_plan_is_bit_identical_to_the_torch_packing(dev):
+    """pack_plan.PackPlan (one mcedm_pack_gather launch) against UNetEngine.pack + pack_train (the ~170 torch
+    permute / flip / cast kernels it replaces): every packed tensor bit for bit, before and after the parameters
+    change in place, for the joint and the single-task network."""
+    from common import stress_unet
+    from mcedm_b200 import pack_plan as PP
+
+    for config in ("config_adm_edm_mcedm_res32", "config_adm_edm_res32_cond_h"):
+        net, _, _ = stress_unet(config)
+        net = net.to(dev)
+        eng = net.engine()
+
+        def snapshot():
+            eng._fmt = 0
+            eng.pack(force=True)
+            eng.pack_train(force=True)
+            return [(name, i, PP._get(o, name, i).clone()) for o, name, i, _ in PP._entries(eng)]
+
+        ref0 = snapshot()
+        assert len(ref0) > 80
+        eng.pack_fused()
+        got = [(name, i, PP._get(o, name, i)) for o, name, i, _ in PP._entries(eng)]
+        assert len(got) == len(ref0)
+        for (n0, i0, a), (n1, i1, b) in zip(ref0, got):
+            assert (n0, i0) == (n1, i1) and a.dtype == b.dtype and a.shape == b.shape
+            assert b.data_ptr() % 512 == 0        # torch allocations are 512-byte aligned; slots are 1 KiB multiples
+            assert torch.equal(a, b), (n0, i0)
+        # in-place update (what the fused Adam kernel does): one more launch refreshes every copy
+        gen = torch.Generator(device=dev).manual_seed(3)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(torch.randn(p.shape, device=dev, generator=gen) * 0.01)
+        plan = eng._pack_plan
+        eng.pack_fused()
+        assert eng._pack_plan is plan
+        got = [PP._get(o, name, i).clone() for o, name, i, _ in PP._entries(eng)]
+        ref1 = snapshot()
+        for (n0, i0, a), b in zip(ref1, got):
+            assert torch.equal(a, b), (n0, i0)
+        assert any(not torch.equal(a[2], b[2]) for a, b in zip(ref0, ref1))
