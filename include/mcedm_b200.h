@@ -343,6 +343,14 @@ MCEDM_API int mcedm_edm_euler_guided(const double* x_hat, const float* D, const 
 MCEDM_API int mcedm_edm_correct_guided(const double* x_hat, const double* x_e, const float* D2, const float* gdx,
                                        const double* d_cur, const float* mask, double t_hat, double t_next,
                                        long long total, double* x_next, void* stream);
+/* RePaint-style conditioning of PlDdim.sample_edm (models/ddim.py:959-1051; mask == 1 means KNOWN):
+ * x0 = double((hu*sqrt_a + noise*sqrt_1ma)*mask + noise*(1-mask)) * t0                          (:987-993) */
+MCEDM_API int mcedm_edm_vp_init(const float* hu, const float* noise, const float* mask, float sqrt_a, float sqrt_1ma,
+                                double t0, long long total, double* x, void* stream);
+/* x = double((sqrt_a*hu + sqrt_1ma*noise)*mask) + x*double(1-mask), in place (:1029-1031); sqrt_a = 1, sqrt_1ma = 0 is
+ * the final replacement `hu*mask + x*(1-mask)` (:1040-1041) */
+MCEDM_API int mcedm_edm_repaint_blend(const float* hu, const float* noise, const float* mask, float sqrt_a,
+                                      float sqrt_1ma, long long total, double* x, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K6: PDE residual of sampled fields and its gradient (pde.cu)                                  */

@@ -72,6 +72,8 @@ _PROTOTYPES = {
     "mcedm_edm_denoised": [_vp, _vp, _f, _f, C.c_longlong, _vp, _vp],
     "mcedm_edm_euler_guided": [_vp, _vp, _vp, _vp, _d, _d, _f, C.c_longlong, _vp, _vp, _vp, _vp],
     "mcedm_edm_correct_guided": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, C.c_longlong, _vp, _vp],
+    "mcedm_edm_vp_init": [_vp, _vp, _vp, _f, _f, _d, C.c_longlong, _vp, _vp],
+    "mcedm_edm_repaint_blend": [_vp, _vp, _vp, _f, _f, C.c_longlong, _vp, _vp],
     "mcedm_swe_fv_loss": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp,
                           _vp],
     "mcedm_swe_fv_grad": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp],

@@ -152,8 +152,6 @@ class DhariwalUNet(torch.nn.Module):
         self.cat_dx = m.cat_dx if _has(m, "cat_dx") else False
         # features of the reference network that have no sm_100a kernel (off in every shipped m-cedm config)
         unsupported = []
-        if self.self_condition:
-            unsupported.append("self_cond")
         if self.dx_cond:
             unsupported.append("dx_cond")
         if augment_dim:
@@ -170,8 +168,12 @@ class DhariwalUNet(torch.nn.Module):
             raise NotImplementedError("mcedm_b200.DhariwalUNet: unsupported options: " + ", ".join(unsupported))
 
         in_channels = m.in_channels
-        self.in_channels = in_channels + cond_channels if self.cat_condition else in_channels
+        # self-conditioning stacks a second copy of the state in front of it (adm_blocks.py:235, :321-324); the first
+        # conv sees [cond | x_self_cond | x], so the kernels treat the self-conditioning block as extra cond channels
+        self.sc_channels = in_channels if self.self_condition else 0
+        self.in_channels = in_channels + self.sc_channels + (cond_channels if self.cat_condition else 0)
         self.cond_channels = cond_channels
+        self.cat_channels = self.in_channels - in_channels            # channels concatenated in front of x
         self.x_channels = in_channels
         self.out_channels = out_channels
         self.ch = ch * channel_mult[0]
@@ -242,8 +244,19 @@ class DhariwalUNet(torch.nn.Module):
     def forward(self, x, noise_labels, cond=None, x_self_cond=None, dx=None, class_labels=None, augment_labels=None):
         """F_x = U-Net(x, c_noise, cond): x [B,Cx,H,W] fp32 CUDA (already scaled by c_in), noise_labels [B] or [1],
         cond [B,Cc,H,W] fp32 or None (zeros, as in models/adm_blocks.py:327-331). Returns [B,out_ch,H,W] fp32."""
-        if x_self_cond is not None or dx is not None or class_labels is not None or augment_labels is not None:
-            raise NotImplementedError("self-conditioning, dx conditioning, class and augment labels are not supported")
+        if dx is not None or class_labels is not None or augment_labels is not None:
+            raise NotImplementedError("dx conditioning, class and augment labels are not supported")
+        if x_self_cond is not None and not self.self_condition:
+            raise ValueError("x_self_cond given to a network built without self_cond")
+        if self.self_condition:                                       # cat_conditioning, adm_blocks.py:319-333
+            sc = torch.zeros_like(x) if x_self_cond is None else x_self_cond
+            if self.cond_channels > 0:
+                if cond is None:
+                    cond = torch.zeros(x.shape[0], self.cond_channels, x.shape[2], x.shape[3], device=x.device,
+                                       dtype=x.dtype)
+                cond = torch.cat([cond, sc], dim=1)
+            else:
+                cond = sc
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training: the autograd node's backward runs the hand-written backward kernels (train_engine.py)
             from .autograd import UNetFunction

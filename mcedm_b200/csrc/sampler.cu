@@ -137,6 +137,32 @@ __global__ void edm_correct_guided_kernel(const double* __restrict__ x_hat, cons
   x_next[i] = __dadd_rn(x_hat[i], __dmul_rn(__dmul_rn(dt, avg), (double)mask[i]));
 }
 
+// ---- RePaint-style known-region handling of PlDdim.sample_edm (models/ddim.py:959-1051) ---------------------------
+// x0 = double( (hu*sa + noise*s1)*m + noise*(1-m) ) * t0 ; sa = sqrt(alpha_bar(t0)), s1 = sqrt(1 - alpha_bar(t0))
+// float32 up to the cast, as torch evaluates :987-993 (mask == 1 means KNOWN here, the opposite of PlMcedm)
+__global__ void edm_vp_init_kernel(const float* __restrict__ hu, const float* __restrict__ noise,
+                                   const float* __restrict__ mask, float sa, float s1, double t0, long long total,
+                                   double* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = mask[i], n = noise[i];
+  const float known = __fadd_rn(__fmul_rn(hu[i], sa), __fmul_rn(n, s1));
+  const float x32 = __fadd_rn(__fmul_rn(known, m), __fmul_rn(n, __fsub_rn(1.0f, m)));
+  x[i] = __dmul_rn((double)x32, t0);
+}
+
+// x = double((sa*hu + s1*noise)*m) + x*double(1-m)   (replace the known part, :1029-1031; sa = 1, s1 = 0 gives the
+// final `hu*m + x*(1-m)` of :1040-1041 exactly)
+__global__ void edm_repaint_blend_kernel(const float* __restrict__ hu, const float* __restrict__ noise,
+                                         const float* __restrict__ mask, float sa, float s1, long long total,
+                                         double* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = mask[i];
+  const float known = __fadd_rn(__fmul_rn(sa, hu[i]), __fmul_rn(s1, noise[i]));
+  x[i] = __dadd_rn((double)__fmul_rn(known, m), __dmul_rn(x[i], (double)__fsub_rn(1.0f, m)));
+}
+
 static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
 }  // namespace mcedm
@@ -226,6 +252,24 @@ extern "C" int mcedm_edm_correct_guided(const double* x_hat, const double* x_e, 
   using namespace mcedm;
   edm_correct_guided_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x_hat, x_e, D2, gdx, d_cur, mask, t_next, (float)t_hat, t_next - t_hat, total, x_next);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_vp_init(const float* hu, const float* noise, const float* mask, float sqrt_a, float sqrt_1ma,
+                                 double t0, long long total, double* x, void* stream) {
+  using namespace mcedm;
+  edm_vp_init_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hu, noise, mask, sqrt_a,
+                                                                                            sqrt_1ma, t0, total, x);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_edm_repaint_blend(const float* hu, const float* noise, const float* mask, float sqrt_a,
+                                       float sqrt_1ma, long long total, double* x, void* stream) {
+  using namespace mcedm;
+  edm_repaint_blend_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      hu, noise, mask, sqrt_a, sqrt_1ma, total, x);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

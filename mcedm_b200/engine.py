@@ -344,11 +344,11 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin, PackMixin):
             raise ValueError(f"unsupported field size {H}x{W} (needs W | 128 and 128 | H*W)")
         dev = x.device
         x = x.contiguous()
-        if u.cond_channels > 0:
+        if u.cat_channels > 0:
             if cond is None:
-                cond = torch.zeros(B, u.cond_channels, H, W, device=dev, dtype=torch.float32)
-            if cond.shape != (B, u.cond_channels, H, W) or cond.dtype != torch.float32:
-                raise ValueError(f"cond must be fp32 [B,{u.cond_channels},H,W], got {cond.dtype} {tuple(cond.shape)}")
+                cond = torch.zeros(B, u.cat_channels, H, W, device=dev, dtype=torch.float32)
+            if cond.shape != (B, u.cat_channels, H, W) or cond.dtype != torch.float32:
+                raise ValueError(f"cond must be fp32 [B,{u.cat_channels},H,W], got {cond.dtype} {tuple(cond.shape)}")
             cond = cond.contiguous()
         else:
             cond = None
@@ -379,7 +379,7 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin, PackMixin):
                                   L.ptr(self.b_m1), L.ptr(self.aff_w), L.ptr(self.aff_b), self.n_aff, Bemb, None,
                                   L.ptr(ws["ss"]), st), "emb_mlp")
         t0, t0_st = self._tensor(ws, "conv_in", B, H, W, dev)
-        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in),
+        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cat_channels, L.ptr(self.w_in),
                                   L.ptr(self.b_in), B, H, W, L.ptr(t0), L.ptr(t0_st), st), "conv_in")
         cur, ch, cw = (t0, t0_st, H * W // 128), H, W
         skips = [cur]

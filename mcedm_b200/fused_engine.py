@@ -214,11 +214,11 @@ class FusedMixin:
         t0 = self._fact(ws, "conv_in", B, H, W, dev)
         if self.w_in_tc is not None:
             # first conv on the tensor cores: horizontal taps folded into K by builder warps, vertical taps stacked into N
-            L.check(lib.mcedm_conv_in_tc16(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in_tc),
+            L.check(lib.mcedm_conv_in_tc16(L.ptr(x), u.x_channels, L.ptr(cond), u.cat_channels, L.ptr(self.w_in_tc),
                                            L.ptr(self.b_in), B, H, L.ptr(t0.t), L.ptr(t0.st), self._fmt, st), "conv_in_tc16")
             t0.parts = 4 * H
         else:
-            L.check(lib.mcedm_conv_in16(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in),
+            L.check(lib.mcedm_conv_in16(L.ptr(x), u.x_channels, L.ptr(cond), u.cat_channels, L.ptr(self.w_in),
                                         L.ptr(self.b_in), B, H, W, L.ptr(t0.t), L.ptr(t0.st), self._fmt, st), "conv_in16")
             t0.parts = H * W // 128
         cur = t0

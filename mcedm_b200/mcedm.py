@@ -284,7 +284,7 @@ class PlMcedm(LightningModule):
         if tg is None:
             if len(graphs) > 4:
                 graphs.clear()
-            tg = TrainStepGraph(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], unet.cond_channels, x.device)
+            tg = TrainStepGraph(self, x.shape[0], x.shape[1], x.shape[2], x.shape[3], unet.cat_channels, x.device)
             tg.load(x, s, noise, cond, mask, weight)
             tg.capture()
             graphs[key] = tg

@@ -160,7 +160,7 @@ class PreciseMixin:
                                   L.ptr(self.b_m1), L.ptr(self.aff_w), L.ptr(self.aff_b), self.n_aff, Bemb, None,
                                   L.ptr(ws["ss"]), st), "emb_mlp")
         t0, t0_st = self._tensor(ws, "conv_in", B, H, W, dev)
-        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in),
+        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cat_channels, L.ptr(self.w_in),
                                   L.ptr(self.b_in), B, H, W, L.ptr(t0), L.ptr(t0_st), st), "conv_in")      # fp32 FMA
         cur, ch, cw = (t0, t0_st, H * W // 128), H, W
         skips = [cur]

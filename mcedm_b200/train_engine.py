@@ -190,10 +190,10 @@ class TrainMixin:
                                   L.ptr(self.w_m1), L.ptr(self.b_m1), L.ptr(self.aff_w), L.ptr(self.aff_b), self.n_aff,
                                   B, None, L.ptr(ss_all), st), "emb_mlp")
         xin_pad = self._t(tw, "xin_pad", (B, H, W, 64), torch.bfloat16, zero=True)
-        L.check(lib.mcedm_nchw_to_nhwc_pad(L.ptr(cond), u.cond_channels if cond is not None else 0, L.ptr(x),
+        L.check(lib.mcedm_nchw_to_nhwc_pad(L.ptr(cond), u.cat_channels if cond is not None else 0, L.ptr(x),
                                            u.x_channels, B, H, W, L.ptr(xin_pad), 0, st), "nchw_to_nhwc_pad")
         t0, t0_st = self._act(tw, "conv_in", B, H, W)
-        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cond_channels, L.ptr(self.w_in),
+        L.check(lib.mcedm_conv_in(L.ptr(x), u.x_channels, L.ptr(cond), u.cat_channels, L.ptr(self.w_in),
                                   L.ptr(self.b_in), B, H, W, L.ptr(t0), L.ptr(t0_st), st), "conv_in")
         cur, ch, cw = ("conv_in", t0, t0_st, H * W // 128), H, W
         skips = [cur]

@@ -136,8 +136,9 @@ def _block(sd, pfx: str, spec: dict, x: Tensor, emb: Tensor) -> Tensor:
 
 
 def unet_forward(sd: Dict[str, Tensor], model_cfg, x: Tensor, noise_labels: Tensor,
-                 cond: Optional[Tensor] = None) -> Tensor:
-    """DhariwalUNet.forward (adm_blocks.py:364-404) for cat_cond=True, no labels / augment / self-cond."""
+                 cond: Optional[Tensor] = None, x_self_cond: Optional[Tensor] = None) -> Tensor:
+    """DhariwalUNet.forward (adm_blocks.py:364-404) for cat_cond=True, no labels / augment; self-conditioning stacks
+    `x_self_cond` (zeros when None) in front of x (:321-324)."""
     ch = model_cfg["ch"]
     half = ch // 2
     freqs = torch.arange(half).to(noise_labels.dtype) / half          # PositionalEmbedding, :192-199
@@ -146,6 +147,8 @@ def unet_forward(sd: Dict[str, Tensor], model_cfg, x: Tensor, noise_labels: Tens
     emb = torch.cat([e.cos(), e.sin()], dim=1)
     emb = F.silu(_linear(emb, sd["map_layer0.weight"], sd["map_layer0.bias"]))
     emb = F.silu(_linear(emb, sd["map_layer1.weight"], sd["map_layer1.bias"]))
+    if model_cfg.get("self_cond", False):
+        x = torch.cat([torch.zeros_like(x) if x_self_cond is None else x_self_cond, x], dim=1)
     cc = model_cfg.get("cond_channels", 0) if model_cfg.get("cat_cond", False) else 0
     if cc > 0:
         if cond is None:
@@ -308,6 +311,93 @@ def cond_training_loss(sd, model_cfg, u: Tensor, sigma: Tensor, noise: Tensor, h
     """PlCondEdm.forward + NoiseEstimationLoss (models/ddim.py:1668-1694, :1723; losses.py:48-53): x_noise = u + noise*sigma,
     loss over every pixel, the condition h is not scaled (and is None when the cond_p coin drops it)."""
     return training_loss(sd, model_cfg, u, sigma, noise, h_cond, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# PlDdim: EDM sampler on the VP sigma grid with RePaint-style conditioning (models/ddim.py:915-1051), BASELINE config 4
+# ------------------------------------------------------------------------------------------------
+class VpGrid:
+    """The diffusion schedule of PlDdim (ddim.py:150-160, ddim_blocks.py:487-490 linear betas) and what
+    set_test_sampler_params derives from it (:121-137); round_sigma (:949-957) and compute_alpha (:700-704)."""
+
+    def __init__(self, beta_start=0.0001, beta_end=0.02, n=1000):
+        self.betas = torch.from_numpy(np.linspace(beta_start, beta_end, n, dtype=np.float64)).float()
+        self.num_timesteps = n
+        alphas_bar = (1.0 - self.betas).cumprod(dim=0)
+        self.edm_steps = ((1 - alphas_bar) / alphas_bar).sqrt().flip(dims=(0,))
+        self.sigma_min = float(self.edm_steps[n - 1])
+        self.sigma_max = float(self.edm_steps[0])
+
+    def round_sigma(self, sigma: Tensor, return_index=False) -> Tensor:
+        sigma32 = sigma.to(torch.float32)
+        index = torch.cdist(sigma32.reshape(1, -1, 1), self.edm_steps.reshape(1, -1, 1)).argmin(2)
+        result = index if return_index else self.edm_steps[index.flatten()]
+        return result.type_as(sigma).reshape(sigma.shape)
+
+    def compute_alpha(self, t: Tensor) -> Tensor:
+        betas = torch.cat([torch.zeros(1), self.betas], dim=0)
+        return (1 - betas).cumprod(dim=0).index_select(0, t.reshape(-1) + 1).view(-1, 1, 1, 1)
+
+
+def vp_denoise(sd, model_cfg, grid: VpGrid, xt: Tensor, t: Tensor):
+    """PlDdim.get_denoised with cond = x_self_cond = dx = None (ddim.py:915-947): c_skip = 1, c_out = -sigma."""
+    xt = xt.to(torch.float32)
+    sigma = t.to(torch.float32).reshape(-1, 1, 1, 1)
+    c_in = 1 / (sigma ** 2 + 1).sqrt()
+    c_noise = grid.num_timesteps - 1 - grid.round_sigma(sigma, return_index=True).to(torch.float32)
+    f_x = unet_forward(sd, model_cfg, c_in * xt, c_noise.flatten(), None)
+    return 1 * xt + (-sigma) * f_x, f_x
+
+
+def ddim_sample_edm(sd, model_cfg, grid: VpGrid, hu: Tensor, hu_noise: Tensor, sparams,
+                    step_noise: Callable[[Tensor], Tensor], h_ch: int = 1, u_ch: int = 1, return_last: bool = True,
+                    record: Optional[list] = None) -> Tensor:
+    """PlDdim.sample_edm (ddim.py:959-1051) with guide_dx False, w = 0.  hu fp32 [B,C,H,W]: the normalised ground truth
+    whose first n_time_h / n_time_u time rows are known (mask == 1 KNOWN); hu_noise: the draw of :967;
+    step_noise(x) -> fp64 draw of :1002 / :1036.  Returns xs [B, T, H, W, C] fp64."""
+    n_repeat, n_time_h, n_time_u = sparams["n_repeat"], sparams["n_time_h"], sparams["n_time_u"]
+    hu_mask = torch.ones_like(hu)
+    hu_mask[:, 0:h_ch, n_time_h:, :] = 0.0
+    hu_mask[:, h_ch:h_ch + u_ch, n_time_u:, :] = 0.0
+    sigma_min = max(sparams["sigma_min"], grid.sigma_min)
+    sigma_max = min(sparams["sigma_max"], grid.sigma_max)
+    num_steps, rho = int(sparams["timesteps"]), sparams["rho"]
+    i_ = torch.arange(num_steps, dtype=torch.float64)
+    t_steps = (sigma_max ** (1 / rho) + i_ / (num_steps - 1) * (sigma_min ** (1 / rho) - sigma_max ** (1 / rho))) ** rho
+    t_steps = torch.cat([grid.round_sigma(t_steps), torch.zeros_like(t_steps[:1])])
+    aT = grid.compute_alpha(t_steps[0].long())
+    hu_t_known = hu * aT.sqrt() + hu_noise * (1.0 - aT).sqrt()
+    x = hu_t_known * hu_mask + hu_noise * (1.0 - hu_mask)
+    x_next = x.to(torch.float64) * t_steps[0]
+    xs = [x_next]
+    s_min, s_max = sparams["S_min"], float(sparams["S_max"])
+    for i, (t_cur, t_next) in enumerate(zip(t_steps[:-1], t_steps[1:])):
+        x_cur = x_next
+        gamma = min(sparams["S_churn"] / num_steps, np.sqrt(2) - 1) if s_min <= t_cur <= s_max else 0
+        t_hat = grid.round_sigma(t_cur + gamma * t_cur)
+        x_hat = x_cur + (t_hat ** 2 - t_cur ** 2).sqrt() * sparams["S_noise"] * step_noise(x_cur)
+        for k in range(n_repeat):
+            d1, _ = vp_denoise(sd, model_cfg, grid, x_hat, t_hat)
+            if record is not None:
+                record.append((i, k, 0, float(t_hat), d1))
+            d_cur = (x_hat - d1.to(torch.float64)) / t_hat
+            x_next = x_hat + (t_next - t_hat) * d_cur
+            if i < num_steps - 1:
+                d2, _ = vp_denoise(sd, model_cfg, grid, x_next, t_next)
+                if record is not None:
+                    record.append((i, k, 1, float(t_next), d2))
+                d_prime = (x_next - d2.to(torch.float64)) / t_next
+                x_next = x_hat + (t_next - t_hat) * (0.5 * d_cur + 0.5 * d_prime)
+            at_next = grid.compute_alpha(t_next.long())
+            hu_t_known = at_next.sqrt() * hu + (1 - at_next).sqrt() * hu_noise
+            x_next = hu_t_known * hu_mask + x_next * (1.0 - hu_mask)
+            if k < n_repeat - 1:
+                t_hat = grid.round_sigma(t_next + (np.sqrt(2) - 1) * t_next)
+                x_hat = x_next + (t_hat ** 2 - t_next ** 2).sqrt() * sparams["S_noise"] * step_noise(x_next)
+        if i == num_steps - 1:
+            x_next = hu * hu_mask + x_next * (1.0 - hu_mask)
+        xs = [x_next] if return_last else xs + [x_next]
+    return torch.stack(xs, dim=0).permute(1, 0, 3, 4, 2)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -157,3 +157,37 @@ def test_oracle_cond_edm_path_matches_reference():
     with torch.no_grad():
         loss, _ = O.cond_training_loss(sd, mcfg, u_n, sigma, noise, h_n)
     assert abs(float(loss) - float(g["train"]["loss"])) < 2e-5 * abs(float(g["train"]["loss"]))
+
+
+def test_oracle_ddim_repaint_sampler_matches_reference():
+    """BASELINE config 4 (PlDdim.sample_edm, n_time_h=0, n_time_u=64, n_repeat=2, ADM network with self_cond): the
+    oracle's VP-grid sampler against the fixture produced by the unmodified reference (tests/golden/make_golden_ddim.py)."""
+    import copy
+
+    g = golden("ddim_path.pt")
+    net, cfg, init_hash = stress_unet("config_adm_ddim_res32")
+    assert init_hash == g["init_hash"]
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    mcfg = dict(cfg.model.hparams.model)
+    grid = O.VpGrid()
+    assert abs(grid.sigma_min - g["sigma_min"]) < 1e-12 and abs(grid.sigma_max - g["sigma_max"]) < 1e-9
+    h, u = D._FIELDS["swe"](1, 128, first_seed=g["field_seed"])
+    st = g["stats"]
+    hu = torch.cat([(torch.from_numpy(h) - st["input_mean"]) / st["input_std"],
+                    (torch.from_numpy(u) - st["target_mean"]) / st["target_std"]], dim=-1).permute(0, 3, 1, 2).contiguous()
+    s = g["sample"]
+    sp = dict(copy.deepcopy(cfg.diff_sampler))
+    sp.update(timesteps=s["steps"], n_time_h=s["n_time_h"], n_time_u=s["n_time_u"], n_repeat=s["n_repeat"])
+    feed = NoiseFeed(s["seed"])
+    hu_noise = feed.draw(hu)
+    rec = []
+    with torch.no_grad():
+        xs = O.ddim_sample_edm(sd, mcfg, grid, hu, hu_noise, sp, feed.draw, record=rec)
+    assert [tuple(c) for c in feed.calls] == [tuple(c) for c in s["calls"]]
+    assert len(rec) == len(s["denoised"])
+    for (i, k, which, sigma, d), ref in zip(rec, s["denoised"]):
+        assert abs(sigma - ref["sigma"]) <= 1e-9 * max(1.0, ref["sigma"])
+        assert rel_l2(d, ref["D"]) < 1e-5
+    assert rel_l2(xs, s["xs"]) < 1e-5
+    # the observed region (u for t < 64) is re-imposed exactly; the rest is generated
+    assert torch.equal(xs[0, 0, :64, :, 1], hu[0, 1, :64].double())
