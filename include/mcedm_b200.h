@@ -242,6 +242,16 @@ MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrst
 /* out[j] (+)= scale * sum_r in[r*stride_r + j*stride_j]  (ordered fp64 sum; folds per-CTA / per-sample partials) */
 MCEDM_API int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r, int n_cols, long long stride_j,
                                 float* out, int accumulate, float scale, void* stream);
+/* The same fold for a device-resident table of jobs in one launch (grid.y = job). The backward of a training step
+ * queues its ~60 bias / gamma / beta folds and runs them together; outputs of different jobs must not overlap. */
+typedef struct mcedm_reduce_job {
+  const float* in;
+  float* out;
+  long long stride_r, stride_j;
+  int n_rows, n_cols, accumulate;
+  float scale;
+} mcedm_reduce_job;
+MCEDM_API int mcedm_reduce_rows_batched(const mcedm_reduce_job* jobs_dev, int n_jobs, int max_cols, void* stream);
 /* K6: masked weighted EDM loss and dL/dF (mcedm.py:213-239, :278; losses.py:48-53). NCHW fp32, chw elements per
  * sample; loss = (1/B) * sum(loss_partial[B][ctas_per_sample]); dF may be NULL (forward value only).
  * dF_pad_bf16 NULL, or bf16 NHWC [B, hw, 64] whose first chw/hw channels receive dL/dF (the other channels must
@@ -270,6 +280,14 @@ MCEDM_API int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int
                                int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, void* stream);
 MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
                                  int co_mul, int co_add, int co_count, int ci_count, int accumulate, void* stream);
+/* Every weight-gradient fold of a step in one launch (same arithmetic and order as mcedm_wgrad_reduce, accumulate = 0);
+ * each job needs its own partial buffer. */
+typedef struct mcedm_wgrad_job {
+  const float* partial;
+  float* dw;
+  int n_ctas, taps, cin_total, ci_off, co_mul, co_add, co_count, ci_count;
+} mcedm_wgrad_job;
+MCEDM_API int mcedm_wgrad_reduce_batched(const mcedm_wgrad_job* jobs_dev, int n_jobs, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* K3  fused self-attention (models/adm_blocks.py:103-109 AttentionOp.forward, :176-178)          */

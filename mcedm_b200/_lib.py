@@ -43,6 +43,8 @@ _PROTOTYPES = {
     "mcedm_gn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp,
                      _vp, _vp, _i, _i, _vp, _vp, _vp],
     "mcedm_reduce_rows": [_vp, _i, C.c_longlong, _i, C.c_longlong, _vp, _i, _f, _vp],
+    "mcedm_reduce_rows_batched": [_vp, _i, _i, _vp],
+    "mcedm_wgrad_reduce_batched": [_vp, _i, _vp],
     "mcedm_edm_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _i, _vp],
     "mcedm_edm_noise_in": [_vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, _vp],
     "mcedm_nchw_to_nhwc_pad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp],

@@ -255,6 +255,30 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int taps, flo
   *o = accumulate ? *o + (float)t : (float)t;
 }
 
+// Every weight-gradient fold of a training step in ONE launch (grid.y = job): 33 folds of 148 partials each are
+// latency-bound (a dependent fp64 chain per thread), ~15 us per launch on their own.
+__global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const mcedm_wgrad_job* __restrict__ jobs) {
+  const mcedm_wgrad_job jb = jobs[blockIdx.y];
+  const int idx = blockIdx.x * 256 + threadIdx.x;        // (tap, co, ci), ci fastest
+  if (idx >= jb.taps * 4096) return;
+  const int ci = idx & 63, co = (idx >> 6) & 63, tap = idx >> 12;
+  if (co >= jb.co_count || ci >= jb.ci_count) return;
+  const long long step = (long long)jb.taps * 4096;
+  const float* p = jb.partial + idx;
+  double t = 0.0;
+  int c = 0;
+  for (; c + 8 <= jb.n_ctas; c += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[(long long)(c + k) * step];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += (double)v[k];
+  }
+  for (; c < jb.n_ctas; ++c) t += (double)p[(long long)c * step];
+  float* o = jb.dw + ((long long)(co * jb.co_mul + jb.co_add) * jb.cin_total + jb.ci_off + ci) * jb.taps + tap;
+  *o = (float)t;
+}
+
 static int wgrad_grid(int B, int H, int W) {
   long long g = (long long)B * H * W / 512;
   if (g < 1) g = 1;
@@ -335,6 +359,15 @@ extern "C" int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, fl
   const int n = taps * 4096;
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partial, n_ctas, taps, dw, cin_total, ci_off, co_mul, co_add, co_count, ci_count, accumulate);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_wgrad_reduce_batched(const mcedm_wgrad_job* jobs_dev, int n_jobs, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(n_jobs >= 1 && n_jobs <= 65535, "wgrad_reduce_batched: bad sizes");
+  dim3 grid(9 * 4096 / 256, n_jobs);
+  wgrad_reduce_batched_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs_dev);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -241,9 +241,39 @@ class TrainMixin:
     def _dense_of(gs):
         return gs["bf"] if gs["flat"] is None else gs["dense"]
 
+    # ---- deferred folds: every bias / gamma / beta / weight-gradient fold only feeds the flat gradient buffer, so the
+    # backward queues them (each with its own partial buffer) and runs them in two batched launches at its end
+    # instead of ~95 latency-bound launches spread through it (mcedm_reduce_rows_batched / mcedm_wgrad_reduce_batched)
+    def _job_id(self):
+        self._jid += 1
+        return self._jid
+
     def _reduce_rows(self, src, n_rows, stride_r, n_cols, stride_j, out, st, accumulate=0):
-        L.check(self.lib.mcedm_reduce_rows(L.ptr(src), n_rows, stride_r, n_cols, stride_j, L.ptr(out), accumulate, 1.0,
-                                           st), "reduce_rows")
+        assert accumulate == 0
+        self._rjobs.append((src.data_ptr(), out.data_ptr(), int(stride_r), int(stride_j), int(n_rows), int(n_cols), 0,
+                            1.0))
+        self._job_refs += [src, out]
+
+    def _flush_deferred(self, tw, st):
+        import struct
+
+        key = (tuple(self._rjobs), tuple(self._wjobs))
+        cache = tw.setdefault("fold_tables", {})
+        tab = cache.get(key)
+        if tab is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise L.McedmError("deferred-fold tables must be built by an eager backward before graph capture")
+            if len(cache) > 4:
+                cache.clear()
+            rb = b"".join(struct.pack("<QQqqiiif", *j) for j in self._rjobs)
+            wb = b"".join(struct.pack("<QQiiiiiiii", *j) for j in self._wjobs)
+            dev = tw["dev"]
+            tab = cache[key] = (torch.frombuffer(bytearray(rb), dtype=torch.uint8).to(dev),
+                                torch.frombuffer(bytearray(wb), dtype=torch.uint8).to(dev),
+                                max(j[5] for j in self._rjobs))
+        rt, wt, max_cols = tab
+        L.check(self.lib.mcedm_wgrad_reduce_batched(L.ptr(wt), len(self._wjobs), st), "wgrad_reduce_batched")
+        L.check(self.lib.mcedm_reduce_rows_batched(L.ptr(rt), len(self._rjobs), max_cols, st), "reduce_rows_batched")
 
     def _bias_grad(self, gs, B, out, st):
         self._reduce_rows(gs["cs"], B * gs["n_cta"], 64, 64, 1, out, st)
@@ -255,10 +285,12 @@ class TrainMixin:
         n_cta = lib.mcedm_gn_bwd_ctas_per_img(Hin, Win, B)
         red = self._t(tw, ("gnred", B * n_cta), (B, n_cta, 64, 2), torch.float32)
         coef = self._t(tw, "gncoef", (B, 64, 4), torch.float32)
-        dgb = self._t(tw, "gndgb", (B, 64, 2), torch.float32)
+        jid = self._job_id()
+        dgb = self._t(tw, ("gndgb", jid), (B, 64, 2), torch.float32)   # per call: folded at the end of the backward
         bf = dense = cs = None
         pitch = blk = 0
         if gs is not None:
+            gs["cs"] = self._t(tw, ("cs", jid), (B * gs["n_cta"], 64), torch.float32)
             out_f32, bf, cs = gs["f32"], gs["bf"], gs["cs"]
             if gs["flat"] is not None:
                 pitch, blk = gs["flat"]
@@ -278,12 +310,12 @@ class TrainMixin:
                co_add=0, co_count=64, ci_count=64):
         lib = self.lib
         n = lib.mcedm_wgrad_ctas(B, H, W)
-        partial = self._t(tw, "wgpart", (192 * 9 * 4096,), torch.float32)      # >= mcedm_wgrad_ctas() CTAs
-        assert n <= 192
+        partial = self._t(tw, ("wgpart", self._job_id()), (n * taps * 4096,), torch.float32)
         L.check(lib.mcedm_conv_wgrad(L.ptr(dy), 1 if dy_flat else 0, dy_ctot, dy_coff, L.ptr(a), 1 if a_flat else 0, 64,
                                      0, B, H, W, taps, L.ptr(partial), st), "conv_wgrad")
-        L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), cin_total, ci_off, co_mul, co_add, co_count,
-                                       ci_count, 0, st), "wgrad_reduce")
+        self._wjobs.append((partial.data_ptr(), dw.data_ptr(), n, taps, cin_total, ci_off, co_mul, co_add, co_count,
+                            ci_count))
+        self._job_refs += [partial, dw]
 
     # ------------------------------------------------------------------ backward
     @torch.no_grad()
@@ -300,6 +332,7 @@ class TrainMixin:
         G = self.grad_of
         dF = dF.contiguous()
         pool = tw["pool"]
+        self._jid, self._rjobs, self._wjobs, self._job_refs, self._post_copies = 0, [], [], [], []
 
         # which (block, source) consumes each activation, in forward order
         consumers: Dict[str, list] = {}
@@ -327,7 +360,7 @@ class TrainMixin:
         self._wgrad(tw, dFp, False, 64, 0, a_out, False, B, H, W, 9, G(u.out_conv.weight), 64, 0, st,
                     co_count=u.out_channels)
         csn = 64
-        cs_tmp = self._t(tw, "cs_tmp", (csn, 64), torch.float32)
+        cs_tmp = self._t(tw, ("cs_tmp", self._job_id()), (csn, 64), torch.float32)
         L.check(lib.mcedm_colsum_bf16(L.ptr(dFp), B * H * W, 64, 0, L.ptr(cs_tmp), csn, st), "colsum")
         self._reduce_rows(cs_tmp, csn, 64, u.out_channels, 1, G(u.out_conv.bias), st)
         self._conv3x3([dFp], [], self.wd_out, None, B, H, W, 64, d_a, None, 0, None, st)
@@ -360,13 +393,14 @@ class TrainMixin:
                 L.check(lib.mcedm_attention_bwd(L.ptr(qkv), L.ptr(att), L.ptr(d_att), L.ptr(pool[(blk.name, "lse")]), B,
                                                 Lq, L.ptr(dvec), L.ptr(dq), L.ptr(dk), L.ptr(dv), st), "attention_bwd")
                 a2 = pool[(blk.name, "a2")]
-                qb = self._t(tw, "qkv_bias_tmp", (3, 64), torch.float32)
+                qb = self._t(tw, ("qkv_bias_tmp", blk.name), (3, 64), torch.float32)   # folded at the end of the backward
                 for j, dj in enumerate((dq, dk, dv)):
                     self._wgrad(tw, dj, False, 64, 0, a2, False, B, Hb, Wb, 1, G(m.qkv.weight), 64, 0, st, co_mul=3,
                                 co_add=j)
+                    cs_tmp = self._t(tw, ("cs_tmp", self._job_id()), (csn, 64), torch.float32)
                     L.check(lib.mcedm_colsum_bf16(L.ptr(dj), B * Lq, 64, 0, L.ptr(cs_tmp), csn, st), "colsum")
                     self._reduce_rows(cs_tmp, csn, 64, 64, 1, qb[j], st)
-                G(m.qkv.bias).view(64, 3).copy_(qb.t())                    # channel order (c*3 + {q,k,v})
+                self._post_copies.append((G(m.qkv.bias).view(64, 3), qb))    # channel order (c*3 + {q,k,v})
                 d_a2 = d_a.view(-1)[:B * Lq * 64].view(B, Hb, Wb, 64)
                 self._conv([dq, dk, dv], [(0, 0, 0), (1, 0, 0), (2, 0, 0)], blk.wdqkv, None, B, Hb, Wb, 64, d_a2, 0, None,
                            0, None, st)
@@ -451,4 +485,7 @@ class TrainMixin:
         torch._foreach_copy_([G(b.mod.affine.weight) for b in blocks], list(d_aff_w.unbind(0)))
         torch._foreach_copy_([G(b.mod.affine.bias) for b in blocks], list(d_aff_b.unbind(0)))
         assert not grads and not pending, (list(grads), list(pending))
+        self._flush_deferred(tw, st)
+        for dst, src in self._post_copies:
+            dst.copy_(src.t())
         return self._gflat
