@@ -130,15 +130,17 @@ MCEDM_API int mcedm_conv_flat(const void* src_flat, const void* w_packed, const 
  *   io_pitch/io_blk > 0 place out and res in the padded-flat layout (sources stay dense).
  * mcedm_gn_apply16: stand-alone apply for the places that still need a materialised operand (2x resampling in front
  *   of conv0, norm2 in front of the qkv projection): x16 raw 16-bit, dense (in_pitch = 0) or padded-flat; coef from
- *   mcedm_gn_coef; act / resample / out_pitch / out_blk as in mcedm_gn_apply.
+ *   mcedm_gn_coef; act / resample / out_pitch / out_blk as in mcedm_gn_apply.  out_pooled16 (resample = 2 only, may
+ *   be NULL): the 2x2 mean of the RAW input in out16's layout — the skip path of a down block (adm_blocks.py:149-151),
+ *   consumed by conv1 as a same-resolution residual instead of a 4-pixel gather in its epilogue.
  * mcedm_conv_in16: mcedm_conv_in writing a 16-bit NHWC tensor.
  */
 MCEDM_API int mcedm_gn_coef(const float* partial, int parts_per_img, const float* gamma, const float* beta,
                             const float* scale_shift, int emb_batch_stride, int emb_shift_offset, float eps, int B,
                             int Hin, int Win, float* coef_out, float* meanrstd_out, void* stream);
 MCEDM_API int mcedm_gn_apply16(const void* x16, int in_pitch, int in_blk, const float* coef, int act, int resample,
-                               int B, int Hin, int Win, int out_pitch, int out_blk, void* out16, int op_fmt,
-                               void* stream);
+                               int B, int Hin, int Win, int out_pitch, int out_blk, void* out16, void* out_pooled16,
+                               int op_fmt, void* stream);
 MCEDM_API int mcedm_conv_rows_fused(const void* const* halo_src, const float* const* halo_coef, int n_halo,
                                     const void* const* ctr_src, int n_ctr, const void* w_packed, const float* bias,
                                     int B, int H, int N, int n_off, int n_total, void* out, int out_16,

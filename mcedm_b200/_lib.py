@@ -26,7 +26,7 @@ _PROTOTYPES = {
     "mcedm_conv_igemm": [_vpp, _i, _ip, _ip, _ip, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp],
     "mcedm_conv_rows": [_vpp, _i, _vpp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp],
     "mcedm_gn_coef": [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp],
-    "mcedm_gn_apply16": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "mcedm_gn_apply16": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp],
     "mcedm_conv_rows_fused": [_vpp, _vpp, _i, _vpp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp, _i,
                               _vp],
     "mcedm_conv_head_fused": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp],

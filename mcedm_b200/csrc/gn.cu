@@ -316,6 +316,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
           const uint4 yo = pack8(lo, hi, p.fmt);
           const long long oi = gn_out_index(p, b, y, x, Ho, Wo);
           out[oi * 8 + c8] = yo;
+          if (p.out_raw) {
+            // 2x2 mean of the RAW input in the same layout: the residual of a down block's conv1 (Conv2d with
+            // kernel=0, down=True on the skip path, adm_blocks.py:149-151), read there like a same-resolution residual
+            const float4* r = xl[u];
+            const float4* s = xh[u];
+            const float4 rl = make_float4(0.25f * ((r[0].x + r[1].x) + (r[2].x + r[3].x)), 0.25f * ((r[0].y + r[1].y) + (r[2].y + r[3].y)),
+                                          0.25f * ((r[0].z + r[1].z) + (r[2].z + r[3].z)), 0.25f * ((r[0].w + r[1].w) + (r[2].w + r[3].w)));
+            const float4 rh = make_float4(0.25f * ((s[0].x + s[1].x) + (s[2].x + s[3].x)), 0.25f * ((s[0].y + s[1].y) + (s[2].y + s[3].y)),
+                                          0.25f * ((s[0].z + s[1].z) + (s[2].z + s[3].z)), 0.25f * ((s[0].w + s[1].w) + (s[2].w + s[3].w)));
+            reinterpret_cast<uint4*>(p.out_raw)[oi * 8 + c8] = pack8(rl, rh, p.fmt);
+          }
           if (p.out_lo) reinterpret_cast<uint4*>(p.out_lo)[oi * 8 + c8] = pack8_rem(lo, hi, yo);
         }
       }
@@ -433,16 +444,18 @@ extern "C" int mcedm_gn_coef(const float* partial, int parts_per_img, const floa
 }
 
 extern "C" int mcedm_gn_apply16(const void* x16, int in_pitch, int in_blk, const float* coef, int act, int resample,
-                                int B, int Hin, int Win, int out_pitch, int out_blk, void* out16, int op_fmt,
-                                void* stream) {
+                                int B, int Hin, int Win, int out_pitch, int out_blk, void* out16, void* out_pooled16,
+                                int op_fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 128 == 0, "gn_apply16: Hin*Win=%d must be a multiple of 128", Hin * Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply16: resample=%d", resample);
   MCEDM_REQUIRE(resample != 2 || (Hin % 2 == 0 && Win % 2 == 0), "gn_apply16: 2x2 mean needs even H, W");
   MCEDM_REQUIRE(coef != nullptr, "gn_apply16: coefficients (mcedm_gn_coef) are required");
+  MCEDM_REQUIRE(out_pooled16 == nullptr || resample == 2, "gn_apply16: the pooled raw copy needs resample = 2");
   GnApplyParams p;
   memset(&p, 0, sizeof(p));
   p.x = reinterpret_cast<const float*>(x16);
+  p.out_raw = out_pooled16;
   p.x16 = 1;
   p.in_pitch = in_pitch;
   p.in_blk = in_blk;

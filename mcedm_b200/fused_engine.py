@@ -80,7 +80,7 @@ class FusedMixin:
                                        B, act.H, act.W, L.ptr(coef), None, st), "gn_coef")
         return coef
 
-    def _fapply16(self, x: Act, coef, act_fn, resample, B, out: Act, st, dense_out=None):
+    def _fapply16(self, x: Act, coef, act_fn, resample, B, out: Act, st, dense_out=None, pooled: Optional[Act] = None):
         ip, ib = x.flat if x.flat is not None else (0, 0)
         if dense_out is not None:
             op, ob, o = 0, 0, dense_out
@@ -88,7 +88,7 @@ class FusedMixin:
             op, ob = out.flat if out.flat is not None else (0, 0)
             o = out.t
         L.check(self.lib.mcedm_gn_apply16(L.ptr(x.t), ip, ib, L.ptr(coef), act_fn, resample, B, x.H, x.W, op, ob, L.ptr(o),
-                                          self._fmt, st), "gn_apply16")
+                                          L.ptr(pooled.t) if pooled is not None else None, self._fmt, st), "gn_apply16")
 
     def _fconv(self, srcs: List[Act], coefs, w, bias, B, out: Act, res, res_mode, st, ctr: Optional[List[Act]] = None,
                 stats=True, ws=None, name=""):
@@ -160,13 +160,21 @@ class FusedMixin:
             H, W, rs, res_mode = x.H, x.W, 0, 1
         eps = blk.mod.norm0.eps
         n = blk.name
+        x_res = x                                                     # residual source of conv1 (identity skip)
         coef0 = [self._fcoef(ws, f"{n}.0.{i}", a, blk.g0[64 * i:64 * (i + 1)], blk.be0[64 * i:64 * (i + 1)], None, 0, eps,
                             B, st) for i, a in enumerate(inputs)]
         h = self._fact(ws, f"h.{H}", B, H, W, dev)
         if rs:
             # resampling conv0 (adm_blocks.py:73-77): materialise silu(norm0(x)) at the new resolution, conv it as is
             op = self._fact(ws, f"op.{H}", B, H, W, dev, stats=False)
-            self._fapply16(x, coef0[0], 1, rs, B, op, st)
+            pooled = None
+            if rs == 2 and not blk.skip_conv:
+                # the skip path of a down block is the 2x2 mean of the raw input: emitted by the same pass (one more
+                # 16-bit store per output pixel) and read by conv1 as a same-resolution residual; gathering the four
+                # source pixels in conv1's epilogue instead cost 240 us per launch at 64x64 (B = 128)
+                pooled = self._fact(ws, f"pool.{H}", B, H, W, dev, stats=False)
+                x_res, res_mode = pooled, 1
+            self._fapply16(x, coef0[0], 1, rs, B, op, st, pooled=pooled)
             self._fconv([op], None, blk.w0, blk.b0, B, h, None, 0, st, ws=ws)
         else:
             self._fconv(inputs, coef0, blk.w0, blk.b0, B, h, None, 0, st, ws=ws)
@@ -176,7 +184,7 @@ class FusedMixin:
         if blk.skip_conv:
             self._fconv([h], [coef1], blk.w1, blk.b1, B, out, None, 0, st, ctr=inputs, ws=ws)
         else:
-            self._fconv([h], [coef1], blk.w1, blk.b1, B, out, x, res_mode, st, ws=ws)
+            self._fconv([h], [coef1], blk.w1, blk.b1, B, out, x_res, res_mode, st, ws=ws)
         if blk.attn:
             coef2 = self._fcoef(ws, f"{n}.2", out, blk.g2, blk.be2, None, 0, eps, B, st)
             a2 = self._fbuf(ws, "att.in", (B, H, W, 64), self._dt16(), dev)

@@ -212,7 +212,8 @@ def test_gn_coef_and_apply16_match_group_norm(L, dev, B, H, W, rs, act, in_flat,
     Ho, Wo = {0: (H, W), 1: (2 * H, 2 * W), 2: (H // 2, W // 2)}[rs]
     op, ob = _geom(L, Ho, Wo) if out_flat else (0, 0)
     out = torch.zeros(B * ob, 64, device=dev, dtype=dt) if out_flat else torch.empty(B, Ho, Wo, 64, device=dev, dtype=dt)
-    L.check(lib.mcedm_gn_apply16(L.ptr(xin), ip, ib, L.ptr(coef), act, rs, B, H, W, op, ob, L.ptr(out), fmt,
+    pooled = torch.zeros_like(out) if rs == 2 else None
+    L.check(lib.mcedm_gn_apply16(L.ptr(xin), ip, ib, L.ptr(coef), act, rs, B, H, W, op, ob, L.ptr(out), L.ptr(pooled), fmt,
                                  L.stream_ptr()), "gn_apply16")
     L.check_watchdog()
     xn = F.group_norm(x.double().permute(0, 3, 1, 2), 16, gamma.double(), beta.double(), 1e-5)
@@ -226,6 +227,10 @@ def test_gn_coef_and_apply16_match_group_norm(L, dev, B, H, W, rs, act, in_flat,
     ref = xn.permute(0, 2, 3, 1)
     got = _from_flat(out, B, Ho, Wo, op, ob) if out_flat else out
     assert rel_l2(got.double(), ref) < (6e-4 if fmt else 4e-3)
+    if rs == 2:      # second output: 2x2 mean of the raw input (the skip path of a down block)
+        pr = F.avg_pool2d(x.double().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        gp = _from_flat(pooled, B, Ho, Wo, op, ob) if out_flat else pooled
+        assert rel_l2(gp.double(), pr) < (6e-4 if fmt else 4e-3)
 
 
 # --------------------------------------------------------------------------------------- conv_igemm16 / conv_in16
