@@ -338,6 +338,7 @@ def run_b200(args):
                              achieved=by_i / max(1e-9, t_i) / 1e6, peak=pk["hbm"], ms_per_eval=t_i,
                              launches_per_eval=len(cin))],
                     end_to_end_tflops=value * EVALS_PER_FIELD * FLOPS_PER_EVAL * (args.timesteps * 2 - 1) / 99 / 1e12 / world)
+        roof["other_kernels"] += pde_kernel_rooflines(pl, dev, pk)
     train = None
     if not args.no_train:
         train = measure_training(args, cfg, dev, rank, world, barrier)
@@ -374,6 +375,36 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pde_kernel_rooflines(pl, dev, pk, B=256, n=20):
+    """Achieved HBM GB/s of the PDE-residual kernels (K6) on a sampled batch in the sampler's own layout (float64 NCHW
+    state): algorithmic bytes = 2 planes x 8 B read per cell (+ 8 B written per cell for the gradient), CUDA events
+    around `n` launches on the launching stream; the 268 MB batch exceeds nothing but is streamed once per launch."""
+    import torch
+
+    x = torch.randn(B, 2, 128, 128, device=dev, dtype=torch.float64)
+    f = pl.pde_loss
+    nh, nu = pl.normalizer_input, pl.normalizer_target
+    out = []
+    for name, fn, byts in (
+            ("swe_fv_loss_kernel (FORCE finite-volume residual + sum, fp64 NCHW state in)",
+             lambda: f.residual(x[:, 0], x[:, 1], nh, nu), B * 128 * 128 * 16.0),
+            ("swe_fv_grad_kernel (analytic residual gradient, one image row per CTA)",
+             lambda: f.gradient(x[:, 0], x[:, 1], nh, nu, mode=0), B * 128 * 128 * 24.0)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out.append(dict(kernel=name, bound="hbm", unit="GB/s", achieved=byts / ms / 1e6, peak=pk["hbm"], ms_per_launch=ms,
+                        batch=B))
+    return out
 
 
 def measure_training(args, cfg, dev, rank, world, barrier):

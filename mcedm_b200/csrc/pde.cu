@@ -78,49 +78,89 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return s;
 }
 
+// typed load of one plane element (compile-time dtype / normalisation: no per-load branches)
+template <bool F64, bool APPLY>
+__device__ __forceinline__ float load_row(const void* row, long long off, float div, float sub) {
+  const float v = F64 ? (float)reinterpret_cast<const double*>(row)[off] : reinterpret_cast<const float*>(row)[off];
+  return APPLY ? __fadd_rn(__fmul_rn(v, div), sub) : v;
+}
+
 // loss[b,t,x,:] = (with_ic[b,t,x,:] - gt[b,t,x,:])^2 / scale ; with_ic[t] = step(pred[t-1]) (t>0), pred[0] (t=0)
+// One CTA walks `rows_per_cta` consecutive (b,t) rows; thread x owns cell x.  The cell a thread loads for the
+// comparison at row t is the centre cell of the step that feeds row t+1, its two neighbours come from the adjacent
+// lanes (warp-edge lanes load them), so every plane element is fetched from memory once (+1/16 at warp edges).
+template <bool HF64, bool UF64, bool APPLY>
 __global__ void __launch_bounds__(1024) swe_fv_loss_kernel(Plane ph, Plane pu, const float* __restrict__ gt, int T, int X,
-                                                           SweConst k, float sc_h, float sc_u,
-                                                           float* __restrict__ loss, double* __restrict__ row_sums) {
+                                                           long long n_rows, int rows_per_cta, SweConst k, float sc_h,
+                                                           float sc_u, float* __restrict__ loss,
+                                                           double* __restrict__ cta_sums) {
   __shared__ double sh[32];
-  const long long b = blockIdx.x / T;
-  const int t = blockIdx.x - (int)b * T;
-  const int x = threadIdx.x;
+  const int x = threadIdx.x, lane = threadIdx.x & 31;
+  const bool act = x < X;
+  const int xc = act ? x : X - 1;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, n_rows);
+  const size_t hsz = HF64 ? 8 : 4, usz = UF64 ? 8 : 4;
+  float ch = 0.f, cu = 0.f;   // cell x of the previous row (un-normalised); valid when have_prev
+  bool have_prev = false;
   double mine = 0.0;
-  if (x < X) {
+  for (long long r = r0; r < r1; ++r) {
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    const char* hrow = reinterpret_cast<const char*>(ph.p) + (size_t)(b * ph.sb + (long long)t * ph.st) * hsz;
+    const char* urow = reinterpret_cast<const char*>(pu.p) + (size_t)(b * pu.sb + (long long)t * pu.st) * usz;
+    // this row's own cell: the comparison target when gt == NULL, and the centre cell of the next row's step
+    const float oh = load_row<HF64, APPLY>(hrow, (long long)xc * ph.sx, ph.div, ph.sub);
+    const float ou = load_row<UF64, APPLY>(urow, (long long)xc * pu.sx, pu.div, pu.sub);
     float vh, vu;
     if (t == 0) {
-      vh = load_plane(ph, b, 0, x);
-      vu = load_plane(pu, b, 0, x);
+      vh = oh;
+      vu = ou;
     } else {
+      if (!have_prev) {   // first row of this CTA: fetch the centre cell of row t-1
+        ch = load_row<HF64, APPLY>(hrow - (size_t)ph.st * hsz, (long long)xc * ph.sx, ph.div, ph.sub);
+        cu = load_row<UF64, APPLY>(urow - (size_t)pu.st * usz, (long long)xc * pu.sx, pu.div, pu.sub);
+      }
       float h[3], u[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int xi = min(max(x - 1 + i, 0), X - 1);
-        h[i] = load_plane(ph, b, t - 1, xi);
-        u[i] = load_plane(pu, b, t - 1, xi);
+      h[1] = ch;
+      u[1] = cu;
+      h[0] = __shfl_up_sync(0xffffffffu, ch, 1);
+      u[0] = __shfl_up_sync(0xffffffffu, cu, 1);
+      h[2] = __shfl_down_sync(0xffffffffu, ch, 1);
+      u[2] = __shfl_down_sync(0xffffffffu, cu, 1);
+      if (lane == 0) {
+        const int xm = max(xc - 1, 0);
+        h[0] = load_row<HF64, APPLY>(hrow - (size_t)ph.st * hsz, (long long)xm * ph.sx, ph.div, ph.sub);
+        u[0] = load_row<UF64, APPLY>(urow - (size_t)pu.st * usz, (long long)xm * pu.sx, pu.div, pu.sub);
+      }
+      if (lane == 31 || x >= X - 1) {
+        const int xp = min(xc + 1, X - 1);
+        h[2] = load_row<HF64, APPLY>(hrow - (size_t)ph.st * hsz, (long long)xp * ph.sx, ph.div, ph.sub);
+        u[2] = load_row<UF64, APPLY>(urow - (size_t)pu.st * usz, (long long)xp * pu.sx, pu.div, pu.sub);
       }
       swe_step_cell(h, u, k, vh, vu);
-      if (vh != vh) vh = 0.f;  // pred_next_with_ic[isnan] = 0   (pde_loss.py:211)
-      if (vu != vu) vu = 0.f;
     }
-    float gh, gu;
-    const long long o = ((b * T + t) * (long long)X + x) * 2;
-    if (gt) {
-      const float2 g = *reinterpret_cast<const float2*>(gt + o);
-      gh = g.x;
-      gu = g.y;
-    } else {
-      gh = load_plane(ph, b, t, x);
-      gu = load_plane(pu, b, t, x);
+    if (vh != vh) vh = 0.f;  // pred_next_with_ic[isnan] = 0   (pde_loss.py:211; the initial-condition row included)
+    if (vu != vu) vu = 0.f;
+    ch = oh;
+    cu = ou;
+    have_prev = t + 1 < T;   // the next row of this CTA belongs to the same sample
+    if (act) {
+      float gh = oh, gu = ou;
+      const long long o = (r * (long long)X + x) * 2;
+      if (gt) {
+        const float2 g = *reinterpret_cast<const float2*>(gt + o);
+        gh = g.x;
+        gu = g.y;
+      }
+      const float dh = __fsub_rn(vh, gh), du = __fsub_rn(vu, gu);
+      const float lh = __fdiv_rn(__fmul_rn(dh, dh), sc_h), lu = __fdiv_rn(__fmul_rn(du, du), sc_u);
+      if (loss) *reinterpret_cast<float2*>(loss + o) = make_float2(lh, lu);
+      mine += (double)lh + (double)lu;
     }
-    const float dh = __fsub_rn(vh, gh), du = __fsub_rn(vu, gu);
-    const float lh = __fdiv_rn(__fmul_rn(dh, dh), sc_h), lu = __fdiv_rn(__fmul_rn(du, du), sc_u);
-    if (loss) *reinterpret_cast<float2*>(loss + o) = make_float2(lh, lu);
-    mine = (double)lh + (double)lu;
   }
   const double s = block_sum(mine, sh);
-  if (threadIdx.x == 0) row_sums[blockIdx.x] = s;
+  if (threadIdx.x == 0) cta_sums[blockIdx.x] = s;
 }
 
 // out[0] = sum of n partial sums, fixed order (one CTA)
@@ -319,10 +359,28 @@ extern "C" int mcedm_swe_fv_loss(const void* h, int h_f64, const long long* h_st
   const Plane ph = make_plane(h, h_f64, h_strides[0], h_strides[1], h_strides[2], apply_norm, h_div, h_sub);
   const Plane pu = make_plane(u, u_f64, u_strides[0], u_strides[1], u_strides[2], apply_norm, u_div, u_sub);
   const SweConst k{half_dt, dx, 1e-8f, 0.5f * g};
-  swe_fv_loss_kernel<<<B * T, round32(X), 0, st>>>(ph, pu, gt, T, X, k, h_div * h_div, u_div * u_div, loss, row_sums);
+  const long long n_rows = (long long)B * T;
+  const int R = T % 8 == 0 ? 8 : 1;                       // rows per CTA (never straddling two samples' step chains)
+  const unsigned grid = (unsigned)((n_rows + R - 1) / R);
+  const int threads = round32(X);
+  const float sh2 = h_div * h_div, su2 = u_div * u_div;
+#define MCEDM_SWE_LOSS(HF, UF, AP) \
+  swe_fv_loss_kernel<HF, UF, AP><<<grid, threads, 0, st>>>(ph, pu, gt, T, X, n_rows, R, k, sh2, su2, loss, row_sums)
+  const int sel = (h_f64 ? 4 : 0) | (u_f64 ? 2 : 0) | (apply_norm ? 1 : 0);
+  switch (sel) {
+    case 0: MCEDM_SWE_LOSS(false, false, false); break;
+    case 1: MCEDM_SWE_LOSS(false, false, true); break;
+    case 2: MCEDM_SWE_LOSS(false, true, false); break;
+    case 3: MCEDM_SWE_LOSS(false, true, true); break;
+    case 4: MCEDM_SWE_LOSS(true, false, false); break;
+    case 5: MCEDM_SWE_LOSS(true, false, true); break;
+    case 6: MCEDM_SWE_LOSS(true, true, false); break;
+    default: MCEDM_SWE_LOSS(true, true, true); break;
+  }
+#undef MCEDM_SWE_LOSS
   MCEDM_CUDA(cudaGetLastError());
   if (total) {
-    pde_sum_kernel<<<1, 1024, 0, st>>>(row_sums, B * T, total);
+    pde_sum_kernel<<<1, 1024, 0, st>>>(row_sums, (int)grid, total);
     MCEDM_CUDA(cudaGetLastError());
   }
   return 0;
