@@ -343,7 +343,9 @@ def run_b200(args):
     if not args.no_train:
         train = measure_training(args, cfg, dev, rank, world, barrier)
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    # the CPU baseline is a rank-0, N = 1 measurement: under torchrun the other ranks spin in the NCCL barrier on the
+    # same host cores (and OMP_NUM_THREADS is forced to 1), which turned a 3 s sample into a 280 s one at N = 8
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if train is not None:
             dt, threads = cpu_train_step(2)
             train["cpu_baseline"] = dict(value=2 / dt, unit="samples/s", cores=threads, kind="port",

@@ -130,9 +130,9 @@ MCEDM_API int mcedm_conv_flat(const void* src_flat, const void* w_packed, const 
  *   io_pitch/io_blk > 0 place out and res in the padded-flat layout (sources stay dense).
  * mcedm_gn_apply16: stand-alone apply for the places that still need a materialised operand (2x resampling in front
  *   of conv0, norm2 in front of the qkv projection): x16 raw 16-bit, dense (in_pitch = 0) or padded-flat; coef from
- *   mcedm_gn_coef; act / resample / out_pitch / out_blk as in mcedm_gn_apply.  out_pooled16 (resample = 2 only, may
- *   be NULL): the 2x2 mean of the RAW input in out16's layout — the skip path of a down block (adm_blocks.py:149-151),
- *   consumed by conv1 as a same-resolution residual instead of a 4-pixel gather in its epilogue.
+ *   mcedm_gn_coef; act / resample / out_pitch / out_blk as in mcedm_gn_apply.  out_pooled16 (resample != 0 only, may
+ *   be NULL): the RAW input resampled the same way (2x2 mean / nearest x2) in out16's layout — the skip path of a down /
+ *   up block (adm_blocks.py:149-151), consumed by conv1 as a same-resolution residual instead of a gather in its epilogue.
  * mcedm_conv_in16: mcedm_conv_in writing a 16-bit NHWC tensor.
  */
 MCEDM_API int mcedm_gn_coef(const float* partial, int parts_per_img, const float* gamma, const float* beta,

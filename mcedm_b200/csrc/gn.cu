@@ -283,6 +283,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
         ol[(o00 + rstride) * 8 + c8] = r;
         ol[(o00 + rstride + 1) * 8 + c8] = r;
       }
+      if (X16 && p.out_raw) {   // nearest-x2 copy of the RAW input: the skip path of an up block (adm_blocks.py:149-151)
+        uint4* orw = reinterpret_cast<uint4*>(p.out_raw);
+        const uint4 r = pack8(xl, xh, p.fmt);
+        orw[o00 * 8 + c8] = r;
+        orw[(o00 + 1) * 8 + c8] = r;
+        orw[(o00 + rstride) * 8 + c8] = r;
+        orw[(o00 + rstride + 1) * 8 + c8] = r;
+      }
     }
   } else {
     const int Wo = p.Win >> 1, Ho = p.Hin >> 1;
@@ -451,7 +459,7 @@ extern "C" int mcedm_gn_apply16(const void* x16, int in_pitch, int in_blk, const
   MCEDM_REQUIRE(resample >= 0 && resample <= 2, "gn_apply16: resample=%d", resample);
   MCEDM_REQUIRE(resample != 2 || (Hin % 2 == 0 && Win % 2 == 0), "gn_apply16: 2x2 mean needs even H, W");
   MCEDM_REQUIRE(coef != nullptr, "gn_apply16: coefficients (mcedm_gn_coef) are required");
-  MCEDM_REQUIRE(out_pooled16 == nullptr || resample == 2, "gn_apply16: the pooled raw copy needs resample = 2");
+  MCEDM_REQUIRE(out_pooled16 == nullptr || resample != 0, "gn_apply16: the raw resampled copy needs resample = 1 or 2");
   GnApplyParams p;
   memset(&p, 0, sizeof(p));
   p.x = reinterpret_cast<const float*>(x16);

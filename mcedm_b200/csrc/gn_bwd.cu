@@ -49,9 +49,13 @@ struct GnBwdParams {
   float* colsum_partial;     // nullptr or [B*ctas_per_img][64]
 };
 
+// d silu(u)/du = s*(1 + u*(1 - s)), s = sigmoid(u) = 0.5 + 0.5*tanh(u/2): ONE special-function op (MUFU.TANH, 2^-11)
+// instead of ex2 + an IEEE reciprocal; the two GroupNorm backward passes were bound by that instruction stream.
 __device__ __forceinline__ float silu_grad(float u) {
-  const float sg = 1.0f / (1.0f + __expf(-u));
-  return sg * (1.0f + u * (1.0f - sg));
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+  const float sg = fmaf(0.5f, t, 0.5f);
+  return sg * fmaf(u, 1.0f - sg, 1.0f);
 }
 
 // mean / rstd of (b, g) as saved by the forward gn_apply (meanrstd[b][16][2])

@@ -171,7 +171,9 @@ class FusedMixin:
             if rs == 2 and not blk.skip_conv:
                 # the skip path of a down block is the 2x2 mean of the raw input: emitted by the same pass (one more
                 # 16-bit store per output pixel) and read by conv1 as a same-resolution residual; gathering the four
-                # source pixels in conv1's epilogue instead cost 240 us per launch at 64x64 (B = 128)
+                # source pixels in conv1's epilogue instead cost 240 us per launch at 64x64 (B = 128).  (The same trick
+                # for the nearest-x2 skip of the up blocks — the kernel can emit that copy too — measured neutral:
+                # the gather reads an L2-resident quarter-size tensor, the copy costs a full-size store.)
                 pooled = self._fact(ws, f"pool.{H}", B, H, W, dev, stats=False)
                 x_res, res_mode = pooled, 1
             self._fapply16(x, coef0[0], 1, rs, B, op, st, pooled=pooled)

@@ -212,7 +212,7 @@ def test_gn_coef_and_apply16_match_group_norm(L, dev, B, H, W, rs, act, in_flat,
     Ho, Wo = {0: (H, W), 1: (2 * H, 2 * W), 2: (H // 2, W // 2)}[rs]
     op, ob = _geom(L, Ho, Wo) if out_flat else (0, 0)
     out = torch.zeros(B * ob, 64, device=dev, dtype=dt) if out_flat else torch.empty(B, Ho, Wo, 64, device=dev, dtype=dt)
-    pooled = torch.zeros_like(out) if rs == 2 else None
+    pooled = torch.zeros_like(out) if rs else None
     L.check(lib.mcedm_gn_apply16(L.ptr(xin), ip, ib, L.ptr(coef), act, rs, B, H, W, op, ob, L.ptr(out), L.ptr(pooled), fmt,
                                  L.stream_ptr()), "gn_apply16")
     L.check_watchdog()
@@ -227,8 +227,9 @@ def test_gn_coef_and_apply16_match_group_norm(L, dev, B, H, W, rs, act, in_flat,
     ref = xn.permute(0, 2, 3, 1)
     got = _from_flat(out, B, Ho, Wo, op, ob) if out_flat else out
     assert rel_l2(got.double(), ref) < (6e-4 if fmt else 4e-3)
-    if rs == 2:      # second output: 2x2 mean of the raw input (the skip path of a down block)
-        pr = F.avg_pool2d(x.double().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    if rs:           # second output: the raw input resampled the same way (the skip path of a down / up block)
+        xr = x.double().permute(0, 3, 1, 2)
+        pr = (F.avg_pool2d(xr, 2) if rs == 2 else xr.repeat_interleave(2, 2).repeat_interleave(2, 3)).permute(0, 2, 3, 1)
         gp = _from_flat(pooled, B, Ho, Wo, op, ob) if out_flat else pooled
         assert rel_l2(gp.double(), pr) < (6e-4 if fmt else 4e-3)
 
