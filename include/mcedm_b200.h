@@ -220,11 +220,12 @@ MCEDM_API int mcedm_gn_apply(const float* x, const float* partial, const float* 
                              int op_fmt, void* stream);
 
 /*
- * Backward of mcedm_gn_apply (training; autograd of adm_blocks.py:95, :161, :166).  Three launches: per-CTA partial
- * sums of (du, du*xh) per channel, a per-sample finalize, and the element pass.
+ * Backward of mcedm_gn_apply (training; autograd of adm_blocks.py:95, :161, :166).  Two launches: per-CTA partial
+ * sums of (du, du*xh) per channel, and the element pass, whose CTAs first fold the partials of their sample in a fixed
+ * order (CTA 0 of each sample also writes dgb_partial / d_scale_shift).
  *   dy            fp32 NHWC gradient w.r.t. the operand gn_apply wrote (at the conv resolution)
  *   x, meanrstd   saved forward input and its (mean, rstd) records
- *   red_partial   scratch fp32 [B][mcedm_gn_bwd_ctas_per_img(Hin,Win,B)][64][2];  coef scratch fp32 [B][64][4]
+ *   red_partial   scratch fp32 [B][mcedm_gn_bwd_ctas_per_img(Hin,Win,B)][64][2];  coef: unused (NULL allowed)
  *   dgb_partial   out fp32 [B][64][2]: per-sample (d gamma, d beta) contributions (sum over b = the gradient)
  *   d_scale_shift NULL or out: d scale at [b*dss_batch_stride + c], d shift at [... + emb_shift_offset + c]
  *   add0/add1     NULL or fp32 tensors added to dx (residual-path gradients); add0_mode 0 same resolution,

@@ -81,6 +81,7 @@ struct GnApplyParams {
   void* out_raw_lo;          // likewise for the raw copy
   int x16;                   // x is a 16-bit NHWC tensor in the operand format (inference: raw activations are 16-bit)
   int in_pitch, in_blk;      // x16 only: x itself is in the padded flat layout (0: dense)
+  int fast_act;              // fp32 input: SiLU through MUFU.TANH as well (training forward: the operand is bf16 anyway)
 };
 
 // pixel index of output (b, y, x) in the dense NHWC layout or in the padded flat layout
@@ -91,13 +92,13 @@ __device__ __forceinline__ long long gn_out_index(const GnApplyParams& p, int b,
 
 // FAST (the 16-bit inference instantiation): SiLU through one MUFU.TANH instead of ex2 + rcp, as in the fused convs
 template <bool FAST = false>
-__device__ __forceinline__ float4 gn_act4(float4 v, const float4 a, const float4 b, int act) {
+__device__ __forceinline__ float4 gn_act4(float4 v, const float4 a, const float4 b, int act, bool fast = false) {
   v.x = fmaf(v.x, a.x, b.x);
   v.y = fmaf(v.y, a.y, b.y);
   v.z = fmaf(v.z, a.z, b.z);
   v.w = fmaf(v.w, a.w, b.w);
   if (act) {
-    if constexpr (FAST) {
+    if (FAST || fast) {
       v.x = silu_from_half_arg(0.5f * v.x);
       v.y = silu_from_half_arg(0.5f * v.y);
       v.z = silu_from_half_arg(0.5f * v.z);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
             const int y = ip / p.Win;
             opix = gn_out_index(p, b, y, ip - y * p.Win, p.Hin, p.Win);
           }
-          const float4 yl = gn_act4<X16>(lo[k], a_lo, b_lo, p.act), yh = gn_act4<X16>(hi[k], a_hi, b_hi, p.act);
+          const float4 yl = gn_act4<X16>(lo[k], a_lo, b_lo, p.act, p.fast_act), yh = gn_act4<X16>(hi[k], a_hi, b_hi, p.act, p.fast_act);
           const uint4 yo = pack8(yl, yh, p.fmt);
           out[opix * 8 + c8] = yo;
           if (p.out_lo) reinterpret_cast<uint4*>(p.out_lo)[opix * 8 + c8] = pack8_rem(yl, yh, yo);
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
       const int y = ip / p.Win, x = ip - y * p.Win;
       float4 xl, xh;
       gn_load8<X16>(p, gn_in_index(p, b, ip), c8, xl, xh);
-      const float4 yl = gn_act4<X16>(xl, a_lo, b_lo, p.act), yh = gn_act4<X16>(xh, a_hi, b_hi, p.act);
+      const float4 yl = gn_act4<X16>(xl, a_lo, b_lo, p.act, p.fast_act), yh = gn_act4<X16>(xh, a_hi, b_hi, p.act, p.fast_act);
       const uint4 v = pack8(yl, yh, p.fmt);
       const long long o00 = gn_out_index(p, b, 2 * y, 2 * x, Ho, Wo);
       out[o00 * 8 + c8] = v;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
           float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float4 l = gn_act4<X16>(xl[u][k], a_lo, b_lo, p.act), h = gn_act4<X16>(xh[u][k], a_hi, b_hi, p.act);
+            const float4 l = gn_act4<X16>(xl[u][k], a_lo, b_lo, p.act, p.fast_act), h = gn_act4<X16>(xh[u][k], a_hi, b_hi, p.act, p.fast_act);
             lo.x += l.x; lo.y += l.y; lo.z += l.z; lo.w += l.w;
             hi.x += h.x; hi.y += h.y; hi.z += h.z; hi.w += h.w;
           }
@@ -388,6 +389,10 @@ static int gn_apply_impl(const float* x, const float* partial, const float* gamm
   p.in_blk = 0;
   p.out_lo = out_lo;
   p.out_raw_lo = out_raw_lo;
+  // training forward (it saves mean / rstd for the backward): the operand is rounded to bf16 (2^-9) anyway, so SiLU may
+  // take the one-MUFU tanh form (2^-11) of the inference kernels; the fp32-accuracy and fallback inference plans keep
+  // the exact form
+  p.fast_act = (meanrstd_out != nullptr && out_lo == nullptr) ? 1 : 0;
   MCEDM_REQUIRE(coef_scratch != nullptr, "gn_apply: coef_scratch (fp32 [B][128]) is required");
   const int work = (resample == 2) ? (Hin * Win / 4) : (Hin * Win);  // pixels iterated per image
   // streaming CTAs of <= 512 pixels (~200 KB of traffic each); keep >= ~4 CTAs per SM when the batch allows it

@@ -47,7 +47,22 @@ struct GnBwdParams {
   int out_pitch, out_blk;    // padded-flat layout parameters of dx_bf16 (0 = dense)
   void* dx_bf16_dense;       // nullptr or a second, always dense NHWC bf16 copy (operand of the 1x1 convolutions)
   float* colsum_partial;     // nullptr or [B*ctas_per_img][64]
+  int w_shift;               // log2(Win) when Win is a power of two (every level of the U-Net), else -1
+  float* dgb_partial;        // [B][64][2] (d gamma, d beta) contributions of sample b (written by CTA 0 of the sample)
+  float* d_scale_shift;      // nullptr or d(scale | shift) of sample b
+  int dss_batch_stride;
 };
+
+// (y, x) of input pixel ip: a shift when the width is a power of two (the integer division was ~1/4 of the loop body)
+__device__ __forceinline__ void gn_row_col(const GnBwdParams& p, int ip, int& y, int& x) {
+  if (p.w_shift >= 0) {
+    y = ip >> p.w_shift;
+    x = ip & (p.Win - 1);
+  } else {
+    y = ip / p.Win;
+    x = ip - y * p.Win;
+  }
+}
 
 // d silu(u)/du = s*(1 + u*(1 - s)), s = sigmoid(u) = 0.5 + 0.5*tanh(u/2): ONE special-function op (MUFU.TANH, 2^-11)
 // instead of ex2 + an IEEE reciprocal; the two GroupNorm backward passes were bound by that instruction stream.
@@ -121,7 +136,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p)
   const int pix0 = blockIdx.x * p.pix_per_cta;
   for (int i = pl; i < p.pix_per_cta; i += 16) {
     const int ip = pix0 + i;
-    const int y = ip / p.Win, x = ip - y * p.Win;
+    int y, x;
+    gn_row_col(p, ip, y, x);
     const float4 xv = *reinterpret_cast<const float4*>(p.x + (((long long)b * p.Hin + y) * p.Win + x) * 64 + c);
     float4 d = gather_dy(p, b, y, x, c);
     if (p.act) {
@@ -150,61 +166,6 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p)
   }
 }
 
-// grid = B, block = 64 (one thread per channel).  Folds the pass-1 partials, writes the pass-2 coefficients and
-// the parameter-gradient contributions of sample b: (d gamma, d beta) rows ([B][64][2], summed over b by
-// mcedm_reduce_rows) and d(scale | shift).
-__global__ void __launch_bounds__(64)
-gn_bwd_finalize_kernel(const float* __restrict__ red_partial, int ctas_per_img, const float* __restrict__ meanrstd,
-                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                       const float* __restrict__ scale_shift, int emb_batch_stride, int emb_shift_offset, int Hin,
-                       int Win, float* __restrict__ coef, float* __restrict__ dgb_partial,
-                       float* __restrict__ d_scale_shift, int dss_batch_stride) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  __shared__ float sG1[64], sG2[64];
-  const float rstd = meanrstd[((long long)b * 16 + (c >> 2)) * 2 + 1];
-  const float cnt = 4.0f * (float)Hin * (float)Win;
-  double a1 = 0.0, a2 = 0.0;
-  const float2* rp = reinterpret_cast<const float2*>(red_partial + ((long long)b * ctas_per_img * 64 + c) * 2);
-  int t = 0;
-  for (; t + 8 <= ctas_per_img; t += 8) {
-    float2 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = rp[(t + k) * 64];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      a1 += (double)v[k].x;
-      a2 += (double)v[k].y;
-    }
-  }
-  for (; t < ctas_per_img; ++t) {
-    const float2 v = rp[t * 64];
-    a1 += (double)v.x;
-    a2 += (double)v.y;
-  }
-  float sc = 1.0f;
-  if (scale_shift) sc = 1.0f + scale_shift[(long long)b * emb_batch_stride + c];
-  const float g = gamma[c], be = beta[c];
-  const float A1 = (float)a1, A2 = (float)a2;
-  const float k1 = g * sc;                      // d xh = k1 * du
-  sG1[c] = k1 * A1;
-  sG2[c] = k1 * A2;
-  __syncthreads();
-  const int g0 = c & ~3;
-  const float m1 = ((sG1[g0] + sG1[g0 + 1]) + (sG1[g0 + 2] + sG1[g0 + 3])) / cnt;
-  const float m2 = ((sG2[g0] + sG2[g0 + 1]) + (sG2[g0 + 2] + sG2[g0 + 3])) / cnt;
-  float* co = coef + ((long long)b * 64 + c) * 4;
-  co[0] = rstd * k1;
-  co[1] = rstd * m1;
-  co[2] = rstd * m2;
-  co[3] = 0.f;
-  dgb_partial[((long long)b * 64 + c) * 2 + 0] = sc * A2;     // d gamma contribution of sample b
-  dgb_partial[((long long)b * 64 + c) * 2 + 1] = sc * A1;     // d beta
-  if (d_scale_shift) {
-    d_scale_shift[(long long)b * dss_batch_stride + c] = g * A2 + be * A1;                  // d scale
-    d_scale_shift[(long long)b * dss_batch_stride + emb_shift_offset + c] = A1;             // d shift
-  }
-}
-
 __device__ __forceinline__ float4 gather_add(const float* add, int mode, int b, int y, int x, int H, int W, int c) {
   if (mode == 0) {
     return *reinterpret_cast<const float4*>(add + (((long long)b * H + y) * W + x) * 64 + c);
@@ -228,6 +189,7 @@ __device__ __forceinline__ float4 gather_add(const float* add, int mode, int b, 
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) {
   __shared__ float sMean[16], sRstd[16];
   __shared__ float sA[64], sB[64];
+  __shared__ float sG1[64], sG2[64], sK[64][3];
   __shared__ float red[16][64];
   const int b = blockIdx.y;
   gn_load_stats(p, b, sMean, sRstd);
@@ -251,13 +213,64 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdParams p) 
   const float4 a4 = *reinterpret_cast<const float4*>(&sA[c]);
   const float4 b4 = *reinterpret_cast<const float4*>(&sB[c]);
   const float rs = sRstd[cq], mr = sMean[cq] * sRstd[cq];
-  const float4* cf = reinterpret_cast<const float4*>(p.coef + ((long long)b * 64 + c) * 4);
-  const float4 k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];   // (k1, rm1, rm2, -) per channel
+  // ---- fold of the pass-1 partials (formerly a separate B-CTA launch between the two passes: 41 latency-bound
+  // launches per training step).  Every CTA of sample b folds the same records in the same order; CTA 0 of the sample
+  // also emits the parameter-gradient rows.
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x;
+    double a1 = 0.0, a2 = 0.0;
+    const float2* rp = reinterpret_cast<const float2*>(p.red_partial + ((long long)b * p.ctas_per_img * 64 + ch) * 2);
+    int t = 0;
+    for (; t + 8 <= p.ctas_per_img; t += 8) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = rp[(t + k) * 64];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a1 += (double)v[k].x;
+        a2 += (double)v[k].y;
+      }
+    }
+    for (; t < p.ctas_per_img; ++t) {
+      const float2 v = rp[t * 64];
+      a1 += (double)v.x;
+      a2 += (double)v.y;
+    }
+    float sc = 1.0f;
+    if (p.scale_shift) sc = 1.0f + p.scale_shift[(long long)b * p.emb_batch_stride + ch];
+    const float g = p.gamma[ch], be = p.beta[ch];
+    const float A1 = (float)a1, A2 = (float)a2;
+    const float kk = g * sc;                      // d xh = kk * du
+    sG1[ch] = kk * A1;
+    sG2[ch] = kk * A2;
+    sK[ch][0] = sRstd[ch >> 2] * kk;
+    if (blockIdx.x == 0) {
+      p.dgb_partial[((long long)b * 64 + ch) * 2 + 0] = sc * A2;     // d gamma contribution of sample b
+      p.dgb_partial[((long long)b * 64 + ch) * 2 + 1] = sc * A1;     // d beta
+      if (p.d_scale_shift) {
+        p.d_scale_shift[(long long)b * p.dss_batch_stride + ch] = g * A2 + be * A1;                  // d scale
+        p.d_scale_shift[(long long)b * p.dss_batch_stride + p.emb_shift_offset + ch] = A1;           // d shift
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x, g0 = ch & ~3;
+    const float cnt = 4.0f * (float)p.Hin * (float)p.Win;
+    const float m1 = ((sG1[g0] + sG1[g0 + 1]) + (sG1[g0 + 2] + sG1[g0 + 3])) / cnt;
+    const float m2 = ((sG2[g0] + sG2[g0 + 1]) + (sG2[g0 + 2] + sG2[g0 + 3])) / cnt;
+    sK[ch][1] = sRstd[ch >> 2] * m1;
+    sK[ch][2] = sRstd[ch >> 2] * m2;
+  }
+  __syncthreads();
+  const float4 k0 = make_float4(sK[c][0], sK[c][1], sK[c][2], 0.f), k1 = make_float4(sK[c + 1][0], sK[c + 1][1], sK[c + 1][2], 0.f);
+  const float4 k2 = make_float4(sK[c + 2][0], sK[c + 2][1], sK[c + 2][2], 0.f), k3 = make_float4(sK[c + 3][0], sK[c + 3][1], sK[c + 3][2], 0.f);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   const int pix0 = blockIdx.x * p.pix_per_cta;
   for (int i = pl; i < p.pix_per_cta; i += 16) {
     const int ip = pix0 + i;
-    const int y = ip / p.Win, x = ip - y * p.Win;
+    int y, x;
+    gn_row_col(p, ip, y, x);
     const long long pix = ((long long)b * p.Hin + y) * p.Win + x;
     const float4 xv = *reinterpret_cast<const float4*>(p.x + pix * 64 + c);
     float4 d = gather_dy(p, b, y, x, c);
@@ -420,21 +433,22 @@ extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrs
   p.eps = eps; p.act = act; p.resample = resample;
   p.B = B; p.Hin = Hin; p.Win = Win;
   const int work = Hin * Win;
+  p.w_shift = (Win & (Win - 1)) == 0 ? __builtin_ctz((unsigned)Win) : -1;
   p.pix_per_cta = pick_pix_per_cta(work, B);
   p.ctas_per_img = work / p.pix_per_cta;
   p.red_partial = red_partial;
-  p.coef = coef;
+  p.coef = coef;   // unused since the fold moved into the apply pass (kept in the ABI as caller-owned scratch)
   p.add0 = add0; p.add0_mode = add0_mode; p.add1 = add1;
   p.dx = dx; p.dx_bf16 = dx_bf16; p.out_pitch = out_pitch; p.out_blk = out_blk;
   p.dx_bf16_dense = dx_bf16_dense;
   p.colsum_partial = colsum_partial;
+  p.dgb_partial = dgb_partial;
+  p.d_scale_shift = d_scale_shift;
+  p.dss_batch_stride = dss_batch_stride;
+  MCEDM_REQUIRE(dgb_partial != nullptr, "gn_bwd: dgb_partial ([B][64][2]) is required");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.ctas_per_img, B);
   gn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p);
-  MCEDM_CUDA(cudaGetLastError());
-  gn_bwd_finalize_kernel<<<B, 64, 0, st>>>(red_partial, p.ctas_per_img, meanrstd, gamma, beta, scale_shift,
-                                            emb_batch_stride, emb_shift_offset, Hin, Win, coef, dgb_partial,
-                                            d_scale_shift, dss_batch_stride);
   MCEDM_CUDA(cudaGetLastError());
   gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(p);
   MCEDM_CUDA(cudaGetLastError());
