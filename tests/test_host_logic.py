@@ -150,3 +150,78 @@ def test_cond_edm_module_surface():
             raise AssertionError("DDIM samplers must raise")
         except NotImplementedError:
             pass
+
+
+def test_ddim_module_surface_and_vp_grid_scalars():
+    """PlDdim host mirror (config 4): state_dict surface, VP sigma grid, sigma snapping, alpha-bar look-ups and the fp32
+    preconditioning scalars against the oracle's restatement (which the reference fixture pins); against the live
+    reference module as well when /root/reference is mounted."""
+    import ref_harness_path  # noqa: F401  (adds tests/golden to sys.path)
+    import ref_harness as R
+    from mcedm_b200.ddim import PlDdim, get_beta_schedule
+
+    cfg = compose("config_adm_ddim_res32")
+    torch.manual_seed(1)
+    pl = PlDdim(copy.deepcopy(cfg.model.hparams))
+    sd = pl.state_dict()
+    assert "betas" in sd and "logvar" in sd and tuple(sd["betas"].shape) == (1000,)
+    assert tuple(sd["model.enc.128x128_conv.weight"].shape) == (64, 4, 3, 3)        # [x_self_cond | x]: 2 + 2 channels
+    assert pl.model.cat_channels == 2 and pl.model.cond_channels == 0 and pl.model.x_channels == 2
+    pl.set_test_sampler_params(cfg.diff_sampler)
+    grid = O.VpGrid()
+    assert torch.equal(pl.edm_steps, grid.edm_steps)
+    assert pl.sigma_min == grid.sigma_min and pl.sigma_max == grid.sigma_max
+    assert torch.equal(get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000), grid.betas)
+    t = pl._edm_grid(cfg.diff_sampler)
+    assert t.dtype == torch.float64 and t.shape == (51,) and float(t[-1]) == 0.0
+    for s in (80.0, 3.3, 0.011, 0.0):
+        sig = torch.tensor(s, dtype=torch.float64)
+        assert torch.equal(pl.round_sigma(sig), grid.round_sigma(sig))
+        assert torch.equal(pl.round_sigma(sig, return_index=True), grid.round_sigma(sig, return_index=True))
+        assert torch.equal(pl.compute_alpha(sig.long()), grid.compute_alpha(sig.long()))
+    for s in t[:5].tolist() + t[-4:-1].tolist():
+        c_out, c_in, c_noise = pl._vp_scalars(s)
+        sigma = torch.tensor(s, dtype=torch.float64).to(torch.float32).reshape(-1, 1, 1, 1)
+        assert c_out == float(-sigma) and c_in == float(1 / (sigma ** 2 + 1).sqrt())
+        assert c_noise == float(999 - grid.round_sigma(sigma, return_index=True).to(torch.float32))
+    hp = copy.deepcopy(cfg.model.hparams)
+    hp.name = "ddim"                                                   # the DDPM U-Net branch has no kernels
+    try:
+        PlDdim(hp)
+        raise AssertionError("PlDdim accepted a non-ADM network")
+    except NotImplementedError:
+        pass
+    if R.reference_available():
+        ref = R.import_reference()
+        torch.manual_seed(1)
+        rp = ref.ddim.PlDdim(copy.deepcopy(cfg.model.hparams))
+        rp.set_test_sampler_params(cfg.diff_sampler)
+        assert set(rp.state_dict()) == set(sd)
+        for k, v in rp.state_dict().items():
+            assert v.shape == sd[k].shape and torch.equal(v, sd[k]), k          # seeded init is bit-identical
+        assert torch.equal(rp.edm_steps, pl.edm_steps) and rp.sigma_max == pl.sigma_max
+
+
+def test_pde_loss_selection_and_cpu_inputs_raise():
+    from mcedm_b200 import _lib as L
+    from mcedm_b200.nn_misc import Normalizer
+    from mcedm_b200.pde_loss import DarcyLoss, SweFvLoss, get_pde_loss_function
+
+    f, fs = get_pde_loss_function("swe_per", False)
+    assert isinstance(f, SweFvLoss) and (f.Tn, f.x_min, f.x_max) == (0.128, -0.5, 0.5) and isinstance(fs, SweFvLoss)
+    f, _ = get_pde_loss_function("swe", False)
+    assert (f.Tn, f.x_min, f.x_max) == (1.28, -2.5, 2.5)
+    f, _ = get_pde_loss_function("anything-else", False)                # loss_helper.py:35-39 default branch
+    assert f.Tn == 1.28
+    d, _ = get_pde_loss_function("darcy", False)
+    assert isinstance(d, DarcyLoss)
+    half_dt, dx = get_pde_loss_function("swe_per", False)[0]._grid(128, 128)
+    assert dx == 2.0 ** -7 and half_dt == 0.5 * 0.128 / 128
+    n = Normalizer(torch.tensor(0.0), torch.tensor(1.0))
+    x = torch.zeros(1, 8, 8, 2)
+    for fn in (lambda: f(x, x, n, n), lambda: f(x, x, n, n, return_d=True), lambda: d(x, x, n, n)):
+        try:
+            fn()
+            raise AssertionError("CPU tensors were accepted")
+        except L.McedmError:
+            pass
