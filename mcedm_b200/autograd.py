@@ -43,7 +43,8 @@ class EdmLossFunction(torch.autograd.Function):
         n_cta = 16
         dF = torch.empty_like(F_x)
         part = torch.empty(B, n_cta, device=F_x.device, dtype=torch.float32)
-        L.check(lib.mcedm_edm_loss(L.ptr(F_x.contiguous()), L.ptr(x_noise), L.ptr(x), L.ptr(mask), L.ptr(c_skip),
+        F_x = F_x.contiguous()                       # a named tensor: L.ptr() only carries the address
+        L.check(lib.mcedm_edm_loss(L.ptr(F_x), L.ptr(x_noise), L.ptr(x), L.ptr(mask), L.ptr(c_skip),
                                    L.ptr(c_out), L.ptr(weight), B, chw, L.ptr(dF), None, 0, L.ptr(part), n_cta,
                                    L.stream_ptr()), "edm_loss")
         loss = torch.empty((), device=F_x.device, dtype=torch.float32)

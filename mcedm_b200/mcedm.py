@@ -267,7 +267,8 @@ class PlMcedm(LightningModule):
         w = weight.to(torch.float32).reshape(-1).contiguous()
         x = x.contiguous()
         x_noise, x_in = torch.empty_like(x), torch.empty_like(x)
-        L.check(lib.mcedm_edm_noise_in(L.ptr(x), L.ptr(noise.contiguous()), L.ptr(mask), L.ptr(s.contiguous()),
+        noise, s = noise.contiguous(), s.contiguous()   # named tensors: L.ptr() only carries the address
+        L.check(lib.mcedm_edm_noise_in(L.ptr(x), L.ptr(noise), L.ptr(mask), L.ptr(s),
                                        L.ptr(c_in), B, chw, L.ptr(x_noise), L.ptr(x_in), L.stream_ptr()), "edm_noise_in")
         F_x = self.model(x_in, c_noise, cond)
         return EdmLossFunction.apply(F_x, x_noise, x, mask, c_skip, c_out, w)

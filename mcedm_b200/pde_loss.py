@@ -42,16 +42,18 @@ _STAT_CACHE = {}
 
 
 def _norm_args(normalizer_h, normalizer_u):
-    """(h_div, h_sub, u_div, u_sub) as python floats; cached per buffer version so that the guided sampler does not
-    synchronise with the device at every network evaluation."""
+    """(h_div, h_sub, u_div, u_sub) as python floats.  Reading a CUDA scalar synchronises with the device, so the values
+    are cached per (buffer objects, their versions); the cache holds the buffers themselves, so an id can never be
+    re-used by another tensor while its entry is alive, and in-place updates (version bump) or `set_stats` (new
+    objects) miss."""
     ts = (normalizer_h.divide, normalizer_h.subtract, normalizer_u.divide, normalizer_u.subtract)
-    key = tuple((id(t), t._version, t.data_ptr()) for t in ts)
+    key = tuple((id(t), t._version) for t in ts)
     hit = _STAT_CACHE.get(key)
-    if hit is None:
+    if hit is None or any(a is not b for a, b in zip(hit[0], ts)):
         if len(_STAT_CACHE) > 64:
             _STAT_CACHE.clear()
-        hit = _STAT_CACHE[key] = tuple(_stat(t) for t in ts)
-    return hit
+        hit = _STAT_CACHE[key] = (ts, tuple(_stat(t) for t in ts))
+    return hit[1]
 
 
 class SweFvLoss(nn.Module):

@@ -52,3 +52,34 @@ n_eval = 2 * steps - 1
 print(f"B={B}: trajectory of {steps} steps {t_traj:.2f} ms; evaluation {t_eval:.3f} ms x {n_eval} = {t_eval * n_eval:.2f} ms; "
       f"outside the network: {(t_traj - t_eval * n_eval) / steps:.3f} ms per step "
       f"({100 * (t_traj - t_eval * n_eval) / t_traj:.1f} % of the trajectory)")
+
+# ---- components of one step outside the network, timed alone (20 launches each)
+from mcedm_b200 import _lib as L  # noqa: E402
+
+lib = L.lib()
+f64 = dict(device=dev, dtype=torch.float64)
+xa, xb, xc2, xd = (torch.randn(B, 2, 128, 128, **f64) for _ in range(4))
+Fb, xin = torch.randn(B, 2, 128, 128, device=dev), torch.empty(B, 2, 128, 128, device=dev)
+tot = xa.numel()
+st = L.stream_ptr()
+
+
+def timed(fn, n=20):
+    fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+parts = {
+    "randn fp64 (torch.randn_like, :608)": lambda: torch.randn_like(xa),
+    "edm_churn": lambda: L.check(lib.mcedm_edm_churn(L.ptr(xa), L.ptr(xb), L.ptr(mask), 1.0, 0.5, tot, L.ptr(xc2), L.ptr(xin), st)),
+    "edm_euler": lambda: L.check(lib.mcedm_edm_euler(L.ptr(xa), L.ptr(Fb), L.ptr(mask), 2.0, 1.5, 0.2, 0.9, 0.5, tot, L.ptr(xd), L.ptr(xc2), L.ptr(xin), None, st)),
+    "edm_correct": lambda: L.check(lib.mcedm_edm_correct(L.ptr(xa), L.ptr(xc2), L.ptr(Fb), L.ptr(xd), L.ptr(mask), 2.0, 1.5, 0.2, 0.9, tot, L.ptr(xb), None, st)),
+    "noise-label copy": lambda: nl.copy_(torch.zeros(1, device=dev)),
+}
+print("  ".join(f"{k}: {timed(v):.1f} us" for k, v in parts.items()))
