@@ -411,6 +411,12 @@ MCEDM_API int mcedm_darcy_loss(const void* a, int a_f64, const long long* a_stri
 /* x_noise = x + mask*noise*sigma[b] ; x_in = c_in[b]*x_noise   (mcedm.py:216, :208); mask may be NULL */
 MCEDM_API int mcedm_edm_noise_in(const float* x, const float* noise, const float* mask, const float* sigma,
                                  const float* c_in, int B, long long chw, float* x_noise, float* x_in, void* stream);
+/* Batch preparation of PlMcedm.training_step in one pass (mcedm.py:257-265 data_transform + rearranges, :241-252
+ * get_cond_in, normalizer.py:28-29): x = ((h - h_sub)/h_div | (u - u_sub)/u_div), cond = x*(1-mask) + randn*mask.
+ * h, u [B,HW]; mask, randn [B,HW,2] channel-last; x, cond, mask_c [B,2,HW] channel-first.  Bit-identical to torch. */
+MCEDM_API int mcedm_mcedm_prep(const float* h, const float* u, const float* mask, const float* randn, float h_sub,
+                               float h_div, float u_sub, float u_div, int B, long long HW, float* x, float* cond,
+                               float* mask_c, void* stream);
 /* channels [c_dst0, c_dst0+Ca+Cb) of a 64-channel bf16 NHWC tensor <- cat(a, b) (NCHW fp32; b may be NULL, Cb = 0) */
 MCEDM_API int mcedm_nchw_to_nhwc_pad(const float* a, int Ca, const float* b, int Cb, int B, int H, int W,
                                      void* dst_bf16, int c_dst0, void* stream);

@@ -33,6 +33,33 @@ edm_noise_in_kernel(const float* __restrict__ x, const float* __restrict__ noise
   }
 }
 
+// Batch preparation of PlMcedm.training_step (models/mcedm.py:257-265, :241-252; models/normalizer.py:28-29):
+//   x[b,0] = (h - h_sub)/h_div ; x[b,1] = (u - u_sub)/u_div                      (data_transform, b h w c)
+//   cond   = x*(1 - mask) + randn*mask                                            (get_cond_in)
+// and the three `b h w c -> b c h w` rearranges, in one pass (the reference: ~10 elementwise / permute launches).
+// Every float32 operation is the torch operation, individually rounded: outputs are bit-identical.
+// h, u: [B,HW] ; mask, randn: [B,HW,2] (channel-last, as the datamodule / torch.randn_like produce them);
+// x, cond, mask_c: [B,2,HW] (channel-first).  One thread per pixel: 8-byte channel-pair loads, coalesced plane stores.
+__global__ void __launch_bounds__(256)
+mcedm_prep_kernel(const float* __restrict__ h, const float* __restrict__ u, const float* __restrict__ mask,
+                  const float* __restrict__ randn, float h_sub, float h_div, float u_sub, float u_div, long long HW,
+                  long long total_pix, float* __restrict__ x, float* __restrict__ cond, float* __restrict__ mask_c) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total_pix) return;
+  const long long b = pix / HW, hw = pix - b * HW;
+  const float xh = __fdiv_rn(__fsub_rn(h[pix], h_sub), h_div);
+  const float xu = __fdiv_rn(__fsub_rn(u[pix], u_sub), u_div);
+  const float2 m = *reinterpret_cast<const float2*>(mask + pix * 2);
+  const float2 r = *reinterpret_cast<const float2*>(randn + pix * 2);
+  const long long o0 = (b * 2) * HW + hw, o1 = o0 + HW;
+  x[o0] = xh;
+  x[o1] = xu;
+  cond[o0] = __fadd_rn(__fmul_rn(xh, __fsub_rn(1.0f, m.x)), __fmul_rn(r.x, m.x));
+  cond[o1] = __fadd_rn(__fmul_rn(xu, __fsub_rn(1.0f, m.y)), __fmul_rn(r.y, m.y));
+  mask_c[o0] = m.x;
+  mask_c[o1] = m.y;
+}
+
 // one thread per pixel; dst channels [c_dst0, c_dst0 + Ca + Cb) <- cat(a, b)[:, :, pix]
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_pad_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ bsrc, int Cb, long long HW,
@@ -279,6 +306,18 @@ extern "C" int mcedm_edm_noise_in(const float* x, const float* noise, const floa
   dim3 grid(gx, B);
   edm_noise_in_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, noise, mask, sigma, c_in, chw,
                                                                                 x_noise, x_in);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_mcedm_prep(const float* h, const float* u, const float* mask, const float* randn, float h_sub,
+                                float h_div, float u_sub, float u_div, int B, long long HW, float* x, float* cond,
+                                float* mask_c, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && HW >= 1, "mcedm_prep: bad sizes");
+  const long long total = HW * B;
+  mcedm_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, u, mask, randn, h_sub, h_div, u_sub, u_div, HW, total, x, cond, mask_c);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

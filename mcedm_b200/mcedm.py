@@ -111,6 +111,7 @@ class PlMcedm(LightningModule):
         self.test_sparams = self.sparams
         self.h_ch = self.u_ch = m.out_ch // 2 if m.out_ch > 1 else 1
         self.use_cuda_graph = True   # replay the captured U-Net launch sequence inside sample_edm
+        self.fused_prep = True       # training_step: normalise + cond_in + rearranges in one kernel (mcedm_mcedm_prep)
         self._noise_hook = None      # tests inject pre-drawn noise here: fn(kind, like) -> tensor
         self._trace = None           # tests: list receiving (step, which, sigma, D_x, x_t)
 
@@ -305,17 +306,43 @@ class PlMcedm(LightningModule):
         return 0 if return_index else torch.as_tensor(sigma)
 
     # ---------------------------------------------------------------- training / evaluation steps
+    def _prep_batch(self, h_unnorm, u_unnorm, mask):
+        """(x, cond_in, mask) as `b c h w` fp32 from the datamodule's `b h w c` tensors: data_transform (:257), get_cond_in
+        (:259, incl. its randn_like draw) and the three rearranges (:263-265) in one kernel (mcedm_mcedm_prep,
+        bit-identical to the torch expressions).  Returns None when an option the kernel does not cover is on."""
+        if not (self.fused_prep and h_unnorm.is_cuda and h_unnorm.shape[-1] == 1 and u_unnorm.shape[-1] == 1
+                and self.normalization != "min_max" and not (self.uniform_dequantization or self.gaussian_dequantization
+                                                             or self.rescaled or self.add_cond_mask or self.add_xt)
+                and h_unnorm.dtype == torch.float32 and mask.dtype == torch.float32):
+            return None
+        from .pde_loss import _norm_args
+
+        h_div, h_sub, u_div, u_sub = _norm_args(self.normalizer_input, self.normalizer_target)
+        B, H, W, _ = h_unnorm.shape
+        h, u, m = h_unnorm.contiguous(), u_unnorm.contiguous(), mask.contiguous()
+        r = self._randn_like("cond", m).contiguous()                 # the draw of get_cond_in (:247): b h w c, fp32
+        x = torch.empty(B, 2, H, W, device=h.device, dtype=torch.float32)
+        cond, mask_c = torch.empty_like(x), torch.empty_like(x)
+        L.check(L.lib().mcedm_mcedm_prep(L.ptr(h), L.ptr(u), L.ptr(m), L.ptr(r), h_sub, h_div, u_sub, u_div, B, H * W,
+                                         L.ptr(x), L.ptr(cond), L.ptr(mask_c), L.stream_ptr()), "mcedm_prep")
+        return x, cond, mask_c
+
     def training_step(self, train_batch, batch_idx):
         h_unnorm, dx, dt, u_unnorm, mask = train_batch
         self.h_ch, self.u_ch = h_unnorm.shape[-1], u_unnorm.shape[-1]
-        x = self.data_transform(h_unnorm, u_unnorm)                 # b h w c
-        cond_in = rearrange(self.get_cond_in(x, mask, dx, dt), "b h w c -> b c h w").contiguous()
-        x = rearrange(x, "b h w c -> b c h w").contiguous()
+        prep = self._prep_batch(h_unnorm, u_unnorm, mask)
+        if prep is not None:
+            x, cond_in, mask_pre = prep
+        else:
+            x = self.data_transform(h_unnorm, u_unnorm)                 # b h w c
+            cond_in = rearrange(self.get_cond_in(x, mask, dx, dt), "b h w c -> b c h w").contiguous()
+            x = rearrange(x, "b h w c -> b c h w").contiguous()
+            mask_pre = None
         noise = self._randn_like("noise", x)
         rnd_normal = torch.randn([x.shape[0], 1, 1, 1]).type_as(x)  # CPU RNG, as :269-270
         sigma = (rnd_normal * self.P_std + self.P_mean).exp()
         weight = self.get_loss_weight(sigma)
-        mask_c = rearrange(mask, "b h w c -> b c h w").contiguous()
+        mask_c = mask_pre if mask_pre is not None else rearrange(mask, "b h w c -> b c h w").contiguous()
         # reference: D_x = self.forward(...); loss = self.criteria(D_x * mask, x * mask, weight)  (:277-278).
         # Here noise injection + c_in scaling, the U-Net, and preconditioning + masked weighted loss (+ dL/dF) are
         # three fused launches/nodes; `loss.backward()` runs the backward kernels.

@@ -465,3 +465,38 @@ def test_pack_plan_is_bit_identical_to_the_torch_packing(dev):
         for (n0, i0, a), b in zip(ref1, got):
             assert torch.equal(a, b), (n0, i0)
         assert any(not torch.equal(a[2], b[2]) for a, b in zip(ref0, ref1))
+
+
+def test_fused_batch_prep_is_bit_identical_to_the_torch_expressions(dev):
+    """mcedm_mcedm_prep (one kernel) against data_transform + get_cond_in + the three rearranges of
+    PlMcedm.training_step (models/mcedm.py:257-265) evaluated with torch on the same inputs and the same injected
+    draw; and the training step gives the same loss through either path."""
+    from common import NoiseFeed, stress_module
+    from einops import rearrange
+    from mcedm_b200 import data as D
+
+    pl, _ = stress_module()
+    pl = pl.to(dev).train()
+    st = D.field_stats("swe_per", 16)
+    pl.normalizer_input.set_stats(st["input_mean"].to(dev), st["input_std"].to(dev))
+    pl.normalizer_target.set_stats(st["target_mean"].to(dev), st["target_std"].to(dev))
+    h, tg, xg, u, mask = (t.to(dev) for t in D.make_batch("swe_per", 3, "train", seed=5))
+    feed = NoiseFeed(41)
+    pl._noise_hook = feed.hook
+    x, cond, mask_c = pl._prep_batch(h, u, mask)
+    assert feed.calls == [((3, 128, 128, 2), "torch.float32")]
+    feed = NoiseFeed(41)
+    pl._noise_hook = feed.hook
+    xr = pl.data_transform(h, u)
+    cr = rearrange(pl.get_cond_in(xr, mask, tg, xg), "b h w c -> b c h w").contiguous()
+    assert torch.equal(x, rearrange(xr, "b h w c -> b c h w").contiguous())
+    assert torch.equal(cond, cr)
+    assert torch.equal(mask_c, rearrange(mask, "b h w c -> b c h w").contiguous())
+    losses = []
+    for fused in (True, False):
+        pl.fused_prep = fused
+        feed = NoiseFeed(42)
+        pl._noise_hook = feed.hook
+        torch.manual_seed(3)
+        losses.append(float(pl.training_step((h, tg, xg, u, mask), 0)))
+    assert losses[0] == losses[1]
