@@ -339,19 +339,21 @@ class VpGrid:
         return (1 - betas).cumprod(dim=0).index_select(0, t.reshape(-1) + 1).view(-1, 1, 1, 1)
 
 
-def vp_denoise(sd, model_cfg, grid: VpGrid, xt: Tensor, t: Tensor):
-    """PlDdim.get_denoised with cond = x_self_cond = dx = None (ddim.py:915-947): c_skip = 1, c_out = -sigma."""
+def vp_denoise(sd, model_cfg, grid: VpGrid, xt: Tensor, t: Tensor, net=None):
+    """PlDdim.get_denoised with cond = x_self_cond = dx = None (ddim.py:915-947): c_skip = 1, c_out = -sigma.
+    net(sd, model_cfg, x, noise_labels): the network — `unet_forward` (ADM branch, `hparams.name` = adm*) by default,
+    `oracle.ddpm_oracle.ddpm_unet_forward` for the DDPM U-Net branch (ddim.py:40-43)."""
     xt = xt.to(torch.float32)
     sigma = t.to(torch.float32).reshape(-1, 1, 1, 1)
     c_in = 1 / (sigma ** 2 + 1).sqrt()
     c_noise = grid.num_timesteps - 1 - grid.round_sigma(sigma, return_index=True).to(torch.float32)
-    f_x = unet_forward(sd, model_cfg, c_in * xt, c_noise.flatten(), None)
+    f_x = (net or unet_forward)(sd, model_cfg, c_in * xt, c_noise.flatten())
     return 1 * xt + (-sigma) * f_x, f_x
 
 
 def ddim_sample_edm(sd, model_cfg, grid: VpGrid, hu: Tensor, hu_noise: Tensor, sparams,
                     step_noise: Callable[[Tensor], Tensor], h_ch: int = 1, u_ch: int = 1, return_last: bool = True,
-                    record: Optional[list] = None) -> Tensor:
+                    record: Optional[list] = None, net=None) -> Tensor:
     """PlDdim.sample_edm (ddim.py:959-1051) with guide_dx False, w = 0.  hu fp32 [B,C,H,W]: the normalised ground truth
     whose first n_time_h / n_time_u time rows are known (mask == 1 KNOWN); hu_noise: the draw of :967;
     step_noise(x) -> fp64 draw of :1002 / :1036.  Returns xs [B, T, H, W, C] fp64."""
@@ -377,13 +379,13 @@ def ddim_sample_edm(sd, model_cfg, grid: VpGrid, hu: Tensor, hu_noise: Tensor, s
         t_hat = grid.round_sigma(t_cur + gamma * t_cur)
         x_hat = x_cur + (t_hat ** 2 - t_cur ** 2).sqrt() * sparams["S_noise"] * step_noise(x_cur)
         for k in range(n_repeat):
-            d1, _ = vp_denoise(sd, model_cfg, grid, x_hat, t_hat)
+            d1, _ = vp_denoise(sd, model_cfg, grid, x_hat, t_hat, net)
             if record is not None:
                 record.append((i, k, 0, float(t_hat), d1))
             d_cur = (x_hat - d1.to(torch.float64)) / t_hat
             x_next = x_hat + (t_next - t_hat) * d_cur
             if i < num_steps - 1:
-                d2, _ = vp_denoise(sd, model_cfg, grid, x_next, t_next)
+                d2, _ = vp_denoise(sd, model_cfg, grid, x_next, t_next, net)
                 if record is not None:
                     record.append((i, k, 1, float(t_next), d2))
                 d_prime = (x_next - d2.to(torch.float64)) / t_next

@@ -75,3 +75,23 @@ def pde_fields(system, n, seed, amp=0.05):
     g = torch.Generator().manual_seed(1000 + seed)
     pred = gt + amp * torch.randn(gt.shape, generator=g)
     return pred, gt, D.field_stats(system, 16)
+
+
+def seeded_weights(shapes, seed=3):
+    """Deterministic fp32 weights for a network given only its state_dict shapes (used for the DDPM U-Net fixture, whose
+    module has no mirror in this repo yet): N(0, 1/fan_in) for matrices / filters, 1 + 0.1 N for norm scales
+    (`norm*.weight`), 0.1 N for every other vector.  One CPU generator, tensors drawn in the given order."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, shape in shapes.items():
+        shape = tuple(shape)
+        if len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            out[name] = torch.randn(shape, generator=g) / fan_in ** 0.5
+        elif "norm" in name and name.endswith("weight"):
+            out[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            out[name] = 0.1 * torch.randn(shape, generator=g)
+    return out

@@ -191,3 +191,42 @@ def test_oracle_ddim_repaint_sampler_matches_reference():
     assert rel_l2(xs, s["xs"]) < 1e-5
     # the observed region (u for t < 64) is re-imposed exactly; the rest is generated
     assert torch.equal(xs[0, 0, :64, :, 1], hu[0, 1, :64].double())
+
+
+def test_oracle_ddpm_unet_and_repaint_sampler_match_reference():
+    """SURVEY §8f rank 2, oracle first: the DDPM U-Net (`ddim_blocks.Model`, what the shipped ddim_res32.yaml builds) and
+    BASELINE config 4 through it — one network evaluation and a 3-step RePaint-conditioned PlDdim.sample_edm trajectory
+    against the unmodified reference (tests/golden/make_golden_ddpm.py).  No CUDA path for this network yet."""
+    from common import seeded_weights
+    from mcedm_b200.utils import state_hash
+    from oracle import ddpm_oracle as DO
+
+    g = golden("ddpm_path.pt")
+    sd = seeded_weights(g["shapes"], seed=3)
+    assert state_hash(sd) == g["weights_hash"]
+    mcfg = g["model_cfg"]
+    gen = torch.Generator().manual_seed(g["forward"]["seed"])
+    x = torch.randn(2, 2, 128, 128, generator=gen)
+    with torch.no_grad():
+        y = DO.ddpm_unet_forward(sd, mcfg, x, g["forward"]["t"])
+    assert rel_l2(y, g["forward"]["y"]) < 1e-6
+    grid = O.VpGrid()
+    h, u = D._FIELDS["swe"](1, 128, first_seed=g["field_seed"])
+    st = g["stats"]
+    hu = torch.cat([(torch.from_numpy(h) - st["input_mean"]) / st["input_std"],
+                    (torch.from_numpy(u) - st["target_mean"]) / st["target_std"]], dim=-1).permute(0, 3, 1, 2).contiguous()
+    s = g["sample"]
+    sp = dict(hparams("config_adm_ddim_res32").diff_sampler)
+    sp.update(timesteps=s["steps"], n_time_h=s["n_time_h"], n_time_u=s["n_time_u"], n_repeat=s["n_repeat"])
+    feed = NoiseFeed(s["seed"])
+    hu_noise = feed.draw(hu)
+    rec = []
+    with torch.no_grad():
+        xs = O.ddim_sample_edm(sd, mcfg, grid, hu, hu_noise, sp, feed.draw, record=rec, net=DO.ddpm_net)
+    assert [tuple(c) for c in feed.calls] == [tuple(c) for c in s["calls"]]
+    assert len(rec) == len(s["denoised"])
+    for (i, k, which, sigma, d), ref in zip(rec, s["denoised"]):
+        assert abs(sigma - ref["sigma"]) <= 1e-9 * max(1.0, ref["sigma"])
+        assert rel_l2(d, ref["D"]) < 1e-5
+    assert rel_l2(xs, s["xs"]) < 1e-5
+    assert torch.equal(xs[0, 0, :64, :, 1], hu[0, 1, :64].double())
