@@ -225,3 +225,33 @@ def test_pde_loss_selection_and_cpu_inputs_raise():
             raise AssertionError("CPU tensors were accepted")
         except L.McedmError:
             pass
+
+
+def test_ddpm_model_mirror_state_dict():
+    """Parameter mirror of the DDPM U-Net: names / shapes / order fixed by the reference fixture (tests/golden/ddpm_path.pt
+    holds the reference's shapes); seeded init bit-identical to the live reference when it is mounted; forward raises."""
+    import ref_harness_path  # noqa: F401
+    import ref_harness as R
+    from common import golden
+    from mcedm_b200.ddpm_blocks import Model
+
+    cfg = compose("config_adm_ddim_res32")
+    hp = copy.deepcopy(cfg.model.hparams)
+    hp.name = "ddim"
+    torch.manual_seed(1)
+    net = Model(hp)
+    sd = net.state_dict()
+    shapes = golden("ddpm_path.pt")["shapes"]
+    assert list(sd) == list(shapes) and all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items())
+    assert sum(v.numel() for v in sd.values()) == 1568514
+    try:
+        net(torch.zeros(1, 2, 128, 128), torch.zeros(1))
+        raise AssertionError("forward ran without kernels")
+    except NotImplementedError:
+        pass
+    if R.reference_available():
+        ref = R.import_reference()
+        torch.manual_seed(1)
+        rnet = ref.ddim.Model(copy.deepcopy(R.reference_hparams("config_ddim_res32").model.hparams))
+        for (k, v), (kr, vr) in zip(sd.items(), rnet.state_dict().items()):
+            assert k == kr and torch.equal(v, vr), k
