@@ -34,6 +34,9 @@ FLOPS_PER_EVAL = 18.797e9          # per sample per U-Net forward (BASELINE.md Â
 EVALS_PER_FIELD = 99
 
 
+_STDOUT = sys.stdout
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,7 +193,7 @@ def run_reference(args):
                             timesteps=args.timesteps, fields_per_step=args.ref_fields),
                 cpu_baseline=dict(value=value, unit="fields/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit="fields/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -373,7 +376,7 @@ def run_b200(args):
                     e2e=dict(value=e2e_value, unit="fields/s", h2d_bytes_per_step=int(2 * rows * 2 * 128 * 128 * 4),
                              d2h_bytes_per_step=int(rows * 2 * 128 * 128 * 8), ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train=train)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_STDOUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -482,6 +485,9 @@ def measure_training(args, cfg, dev, rank, world, barrier):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: anything a library prints on the way goes to stderr
+    _STDOUT = sys.stdout
+    sys.stdout = sys.stderr
     a = parse()
     if a.impl == "reference":
         run_reference(a)

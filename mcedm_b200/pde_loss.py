@@ -14,6 +14,8 @@ There is no CPU path: CPU tensors raise.  Not implemented (raise NotImplementedE
 """
 from __future__ import annotations
 
+import sys
+
 import torch
 from torch import nn
 
@@ -197,7 +199,8 @@ class DarcyLoss(nn.Module):
 
 def get_pde_loss_function(system, flip_xy, Tn_mult=1.0):
     """loss_helper.py:14-41 (the undefined `ReactorLoss` branch raises NameError there; here NotImplementedError)."""
-    print(f"PDE error: system = {system}")
+    # the reference prints this line to stdout (loss_helper.py:15); stderr here: bench.py's stdout is one JSON line
+    print(f"PDE error: system = {system}", file=sys.stderr)
     if system == "swe_per":
         Tn = 0.128 * Tn_mult
         return (SweFvLoss(Tn=Tn, x_min=-0.5, x_max=0.5, flip_xy=flip_xy),
