@@ -255,3 +255,21 @@ def test_ddpm_model_mirror_state_dict():
         rnet = ref.ddim.Model(copy.deepcopy(R.reference_hparams("config_ddim_res32").model.hparams))
         for (k, v), (kr, vr) in zip(sd.items(), rnet.state_dict().items()):
             assert k == kr and torch.equal(v, vr), k
+
+
+def test_reference_arm_contract_under_torchrun_env():
+    """`bench.py --impl reference`: rank 0 prints exactly one JSON object on stdout (banners go to stderr), every other
+    rank exits 0 without output."""
+    import json
+
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env["RANK"] = "0"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--timesteps", "3", "--gpus", "2"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    d = json.loads(r.stdout)                                   # the whole of stdout is one JSON object
+    assert d["impl"] == "reference" and d["unit"] == "fields/s" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
