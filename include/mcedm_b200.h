@@ -453,6 +453,9 @@ MCEDM_API int mcedm_pack_gather(const float* base, const long long* idx_a, const
 /* tensor-pipe + shared-memory operand-fetch ceiling: every SM issues n_tiles x 36 tcgen05.mma (M=128, N, K=16, the conv
  * kernels' descriptor pattern) and nothing else; cycles_per_cta[sm] = clock64 ticks (DEVICE int64 [#SMs]). */
 MCEDM_API int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_cta, void* stream);
+/* issue-queue depth of tcgen05.mma: per iteration n_mma x (M=128, N=192, K=16) + one commit, then `idle` cycles of
+ * nothing on the issuing warp; out3_per_cta[sm] = {total, issue, commit} clock64 ticks (DEVICE int64 [#SMs][3]). */
+MCEDM_API int mcedm_probe_mma_queue(int iters, int n_mma, int idle, long long* out3_per_cta, void* stream);
 /* bring-up: per-CTA cycles spent in each role's barrier waits by the last fused conv_rows launch run with MCEDM_DBG=32
  * (HOST int64 [160][8]: h_empty, acc_empty, h_ready, acc_full, h_full waits; epilogue, MMA, producer role totals) */
 MCEDM_API int mcedm_debug_rows(long long* host_out);

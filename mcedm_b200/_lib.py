@@ -82,6 +82,7 @@ _PROTOTYPES = {
     "mcedm_swe_fv_grad": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp],
     "mcedm_darcy_loss": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _i, _i, _f, _vp, _vp, _vp, _vp],
     "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
+    "mcedm_probe_mma_queue": [_i, _i, _i, _vp, _vp],
     "mcedm_debug_rows": [_vp],
     "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
     "mcedm_conv_direct_ref": [_vpp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],

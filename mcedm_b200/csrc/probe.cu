@@ -201,6 +201,91 @@ extern "C" int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_ct
   return 0;
 }
 
+namespace mcedm {
+// Issue-queue probe: per iteration one elected lane issues `n_mma` tcgen05.mma (M = 128, N = 192, K = 16, the stacked
+// shape of conv_rows_fused) + one commit, then the warp idles `idle` cycles (what the issuing warp's waits / address
+// arithmetic / loop control look like to the tensor pipe).  If MMAs queue deeply, cycles/iteration = max(tensor time,
+// idle + issue); if issue is (nearly) synchronous with execution, it is their SUM.  out[cta] = {total, issue, commit}.
+__global__ void __launch_bounds__(64, 1) probe_mma_queue_kernel(int iters, int n_mma, int idle, long long* out,
+                                                                unsigned int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_smem = smem;                          // 192 x 128 B x 4 K-steps worth (re-read)
+  uint8_t* a_smem = smem + 72 * 1024;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + 3 * 17408);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 1) {
+    const uint32_t idesc = umma_idesc_16(128, 192, 0, 0, 1);
+    const uint32_t w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);
+    const uint32_t a_lo = (smem_u32(a_smem) >> 4) | (1u << 16);
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(kHi) << 32) | lo; };
+    long long t_issue = 0, t_commit = 0;
+    const long long t0 = clock64();
+    for (int t = 0; t < iters; ++t) {
+      const long long c0 = clock64();
+      if (elect_one()) {
+        for (int i = 0; i < n_mma; ++i) {
+          const int kx = (i >> 2) % 3, ks = i & 3;
+          umma_f16(tmem_base + (uint32_t)((t & 1) * 192), desc(a_lo + kx * 8 + ks * 2),
+                   desc(w_lo + kx * 3 * (64 * 128 >> 4) + ks * 2), idesc, i != 0 ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      const long long c1 = clock64();
+      if (elect_one()) umma_commit(&bars[t & 3]);
+      __syncwarp();
+      const long long c2 = clock64();
+      t_issue += c1 - c0;
+      t_commit += c2 - c1;
+      while (clock64() - c2 < idle) {}
+    }
+    for (int t = (iters > 4 ? iters - 4 : 0); t < iters; ++t) {
+      const int uses_before = t / 4;      // completions of bars[t & 3] before iteration t
+      mbar_wait(&bars[t & 3], (uint32_t)uses_before & 1u, err, 0x930 + (t & 3));
+    }
+    const long long t1 = clock64();
+    if (elect_one()) {
+      out[blockIdx.x * 3 + 0] = t1 - t0;
+      out[blockIdx.x * 3 + 1] = t_issue;
+      out[blockIdx.x * 3 + 2] = t_commit;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace mcedm
+
+extern "C" int mcedm_probe_mma_queue(int iters, int n_mma, int idle, long long* out3_per_cta, void* stream) {
+  using namespace mcedm;
+  unsigned int* err = watchdog_ptr();
+  MCEDM_REQUIRE(err != nullptr, "probe_mma_queue: no watchdog word");
+  MCEDM_REQUIRE(iters >= 1 && n_mma >= 1 && idle >= 0, "probe_mma_queue: bad arguments");
+  const int smem = 1024 + 72 * 1024 + 3 * 17408 + 256;
+  MCEDM_CUDA(cudaFuncSetAttribute(probe_mma_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_mma_queue_kernel<<<num_sms(), 64, smem, reinterpret_cast<cudaStream_t>(stream)>>>(iters, n_mma, idle,
+                                                                                        out3_per_cta, err);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int row_shift, int base_offset,
                                 int b_mn_major, float* out, void* stream) {
   using namespace mcedm;

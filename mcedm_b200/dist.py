@@ -62,12 +62,31 @@ def gather_rows(local: torch.Tensor, n_rows: int) -> torch.Tensor:
     return torch.cat([out[r * max_rows: r * max_rows + (hi - lo)] for r, (lo, hi) in enumerate(counts)], dim=0)
 
 
-def sample_edm_sharded(module, hu, cond, hu_mask, sparams, return_last=True):
-    """`module.sample_edm` on this rank's row block, then one gather: returns xs for ALL rows on every rank."""
+def sample_rows(module, hu, cond, hu_mask, sparams, return_last=True, chunk=None):
+    """`module.sample_edm` over the given rows in micro-batches of `chunk` rows (None: one call).  Rows are independent
+    trajectories (bit-identical alone or inside any batch: tests/test_gpu_parity.py::test_full_size_micro_batch_properties),
+    so the micro-batching only bounds the activation workspace; cond / mask may live in pinned host memory."""
+    n = hu.shape[0]
+    if chunk is None or chunk >= n:
+        dev = next(module.parameters()).device
+        return module.sample_edm(hu, cond.to(dev, non_blocking=True), hu_mask.to(dev, non_blocking=True), sparams,
+                                 return_last=return_last)
+    dev = next(module.parameters()).device
+    outs = []
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        outs.append(module.sample_edm(hu[lo:hi], cond[lo:hi].to(dev, non_blocking=True),
+                                      hu_mask[lo:hi].to(dev, non_blocking=True), sparams, return_last=return_last))
+    return torch.cat(outs, dim=0)
+
+
+def sample_edm_sharded(module, hu, cond, hu_mask, sparams, return_last=True, chunk=None):
+    """`module.sample_edm` on this rank's row block, then one gather: returns xs for ALL rows on every rank.
+    hu / cond / hu_mask hold ALL rows (the reference stacks n_samples * b rows on one GPU, models/mcedm.py:352-376);
+    each rank touches only its [lo, hi) block."""
     n = hu.shape[0]
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return module.sample_edm(hu, cond, hu_mask, sparams, return_last=return_last)
+        return sample_rows(module, hu, cond, hu_mask, sparams, return_last, chunk)
     lo, hi = shard_rows(n, dist.get_rank(), dist.get_world_size())
-    xs = module.sample_edm(hu[lo:hi].contiguous(), cond[lo:hi].contiguous(), hu_mask[lo:hi].contiguous(), sparams,
-                           return_last=return_last)
+    xs = sample_rows(module, hu[lo:hi], cond[lo:hi], hu_mask[lo:hi], sparams, return_last, chunk)
     return gather_rows(xs.contiguous(), n)

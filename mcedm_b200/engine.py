@@ -414,6 +414,10 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin, PackMixin):
         """Forward pass on caller-owned STATIC buffers (same addresses every call): the ~125 launches are
         captured once into a CUDA graph and replayed, which removes the per-launch host cost from the
         99-evaluations-per-field sampling loop.  `nl` is a device tensor whose VALUE may change between calls."""
+        # the training entry points leave `_fmt = 0` (bf16 operands) on the engine: inference always runs its own format,
+        # whatever ran before on this engine (sampling with `ema: False` after a training step used to fall back to the
+        # unfused bf16 plan)
+        self._fmt = self.infer_fmt
         self.pack()
         if not use_graph:
             return self._launch_all(x, nl, cond, out)

@@ -8,6 +8,7 @@ of one contiguous buffer, which is also what the data-parallel gradient all-redu
 """
 from __future__ import annotations
 
+import weakref
 from typing import Optional
 
 import torch
@@ -15,7 +16,10 @@ import torch
 from . import _lib as L
 
 
-_FLAT = {}      # data_ptr of the first parameter -> the flat buffer its parameter list lives in
+# data_ptr of the first parameter -> the flat buffer its parameter list lives in.  Weak values: the buffer is owned by
+# the optimizer / EMA state that created it (and by the parameter views into it); a re-bind or a dead owner drops the
+# entry instead of pinning ~6 MB of device memory per stale binding for the life of the process.
+_FLAT = weakref.WeakValueDictionary()
 
 
 def _flatten_(params):
@@ -61,6 +65,7 @@ class FusedAdam(torch.optim.Adam):
         self._params = list(self.param_groups[0]["params"])
         self._flat_p = None
         self._flat_g = None
+        self._pending_g = None                  # the flat gradient of the current step, once fetched (see flat_grads)
         self._steps = 0
         self._n_partial = 128
         if self._params[0].is_cuda:             # normally true: optimizers are configured after the module moved
@@ -69,13 +74,15 @@ class FusedAdam(torch.optim.Adam):
     def _bind(self):
         if not self._params[0].is_cuda:
             raise L.McedmError("FusedAdam needs CUDA parameters: the optimizer kernels have no CPU path")
-        if self._flat_p is None:
-            dev = self._params[0].device
+        dev = self._params[0].device
+        if self._flat_p is None or self._partial.device != dev:      # first bind, or the module moved to another device
             self.last_grad_norm = torch.zeros(1, device=dev)
             self._partial = torch.empty(self._n_partial, device=dev, dtype=torch.float64)
         old_m = old_v = None
         if self._flat_p is not None:            # parameters were moved (Module.to): keep the moments
             old_m, old_v = self._m, self._v
+            _FLAT.pop(self._flat_p.data_ptr(), None)
+        self._pending_g = None
         self._flat_p = _flatten_(self._params)
         dev = self._flat_p.device
         self._m = torch.zeros_like(self._flat_p) if old_m is None else old_m.to(dev)
@@ -96,7 +103,21 @@ class FusedAdam(torch.optim.Adam):
 
     def flat_grads(self) -> torch.Tensor:
         """All gradients as one contiguous tensor: the engine's own flat buffer when `.grad` already aliases it
-        (the normal case after UNetFunction.backward), otherwise a gathered copy."""
+        (the normal case after UNetFunction.backward), otherwise a gathered copy.  Idempotent within a step: the
+        tensor fetched first is the one `step()` consumes, so `dist.all_reduce(opt.flat_grads())` followed by
+        `opt.step()` steps on the REDUCED gradient on either path (a second gather used to overwrite it with the
+        local gradients).  Cleared by step() and zero_grad()."""
+        if self._pending_g is not None:
+            return self._pending_g
+        g = self._fetch_flat_grads()
+        self._pending_g = g
+        return g
+
+    def zero_grad(self, set_to_none: bool = True):
+        self._pending_g = None
+        return super().zero_grad(set_to_none=set_to_none)
+
+    def _fetch_flat_grads(self) -> torch.Tensor:
         ps = self._params
         g0 = ps[0].grad
         if g0 is None:
@@ -146,6 +167,7 @@ class FusedAdam(torch.optim.Adam):
                                     self._n_partial, float(self.max_grad_norm or 0.0), float(self.grad_scale),
                                     L.ptr(self.last_grad_norm), st), "adam_step")
         self._step_t.fill_(float(self._steps))
+        self._pending_g = None
         WEIGHT_EPOCH[0] += 1                    # packed bf16 weights of every engine are stale now
         return loss
 

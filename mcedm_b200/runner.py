@@ -11,7 +11,13 @@ this module provides the minimum that keeps the reference's module code shape in
     flat buffer per step, gradient-norm clipping as `gradient_clip_val` (trainer_ddim.yaml:8-9),
     hooks called in Lightning's order: setup('fit') -> training_step -> backward -> [all-reduce] ->
     clip -> optimizer_step (module hook, which also updates the EMA) -> validation_step / test_step;
-  * `ModelCheckpoint` — `checkpoints/last.ckpt` with Lightning's `state_dict` key layout.
+  * `ModelCheckpoint` — `checkpoints/last.ckpt` with Lightning's top-level key layout (`state_dict`,
+    `optimizer_states`, `epoch`, `global_step`, `hyper_parameters`, ...); `fit(ckpt_path=...)` resumes like
+    `trainer.fit(ckpt_path=...)` of run.py:99: weights, Adam moments + step counter, global step, next epoch.
+
+Data parallelism is THIS trainer's flat all-reduce; the kernels' autograd nodes bind `p.grad` to slices of the engine's
+flat gradient buffer directly, so the per-parameter reducer hooks of `torch.nn.parallel.DistributedDataParallel`
+(Lightning's `strategy: ddp`) never fire: under a real Lightning Trainer the module runs on one device only.
 """
 from __future__ import annotations
 
@@ -74,14 +80,28 @@ class ModelCheckpoint:
     def __init__(self, dirpath="checkpoints/", filename="epoch", save_last=True, **_unused):
         self.dirpath, self.filename, self.save_last = dirpath, filename, save_last
 
+    def format_name(self, epoch: int, step: int) -> str:
+        """Lightning's naming: `{epoch}` / `{step}` fields are substituted as `epoch=3`; a filename without fields gets
+        the default `epoch=E-step=S` suffix-free form only when it is None."""
+        name = self.filename if self.filename is not None else "{epoch}-{step}"
+        return name.replace("{epoch}", f"epoch={epoch}").replace("{step}", f"step={step}")
+
     def save(self, trainer, module, epoch):
         if trainer.global_rank != 0:
             return
         os.makedirs(self.dirpath, exist_ok=True)
-        ckpt = {"epoch": epoch, "global_step": module.global_step, "state_dict": module.state_dict()}
+        hp = getattr(module, "hparams", None)
+        ckpt = {
+            "epoch": epoch, "global_step": module.global_step,
+            # Lightning reads these when a checkpoint is handed to `trainer.fit/test(ckpt_path=...)` (eval_model.py:77)
+            "pytorch-lightning_version": getattr(_pl, "__version__", "1.9.0") if _pl is not None else "1.9.0",
+            "state_dict": module.state_dict(),
+            "loops": None, "callbacks": {}, "lr_schedulers": [],
+            "hyper_parameters": hp if isinstance(hp, dict) else ({} if hp is None else dict(hp)),
+        }
         if trainer.optimizer is not None:
             ckpt["optimizer_states"] = [trainer.optimizer.state_dict()]
-        torch.save(ckpt, os.path.join(self.dirpath, f"{self.filename}.ckpt"))
+        torch.save(ckpt, os.path.join(self.dirpath, f"{self.format_name(epoch, module.global_step)}.ckpt"))
         if self.save_last:
             torch.save(ckpt, os.path.join(self.dirpath, "last.ckpt"))
 
@@ -173,13 +193,19 @@ class Trainer:
         if fused:
             self.optimizer.max_grad_norm = self.gradient_clip_val or None
             self.optimizer.grad_scale = 1.0 / self.world_size
-        if ckpt_path:
-            ckpt = torch.load(ckpt_path, map_location=self._device)
-            module.load_state_dict(ckpt["state_dict"])
-            module.current_epoch = ckpt.get("epoch", 0)
-        history = []
         step = 0
-        for epoch in range(module.current_epoch, self.max_epochs):
+        first_epoch = module.current_epoch
+        if ckpt_path:
+            # resume as `trainer.fit(model, datamodule, ckpt_path=...)` (run.py:99): weights, optimizer moments and
+            # step counter (bias correction continues), global step; the saved epoch is complete -> start at the next
+            ckpt = torch.load(ckpt_path, map_location=self._device, weights_only=False)
+            module.load_state_dict(ckpt["state_dict"])
+            if ckpt.get("optimizer_states"):
+                self.optimizer.load_state_dict(ckpt["optimizer_states"][0])
+            module.global_step = step = int(ckpt.get("global_step", 0))
+            first_epoch = int(ckpt.get("epoch", -1)) + 1
+        history = []
+        for epoch in range(first_epoch, self.max_epochs):
             module.current_epoch = epoch
             module.train()
             for batch_idx, batch in enumerate(datamodule.train_dataloader()):
@@ -189,7 +215,8 @@ class Trainer:
                 loss.backward()
                 if fused:
                     # gradients already live in one flat buffer: all-reduce it in place (sum; the 1/world factor and
-                    # the clip coefficient are folded into the Adam kernel)
+                    # the clip coefficient are folded into the Adam kernel).  flat_grads() is idempotent within a step,
+                    # so the optimizer.step() inside the module's optimizer_step hook consumes this reduced tensor.
                     if self.world_size > 1:
                         dist.all_reduce(self.optimizer.flat_grads())
                 else:
@@ -224,7 +251,7 @@ class Trainer:
         self._attach(module, datamodule)
         datamodule.setup("test")
         if ckpt_path:
-            module.load_state_dict(torch.load(ckpt_path, map_location=self._device)["state_dict"])
+            module.load_state_dict(torch.load(ckpt_path, map_location=self._device, weights_only=False)["state_dict"])
         module.eval()
         outs = [module.test_step(self._to_device(b), i) for i, b in enumerate(datamodule.test_dataloader())]
         return outs, self.epoch_metrics()

@@ -88,10 +88,10 @@ def _conv(x: Tensor, w: Optional[Tensor], b: Optional[Tensor], up=False, down=Fa
     `down` as a stride-2 depthwise conv (= 2x2 mean); both happen BEFORE the kxk filter."""
     c = x.shape[1]
     if up:
-        f = torch.full((c, 1, 2, 2), 1.0, dtype=x.dtype)
+        f = torch.full((c, 1, 2, 2), 1.0, dtype=x.dtype, device=x.device)
         x = F.conv_transpose2d(x, f, groups=c, stride=2)
     if down:
-        f = torch.full((c, 1, 2, 2), 0.25, dtype=x.dtype)
+        f = torch.full((c, 1, 2, 2), 0.25, dtype=x.dtype, device=x.device)
         x = F.conv2d(x, f, groups=c, stride=2)
     if w is not None:
         x = F.conv2d(x, w.to(x.dtype), padding=w.shape[-1] // 2)
@@ -141,7 +141,7 @@ def unet_forward(sd: Dict[str, Tensor], model_cfg, x: Tensor, noise_labels: Tens
     `x_self_cond` (zeros when None) in front of x (:321-324)."""
     ch = model_cfg["ch"]
     half = ch // 2
-    freqs = torch.arange(half).to(noise_labels.dtype) / half          # PositionalEmbedding, :192-199
+    freqs = torch.arange(half, device=noise_labels.device).to(noise_labels.dtype) / half          # PositionalEmbedding, :192-199
     freqs = (1 / 10000) ** freqs
     e = noise_labels.ger(freqs)
     emb = torch.cat([e.cos(), e.sin()], dim=1)
@@ -152,7 +152,7 @@ def unet_forward(sd: Dict[str, Tensor], model_cfg, x: Tensor, noise_labels: Tens
     cc = model_cfg.get("cond_channels", 0) if model_cfg.get("cat_cond", False) else 0
     if cc > 0:
         if cond is None:
-            cond = torch.zeros(x.shape[0], cc, x.shape[2], x.shape[3], dtype=x.dtype)
+            cond = torch.zeros(x.shape[0], cc, x.shape[2], x.shape[3], dtype=x.dtype, device=x.device)
         x = torch.cat([cond, x], dim=1)                                 # :327-332, order [cond, x]
     plan = unet_plan(model_cfg)
     skips = []

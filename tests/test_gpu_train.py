@@ -405,7 +405,7 @@ def test_fused_optimizer_step_and_ema_inside_trainer_loop(dev):
     opt.max_grad_norm = 1.0
     p0 = [p.detach().clone() for p in pl.model.parameters()]
     e0 = [p.detach().clone() for p in pl.ema_model.ma_model.parameters()]
-    losses = []
+    losses, p_hist = [], []
     for it in range(2):
         feed = NoiseFeed(g["noise_seed"])
         pl._noise_hook = feed.hook
@@ -415,14 +415,128 @@ def test_fused_optimizer_step_and_ema_inside_trainer_loop(dev):
         loss.backward()
         pl.optimizer_step(0, it, opt)
         losses.append(float(loss))
+        p_hist.append([p.detach().clone() for p in pl.model.parameters()])
     assert losses[1] != losses[0] and all(l == l for l in losses)
     moved = torch.cat([(a - b).flatten() for a, b in zip(pl.model.parameters(), p0)])
     assert 0 < moved.abs().max().item() <= 2 * 2e-4 * 1.01          # Adam step is bounded by lr per step
-    for e, e_old, p in zip(pl.ema_model.ma_model.parameters(), e0, pl.model.parameters()):
-        assert torch.isfinite(e).all()
+    # EMA rule of ddim_blocks.py:48-56 applied after each optimizer step: ema <- 0.999 ema + 0.001 p
+    beta = pl.ema_model.beta
+    for e, e_old, p1, p2 in zip(pl.ema_model.ma_model.parameters(), e0, p_hist[0], p_hist[1]):
+        want = (e_old * beta + (1 - beta) * p1) * beta + (1 - beta) * p2
+        assert torch.allclose(e, want, rtol=0, atol=2e-7), float((e - want).abs().max())
     sd = opt.state_dict()
     assert len(sd["state"]) == len(p0) and set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
     assert float(sd["state"][0]["step"]) == 2.0
+
+
+def test_flat_grads_is_idempotent_and_consumed_by_step(dev):
+    """The tensor `FusedAdam.flat_grads()` returns first is the one `step()` consumes, on the eager autograd path too
+    (a second gather used to overwrite an all-reduced buffer with the local gradients): zeroing the fetched
+    tensor must leave the parameters untouched by the following step."""
+    from common import NoiseFeed, golden, stress_module
+
+    g = golden("train_step.pt")
+    for graph in (False, True):
+        pl, _ = stress_module()
+        pl = pl.to(dev).train()
+        pl.use_cuda_graph = graph
+        opt = pl.configure_optimizers()["optimizer"]
+        pl._noise_hook = NoiseFeed(g["noise_seed"]).hook
+        torch.manual_seed(g["cpu_seed"])
+        opt.zero_grad(set_to_none=True)
+        pl.training_step(_train_batch(g, dev), 0).backward()
+        fg = opt.flat_grads()
+        assert opt.flat_grads() is fg
+        ref = torch.cat([p.grad.flatten() for p in pl.model.parameters()])
+        assert torch.equal(fg, ref)
+        p0 = opt.flat_params().clone()
+        fg.zero_()                                   # stands in for "the all-reduce changed it"
+        opt.step()
+        assert torch.equal(opt.flat_params(), p0), "step() did not consume the tensor flat_grads() handed out"
+        assert opt._pending_g is None
+
+
+def test_fused_adam_state_dict_resumes_moments_and_step(dev):
+    """optimizer_states of a checkpoint restore FusedAdam exactly: a resumed optimizer takes the same third step."""
+    from mcedm_b200.optim import FusedAdam
+
+    def make():
+        torch.manual_seed(0)
+        return [torch.nn.Parameter(torch.randn(33, 5, device=dev)), torch.nn.Parameter(torch.randn(17, device=dev))]
+
+    gen = torch.Generator().manual_seed(5)
+    grads = [[torch.randn(33, 5, generator=gen).to(dev), torch.randn(17, generator=gen).to(dev)] for _ in range(3)]
+    pa = make()
+    oa = FusedAdam(pa, lr=1e-2)
+    for k in range(2):
+        for p, gr in zip(pa, grads[k]):
+            p.grad = gr.clone()
+        oa.step()
+        oa.zero_grad()
+    sd = {k: (v if not isinstance(v, dict) else {i: {n: (t.clone() if torch.is_tensor(t) else t) for n, t in st.items()}
+                                                  for i, st in v.items()}) for k, v in oa.state_dict().items()}
+    pb = make()
+    with torch.no_grad():
+        for b, a in zip(pb, pa):
+            b.copy_(a)
+    ob = FusedAdam(pb, lr=1e-2)
+    ob.load_state_dict(sd)
+    assert ob._steps == 2
+    for o, ps in ((oa, pa), (ob, pb)):
+        for p, gr in zip(ps, grads[2]):
+            p.grad = gr.clone()
+        o.step()
+    for a, b in zip(pa, pb):
+        assert torch.equal(a, b)
+
+
+def test_sampling_after_a_training_step_runs_the_fused_fp16_plan(dev):
+    """the training entry points leave bf16 operands selected on the engine; sampling / get_denoised
+    on the SAME engine afterwards (model.ema: False) must still run the fused fp16 inference plan: fused kernel
+    launches and the 1.4e-3-class error against the reference fixture, not the 1e-2-class unfused bf16 plan."""
+    from common import NoiseFeed, golden, stress_module
+    from mcedm_b200 import _lib
+
+    g = golden("train_step.pt")
+    d = golden("denoise.pt")
+    pl, _ = stress_module()
+    pl = pl.to(dev).train()
+    pl._noise_hook = NoiseFeed(g["noise_seed"]).hook
+    torch.manual_seed(g["cpu_seed"])
+    pl.training_step(_train_batch(g, dev), 0).backward()          # no optimizer step: the weights stay the fixture's
+    eng = pl.model.engine()
+    assert eng._fmt == 0
+    pl.eval()
+    names = []
+    real = eng.lib
+
+    class Spy:
+        def __getattr__(self, n):
+            if n.startswith("mcedm_"):
+                names.append(n)
+            return getattr(real, n)
+
+    eng.lib = Spy()
+    try:
+        with torch.no_grad():
+            case = d["cases"][1]
+            D_x, _ = pl.get_denoised(pl.model, case["xt"].to(dev), torch.tensor(case["sigma"], dtype=torch.float64),
+                                     cond=case["cond"].to(dev), w=0.0)
+            err_eager = rel_l2(D_x, case["D"])
+            # the sampler's own entry (static buffers, graph off so the spy sees the launches)
+            x_in = torch.randn(1, 2, 128, 128, device=dev)
+            nl = torch.tensor([0.1], device=dev)
+            out = torch.empty(1, 2, 128, 128, device=dev)
+            eng._fmt = 0
+            names.clear()
+            eng.forward_static(x_in, nl, case["cond"].to(dev)[:1].contiguous(), out, use_graph=False)
+    finally:
+        eng.lib = real
+    _lib.check_watchdog()
+    assert eng._fmt == eng.infer_fmt == 1
+    assert names.count("mcedm_conv_rows_fused") >= 10 and names.count("mcedm_conv_flat_fused") >= 20, names
+    assert "mcedm_conv_rows" not in names and "mcedm_gn_apply" not in names
+    assert err_eager < 3e-3, err_eager
 
 
 def test_pack_plan_is_bit_identical_to_the_torch_packing(dev):

@@ -273,3 +273,60 @@ def test_reference_arm_contract_under_torchrun_env():
     d = json.loads(r.stdout)                                   # the whole of stdout is one JSON object
     assert d["impl"] == "reference" and d["unit"] == "fields/s" and d["n_gpus"] == 2 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+
+
+def test_trainer_resume_matches_uninterrupted_run(tmp_path):
+    """`Trainer.fit(ckpt_path=last.ckpt)` continues like the reference's `trainer.fit(ckpt_path=...)` (run.py:99):
+    weights, Adam moments + step counter, global step and the NEXT epoch — 2 epochs + resume for 1 == 3 epochs."""
+    from mcedm_b200.runner import ModelCheckpoint, Trainer, _ShimLightningModule
+
+    class Tiny(_ShimLightningModule):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.lin = torch.nn.Linear(4, 3)
+
+        def configure_optimizers(self):
+            return {"optimizer": torch.optim.Adam(self.parameters(), lr=1e-2)}
+
+        def training_step(self, batch, idx):
+            x, y = batch
+            loss = ((self.lin(x) - y) ** 2).mean()
+            self.log("train_loss", loss)
+            return loss
+
+        def validation_step(self, batch, idx):
+            return {}
+
+    class DM:
+        def setup(self, stage):
+            g = torch.Generator().manual_seed(3)
+            self.batches = [(torch.randn(8, 4, generator=g), torch.randn(8, 3, generator=g)) for _ in range(3)]
+
+        def train_dataloader(self):
+            return self.batches
+
+        def val_dataloader(self):
+            return []
+
+    full = Tiny()
+    Trainer(max_epochs=3, gradient_clip_val=1.0).fit(full, DM())
+    part = Tiny()
+    cb = ModelCheckpoint(dirpath=str(tmp_path), filename="{epoch}")
+    Trainer(max_epochs=2, gradient_clip_val=1.0, callbacks=[cb]).fit(part, DM())
+    assert os.path.exists(tmp_path / "epoch=0.ckpt") and os.path.exists(tmp_path / "epoch=1.ckpt")
+    ckpt = torch.load(tmp_path / "last.ckpt", weights_only=False)
+    for key in ("epoch", "global_step", "pytorch-lightning_version", "state_dict", "optimizer_states", "lr_schedulers",
+                "hyper_parameters", "loops", "callbacks"):
+        assert key in ckpt, key
+    assert ckpt["epoch"] == 1 and ckpt["global_step"] == 6
+    resumed = Tiny()
+    with torch.no_grad():
+        for p in resumed.parameters():
+            p.add_(1.0)                                         # must be overwritten by the checkpoint
+    tr = Trainer(max_epochs=3, gradient_clip_val=1.0)
+    hist = tr.fit(resumed, DM(), ckpt_path=str(tmp_path / "last.ckpt"))
+    assert len(hist) == 1 and resumed.current_epoch == 2 and resumed.global_step == 9
+    assert int(tr.optimizer.state_dict()["state"][0]["step"]) == 9
+    for a, b in zip(full.parameters(), resumed.parameters()):
+        assert torch.equal(a, b)
