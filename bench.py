@@ -661,7 +661,7 @@ def measure_training(args, cfg, dev, rank, world, barrier):
                 prefetch((i + 1) & 1)
             loss = step(e2e, i & 1)
             if e2e:
-                host_loss[i & 1].copy_(loss, non_blocking=True)      # device -> host read of the step's loss
+                host_loss[i & 1].copy_(loss.detach(), non_blocking=True)      # device -> host read of the step's loss
                 loss_done[i & 1].record()
                 if i >= 1:
                     loss_done[(i - 1) & 1].synchronize()

@@ -30,6 +30,11 @@
 #include "../../include/mcedm_b200.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
+
+#ifndef MCEDM_XF_H2
+#define MCEDM_XF_H2 0   // GroupNorm+SiLU transform in packed half arithmetic (see conv_rows.cu: +2 % speed, 2.5x the error: off)
+#endif
 
 namespace mcedm {
 
@@ -52,6 +57,7 @@ struct FlatParams {
   int out_f32;             // out is fp32 padded-flat [B*blk][N] (K-split partial) instead of 16-bit padded-flat
   int res_f32;             // res (mode 1 only) is fp32 padded-flat
   int res_pitch, res_blk;  // layout of the 16-bit residual tensor at ITS resolution: 0,0 dense NHWC, else padded-flat
+  int dbg;                 // bring-up switches (MCEDM_DBG): 1 = fp32 transform arithmetic
 };
 
 template <int N, bool FUSED>
@@ -477,6 +483,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int prow = t >> 3;
     int cur_b = -1;
     float ca[8], cb[8];
+    uint32_t ca2[4], cb2[4];
     for (int k = 0; k < n_tiles + 2; ++k) {
       const uint32_t slot = (uint32_t)k % (uint32_t)S, ph = ((uint32_t)k / (uint32_t)S) & 1u;
       mbar_wait(&c_full[slot], ph, p.err, 0x3600 + slot);
@@ -494,6 +501,11 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           for (int e = 0; e < 8; ++e) {
             ca[e] *= 0.5f;
             cb[e] *= 0.5f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ca2[e] = pack_f16x2(ca[2 * e], ca[2 * e + 1]);
+            cb2[e] = pack_f16x2(cb[2 * e], cb[2 * e + 1]);
           }
         }
         const uint32_t base = smem_u32(ring) + slot * kChunkBytes;
@@ -520,10 +532,17 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           const int pi = prow + 16 * i;
           // branch-free (lanes of a warp sit on different positions): padding positions hold zeros and get them back
           uint4 o;
-          o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], fmt);
-          o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], fmt);
-          o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], fmt);
-          o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], fmt);
+          if (MCEDM_XF_H2 && fmt == 1 && !(p.dbg & 1)) {        // MCEDM_DBG=1: fp32 transform (A/B switch)
+            o.x = silu_affine_h2(v[i].x, ca2[0], cb2[0]);
+            o.y = silu_affine_h2(v[i].y, ca2[1], cb2[1]);
+            o.z = silu_affine_h2(v[i].z, ca2[2], cb2[2]);
+            o.w = silu_affine_h2(v[i].w, ca2[3], cb2[3]);
+          } else {
+            o.x = flat_xf_pair(v[i].x, ca[0], cb[0], ca[1], cb[1], fmt);
+            o.y = flat_xf_pair(v[i].y, ca[2], cb[2], ca[3], cb[3], fmt);
+            o.z = flat_xf_pair(v[i].z, ca[4], cb[4], ca[5], cb[5], fmt);
+            o.w = flat_xf_pair(v[i].w, ca[6], cb[6], ca[7], cb[7], fmt);
+          }
           if (!ok[i]) o = v[i];
           const int off = pi * 128 + ((jc ^ (pi & 7)) << 4);
           sts128(base + off, o);
@@ -640,6 +659,7 @@ extern "C" int mcedm_conv_flat_fused(const void* src_flat16, const float* coef, 
   p.stats = stats_partial;
   p.fmt = op_fmt ? 1 : 0;
   p.coef = coef;
+  if (const char* e = getenv("MCEDM_DBG")) p.dbg = atoi(e);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (!p.out_f32 && p.res_mode == 0) return launch_flat<true, 0>(p, src_flat16, w_packed, B, blk, st);
   if (!p.out_f32 && p.res_mode == 1 && !p.res_f32) return launch_flat<true, 1>(p, src_flat16, w_packed, B, blk, st);

@@ -48,6 +48,11 @@
 #ifndef MCEDM_EPI16
 #define MCEDM_EPI16 0
 #endif
+#ifndef MCEDM_XF_H2
+#define MCEDM_XF_H2 0   // GroupNorm+SiLU transform in packed half arithmetic: 3 instructions per 2 elements instead of 9, but
+                        // measured +2 % only (the row is bounded by shared-memory bytes, not by the transform's ALU work) at
+                        // 2.5x the operand error -> off
+#endif
 
 namespace mcedm {
 
@@ -78,6 +83,7 @@ struct RowsParams {
   int nchw_c;            // FUSED N = 16 head: > 0 -> out is fp32 NCHW [B, nchw_c, H, 128] (the network output F_x)
   int dbg;               // bring-up instrumentation (MCEDM_DBG): 32 time every role's barrier waits, 64 time MMA issue / commits
   int res_pitch, res_blk; // FUSED, res_mode 2: the half-resolution residual is padded-flat (0,0: dense NHWC)
+  int row_align;          // CTA row ranges are multiples of this many rows (1, or 4: see r_begin)
 };
 
 template <int N, bool FUSED>
@@ -91,7 +97,9 @@ struct RowsCfg {
   // work per row, so there the transform is the pacer and gets eight
   static constexpr int XF_WARPS = FUSED ? ((N == 16 || (N == 64 && MCEDM_XF8)) ? 8 : 4) : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
-  static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
+  // fused N = 64: the epilogue transposes through a 16-BIT staging tile (32 pixels x 64 B per warp), see the epilogue
+  static constexpr bool EPI_H16 = FUSED && N == 64 && !MCEDM_EPI16;
+  static constexpr int STAGE_BYTES = EPI_H16 ? EPI_WARPS * 2048 : EPI_WARPS * 32 * CH * 4;
   // STACK (fused N = 64): the three vertical taps of a filter column are stacked into ONE N = 192 MMA per input row
   // (see the MMA issuer); eight 64-column accumulators then rotate through all 512 TMEM columns.
   static constexpr bool STACK = FUSED && (N == 64 || N == 16);   // N = 16: the head conv, 48 stacked B-rows
@@ -170,9 +178,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // balanced contiguous row range of this CTA
-  const long long r_begin = p.total_rows * blockIdx.x / gridDim.x;
-  const long long r_end = p.total_rows * (blockIdx.x + 1) / gridDim.x;
+  // balanced contiguous row range of this CTA, in units of `row_align` rows (4 for the fused N = 64 kernel, whose
+  // GroupNorm partial sums are accumulated per 4-row block of an image: blocks must not straddle CTAs, and a record's
+  // summation order must not depend on the batch size, which is what keeps row sharding bit-exact)
+  const long long n_units = p.total_rows / p.row_align;
+  const long long r_begin = n_units * blockIdx.x / gridDim.x * p.row_align;
+  const long long r_end = n_units * (blockIdx.x + 1) / gridDim.x * p.row_align;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_w);
@@ -494,6 +505,128 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter
     const int ew = warp - 2;                // 0 .. EPI_WARPS-1
     const int ch = ew >> 2;                 // column chunk drained by this warp
+    if constexpr (Cfg::EPI_H16) {
+      // ---------------------------------------------------------------------------------------------------------
+      // 16-bit staging.  The kernel is bounded by shared-memory BYTES per row (MMA operand fetch 120 KB + TMA 17 KB +
+      // transform 32 KB + epilogue staging; scripts/rows_ablate.py: 9.7 cycles per KB), and the fp32 staging tile
+      // (32 KB written + 32 KB read back per row) was the largest item the kernel itself controls.  Now each thread
+      // rounds its pixel's 32 accumulators to fp16 FIRST and stages 64 B (4 x 16-byte chunks, XOR-swizzled with
+      // (pixel >> 1) & 3: conflict-free both ways); after the transposition a lane owns 8 channels (16 B) of 4
+      // pixels per pass, adds bias and the residual in fp32, accumulates the GroupNorm sums, rounds again and stores
+      // 16 B (4 lanes = one pixel's 64-byte chunk, 8 pixels per store instruction).  16 KB + 16 KB per row instead of
+      // 32 + 32; half as many shared and global memory instructions.  Price: the accumulator is rounded to fp16
+      // before bias / residual are added (one extra 2^-12 relative rounding on a tensor that is stored in fp16 anyway).
+      // GroupNorm partial sums are kept in registers across the 4 rows of an image-row block and written once per
+      // block: one record per (4-row block, lane quarter) = H records per image instead of 4 H.
+      // ---------------------------------------------------------------------------------------------------------
+      const int u = lane & 3, rsub = lane >> 2;      // 16-byte channel chunk / pixel inside an 8-pixel pass
+      const int NT = p.n_total;
+      const int cg = p.n_off + ch * 32 + u * 8;      // first of this lane's 8 channels inside the out / res rows
+      float bz[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bz[e] = p.bias ? __ldg(p.bias + cg + e) : 0.f;
+      const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.res);
+      uint16_t* out16p = reinterpret_cast<uint16_t*>(p.out);
+      const uint32_t st16 = smem_u32(stage_smem) + ew * 2048;
+      uint4 rn[4];                                   // residual of the NEXT tile (requested one tile ahead)
+      auto load_res = [&](long long r) {
+        if (res_mode == 1) {
+          const long long o = (r * 128 + q * 32 + rsub) * NT + cg;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) rn[it] = *reinterpret_cast<const uint4*>(res16 + o + (long long)it * 8 * NT);
+        } else if (res_mode == 2) {
+          const int bimg = (int)(r / p.H);
+          const int y = (int)(r - (long long)bimg * p.H);
+          const long long rrow = (p.res_pitch > 0)
+                                     ? ((long long)bimg * p.res_blk + (long long)((y >> 1) + 1) * p.res_pitch) * NT + cg
+                                     : ((long long)bimg * (p.H >> 1) + (y >> 1)) * 64 * NT + cg;
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            rn[it] = *reinterpret_cast<const uint4*>(res16 + rrow + ((q * 32 + it * 8 + rsub) >> 1) * NT);
+        }
+      };
+      if (r_begin < r_end) load_res(r_begin);
+      float sa1 = 0.f, sa2 = 0.f, sb1 = 0.f, sb2 = 0.f;     // (sum, sum of squares) of this lane's two 4-channel groups
+      long long dbg_w3 = 0;
+      const long long dbg_t0 = clock64();
+      uint32_t tcount = 0;
+      for (long long r = r_begin; r < r_end; ++r, ++tcount) {
+        const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
+        uint4 rh[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) rh[it] = rn[it];
+        if (r + 1 < r_end) load_res(r + 1);
+        timed_wait(&acc_full[buf], aph, p.err, 0x2700 + buf, dbg_w3, (p.dbg & 32) != 0);
+        tc_fence_after();
+        uint32_t v[32];
+        const uint32_t acc_col = ((8u - buf) & 7u) * (uint32_t)N;          // STACK: descending tile order
+        tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + ch * 32, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(&acc_empty[buf]);
+        if (p.dbg & 2) continue;                  // bring-up: drain-only epilogue
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 o;
+          o.x = pack_f16x2(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
+          o.y = pack_f16x2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+          o.z = pack_f16x2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+          o.w = pack_f16x2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+          sts128(st16 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), o);
+        }
+        __syncwarp();
+        const long long pix0 = r * 128 + q * 32;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rsub;
+          const uint4 t = lds128(st16 + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+          float a[8];
+          {
+            const float2 t0 = unpack_f16x2(t.x), t1 = unpack_f16x2(t.y), t2 = unpack_f16x2(t.z), t3 = unpack_f16x2(t.w);
+            a[0] = t0.x + bz[0]; a[1] = t0.y + bz[1]; a[2] = t1.x + bz[2]; a[3] = t1.y + bz[3];
+            a[4] = t2.x + bz[4]; a[5] = t2.y + bz[5]; a[6] = t3.x + bz[6]; a[7] = t3.y + bz[7];
+          }
+          if (res_mode != 0) {
+            const float2 r0 = unpack_f16x2(rh[it].x), r1 = unpack_f16x2(rh[it].y), r2 = unpack_f16x2(rh[it].z),
+                         r3 = unpack_f16x2(rh[it].w);
+            a[0] += r0.x; a[1] += r0.y; a[2] += r1.x; a[3] += r1.y;
+            a[4] += r2.x; a[5] += r2.y; a[6] += r3.x; a[7] += r3.y;
+          }
+          sa1 += (a[0] + a[1]) + (a[2] + a[3]);
+          sa2 += (a[0] * a[0] + a[1] * a[1]) + (a[2] * a[2] + a[3] * a[3]);
+          sb1 += (a[4] + a[5]) + (a[6] + a[7]);
+          sb2 += (a[4] * a[4] + a[5] * a[5]) + (a[6] * a[6] + a[7] * a[7]);
+          uint4 o;
+          o.x = pack_f16x2(a[0], a[1]);
+          o.y = pack_f16x2(a[2], a[3]);
+          o.z = pack_f16x2(a[4], a[5]);
+          o.w = pack_f16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(out16p + (pix0 + rr) * NT + cg) = o;
+        }
+        if ((r & 3) == 3) {
+          // end of a 4-row block (ranges are block-aligned and H % 4 == 0, so blocks never straddle images or CTAs):
+          // lanes with equal `u` hold the same two groups
+          if (p.stats) {
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+              sa1 += __shfl_xor_sync(0xffffffffu, sa1, off);
+              sa2 += __shfl_xor_sync(0xffffffffu, sa2, off);
+              sb1 += __shfl_xor_sync(0xffffffffu, sb1, off);
+              sb2 += __shfl_xor_sync(0xffffffffu, sb2, off);
+            }
+            if (lane < 4)
+              *reinterpret_cast<float4*>(p.stats + (((r >> 2) * 4 + q) * (NT / 4) + (cg >> 2)) * 2) =
+                  make_float4(sa1, sa2, sb1, sb2);
+          }
+          sa1 = sa2 = sb1 = sb2 = 0.f;
+        }
+        __syncwarp();                              // the staging tile is rewritten by the next tile
+      }
+      if ((p.dbg & 32) && warp == 2 && lane == 0) {
+        g_rows_dbg[blockIdx.x][3] = dbg_w3;
+        g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
+      }
+    } else {
     const uint32_t my_stage = smem_u32(stage_smem) + ew * (32 * Cfg::CH * 4);
     const int unit = lane % Cfg::U;
     const int row_in_it = lane / Cfg::U;
@@ -554,6 +687,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive_warp(&acc_empty[buf]);
+      if (FUSED && (p.dbg & 2)) continue;       // bring-up: drain-only epilogue (what would a free epilogue buy?)
       if constexpr (FUSED && N == 16) {
         if (p.nchw_c > 0) {
           // output head (adm_blocks.py:403): the TMEM layout (lane = pixel) IS the NCHW order along x, so the first
@@ -625,6 +759,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       g_rows_dbg[blockIdx.x][3] = dbg_w3;
       g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
     }
+    }
   } else {
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
@@ -642,6 +777,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       const int y0 = (int)(r - (long long)b * p.H);
       const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
       float ca[2][8], cb[2][8];
+      uint32_t ca2[2][4], cb2[2][4];          // the same, pre-halved and packed fp16 (MCEDM_XF_H2)
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         if (s < n_halo && p.coef[0] != nullptr) {
@@ -655,6 +791,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           for (int e = 0; e < 8; ++e) {
             ca[s][e] *= 0.5f;
             cb[s][e] *= 0.5f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ca2[s][e] = pack_f16x2(ca[s][2 * e], ca[s][2 * e + 1]);
+            cb2[s][e] = pack_f16x2(cb[s][2 * e], cb[s][2 * e + 1]);
           }
         }
       }
@@ -677,10 +818,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
               for (int i = 0; i < XF_IT; ++i) {
                 const int px = 1 + prow + XF_ROWS * i;
                 uint4 o;
-                o.x = xf_pair(v[i].x, ca[s][0], cb[s][0], ca[s][1], cb[s][1], fmt);
-                o.y = xf_pair(v[i].y, ca[s][2], cb[s][2], ca[s][3], cb[s][3], fmt);
-                o.z = xf_pair(v[i].z, ca[s][4], cb[s][4], ca[s][5], cb[s][5], fmt);
-                o.w = xf_pair(v[i].w, ca[s][6], cb[s][6], ca[s][7], cb[s][7], fmt);
+                if (MCEDM_XF_H2 && fmt == 1 && !(p.dbg & 1)) {      // MCEDM_DBG=1: fp32 transform (A/B switch)
+                  o.x = silu_affine_h2(v[i].x, ca2[s][0], cb2[s][0]);
+                  o.y = silu_affine_h2(v[i].y, ca2[s][1], cb2[s][1]);
+                  o.z = silu_affine_h2(v[i].z, ca2[s][2], cb2[s][2]);
+                  o.w = silu_affine_h2(v[i].w, ca2[s][3], cb2[s][3]);
+                } else {
+                  o.x = xf_pair(v[i].x, ca[s][0], cb[s][0], ca[s][1], cb[s][1], fmt);
+                  o.y = xf_pair(v[i].y, ca[s][2], cb[s][2], ca[s][3], cb[s][3], fmt);
+                  o.z = xf_pair(v[i].z, ca[s][4], cb[s][4], ca[s][5], cb[s][5], fmt);
+                  o.w = xf_pair(v[i].w, ca[s][6], cb[s][6], ca[s][7], cb[s][7], fmt);
+                }
                 sts128(base + px * 128 + ((j ^ (px & 7)) << 4), o);
               }
             }
@@ -728,7 +876,8 @@ static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const C
     MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  long long grid = p.total_rows < num_sms() ? p.total_rows : num_sms();
+  const long long units = p.total_rows / p.row_align;
+  long long grid = units < num_sms() ? units : num_sms();
   conv_rows_kernel<N, FUSED, RM><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
@@ -745,6 +894,8 @@ static int rows_common(RowsParams& p, CUtensorMap& tm_w, CUtensorMap* tm_h, CUte
   p.n_ctr = n_ctr;
   p.H = H;
   p.total_rows = (long long)B * H;
+  if (p.row_align < 1) p.row_align = 1;
+  MCEDM_REQUIRE(H % p.row_align == 0, "conv_rows: H=%d must be a multiple of %d for this kernel", H, p.row_align);
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "conv_rows: cannot allocate the watchdog word");
   int rc = make_tmap_rows64_bf16(&tm_w, w_packed, (long long)(n_halo * 9 + n_ctr) * p.w_rows, N);
@@ -809,6 +960,7 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
   p.w_rows = n_total;
   p.res_pitch = res_pitch;
   p.res_blk = res_blk;
+  p.row_align = (N == 64 && !MCEDM_EPI16) ? 4 : 1;     // GroupNorm records per 4-row block (see the epilogue)
   if (const char* e = getenv("MCEDM_DBG")) p.dbg = atoi(e);
   for (int i = 0; i < n_halo && i < 2; ++i) {
     p.coef[i] = halo_coef ? halo_coef[i] : nullptr;      // all NULL: the sources are already-normalised operands

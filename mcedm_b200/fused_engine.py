@@ -117,7 +117,7 @@ class FusedMixin:
                                                        64, 0, 64, L.ptr(out.t), 1, L.ptr(res.t) if res is not None else None,
                                                        res_mode, rp, rb, L.ptr(out.st) if stats else None, self._fmt, st),
                         "conv_rows_fused")
-            out.parts = 4 * H
+            out.parts = H        # one record per (4-row block, TMEM lane quarter): H / 4 * 4 per image
             return
         # ---------------- W <= 64: padded-flat kernel
         pitch, blk = out.flat
