@@ -69,7 +69,7 @@ struct FlatCfg {
   static constexpr int EPI_WARPS = 4 * NCH;
   static constexpr int XF_WARPS = FUSED ? 4 : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
-  static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;
+  static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;   // (the 16-bit fast-path epilogue uses half of it)
   static constexpr int ACC_BUFS = 4;
   static constexpr int TMEM_COLS = (ACC_BUFS * N <= 256) ? 256 : 512;
 };
@@ -292,39 +292,49 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // lane needs one base offset per tile and immediate offsets per row; padding rows are stored as zeros (which is
     // what they hold anyway) instead of being branched around, and add nothing to the statistics.
     if constexpr (FUSED && (FM == 0 || FM == 1)) {
+      // 16-bit staging, as in conv_rows.cu (the kernel is bounded by shared-memory bytes per tile): the thread rounds
+      // its position's 32 accumulators to fp16 and stages 64 B (XOR-swizzled 16-byte chunks); after the transposition a
+      // lane owns 8 channels of 4 positions per pass, adds bias / residual in fp32, accumulates the GroupNorm sums,
+      // rounds again and stores 16 B.  Half the staging bytes, half the shared / global memory instructions.
       const uint16_t* r16 = reinterpret_cast<const uint16_t*>(p.res);
       uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out);
       constexpr bool has_res = FM == 1;
-      uint2 rn[8];
-      long long base = ((t_begin * 128) + q * 32 + row_in_it) * N + c0;     // element offset of this lane's first row
+      const int u = lane & 3, rsub = lane >> 2;
+      const int cc = ch * Cfg::CH + u * 8;                                   // first of this lane's 8 channels
+      const uint32_t st16 = smem_u32(stage_smem) + ew * 2048;
+      float bz8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bz8[e] = p.bias ? __ldg(p.bias + cc + e) : 0.f;
+      uint4 rn[4];
+      long long base = ((t_begin * 128) + q * 32 + rsub) * N + cc;          // element offset of this lane's first row
       if (has_res && n_tiles > 0) {
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) rn[itr] = *reinterpret_cast<const uint2*>(r16 + base + itr * 4 * N);
+        for (int it = 0; it < 4; ++it) rn[it] = *reinterpret_cast<const uint4*>(r16 + base + it * 8 * N);
       }
       int tin = (int)(t_begin % p.tiles_per_img);                            // tile index inside its image
       for (int j = 0; j < n_tiles; ++j, base += 128 * N) {
         const long long tile = t_begin + j;
         const uint32_t buf = (uint32_t)j % Cfg::ACC_BUFS, aph = ((uint32_t)j / Cfg::ACC_BUFS) & 1u;
-        // validity of the lane's 8 rows (4 positions apart): one division per tile
-        const int pos = tin * 128 + q * 32 + row_in_it;
+        // validity of the lane's 4 rows (8 positions apart; P >= 17: at most one row wrap per step): one division per tile
+        const int pos = tin * 128 + q * 32 + rsub;
         int row = pos / p.P;
         int x = pos - row * p.P;
         uint32_t vmask = 0;
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr, x += 4) {
+        for (int it = 0; it < 4; ++it, x += 8) {
           if (x >= p.P) {
             x -= p.P;
             ++row;
           }
-          vmask |= ((row >= 1) && (row <= p.H) && (x < p.W)) ? (1u << itr) : 0u;
+          vmask |= ((row >= 1) && (row <= p.H) && (x < p.W)) ? (1u << it) : 0u;
         }
         if (++tin == p.tiles_per_img) tin = 0;
-        uint2 rh[8];
+        uint4 rh[4];
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) rh[itr] = rn[itr];
+        for (int it = 0; it < 4; ++it) rh[it] = rn[it];
         if (has_res && j + 1 < n_tiles) {
 #pragma unroll
-          for (int itr = 0; itr < 8; ++itr) rn[itr] = *reinterpret_cast<const uint2*>(r16 + base + (128 + itr * 4) * N);
+          for (int it = 0; it < 4; ++it) rn[it] = *reinterpret_cast<const uint4*>(r16 + base + (128 + it * 8) * N);
         }
         mbar_wait(&acc_full[buf], aph, p.err, 0x3500 + buf);
         tc_fence_after();
@@ -334,39 +344,57 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         tc_fence_before();
         mbar_arrive_warp(&acc_empty[buf]);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int pj = jj ^ (lane & 7);
-          sts128(my_stage + lane * 128 + pj * 16, make_uint4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]));
+        for (int c = 0; c < 4; ++c) {
+          uint4 o;
+          o.x = pack_f16x2(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
+          o.y = pack_f16x2(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+          o.z = pack_f16x2(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+          o.w = pack_f16x2(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+          sts128(st16 + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), o);
         }
         __syncwarp();
-        float s1 = 0.f, s2 = 0.f;
+        float sa1 = 0.f, sa2 = 0.f, sb1 = 0.f, sb2 = 0.f;
 #pragma unroll
-        for (int itr = 0; itr < 8; ++itr) {
-          const int rw = itr * 4 + row_in_it;
-          const int pu = unit ^ (rw & 7);
-          float4 a = lds128f(my_stage + rw * 128 + pu * 16);
-          a.x += bz.x; a.y += bz.y; a.z += bz.z; a.w += bz.w;
-          if (has_res) {
-            const float4 r = flat_unpack4(rh[itr], fmt);
-            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rsub;
+          const uint4 t = lds128(st16 + rr * 64 + ((u ^ ((rr >> 1) & 3)) << 4));
+          const float m = (vmask >> it) & 1u ? 1.0f : 0.0f;                  // padding positions are stored as zeros
+          float a[8];
+          {
+            const float2 t0 = unpack_f16x2(t.x), t1 = unpack_f16x2(t.y), t2 = unpack_f16x2(t.z), t3 = unpack_f16x2(t.w);
+            a[0] = t0.x + bz8[0]; a[1] = t0.y + bz8[1]; a[2] = t1.x + bz8[2]; a[3] = t1.y + bz8[3];
+            a[4] = t2.x + bz8[4]; a[5] = t2.y + bz8[5]; a[6] = t3.x + bz8[6]; a[7] = t3.y + bz8[7];
           }
-          const float m = (vmask >> itr) & 1u ? 1.0f : 0.0f;
-          a.x *= m; a.y *= m; a.z *= m; a.w *= m;
-          s1 += (a.x + a.y) + (a.z + a.w);
-          s2 += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
-          uint2 o;
-          o.x = pack_op2(a.x, a.y, fmt);
-          o.y = pack_op2(a.z, a.w, fmt);
-          *reinterpret_cast<uint2*>(o16 + base + itr * 4 * N) = o;
+          if (has_res) {
+            const float2 r0 = unpack_f16x2(rh[it].x), r1 = unpack_f16x2(rh[it].y), r2 = unpack_f16x2(rh[it].z),
+                         r3 = unpack_f16x2(rh[it].w);
+            a[0] += r0.x; a[1] += r0.y; a[2] += r1.x; a[3] += r1.y;
+            a[4] += r2.x; a[5] += r2.y; a[6] += r3.x; a[7] += r3.y;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[e] *= m;
+          sa1 += (a[0] + a[1]) + (a[2] + a[3]);
+          sa2 += (a[0] * a[0] + a[1] * a[1]) + (a[2] * a[2] + a[3] * a[3]);
+          sb1 += (a[4] + a[5]) + (a[6] + a[7]);
+          sb2 += (a[4] * a[4] + a[5] * a[5]) + (a[6] * a[6] + a[7] * a[7]);
+          uint4 o;
+          o.x = pack_f16x2(a[0], a[1]);
+          o.y = pack_f16x2(a[2], a[3]);
+          o.z = pack_f16x2(a[4], a[5]);
+          o.w = pack_f16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(o16 + base + it * 8 * N) = o;
         }
         if (p.stats) {
 #pragma unroll
-          for (int off = 8; off < 32; off <<= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+          for (int off = 4; off < 32; off <<= 1) {
+            sa1 += __shfl_xor_sync(0xffffffffu, sa1, off);
+            sa2 += __shfl_xor_sync(0xffffffffu, sa2, off);
+            sb1 += __shfl_xor_sync(0xffffffffu, sb1, off);
+            sb2 += __shfl_xor_sync(0xffffffffu, sb2, off);
           }
-          if (lane < 8)
-            *reinterpret_cast<float2*>(p.stats + ((tile * 4 + q) * (N / 4) + ch * 8 + lane) * 2) = make_float2(s1, s2);
+          if (lane < 4)
+            *reinterpret_cast<float4*>(p.stats + ((tile * 4 + q) * (N / 4) + ch * 8 + u * 2) * 2) =
+                make_float4(sa1, sa2, sb1, sb2);
         }
         __syncwarp();
       }
