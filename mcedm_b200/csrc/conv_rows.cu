@@ -65,7 +65,7 @@ struct RowsParams {
   int n_halo;            // 1..2 sources with 9 taps each
   int n_ctr;             // 0..2 centre-tap sources
   int n_slots;           // halo ring depth (input rows)
-  int n_cslots;          // centre ring depth (output rows)
+  int n_cslots;          // centre ring depth in 16 KB TILES (one tile = one centre source of one output row)
   int H;                 // image height; W == 128
   long long total_rows;  // B * H
   const float* bias;
@@ -160,11 +160,10 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_seg = n_halo * 9 + p.n_ctr;
   const int slot_bytes = n_halo * kHaloBytes;
-  const int cslot_bytes = p.n_ctr * kCtrBytes;
   uint8_t* w_smem = smem;
   uint8_t* h_smem = w_smem + n_seg * Cfg::W_SEG_BYTES;
   uint8_t* c_smem = h_smem + p.n_slots * slot_bytes;
-  uint8_t* stage_smem = c_smem + p.n_cslots * cslot_bytes;
+  uint8_t* stage_smem = c_smem + p.n_cslots * kCtrBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + Cfg::STAGE_BYTES);
   uint64_t* w_full = bars;
   uint64_t* acc_full = bars + 1;                     // ACC_BUFS
@@ -239,12 +238,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             tma_load_4d(h_smem + slot * slot_bytes + kHaloBytes, &tm_h1, &h_full[slot], 0, -1, y0 - 1 + k, b);
           ++hl;
           if (p.n_ctr > 0 && k >= 2) {
-            const uint32_t cs = cl % (uint32_t)p.n_cslots, cph = (cl / (uint32_t)p.n_cslots) & 1u;
-            mbar_wait(&c_empty[cs], cph ^ 1u, p.err, 0x2200 + cs);
-            mbar_expect_tx(&c_full[cs], (uint32_t)(p.n_ctr * kCtrBytes));
-            tma_load_4d(c_smem + cs * cslot_bytes, &tm_c0, &c_full[cs], 0, 0, y0 + k - 2, b);
-            if (p.n_ctr > 1) tma_load_4d(c_smem + cs * cslot_bytes + kCtrBytes, &tm_c1, &c_full[cs], 0, 0, y0 + k - 2, b);
-            ++cl;
+            // the centre ring is tile-granular (one 16 KB tile per source and output row), so with n_ctr + 1 tiles the
+            // next row's first source is already in flight while this row's tiles are consumed (a ring of whole rows
+            // needed 2 x n_ctr tiles for any overlap, which the resident weights leave no room for)
+            for (int s = 0; s < p.n_ctr; ++s, ++cl) {
+              const uint32_t cs = cl % (uint32_t)p.n_cslots, cph = (cl / (uint32_t)p.n_cslots) & 1u;
+              mbar_wait(&c_empty[cs], cph ^ 1u, p.err, 0x2200 + cs);
+              mbar_expect_tx(&c_full[cs], (uint32_t)kCtrBytes);
+              tma_load_4d(c_smem + cs * kCtrBytes, s == 0 ? &tm_c0 : &tm_c1, &c_full[cs], 0, 0, y0 + k - 2, b);
+            }
           }
         }
         r += R;
@@ -301,7 +303,18 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
           timed_wait(&h_ready[hs], hph, p.err, 0x2500 + hs, dbg_w2, (p.dbg & 32) != 0);
           const bool ctr_now = p.n_ctr > 0 && k >= 2;      // centre tiles of output row k-2, just before it completes
-          if (ctr_now) mbar_wait(&c_full[cs], cph, p.err, 0x2600 + cs);
+          uint32_t cidx[2] = {0u, 0u};
+          if (ctr_now) {
+            uint32_t c = cs, ph = cph;
+            for (int s = 0; s < p.n_ctr; ++s) {
+              mbar_wait(&c_full[c], ph, p.err, 0x2600 + c);
+              cidx[s] = c;
+              if (++c == (uint32_t)p.n_cslots) {
+                c = 0;
+                ph ^= 1u;
+              }
+            }
+          }
           tc_fence_after();
           const uint32_t a_row = h_lo + hs * slot16;
           const int kyA = k - (R - 1) > 0 ? k - (R - 1) : 0;   // output row k - ky must lie in [0, R)
@@ -361,12 +374,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
               if (ctr_now) {
                 const uint32_t blk = (8u - (td & 7u)) & 7u;
                 for (int s = 0; s < p.n_ctr; ++s) {
-                  const uint64_t ad = desc(c_lo + ((cs * (uint32_t)cslot_bytes + s * kCtrBytes) >> 4));
+                  const uint64_t ad = desc(c_lo + cidx[s] * (uint32_t)(kCtrBytes >> 4));
                   const uint64_t bd = desc(w_lo + (9 + s) * (Cfg::W_SEG_BYTES >> 4));
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_base + blk * (uint32_t)N, ad + 2 * ks, bd + 2 * ks, idesc1, 1u);
+                  umma_commit(&c_empty[cidx[s]]);
                 }
-                umma_commit(&c_empty[cs]);
               }
               umma_commit(&acc_full[td & 7u]);
             }
@@ -381,9 +394,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             hs = 0;
             hph ^= 1u;
           }
-          if (ctr_now && ++cs == (uint32_t)p.n_cslots) {
-            cs = 0;
-            cph ^= 1u;
+          if (ctr_now) {
+            for (int s = 0; s < p.n_ctr; ++s) {
+              if (++cs == (uint32_t)p.n_cslots) {
+                cs = 0;
+                cph ^= 1u;
+              }
+            }
           }
         }
         t0 += (uint32_t)R;
@@ -463,20 +480,29 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
               }
             }
           }
+          uint32_t cidx[2] = {0u, 0u};
           if (p.n_ctr > 0) {
-            // centre tiles last: their (single-buffered) slot is the one most likely to be late
-            mbar_wait(&c_full[cs], cph, p.err, 0x2600 + cs);
+            // centre tiles last: they are the ones most likely to be late
+            uint32_t c = cs, ph = cph;
+            for (int s = 0; s < p.n_ctr; ++s) {
+              mbar_wait(&c_full[c], ph, p.err, 0x2600 + c);
+              cidx[s] = c;
+              if (++c == (uint32_t)p.n_cslots) {
+                c = 0;
+                ph ^= 1u;
+              }
+            }
             tc_fence_after();
           }
           if (elect_one()) {
             if (p.n_ctr > 0) {
               for (int s = 0; s < p.n_ctr; ++s) {
-                const uint64_t ad = desc(c_lo + ((cs * (uint32_t)cslot_bytes + s * kCtrBytes) >> 4));
+                const uint64_t ad = desc(c_lo + cidx[s] * (uint32_t)(kCtrBytes >> 4));
                 const uint64_t bd = desc(w_lo + (n_halo * 9 + s) * (Cfg::W_SEG_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                umma_commit(&c_empty[cidx[s]]);
               }
-              umma_commit(&c_empty[cs]);
             }
             // input row s0 has no further user; the last output row of a segment also frees the two rows below it
             umma_commit(&h_empty[s0]);
@@ -488,9 +514,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
           __syncwarp();
           s0 = s1;
-          if (p.n_ctr > 0 && ++cs == (uint32_t)p.n_cslots) {
-            cs = 0;
-            cph ^= 1u;
+          for (int s = 0; s < p.n_ctr; ++s) {
+            if (++cs == (uint32_t)p.n_cslots) {
+              cs = 0;
+              cph ^= 1u;
+            }
           }
         }
         // the next segment starts two rows further on (its own top halo row and the one above it)
@@ -857,20 +885,29 @@ static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const C
   const int n_seg = p.n_halo * 9 + p.n_ctr;
   const int fixed = 1024 + n_seg * Cfg::W_SEG_BYTES + Cfg::STAGE_BYTES + 512;
   const int slot_bytes = p.n_halo * kHaloBytes;
-  p.n_cslots = p.n_ctr ? 2 : 0;
-  int avail = 232448 - fixed - p.n_cslots * p.n_ctr * kCtrBytes;
-  int slots = avail / slot_bytes;
-  if (slots < (FUSED ? 5 : 4) && p.n_ctr) {            // trade the centre double-buffer for halo depth
-    p.n_cslots = 1;
-    avail = 232448 - fixed - p.n_cslots * p.n_ctr * kCtrBytes;
-    slots = avail / slot_bytes;
+  // centre ring: 2 x n_ctr tiles if the halo ring keeps its preferred depth, else n_ctr + 1 (still one tile of
+  // look-ahead), else n_ctr (MCEDM_CSLOTS overrides, bring-up)
+  const int min_pref = FUSED ? 5 : 4, min_ok = FUSED ? 4 : 3;
+  int slots = 0;
+  p.n_cslots = 0;
+  const int cand[3] = {2 * p.n_ctr, p.n_ctr + 1, p.n_ctr};
+  int forced = 0;
+  if (const char* e = getenv("MCEDM_CSLOTS")) forced = atoi(e);
+  for (int i = 0; i < 3; ++i) {
+    const int nc = forced >= p.n_ctr && p.n_ctr > 0 ? forced : cand[i];
+    const int sl = (232448 - fixed - nc * kCtrBytes) / slot_bytes;
+    if (sl >= (i == 0 ? min_pref : min_ok) || i == 2 || forced) {
+      p.n_cslots = nc;
+      slots = sl;
+      break;
+    }
   }
   if (slots > 8) slots = 8;
   MCEDM_REQUIRE(slots >= (FUSED ? 4 : 3),
                 "conv_rows: %d halo sources + %d centre sources with N=%d do not fit in shared memory", p.n_halo,
                 p.n_ctr, N);
   p.n_slots = slots;
-  const int smem = fixed + slots * slot_bytes + p.n_cslots * p.n_ctr * kCtrBytes;
+  const int smem = fixed + slots * slot_bytes + p.n_cslots * kCtrBytes;
   static bool attr_set = false;
   if (!attr_set) {
     MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
