@@ -448,6 +448,35 @@ MCEDM_API int mcedm_pack_gather(const float* base, const long long* idx_a, const
                                 long long n32, int fmt, void* dst16, float* dst32, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* K7  DDPM U-Net pieces (models/ddim_blocks.py:222-470 `Model`; its convolutions and attention run   */
+/*     on the K1f / K3 kernels above)                                                               */
+/* -------------------------------------------------------------------------------------------- */
+/* Per-(sample, channel) statistics of a raw 16-bit activation [B][positions_per_img][64] (dense NHWC: H*W positions;
+ * padded-flat: block positions, whose stored zeros add nothing): partial fp32 [B][n_split][64][2] = (sum, sum of squares)
+ * over the n_split position ranges of each image.  Replaces the statistics half of Normalize (ddim_blocks.py:60-61,
+ * GroupNorm(32, eps 1e-6): 2 channels per group at 64 channels — finer than the conv epilogues' 4-channel records). */
+MCEDM_API int mcedm_gn_stats16(const void* x16, long long positions_per_img, int B, int op_fmt, int n_split,
+                               float* partial, void* stream);
+/* coef_out fp32 [B][128] = (a | b) of y = act(a*x + b) == act(GroupNorm(x + shift)) for groups of channels_per_group
+ * consecutive channels of this 64-channel tensor (gamma / beta fp32 [64]: the tensor's slice of a wider norm),
+ * pixels_per_img = H*W data positions.  shift NULL, or fp32 [B or 1][64] (shift_batch_stride 64 or 0): the per-sample
+ * temb_proj(swish(temb)) term ResnetBlock adds between conv1 and norm2 (ddim_blocks.py:140-146), folded into the
+ * statistics and into b so that x + shift is never materialised. */
+MCEDM_API int mcedm_gn_coef_groups(const float* partial, int n_split, long long pixels_per_img, const float* gamma,
+                                   const float* beta, int channels_per_group, float eps, const float* shift,
+                                   int shift_batch_stride, int B, float* coef_out, void* stream);
+/* out16[b, i, j, :] = src16[b, 2i+1, 2j+1, :] (64 channels, 16-bit), each side dense NHWC (pitch 0) or padded-flat:
+ * the sampling half of Downsample (ddim_blocks.py:97-101: pad (0,1,0,1) + stride-2 3x3 conv == the stride-1 same conv at
+ * the odd positions). */
+MCEDM_API int mcedm_decimate16(const void* src16, int in_pitch, int in_blk, int B, int H, int W, void* out16,
+                               int out_pitch, int out_blk, void* stream);
+/* Timestep embedding (ddim_blocks.py:12-30, :422-425) and every ResnetBlock's temb_proj(swish(temb)) (:140):
+ * t fp32 [Bt]; w0 [256][64], w1 [256][256]; w_proj [n_blocks][64][256], b_proj [n_blocks][64];
+ * out fp32 [n_blocks][Bt][64]. */
+MCEDM_API int mcedm_ddpm_temb(const float* t, int Bt, const float* w0, const float* b0, const float* w1, const float* b1,
+                              const float* w_proj, const float* b_proj, int n_blocks, float* out, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* bring-up / checker kernels (tests only; not on the product path)                              */
 /* -------------------------------------------------------------------------------------------- */
 /* tensor-pipe + shared-memory operand-fetch ceiling: every SM issues n_tiles x 36 tcgen05.mma (M=128, N, K=16, the conv

@@ -81,6 +81,10 @@ _PROTOTYPES = {
                           _vp],
     "mcedm_swe_fv_grad": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp],
     "mcedm_darcy_loss": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _i, _i, _f, _vp, _vp, _vp, _vp],
+    "mcedm_gn_stats16": [_vp, C.c_longlong, _i, _i, _i, _vp, _vp],
+    "mcedm_gn_coef_groups": [_vp, _i, C.c_longlong, _vp, _vp, _i, _f, _vp, _i, _i, _vp, _vp],
+    "mcedm_decimate16": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp],
+    "mcedm_ddpm_temb": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
     "mcedm_probe_mma_queue": [_i, _i, _i, _vp, _vp],
     "mcedm_debug_rows": [_vp],

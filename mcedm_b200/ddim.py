@@ -10,8 +10,9 @@ RePaint-style conditioning — BASELINE config 4 (`diff_sampler=edm_sampler, n_t
     test_step (MAE / masked MAE / known-region metrics)                    :372-533 (core metrics)
 
 The reference builds the network from `hparams.name`: `DhariwalUNet` when it starts with "adm", the DDPM U-Net
-`ddim_blocks.Model` otherwise (:40-43).  Only the ADM branch has kernels here (`configs/config_adm_ddim_res32.yaml`);
-the DDPM U-Net (stride-2 convs, 32-group GroupNorm, 256-wide time embedding) is SURVEY §8f rank 2 and raises.
+`ddim_blocks.Model` otherwise (:40-43).  Both run on the kernels: `configs/config_adm_ddim_res32.yaml` (ADM branch) and
+the shipped `configs/config_ddim_res32.yaml` (`ddpm_blocks.Model` on `ddpm_engine.DdpmEngine`: stride-2 convs, 32-group
+GroupNorm, 256-wide time embedding).
 
 Kernel path: the Heun updates are the PlMcedm kernels with an all-ones mask (exact: `*1.0`), `c_skip = 1`,
 `c_out = -sigma`; the known-region handling is `mcedm_edm_vp_init` / `mcedm_edm_repaint_blend` (mask == 1 means KNOWN
@@ -58,10 +59,7 @@ def _f32(x) -> np.float32:
 
 class PlDdim(PlMcedm):
     def __init__(self, hparams):
-        if not hparams.name.startswith("adm"):
-            raise NotImplementedError("PlDdim: only the ADM U-Net branch (hparams.name 'adm*', models/ddim.py:40-41) has "
-                                      "kernels; the DDPM U-Net (ddim_blocks.Model) is SURVEY §8f rank 2")
-        super().__init__(hparams)
+        super().__init__(hparams)                                     # 'adm*' -> DhariwalUNet, else ddim_blocks.Model (:40-43)
         self.cond_p = 0.0                                             # :30
         self.model_var_type = hparams.model.var_type
         betas, posterior_variance = self.get_diffusion_schedule(hparams)

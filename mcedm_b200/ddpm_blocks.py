@@ -5,9 +5,10 @@ default) initialisation drawn in the same order, so `torch.manual_seed(s)` gives
 code bases and reference checkpoints of the `config_ddim_res32*` / `config_edm_res32_cond_h` experiments load with
 `strict=True` (tests/test_host_logic.py::test_ddpm_model_mirror_state_dict).
 
-There are NO kernels for this network yet: `forward` raises.  The CPU oracle of its arithmetic
-(oracle/ddpm_oracle.py) and the fixtures from the unmodified reference (tests/golden/ddpm_path.pt) are in place;
-DESIGN.md §8 item 2 lists how its layers map onto the existing kernels and which pieces are new.
+`forward` runs the sm_100a launch plan of `ddpm_engine.DdpmEngine` (the fused 16-bit convolution / attention kernels
+of the ADM path + csrc/ddpm.cu: per-channel GroupNorm(32, eps 1e-6) statistics, temb folded into norm2's coefficients,
+decimating Downsample, timestep MLP); the sub-modules below are parameter containers only.  Checked against the
+fixtures from the unmodified reference (tests/golden/ddpm_path.pt) by tests/test_gpu_ddim.py.
 """
 from __future__ import annotations
 
@@ -146,7 +147,52 @@ class Model(nn.Module):
 
         self.norm_out = Normalize(block_in)
         self.conv_out = nn.Conv2d(block_in, out_channels, kernel_size=3, stride=1, padding=1)
+        # what the samplers / engine read (same names as DhariwalUNet)
+        self.attn_resolutions = list(attn_resolutions)
+        self.resamp_with_conv = resamp_with_conv
+        self.x_channels = m.in_channels
+        self.out_channels = out_channels
+        self.cat_channels = self.in_channels - m.in_channels          # self-conditioning copy + concatenated condition
+        self._engine = None
+
+    # the engine holds packed 16-bit weights and workspaces; it is not part of the module state
+    def engine(self):
+        if self._engine is None:
+            from .ddpm_engine import DdpmEngine
+
+            self._engine = DdpmEngine(self)
+        return self._engine
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        return d
 
     def forward(self, x, t, cond=None, x_self_cond=None, dx=None):
-        raise NotImplementedError("the DDPM U-Net has no sm_100a kernel path yet (SURVEY §8f rank 2): parameters, oracle "
-                                  "and fixtures only; use an `adm*` experiment (DhariwalUNet)")
+        """Model.forward (ddim_blocks.py:415-470): x [B,C,128,128] fp32 CUDA, t [B] or [1] (timestep / c_noise),
+        cond concatenated in front when `cat_cond`, x_self_cond (zeros when None) in front of x when `self_cond`
+        (cat_conditioning, :378-390).  Returns [B,out_ch,128,128] fp32.  Inference only: no backward kernels."""
+        if dx is not None:
+            raise NotImplementedError("dx conditioning is not supported")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the DDPM U-Net has an inference launch plan only (PlDdim's DDPM training loss is "
+                                      "outside the hot path); call it in eval mode / under torch.no_grad()")
+        cat_in = None
+        if self.self_condition:
+            cat_in = torch.zeros_like(x) if x_self_cond is None else x_self_cond
+        elif x_self_cond is not None:
+            raise ValueError("x_self_cond given to a network built without self_cond")
+        if self.cat_condition and self.cond_channels > 0:
+            if cond is None:
+                cond = torch.zeros(x.shape[0], self.cond_channels, x.shape[2], x.shape[3], device=x.device, dtype=x.dtype)
+            cat_in = cond if cat_in is None else torch.cat([cond, cat_in], dim=1)
+        return self.engine().forward(x, t, cat_in)

@@ -76,10 +76,12 @@ class PlMcedm(LightningModule):
             m.cond_channels = m.cond_channels + 2                  # :32-34
         if self.dx_cond:
             raise NotImplementedError("dx_cond (PDE-gradient conditioning) has no sm_100a kernel yet (SURVEY §8f)")
-        if not hparams.name.startswith("adm"):
-            raise NotImplementedError("only the ADM U-Net ('adm*' experiments) is implemented; the DDPM U-Net "
-                                      "(models/ddim_blocks.py Model) is outside the hot path")
-        self.model = DhariwalUNet(hparams)
+        if hparams.name.startswith("adm"):                            # :36-39
+            self.model = DhariwalUNet(hparams)
+        else:
+            from .ddpm_blocks import Model
+
+            self.model = Model(hparams)
         self.ema_model = EmaModel(self.model, beta=m.ema_rate) if m.ema else None
 
         # EDM constants (:45-50)

@@ -185,12 +185,10 @@ def test_ddim_module_surface_and_vp_grid_scalars():
         assert c_out == float(-sigma) and c_in == float(1 / (sigma ** 2 + 1).sqrt())
         assert c_noise == float(999 - grid.round_sigma(sigma, return_index=True).to(torch.float32))
     hp = copy.deepcopy(cfg.model.hparams)
-    hp.name = "ddim"                                                   # the DDPM U-Net branch has no kernels
-    try:
-        PlDdim(hp)
-        raise AssertionError("PlDdim accepted a non-ADM network")
-    except NotImplementedError:
-        pass
+    hp.name = "ddim"                                                   # any other name builds the DDPM U-Net (ddim.py:40-43)
+    from mcedm_b200.ddpm_blocks import Model
+
+    assert isinstance(PlDdim(hp).model, Model)
     if R.reference_available():
         ref = R.import_reference()
         torch.manual_seed(1)
@@ -229,26 +227,34 @@ def test_pde_loss_selection_and_cpu_inputs_raise():
 
 def test_ddpm_model_mirror_state_dict():
     """Parameter mirror of the DDPM U-Net: names / shapes / order fixed by the reference fixture (tests/golden/ddpm_path.pt
-    holds the reference's shapes); seeded init bit-identical to the live reference when it is mounted; forward raises."""
+    holds the reference's shapes); seeded init bit-identical to the live reference when it is mounted; without a CUDA
+    device the forward fails loudly (no CPU path); the shipped config builds it through PlDdim."""
     import ref_harness_path  # noqa: F401
     import ref_harness as R
     from common import golden
     from mcedm_b200.ddpm_blocks import Model
 
-    cfg = compose("config_adm_ddim_res32")
+    cfg = compose("config_ddim_res32")
     hp = copy.deepcopy(cfg.model.hparams)
-    hp.name = "ddim"
+    assert hp.name == "ddim"
     torch.manual_seed(1)
     net = Model(hp)
+    assert (net.x_channels, net.cat_channels, net.out_channels) == (2, 2, 2)
     sd = net.state_dict()
     shapes = golden("ddpm_path.pt")["shapes"]
     assert list(sd) == list(shapes) and all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items())
     assert sum(v.numel() for v in sd.values()) == 1568514
-    try:
-        net(torch.zeros(1, 2, 128, 128), torch.zeros(1))
-        raise AssertionError("forward ran without kernels")
-    except NotImplementedError:
-        pass
+    if not torch.cuda.is_available():
+        import pytest
+
+        with pytest.raises(Exception):                 # McedmError: parameters / inputs must live on a CUDA device
+            with torch.no_grad():
+                net.eval()(torch.zeros(1, 2, 128, 128), torch.zeros(1))
+    from mcedm_b200.ddim import PlDdim
+
+    torch.manual_seed(1)
+    pl = PlDdim(copy.deepcopy(cfg.model.hparams))
+    assert isinstance(pl.model, Model) and list(pl.model.state_dict()) == list(shapes)
     if R.reference_available():
         ref = R.import_reference()
         torch.manual_seed(1)
