@@ -477,6 +477,29 @@ MCEDM_API int mcedm_ddpm_temb(const float* t, int Bt, const float* w0, const flo
                               const float* w_proj, const float* b_proj, int n_blocks, float* out, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* K8  fused validation / test reductions                                       */
+/* -------------------------------------------------------------------------------------------- */
+/* One pass over the sampled fields for PlMcedm.test_step / validation_step (models/mcedm.py:385-408):
+ *   mean over n_samples (mcedm.py:385-386), MaskedLoss('l1') on the normalised state and on the inverse-normalised
+ *   state (losses.py:62-78, normalizer.py:28-29), restricted to channels [c0, c1) (`loss_dim`).
+ * xs fp64 [n_samples][b][pixels][C] (channel-last, n-major as rearrange '(n b) ...'); gt fp32 [b][pixels][C];
+ * gt_unnorm_a fp32 [b][pixels][Ca] and gt_unnorm_b fp32 [b][pixels][C-Ca] (h_unnorm, u_unnorm as the datamodule delivers
+ * them; both NULL: skip the un-normalised error); mask fp32 [b][pixels][C] (1 = scored); sub / div DEVICE fp64 [C]
+ * (Normalizer buffers per channel); clamp01: clamp to [0,1] before the inverse transform (min_max normalisation).
+ * mean_out NULL or fp64 [b][pixels][C]; partial_scratch DEVICE fp64 [n_cta][3];
+ * out3 DEVICE fp64 [3] = (masked MAE, masked MAE un-normalised, number of scored entries). */
+MCEDM_API int mcedm_masked_mae_mean(const double* xs, int n_samples, int b, long long pixels, int C, const float* gt,
+                                    const float* gt_unnorm_a, const float* gt_unnorm_b, int Ca, const float* mask, int c0,
+                                    int c1, const double* sub, const double* div, int clamp01, double* mean_out,
+                                    double* partial_scratch, int n_cta, double* out3, void* stream);
+/* Per (sample, channel) of pred fp64 [b][pixels][C] vs target fp32 [b][pixels][C]: Pearson correlation exactly as
+ * CorrelationLoss.calculate_correlation (losses.py:101-116: centred sums, zero denominators += 1e-7) into corr_bc fp64
+ * [b][C] (NULL: skip; target may then be NULL), and min / max of pred into min_bc / max_bc fp64 [b][C] (NULL: skip) — the
+ * reductions of scale_each_min_max (ddim.py:689-698). */
+MCEDM_API int mcedm_corr_minmax(const double* pred, const float* target, int b, long long pixels, int C, double* corr_bc,
+                                double* min_bc, double* max_bc, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* bring-up / checker kernels (tests only; not on the product path)                              */
 /* -------------------------------------------------------------------------------------------- */
 /* tensor-pipe + shared-memory operand-fetch ceiling: every SM issues n_tiles x 36 tcgen05.mma (M=128, N, K=16, the conv

@@ -85,6 +85,9 @@ _PROTOTYPES = {
     "mcedm_gn_coef_groups": [_vp, _i, C.c_longlong, _vp, _vp, _i, _f, _vp, _i, _i, _vp, _vp],
     "mcedm_decimate16": [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp],
     "mcedm_ddpm_temb": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
+    "mcedm_masked_mae_mean": [_vp, _i, _i, C.c_longlong, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i,
+                              _vp, _vp],
+    "mcedm_corr_minmax": [_vp, _vp, _i, C.c_longlong, _i, _vp, _vp, _vp, _vp],
     "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
     "mcedm_probe_mma_queue": [_i, _i, _i, _vp, _vp],
     "mcedm_debug_rows": [_vp],

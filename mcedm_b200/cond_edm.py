@@ -151,8 +151,19 @@ class PlCondEdm(PlMcedm):
     @staticmethod
     def scale_each_min_max(state, return_min_max=False):              # ddim.py:689-698
         flat = rearrange(state, "b h w c -> b c (h w)")
-        lo = torch.min(flat, dim=2, keepdim=True)[0]
-        hi = torch.max(flat, dim=2, keepdim=True)[0]
+        if state.is_cuda and state.dtype == torch.float64:
+            # the two range reductions as one kernel over the channel-last fields (csrc/metrics.cu mcedm_corr_minmax)
+            from . import _lib as L
+
+            b, H, W, C = state.shape
+            sc = state.contiguous()
+            lo = torch.empty(b, C, 1, device=state.device, dtype=torch.float64)
+            hi = torch.empty(b, C, 1, device=state.device, dtype=torch.float64)
+            L.check(L.lib().mcedm_corr_minmax(L.ptr(sc), None, b, H * W, C, None, L.ptr(lo), L.ptr(hi), L.stream_ptr()),
+                    "corr_minmax")
+        else:
+            lo = torch.min(flat, dim=2, keepdim=True)[0]
+            hi = torch.max(flat, dim=2, keepdim=True)[0]
         scaled = rearrange((flat - lo) / (hi - lo), "b c (h w) -> b h w c", h=state.size(1), w=state.size(2))
         return (scaled, lo, hi) if return_min_max else scaled
 

@@ -37,7 +37,7 @@ from einops import rearrange
 from . import _lib as L
 from .adm_blocks import DhariwalUNet
 from .config import AttrDict
-from .nn_misc import EmaModel, MaskedLoss, NoiseEstimationLoss, Normalizer
+from .nn_misc import EmaModel, MaskedLoss, NoiseEstimationLoss, Normalizer, fused_masked_mae
 from .pde_loss import DarcyLoss, get_pde_loss_function
 from .runner import LightningModule
 
@@ -369,12 +369,16 @@ class PlMcedm(LightningModule):
                 raise TypeError("Non EDM sampler is not supported for the model")
             xs = self.sample_edm(noise, cond_in, mask_c, self.sparams, return_last=True,
                                  guide_dx=self.sparams.guide_dx)
-            hu_last = xs[:, -1]
-            loss_hu = self.mae_criterion(hu_last, state_gt, mask)
-            h_last, u_last = xs[:, -1, :, :, 0:h_ch], xs[:, -1, :, :, h_ch:u_ch + h_ch]
-            h_un, u_un = self.inverse_data_transform(h_last, u_last)
-            loss_hu_un = self.mae_criterion(torch.cat([h_un, u_un], dim=-1), torch.cat([h_unnorm, u_unnorm], dim=-1),
-                                            mask)
+            fm = self._fused_mae(xs[:, -1], 1, state_gt, h_unnorm, u_unnorm, mask, 0, h_ch + u_ch)
+            if fm is not None:                                        # one kernel pass (csrc/metrics.cu), :309-320
+                loss_hu, loss_hu_un = fm
+            else:
+                hu_last = xs[:, -1]
+                loss_hu = self.mae_criterion(hu_last, state_gt, mask)
+                h_last, u_last = xs[:, -1, :, :, 0:h_ch], xs[:, -1, :, :, h_ch:u_ch + h_ch]
+                h_un, u_un = self.inverse_data_transform(h_last, u_last)
+                loss_hu_un = self.mae_criterion(torch.cat([h_un, u_un], dim=-1),
+                                                torch.cat([h_unnorm, u_unnorm], dim=-1), mask)
             self.log(f"val_mae_{name}", loss_hu, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             self.log(f"val_mae_{name}_un", loss_hu_un, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             pde_loss = self.get_pde_loss(xs[:, -1], clamp_loss=False, do_rearrange=False) / len(h_unnorm)   # :325-328
@@ -410,8 +414,6 @@ class PlMcedm(LightningModule):
                 raise TypeError("Non EDM sampler is not supported for the model")
             xs = self.sample_edm(noise, cond_in_rep, mask_c_rep, self.test_sparams, return_last=return_last,
                                  guide_dx=guide_dx)
-            xs_mean = torch.mean(rearrange(xs, "(n b) t h w c -> n b t h w c", n=n_samples), dim=0)
-            hu_last = xs_mean[:, -1]
             if down_factor > 1:
                 each_x = 2 ** (down_factor - 1)
                 mask_down = torch.zeros_like(mask)
@@ -419,10 +421,18 @@ class PlMcedm(LightningModule):
                 mask_loss = mask * mask_down
             else:
                 mask_loss = mask
-            loss_hu = self.mae_criterion(hu_last, state_gt, mask_loss, loss_dim)
-            h_un, u_un = self.inverse_data_transform(xs_mean[:, -1, :, :, 0:h_ch], xs_mean[:, -1, :, :, h_ch:u_ch + h_ch])
-            loss_hu_un = self.mae_criterion(torch.cat([h_un, u_un], dim=-1), torch.cat([h_unnorm, u_unnorm], dim=-1),
-                                            mask_loss, loss_dim)
+            # mean over n_samples (:385-386) + both masked errors (:398-408) in one kernel pass over the fp64 fields
+            fm = self._fused_mae(xs[:, -1], n_samples, state_gt, h_unnorm, u_unnorm, mask_loss, start, end)
+            if fm is not None:
+                loss_hu, loss_hu_un = fm
+            else:
+                xs_mean = torch.mean(rearrange(xs, "(n b) t h w c -> n b t h w c", n=n_samples), dim=0)
+                hu_last = xs_mean[:, -1]
+                loss_hu = self.mae_criterion(hu_last, state_gt, mask_loss, loss_dim)
+                h_un, u_un = self.inverse_data_transform(xs_mean[:, -1, :, :, 0:h_ch],
+                                                         xs_mean[:, -1, :, :, h_ch:u_ch + h_ch])
+                loss_hu_un = self.mae_criterion(torch.cat([h_un, u_un], dim=-1),
+                                                torch.cat([h_unnorm, u_unnorm], dim=-1), mask_loss, loss_dim)
             self.log(f"test_mae_{name}", loss_hu, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             self.log(f"test_mae_{name}_un", loss_hu_un, prog_bar=True, on_epoch=True, on_step=False, sync_dist=True)
             # PDE residual of every prediction, then of the ground truth (:416-428)
@@ -438,6 +448,14 @@ class PlMcedm(LightningModule):
                                                         n=n_samples).unsqueeze(dim=1)
                 result_dict[f"gt_{name}"] = state_gt
         return result_dict
+
+    def _fused_mae(self, xs_last, n_samples, state_gt, h_unnorm, u_unnorm, mask, c0, c1):
+        """(masked MAE, masked MAE un-normalised) of the sample mean through csrc/metrics.cu, or None when an option the
+        kernel does not cover is on (`rescaled`: the inverse transform is not the plain x*divide + subtract)."""
+        if self.rescaled or not getattr(self, "fused_metrics", True):
+            return None
+        return fused_masked_mae(xs_last, n_samples, state_gt, h_unnorm, u_unnorm, mask, c0, c1, self.normalizer_input,
+                                self.normalizer_target, clamp01=self.normalization == "min_max")
 
     # ---------------------------------------------------------------- PDE residual (K6) and guidance
     def _pde_planes(self, h, u):

@@ -111,8 +111,54 @@ class MaskedLoss(nn.Module):
         return total / torch.sum(mask)
 
 
+def fused_masked_mae(xs_last, n_samples, state_gt, h_unnorm, u_unnorm, mask, c0, c1, norm_h, norm_u, clamp01=False):
+    """(MaskedLoss on the normalised state, MaskedLoss on the inverse-normalised state) of the sample mean, as 0-dim fp64
+    tensors, through ONE kernel pass over the fields (csrc/metrics.cu mcedm_masked_mae_mean) — the metrics block of
+    PlMcedm.test_step / validation_step (models/mcedm.py:385-408; losses.py:62-78; normalizer.py:28-29).
+    xs_last fp64 [(n b), H, W, C] CUDA; state_gt / mask fp32 [b, H, W, C]; h_unnorm / u_unnorm fp32 [b, H, W, ch].
+    Returns None when the inputs are not in that form (the caller then evaluates the torch expressions)."""
+    from . import _lib as L
+
+    if not (xs_last.is_cuda and xs_last.dtype == torch.float64 and state_gt.dtype == torch.float32
+            and mask.dtype == torch.float32 and h_unnorm.dtype == torch.float32 and u_unnorm.dtype == torch.float32
+            and xs_last.dim() == 4 and mask.shape == state_gt.shape):
+        return None
+    nb, H, W, C = xs_last.shape
+    b = nb // n_samples
+    Ca = h_unnorm.shape[-1]
+    if b * n_samples != nb or state_gt.shape != (b, H, W, C) or Ca + u_unnorm.shape[-1] != C:
+        return None
+    dev = xs_last.device
+    key = tuple((id(t), t._version) for t in (norm_h.subtract, norm_h.divide, norm_u.subtract, norm_u.divide)) + (Ca, C, dev)
+    hit = _METRIC_STATS.get(key)
+    if hit is None:
+        if len(_METRIC_STATS) > 16:
+            _METRIC_STATS.clear()
+        sub = torch.cat([norm_h.subtract.reshape(-1).expand(Ca), norm_u.subtract.reshape(-1).expand(C - Ca)]).double()
+        div = torch.cat([norm_h.divide.reshape(-1).expand(Ca), norm_u.divide.reshape(-1).expand(C - Ca)]).double()
+        # the buffers are kept in the entry: their ids cannot be re-used while it is alive
+        hit = _METRIC_STATS[key] = (sub.to(dev).contiguous(), div.to(dev).contiguous(),
+                                    (norm_h.subtract, norm_h.divide, norm_u.subtract, norm_u.divide))
+    sub, div, _ = hit
+    n_cta = 592
+    xs_c, gt_c, m_c = xs_last.contiguous(), state_gt.contiguous(), mask.contiguous()
+    ha, ub = h_unnorm.contiguous(), u_unnorm.contiguous()
+    part = torch.empty(n_cta, 3, device=dev, dtype=torch.float64)
+    out = torch.empty(3, device=dev, dtype=torch.float64)
+    L.check(L.lib().mcedm_masked_mae_mean(L.ptr(xs_c), n_samples, b, H * W, C, L.ptr(gt_c), L.ptr(ha), L.ptr(ub), Ca,
+                                          L.ptr(m_c), int(c0), int(c1), L.ptr(sub), L.ptr(div), 1 if clamp01 else 0, None,
+                                          L.ptr(part), n_cta, L.ptr(out), L.stream_ptr()), "masked_mae_mean")
+    L.LAUNCHES[0] += 1                                               # streaming pass + fold
+    return out[0], out[1]
+
+
+_METRIC_STATS = {}
+
+
 class CorrelationLoss(nn.Module):
-    """Pearson correlation per channel between prediction and target, averaged over the batch."""
+    """Pearson correlation per channel between prediction and target, averaged over the batch (losses.py:96-128).
+    fp64 CUDA predictions against an fp32 target (what the test steps pass) run as one kernel
+    (csrc/metrics.cu mcedm_corr_minmax); anything else evaluates the torch expressions."""
 
     def __init__(self, reduction="none"):
         super().__init__()
@@ -130,7 +176,17 @@ class CorrelationLoss(nn.Module):
     def forward(self, pred, target):
         pred = pred.reshape(pred.shape[0], -1, pred.shape[-1])
         target = target.reshape(target.shape[0], -1, target.shape[-1])
-        corr = self.calculate_correlation(pred, target)
+        if pred.is_cuda and pred.dtype == torch.float64 and target.dtype == torch.float32 and pred.shape == target.shape:
+            from . import _lib as L
+
+            b, P, C = pred.shape
+            pc, tc = pred.contiguous(), target.contiguous()
+            cb = torch.empty(b, C, device=pred.device, dtype=torch.float64)
+            L.check(L.lib().mcedm_corr_minmax(L.ptr(pc), L.ptr(tc), b, P, C, L.ptr(cb), None, None, L.stream_ptr()),
+                    "corr_minmax")
+            corr = torch.mean(cb, dim=0)
+        else:
+            corr = self.calculate_correlation(pred, target)
         if self.reduction == "mean":
             return torch.mean(corr)
         if self.reduction == "sum":
