@@ -417,6 +417,13 @@ MCEDM_API int mcedm_edm_noise_in(const float* x, const float* noise, const float
 MCEDM_API int mcedm_mcedm_prep(const float* h, const float* u, const float* mask, const float* randn, float h_sub,
                                float h_div, float u_sub, float u_div, int B, long long HW, float* x, float* cond,
                                float* mask_c, void* stream);
+/* mcedm_mcedm_prep with the mask generated on the device (h5_dataset.py:232-255, :306-393): every
+ * mask of the reference's datasets is "channel c missing from time row obs_rows[b][c] on" (0 = whole channel missing,
+ * H = observed), so obs_rows DEVICE int32 [B][2] replaces the [B,H,W,2] mask tensor.  mask_bhwc: NULL, or fp32 [B,H,W,2]
+ * receiving the channel-last mask the module logs / scores with.  Bit-identical to mcedm_mcedm_prep on the expanded mask. */
+MCEDM_API int mcedm_mcedm_prep_rows(const float* h, const float* u, const int* obs_rows, const float* randn, float h_sub,
+                                    float h_div, float u_sub, float u_div, int B, int H, int W, float* x, float* cond,
+                                    float* mask_c, float* mask_bhwc, void* stream);
 /* channels [c_dst0, c_dst0+Ca+Cb) of a 64-channel bf16 NHWC tensor <- cat(a, b) (NCHW fp32; b may be NULL, Cb = 0) */
 MCEDM_API int mcedm_nchw_to_nhwc_pad(const float* a, int Ca, const float* b, int Cb, int B, int H, int W,
                                      void* dst_bf16, int c_dst0, void* stream);

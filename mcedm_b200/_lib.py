@@ -48,6 +48,7 @@ _PROTOTYPES = {
     "mcedm_edm_loss": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _i, _vp],
     "mcedm_edm_noise_in": [_vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _vp, _vp, _vp],
     "mcedm_mcedm_prep": [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, C.c_longlong, _vp, _vp, _vp, _vp],
+    "mcedm_mcedm_prep_rows": [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_nchw_to_nhwc_pad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "mcedm_colsum_bf16": [_vp, C.c_longlong, _i, _i, _vp, _i, _vp],
     "mcedm_emb_mlp_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

@@ -60,6 +60,34 @@ mcedm_prep_kernel(const float* __restrict__ h, const float* __restrict__ u, cons
   mask_c[o1] = m.y;
 }
 
+// The same with the mask GENERATED on the device: every mask the reference's datasets produce
+// (h5_dataset.py:232-255 channel masks, :306-393 time masks) is "channel c is missing from time row obs_rows[b][c]
+// on" (0: whole channel missing, H: fully observed, t_max: random observation horizon), so the DataLoader only has to
+// deliver the two integers per item it drew with the reference's RNG calls; the [B,H,W,2] mask never crosses PCIe and
+// the per-item torch.cat / ones_like / zeros_like work of the worker processes disappears.
+__global__ void __launch_bounds__(256)
+mcedm_prep_rows_kernel(const float* __restrict__ h, const float* __restrict__ u, const int* __restrict__ obs_rows,
+                       const float* __restrict__ randn, float h_sub, float h_div, float u_sub, float u_div, long long HW,
+                       int W, long long total_pix, float* __restrict__ x, float* __restrict__ cond,
+                       float* __restrict__ mask_c, float* __restrict__ mask_bhwc) {
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= total_pix) return;
+  const long long b = pix / HW, hw = pix - b * HW;
+  const int t = (int)(hw / W);
+  const float xh = __fdiv_rn(__fsub_rn(h[pix], h_sub), h_div);
+  const float xu = __fdiv_rn(__fsub_rn(u[pix], u_sub), u_div);
+  const float2 m = make_float2(t >= obs_rows[b * 2] ? 1.0f : 0.0f, t >= obs_rows[b * 2 + 1] ? 1.0f : 0.0f);
+  const float2 r = *reinterpret_cast<const float2*>(randn + pix * 2);
+  const long long o0 = (b * 2) * HW + hw, o1 = o0 + HW;
+  x[o0] = xh;
+  x[o1] = xu;
+  cond[o0] = __fadd_rn(__fmul_rn(xh, __fsub_rn(1.0f, m.x)), __fmul_rn(r.x, m.x));
+  cond[o1] = __fadd_rn(__fmul_rn(xu, __fsub_rn(1.0f, m.y)), __fmul_rn(r.y, m.y));
+  mask_c[o0] = m.x;
+  mask_c[o1] = m.y;
+  if (mask_bhwc) *reinterpret_cast<float2*>(mask_bhwc + pix * 2) = m;
+}
+
 // one thread per pixel; dst channels [c_dst0, c_dst0 + Ca + Cb) <- cat(a, b)[:, :, pix]
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_pad_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ bsrc, int Cb, long long HW,
@@ -318,6 +346,18 @@ extern "C" int mcedm_mcedm_prep(const float* h, const float* u, const float* mas
   const long long total = HW * B;
   mcedm_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       h, u, mask, randn, h_sub, h_div, u_sub, u_div, HW, total, x, cond, mask_c);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_mcedm_prep_rows(const float* h, const float* u, const int* obs_rows, const float* randn, float h_sub,
+                                    float h_div, float u_sub, float u_div, int B, int H, int W, float* x, float* cond,
+                                    float* mask_c, float* mask_bhwc, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && H >= 1 && W >= 1 && obs_rows != nullptr, "mcedm_prep_rows: bad arguments");
+  const long long HW = (long long)H * W, total = HW * B;
+  mcedm_prep_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, u, obs_rows, randn, h_sub, h_div, u_sub, u_div, HW, W, total, x, cond, mask_c, mask_bhwc);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

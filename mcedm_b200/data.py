@@ -151,6 +151,36 @@ def sample_time_mask(inp: torch.Tensor, target: torch.Tensor, is_train: bool, ad
     return masks
 
 
+# ---- the same masks as two integers per item (device-side generation) -------------------------------
+# Every training mask above is "channel c is missing from time row r_c on": r = 0 (whole channel missing), r = res
+# (observed), or the random horizon t_max.  `*_rows` make EXACTLY the RNG calls of their tensor-valued counterparts (same
+# generator state afterwards) and return (r_h, r_u); `expand_mask_rows` is the host restatement of what
+# mcedm_mcedm_prep_rows expands on the device (bit-identical to sample_mask / sample_time_mask for h_ch = u_ch = 1).
+def sample_mask_rows(res: int) -> torch.Tensor:
+    """HDF5MaskDataset.sample_mask(is_train=True) (h5_dataset.py:236-243) as observation rows."""
+    if torch.rand(1) > 0.5:
+        return torch.tensor([res, 0], dtype=torch.int32)              # u missing
+    return torch.tensor([0, res], dtype=torch.int32)                  # h missing
+
+
+def sample_time_mask_rows(res: int) -> torch.Tensor:
+    """HDF5TimeMaskDataset training mask (h5_dataset.py:326-345) as observation rows."""
+    var = torch.rand(1)
+    t1 = int(res // 2 + torch.randint(res // 2 + 1, (1,)))
+    t2 = int(res // 2 + torch.randint(res // 2 + 1, (1,)))
+    if var <= 0.4:
+        return torch.tensor([t1, 0], dtype=torch.int32)               # u missing entirely, h observed up to its horizon
+    if var <= 0.8:
+        return torch.tensor([0, t2], dtype=torch.int32)
+    return torch.tensor([t1, t2], dtype=torch.int32)
+
+
+def expand_mask_rows(rows: torch.Tensor, res_t: int, res_x: int) -> torch.Tensor:
+    """[.., 2] observation rows -> fp32 mask [.., res_t, res_x, 2] (1 = missing)."""
+    t = torch.arange(res_t, device=rows.device).reshape(res_t, 1, 1)
+    return (t >= rows.reshape(*rows.shape[:-1], 1, 1, 2)).float().expand(*rows.shape[:-1], res_t, res_x, 2).contiguous()
+
+
 # ---------------------------------------------------------------------------------------------
 # datasets / datamodules
 # ---------------------------------------------------------------------------------------------
@@ -174,6 +204,10 @@ class _FieldDataset(Dataset):
         inp, tar = self.h[idx], self.u[idx]
         if self.mask_mode == "none":
             return inp, self.g0, self.g1, tar
+        if self.is_train and getattr(self, "device_masks", False) and inp.shape[-1] == 1 and tar.shape[-1] == 1:
+            # training masks as observation rows: the mask tensor is expanded on the device (mcedm_mcedm_prep_rows)
+            rows = sample_time_mask_rows(inp.shape[0]) if self.mask_mode == "time" else sample_mask_rows(inp.shape[0])
+            return inp, self.g0, self.g1, tar, rows
         if self.mask_mode == "time":
             mask = sample_time_mask(inp, tar, self.is_train, self.add_time_masks)
         else:
@@ -195,6 +229,7 @@ class SyntheticDatamodule:
         self.test_batch_size = test_batch_size if test_batch_size and test_batch_size > 0 else batch_size
         self.down_factor, self.down_interp = down_factor, True
         self.return_grid, self.add_time_masks, self.resolution = return_grid, add_time_masks, resolution
+        self.device_masks = bool(_ignored.get("device_masks", False))   # training masks as [B,2] observation rows
         self.eps = 1e-8
         self._built = False
 
@@ -217,6 +252,7 @@ class SyntheticDatamodule:
         mk = lambda d, tr: _FieldDataset(d[0], d[1], self.mask_mode, tr, self.add_time_masks, self.return_grid)  # noqa
         self.train_dataset, self.val_dataset, self.test_dataset = mk(self._train, True), mk(self._test, False), \
             mk(self._test, False)
+        self.train_dataset.device_masks = self.device_masks
 
     def get_norm_stats(self) -> AttrDict:
         self._build()

@@ -315,16 +315,28 @@ class PlMcedm(LightningModule):
         if not (self.fused_prep and h_unnorm.is_cuda and h_unnorm.shape[-1] == 1 and u_unnorm.shape[-1] == 1
                 and self.normalization != "min_max" and not (self.uniform_dequantization or self.gaussian_dequantization
                                                              or self.rescaled or self.add_cond_mask or self.add_xt)
-                and h_unnorm.dtype == torch.float32 and mask.dtype == torch.float32):
+                and h_unnorm.dtype == torch.float32 and (mask.dtype == torch.float32 or mask.dim() == 2)):
+            if mask.dim() == 2:
+                raise NotImplementedError("observation-row masks (device_masks datamodule) need the fused batch "
+                                          "preparation: fp32 CUDA inputs, gauss normalisation, no dequantisation")
             return None
         from .pde_loss import _norm_args
 
         h_div, h_sub, u_div, u_sub = _norm_args(self.normalizer_input, self.normalizer_target)
         B, H, W, _ = h_unnorm.shape
-        h, u, m = h_unnorm.contiguous(), u_unnorm.contiguous(), mask.contiguous()
-        r = self._randn_like("cond", m).contiguous()                 # the draw of get_cond_in (:247): b h w c, fp32
+        h, u = h_unnorm.contiguous(), u_unnorm.contiguous()
         x = torch.empty(B, 2, H, W, device=h.device, dtype=torch.float32)
         cond, mask_c = torch.empty_like(x), torch.empty_like(x)
+        if mask.dim() == 2:
+            # [B, 2] int32 observation rows from a `device_masks` datamodule: the mask is expanded inside the kernel
+            rows = mask.to(device=h.device, dtype=torch.int32).contiguous()
+            r = self._randn_like("cond", torch.empty(B, H, W, 2, device=h.device, dtype=torch.float32)).contiguous()
+            L.check(L.lib().mcedm_mcedm_prep_rows(L.ptr(h), L.ptr(u), L.ptr(rows), L.ptr(r), h_sub, h_div, u_sub, u_div,
+                                                  B, H, W, L.ptr(x), L.ptr(cond), L.ptr(mask_c), None, L.stream_ptr()),
+                    "mcedm_prep_rows")
+            return x, cond, mask_c
+        m = mask.contiguous()
+        r = self._randn_like("cond", m).contiguous()                 # the draw of get_cond_in (:247): b h w c, fp32
         L.check(L.lib().mcedm_mcedm_prep(L.ptr(h), L.ptr(u), L.ptr(m), L.ptr(r), h_sub, h_div, u_sub, u_div, B, H * W,
                                          L.ptr(x), L.ptr(cond), L.ptr(mask_c), L.stream_ptr()), "mcedm_prep")
         return x, cond, mask_c

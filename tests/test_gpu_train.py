@@ -429,6 +429,63 @@ def test_fused_optimizer_step_and_ema_inside_trainer_loop(dev):
     assert float(sd["state"][0]["step"]) == 2.0
 
 
+def test_device_side_masks_are_bit_identical_to_the_host_masks(dev):
+    """SURVEY 8f rank 3: a `device_masks` datamodule delivers two observation rows per item instead of the [H,W,2] mask;
+    mcedm_mcedm_prep_rows expands them inside the batch-preparation kernel.  x / cond / mask are bit-identical to the
+    kernel fed with the host-generated mask of the same RNG draws, for channel masks and time masks."""
+    from mcedm_b200 import _lib as L
+    from mcedm_b200 import data as D
+
+    lib = L.lib()
+    B, H, W = 6, 128, 128
+    gen = torch.Generator().manual_seed(2)
+    h = (torch.randn(B, H, W, 1, generator=gen) * 0.3 + 1.5).to(dev)
+    u = torch.randn(B, H, W, 1, generator=gen).to(dev)
+    r = torch.randn(B, H, W, 2, generator=gen).to(dev)
+    for sampler_rows, sampler_mask in ((D.sample_mask_rows, lambda: D.sample_mask(h[0].cpu(), u[0].cpu(), True)),
+                                       (D.sample_time_mask_rows, lambda: D.sample_time_mask(h[0].cpu(), u[0].cpu(), True))):
+        torch.manual_seed(31)
+        rows = torch.stack([sampler_rows(H) for _ in range(B)])
+        torch.manual_seed(31)
+        mask = torch.stack([sampler_mask() for _ in range(B)]).to(dev)
+        assert torch.equal(D.expand_mask_rows(rows, H, W), mask.cpu())
+        outs = []
+        for use_rows in (False, True):
+            x = torch.empty(B, 2, H, W, device=dev)
+            cond, mc = torch.empty_like(x), torch.empty_like(x)
+            if use_rows:
+                rd = rows.to(dev)
+                mb = torch.empty(B, H, W, 2, device=dev)
+                L.check(lib.mcedm_mcedm_prep_rows(L.ptr(h), L.ptr(u), L.ptr(rd), L.ptr(r), 1.5, 0.3, 0.1, 0.2, B, H, W, L.ptr(x),
+                                                  L.ptr(cond), L.ptr(mc), L.ptr(mb), L.stream_ptr()))
+                assert torch.equal(mb, mask)
+            else:
+                L.check(lib.mcedm_mcedm_prep(L.ptr(h), L.ptr(u), L.ptr(mask), L.ptr(r), 1.5, 0.3, 0.1, 0.2, B, H * W, L.ptr(x),
+                                             L.ptr(cond), L.ptr(mc), L.stream_ptr()))
+            outs.append((x, cond, mc))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+    # end to end: training_step on a device_masks datamodule batch == training_step on the expanded mask (same draws)
+    from common import NoiseFeed, stress_module
+
+    dm = D.SyntheticMaskDatamodule(system="swe_per", n_train=4, n_test=1, batch_size=2, device_masks=True)
+    dm.setup("fit")
+    torch.manual_seed(5)
+    hb, g0, g1, ub, rows = [t.to(dev) for t in next(iter(dm.train_dataloader()))]
+    assert rows.shape == (2, 2) and rows.dtype == torch.int32
+    pl, _ = stress_module()
+    pl = pl.to(dev).train()
+    st = dm.get_norm_stats()
+    pl.normalizer_input.set_stats(st["input_mean"].to(dev), st["input_std"].to(dev))
+    pl.normalizer_target.set_stats(st["target_mean"].to(dev), st["target_std"].to(dev))
+    losses = []
+    for m in (rows, D.expand_mask_rows(rows.cpu(), 128, 128).to(dev)):
+        pl._noise_hook = NoiseFeed(9).hook
+        torch.manual_seed(4)
+        losses.append(float(pl.training_step((hb, g0, g1, ub, m), 0).detach()))
+    assert losses[0] == losses[1] and losses[0] == losses[0]
+
+
 def test_flat_grads_is_idempotent_and_consumed_by_step(dev):
     """The tensor `FusedAdam.flat_grads()` returns first is the one `step()` consumes, on the eager autograd path too
     (a second gather used to overwrite an all-reduced buffer with the local gradients): zeroing the fetched

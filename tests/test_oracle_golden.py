@@ -107,6 +107,20 @@ def test_mask_generators_bit_identical():
     torch.manual_seed(g["time_seed"])
     mine_t = torch.stack([D.sample_time_mask(h[0], u[0], True) for _ in range(8)])
     assert torch.equal(mine_t.to(torch.uint8), g["time_train"])
+    # the same masks as two observation rows per item (device-side generation, data.sample_*_rows): same RNG calls, and
+    # their expansion is the reference-generated mask bit for bit
+    torch.manual_seed(g["train_seed"])
+    rows = torch.stack([D.sample_mask_rows(128) for _ in range(8)])
+    assert torch.equal(D.expand_mask_rows(rows, 128, 128).to(torch.uint8), g["train_masks"])
+    torch.manual_seed(g["train_seed"])
+    [D.sample_mask(h[0], u[0], True) for _ in range(8)]
+    after_ref = torch.rand(1)
+    torch.manual_seed(g["train_seed"])
+    [D.sample_mask_rows(128) for _ in range(8)]
+    assert torch.equal(torch.rand(1), after_ref)                      # generator left in the same state
+    torch.manual_seed(g["time_seed"])
+    rows_t = torch.stack([D.sample_time_mask_rows(128) for _ in range(8)])
+    assert torch.equal(D.expand_mask_rows(rows_t, 128, 128).to(torch.uint8), g["time_train"])
     ev = D.sample_mask(h[0], u[0], False)
     assert torch.equal(ev["u"].to(torch.uint8), g["eval_u"]) and torch.equal(ev["h"].to(torch.uint8), g["eval_h"])
     oe = O.eval_masks(h[0], u[0])
