@@ -17,6 +17,14 @@
 //           sum is accumulated in fp32 from the same exponentials.
 // The second QK^T costs 50 % more MMA work but removes every accumulator rescale; the kernel is
 // bound by the exp/convert work of the 4 softmax warps, not by the tensor pipe.
+//
+// SINGLE-PASS variant (inference, round 2).  What bounds the two-pass kernel is not the exponentials but reading S out
+// of TMEM twice (64 B per cycle per SM: 1024 cycles per 128 x 128 fp32 block, per pass — as long as the block's MUFU
+// work).  Softmax is invariant to the shift, so the shift need not be the row maximum: the single-pass kernel takes
+// m_ref = the exact row maximum of key block 0 and never rescales.  Later blocks may exceed m_ref; P = exp2(.) then
+// exceeds 1, which fp16 holds up to 2^16.  A CTA whose exponent argument ever exceeds 15 (a score 83 above its first
+// block's maximum: not seen on normalised inputs, but legal) raises its flag and the caller re-runs exactly those tiles
+// with the two-pass kernel, whose CTAs return at once when their flag is clear.
 //   warp 0 : TMA producer (Q once; K blocks in pass 1; K and V blocks in pass 2; 3-stage ring)
 //   warp 1 : MMA issuer (S double-buffered in TMEM so softmax of block j overlaps QK^T of block j+1)
 //   warps 2-9 : softmax / epilogue: two warps per TMEM lane quarter, each owning one 64-key half of every S block of
@@ -28,6 +36,7 @@
 #include "../../include/mcedm_b200.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace mcedm {
 
@@ -40,9 +49,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// SINGLE: one pass over the keys (see the header); flags = per-CTA overflow flags, WRITTEN by the single-pass kernel and
+// READ by the two-pass kernel launched after it (NULL: every CTA of the two-pass kernel runs).
+template <bool SINGLE>
 __global__ void __launch_bounds__(320, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out,
-            float* __restrict__ lse_out, int fmt, unsigned int* err) {
+            float* __restrict__ lse_out, int fmt, unsigned int* err, unsigned int* __restrict__ flags) {
+  if (!SINGLE && flags != nullptr && flags[blockIdx.x] == 0u) return;      // fallback launch: only the flagged tiles
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                                  // 16 KB
@@ -65,9 +78,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   const int nblk = L / 128;
   const int b = blockIdx.x / nblk;
   const int q0 = (blockIdx.x - b * nblk) * 128;
-  const int n_it = 2 * nblk;
+  const int p2_start = SINGLE ? 0 : nblk;      // first iteration of the exponentiating pass
+  const int n_it = p2_start + nblk;
 
   if (warp == 0 && lane == 0) {
+    if (SINGLE && flags) flags[blockIdx.x] = 0u;
     prefetch_tmap(&tm_qkv);
     mbar_init(q_full, 1);
     mbar_init(o_full, 1);
@@ -98,7 +113,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       mbar_expect_tx(q_full, kTile);
       tma_load_4d(q_smem, &tm_qkv, q_full, 0, q0, 0, b);
       for (int it = 0; it < n_it; ++it) {
-        const int pass = it / nblk, j = it - pass * nblk;
+        const int pass = it >= p2_start ? 1 : 0, j = it - pass * p2_start;
         const uint32_t s = it % kKvStages, n = it / kKvStages;
         mbar_wait(&kv_empty[s], (n & 1u) ^ 1u, err, 0x1100 + s);
         mbar_expect_tx(&kv_full[s], pass ? 2 * kTile : kTile);
@@ -116,7 +131,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       const uint32_t q_base = smem_u32(q_smem);
       for (int it = 0; it <= n_it; ++it) {
         if (it < n_it) {
-          const int pass = it / nblk;
+          const int pass = it >= p2_start ? 1 : 0;
           const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
           const uint32_t s = it % kKvStages, n = it / kKvStages;
           mbar_wait(&s_empty[sb], (ns & 1u) ^ 1u, err, 0x1300 + sb);
@@ -132,8 +147,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
           }
           __syncwarp();
         }
-        if (it >= nblk + 1) {
-          const int jp = it - 1 - nblk;                    // P V of the previous pass-2 block
+        if (it >= p2_start + 1) {
+          const int jp = it - 1 - p2_start;                // P V of the previous pass-2 block
           const uint32_t pb = jp & 1u, np = (uint32_t)jp >> 1;
           const uint32_t sp = (it - 1) % kKvStages;
           mbar_wait(&p_full[pb], np & 1u, err, 0x1500 + pb);
@@ -163,7 +178,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     const float c1 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
     float m = -INFINITY, l = 0.f;
     // ---------------- pass 1: row maximum only (the row sum is accumulated from the pass-2 exponentials) -----
-    for (int it = 0; it < nblk; ++it) {
+    for (int it = 0; it < p2_start; ++it) {
       const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
       mbar_wait(&s_full[sb], ns & 1u, err, 0x1600 + sb);
       tc_fence_after();
@@ -183,14 +198,34 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       tc_fence_before();
       mbar_arrive_warp(&s_empty[sb]);
     }
+    if constexpr (SINGLE) {
+      // m_ref = exact row maximum of key block 0 (its S buffer is read again by the loop below; s_empty is not
+      // arrived on here, so the buffer stays valid)
+      mbar_wait(&s_full[0], 0u, err, 0x1650);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 2 * hsel; c < 2 * hsel + 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_addr + c * 32, v);
+        tmem_wait_ld();
+        float cm0 = __uint_as_float(v[0]), cm1 = __uint_as_float(v[1]);
+#pragma unroll
+        for (int i = 2; i < 32; i += 2) {
+          cm0 = fmaxf(cm0, __uint_as_float(v[i]));
+          cm1 = fmaxf(cm1, __uint_as_float(v[i + 1]));
+        }
+        m = fmaxf(m, fmaxf(cm0, cm1));
+      }
+    }
     // the two halves of a row exchange their partial maxima
     xch_m[hsel * 128 + row] = m;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     m = fmaxf(xch_m[row], xch_m[128 + row]);
     const float mc = m * c1;
+    float amax = 0.f;                         // SINGLE: largest exponent argument seen (0 at the reference maximum)
     // ---------------- pass 2: P = exp2(S*c1 - m*c1) -> bf16 -> smem ----------------
     for (int j = 0; j < nblk; ++j) {
-      const int it = nblk + j;
+      const int it = p2_start + j;
       const uint32_t sb = it & 1u, ns = (uint32_t)it >> 1;
       const uint32_t pb = j & 1u, np = (uint32_t)j >> 1;
       mbar_wait(&s_full[sb], ns & 1u, err, 0x1700 + sb);
@@ -209,8 +244,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
           uint32_t* op = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[u * 8 + 2 * e]), c1, -mc));
-            const float p1 = ex2(fmaf(__uint_as_float(v[u * 8 + 2 * e + 1]), c1, -mc));
+            const float a0 = fmaf(__uint_as_float(v[u * 8 + 2 * e]), c1, -mc);
+            const float a1 = fmaf(__uint_as_float(v[u * 8 + 2 * e + 1]), c1, -mc);
+            if constexpr (SINGLE) amax = fmaxf(amax, fmaxf(a0, a1));
+            const float p0 = ex2(a0);
+            const float p1 = ex2(a1);
             op[e] = pack_op2(p0, p1, fmt);
             // normalise by what the P V product actually sums (the rounded weights)
             if (fmt) {
@@ -228,6 +266,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       mbar_arrive_warp(&s_empty[sb]);
       fence_proxy_async_smem();     // generic-proxy P writes -> visible to the UMMA (async proxy) reads
       mbar_arrive_warp(&p_full[pb]);
+    }
+    if constexpr (SINGLE) {
+      // fp16 weights hold exp2(a) up to a < 16; beyond 15 (or a non-finite score) the tile is redone by the two-pass kernel
+      if (__any_sync(0xffffffffu, !(amax <= 15.0f)) && lane == 0 && flags) flags[blockIdx.x] = 1u;
     }
     // ---------------- epilogue: O / l -> bf16 ----------------
     xch_l[hsel * 128 + row] = l;
@@ -299,6 +341,26 @@ __global__ void attn_ref_kernel(const __nv_bfloat16* __restrict__ qkv, int L, fl
 
 }  // namespace mcedm
 
+namespace mcedm {
+// per-CTA overflow flags of the single-pass kernel (device memory, grown on demand outside graph capture)
+static unsigned int* attn_flags(long long n) {
+  static unsigned int* buf = nullptr;
+  static long long cap = 0;
+  if (n > cap) {
+    if (buf) cudaFree(buf);
+    const long long want = n < 16384 ? 16384 : n;
+    if (cudaMalloc(&buf, sizeof(unsigned int) * want) != cudaSuccess) {
+      buf = nullptr;
+      cap = 0;
+      return nullptr;
+    }
+    cudaMemset(buf, 0, sizeof(unsigned int) * want);
+    cap = want;
+  }
+  return buf;
+}
+}  // namespace mcedm
+
 extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16, float* lse_out, int op_fmt,
                                void* stream) {
   using namespace mcedm;
@@ -311,11 +373,32 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
   const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 256 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
-    MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  attn_kernel<<<B * (L / 128), 320, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0, err);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)(B * (L / 128));
+  // inference (no log-sum-exp requested): single pass over the keys + a fallback launch whose CTAs return at once
+  // unless the single-pass CTA flagged an exponent beyond fp16's range.  MCEDM_ATTN_2PASS=1 forces the two-pass kernel.
+  static int force2 = -1;
+  if (force2 < 0) {
+    const char* e = getenv("MCEDM_ATTN_2PASS");
+    force2 = (e && atoi(e)) ? 1 : 0;
+  }
+  if (lse_out == nullptr && !force2) {
+    unsigned int* flags = attn_flags(grid);
+    MCEDM_REQUIRE(flags != nullptr, "attention: cannot allocate the overflow flags");
+    attn_kernel<true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, op_fmt ? 1 : 0,
+                                               err, flags);
+    MCEDM_CUDA(cudaGetLastError());
+    attn_kernel<false><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, op_fmt ? 1 : 0,
+                                                err, flags);
+    MCEDM_CUDA(cudaGetLastError());
+    return 0;
+  }
+  attn_kernel<false><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0,
+                                              err, nullptr);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

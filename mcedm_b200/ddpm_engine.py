@@ -214,6 +214,7 @@ class DdpmEngine(FusedMixin):
         att = self._fbuf(ws, "att.out", (B, H * W, 64), self._dt16(), dev)
         self._conv([a2], [(0, 0, 0)], a.wqkv, a.bqkv, B, H, W, 192, qkv, 1, None, 0, None, st)
         L.check(self.lib.mcedm_attention(L.ptr(qkv), B, H * W, L.ptr(att), None, self._fmt, st), "attention")
+        L.LAUNCHES[0] += 1                       # single-pass kernel + the flagged-tile two-pass launch
         out = self._fact(ws, a.name, B, H, W, dev, stats=False)
         pitch, fblk = out.flat if out.flat is not None else (0, 0)
         L.check(self.lib.mcedm_conv_igemm16(L.ptr_array([att]), 1, L.int_array([0]), L.int_array([0]), L.int_array([0]), 1,

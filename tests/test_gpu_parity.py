@@ -199,6 +199,40 @@ def test_attention_matches_fp32_softmax(L, dev, B, Lq, scale):
     assert rel_l2(chk, ref) < 1e-5
 
 
+@pytest.mark.parametrize("fmt", [1, 0])
+def test_attention_single_pass_overflow_falls_back_to_two_pass(L, dev, fmt):
+    """Inference attention runs ONE pass over the keys with the first key block's row maximum as the softmax shift; a tile
+    whose later keys score far above that (exponent argument > 15: beyond fp16's range) is flagged and redone by the
+    two-pass kernel.  Scores here rise by ~+40 log2 units from key block 0 to the last one in sample 0 (every tile
+    overflows), stay moderate in sample 1 (no tile does); both must match fp32 softmax, and so must the forced two-pass."""
+    import os
+
+    lib = L.lib()
+    B, Lq = 2, 1024
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(B, Lq, 64, generator=g) * 1.5
+    k = torch.randn(B, Lq, 64, generator=g)
+    v = torch.randn(B, Lq, 64, generator=g)
+    k[0] = k[0] * 0.05
+    k[0, 896:] = q[0, :128] * 1.2              # the last key block aligns with the queries: scores ~ 1.2 |q|^2 ~ 170
+    dt = torch.float16 if fmt else torch.bfloat16
+    qkv = torch.cat([q, k, v], dim=2).to(dev).to(dt).contiguous()
+    out = torch.full((B, Lq, 64), float("nan"), device=dev, dtype=dt)
+    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), None, fmt, L.stream_ptr()), "attention")
+    L.check_watchdog()
+    qd, kd, vd = qkv.double().split(64, dim=2)
+    ref = torch.softmax(qd @ kd.transpose(1, 2) / 8.0, dim=2) @ vd
+    tol = 2e-3 if fmt else 8e-3
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out[0].float(), ref[0]) < tol and rel_l2(out[1].float(), ref[1]) < tol
+    # with the log-sum-exp requested (training) the two-pass kernel runs alone: same answer
+    lse = torch.empty(B, Lq, device=dev)
+    out2 = torch.empty_like(out)
+    L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out2), L.ptr(lse), fmt, L.stream_ptr()), "attention")
+    assert rel_l2(out2.float(), ref) < tol
+    assert rel_l2(out[1].float(), out2[1].float()) < tol
+
+
 # ----------------------------------------------------------------------------------------------- K5
 def test_sampler_updates_bit_exact_against_torch_fp64(L, dev):
     lib = L.lib()
