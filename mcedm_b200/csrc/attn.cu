@@ -25,6 +25,12 @@
 // exceeds 1, which fp16 holds up to 2^16.  A CTA whose exponent argument ever exceeds 15 (a score 83 above its first
 // block's maximum: not seen on normalised inputs, but legal) raises its flag and the caller re-runs exactly those tiles
 // with the two-pass kernel, whose CTAs return at once when their flag is clear.
+//
+// H2 (single pass, fp16 operands): after the single pass the softmax warps themselves were the pacer (per element: FFMA,
+// MUFU.EX2, half of a pack, unpack + add for the row sum).  Now the exponent argument is rounded to fp16 PAIRS and one
+// `ex2.approx.f16x2` produces two weights already in operand format (no pack), and the row sums come from the tensor
+// core: l = P . 1 as eight extra N = 16 MMAs per key block against a constant all-ones K-major tile (exactly the sum of
+// the ROUNDED weights the P V product uses).  ~2.5 instructions per element instead of ~8, half the MUFU work.
 //   warp 0 : TMA producer (Q once; K blocks in pass 1; K and V blocks in pass 2; 3-stage ring)
 //   warp 1 : MMA issuer (S double-buffered in TMEM so softmax of block j overlaps QK^T of block j+1)
 //   warps 2-9 : softmax / epilogue: two warps per TMEM lane quarter, each owning one 64-key half of every S block of
@@ -51,7 +57,7 @@ __device__ __forceinline__ float ex2(float x) {
 
 // SINGLE: one pass over the keys (see the header); flags = per-CTA overflow flags, WRITTEN by the single-pass kernel and
 // READ by the two-pass kernel launched after it (NULL: every CTA of the two-pass kernel runs).
-template <bool SINGLE>
+template <bool SINGLE, bool H2 = false>
 __global__ void __launch_bounds__(320, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out,
             float* __restrict__ lse_out, int fmt, unsigned int* err, unsigned int* __restrict__ flags) {
@@ -61,7 +67,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   uint8_t* q_smem = smem;                                  // 16 KB
   uint8_t* kv_smem = q_smem + kTile;                       // stages x (K 16 KB | V 16 KB)
   uint8_t* p_smem = kv_smem + kKvStages * 2 * kTile;       // 2 buffers x 32 KB (2 atoms of 64 keys)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * 2 * kTile);
+  uint8_t* ones_smem = p_smem + 2 * 2 * kTile;            // 2 KB: 16 rows x 64 fp16 ones (B operand of the row-sum MMAs)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones_smem + 2048);
   uint64_t* q_full = bars;            // 1
   uint64_t* o_full = bars + 1;        // 1
   uint64_t* s_full = bars + 2;        // 2
@@ -71,7 +78,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   uint64_t* kv_full = bars + 10;      // stages
   uint64_t* kv_empty = bars + 10 + kKvStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kKvStages);
-  float* xch_m = reinterpret_cast<float*>(p_smem + 2 * 2 * kTile + 256);   // [2 halves][128 rows] partial row maxima
+  float* xch_m = reinterpret_cast<float*>(ones_smem + 2048 + 256);         // [2 halves][128 rows] partial row maxima
   float* xch_l = xch_m + 256;                                              // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,11 +109,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (H2 && warp >= 2) {
+    // all-ones tile (uniform, so the 128-byte swizzle does not matter), made visible to the async proxy
+    reinterpret_cast<uint32_t*>(ones_smem)[threadIdx.x - 64] = 0x3C003C00u;
+    reinterpret_cast<uint32_t*>(ones_smem)[threadIdx.x - 64 + 256] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_l = tmem_base + 320;      // H2: 16 columns, every one the row sum of the rounded weights
 
   if (warp == 0) {
     if (lane == 0) {
@@ -126,6 +140,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     {
       const uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, fmt);
       const uint32_t idesc_o = umma_idesc_16(128, 64, 0, 1, fmt);    // B = V, MN-major
+      const uint32_t idesc_l = umma_idesc_16(128, 16, 0, 0, fmt);    // B = ones, K-major
+      const uint64_t od = umma_desc_k_sw128(smem_u32(ones_smem));
       mbar_wait(q_full, 0, err, 0x1200);
       tc_fence_after();
       const uint32_t q_base = smem_u32(q_smem);
@@ -161,6 +177,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
             for (int kk = 0; kk < 8; ++kk)
               umma_f16(tmem_o, pd + (uint64_t)(((kk >> 2) * kTile + (kk & 3) * 32) >> 4), vd + (uint64_t)((kk * 2048) >> 4),
                        idesc_o, (uint32_t)((jp | kk) != 0));
+            if constexpr (H2) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_f16(tmem_l, pd + (uint64_t)(((kk >> 2) * kTile + (kk & 3) * 32) >> 4), od, idesc_l,
+                         (uint32_t)((jp | kk) != 0));
+            }
             umma_commit(&p_empty[pb]);
             umma_commit(&kv_empty[sp]);
           }
@@ -223,6 +245,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     m = fmaxf(xch_m[row], xch_m[128 + row]);
     const float mc = m * c1;
     float amax = 0.f;                         // SINGLE: largest exponent argument seen (0 at the reference maximum)
+    uint32_t hmax = 0u;                       // H2: the same as a packed fp16 pair
     // ---------------- pass 2: P = exp2(S*c1 - m*c1) -> bf16 -> smem ----------------
     for (int j = 0; j < nblk; ++j) {
       const int it = p2_start + j;
@@ -242,6 +265,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
         for (int u = 0; u < 4; ++u) {
           uint4 o;
           uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+          if constexpr (H2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = fmaf(__uint_as_float(v[u * 8 + 2 * e]), c1, -mc);
+              const float a1 = fmaf(__uint_as_float(v[u * 8 + 2 * e + 1]), c1, -mc);
+              uint32_t hh;
+              asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(a1), "f"(a0));
+              asm("max.NaN.f16x2 %0, %0, %1;" : "+r"(hmax) : "r"(hh));
+              asm("ex2.approx.f16x2 %0, %1;" : "=r"(op[e]) : "r"(hh));
+            }
+            const int unit = ((c & 1) * 4 + u) ^ (row & 7);
+            sts128(atom_row + unit * 16, o);
+            continue;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float a0 = fmaf(__uint_as_float(v[u * 8 + 2 * e]), c1, -mc);
@@ -267,6 +304,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       fence_proxy_async_smem();     // generic-proxy P writes -> visible to the UMMA (async proxy) reads
       mbar_arrive_warp(&p_full[pb]);
     }
+    if constexpr (H2) {
+      const float2 hm = unpack_f16x2(hmax);
+      amax = (hm.x != hm.x || hm.y != hm.y) ? __int_as_float(0x7fc00000) : fmaxf(hm.x, hm.y);
+    }
     if constexpr (SINGLE) {
       // fp16 weights hold exp2(a) up to a < 16; beyond 15 (or a non-finite score) the tile is redone by the two-pass kernel
       if (__any_sync(0xffffffffu, !(amax <= 15.0f)) && lane == 0 && flags) flags[blockIdx.x] = 1u;
@@ -277,6 +318,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     l = xch_l[row] + xch_l[128 + row];
     mbar_wait(o_full, 0, err, 0x1900);
     tc_fence_after();
+    if constexpr (H2) {
+      uint32_t lv[16];
+      tmem_ld_x16(tmem_l + lane_addr, lv);
+      tmem_wait_ld();
+      l = __uint_as_float(lv[0]);
+    }
     const float inv_l = 1.0f / l;
     // saved for the backward: P[i][j] = exp2(S[i][j] * c1 - lse2[i])
     if (lse_out && hsel == 0) lse_out[(long long)b * L + q0 + row] = mc + log2f(l);
@@ -370,27 +417,34 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
   if (rc) return rc;
   unsigned int* err = watchdog_ptr();
   MCEDM_REQUIRE(err != nullptr, "attention: no watchdog word");
-  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 256 + 2048;
+  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 2048 + 256 + 2048;
   static bool attr_set = false;
   if (!attr_set) {
     MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MCEDM_CUDA((cudaFuncSetAttribute(attn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     attr_set = true;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)(B * (L / 128));
   // inference (no log-sum-exp requested): single pass over the keys + a fallback launch whose CTAs return at once
   // unless the single-pass CTA flagged an exponent beyond fp16's range.  MCEDM_ATTN_2PASS=1 forces the two-pass kernel.
-  static int force2 = -1;
+  static int force2 = -1, no_h2 = 0;
   if (force2 < 0) {
     const char* e = getenv("MCEDM_ATTN_2PASS");
     force2 = (e && atoi(e)) ? 1 : 0;
+    const char* h = getenv("MCEDM_ATTN_H2");
+    no_h2 = (h && !atoi(h)) ? 1 : 0;                   // MCEDM_ATTN_H2=0: fp32 exponentials in the single-pass kernel
   }
   if (lse_out == nullptr && !force2) {
     unsigned int* flags = attn_flags(grid);
     MCEDM_REQUIRE(flags != nullptr, "attention: cannot allocate the overflow flags");
-    attn_kernel<true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, op_fmt ? 1 : 0,
-                                               err, flags);
+    if (op_fmt && !no_h2)
+      attn_kernel<true, true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1, err,
+                                                       flags);
+    else
+      attn_kernel<true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
+                                                 op_fmt ? 1 : 0, err, flags);
     MCEDM_CUDA(cudaGetLastError());
     attn_kernel<false><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, op_fmt ? 1 : 0,
                                                 err, flags);
