@@ -511,6 +511,10 @@ MCEDM_API int mcedm_corr_minmax(const double* pred, const float* target, int b, 
 /* -------------------------------------------------------------------------------------------- */
 /* tensor-pipe + shared-memory operand-fetch ceiling: every SM issues n_tiles x 36 tcgen05.mma (M=128, N, K=16, the conv
  * kernels' descriptor pattern) and nothing else; cycles_per_cta[sm] = clock64 ticks (DEVICE int64 [#SMs]). */
+/* Saturation audit of the fp16 activation storage: with MCEDM_DBG=4 in the environment the fused 16-bit convolution
+ * epilogues (conv_rows_fused N=64, conv_flat_fused fast paths) count every accumulator / output value whose magnitude
+ * exceeds 65504 (clamped by the saturating conversion) or is NaN; *host_out receives the count since the last reset. */
+MCEDM_API int mcedm_saturation_count(long long* host_out, int reset, void* stream);
 MCEDM_API int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_cta, void* stream);
 /* issue-queue depth of tcgen05.mma: per iteration n_mma x (M=128, N=192, K=16) + one commit, then `idle` cycles of
  * nothing on the issuing warp; out3_per_cta[sm] = {total, issue, commit} clock64 ticks (DEVICE int64 [#SMs][3]). */

@@ -89,6 +89,7 @@ _PROTOTYPES = {
     "mcedm_masked_mae_mean": [_vp, _i, _i, C.c_longlong, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i,
                               _vp, _vp],
     "mcedm_corr_minmax": [_vp, _vp, _i, C.c_longlong, _i, _vp, _vp, _vp, _vp],
+    "mcedm_saturation_count": [_llp, _i, _vp],
     "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
     "mcedm_probe_mma_queue": [_i, _i, _i, _vp, _vp],
     "mcedm_debug_rows": [_vp],

@@ -57,11 +57,13 @@ __device__ __forceinline__ float ex2(float x) {
 
 // SINGLE: one pass over the keys (see the header); flags = per-CTA overflow flags, WRITTEN by the single-pass kernel and
 // READ by the two-pass kernel launched after it (NULL: every CTA of the two-pass kernel runs).
-template <bool SINGLE, bool H2 = false>
-__global__ void __launch_bounds__(320, 1)
+// KS: softmax warps per TMEM lane quarter (each owns 128 / KS key columns of every S block).  2 for the two-pass /
+// fp32-exponential kernels; 4 for H2, whose per-warp chain (tcgen05.ld -> FFMA -> cvt -> MUFU -> st.shared) was latency-
+// bound at 10 resident warps (ncu: issue slots 29 % active, top stalls long scoreboard / wait / MIO throttle).
+template <bool SINGLE, bool H2 = false, int KS = 2, bool LMMA = false>
+__global__ void __launch_bounds__(64 + 128 * KS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __restrict__ out,
-            float* __restrict__ lse_out, int fmt, unsigned int* err, unsigned int* __restrict__ flags) {
-  if (!SINGLE && flags != nullptr && flags[blockIdx.x] == 0u) return;      // fallback launch: only the flagged tiles
+            float* __restrict__ lse_out, int fmt, unsigned int* err, unsigned int* __restrict__ flags, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                                  // 16 KB
@@ -78,25 +80,35 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   uint64_t* kv_full = bars + 10;      // stages
   uint64_t* kv_empty = bars + 10 + kKvStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kKvStages);
-  float* xch_m = reinterpret_cast<float*>(ones_smem + 2048 + 256);         // [2 halves][128 rows] partial row maxima
-  float* xch_l = xch_m + 256;                                              // [2 halves][128 rows] partial row sums
+  float* xch_m = reinterpret_cast<float*>(ones_smem + 2048 + 256);         // [KS][128 rows] partial row maxima
+  float* xch_l = xch_m + 128 * KS;                                         // [KS][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = L / 128;
-  const int b = blockIdx.x / nblk;
-  const int q0 = (blockIdx.x - b * nblk) * 128;
   const int p2_start = SINGLE ? 0 : nblk;      // first iteration of the exponentiating pass
   const int n_it = p2_start + nblk;
+  // One tile (128 queries of one sample) per CTA when the grid covers all tiles (the single-pass kernel and the
+  // stand-alone two-pass kernel).  The FALLBACK launch of the two-pass kernel (flags != NULL) runs a small grid whose
+  // CTAs stride over the tiles and redo only the flagged ones: with no flag raised — the normal case — it costs a
+  // launch and a few flag reads per CTA instead of 2048 empty 180 KB-shared-memory CTAs (17 us).
+  bool first_tile = true;
+  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
+  if (!SINGLE && flags != nullptr && flags[tile] == 0u) continue;
+  const int b = tile / nblk;
+  const int q0 = (tile - b * nblk) * 128;
 
   if (warp == 0 && lane == 0) {
-    if (SINGLE && flags) flags[blockIdx.x] = 0u;
+    if (SINGLE && flags) flags[tile] = 0u;
+    if (!first_tile) {                       // barriers of the previous tile: every role is past them (__syncthreads below)
+      for (int i = 0; i < 10 + 2 * kKvStages; ++i) mbar_inval(&bars[i]);
+    }
     prefetch_tmap(&tm_qkv);
     mbar_init(q_full, 1);
     mbar_init(o_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);                              // one arrival per softmax warp
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], 4 * KS);                         // one arrival per softmax warp
+      mbar_init(&p_full[i], 4 * KS);
       mbar_init(&p_empty[i], 1);
     }
     for (int i = 0; i < kKvStages; ++i) {
@@ -109,7 +121,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (H2 && warp >= 2) {
+  if (H2 && warp >= 2 && warp < 10) {
     // all-ones tile (uniform, so the 128-byte swizzle does not matter), made visible to the async proxy
     reinterpret_cast<uint32_t*>(ones_smem)[threadIdx.x - 64] = 0x3C003C00u;
     reinterpret_cast<uint32_t*>(ones_smem)[threadIdx.x - 64 + 256] = 0x3C003C00u;
@@ -177,7 +189,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
             for (int kk = 0; kk < 8; ++kk)
               umma_f16(tmem_o, pd + (uint64_t)(((kk >> 2) * kTile + (kk & 3) * 32) >> 4), vd + (uint64_t)((kk * 2048) >> 4),
                        idesc_o, (uint32_t)((jp | kk) != 0));
-            if constexpr (H2) {
+            if constexpr (H2 && LMMA) {
 #pragma unroll
               for (int kk = 0; kk < 8; ++kk)
                 umma_f16(tmem_l, pd + (uint64_t)(((kk >> 2) * kTile + (kk & 3) * 32) >> 4), od, idesc_l,
@@ -194,7 +206,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     }
   } else {
     const int q = warp & 3;
-    const int hsel = (warp - 2) >> 2;          // which 64-key half of every S block this warp owns
+    const int hsel = (warp - 2) >> 2;          // which 128 / KS-key slice of every S block this warp owns
+    constexpr int CPW = 4 / KS;                // 32-column chunks per warp and S block
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float c1 = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
@@ -205,7 +218,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       mbar_wait(&s_full[sb], ns & 1u, err, 0x1600 + sb);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 2 * hsel; c < 2 * hsel + 2; ++c) {
+      for (int c = CPW * hsel; c < CPW * hsel + CPW; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
         tmem_wait_ld();
@@ -226,7 +239,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       mbar_wait(&s_full[0], 0u, err, 0x1650);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 2 * hsel; c < 2 * hsel + 2; ++c) {
+      for (int c = CPW * hsel; c < CPW * hsel + CPW; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + c * 32, v);
         tmem_wait_ld();
@@ -241,8 +254,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     }
     // the two halves of a row exchange their partial maxima
     xch_m[hsel * 128 + row] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(xch_m[row], xch_m[128 + row]);
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * KS) : "memory");
+    m = xch_m[row];
+#pragma unroll
+    for (int k = 1; k < KS; ++k) m = fmaxf(m, xch_m[k * 128 + row]);
     const float mc = m * c1;
     float amax = 0.f;                         // SINGLE: largest exponent argument seen (0 at the reference maximum)
     uint32_t hmax = 0u;                       // H2: the same as a packed fp16 pair
@@ -256,7 +271,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       tc_fence_after();
       uint8_t* prow = p_smem + pb * 2 * kTile + row * 128;
 #pragma unroll 1
-      for (int c = 2 * hsel; c < 2 * hsel + 2; ++c) {
+      for (int c = CPW * hsel; c < CPW * hsel + CPW; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_addr + sb * 128 + c * 32, v);
         tmem_wait_ld();
@@ -274,6 +289,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
               asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(a1), "f"(a0));
               asm("max.NaN.f16x2 %0, %0, %1;" : "+r"(hmax) : "r"(hh));
               asm("ex2.approx.f16x2 %0, %1;" : "=r"(op[e]) : "r"(hh));
+            }
+            if constexpr (!LMMA) {
+              // row sum of the ROUNDED weights: three packed fp16 adds over the 8 values, then fp32 (the fp16 partial of 8
+              // terms carries ~2^-11 relative error, random over the 128 partials of a row)
+              uint32_t s01, s23, s4;
+              asm("add.rn.f16x2 %0, %1, %2;" : "=r"(s01) : "r"(op[0]), "r"(op[1]));
+              asm("add.rn.f16x2 %0, %1, %2;" : "=r"(s23) : "r"(op[2]), "r"(op[3]));
+              asm("add.rn.f16x2 %0, %1, %2;" : "=r"(s4) : "r"(s01), "r"(s23));
+              const float2 sf = unpack_f16x2(s4);
+              l += sf.x + sf.y;
             }
             const int unit = ((c & 1) * 4 + u) ^ (row & 7);
             sts128(atom_row + unit * 16, o);
@@ -310,15 +335,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     }
     if constexpr (SINGLE) {
       // fp16 weights hold exp2(a) up to a < 16; beyond 15 (or a non-finite score) the tile is redone by the two-pass kernel
-      if (__any_sync(0xffffffffu, !(amax <= 15.0f)) && lane == 0 && flags) flags[blockIdx.x] = 1u;
+      if (__any_sync(0xffffffffu, !(amax <= 15.0f)) && lane == 0 && flags) flags[tile] = 1u;
     }
     // ---------------- epilogue: O / l -> bf16 ----------------
     xch_l[hsel * 128 + row] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l = xch_l[row] + xch_l[128 + row];
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * KS) : "memory");
+    l = xch_l[row];
+#pragma unroll
+    for (int k = 1; k < KS; ++k) l += xch_l[k * 128 + row];
     mbar_wait(o_full, 0, err, 0x1900);
     tc_fence_after();
-    if constexpr (H2) {
+    if constexpr (H2 && LMMA) {
       uint32_t lv[16];
       tmem_ld_x16(tmem_l + lane_addr, lv);
       tmem_wait_ld();
@@ -329,7 +356,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     if (lse_out && hsel == 0) lse_out[(long long)b * L + q0 + row] = mc + log2f(l);
     __nv_bfloat16* orow = out + ((long long)b * L + q0 + row) * 64;
 #pragma unroll 1
-    for (int c = hsel; c < hsel + 1; ++c) {
+    for (int c = hsel; c < (hsel < 2 ? hsel + 1 : hsel); ++c) {      // O has two 32-column chunks: slices 0 and 1 store them
       uint32_t v[32];
       tmem_ld_x32(tmem_o + lane_addr + c * 32, v);
       tmem_wait_ld();
@@ -351,6 +378,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  first_tile = false;
+  __syncthreads();
+  }   // tile loop
 }
 
 // CUDA-core fp32 checker (tests only): one warp per query.
@@ -417,42 +447,56 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
   if (rc) return rc;
   unsigned int* err = watchdog_ptr();
   MCEDM_REQUIRE(err != nullptr, "attention: no watchdog word");
-  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 2048 + 256 + 2048;
+  const int smem = 1024 + kTile + kKvStages * 2 * kTile + 4 * kTile + 2048 + 256 + 4096;
   static bool attr_set = false;
   if (!attr_set) {
     MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MCEDM_CUDA(cudaFuncSetAttribute(attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MCEDM_CUDA((cudaFuncSetAttribute(attn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    MCEDM_CUDA((cudaFuncSetAttribute(attn_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+    MCEDM_CUDA((cudaFuncSetAttribute(attn_kernel<true, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
     attr_set = true;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)(B * (L / 128));
   // inference (no log-sum-exp requested): single pass over the keys + a fallback launch whose CTAs return at once
   // unless the single-pass CTA flagged an exponent beyond fp16's range.  MCEDM_ATTN_2PASS=1 forces the two-pass kernel.
-  static int force2 = -1, no_h2 = 0;
+  static int force2 = -1, no_h2 = 0, ks4 = 1, lmma = 0;
   if (force2 < 0) {
     const char* e = getenv("MCEDM_ATTN_2PASS");
     force2 = (e && atoi(e)) ? 1 : 0;
     const char* h = getenv("MCEDM_ATTN_H2");
     no_h2 = (h && !atoi(h)) ? 1 : 0;                   // MCEDM_ATTN_H2=0: fp32 exponentials in the single-pass kernel
+    const char* k4 = getenv("MCEDM_ATTN_KS");
+    ks4 = (k4 && atoi(k4) == 2) ? 0 : 1;               // MCEDM_ATTN_KS=2: 8 softmax warps instead of 16
+    const char* lm = getenv("MCEDM_ATTN_LMMA");
+    lmma = (lm && atoi(lm)) ? 1 : 0;                   // MCEDM_ATTN_LMMA=1 (with KS=2): row sums from P . 1 MMAs
+    if (lmma) ks4 = 0;
   }
   if (lse_out == nullptr && !force2) {
     unsigned int* flags = attn_flags(grid);
     MCEDM_REQUIRE(flags != nullptr, "attention: cannot allocate the overflow flags");
-    if (op_fmt && !no_h2)
+    if (op_fmt && !no_h2 && ks4)
+      attn_kernel<true, true, 4><<<grid, 576, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1,
+                                                          err, flags, (int)grid);
+    else if (op_fmt && !no_h2 && lmma)
+      attn_kernel<true, true, 2, true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
+                                                                1, err, flags, (int)grid);
+    else if (op_fmt && !no_h2)
       attn_kernel<true, true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1, err,
-                                                       flags);
+                                                       flags, (int)grid);
     else
       attn_kernel<true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
-                                                 op_fmt ? 1 : 0, err, flags);
+                                                 op_fmt ? 1 : 0, err, flags, (int)grid);
     MCEDM_CUDA(cudaGetLastError());
-    attn_kernel<false><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, op_fmt ? 1 : 0,
-                                                err, flags);
+    const unsigned fb_grid = grid < (unsigned)num_sms() ? grid : (unsigned)num_sms();
+    attn_kernel<false><<<fb_grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
+                                                   op_fmt ? 1 : 0, err, flags, (int)grid);
     MCEDM_CUDA(cudaGetLastError());
     return 0;
   }
   attn_kernel<false><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0,
-                                              err, nullptr);
+                                              err, nullptr, (int)grid);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

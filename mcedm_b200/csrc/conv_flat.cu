@@ -343,6 +343,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive_warp(&acc_empty[buf]);
+        if (p.dbg & 4) {                          // the accumulator itself is rounded to fp16 for the staging tile
+          float acc[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+          sat_audit(p.err, acc);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 o;
@@ -373,6 +379,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) a[e] *= m;
+          if (p.dbg & 4) sat_audit(p.err, a);
           sa1 += (a[0] + a[1]) + (a[2] + a[3]);
           sa2 += (a[0] * a[0] + a[1] * a[1]) + (a[2] * a[2] + a[3] * a[3]);
           sb1 += (a[4] + a[5]) + (a[6] + a[7]);

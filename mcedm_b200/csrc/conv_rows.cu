@@ -593,6 +593,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         tc_fence_before();
         mbar_arrive_warp(&acc_empty[buf]);
         if (p.dbg & 2) continue;                  // bring-up: drain-only epilogue
+        if (p.dbg & 4) {                          // the accumulator itself is rounded to fp16 for the staging tile
+          float acc[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+          sat_audit(p.err, acc);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 o;
@@ -624,6 +630,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           sa2 += (a[0] * a[0] + a[1] * a[1]) + (a[2] * a[2] + a[3] * a[3]);
           sb1 += (a[4] + a[5]) + (a[6] + a[7]);
           sb2 += (a[4] * a[4] + a[5] * a[5]) + (a[6] * a[6] + a[7] * a[7]);
+          if (p.dbg & 4) sat_audit(p.err, a);
           uint4 o;
           o.x = pack_f16x2(a[0], a[1]);
           o.y = pack_f16x2(a[2], a[3]);

@@ -44,6 +44,9 @@ __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -269,6 +272,16 @@ __device__ __forceinline__ uint32_t silu_affine_h2(uint32_t x2, uint32_t a2, uin
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
   asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(h), "r"(t));
   return y;
+}
+// Saturation audit of the fp16 activation storage (MCEDM_DBG & 4): counts values whose magnitude exceeds the largest
+// finite fp16 (65504; the packing conversions clamp them, `satfinite`) into word 8 of the watchdog buffer, so that a
+// residual stream drifting out of fp16's range is REPORTED (mcedm_saturation_count) instead of silently clipped.
+template <int NV>
+__device__ __forceinline__ void sat_audit(unsigned int* err, const float (&a)[NV]) {
+  unsigned int c = 0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) c += (fabsf(a[i]) > 65504.0f || a[i] != a[i]) ? 1u : 0u;
+  if (c) atomicAdd(err + 8, c);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }

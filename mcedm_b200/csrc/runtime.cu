@@ -144,4 +144,21 @@ int mcedm_check_watchdog(void* stream) {
   return 0;
 }
 
+// Saturation audit (MCEDM_DBG=4, see ptx.cuh sat_audit): number of activation values beyond fp16's range that the fused
+// 16-bit convolution epilogues clamped since the last reset.
+int mcedm_saturation_count(long long* host_out, int reset, void* stream) {
+  unsigned int* p = mcedm::watchdog_ptr();
+  if (!p) return mcedm::fail(-2, "watchdog word unavailable");
+  unsigned int h = 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MCEDM_CUDA(cudaMemcpyAsync(&h, p + 8, sizeof(h), cudaMemcpyDeviceToHost, s));
+  MCEDM_CUDA(cudaStreamSynchronize(s));
+  if (host_out) *host_out = (long long)h;
+  if (reset) {
+    MCEDM_CUDA(cudaMemsetAsync(p + 8, 0, sizeof(h), s));
+    MCEDM_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
 }  // extern "C"
