@@ -709,8 +709,12 @@ def measure_training(args, cfg, dev, rank, world, barrier):
 
 
 if __name__ == "__main__":
-    # stdout carries exactly ONE JSON line: anything a library prints on the way goes to stderr
-    _STDOUT = sys.stdout
+    # stdout carries exactly ONE JSON line: anything a library prints on the way goes to stderr — at the file-descriptor
+    # level, because NCCL writes its version banner to fd 1 from C (seen in front of the N = 2 line)
+    sys.stdout.flush()
+    _real_fd = os.dup(1)
+    os.dup2(2, 1)
+    _STDOUT = os.fdopen(_real_fd, "w")
     sys.stdout = sys.stderr
     a = parse()
     if a.impl == "reference":
