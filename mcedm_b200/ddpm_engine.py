@@ -71,6 +71,7 @@ class DdpmEngine(FusedMixin):
     _conv = UNetEngine._conv
     _param_key = UNetEngine._param_key
     forward_static = UNetEngine.forward_static
+    _forward_static = UNetEngine._forward_static
     forward = UNetEngine.forward
 
     def __init__(self, net):

@@ -219,9 +219,26 @@ class FusedMixin:
         self._ss_rows = Bemb
         emb_stride = 128 if Bemb == B and B > 1 else 0
         ss = ws["ss"] = self._fbuf(ws, "ss_buf", (self.n_aff * B * 128,), torch.float32, dev)
+        if getattr(self, "_ss_external", False):
+            # the caller placed this evaluation's (scale | shift) rows in `ss` (UNetEngine.embedding_table): one noise
+            # level for the whole batch, laid out as [n_aff][1][128]
+            Bemb, emb_stride = 1, 0
+            self._ss_rows = 1
+        else:
+            self._launch_emb(nl, Bemb, ss, st)
+        self._launch_rest_fused(x, cond, out, ws, B, H, dev, emb_stride, st)
+        return out
+
+    def _launch_emb(self, nl, Bemb, ss, st):
+        lib = self.lib
         L.check(lib.mcedm_emb_mlp(L.ptr(nl), L.ptr(self.freqs), L.ptr(self.w_m0), L.ptr(self.b_m0), L.ptr(self.w_m1),
                                   L.ptr(self.b_m1), L.ptr(self.aff_w), L.ptr(self.aff_b), self.n_aff, Bemb, None,
                                   L.ptr(ss), st), "emb_mlp")
+
+    def _launch_rest_fused(self, x, cond, out, ws, B, H, dev, emb_stride, st):
+        u = self.unet
+        lib = self.lib
+        W = 128
         t0 = self._fact(ws, "conv_in", B, H, W, dev)
         if self.w_in_tc is not None:
             # first conv on the tensor cores: horizontal taps folded into K by builder warps, vertical taps stacked into N

@@ -586,7 +586,13 @@ class PlMcedm(LightningModule):
         x_in_c, cond_c = engine._check_inputs(x_in, nl, cond)[0::2]
         assert x_in_c.data_ptr() == x_in.data_ptr()
 
+        # all (scale | shift) rows of the trajectory's noise levels from one embedding-MLP launch; an evaluation then
+        # only copies its row (engine.embedding_table); plans that do not take rows evaluate the MLP per evaluation
+        table = engine.embedding_table(c_noise_dev) if getattr(engine, "supports_ss_rows", False) else None
+
         def net_eval(k):
+            if table is not None:
+                return engine.forward_static(x_in, nl, cond_c, F_buf, use_graph=self.use_cuda_graph, ss_rows=table[:, k])
             nl.copy_(c_noise_dev[k:k + 1])
             return engine.forward_static(x_in, nl, cond_c, F_buf, use_graph=self.use_cuda_graph)
 

@@ -587,3 +587,34 @@ def test_full_size_micro_batch_properties(dev):
     xs_sub = pl.sample_edm(torch.zeros(hi - lo, 2, 128, 128, device=dev), cond[lo:hi].contiguous(),
                            mask[lo:hi].contiguous(), sp, return_last=True)
     assert torch.equal(xs_sub, xs[lo:hi])
+
+
+def test_precomputed_embedding_rows_are_bit_identical(dev):
+    """The sampler evaluates the noise-embedding MLP + per-block affines for all of a trajectory's noise levels in one
+    launch (UNetEngine.embedding_table) and hands each evaluation its row; the fields must be bit-identical to evaluating
+    the MLP inside every evaluation, with and without CUDA-graph replay."""
+    import copy
+
+    from common import NoiseFeed
+
+    pl, cfg = stress_module()
+    pl = pl.to(dev).eval()
+    sp = copy.deepcopy(cfg.diff_sampler)
+    sp.timesteps = 3
+    g = torch.Generator().manual_seed(3)
+    cond = torch.randn(2, 2, 128, 128, generator=g).to(dev)
+    mask = torch.zeros(2, 2, 128, 128)
+    mask[0, 1] = 1.0
+    mask[1, 0] = 1.0
+    mask = mask.to(dev)
+    hu = torch.zeros(2, 2, 128, 128, device=dev)
+    eng = pl.ema_model.ma_model.engine()
+    outs = []
+    for rows, graph in ((True, True), (False, True), (True, False)):
+        eng.supports_ss_rows = rows
+        pl.use_cuda_graph = graph
+        pl._noise_hook = NoiseFeed(17).hook
+        outs.append(pl.sample_edm(hu, cond, mask, sp))
+    del eng.supports_ss_rows
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
