@@ -48,6 +48,9 @@
 #ifndef MCEDM_EPI16
 #define MCEDM_EPI16 0
 #endif
+#ifndef MCEDM_DUAL
+#define MCEDM_DUAL 1   // two MMA-issuing warps taking alternate input rows (stacked kernels), see the MMA issuer
+#endif
 #ifndef MCEDM_XF_H2
 #define MCEDM_XF_H2 0   // GroupNorm+SiLU transform in packed half arithmetic: 3 instructions per 2 elements instead of 9, but
                         // measured +2 % only (the row is bounded by shared-memory bytes, not by the transform's ALU work) at
@@ -96,7 +99,10 @@ struct RowsCfg {
   // GroupNorm+SiLU transform warps (after the epilogue warps); the 16-wide head conv has a quarter of the MMA / epilogue
   // work per row, so there the transform is the pacer and gets eight
   static constexpr int XF_WARPS = FUSED ? ((N == 16 || (N == 64 && MCEDM_XF8)) ? 8 : 4) : 0;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
+  // DUAL: a second MMA-issuing warp (the last warp of the CTA) for the stacked kernels
+  static constexpr bool DUAL = FUSED && (N == 64 || N == 16) && MCEDM_DUAL;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
+  static constexpr int MMA2_WARP = DUAL ? THREADS / 32 - 1 : -1;
   // fused N = 64: the epilogue transposes through a 16-BIT staging tile (32 pixels x 64 B per warp), see the epilogue
   static constexpr bool EPI_H16 = FUSED && N == 64 && !MCEDM_EPI16;
   static constexpr int STAGE_BYTES = EPI_H16 ? EPI_WARPS * 2048 : EPI_WARPS * 32 * CH * 4;
@@ -173,7 +179,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   uint64_t* c_full = h_empty + p.n_slots;   // n_cslots
   uint64_t* c_empty = c_full + p.n_cslots;
   uint64_t* h_ready = c_empty + p.n_cslots;   // n_slots (FUSED: row transformed and visible to the async proxy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + p.n_slots);
+  uint64_t* turn = h_ready + p.n_slots;       // 2 (DUAL: hand-over of the issue order between the two MMA warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,6 +208,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 1);
     }
+    mbar_init(&turn[0], 1);
+    mbar_init(&turn[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -256,7 +265,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         g_rows_dbg[blockIdx.x][7] = clock64() - dbg_t0;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == Cfg::MMA2_WARP) {
     // ====================================== MMA issuer ======================================
     // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one
     // elected lane issues each tcgen05 instruction.  (Running this under `if (lane == 0)` made ptxas
@@ -291,12 +300,46 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       uint32_t t0 = 0;                      // tile counter of the current segment's first output row
       long long dbg_w1 = 0, dbg_w2 = 0;
       const long long dbg_t0 = clock64();
+      // ---------------------------------------------------------------------------------------------------------
+      // DUAL issue.  tcgen05.mma queues only ~2 instructions deep (scripts/probe_mma_queue.py: cycles per row = tensor
+      // time + whatever the issuing thread spends NOT issuing), and one row costs this warp ~1100 cycles of waits,
+      // descriptor arithmetic, commits and loop control next to its 1152 cycles of MMAs: the tensor pipe idled for
+      // almost half of every row.  Two warps now take alternate input rows ("steps").  Both run the identical control
+      // flow and counters; a warp executes only the steps of its parity.  Accumulation order matters (the first MMA
+      // into an output row's accumulator must precede every later contribution, and those come from the next two
+      // steps), so the issue ORDER is handed over through two mbarriers: after its last MMA of step s the issuing lane
+      // arrives on turn[other], which the other warp waits for before issuing step s + 1; while it issues, this warp
+      // does its commits and the waits / arithmetic of step s + 2.  A commit tracks only its own thread's MMAs, but the
+      // pipe executes in issue order, so when step s's MMAs are complete so are those of step s - 1.
+      // (MCEDM_DBG & 8: single issuer, the second warp idles: A/B switch.)
+      // ---------------------------------------------------------------------------------------------------------
+      const bool dual = Cfg::DUAL && !(p.dbg & 8);
+      const uint32_t my_par = (warp == 1) ? 0u : 1u;
+      if (!dual && warp != 1) goto mma_done;
+      {
+      uint32_t step = 0, my_n = 0;          // global step counter / steps issued by this warp
       long long r = r_begin;
       while (r < r_end) {
         const int b = (int)(r / p.H);
         const int y0 = (int)(r - (long long)b * p.H);
         const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
-        for (int k = 0; k < R + 2; ++k) {
+        for (int k = 0; k < R + 2; ++k, ++step) {
+          const bool ctr_step = p.n_ctr > 0 && k >= 2;
+          if (dual && (step & 1u) != my_par) {       // the other warp's step: advance the ring counters only
+            if (++hs == ns) {
+              hs = 0;
+              hph ^= 1u;
+            }
+            if (ctr_step) {
+              for (int s = 0; s < p.n_ctr; ++s) {
+                if (++cs == (uint32_t)p.n_cslots) {
+                  cs = 0;
+                  cph ^= 1u;
+                }
+              }
+            }
+            continue;
+          }
           if (k < R) {                      // output row k receives its first contribution from this input row
             const uint32_t tn = t0 + (uint32_t)k;
             timed_wait(&acc_empty[tn & 7u], ((tn >> 3) & 1u) ^ 1u, p.err, 0x2400 + (tn & 7u), dbg_w1, (p.dbg & 32) != 0);
@@ -330,6 +373,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           const uint32_t d1 = tmem_base + ((blk0 + (uint32_t)split) & 7u) * (uint32_t)N;   // piece after the wrap
           const uint32_t wrow = w_lo + (uint32_t)kyA * (Cfg::W_SEG_BYTES >> 4);
           const bool fresh = kyA == 0;        // output row k starts here: its very first MMA must not accumulate
+          if (dual) {
+            // issue order: step s - 1 (other warp) must have been issued.  Warp 0's n-th step waits for the other's n-th
+            // arrival (none for n = 0), warp 1's n-th step for the (n + 1)-th.
+            if (my_par == 1u) mbar_wait(&turn[1], my_n & 1u, p.err, 0x2a01);
+            else if (my_n > 0) mbar_wait(&turn[0], (my_n - 1u) & 1u, p.err, 0x2a00);
+          }
           const long long dbg_c0 = (p.dbg & 64) ? clock64() : 0;
           if (nky == 3 && split == 3) {
             // interior row, contiguous window: N = 64 (fresh) + N = 128, then 11 x N = 192
@@ -368,6 +417,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
           const long long dbg_c1 = (p.dbg & 64) ? clock64() : 0;
           if (elect_one()) {
+            if (dual && !(p.n_ctr > 0 && k >= 2)) mbar_arrive(&turn[my_par ^ 1u]);   // hand the issue order over
             umma_commit(&h_empty[hs]);                       // an input row is consumed entirely by its own step
             if (k >= 2) {
               const uint32_t td = t0 + (uint32_t)(k - 2);    // output row k-2 is complete after this step
@@ -380,6 +430,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                   for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_base + blk * (uint32_t)N, ad + 2 * ks, bd + 2 * ks, idesc1, 1u);
                   umma_commit(&c_empty[cidx[s]]);
                 }
+                if (dual) mbar_arrive(&turn[my_par ^ 1u]);   // (centre MMAs of this step issued: hand over now)
               }
               umma_commit(&acc_full[td & 7u]);
             }
@@ -390,6 +441,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             dbg_w2 += dbg_c2 - dbg_c1;                       // commits
           }
           __syncwarp();
+          ++my_n;
           if (++hs == ns) {
             hs = 0;
             hph ^= 1u;
@@ -406,6 +458,11 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         t0 += (uint32_t)R;
         r += R;
       }
+      }
+    mma_done:
+      if (warp != 1) {
+        // (second issuer: no instrumentation)
+      } else
       if (p.dbg & 64) {                                      // only the elected lane measured: take the warp maximum
         for (int off = 16; off; off >>= 1) {
           const long long o1 = __shfl_xor_sync(0xffffffffu, dbg_w1, off), o2 = __shfl_xor_sync(0xffffffffu, dbg_w2, off);
@@ -413,7 +470,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           dbg_w2 = o2 > dbg_w2 ? o2 : dbg_w2;
         }
       }
-      if ((p.dbg & 96) && lane == 0) {
+      if ((p.dbg & 96) && lane == 0 && warp == 1) {
         g_rows_dbg[blockIdx.x][1] = dbg_w1;
         g_rows_dbg[blockIdx.x][2] = dbg_w2;
         g_rows_dbg[blockIdx.x][6] = clock64() - dbg_t0;
@@ -795,7 +852,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
     }
     }
-  } else {
+  } else if (warp < 2 + Cfg::EPI_WARPS + Cfg::XF_WARPS) {
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
     // halo row; the chunk's physical position follows SWIZZLE_128B: chunk ^ (pixel row & 7) (slots are 1 KB aligned).
