@@ -32,6 +32,9 @@
 #include <cuda_bf16.h>
 #include <cstdlib>
 
+#ifndef MCEDM_DUAL
+#define MCEDM_DUAL 1   // two MMA-issuing warps taking alternate tiles (fused kernel), see conv_rows.cu
+#endif
 #ifndef MCEDM_XF_H2
 #define MCEDM_XF_H2 0   // GroupNorm+SiLU transform in packed half arithmetic (see conv_rows.cu: +2 % speed, 2.5x the error: off)
 #endif
@@ -68,7 +71,9 @@ struct FlatCfg {
   static constexpr int W_SEG_BYTES = N * 128;
   static constexpr int EPI_WARPS = 4 * NCH;
   static constexpr int XF_WARPS = FUSED ? 4 : 0;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
+  static constexpr bool DUAL = FUSED && MCEDM_DUAL;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
+  static constexpr int MMA2_WARP = DUAL ? THREADS / 32 - 1 : -1;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;   // (the 16-bit fast-path epilogue uses half of it)
   static constexpr int ACC_BUFS = 4;
   static constexpr int TMEM_COLS = (ACC_BUFS * N <= 256) ? 256 : 512;
@@ -168,7 +173,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   uint64_t* c_full = acc_empty + Cfg::ACC_BUFS;                 // S
   uint64_t* c_empty = c_full + S;                               // S
   uint64_t* c_ready = c_empty + S;                              // S (FUSED: chunk transformed, visible to the MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_ready + S);
+  uint64_t* turn = c_ready + S;                                 // 2 (DUAL: issue-order hand-over between the MMA warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -189,6 +195,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       mbar_init(&c_empty[i], 1);
       mbar_init(&c_ready[i], FUSED ? Cfg::XF_WARPS : 1);
     }
+    mbar_init(&turn[0], 1);
+    mbar_init(&turn[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -216,9 +224,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         if (mirror) tma_load_2d(ring + (S + slot) * kChunkBytes, &tm_a, &c_full[slot], 0, (int)row0);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == Cfg::MMA2_WARP) {
     // ====================================== MMA issuer ======================================
     // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
+    // DUAL (fused kernel): two warps take alternate tiles.  Tiles own separate accumulators, but the chunk ring is
+    // released by commits that track only their own thread's MMAs, so the issue ORDER is handed over exactly as in
+    // conv_rows.cu (the pipe executes in issue order: when tile j is complete so is tile j - 1).  MCEDM_DBG & 8: single.
     // lean issue loop (see conv_rows.cu): wrap-around ring counters, one election per tile, immediate offsets
     {
       const uint32_t idesc = umma_idesc_16(128, N, 0, 0, fmt);
@@ -234,7 +245,14 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       for (int t = 0; t < 9; ++t) tap_off[t] = ((t / 3 - 1) * p.P + (t % 3 - 1)) * 8;
       uint32_t slot = 0, wslot = 0, wph = 0;
       int waited = 0;
-      for (int j = 0; j < n_tiles; ++j) {
+      const bool dual = Cfg::DUAL && !(p.dbg & 8);
+      const uint32_t my_par = (warp == 1) ? 0u : 1u;
+      uint32_t my_n = 0;
+      for (int j = (!dual && warp != 1) ? n_tiles : 0; j < n_tiles; ++j) {
+        if (dual && ((uint32_t)j & 1u) != my_par) {              // the other warp's tile: only the ring position moves
+          slot = (slot + 1 == (uint32_t)S) ? 0u : slot + 1;
+          continue;
+        }
         const uint32_t buf = (uint32_t)j % Cfg::ACC_BUFS, aph = ((uint32_t)j / Cfg::ACC_BUFS) & 1u;
         mbar_wait(&acc_empty[buf], aph ^ 1u, p.err, 0x3300 + buf);
         while (waited < j + 3) {
@@ -255,6 +273,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         uint32_t al[9];
 #pragma unroll
         for (int t = 0; t < 9; ++t) al[t] = centre + (uint32_t)tap_off[t];
+        if (dual) {
+          if (my_par == 1u) mbar_wait(&turn[1], my_n & 1u, p.err, 0x3a01);
+          else if (my_n > 0) mbar_wait(&turn[0], (my_n - 1u) & 1u, p.err, 0x3a00);
+        }
         if (elect_one()) {
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
@@ -265,6 +287,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             umma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
             umma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
           }
+          if (dual) mbar_arrive(&turn[my_par ^ 1u]);      // tile j issued: the other warp may issue tile j + 1
           umma_commit(&c_empty[slot]);        // chunk j has no further user
           if (j == n_tiles - 1) {
             umma_commit(&c_empty[s1]);
@@ -273,6 +296,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           umma_commit(&acc_full[buf]);
         }
         __syncwarp();
+        ++my_n;
         slot = s1;
       }
     }
@@ -509,7 +533,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       __syncwarp();
     }
     }
-  } else {
+  } else if (warp < 2 + Cfg::EPI_WARPS + Cfg::XF_WARPS) {
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk jc = t & 7 (channels 8jc .. 8jc+7) of positions (t >> 3) + 16 i of every
     // 128-position chunk; physical 16-byte slot = jc ^ (position & 7) (SWIZZLE_128B, 1 KB-aligned chunk slots).
