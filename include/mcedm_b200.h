@@ -454,6 +454,23 @@ MCEDM_API int mcedm_ema_update(float* ema, const float* p, long long n, float be
 MCEDM_API int mcedm_pack_gather(const float* base, const long long* idx_a, const long long* idx_b, long long n16,
                                 long long n32, int fmt, void* dst16, float* dst32, void* stream);
 
+/* DDIM sampler with known-region replacement and repeats — PlDdim.sample_with_repeat (models/ddim.py:808-913).
+ * fp32 state [total] elements, known_mask == 1 where the ground truth hu is imposed; bit-identical to the torch
+ * expressions.  Scalars are the fp32 values of sqrt(a_t), sqrt(1 - a_t), sqrt(a_next), c1, c2 the reference forms
+ * (:866-867, :885-891).
+ *   mcedm_ddim_init: x = (hu*sqrt_a + noise*sqrt_1ma)*mask + noise*(1 - mask)                          (:842-843)
+ *   mcedm_ddim_x0:   x0 = (xt - et*sqrt_1ma)/sqrt_a; x0 = hu*mask + x0*(1 - mask); xt_out (NULL: skip) =
+ *                    sqrt_a*x0 + sqrt_1ma*et, the re-noised input of the next repeat                  (:876-883)
+ *   mcedm_ddim_next: xt' = sqrt_a_next*x0 [+ c1*rand] + c2*et; x_next = (sqrt_a_next*hu + c2*noise)*mask + xt'*(1 - mask)
+ *                    (rand_or_null NULL for eta == 0)                                                 (:885-895) */
+MCEDM_API int mcedm_ddim_init(const float* hu, const float* noise, const float* known_mask, float sqrt_a, float sqrt_1ma,
+                              long long total, float* x, void* stream);
+MCEDM_API int mcedm_ddim_x0(const float* xt, const float* et, const float* hu, const float* known_mask, float sqrt_a,
+                            float sqrt_1ma, long long total, float* x0_out, float* xt_out, void* stream);
+MCEDM_API int mcedm_ddim_next(const float* x0, const float* et, const float* hu, const float* noise,
+                              const float* known_mask, const float* rand_or_null, float sqrt_a_next, float c1, float c2,
+                              long long total, float* x_next, void* stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* K7  DDPM U-Net pieces (models/ddim_blocks.py:222-470 `Model`; its convolutions and attention run   */
 /*     on the K1f / K3 kernels above)                                                               */

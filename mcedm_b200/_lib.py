@@ -78,6 +78,9 @@ _PROTOTYPES = {
     "mcedm_edm_correct_guided": [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, C.c_longlong, _vp, _vp],
     "mcedm_edm_vp_init": [_vp, _vp, _vp, _f, _f, _d, C.c_longlong, _vp, _vp],
     "mcedm_edm_repaint_blend": [_vp, _vp, _vp, _f, _f, C.c_longlong, _vp, _vp],
+    "mcedm_ddim_init": [_vp, _vp, _vp, _f, _f, C.c_longlong, _vp, _vp],
+    "mcedm_ddim_x0": [_vp, _vp, _vp, _vp, _f, _f, C.c_longlong, _vp, _vp, _vp],
+    "mcedm_ddim_next": [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, C.c_longlong, _vp, _vp],
     "mcedm_swe_fv_loss": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp,
                           _vp],
     "mcedm_swe_fv_grad": [_vp, _i, _llp, _vp, _i, _llp, _i, _f, _f, _f, _f, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp],

@@ -165,6 +165,47 @@ __global__ void edm_repaint_blend_kernel(const float* __restrict__ hu, const flo
 
 static inline unsigned blocks_for(long long total) { return (unsigned)((total + 255) / 256); }
 
+// ---- DDIM sampler with known-region replacement and repeats: PlDdim.sample_with_repeat (models/ddim.py:808-913) -------
+// fp32 state, every operation in torch's evaluation order (explicit _rn intrinsics: bit-identical to the expressions).
+// x = (hu*sa + noise*s1)*mask + noise*(1-mask)    (:842-843; sa = sqrt(a_T-1), s1 = sqrt(1 - a_T-1); mask == 1 KNOWN)
+__global__ void ddim_init_kernel(const float* __restrict__ hu, const float* __restrict__ noise,
+                                 const float* __restrict__ mask, float sa, float s1, long long total,
+                                 float* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = mask[i], nz = noise[i];
+  const float known = __fadd_rn(__fmul_rn(hu[i], sa), __fmul_rn(nz, s1));
+  x[i] = __fadd_rn(__fmul_rn(known, m), __fmul_rn(nz, __fsub_rn(1.0f, m)));
+}
+
+// x0 = (xt - et*s1)/sa ; x0 = hu*mask + x0*(1-mask) ; optionally xt' = sa*x0 + s1*et   (:876-883)
+__global__ void ddim_x0_kernel(const float* __restrict__ xt, const float* __restrict__ et, const float* __restrict__ hu,
+                               const float* __restrict__ mask, float sa, float s1, long long total,
+                               float* __restrict__ x0_out, float* __restrict__ xt_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = mask[i], e = et[i];
+  float x0 = __fdiv_rn(__fsub_rn(xt[i], __fmul_rn(e, s1)), sa);
+  x0 = __fadd_rn(__fmul_rn(hu[i], m), __fmul_rn(x0, __fsub_rn(1.0f, m)));
+  x0_out[i] = x0;
+  if (xt_out) xt_out[i] = __fadd_rn(__fmul_rn(sa, x0), __fmul_rn(s1, e));
+}
+
+// xt_next = sa_n*x0 [+ c1*rand] + c2*et ; known = sa_n*hu + c2*noise ; x = known*mask + xt_next*(1-mask)   (:885-895)
+__global__ void ddim_next_kernel(const float* __restrict__ x0, const float* __restrict__ et, const float* __restrict__ hu,
+                                 const float* __restrict__ noise, const float* __restrict__ mask,
+                                 const float* __restrict__ rnd, float sa_n, float c1, float c2, long long total,
+                                 float* __restrict__ x_next) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float m = mask[i];
+  float xn = __fmul_rn(sa_n, x0[i]);
+  if (rnd) xn = __fadd_rn(xn, __fmul_rn(c1, rnd[i]));
+  xn = __fadd_rn(xn, __fmul_rn(c2, et[i]));
+  const float known = __fadd_rn(__fmul_rn(sa_n, hu[i]), __fmul_rn(c2, noise[i]));
+  x_next[i] = __fadd_rn(__fmul_rn(known, m), __fmul_rn(xn, __fsub_rn(1.0f, m)));
+}
+
 }  // namespace mcedm
 
 extern "C" int mcedm_edm_init(const float* noise, const float* cond, int Ccond, const float* mask, double t0, int B,
@@ -270,6 +311,37 @@ extern "C" int mcedm_edm_repaint_blend(const float* hu, const float* noise, cons
   using namespace mcedm;
   edm_repaint_blend_kernel<<<blocks_for(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       hu, noise, mask, sqrt_a, sqrt_1ma, total, x);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_ddim_init(const float* hu, const float* noise, const float* known_mask, float sqrt_a, float sqrt_1ma,
+                               long long total, float* x, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(total >= 1, "ddim_init: empty");
+  ddim_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      hu, noise, known_mask, sqrt_a, sqrt_1ma, total, x);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_ddim_x0(const float* xt, const float* et, const float* hu, const float* known_mask, float sqrt_a,
+                             float sqrt_1ma, long long total, float* x0_out, float* xt_out, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(total >= 1, "ddim_x0: empty");
+  ddim_x0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      xt, et, hu, known_mask, sqrt_a, sqrt_1ma, total, x0_out, xt_out);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_ddim_next(const float* x0, const float* et, const float* hu, const float* noise,
+                               const float* known_mask, const float* rand_or_null, float sqrt_a_next, float c1, float c2,
+                               long long total, float* x_next, void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(total >= 1, "ddim_next: empty");
+  ddim_next_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x0, et, hu, noise, known_mask, rand_or_null, sqrt_a_next, c1, c2, total, x_next);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

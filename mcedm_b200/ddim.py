@@ -20,8 +20,11 @@ here — the opposite of PlMcedm).  Scalars (sigma grid look-ups, alpha-bar valu
 reference's own torch expressions on CPU tensors.  Mask polarity, `t.long()` truncation of a *sigma* used as a timestep
 index (:989, :1029) and the `t_hat` re-noising rule (:1035) are reproduced as they are.
 
-Not mirrored: the DDPM noise-prediction training loss and the DDIM samplers (`sample`, `sample_with_repeat`), PDE
-guidance (`guide_dx`) and `dx_cond` for this module.
+    sample_with_repeat (DDIM steps on the VP schedule, known region re-imposed on every x0 prediction and every x_t,
+                n_repeat evaluations per timestep, self-conditioning on the previous x0 prediction)   :808-913
+
+Not mirrored: the DDPM noise-prediction training loss, the plain DDIM sampler `sample` (no conditioning), PDE guidance
+(`guide_dx`) and `dx_cond` for this module.
 """
 from __future__ import annotations
 
@@ -257,6 +260,83 @@ class PlDdim(PlMcedm):
                 xs.append(x_cur.clone())
         xs = torch.stack(xs, dim=0) if xs is not None else x_cur.clone().unsqueeze(0)
         return rearrange(xs, "t b c h w -> b t h w c")
+
+    @torch.no_grad()
+    def sample_with_repeat(self, h, u, sparams, return_last=True, guide_dx=False):
+        """PlDdim.sample_with_repeat (:808-913) on the kernels: returns (xs, x0_preds), each [b, t, h, w, c] float32.
+        The state updates are mcedm_ddim_init / _x0 / _next (bit-identical to the torch expressions, scalars evaluated on
+        the host with the reference's fp32 tensor ops); every e_t is one evaluation of the network with the per-sample
+        timestep vector and the previous x0 prediction as self-conditioning input."""
+        if guide_dx:
+            raise NotImplementedError("guide_dx is not supported by PlDdim on the kernels")
+        w = sparams.w
+        if not (w is None or abs(w) < 0.001):
+            raise NotImplementedError("classifier-free guidance (w != 0) is not supported")
+        if not h.is_cuda:
+            raise L.McedmError("sample_with_repeat needs CUDA tensors: the sm_100a kernels have no CPU fallback")
+        lib = L.lib()
+        model = self.ema_model if self.ema_model is not None else self.model
+        unet = self._unet_of(model)
+        n_repeat, n_time_h, n_time_u = sparams.n_repeat, sparams.n_time_h, sparams.n_time_u
+        hu = rearrange(torch.cat([h, u], dim=-1), "b h w c -> b c h w").contiguous().float()
+        hu_mask = torch.ones_like(hu)
+        hu_mask[:, 0:self.h_ch, n_time_h:, :] = 0.0
+        hu_mask[:, self.h_ch:self.h_ch + self.u_ch, n_time_u:, :] = 0.0
+        T = self.num_timesteps
+        if sparams.skip_type == "uniform":
+            seq = list(range(0, T, T // sparams.timesteps))
+        elif sparams.skip_type == "quad":
+            seq = [int(v) for v in (np.linspace(0, np.sqrt(T * 0.8), sparams.timesteps) ** 2)]
+        else:
+            raise NotImplementedError
+        hu_noise = self._randn_like("init", hu).to(torch.float32).contiguous()      # :836
+        a = (1 - self.betas.detach().cpu()).cumprod(dim=0)                          # :838, host copy
+        total, st, n = hu.numel(), L.stream_ptr(), hu.shape[0]
+        x = torch.empty_like(hu)
+        L.check(lib.mcedm_ddim_init(L.ptr(hu), L.ptr(hu_noise), L.ptr(hu_mask), float(a[T - 1].sqrt()),
+                                    float((1.0 - a[T - 1]).sqrt()), total, L.ptr(x), st), "ddim_init")
+        seq_next = [-1] + list(seq[:-1])
+        xs, x0_preds, x0_t = [x], [], None
+        self_cond = bool(getattr(unet, "self_condition", False))
+        for i, j in zip(reversed(seq), reversed(seq_next)):
+            t_host = torch.ones(n) * i
+            at = self.compute_alpha(t_host.long())[0].reshape(())                   # fp32 scalars as the reference forms them
+            at_next = self.compute_alpha((torch.ones(n) * j).long())[0].reshape(())
+            sa, s1 = float(at.sqrt()), float((1 - at).sqrt())
+            t_dev = t_host.to(hu.device, torch.float32)
+            xt = xs[-1]
+            et = None
+            for k in range(n_repeat):
+                et = unet(xt, t_dev, x_self_cond=x0_t if self_cond else None).contiguous()
+                if self._trace is not None:
+                    self._trace.append(dict(t=float(i), k=k, xt=xt.clone(), x_self_cond=None if x0_t is None else x0_t.clone(),
+                                            et=et.clone()))
+                x0_new = torch.empty_like(hu)
+                xt_new = torch.empty_like(hu) if k < n_repeat - 1 else None
+                L.check(lib.mcedm_ddim_x0(L.ptr(xt), L.ptr(et), L.ptr(hu), L.ptr(hu_mask), sa, s1, total, L.ptr(x0_new),
+                                          L.ptr(xt_new), st), "ddim_x0")
+                x0_t = x0_new
+                if xt_new is not None:
+                    xt = xt_new
+            rnd, c1 = None, 0.0
+            if abs(sparams.eta) > 1e-10:
+                c1_t = sparams.eta * ((1 - at / at_next) * (1 - at_next) / (1 - at)).sqrt()
+                c2_t = ((1 - at_next) - c1_t ** 2).sqrt()
+                c1, c2 = float(c1_t), float(c2_t)
+                rnd = (self._noise_hook("rand", x) if self._noise_hook is not None else torch.rand_like(x)).contiguous()
+            else:
+                c2 = float((1 - at_next).sqrt())
+            x_next = torch.empty_like(hu)
+            L.check(lib.mcedm_ddim_next(L.ptr(x0_t), L.ptr(et), L.ptr(hu), L.ptr(hu_noise), L.ptr(hu_mask), L.ptr(rnd),
+                                        float(at_next.sqrt()), c1, c2, total, L.ptr(x_next), st), "ddim_next")
+            if return_last:
+                x0_preds, xs = [x0_t], [x_next]
+            else:
+                x0_preds.append(x0_t)
+                xs.append(x_next)
+        xs = rearrange(torch.stack(xs, dim=0), "t b c h w -> b t h w c")
+        x0_preds = rearrange(torch.stack(x0_preds, dim=0), "t b c h w -> b t h w c")
+        return xs, x0_preds
 
     # ---------------------------------------------------------------- evaluation
     def validation_step(self, val_batch, batch_idx):

@@ -123,6 +123,6 @@ def ddpm_unet_forward(sd: Dict[str, Tensor], model_cfg, x: Tensor, t: Tensor, co
     return _conv(sd, "conv_out", _swish(_norm(sd, "norm_out", h)))
 
 
-def ddpm_net(sd, model_cfg, x, noise_labels):
-    """Adapter with the signature oracle.edm_oracle.vp_denoise expects (cond = x_self_cond = None)."""
-    return ddpm_unet_forward(sd, model_cfg, x, noise_labels)
+def ddpm_net(sd, model_cfg, x, noise_labels, x_self_cond=None):
+    """Adapter with the signature oracle.edm_oracle.vp_denoise / ddim_sample_with_repeat expect (cond = None)."""
+    return ddpm_unet_forward(sd, model_cfg, x, noise_labels, x_self_cond=x_self_cond)

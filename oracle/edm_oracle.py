@@ -402,6 +402,62 @@ def ddim_sample_edm(sd, model_cfg, grid: VpGrid, hu: Tensor, hu_noise: Tensor, s
     return torch.stack(xs, dim=0).permute(1, 0, 3, 4, 2)
 
 
+def ddim_sample_with_repeat(sd, model_cfg, grid: VpGrid, hu: Tensor, hu_noise: Tensor, sparams, net, h_ch: int = 1,
+                            u_ch: int = 1, return_last: bool = True, record: Optional[list] = None,
+                            rand_like: Optional[Callable[[Tensor], Tensor]] = None):
+    """PlDdim.sample_with_repeat (ddim.py:808-913) with guide_dx False, w = 0, dx_cond False: DDIM steps on the VP
+    schedule, the known region (mask == 1) re-imposed on every x0 prediction and on every x_t, n_repeat evaluations per
+    timestep, self-conditioning on the previous x0 prediction.  hu fp32 [B,C,H,W]; hu_noise: the draw of :836;
+    net(sd, model_cfg, x, t, x_self_cond) -> e_t.  Returns (xs, x0_preds) as [B, T, H, W, C] fp32."""
+    n_repeat, n_time_h, n_time_u = sparams["n_repeat"], sparams["n_time_h"], sparams["n_time_u"]
+    hu_mask = torch.ones_like(hu)
+    hu_mask[:, 0:h_ch, n_time_h:, :] = 0.0
+    hu_mask[:, h_ch:h_ch + u_ch, n_time_u:, :] = 0.0
+    T = grid.num_timesteps
+    if sparams["skip_type"] == "uniform":
+        seq = list(range(0, T, T // int(sparams["timesteps"])))
+    elif sparams["skip_type"] == "quad":
+        seq = [int(v) for v in (np.linspace(0, np.sqrt(T * 0.8), int(sparams["timesteps"])) ** 2)]
+    else:
+        raise NotImplementedError
+    a = (1 - grid.betas).cumprod(dim=0)
+    hu_t_known = hu * a[T - 1].sqrt() + hu_noise * (1.0 - a[T - 1]).sqrt()
+    x = hu_t_known * hu_mask + hu_noise * (1.0 - hu_mask)
+    n = hu.size(0)
+    seq_next = [-1] + list(seq[:-1])
+    xs, x0_preds, x0_t = [x], [], None
+    self_cond = bool(model_cfg.get("self_cond", False))
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t = (torch.ones(n) * i).type_as(hu)
+        next_t = (torch.ones(n) * j).type_as(hu)
+        at, at_next = grid.compute_alpha(t.long()), grid.compute_alpha(next_t.long())
+        xt = xs[-1]
+        for k in range(n_repeat):
+            et = net(sd, model_cfg, xt, t, x0_t if self_cond else None)
+            if record is not None:
+                record.append(dict(t=float(i), k=k, xt=xt, x_self_cond=x0_t if self_cond else None, et=et))
+            et = et - 5.0 * (1 - at).sqrt() * torch.zeros_like(xt)
+            x0_t = (xt - et * (1 - at).sqrt()) / at.sqrt()
+            x0_t = hu * hu_mask + x0_t * (1.0 - hu_mask)
+            if k < n_repeat - 1:
+                xt = at.sqrt() * x0_t + (1 - at).sqrt() * et
+        if abs(sparams["eta"]) > 1e-10:
+            c1 = sparams["eta"] * ((1 - at / at_next) * (1 - at_next) / (1 - at)).sqrt()
+            c2 = ((1 - at_next) - c1 ** 2).sqrt()
+            xt_next = at_next.sqrt() * x0_t + c1 * rand_like(x) + c2 * et
+        else:
+            c2 = (1 - at_next).sqrt()
+            xt_next = at_next.sqrt() * x0_t + c2 * et
+        hu_t_known = at_next.sqrt() * hu + c2 * hu_noise
+        xt_next = hu_t_known * hu_mask + xt_next * (1.0 - hu_mask)
+        if return_last:
+            x0_preds, xs = [x0_t], [xt_next]
+        else:
+            x0_preds.append(x0_t)
+            xs.append(xt_next)
+    return torch.stack(xs, dim=0).permute(1, 0, 3, 4, 2), torch.stack(x0_preds, dim=0).permute(1, 0, 3, 4, 2)
+
+
 # ------------------------------------------------------------------------------------------------
 # mask generators (datamodules/h5_dataset.py), mask == 1 -> missing / to be generated
 # ------------------------------------------------------------------------------------------------

@@ -279,3 +279,62 @@ def test_ddpm_config4_sampler_against_reference(dev):
     pl.use_cuda_graph = False
     xs2 = pl.sample_edm(state[..., :1], state[..., 1:2], sp, return_last=True, guide_dx=False)
     assert torch.equal(xs2, xs)
+
+
+def test_ddim_sample_with_repeat_against_reference(dev):
+    """PlDdim.sample_with_repeat (models/ddim.py:808-913; the DDIM sampler with known-region replacement, repeats and
+    self-conditioning) on the kernels with the DDPM U-Net: (1) the state-update kernels are bit-identical to the torch
+    expressions on the traced inputs; (2) every network evaluation is within the 16-bit bar of the oracle on the SAME
+    inputs (x_t, timestep vector, self-conditioning input); (3) the known region of every x0 prediction and of the final
+    state is the data bit for bit; (4) RNG call sequence as the unmodified reference's."""
+    from oracle import ddpm_oracle as DO
+
+    pl, cfg, sd, gd = _ddpm_module(dev)
+    g = golden("ddim_repeat.pt")
+    mcfg = gd["model_cfg"]
+    sp = copy.deepcopy(cfg.diff_sampler)
+    sp.type, sp.skip_type, sp.eta = "ddim", "uniform", 0.0
+    sp.timesteps, sp.n_time_h, sp.n_time_u, sp.n_repeat = g["steps"], g["n_time_h"], g["n_time_u"], g["n_repeat"]
+    st = g["stats"]
+    pl.normalizer_input.set_stats(st["input_mean"].to(dev), st["input_std"].to(dev))
+    pl.normalizer_target.set_stats(st["target_mean"].to(dev), st["target_std"].to(dev))
+    pl.h_ch = pl.u_ch = 1
+    h, u = D._FIELDS["swe"](1, 128, first_seed=g["field_seed"])
+    state = pl.data_transform(torch.from_numpy(h).to(dev), torch.from_numpy(u).to(dev))
+    feed = NoiseFeed(g["seed"])
+    pl._noise_hook = feed.hook
+    pl._trace = []
+    xs, x0 = pl.sample_with_repeat(state[..., :1], state[..., 1:2], sp, return_last=False)
+    trace, pl._trace, pl._noise_hook = pl._trace, None, None
+    assert [tuple(c) for c in feed.calls] == [tuple(c) for c in g["calls"]]
+    assert xs.shape == g["xs"].shape and x0.shape == g["x0_preds"].shape and xs.dtype == torch.float32
+    assert len(trace) == len(g["evals"])
+    grid = O.VpGrid()
+    hu = state.permute(0, 3, 1, 2).contiguous()
+    mask = torch.ones_like(hu)
+    mask[:, 0:1, g["n_time_h"]:, :] = 0.0
+    mask[:, 1:2, g["n_time_u"]:, :] = 0.0
+    worst = 0.0
+    for rec, ref in zip(trace, g["evals"]):
+        assert rec["t"] == ref["t"] and (rec["x_self_cond"] is not None) == ref["self_cond"]
+        tv = torch.full((1,), rec["t"])
+        with torch.no_grad():
+            e_or = DO.ddpm_net(sd, mcfg, rec["xt"].cpu(), tv, None if rec["x_self_cond"] is None else rec["x_self_cond"].cpu())
+        worst = max(worst, rel_l2(rec["et"], e_or))
+    print("sample_with_repeat: worst per-evaluation e_t error", worst)
+    assert worst < 1e-2, worst
+    # state updates bit-identical to the torch expressions on the traced tensors (last timestep: t = 0, next = -1)
+    rec = trace[-1]
+    at, at_next = grid.compute_alpha(torch.tensor([0])).to(dev), grid.compute_alpha(torch.tensor([-1])).to(dev)
+    x0_ref = (rec["xt"] - rec["et"] * (1 - at).sqrt()) / at.sqrt()
+    x0_ref = hu * mask + x0_ref * (1.0 - mask)
+    assert torch.equal(x0[0, -1].permute(2, 0, 1), x0_ref[0])
+    c2 = (1 - at_next).sqrt()
+    xn = at_next.sqrt() * x0_ref + c2 * rec["et"]
+    hu_noise = NoiseFeed(g["seed"]).draw(hu.cpu()).to(dev)
+    xn = (at_next.sqrt() * hu + c2 * hu_noise) * mask + xn * (1.0 - mask)
+    assert torch.equal(xs[0, -1].permute(2, 0, 1), xn[0])
+    for k in range(x0.shape[1]):
+        assert torch.equal(x0[0, k, :64, :, 1], state[0, :64, :, 1])
+    assert torch.equal(xs[0, -1, :64, :, 1], state[0, :64, :, 1])
+    assert torch.isfinite(xs).all() and rel_l2(xs[:, 0], g["xs"][:, 0]) < 1e-6      # the initial state: same draws

@@ -244,3 +244,36 @@ def test_oracle_ddpm_unet_and_repaint_sampler_match_reference():
         assert rel_l2(d, ref["D"]) < 1e-5
     assert rel_l2(xs, s["xs"]) < 1e-5
     assert torch.equal(xs[0, 0, :64, :, 1], hu[0, 1, :64].double())
+
+
+def test_oracle_ddim_sample_with_repeat_matches_reference():
+    """PlDdim.sample_with_repeat (models/ddim.py:808-913) through the DDPM U-Net: the oracle against the unmodified
+    reference (tests/golden/make_golden_ddim_repeat.py): per-evaluation network outputs, every x_t and x0 prediction."""
+    from common import seeded_weights
+    from oracle import ddpm_oracle as DO
+
+    g = golden("ddim_repeat.pt")
+    gd = golden("ddpm_path.pt")
+    sd = seeded_weights(gd["shapes"], seed=3)
+    mcfg = gd["model_cfg"]
+    grid = O.VpGrid()
+    h, u = D._FIELDS["swe"](1, 128, first_seed=g["field_seed"])
+    st = g["stats"]
+    hu = torch.cat([(torch.from_numpy(h) - st["input_mean"]) / st["input_std"],
+                    (torch.from_numpy(u) - st["target_mean"]) / st["target_std"]], dim=-1).permute(0, 3, 1, 2).contiguous()
+    sp = dict(hparams("config_ddim_res32").diff_sampler)
+    sp.update(type="ddim", skip_type="uniform", eta=0.0, timesteps=g["steps"], n_time_h=g["n_time_h"],
+              n_time_u=g["n_time_u"], n_repeat=g["n_repeat"])
+    feed = NoiseFeed(g["seed"])
+    hu_noise = feed.draw(hu)
+    rec = []
+    with torch.no_grad():
+        xs, x0 = O.ddim_sample_with_repeat(sd, mcfg, grid, hu, hu_noise, sp, DO.ddpm_net, return_last=False, record=rec)
+    assert [tuple(c) for c in feed.calls] == [tuple(c) for c in g["calls"]]
+    assert len(rec) == len(g["evals"]) == 8
+    for mine, ref in zip(rec, g["evals"]):
+        assert mine["t"] == ref["t"] and (mine["x_self_cond"] is not None) == ref["self_cond"]
+        assert rel_l2(mine["et"], ref["et"]) < 2e-5
+    assert xs.shape == g["xs"].shape and x0.shape == g["x0_preds"].shape
+    assert rel_l2(xs, g["xs"]) < 1e-4 and rel_l2(x0, g["x0_preds"]) < 1e-4
+    assert torch.equal(xs[0, -1, :64, :, 1], hu[0, 1, :64])            # known region of the final state: exactly the data
