@@ -351,10 +351,12 @@ class PlDdim(PlMcedm):
         sp = self.test_sparams
         n_samples = sp.n_samples
         state_gt_rep = state_gt.repeat(n_samples, 1, 1, 1)
-        if sp.type != "edm":
-            raise NotImplementedError("only the EDM sampler of PlDdim is implemented")
-        xs = self.sample_edm(state_gt_rep[..., 0:h_ch], state_gt_rep[..., h_ch:u_ch + h_ch], sp,
-                             return_last=sp.return_last, guide_dx=sp.guide_dx)
+        if sp.type == "edm":                                             # :398-402
+            xs = self.sample_edm(state_gt_rep[..., 0:h_ch], state_gt_rep[..., h_ch:u_ch + h_ch], sp,
+                                 return_last=sp.return_last, guide_dx=sp.guide_dx)
+        else:
+            xs, _ = self.sample_with_repeat(state_gt_rep[..., 0:h_ch], state_gt_rep[..., h_ch:u_ch + h_ch], sp,
+                                            return_last=sp.return_last, guide_dx=sp.guide_dx)
         xs_mean = torch.mean(rearrange(xs, "(n b) t h w c -> n b t h w c", n=n_samples), dim=0)
         h_last, u_last = xs_mean[:, -1, :, :, 0:h_ch], xs_mean[:, -1, :, :, h_ch:u_ch + h_ch]
         loss_h, loss_u = self.mae_criterion(h_last, h), self.mae_criterion(u_last, u)
