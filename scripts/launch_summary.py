@@ -1,6 +1,7 @@
 """Markdown summary of an ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none --csv`):
-    python scripts/launch_summary.py launches.csv [first_kernel_substring]
-With a kernel-name substring, only one period (from its first occurrence to just before the next) is summarised."""
+    python scripts/launch_summary.py launches.csv [first_kernel_substring [period]]
+With a kernel-name substring, only one period (from its `period`-th occurrence, default the first, to just before the
+next) is summarised."""
 import collections
 import csv
 import re
@@ -30,8 +31,9 @@ def main():
     data = load(sys.argv[1])
     if len(sys.argv) > 2:
         idx = [i for i, (n, _) in enumerate(data) if sys.argv[2] in n]
-        if len(idx) >= 2:
-            data = data[idx[0]:idx[1]]
+        k = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+        if len(idx) >= k + 2:
+            data = data[idx[k]:idx[k + 1]]
     agg = collections.OrderedDict()
     for n, v in data:
         a = agg.setdefault(n[:70], [0, 0.0])
