@@ -242,6 +242,26 @@ MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrst
                            float* dgb_partial, float* d_scale_shift, int dss_batch_stride, const float* add0,
                            int add0_mode, const float* add1, float* dx, void* dx_bf16, int out_pitch, int out_blk,
                            void* dx_bf16_dense, float* colsum_partial, void* stream);
+/*
+ * The same backward for the 16-bit training plan ("fused16", train_engine.py): x16 is the RAW 16-bit activation the
+ * fused forward stored, dy16 the 16-bit output of a data-gradient conv, both in op_fmt (0 bf16, 1 fp16); residual-path
+ * gradients (add0 / add1) and dx stay fp32.  Every tensor carries its own layout: (pitch, blk) = (0, 0) dense NHWC, else
+ * the padded-flat layout of mcedm_flat_geometry AT THAT TENSOR'S RESOLUTION (dy: the conv resolution; add0: per
+ * add0_mode; x, add1, dx, dx16: Hin x Win).  dx16: 16-bit copy in x's layout; dx16_dense: a second, dense copy.
+ * add16 != 0: add0 / add1 are 16-bit (op_fmt) too — the gradient of the residual stream without an fp32 master copy.
+ * kcoef: scratch fp32 [B][64][4]; ticket: uint32 [B], ZERO before the first launch (each launch leaves it zero): the
+ * last CTA of a sample to finish pass 1 folds that sample's partials once (fixed order: deterministic).
+ * Win must be a power of two.  red_partial / dgb_partial / colsum_partial as in mcedm_gn_bwd, sized with
+ * mcedm_gn_bwd16_ctas_per_img.
+ */
+MCEDM_API int mcedm_gn_bwd16_ctas_per_img(int Hin, int Win, int B);
+MCEDM_API int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const void* x16, int x_pitch, int x_blk,
+                             int op_fmt, const float* meanrstd, const float* gamma, const float* beta,
+                             const float* scale_shift, int emb_batch_stride, int emb_shift_offset, int act,
+                             int resample, int B, int Hin, int Win, float* red_partial, float* kcoef,
+                             unsigned int* ticket, float* dgb_partial, float* d_scale_shift, int dss_batch_stride,
+                             const void* add0, int add0_mode, int add0_pitch, int add0_blk, const void* add1,
+                             int add16, float* dx, void* dx16, void* dx16_dense, float* colsum_partial, void* stream);
 /* out[j] (+)= scale * sum_r in[r*stride_r + j*stride_j]  (ordered fp64 sum; folds per-CTA / per-sample partials) */
 MCEDM_API int mcedm_reduce_rows(const float* in, int n_rows, long long stride_r, int n_cols, long long stride_j,
                                 float* out, int accumulate, float scale, void* stream);
@@ -281,6 +301,10 @@ MCEDM_API int mcedm_edm_loss(const float* F, const float* x_noise, const float* 
 MCEDM_API int mcedm_wgrad_ctas(int B, int H, int W);
 MCEDM_API int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
                                int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, void* stream);
+/* mcedm_conv_wgrad with both operands in op_fmt (0 bf16, 1 fp16; kind::f16 MMAs need one format for A and B). */
+MCEDM_API int mcedm_conv_wgrad16(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
+                                 int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, int op_fmt,
+                                 void* stream);
 MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
                                  int co_mul, int co_add, int co_count, int ci_count, int accumulate, void* stream);
 /* Every weight-gradient fold of a step in one launch (same arithmetic and order as mcedm_wgrad_reduce, accumulate = 0);
@@ -308,6 +332,9 @@ MCEDM_API int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf16
  */
 MCEDM_API int mcedm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16, const float* lse,
                                   int B, int L, float* dvec, void* dq_bf16, void* dk_bf16, void* dv_bf16, void* stream);
+/* The same with every 16-bit tensor (inputs, P / dS operand tiles, outputs) in op_fmt (0 bf16, 1 fp16). */
+MCEDM_API int mcedm_attention_bwd16(const void* qkv16, const void* out16, const void* d_out16, const float* lse, int B,
+                                    int L, float* dvec, void* dq16, void* dk16, void* dv16, int op_fmt, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* embedding MLP, first conv, output head                                                        */
@@ -430,6 +457,12 @@ MCEDM_API int mcedm_nchw_to_nhwc_pad(const float* a, int Ca, const float* b, int
 /* partial[cta][64] = column sums over the CTA's pixel range of channels [c_off, c_off+64) of bf16 [pixels, C] */
 MCEDM_API int mcedm_colsum_bf16(const void* x_bf16, long long pixels, int C, int c_off, float* partial, int n_ctas,
                                 void* stream);
+/* The two helpers above for either 16-bit format (op_fmt 0 bf16, 1 fp16); the pad variant multiplies by `scale` first
+ * (the loss scale of the fp16 training plan: dL/dF enters the backward as scale * dL/dF). */
+MCEDM_API int mcedm_nchw_to_nhwc_pad16(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, void* dst16,
+                                       int c_dst0, float scale, int op_fmt, void* stream);
+MCEDM_API int mcedm_colsum16(const void* x16, long long pixels, int C, int c_off, float* partial, int n_ctas, int op_fmt,
+                             void* stream);
 /* backward of mcedm_emb_mlp: dss fp32 [n_aff][B][128] = gradient of every block's (scale | shift);
  * vec_scratch fp32 [B][320]; outputs in the reference parameter shapes (affine [n_aff][128][64] / [n_aff][128],
  * map_layer1, map_layer0 [64][64] / [64]) */

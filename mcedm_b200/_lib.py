@@ -42,6 +42,9 @@ _PROTOTYPES = {
     "mcedm_gn_bwd_ctas_per_img": [_i, _i, _i],
     "mcedm_gn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp,
                      _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "mcedm_gn_bwd16_ctas_per_img": [_i, _i, _i],
+    "mcedm_gn_bwd16": [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+                       _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_reduce_rows": [_vp, _i, C.c_longlong, _i, C.c_longlong, _vp, _i, _f, _vp],
     "mcedm_reduce_rows_batched": [_vp, _i, _i, _vp],
     "mcedm_wgrad_reduce_batched": [_vp, _i, _vp],
@@ -51,6 +54,8 @@ _PROTOTYPES = {
     "mcedm_mcedm_prep_rows": [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_nchw_to_nhwc_pad": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "mcedm_colsum_bf16": [_vp, C.c_longlong, _i, _i, _vp, _i, _vp],
+    "mcedm_nchw_to_nhwc_pad16": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _f, _i, _vp],
+    "mcedm_colsum16": [_vp, C.c_longlong, _i, _i, _vp, _i, _i, _vp],
     "mcedm_emb_mlp_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mcedm_sumsq_partial": [_vp, C.c_longlong, _vp, _i, _vp],
     "mcedm_adam_step": [_vp, _vp, _vp, _vp, C.c_longlong, _f, _f, _f, _f, _f, _i, _vp, _i, _f, _f, _vp, _vp],
@@ -58,11 +63,13 @@ _PROTOTYPES = {
     "mcedm_pack_gather": [_vp, _vp, _vp, C.c_longlong, C.c_longlong, _i, _vp, _vp, _vp],
     "mcedm_wgrad_ctas": [_i, _i, _i],
     "mcedm_conv_wgrad": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "mcedm_conv_wgrad16": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mcedm_flat_geometry": [_i, _i, _ip, _ip],
     "mcedm_conv_flat": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
     "mcedm_attention": [_vp, _i, _i, _vp, _vp, _i, _vp],
     "mcedm_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "mcedm_attention_bwd16": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
     "mcedm_attention_ref": [_vp, _i, _i, _vp, _vp],
     "mcedm_emb_mlp": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "mcedm_conv_in": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],

@@ -39,13 +39,22 @@ __device__ __forceinline__ float ex2b(float x) {
 
 // D[b, i] = sum_c dO[b,i,c] * O[b,i,c]; one thread per (b, i) row of 64 bf16 (128 B).
 __global__ void attn_bwd_prep_kernel(const uint4* __restrict__ o, const uint4* __restrict__ d_o, long long rows,
-                                     float* __restrict__ dvec) {
+                                     float* __restrict__ dvec, int fmt) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float acc = 0.f;
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const uint4 a = o[r * 8 + u], g = d_o[r * 8 + u];
+    if (fmt) {
+      const uint32_t av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = unpack_f16x2(av[k]), y = unpack_f16x2(gv[k]);
+        acc += x.x * y.x + x.y * y.y;
+      }
+      continue;
+    }
     acc += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x);
     acc += bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y);
     acc += bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z);
@@ -61,6 +70,7 @@ struct AttnBwdParams {
   __nv_bfloat16* out1;  // MODE 1: dV ; MODE 0: unused
   __nv_bfloat16* out2;  // MODE 1: dK ; MODE 0: dQ
   unsigned int* err;
+  int fmt;              // 16-bit format of every operand / output: 0 bf16, 1 fp16
 };
 
 template <int MODE>
@@ -141,8 +151,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 1);    // B = streamed tile, MN-major
+    const uint32_t idesc_t = umma_idesc_16(128, 128, 0, 0, p.fmt);
+    const uint32_t idesc_acc = umma_idesc_16(128, 64, 0, 1, p.fmt);    // B = streamed tile, MN-major
     mbar_wait(x_full, 0, p.err, 0x5200);
     tc_fence_after();
     const uint64_t x1d = umma_desc_k_sw128(smem_u32(x_smem));
@@ -238,8 +248,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const float p1 = ex2b(fmaf(__uint_as_float(s[i0 + 1]), c1, -l1));
             const float ds0 = p0 * (__uint_as_float(g[i0]) - d0) * 0.125f;
             const float ds1 = p1 * (__uint_as_float(g[i0 + 1]) - d1) * 0.125f;
-            pp[e] = pack_bf16x2(p0, p1);
-            dp[e] = pack_bf16x2(ds0, ds1);
+            pp[e] = pack_op2(p0, p1, p.fmt);
+            dp[e] = pack_op2(ds0, ds1, p.fmt);
           }
           const int unit = ((c & 1) * 4 + u) ^ (row & 7);
           if (MODE == 1) *reinterpret_cast<uint4*>(prow + (c >> 1) * kBTile + unit * 16) = po;
@@ -267,10 +277,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[u * 8 + 0]), __uint_as_float(v[u * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]));
+          o.x = pack_op2(__uint_as_float(v[u * 8 + 0]), __uint_as_float(v[u * 8 + 1]), p.fmt);
+          o.y = pack_op2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3]), p.fmt);
+          o.z = pack_op2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5]), p.fmt);
+          o.w = pack_op2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7]), p.fmt);
           *reinterpret_cast<uint4*>(dst + c * 32 + u * 8) = o;
         }
       }
@@ -290,6 +300,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 extern "C" int mcedm_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16,
                                    const float* lse, int B, int L, float* dvec, void* dq_bf16, void* dk_bf16,
                                    void* dv_bf16, void* stream) {
+  return mcedm_attention_bwd16(qkv_bf16, out_bf16, d_out_bf16, lse, B, L, dvec, dq_bf16, dk_bf16, dv_bf16, 0, stream);
+}
+
+extern "C" int mcedm_attention_bwd16(const void* qkv_bf16, const void* out_bf16, const void* d_out_bf16,
+                                     const float* lse, int B, int L, float* dvec, void* dq_bf16, void* dk_bf16,
+                                     void* dv_bf16, int op_fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && L >= 128 && L % 128 == 0, "attention_bwd: L=%d must be a positive multiple of 128", L);
   CUtensorMap tm_qkv, tm_do;
@@ -300,12 +316,13 @@ extern "C" int mcedm_attention_bwd(const void* qkv_bf16, const void* out_bf16, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long rows = (long long)B * L;
   attn_bwd_prep_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(
-      reinterpret_cast<const uint4*>(out_bf16), reinterpret_cast<const uint4*>(d_out_bf16), rows, dvec);
+      reinterpret_cast<const uint4*>(out_bf16), reinterpret_cast<const uint4*>(d_out_bf16), rows, dvec, op_fmt ? 1 : 0);
   MCEDM_CUDA(cudaGetLastError());
   AttnBwdParams p;
   p.L = L;
   p.lse = lse;
   p.dvec = dvec;
+  p.fmt = op_fmt ? 1 : 0;
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "attention_bwd: no watchdog word");
   const int smem = 1024 + 2 * kBTile + kBStages * 2 * kBTile + 4 * kBTile + 2 * 256 * 4 + 256;

@@ -41,6 +41,7 @@ struct WgradParams {
   int dy_slot_bytes;       // W * 128
   int a_slot_bytes;        // (W + 2) * 128 rounded up to 1024
   float* partial;          // [gridDim.x][taps][64][64]
+  uint32_t idesc;          // M = 128, N = 64, A and B both MN-major, operand format of the launch
   unsigned int* err;
 };
 
@@ -122,7 +123,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);    // A and B both MN-major
+    const uint32_t idesc = p.idesc;
     const uint32_t dy_base = smem_u32(dy_smem);
     const uint32_t a_base = smem_u32(a_smem);
     const uint32_t lbo = (uint32_t)p.dy_slot_bytes;
@@ -307,6 +308,13 @@ extern "C" int mcedm_wgrad_ctas(int B, int H, int W) { return mcedm::wgrad_grid(
 extern "C" int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
                                 int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial,
                                 void* stream) {
+  return mcedm_conv_wgrad16(dy, dy_layout, dy_ctotal, dy_coff, a, a_layout, a_ctotal, a_coff, B, H, W, taps, partial, 0,
+                            stream);
+}
+
+extern "C" int mcedm_conv_wgrad16(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
+                                  int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, int op_fmt,
+                                  void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(B >= 1 && H >= 1 && W >= 16 && W <= 128 && W % 16 == 0, "conv_wgrad: unsupported W=%d", W);
   MCEDM_REQUIRE(taps == 9 || taps == 1, "conv_wgrad: taps=%d (9 or 1)", taps);
@@ -332,6 +340,7 @@ extern "C" int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, in
   if (p.n_aslots < 3) p.n_aslots = 3;
   if (p.n_aslots > 12) p.n_aslots = 12;
   p.partial = partial;
+  p.idesc = umma_idesc_16(128, 64, 1, 1, op_fmt ? 1 : 0);
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "conv_wgrad: cannot allocate the watchdog word");
   CUtensorMap tm_dy, tm_a;

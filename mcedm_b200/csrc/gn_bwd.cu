@@ -401,6 +401,411 @@ edm_loss_kernel(const float* __restrict__ F, const float* __restrict__ x_noise, 
   if (threadIdx.x == 0) loss_partial[(long long)b * gridDim.x + blockIdx.x] = sm[0];
 }
 
+
+// ------------------------------------------------------------------------------------------------ 16-bit plan
+// The same two passes for the 16-bit training plan (train16_engine.py, plan "fused16"): x is the RAW 16-bit activation
+// the fused forward stored (dense NHWC or padded-flat), dy the 16-bit output of a data-gradient conv (same layouts), the
+// residual-path gradients are fp32 or 16-bit.  Every tensor carries its own (pitch, blk): 0 = dense NHWC, > 0 = the
+// padded-flat layout of conv_flat.cu at that tensor's resolution.  The fold of the pass-1 partials is done ONCE per
+// sample, by the last CTA of the sample to finish pass 1 (ticket counter; the fold order is
+// fixed, so the result does not depend on which CTA that is); pass 2 reads three coefficients per channel.
+struct GnBwd16Params {
+  const void* dy; int dy_pitch, dy_blk;        // at the conv resolution (Hin x Win, 2x for resample 1, 1/2 for 2)
+  const void* x; int x_pitch, x_blk;           // at Hin x Win; dx / dx16 / add1 share this layout
+  int fmt;                                     // 16-bit format of x, dy, dx16 (and of 16-bit adds): 0 bf16, 1 fp16
+  const float* meanrstd;
+  const float* gamma;
+  const float* beta;
+  const float* scale_shift;
+  int emb_batch_stride, emb_shift_offset;
+  int act, resample;
+  int B, Hin, Win, w_shift;
+  int ctas_per_img, pix_per_cta;
+  float* red_partial;                          // [B][ctas_per_img][64][2]
+  float* kcoef;                                // [B][64][4] = (rstd*k, rstd*m1, rstd*m2, -) written by the fold
+  unsigned int* ticket;                        // [B], zero before the launch, zero again after it
+  const void* add0; int add0_mode, add0_pitch, add0_blk;   // at ITS resolution (mode as in GnBwdParams)
+  const void* add1;
+  int add16;                                   // add0 / add1 are 16-bit (fmt) instead of fp32
+  float* dx;
+  void* dx16;
+  void* dx16_dense;
+  float* colsum_partial;
+  float* dgb_partial;
+  float* d_scale_shift;
+  int dss_batch_stride;
+};
+
+__device__ __forceinline__ long long lay_index(int pitch, int blk, int b, int y, int x, int H, int W) {
+  if (pitch > 0) return (long long)b * blk + (long long)(y + 1) * pitch + x;
+  return ((long long)b * H + y) * W + x;
+}
+// per-(sample, channel) forward coefficients (shared prologue of both passes): sA / sB = (a, b) of u = a x + b
+__device__ __forceinline__ void gn16_prologue(const GnBwd16Params& p, int b, float* sMean, float* sRstd, float* sA,
+                                              float* sB) {
+  if (threadIdx.x < 16) {
+    const float2 v = *reinterpret_cast<const float2*>(p.meanrstd + ((long long)b * 16 + threadIdx.x) * 2);
+    sMean[threadIdx.x] = v.x;
+    sRstd[threadIdx.x] = v.y;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    float a = sRstd[c >> 2] * p.gamma[c];
+    float bb = p.beta[c] - sMean[c >> 2] * a;
+    if (p.scale_shift) {
+      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
+      const float sc = 1.0f + ss[c];
+      a *= sc;
+      bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
+    }
+    sA[c] = a;
+    sB[c] = bb;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void unpack8(const uint4 r, int fmt, float (&v)[8]) {
+  if (fmt) {
+    const float2 a = unpack_f16x2(r.x), b = unpack_f16x2(r.y), c = unpack_f16x2(r.z), d = unpack_f16x2(r.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  } else {
+    v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+    v[4] = bf16_lo(r.z); v[5] = bf16_hi(r.z); v[6] = bf16_lo(r.w); v[7] = bf16_hi(r.w);
+  }
+}
+__device__ __forceinline__ uint4 pack8v(const float (&v)[8], int fmt) {
+  uint4 o;
+  o.x = pack_op2(v[0], v[1], fmt);
+  o.y = pack_op2(v[2], v[3], fmt);
+  o.z = pack_op2(v[4], v[5], fmt);
+  o.w = pack_op2(v[6], v[7], fmt);
+  return o;
+}
+__device__ __forceinline__ uint4 ldg16(const void* base, long long pix, int oct) {
+  return reinterpret_cast<const uint4*>(base)[pix * 8 + oct];
+}
+// 8 channels of a tensor that is fp32 or 16-bit
+__device__ __forceinline__ void load8_any(const void* base, long long pix, int oct, int is16, int fmt, float (&v)[8]) {
+  if (is16) {
+    unpack8(ldg16(base, pix, oct), fmt, v);
+  } else {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + pix * 64 + oct * 8);
+    const float4 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+// resample^T(t) for 8 channels of input pixel (b, y, x): t lives at Hin x Win (mode 0), 2x (mode 1: sum of the four
+// pixels the input fed) or 1/2 resolution (mode 2: a quarter of the one pixel it fed)
+__device__ __forceinline__ void gather8(const void* t, int mode, int pitch, int blk, int is16, int fmt, int b, int y,
+                                        int x, int H, int W, int oct, float (&d)[8]) {
+  if (mode == 0) {
+    load8_any(t, lay_index(pitch, blk, b, y, x, H, W), oct, is16, fmt, d);
+  } else if (mode == 1) {
+    const long long o00 = lay_index(pitch, blk, b, 2 * y, 2 * x, 2 * H, 2 * W);
+    const long long rstride = pitch > 0 ? pitch : 2 * W;
+    float t0[8], t1[8], t2[8], t3[8];
+    load8_any(t, o00, oct, is16, fmt, t0);
+    load8_any(t, o00 + 1, oct, is16, fmt, t1);
+    load8_any(t, o00 + rstride, oct, is16, fmt, t2);
+    load8_any(t, o00 + rstride + 1, oct, is16, fmt, t3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = (t0[k] + t1[k]) + (t2[k] + t3[k]);
+  } else {
+    load8_any(t, lay_index(pitch, blk, b, y >> 1, x >> 1, H >> 1, W >> 1), oct, is16, fmt, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] *= 0.25f;
+  }
+}
+
+struct Gn16Coef {
+  float a[8], bb[8];
+  float rs0, mr0, rs1, mr1;      // the 8 channels span two 4-channel groups
+};
+__device__ __forceinline__ void gn16_coef(const float* sMean, const float* sRstd, const float* sA, const float* sB,
+                                          int oct, Gn16Coef& cf) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    cf.a[k] = sA[oct * 8 + k];
+    cf.bb[k] = sB[oct * 8 + k];
+  }
+  cf.rs0 = sRstd[2 * oct];
+  cf.mr0 = sMean[2 * oct] * cf.rs0;
+  cf.rs1 = sRstd[2 * oct + 1];
+  cf.mr1 = sMean[2 * oct + 1] * cf.rs1;
+}
+
+// 256 threads = 8 channel octets x 32 pixel lanes; FAST (no resampling anywhere): NP pixels' 128-bit loads are issued
+// before any dependent work (a 16-bit stream has half the bytes per load of the fp32 kernels above: with one pixel in
+// flight per thread these passes were latency-bound at a third of the HBM rate).
+constexpr int kGnNP = 4;    // pass 1: two streams
+constexpr int kGnNPa = 2;   // pass 2: up to four streams + the stores
+
+template <bool FAST>
+__global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Params p) {
+  __shared__ float sMean[16], sRstd[16], sA[64], sB[64];
+  __shared__ float red[32][64][2];
+  __shared__ float sG1[64], sG2[64];
+  __shared__ unsigned int sLast;
+  const int b = blockIdx.y;
+  gn16_prologue(p, b, sMean, sRstd, sA, sB);
+  const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  Gn16Coef cf;
+  gn16_coef(sMean, sRstd, sA, sB, oct, cf);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  const int pix0 = blockIdx.x * p.pix_per_cta;
+  if (FAST) {
+    for (int i = pl; i < p.pix_per_cta; i += 32 * kGnNP) {
+      uint4 xr[kGnNP], dr[kGnNP];
+#pragma unroll
+      for (int u = 0; u < kGnNP; ++u) {
+        if (i + 32 * u < p.pix_per_cta) {
+          const int ip = pix0 + i + 32 * u;
+          const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+          xr[u] = ldg16(p.x, lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win), oct);
+          dr[u] = ldg16(p.dy, lay_index(p.dy_pitch, p.dy_blk, b, y, x, p.Hin, p.Win), oct);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGnNP; ++u) {
+        if (i + 32 * u < p.pix_per_cta) {
+          float xv[8], d[8];
+          unpack8(xr[u], p.fmt, xv);
+          unpack8(dr[u], p.fmt, d);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float dk = d[k];
+            if (p.act) dk *= silu_grad(fmaf(xv[k], cf.a[k], cf.bb[k]));
+            s1[k] += dk;
+            s2[k] += dk * (k < 4 ? fmaf(xv[k], cf.rs0, -cf.mr0) : fmaf(xv[k], cf.rs1, -cf.mr1));
+          }
+        }
+      }
+    }
+  } else {
+    for (int i = pl; i < p.pix_per_cta; i += 32) {
+      const int ip = pix0 + i;
+      const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+      float xv[8], d[8];
+      unpack8(ldg16(p.x, lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win), oct), p.fmt, xv);
+      gather8(p.dy, p.resample, p.dy_pitch, p.dy_blk, 1, p.fmt, b, y, x, p.Hin, p.Win, oct, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dk = d[k];
+        if (p.act) dk *= silu_grad(fmaf(xv[k], cf.a[k], cf.bb[k]));
+        s1[k] += dk;
+        s2[k] += dk * (k < 4 ? fmaf(xv[k], cf.rs0, -cf.mr0) : fmaf(xv[k], cf.rs1, -cf.mr1));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[pl][oct * 8 + k][0] = s1[k];
+    red[pl][oct * 8 + k][1] = s2[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cc = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][cc][k];
+    p.red_partial[(((long long)b * p.ctas_per_img + blockIdx.x) * 64 + cc) * 2 + k] = t;
+  }
+  // ---- the last CTA of sample b folds the sample's records (fixed order, fp64) into the pass-2 coefficients and
+  // the parameter-gradient rows
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) sLast = (atomicAdd(p.ticket + b, 1u) == (unsigned)p.ctas_per_img - 1u) ? 1u : 0u;
+  __syncthreads();
+  if (!sLast) return;
+  __threadfence();
+  float kk = 0.f, rstd_c = 0.f;
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x;
+    double a1 = 0.0, a2 = 0.0;
+    const float2* rp = reinterpret_cast<const float2*>(p.red_partial + ((long long)b * p.ctas_per_img * 64 + ch) * 2);
+    int t = 0;
+    for (; t + 8 <= p.ctas_per_img; t += 8) {
+      float2 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(rp + (t + k) * 64);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a1 += (double)v[k].x;
+        a2 += (double)v[k].y;
+      }
+    }
+    for (; t < p.ctas_per_img; ++t) {
+      const float2 v = __ldcg(rp + t * 64);
+      a1 += (double)v.x;
+      a2 += (double)v.y;
+    }
+    float sc = 1.0f;
+    if (p.scale_shift) sc = 1.0f + p.scale_shift[(long long)b * p.emb_batch_stride + ch];
+    const float g = p.gamma[ch], be = p.beta[ch];
+    const float A1 = (float)a1, A2 = (float)a2;
+    kk = g * sc;                                  // d xh = kk * du
+    rstd_c = sRstd[ch >> 2];
+    sG1[ch] = kk * A1;
+    sG2[ch] = kk * A2;
+    p.dgb_partial[((long long)b * 64 + ch) * 2 + 0] = sc * A2;     // d gamma contribution of sample b
+    p.dgb_partial[((long long)b * 64 + ch) * 2 + 1] = sc * A1;     // d beta
+    if (p.d_scale_shift) {
+      p.d_scale_shift[(long long)b * p.dss_batch_stride + ch] = g * A2 + be * A1;                  // d scale
+      p.d_scale_shift[(long long)b * p.dss_batch_stride + p.emb_shift_offset + ch] = A1;           // d shift
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x, g0 = ch & ~3;
+    const float cnt = 4.0f * (float)p.Hin * (float)p.Win;
+    const float m1 = ((sG1[g0] + sG1[g0 + 1]) + (sG1[g0 + 2] + sG1[g0 + 3])) / cnt;
+    const float m2 = ((sG2[g0] + sG2[g0 + 1]) + (sG2[g0 + 2] + sG2[g0 + 3])) / cnt;
+    *reinterpret_cast<float4*>(p.kcoef + ((long long)b * 64 + ch) * 4) =
+        make_float4(rstd_c * kk, rstd_c * m1, rstd_c * m2, 0.f);
+  }
+  if (threadIdx.x == 0) p.ticket[b] = 0u;         // ready for the next launch on this stream
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Params p) {
+  __shared__ float sMean[16], sRstd[16], sA[64], sB[64];
+  __shared__ float red[32][64];
+  const int b = blockIdx.y;
+  gn16_prologue(p, b, sMean, sRstd, sA, sB);
+  const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  Gn16Coef cf;
+  gn16_coef(sMean, sRstd, sA, sB, oct, cf);
+  // dx = k0[c] du - (k1 + xh k2) with k1, k2 constant inside a 4-channel group
+  float k0[8], cs[8];
+  const float4* kc = reinterpret_cast<const float4*>(p.kcoef + ((long long)b * 64 + oct * 8) * 4);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    k0[k] = kc[k].x;
+    cs[k] = 0.f;
+  }
+  const float k1a = kc[0].y, k2a = kc[0].z, k1b = kc[4].y, k2b = kc[4].z;
+  const int pix0 = blockIdx.x * p.pix_per_cta;
+  if (FAST) {
+    // no resampling, residual-path gradients (if any) 16-bit at the same resolution
+    for (int i = pl; i < p.pix_per_cta; i += 32 * kGnNPa) {
+      uint4 xr[kGnNPa], dr[kGnNPa], ar[kGnNPa], br[kGnNPa];
+      long long pix[kGnNPa];
+#pragma unroll
+      for (int u = 0; u < kGnNPa; ++u) {
+        if (i + 32 * u < p.pix_per_cta) {
+          const int ip = pix0 + i + 32 * u;
+          const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+          pix[u] = lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win);
+          xr[u] = ldg16(p.x, pix[u], oct);
+          dr[u] = ldg16(p.dy, lay_index(p.dy_pitch, p.dy_blk, b, y, x, p.Hin, p.Win), oct);
+          if (p.add0) ar[u] = ldg16(p.add0, lay_index(p.add0_pitch, p.add0_blk, b, y, x, p.Hin, p.Win), oct);
+          if (p.add1) br[u] = ldg16(p.add1, pix[u], oct);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGnNPa; ++u) {
+        if (i + 32 * u < p.pix_per_cta) {
+          float xv[8], d[8], o[8];
+          unpack8(xr[u], p.fmt, xv);
+          unpack8(dr[u], p.fmt, d);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float dk = d[k];
+            if (p.act) dk *= silu_grad(fmaf(xv[k], cf.a[k], cf.bb[k]));
+            const float t = k < 4 ? fmaf(fmaf(xv[k], cf.rs0, -cf.mr0), k2a, k1a) : fmaf(fmaf(xv[k], cf.rs1, -cf.mr1), k2b, k1b);
+            o[k] = fmaf(k0[k], dk, -t);
+          }
+          if (p.add0) {
+            float r[8];
+            unpack8(ar[u], p.fmt, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += r[k];
+          }
+          if (p.add1) {
+            float r[8];
+            unpack8(br[u], p.fmt, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += r[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) cs[k] += o[k];
+          if (p.dx) {
+            float4* q = reinterpret_cast<float4*>(p.dx + pix[u] * 64 + oct * 8);
+            q[0] = make_float4(o[0], o[1], o[2], o[3]);
+            q[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          const uint4 ov = pack8v(o, p.fmt);
+          if (p.dx16) reinterpret_cast<uint4*>(p.dx16)[pix[u] * 8 + oct] = ov;
+          if (p.dx16_dense) {
+            const int ip = pix0 + i + 32 * u;
+            reinterpret_cast<uint4*>(p.dx16_dense)[((long long)b * p.Hin * p.Win + ip) * 8 + oct] = ov;
+          }
+        }
+      }
+    }
+  } else {
+    for (int i = pl; i < p.pix_per_cta; i += 32) {
+      const int ip = pix0 + i;
+      const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+      const long long pix = lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win);
+      float xv[8], d[8], o[8];
+      unpack8(ldg16(p.x, pix, oct), p.fmt, xv);
+      gather8(p.dy, p.resample, p.dy_pitch, p.dy_blk, 1, p.fmt, b, y, x, p.Hin, p.Win, oct, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dk = d[k];
+        if (p.act) dk *= silu_grad(fmaf(xv[k], cf.a[k], cf.bb[k]));
+        const float t = k < 4 ? fmaf(fmaf(xv[k], cf.rs0, -cf.mr0), k2a, k1a) : fmaf(fmaf(xv[k], cf.rs1, -cf.mr1), k2b, k1b);
+        o[k] = fmaf(k0[k], dk, -t);
+      }
+      if (p.add0) {
+        float r[8];
+        gather8(p.add0, p.add0_mode, p.add0_pitch, p.add0_blk, p.add16, p.fmt, b, y, x, p.Hin, p.Win, oct, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += r[k];
+      }
+      if (p.add1) {
+        float r[8];
+        load8_any(p.add1, pix, oct, p.add16, p.fmt, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += r[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] += o[k];
+      if (p.dx) {
+        float4* q = reinterpret_cast<float4*>(p.dx + pix * 64 + oct * 8);
+        q[0] = make_float4(o[0], o[1], o[2], o[3]);
+        q[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      const uint4 ov = pack8v(o, p.fmt);
+      if (p.dx16) reinterpret_cast<uint4*>(p.dx16)[pix * 8 + oct] = ov;
+      if (p.dx16_dense) reinterpret_cast<uint4*>(p.dx16_dense)[((long long)b * p.Hin * p.Win + ip) * 8 + oct] = ov;
+    }
+  }
+  if (p.colsum_partial) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[pl][oct * 8 + k] = cs[k];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+      p.colsum_partial[((long long)b * p.ctas_per_img + blockIdx.x) * 64 + threadIdx.x] = t;
+    }
+  }
+}
+
+// CTAs of the 16-bit passes: >= 128 pixels (32 lanes x 4 pixels in flight), ~4 per SM when the batch allows it
+static int pick_pix_per_cta16(int work, int B) {
+  int per = 2048;
+  while (per > 128 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
+  while (per > 16 && (work % per) != 0) per >>= 1;
+  return per;
+}
+
 static int pick_pix_per_cta(int work, int B) {
   int per = 2048;
   while (per > 16 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
@@ -410,6 +815,11 @@ static int pick_pix_per_cta(int work, int B) {
 }
 
 }  // namespace mcedm
+
+extern "C" int mcedm_gn_bwd16_ctas_per_img(int Hin, int Win, int B) {
+  const int work = Hin * Win;
+  return work / mcedm::pick_pix_per_cta16(work, B);
+}
 
 extern "C" int mcedm_gn_bwd_ctas_per_img(int Hin, int Win, int B) {
   const int work = Hin * Win;
@@ -451,6 +861,63 @@ extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrs
   gn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p);
   MCEDM_CUDA(cudaGetLastError());
   gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(p);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+extern "C" int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const void* x16, int x_pitch, int x_blk,
+                              int op_fmt, const float* meanrstd, const float* gamma, const float* beta,
+                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, int act,
+                              int resample, int B, int Hin, int Win, float* red_partial, float* kcoef,
+                              unsigned int* ticket, float* dgb_partial, float* d_scale_shift, int dss_batch_stride,
+                              const void* add0, int add0_mode, int add0_pitch, int add0_blk, const void* add1,
+                              int add16, float* dx, void* dx16, void* dx16_dense, float* colsum_partial,
+                              void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 16 == 0 && (Win & (Win - 1)) == 0, "gn_bwd16: bad shape %dx%d", Hin, Win);
+  MCEDM_REQUIRE(resample >= 0 && resample <= 2 && add0_mode >= 0 && add0_mode <= 2, "gn_bwd16: resample=%d add0_mode=%d",
+                resample, add0_mode);
+  MCEDM_REQUIRE(dy16 && x16 && meanrstd && red_partial && dgb_partial && kcoef && ticket, "gn_bwd16: missing buffers");
+  GnBwd16Params p;
+  memset(&p, 0, sizeof(p));
+  p.dy = dy16; p.dy_pitch = dy_pitch; p.dy_blk = dy_blk;
+  p.x = x16; p.x_pitch = x_pitch; p.x_blk = x_blk;
+  p.fmt = op_fmt ? 1 : 0;
+  p.meanrstd = meanrstd; p.gamma = gamma; p.beta = beta; p.scale_shift = scale_shift;
+  p.emb_batch_stride = emb_batch_stride; p.emb_shift_offset = emb_shift_offset;
+  p.act = act; p.resample = resample;
+  p.B = B; p.Hin = Hin; p.Win = Win;
+  p.w_shift = __builtin_ctz((unsigned)Win);
+  const int work = Hin * Win;
+  p.pix_per_cta = pick_pix_per_cta16(work, B);
+  p.ctas_per_img = work / p.pix_per_cta;
+  p.red_partial = red_partial;
+  p.kcoef = kcoef;
+  p.ticket = ticket;
+  p.add0 = add0; p.add0_mode = add0_mode; p.add0_pitch = add0_pitch; p.add0_blk = add0_blk;
+  p.add1 = add1;
+  p.add16 = add16 ? 1 : 0;
+  p.dx = dx; p.dx16 = dx16; p.dx16_dense = dx16_dense;
+  p.colsum_partial = colsum_partial;
+  p.dgb_partial = dgb_partial;
+  p.d_scale_shift = d_scale_shift;
+  p.dss_batch_stride = dss_batch_stride;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(p.ctas_per_img, B);
+  if (resample == 0) {
+    gn_bwd16_reduce_kernel<true><<<grid, 256, 0, st>>>(p);
+  } else {
+    gn_bwd16_reduce_kernel<false><<<grid, 256, 0, st>>>(p);
+  }
+  MCEDM_CUDA(cudaGetLastError());
+  // the batched pass takes 16-bit residual-path gradients at the same resolution only
+  const bool fast = resample == 0 && (add0 == nullptr || (add0_mode == 0 && p.add16)) && (add1 == nullptr || p.add16);
+  if (fast) {
+    gn_bwd16_apply_kernel<true><<<grid, 256, 0, st>>>(p);
+  } else {
+    gn_bwd16_apply_kernel<false><<<grid, 256, 0, st>>>(p);
+  }
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

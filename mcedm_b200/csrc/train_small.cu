@@ -91,20 +91,21 @@ mcedm_prep_rows_kernel(const float* __restrict__ h, const float* __restrict__ u,
 // one thread per pixel; dst channels [c_dst0, c_dst0 + Ca + Cb) <- cat(a, b)[:, :, pix]
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_pad_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ bsrc, int Cb, long long HW,
-                        long long total_pix, __nv_bfloat16* __restrict__ dst, int c_dst0) {
+                        long long total_pix, unsigned short* __restrict__ dst, int c_dst0, float scale, int fmt) {
   const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
   if (pix >= total_pix) return;
   const long long b = pix / HW, hw = pix - b * HW;
-  __nv_bfloat16* d = dst + pix * 64 + c_dst0;
-  for (int c = 0; c < Ca; ++c) d[c] = __float2bfloat16(a[(b * Ca + c) * HW + hw]);
-  for (int c = 0; c < Cb; ++c) d[Ca + c] = __float2bfloat16(bsrc[(b * Cb + c) * HW + hw]);
+  unsigned short* d = dst + pix * 64 + c_dst0;
+  for (int c = 0; c < Ca; ++c) d[c] = (unsigned short)(pack_op2(scale * a[(b * Ca + c) * HW + hw], 0.f, fmt) & 0xffffu);
+  for (int c = 0; c < Cb; ++c)
+    d[Ca + c] = (unsigned short)(pack_op2(scale * bsrc[(b * Cb + c) * HW + hw], 0.f, fmt) & 0xffffu);
 }
 
 // grid = n_ctas, block = 256 = 8 channel-octets x 32 pixel lanes; x is [pixels][C] bf16, this launch sums the
 // 64 channels starting at c_off.  partial[cta][64]
 __global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long pixels, int C, int c_off,
-                   float* __restrict__ partial) {
+colsum_bf16_kernel(const unsigned short* __restrict__ x, long long pixels, int C, int c_off,
+                   float* __restrict__ partial, int fmt) {
   __shared__ float red[32][64];
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   float acc[8];
@@ -115,10 +116,16 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long pixels, int C,
   const long long p1 = p0 + per < pixels ? p0 + per : pixels;
   for (long long pix = p0 + pl; pix < p1; pix += 32) {
     const uint4 v = *reinterpret_cast<const uint4*>(x + pix * C + c_off + oct * 8);
-    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x);
-    acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z);
-    acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    if (fmt) {
+      const float2 a = unpack_f16x2(v.x), b = unpack_f16x2(v.y), c = unpack_f16x2(v.z), d = unpack_f16x2(v.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    } else {
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x);
+      acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z);
+      acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[pl][oct * 8 + i] = acc[i];
@@ -362,25 +369,35 @@ extern "C" int mcedm_mcedm_prep_rows(const float* h, const float* u, const int* 
   return 0;
 }
 
-extern "C" int mcedm_nchw_to_nhwc_pad(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, void* dst_bf16,
-                                      int c_dst0, void* stream) {
+extern "C" int mcedm_nchw_to_nhwc_pad16(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, void* dst16,
+                                        int c_dst0, float scale, int op_fmt, void* stream) {
   using namespace mcedm;
   MCEDM_REQUIRE(Ca >= 0 && Cb >= 0 && Ca + Cb >= 1 && c_dst0 >= 0 && c_dst0 + Ca + Cb <= 64, "nchw_to_nhwc_pad: channels");
   const long long HW = (long long)H * W, total = HW * B;
   nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, Ca, b, Cb, HW, total, reinterpret_cast<__nv_bfloat16*>(dst_bf16), c_dst0);
+      a, Ca, b, Cb, HW, total, reinterpret_cast<unsigned short*>(dst16), c_dst0, scale, op_fmt ? 1 : 0);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_nchw_to_nhwc_pad(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, void* dst_bf16,
+                                      int c_dst0, void* stream) {
+  return mcedm_nchw_to_nhwc_pad16(a, Ca, b, Cb, B, H, W, dst_bf16, c_dst0, 1.0f, 0, stream);
+}
+
+extern "C" int mcedm_colsum16(const void* x16, long long pixels, int C, int c_off, float* partial, int n_ctas, int op_fmt,
+                              void* stream) {
+  using namespace mcedm;
+  MCEDM_REQUIRE(pixels >= 1 && C % 8 == 0 && c_off % 8 == 0 && c_off + 64 <= C && n_ctas >= 1, "colsum16: bad sizes");
+  colsum_bf16_kernel<<<n_ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const unsigned short*>(x16), pixels, C, c_off, partial, op_fmt ? 1 : 0);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int mcedm_colsum_bf16(const void* x_bf16, long long pixels, int C, int c_off, float* partial, int n_ctas,
                                  void* stream) {
-  using namespace mcedm;
-  MCEDM_REQUIRE(pixels >= 1 && C % 8 == 0 && c_off % 8 == 0 && c_off + 64 <= C && n_ctas >= 1, "colsum_bf16: bad sizes");
-  colsum_bf16_kernel<<<n_ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x_bf16), pixels, C, c_off, partial);
-  MCEDM_CUDA(cudaGetLastError());
-  return 0;
+  return mcedm_colsum16(x_bf16, pixels, C, c_off, partial, n_ctas, 0, stream);
 }
 
 extern "C" int mcedm_emb_mlp_bwd(const float* c_noise, const float* freqs, const float* w0, const float* b0,

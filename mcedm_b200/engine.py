@@ -30,6 +30,7 @@ from .fused_engine import FusedMixin
 from .pack_plan import PackMixin
 from .precise_engine import PreciseMixin
 from .train_engine import TrainMixin
+from .train16_engine import Train16Mixin
 
 WEIGHT_EPOCH = [0]
 _SEG9 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
@@ -84,7 +85,7 @@ class _Block:
             self.be2 = m.norm2.bias.detach().float().contiguous()
 
 
-class UNetEngine(TrainMixin, FusedMixin, PreciseMixin, PackMixin):
+class UNetEngine(TrainMixin, Train16Mixin, FusedMixin, PreciseMixin, PackMixin):
     supports_ss_rows = True      # forward_static can take precomputed (scale | shift) rows (embedding_table)
 
     def __init__(self, unet):
@@ -125,12 +126,20 @@ class UNetEngine(TrainMixin, FusedMixin, PreciseMixin, PackMixin):
         # normalised and weights O(1), so the narrower range is safe); training always runs bf16.
         self.infer_fmt = 1
         self._fmt = 1
+        # training plan: "fused16" = 16-bit activations end to end, fp16 operands, loss-scaled fp16 gradients
+        # (train16_engine.py); "fp32" = the fp32-stream plan with bf16 operands (train_engine.py; any field width)
+        self.train_plan = os.environ.get("MCEDM_TRAIN_PLAN", "fused16")
         # inference plan: True = GroupNorm fused into the convs + 16-bit activations (fused_engine.py);
         # False = the unfused fp32-stream plan below (what training's forward uses)
         self.fused = os.environ.get("MCEDM_FUSED", "1") != "0"
         # "fp16": the plans above (bar 1e-2);  "fp32": split-operand fp32-accuracy plan (bar 1e-4, precise_engine.py)
         self.precision = "fp16"
         self._gn_coef: Dict[tuple, torch.Tensor] = {}
+
+    @property
+    def train_fmt(self) -> int:
+        """16-bit operand format of the training plan (include/mcedm_b200.h `op_fmt`)."""
+        return 1 if self.train_plan == "fused16" else 0
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):

@@ -29,7 +29,7 @@ from . import _lib as L
 
 class Act:
     """A raw 16-bit activation: tensor, GroupNorm partial sums, records per image, geometry."""
-    __slots__ = ("t", "st", "parts", "H", "W", "flat")
+    __slots__ = ("t", "st", "parts", "H", "W", "flat", "__weakref__")
 
     def __init__(self, t, st, parts, H, W, flat):
         self.t, self.st, self.parts, self.H, self.W, self.flat = t, st, parts, H, W, flat
@@ -37,11 +37,11 @@ class Act:
 
 class FusedMixin:
     # ------------------------------------------------------------------ buffers
-    def _fws(self, B, H, W, dev) -> dict:
-        key = ("fused", B, H, W, dev.index, self._fmt)
+    def _fws(self, B, H, W, dev, tag="fused") -> dict:
+        key = (tag, B, H, W, dev.index, self._fmt)
         ws = self._ws.get(key)
         if ws is None:
-            ws = self._ws[key] = {"geom": {}}
+            ws = self._ws[key] = {"geom": {}, "pool": {}, "dev": dev}
         return ws
 
     def _fgeom(self, ws, H, W):
@@ -74,11 +74,14 @@ class FusedMixin:
         return t
 
     # ------------------------------------------------------------------ launches
-    def _fcoef(self, ws, name, act: Act, gamma, beta, ss, ss_stride, eps, B, st):
+    def _fcoef(self, ws, name, act: Act, gamma, beta, ss, ss_stride, eps, B, st, save_mr=False):
+        """Per-(sample, channel) coefficients of one GroupNorm; save_mr (training forward): also the (mean, rstd) per
+        group that the backward needs -> returns (coef, meanrstd)."""
         coef = self._fbuf(ws, "coef." + name, (B, 128), torch.float32, act.t.device)
+        mr = self._fbuf(ws, "mr." + name, (B, 16, 2), torch.float32, act.t.device) if save_mr else None
         L.check(self.lib.mcedm_gn_coef(L.ptr(act.st), act.parts, L.ptr(gamma), L.ptr(beta), L.ptr(ss), ss_stride, 64, eps,
-                                       B, act.H, act.W, L.ptr(coef), None, st), "gn_coef")
-        return coef
+                                       B, act.H, act.W, L.ptr(coef), L.ptr(mr), st), "gn_coef")
+        return (coef, mr) if save_mr else coef
 
     def _fapply16(self, x: Act, coef, act_fn, resample, B, out: Act, st, dense_out=None, pooled: Optional[Act] = None):
         ip, ib = x.flat if x.flat is not None else (0, 0)
@@ -150,8 +153,13 @@ class FusedMixin:
         out.parts = 4 * (blk // 128)
 
     # ------------------------------------------------------------------ one UNetBlock
-    def _run_block_fused(self, blk, inputs: List[Act], B, ws, emb_stride, st, dev) -> Act:
+    def _run_block_fused(self, blk, inputs: List[Act], B, ws, emb_stride, st, dev, tape=None) -> Act:
+        """tape (training forward, train16_engine.py): a list receiving one record per block; every tensor the backward
+        reads (conv0 output, qkv, attention output, log-sum-exp, coefficients, mean / rstd) then gets a per-block buffer
+        instead of the per-level ones inference reuses."""
         x = inputs[0]
+        train = tape is not None
+        uq = (lambda s_: f"{s_}@{blk.name}") if train else (lambda s_: s_)
         if blk.up:
             H, W, rs, res_mode = x.H * 2, x.W * 2, 1, 2
         elif blk.down:
@@ -162,8 +170,12 @@ class FusedMixin:
         n = blk.name
         x_res = x                                                     # residual source of conv1 (identity skip)
         coef0 = [self._fcoef(ws, f"{n}.0.{i}", a, blk.g0[64 * i:64 * (i + 1)], blk.be0[64 * i:64 * (i + 1)], None, 0, eps,
-                            B, st) for i, a in enumerate(inputs)]
-        h = self._fact(ws, f"h.{H}", B, H, W, dev)
+                            B, st, save_mr=train) for i, a in enumerate(inputs)]
+        mr0 = None
+        if train:
+            mr0 = [c[1] for c in coef0]
+            coef0 = [c[0] for c in coef0]
+        h = self._fact(ws, uq(f"h.{H}"), B, H, W, dev)
         if rs:
             # resampling conv0 (adm_blocks.py:73-77): materialise silu(norm0(x)) at the new resolution, conv it as is
             op = self._fact(ws, f"op.{H}", B, H, W, dev, stats=False)
@@ -181,28 +193,42 @@ class FusedMixin:
         else:
             self._fconv(inputs, coef0, blk.w0, blk.b0, B, h, None, 0, st, ws=ws)
         ss = ws["ss"][blk.aff_index * self._ss_rows * 128:]
-        coef1 = self._fcoef(ws, f"{n}.1", h, blk.g1, blk.be1, ss, emb_stride, eps, B, st)
+        coef1 = self._fcoef(ws, f"{n}.1", h, blk.g1, blk.be1, ss, emb_stride, eps, B, st, save_mr=train)
+        mr1 = None
+        if train:
+            coef1, mr1 = coef1
         out = self._fact(ws, n, B, H, W, dev)
+        rec = dict(blk=blk, inputs=list(inputs), coef0=coef0, mr0=mr0, h=h, coef1=coef1, mr1=mr1, out=out, final=out,
+                   H=H, W=W, rs=rs) if train else None
         if blk.skip_conv:
             self._fconv([h], [coef1], blk.w1, blk.b1, B, out, None, 0, st, ctr=inputs, ws=ws)
         else:
             self._fconv([h], [coef1], blk.w1, blk.b1, B, out, x_res, res_mode, st, ws=ws)
         if blk.attn:
-            coef2 = self._fcoef(ws, f"{n}.2", out, blk.g2, blk.be2, None, 0, eps, B, st)
+            coef2 = self._fcoef(ws, f"{n}.2", out, blk.g2, blk.be2, None, 0, eps, B, st, save_mr=train)
+            mr2 = None
+            if train:
+                coef2, mr2 = coef2
             a2 = self._fbuf(ws, "att.in", (B, H, W, 64), self._dt16(), dev)
             self._fapply16(out, coef2, 0, 0, B, None, st, dense_out=a2)
-            qkv = self._fbuf(ws, "att.qkv", (B, H * W, 192), self._dt16(), dev)
-            att = self._fbuf(ws, "att.out", (B, H * W, 64), self._dt16(), dev)
+            qkv = self._fbuf(ws, uq("att.qkv"), (B, H * W, 192), self._dt16(), dev)
+            att = self._fbuf(ws, uq("att.out"), (B, H * W, 64), self._dt16(), dev)
+            lse = self._fbuf(ws, uq("att.lse"), (B, H * W), torch.float32, dev) if train else None
             self._conv([a2], [(0, 0, 0)], blk.wqkv, blk.bqkv, B, H, W, 192, qkv, 1, None, 0, None, st)
-            L.check(self.lib.mcedm_attention(L.ptr(qkv), B, H * W, L.ptr(att), None, self._fmt, st), "attention")
-            L.LAUNCHES[0] += 1                   # single-pass kernel + the flagged-tile two-pass launch
+            L.check(self.lib.mcedm_attention(L.ptr(qkv), B, H * W, L.ptr(att), L.ptr(lse), self._fmt, st), "attention")
+            if not train:
+                L.LAUNCHES[0] += 1               # single-pass kernel + the flagged-tile two-pass launch
             out2 = self._fact(ws, n + ".attn", B, H, W, dev)
             pitch, fblk = out2.flat if out2.flat is not None else (0, 0)
             L.check(self.lib.mcedm_conv_igemm16(L.ptr_array([att]), 1, L.int_array([0]), L.int_array([0]), L.int_array([0]), 1,
                                                 L.ptr(blk.wproj), L.ptr(blk.bproj), B, H, W, 64, L.ptr(out2.t), L.ptr(out.t),
                                                 1, pitch, fblk, L.ptr(out2.st), self._fmt, st), "conv_igemm16")
             out2.parts = H * W // 128
+            if train:
+                rec.update(coef2=coef2, mr2=mr2, qkv=qkv, att=att, lse=lse, final=out2)
             out = out2
+        if train:
+            tape.append(rec)
         return out
 
     # ------------------------------------------------------------------ whole network
@@ -235,8 +261,10 @@ class FusedMixin:
                                   L.ptr(self.b_m1), L.ptr(self.aff_w), L.ptr(self.aff_b), self.n_aff, Bemb, None,
                                   L.ptr(ss), st), "emb_mlp")
 
-    def _launch_rest_fused(self, x, cond, out, ws, B, H, dev, emb_stride, st):
+    def _launch_rest_fused(self, x, cond, out, ws, B, H, dev, emb_stride, st, tape=None):
         u = self.unet
+        train = tape is not None
+        blocks_tape = [] if train else None
         lib = self.lib
         W = 128
         t0 = self._fact(ws, "conv_in", B, H, W, dev)
@@ -252,15 +280,18 @@ class FusedMixin:
         cur = t0
         skips = [cur]
         for blk in self.blocks_enc:
-            cur = self._run_block_fused(blk, [cur], B, ws, emb_stride, st, dev)
+            cur = self._run_block_fused(blk, [cur], B, ws, emb_stride, st, dev, tape=blocks_tape)
             skips.append(cur)
         for blk in self.blocks_dec:
             inputs = [cur]
             if blk.n_src == 2:
                 inputs.append(skips.pop())
-            cur = self._run_block_fused(blk, inputs, B, ws, emb_stride, st, dev)
+            cur = self._run_block_fused(blk, inputs, B, ws, emb_stride, st, dev, tape=blocks_tape)
         # out_conv(silu(out_norm(x)))  (adm_blocks.py:403): the normalisation rides in the conv like everywhere else
-        coef = self._fcoef(ws, "out", cur, self.g_out, self.be_out, None, 0, u.out_norm.eps, B, st)
+        coef = self._fcoef(ws, "out", cur, self.g_out, self.be_out, None, 0, u.out_norm.eps, B, st, save_mr=train)
+        if train:
+            coef, mr_out = coef
+            tape.update(blocks=blocks_tape, t0=t0, last=cur, coef_out=coef, mr_out=mr_out)
         L.check(lib.mcedm_conv_head_fused(L.ptr(cur.t), L.ptr(coef), L.ptr(self.w_out), L.ptr(self.b_out), B, H,
                                           u.out_channels, L.ptr(out), self._fmt, st), "conv_head_fused")
         return out

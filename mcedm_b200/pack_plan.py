@@ -96,10 +96,11 @@ class PackPlan:
             p.data = torch.arange(off, off + p.numel(), dtype=torch.float32, device=dev).view(p.shape)
             off += p.numel()
         fmt0 = eng._fmt
+        self.fmt = eng.train_fmt
         try:
             eng._pack_dtype_override = torch.float32
             train_engine.DGRAD_DTYPE[0] = torch.float32
-            eng._fmt = 0
+            eng._fmt = self.fmt
             eng.pack(force=True)
             eng.pack_train(force=True)
             probe = []
@@ -116,9 +117,9 @@ class PackPlan:
             for p, d in zip(params, saved):
                 p.data = d
             eng._pack_dtype_override = None
-            train_engine.DGRAD_DTYPE[0] = torch.bfloat16
+            train_engine.DGRAD_DTYPE[0] = None
         # ---- 2. real mode: shapes / dtypes of the packed tensors, and the buffer layout
-        eng._fmt = 0
+        eng._fmt = self.fmt
         eng.pack(force=True)
         eng.pack_train(force=True)
         self.entries = _entries(eng)
@@ -143,14 +144,14 @@ class PackPlan:
         self.n16, self.n32 = n16, n32
         self.idx_a = table[torch.cat(idx16 + idx32a)].contiguous()
         self.idx_b = table[torch.cat(idx32b)].contiguous()
-        self.dtype16 = torch.bfloat16
+        self.dtype16 = torch.float16 if self.fmt else torch.bfloat16
         self.buf16 = torch.zeros(n16, dtype=self.dtype16, device=dev)
         self.buf32 = torch.zeros(n32, dtype=torch.float32, device=dev)
         self._base_holder = min(params, key=lambda p: p.data_ptr())    # keeps `base` alive
         eng._fmt = fmt0
 
     def valid_for(self, eng) -> bool:
-        return self.key == tuple(p.data_ptr() for p in eng.unet.parameters())
+        return self.key == tuple(p.data_ptr() for p in eng.unet.parameters()) and self.fmt == eng.train_fmt
 
     def bind(self):
         """Points the engine's packed attributes at the plan's buffers (cheap; no device work)."""
@@ -165,17 +166,18 @@ class PackPlan:
         import ctypes as C
 
         L.check(L.lib().mcedm_pack_gather(C.c_void_p(self.base_ptr), L.ptr(self.idx_a), L.ptr(self.idx_b), self.n16,
-                                          self.n32, 0, L.ptr(self.buf16), L.ptr(self.buf32), L.stream_ptr()),
+                                          self.n32, self.fmt, L.ptr(self.buf16), L.ptr(self.buf32), L.stream_ptr()),
                 "pack_gather")
 
 
 class PackMixin:
     def pack_fused(self):
-        """Training-time replacement of `pack(force=True); pack_train(force=True)`: one gather launch (bf16)."""
+        """Training-time replacement of `pack(force=True); pack_train(force=True)`: one gather launch, in the training
+        plan's operand format (`train_fmt`: fp16 for the fused 16-bit plan, bf16 for the fp32-stream plan)."""
         plan = getattr(self, "_pack_plan", None)
         if plan is None or not plan.valid_for(self):
             plan = self._pack_plan = PackPlan(self)
-        self._fmt = 0
+        self._fmt = self.train_fmt
         plan.run()
         plan.bind()
         self._packed_key = self._param_key()

@@ -26,21 +26,21 @@ import torch
 from . import _lib as L
 
 
-DGRAD_DTYPE = [torch.bfloat16]       # pack_plan.PackPlan probes the layouts with fp32 "index" weights
+DGRAD_DTYPE = [None]       # pack_plan.PackPlan probes the layouts with fp32 "index" weights (override of `dtype`)
 
 
-def pack_dgrad3x3(weight: torch.Tensor) -> torch.Tensor:
-    """[Cout, 64, 3, 3] (one 64-channel input slice) -> bf16 [9][ci][co(_pad 64)]: taps flipped, channels swapped."""
+def pack_dgrad3x3(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """[Cout, 64, 3, 3] (one 64-channel input slice) -> 16-bit [9][ci][co(_pad 64)]: taps flipped, channels swapped."""
     cout = weight.shape[0]
     w = weight.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, 64, cout)
     if cout < 64:
         w = torch.cat([w, w.new_zeros(9, 64, 64 - cout)], dim=2)
-    return w.to(DGRAD_DTYPE[0]).contiguous()
+    return w.to(DGRAD_DTYPE[0] or dtype).contiguous()
 
 
-def pack_dgrad1x1(weight2d: torch.Tensor) -> torch.Tensor:
-    """[co, ci] -> bf16 [1][ci][co]"""
-    return weight2d.detach().t().reshape(1, weight2d.shape[1], weight2d.shape[0]).to(DGRAD_DTYPE[0]).contiguous()
+def pack_dgrad1x1(weight2d: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """[co, ci] -> 16-bit [1][ci][co]"""
+    return weight2d.detach().t().reshape(1, weight2d.shape[1], weight2d.shape[0]).to(DGRAD_DTYPE[0] or dtype).contiguous()
 
 
 class TrainMixin:
@@ -67,23 +67,26 @@ class TrainMixin:
 
     # ------------------------------------------------------------------ packed weights of the data-gradient convs
     def pack_train(self, force: bool = False):
-        self._fmt = 0                     # training runs bf16 operands throughout (gradients need the range)
+        # operand format of the training plan: fp16 for the fused 16-bit plan (loss-scaled gradients), bf16 for the
+        # fp32-stream plan
+        self._fmt = self.train_fmt
         self.pack()
         if not force and getattr(self, "_packed_train_key", None) == self._packed_key:
             return
+        dt = torch.float16 if self._fmt else torch.bfloat16
         with torch.no_grad():
             for b in self.blocks_enc + self.blocks_dec:
                 m = b.mod
-                b.wd0 = [pack_dgrad3x3(m.conv0.weight[:, 64 * i:64 * (i + 1)]) for i in range(b.n_src)]
-                b.wd1 = pack_dgrad3x3(m.conv1.weight)
+                b.wd0 = [pack_dgrad3x3(m.conv0.weight[:, 64 * i:64 * (i + 1)], dt) for i in range(b.n_src)]
+                b.wd1 = pack_dgrad3x3(m.conv1.weight, dt)
                 if b.skip_conv:
-                    b.wdskip = [pack_dgrad1x1(m.skip.weight[:, 64 * i:64 * (i + 1), 0, 0]) for i in range(b.n_src)]
+                    b.wdskip = [pack_dgrad1x1(m.skip.weight[:, 64 * i:64 * (i + 1), 0, 0], dt) for i in range(b.n_src)]
                 if b.attn:
                     perm = torch.arange(192, device=m.qkv.weight.device).reshape(64, 3).t().reshape(-1)
                     wq = m.qkv.weight.detach()[perm][:, :, 0, 0]                      # [(q|k|v) x 64, ci]
-                    b.wdqkv = torch.cat([pack_dgrad1x1(wq[64 * j:64 * (j + 1)]) for j in range(3)], 0).contiguous()
-                    b.wdproj = pack_dgrad1x1(m.proj.weight[:, :, 0, 0])
-            self.wd_out = pack_dgrad3x3(self.unet.out_conv.weight)
+                    b.wdqkv = torch.cat([pack_dgrad1x1(wq[64 * j:64 * (j + 1)], dt) for j in range(3)], 0).contiguous()
+                    b.wdproj = pack_dgrad1x1(m.proj.weight[:, :, 0, 0], dt)
+            self.wd_out = pack_dgrad3x3(self.unet.out_conv.weight, dt)
         self._packed_train_key = self._packed_key
 
     # ------------------------------------------------------------------ training workspace
@@ -170,13 +173,17 @@ class TrainMixin:
     def forward_train(self, x: torch.Tensor, noise_labels: torch.Tensor, cond: Optional[torch.Tensor]) -> torch.Tensor:
         """Forward pass that keeps what `backward` needs. Returns F_x [B,out_ch,H,W] fp32 (a fresh tensor)."""
         x, nl, cond = self._check_inputs(x, noise_labels, cond)
-        self._fmt = 0
-        u = self.unet
         B, _, H, W = x.shape
-        if (W >> 2) % 16 != 0:
-            raise ValueError(f"training needs the coarsest level to be a multiple of 16 pixels wide (W={W})")
         if nl.numel() == 1:
             nl = nl.expand(B).contiguous()
+        if self.train_plan == "fused16" and W != 128:
+            self.train_plan = "fp32"          # the 16-bit plan is laid out for 128-pixel-wide fields
+        if self.train_plan == "fused16":
+            return self.forward_train16(x, nl, cond)
+        self._fmt = 0
+        u = self.unet
+        if (W >> 2) % 16 != 0:
+            raise ValueError(f"training needs the coarsest level to be a multiple of 16 pixels wide (W={W})")
         self.pack_train()
         self._grad_layout()
         dev = x.device
@@ -311,8 +318,8 @@ class TrainMixin:
         lib = self.lib
         n = lib.mcedm_wgrad_ctas(B, H, W)
         partial = self._t(tw, ("wgpart", self._job_id()), (n * taps * 4096,), torch.float32)
-        L.check(lib.mcedm_conv_wgrad(L.ptr(dy), 1 if dy_flat else 0, dy_ctot, dy_coff, L.ptr(a), 1 if a_flat else 0, 64,
-                                     0, B, H, W, taps, L.ptr(partial), st), "conv_wgrad")
+        L.check(lib.mcedm_conv_wgrad16(L.ptr(dy), 1 if dy_flat else 0, dy_ctot, dy_coff, L.ptr(a), 1 if a_flat else 0, 64,
+                                       0, B, H, W, taps, L.ptr(partial), self._fmt, st), "conv_wgrad")
         self._wjobs.append((partial.data_ptr(), dw.data_ptr(), n, taps, cin_total, ci_off, co_mul, co_add, co_count,
                             ci_count))
         self._job_refs += [partial, dw]
@@ -324,6 +331,8 @@ class TrainMixin:
         T = self._tape
         if T is None:
             raise L.McedmError("backward() without a preceding forward_train()")
+        if T.get("plan") == "fused16":
+            return self.backward16(dF)
         self._fmt = 0
         u, lib = self.unet, self.lib
         B, H, W, tw, tape = T["B"], T["H"], T["W"], T["tw"], T["tape"]

@@ -562,7 +562,7 @@ def test_sampling_after_a_training_step_runs_the_fused_fp16_plan(dev):
     torch.manual_seed(g["cpu_seed"])
     pl.training_step(_train_batch(g, dev), 0).backward()          # no optimizer step: the weights stay the fixture's
     eng = pl.model.engine()
-    assert eng._fmt == 0
+    assert eng._fmt == eng.train_fmt
     pl.eval()
     names = []
     real = eng.lib
@@ -596,10 +596,12 @@ def test_sampling_after_a_training_step_runs_the_fused_fp16_plan(dev):
     assert err_eager < 3e-3, err_eager
 
 
-def test_pack_plan_is_bit_identical_to_the_torch_packing(dev):
+@pytest.mark.parametrize("plan", ["fused16", "fp32"])
+def test_pack_plan_is_bit_identical_to_the_torch_packing(dev, plan):
     """pack_plan.PackPlan (one mcedm_pack_gather launch) against UNetEngine.pack + pack_train (the ~170 torch
     permute / flip / cast kernels it replaces): every packed tensor bit for bit, before and after the parameters
-    change in place, for the joint and the single-task network."""
+    change in place, for the joint and the single-task network, in the operand format of either training plan
+    (fp16 for "fused16", bf16 for the fp32-stream plan)."""
     from common import stress_unet
     from mcedm_b200 import pack_plan as PP
 
@@ -607,9 +609,10 @@ def test_pack_plan_is_bit_identical_to_the_torch_packing(dev):
         net, _, _ = stress_unet(config)
         net = net.to(dev)
         eng = net.engine()
+        eng.train_plan = plan
 
         def snapshot():
-            eng._fmt = 0
+            eng._fmt = eng.train_fmt
             eng.pack(force=True)
             eng.pack_train(force=True)
             return [(name, i, PP._get(o, name, i).clone()) for o, name, i, _ in PP._entries(eng)]
@@ -619,6 +622,7 @@ def test_pack_plan_is_bit_identical_to_the_torch_packing(dev):
         eng.pack_fused()
         got = [(name, i, PP._get(o, name, i)) for o, name, i, _ in PP._entries(eng)]
         assert len(got) == len(ref0)
+        assert {t.dtype for _, _, t in got if t.element_size() == 2} == {torch.float16 if plan == "fused16" else torch.bfloat16}
         for (n0, i0, a), (n1, i1, b) in zip(ref0, got):
             assert (n0, i0) == (n1, i1) and a.dtype == b.dtype and a.shape == b.shape
             assert b.data_ptr() % 512 == 0        # torch allocations are 512-byte aligned; slots are 1 KiB multiples
