@@ -249,16 +249,17 @@ MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrst
  * the padded-flat layout of mcedm_flat_geometry AT THAT TENSOR'S RESOLUTION (dy: the conv resolution; add0: per
  * add0_mode; x, add1, dx, dx16: Hin x Win).  dx16: 16-bit copy in x's layout; dx16_dense: a second, dense copy.
  * add16 != 0: add0 / add1 are 16-bit (op_fmt) too — the gradient of the residual stream without an fp32 master copy.
- * kcoef: scratch fp32 [B][64][4]; ticket: uint32 [B], ZERO before the first launch (each launch leaves it zero): the
+ * meanrstd / coef_ab: what the forward's mcedm_gn_coef wrote for this GroupNorm ([B][16][2], [B][128]).
+ * kcoef: scratch fp32 [B][192]; ticket: uint32 [B], ZERO before the first launch (each launch leaves it zero): the
  * last CTA of a sample to finish pass 1 folds that sample's partials once (fixed order: deterministic).
  * Win must be a power of two.  red_partial / dgb_partial / colsum_partial as in mcedm_gn_bwd, sized with
  * mcedm_gn_bwd16_ctas_per_img.
  */
 MCEDM_API int mcedm_gn_bwd16_ctas_per_img(int Hin, int Win, int B);
 MCEDM_API int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const void* x16, int x_pitch, int x_blk,
-                             int op_fmt, const float* meanrstd, const float* gamma, const float* beta,
-                             const float* scale_shift, int emb_batch_stride, int emb_shift_offset, int act,
-                             int resample, int B, int Hin, int Win, float* red_partial, float* kcoef,
+                             int op_fmt, const float* meanrstd, const float* coef_ab, const float* gamma,
+                             const float* beta, const float* scale_shift, int emb_batch_stride, int emb_shift_offset,
+                             int act, int resample, int B, int Hin, int Win, float* red_partial, float* kcoef,
                              unsigned int* ticket, float* dgb_partial, float* d_scale_shift, int dss_batch_stride,
                              const void* add0, int add0_mode, int add0_pitch, int add0_blk, const void* add1,
                              int add16, float* dx, void* dx16, void* dx16_dense, float* colsum_partial, void* stream);
@@ -305,6 +306,13 @@ MCEDM_API int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, int
 MCEDM_API int mcedm_conv_wgrad16(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
                                  int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, int op_fmt,
                                  void* stream);
+/* The same with `a` a RAW 64-channel activation: the operand act(a_coef.a * x + a_coef.b) (a_coef fp32 [B][128] from
+ * mcedm_gn_coef; a_act 1 SiLU, 0 identity) is formed row by row in shared memory by the warps that otherwise only run
+ * the epilogue, so the normalised operand of a weight gradient never exists in HBM (adm_blocks.py:161 / :166).
+ * a_coef NULL = mcedm_conv_wgrad16. */
+MCEDM_API int mcedm_conv_wgrad16_fused(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a,
+                                       int a_layout, int a_ctotal, int a_coff, const float* a_coef, int a_act, int B,
+                                       int H, int W, int taps, float* partial, int op_fmt, void* stream);
 MCEDM_API int mcedm_wgrad_reduce(const float* partial, int n_ctas, int taps, float* dw, int cin_total, int ci_off,
                                  int co_mul, int co_add, int co_count, int ci_count, int accumulate, void* stream);
 /* Every weight-gradient fold of a step in one launch (same arithmetic and order as mcedm_wgrad_reduce, accumulate = 0);

@@ -43,7 +43,7 @@ _PROTOTYPES = {
     "mcedm_gn_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp,
                      _vp, _vp, _i, _i, _vp, _vp, _vp],
     "mcedm_gn_bwd16_ctas_per_img": [_i, _i, _i],
-    "mcedm_gn_bwd16": [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
+    "mcedm_gn_bwd16": [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp,
                        _vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_reduce_rows": [_vp, _i, C.c_longlong, _i, C.c_longlong, _vp, _i, _f, _vp],
     "mcedm_reduce_rows_batched": [_vp, _i, _i, _vp],
@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "mcedm_wgrad_ctas": [_i, _i, _i],
     "mcedm_conv_wgrad": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "mcedm_conv_wgrad16": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "mcedm_conv_wgrad16_fused": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "mcedm_wgrad_reduce": [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mcedm_flat_geometry": [_i, _i, _ip, _ip],
     "mcedm_conv_flat": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],

@@ -42,6 +42,10 @@ struct WgradParams {
   int a_slot_bytes;        // (W + 2) * 128 rounded up to 1024
   float* partial;          // [gridDim.x][taps][64][64]
   uint32_t idesc;          // M = 128, N = 64, A and B both MN-major, operand format of the launch
+  const float* coef;       // NULL, or fp32 [B][128] = (a | b): `a` is a RAW activation and the operand is act(a*x + b),
+                           // applied to each row in shared memory by the (otherwise idle) epilogue warps
+  int act;                 // 1 SiLU, 0 identity
+  int fmt;                 // 0 bf16, 1 fp16
   unsigned int* err;
 };
 
@@ -59,7 +63,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   uint64_t* dy_empty = dy_full + S;
   uint64_t* a_full = dy_empty + S;
   uint64_t* a_empty = a_full + SA;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + SA);
+  uint64_t* a_ready = a_empty + SA;            // row transformed and visible to the async proxy (p.coef only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + SA);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r_begin = p.total_rows * blockIdx.x / gridDim.x;
@@ -76,6 +81,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     for (int i = 0; i < SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+      mbar_init(&a_ready[i], 4);
     }
     fence_barrier_init();
   }
@@ -142,7 +148,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
           ++waited;
         }
         const uint32_t as = ac % (uint32_t)SA, aph = (ac / (uint32_t)SA) & 1u;
-        mbar_wait(&a_full[as], aph, p.err, 0x4400 + as);
+        mbar_wait(p.coef ? &a_ready[as] : &a_full[as], aph, p.err, 0x4400 + as);
         tc_fence_after();
         // window slots w, w+1, w+2 hold dy rows y'-1, y', y'+1 (mirrors keep them contiguous)
         const uint32_t w0 = dy_base + ((hbase + j) % (uint32_t)S) * lbo;
@@ -183,6 +189,78 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     if (elect_one()) umma_commit(acc_full);
     __syncwarp();
   } else {
+    // ============== GroupNorm + SiLU transform of the `a` rows (raw activations), then the epilogue ==============
+    // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
+    // row (pixel 0 and pixel W+1 are the zero halo and stay zero); physical chunk = j ^ (pixel & 7) (SWIZZLE_128B,
+    // slots are 1 KB aligned) - the scheme of conv_rows.cu's transform warps.
+    if (p.coef != nullptr) {
+      const int t = (int)threadIdx.x - 64;
+      const int j = t & 7, prow = t >> 3;
+      uint32_t ac = 0;
+      long long r = r_begin;
+      while (r < r_end) {
+        const int b = (int)(r / p.H);
+        const int y0 = (int)(r - (long long)b * p.H);
+        const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+        float ca[8], cb[8];
+        {
+          const float4* cf = reinterpret_cast<const float4*>(p.coef + (long long)b * 128 + j * 8);
+          const float4 a0 = __ldg(cf), a1 = __ldg(cf + 1), b0 = __ldg(cf + 16), b1 = __ldg(cf + 17);
+          ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+          cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+          if (p.act) {     // silu(u) = h (1 + tanh h), h = u / 2: the coefficients are halved once
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              ca[e] *= 0.5f;
+              cb[e] *= 0.5f;
+            }
+          }
+        }
+        for (int jr = 0; jr < R; ++jr, ++ac) {
+          const uint32_t as = ac % (uint32_t)SA, aph = (ac / (uint32_t)SA) & 1u;
+          mbar_wait(&a_full[as], aph, p.err, 0x4600 + as);
+          const uint32_t base = smem_u32(a_smem) + as * (uint32_t)p.a_slot_bytes;
+          for (int px0 = 1 + prow; px0 <= p.W; px0 += 64) {
+            uint4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int px = px0 + 16 * i;
+              if (px <= p.W) v[i] = lds128(base + px * 128 + ((j ^ (px & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int px = px0 + 16 * i;
+              if (px <= p.W) {
+                const uint32_t in[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float x0, x1;
+                  if (p.fmt) {
+                    const float2 f = unpack_f16x2(in[e]);
+                    x0 = f.x;
+                    x1 = f.y;
+                  } else {
+                    x0 = bf16_lo(in[e]);
+                    x1 = bf16_hi(in[e]);
+                  }
+                  float y0v = fmaf(x0, ca[2 * e], cb[2 * e]), y1v = fmaf(x1, ca[2 * e + 1], cb[2 * e + 1]);
+                  if (p.act) {
+                    y0v = silu_from_half_arg(y0v);
+                    y1v = silu_from_half_arg(y1v);
+                  }
+                  o[e] = pack_op2(y0v, y1v, p.fmt);
+                }
+                sts128(base + px * 128 + ((j ^ (px & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive_warp(&a_ready[as]);
+        }
+        r += R;
+      }
+    }
     // ======================================= epilogue =======================================
     const int q = warp & 3;
     const int m = q * 32 + lane;            // accumulator row: co = m & 63, upper half = second tap of the pair
@@ -315,7 +393,15 @@ extern "C" int mcedm_conv_wgrad(const void* dy, int dy_layout, int dy_ctotal, in
 extern "C" int mcedm_conv_wgrad16(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a, int a_layout,
                                   int a_ctotal, int a_coff, int B, int H, int W, int taps, float* partial, int op_fmt,
                                   void* stream) {
+  return mcedm_conv_wgrad16_fused(dy, dy_layout, dy_ctotal, dy_coff, a, a_layout, a_ctotal, a_coff, nullptr, 0, B, H, W,
+                                  taps, partial, op_fmt, stream);
+}
+
+extern "C" int mcedm_conv_wgrad16_fused(const void* dy, int dy_layout, int dy_ctotal, int dy_coff, const void* a,
+                                        int a_layout, int a_ctotal, int a_coff, const float* a_coef, int a_act, int B,
+                                        int H, int W, int taps, float* partial, int op_fmt, void* stream) {
   using namespace mcedm;
+  MCEDM_REQUIRE(a_coef == nullptr || a_ctotal == 64, "conv_wgrad: the in-kernel transform takes a 64-channel tensor");
   MCEDM_REQUIRE(B >= 1 && H >= 1 && W >= 16 && W <= 128 && W % 16 == 0, "conv_wgrad: unsupported W=%d", W);
   MCEDM_REQUIRE(taps == 9 || taps == 1, "conv_wgrad: taps=%d (9 or 1)", taps);
   MCEDM_REQUIRE(dy_ctotal % 64 == 0 && a_ctotal % 64 == 0 && dy_coff % 64 == 0 && a_coff % 64 == 0 &&
@@ -341,6 +427,9 @@ extern "C" int mcedm_conv_wgrad16(const void* dy, int dy_layout, int dy_ctotal, 
   if (p.n_aslots > 12) p.n_aslots = 12;
   p.partial = partial;
   p.idesc = umma_idesc_16(128, 64, 1, 1, op_fmt ? 1 : 0);
+  p.coef = a_coef;
+  p.act = a_act ? 1 : 0;
+  p.fmt = op_fmt ? 1 : 0;
   p.err = watchdog_ptr();
   MCEDM_REQUIRE(p.err != nullptr, "conv_wgrad: cannot allocate the watchdog word");
   CUtensorMap tm_dy, tm_a;
@@ -348,7 +437,7 @@ extern "C" int mcedm_conv_wgrad16(const void* dy, int dy_layout, int dy_ctotal, 
   if (rc) return rc;
   rc = make_pix_tmap(&tm_a, a, a_layout, a_ctotal, B, H, W, W + 2, &p.a_row_off);
   if (rc) return rc;
-  const int smem = 1024 + (p.n_slots + 2) * p.dy_slot_bytes + p.n_aslots * p.a_slot_bytes + 256;
+  const int smem = 1024 + (p.n_slots + 2) * p.dy_slot_bytes + p.n_aslots * p.a_slot_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MCEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

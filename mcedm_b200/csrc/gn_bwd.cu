@@ -414,6 +414,7 @@ struct GnBwd16Params {
   const void* x; int x_pitch, x_blk;           // at Hin x Win; dx / dx16 / add1 share this layout
   int fmt;                                     // 16-bit format of x, dy, dx16 (and of 16-bit adds): 0 bf16, 1 fp16
   const float* meanrstd;
+  const float* coef_ab;                        // [B][128] = (a | b) of u = a x + b, from the forward's mcedm_gn_coef
   const float* gamma;
   const float* beta;
   const float* scale_shift;
@@ -422,7 +423,7 @@ struct GnBwd16Params {
   int B, Hin, Win, w_shift;
   int ctas_per_img, pix_per_cta;
   float* red_partial;                          // [B][ctas_per_img][64][2]
-  float* kcoef;                                // [B][64][4] = (rstd*k, rstd*m1, rstd*m2, -) written by the fold
+  float* kcoef;                                // [B][3][64] = rstd*k | rstd*m1 | rstd*m2 written by the fold
   unsigned int* ticket;                        // [B], zero before the launch, zero again after it
   const void* add0; int add0_mode, add0_pitch, add0_blk;   // at ITS resolution (mode as in GnBwdParams)
   const void* add1;
@@ -440,31 +441,6 @@ __device__ __forceinline__ long long lay_index(int pitch, int blk, int b, int y,
   if (pitch > 0) return (long long)b * blk + (long long)(y + 1) * pitch + x;
   return ((long long)b * H + y) * W + x;
 }
-// per-(sample, channel) forward coefficients (shared prologue of both passes): sA / sB = (a, b) of u = a x + b
-__device__ __forceinline__ void gn16_prologue(const GnBwd16Params& p, int b, float* sMean, float* sRstd, float* sA,
-                                              float* sB) {
-  if (threadIdx.x < 16) {
-    const float2 v = *reinterpret_cast<const float2*>(p.meanrstd + ((long long)b * 16 + threadIdx.x) * 2);
-    sMean[threadIdx.x] = v.x;
-    sRstd[threadIdx.x] = v.y;
-  }
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    const int c = threadIdx.x;
-    float a = sRstd[c >> 2] * p.gamma[c];
-    float bb = p.beta[c] - sMean[c >> 2] * a;
-    if (p.scale_shift) {
-      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
-      const float sc = 1.0f + ss[c];
-      a *= sc;
-      bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
-    }
-    sA[c] = a;
-    sB[c] = bb;
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ void unpack8(const uint4 r, int fmt, float (&v)[8]) {
   if (fmt) {
     const float2 a = unpack_f16x2(r.x), b = unpack_f16x2(r.y), c = unpack_f16x2(r.z), d = unpack_f16x2(r.w);
@@ -522,17 +498,17 @@ struct Gn16Coef {
   float a[8], bb[8];
   float rs0, mr0, rs1, mr1;      // the 8 channels span two 4-channel groups
 };
-__device__ __forceinline__ void gn16_coef(const float* sMean, const float* sRstd, const float* sA, const float* sB,
-                                          int oct, Gn16Coef& cf) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    cf.a[k] = sA[oct * 8 + k];
-    cf.bb[k] = sB[oct * 8 + k];
-  }
-  cf.rs0 = sRstd[2 * oct];
-  cf.mr0 = sMean[2 * oct] * cf.rs0;
-  cf.rs1 = sRstd[2 * oct + 1];
-  cf.mr1 = sMean[2 * oct + 1] * cf.rs1;
+// forward coefficients of the thread's 8 channels straight from global memory (independent loads, no barrier)
+__device__ __forceinline__ void gn16_coef(const GnBwd16Params& p, int b, int oct, Gn16Coef& cf) {
+  const float4* ab = reinterpret_cast<const float4*>(p.coef_ab + (long long)b * 128 + oct * 8);
+  const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1), b0 = __ldg(ab + 16), b1 = __ldg(ab + 17);
+  const float4 m = __ldg(reinterpret_cast<const float4*>(p.meanrstd + ((long long)b * 16 + 2 * oct) * 2));
+  cf.a[0] = a0.x; cf.a[1] = a0.y; cf.a[2] = a0.z; cf.a[3] = a0.w;
+  cf.a[4] = a1.x; cf.a[5] = a1.y; cf.a[6] = a1.z; cf.a[7] = a1.w;
+  cf.bb[0] = b0.x; cf.bb[1] = b0.y; cf.bb[2] = b0.z; cf.bb[3] = b0.w;
+  cf.bb[4] = b1.x; cf.bb[5] = b1.y; cf.bb[6] = b1.z; cf.bb[7] = b1.w;
+  cf.rs0 = m.y; cf.mr0 = m.x * m.y;
+  cf.rs1 = m.w; cf.mr1 = m.z * m.w;
 }
 
 // 256 threads = 8 channel octets x 32 pixel lanes; FAST (no resampling anywhere): NP pixels' 128-bit loads are issued
@@ -543,15 +519,13 @@ constexpr int kGnNPa = 2;   // pass 2: up to four streams + the stores
 
 template <bool FAST>
 __global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Params p) {
-  __shared__ float sMean[16], sRstd[16], sA[64], sB[64];
   __shared__ float red[32][64][2];
   __shared__ float sG1[64], sG2[64];
   __shared__ unsigned int sLast;
   const int b = blockIdx.y;
-  gn16_prologue(p, b, sMean, sRstd, sA, sB);
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   Gn16Coef cf;
-  gn16_coef(sMean, sRstd, sA, sB, oct, cf);
+  gn16_coef(p, b, oct, cf);
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
@@ -647,7 +621,7 @@ __global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Param
     const float g = p.gamma[ch], be = p.beta[ch];
     const float A1 = (float)a1, A2 = (float)a2;
     kk = g * sc;                                  // d xh = kk * du
-    rstd_c = sRstd[ch >> 2];
+    rstd_c = p.meanrstd[((long long)b * 16 + (ch >> 2)) * 2 + 1];
     sG1[ch] = kk * A1;
     sG2[ch] = kk * A2;
     p.dgb_partial[((long long)b * 64 + ch) * 2 + 0] = sc * A2;     // d gamma contribution of sample b
@@ -663,30 +637,31 @@ __global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Param
     const float cnt = 4.0f * (float)p.Hin * (float)p.Win;
     const float m1 = ((sG1[g0] + sG1[g0 + 1]) + (sG1[g0 + 2] + sG1[g0 + 3])) / cnt;
     const float m2 = ((sG2[g0] + sG2[g0 + 1]) + (sG2[g0 + 2] + sG2[g0 + 3])) / cnt;
-    *reinterpret_cast<float4*>(p.kcoef + ((long long)b * 64 + ch) * 4) =
-        make_float4(rstd_c * kk, rstd_c * m1, rstd_c * m2, 0.f);
+    float* kc = p.kcoef + (long long)b * 192 + ch;
+    kc[0] = rstd_c * kk;
+    kc[64] = rstd_c * m1;
+    kc[128] = rstd_c * m2;
   }
   if (threadIdx.x == 0) p.ticket[b] = 0u;         // ready for the next launch on this stream
 }
 
 template <bool FAST>
 __global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Params p) {
-  __shared__ float sMean[16], sRstd[16], sA[64], sB[64];
   __shared__ float red[32][64];
   const int b = blockIdx.y;
-  gn16_prologue(p, b, sMean, sRstd, sA, sB);
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   Gn16Coef cf;
-  gn16_coef(sMean, sRstd, sA, sB, oct, cf);
+  gn16_coef(p, b, oct, cf);
   // dx = k0[c] du - (k1 + xh k2) with k1, k2 constant inside a 4-channel group
   float k0[8], cs[8];
-  const float4* kc = reinterpret_cast<const float4*>(p.kcoef + ((long long)b * 64 + oct * 8) * 4);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    k0[k] = kc[k].x;
-    cs[k] = 0.f;
+  const float* kc = p.kcoef + (long long)b * 192 + oct * 8;
+  {
+    const float4 q0 = *reinterpret_cast<const float4*>(kc), q1 = *reinterpret_cast<const float4*>(kc + 4);
+    k0[0] = q0.x; k0[1] = q0.y; k0[2] = q0.z; k0[3] = q0.w; k0[4] = q1.x; k0[5] = q1.y; k0[6] = q1.z; k0[7] = q1.w;
   }
-  const float k1a = kc[0].y, k2a = kc[0].z, k1b = kc[4].y, k2b = kc[4].z;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+  const float k1a = kc[64], k2a = kc[128], k1b = kc[68], k2b = kc[132];
   const int pix0 = blockIdx.x * p.pix_per_cta;
   if (FAST) {
     // no resampling, residual-path gradients (if any) 16-bit at the same resolution
@@ -798,10 +773,11 @@ __global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Par
   }
 }
 
-// CTAs of the 16-bit passes: >= 128 pixels (32 lanes x 4 pixels in flight), ~4 per SM when the batch allows it
+// CTAs of the 16-bit passes: >= 128 pixels (32 lanes x 4 pixels in flight); about ONE wave of equal CTAs (2 resident per
+// SM) when the batch allows it, so the per-CTA prologue (coefficient loads) is paid once
 static int pick_pix_per_cta16(int work, int B) {
   int per = 2048;
-  while (per > 128 && ((work % per) != 0 || (long long)(work / per) * B < 4LL * num_sms())) per >>= 1;
+  while (per > 128 && ((work % per) != 0 || 2LL * (work / per) * B < 3LL * num_sms())) per >>= 1;
   while (per > 16 && (work % per) != 0) per >>= 1;
   return per;
 }
@@ -867,9 +843,9 @@ extern "C" int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrs
 
 
 extern "C" int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const void* x16, int x_pitch, int x_blk,
-                              int op_fmt, const float* meanrstd, const float* gamma, const float* beta,
-                              const float* scale_shift, int emb_batch_stride, int emb_shift_offset, int act,
-                              int resample, int B, int Hin, int Win, float* red_partial, float* kcoef,
+                              int op_fmt, const float* meanrstd, const float* coef_ab, const float* gamma,
+                              const float* beta, const float* scale_shift, int emb_batch_stride, int emb_shift_offset,
+                              int act, int resample, int B, int Hin, int Win, float* red_partial, float* kcoef,
                               unsigned int* ticket, float* dgb_partial, float* d_scale_shift, int dss_batch_stride,
                               const void* add0, int add0_mode, int add0_pitch, int add0_blk, const void* add1,
                               int add16, float* dx, void* dx16, void* dx16_dense, float* colsum_partial,
@@ -878,13 +854,14 @@ extern "C" int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const 
   MCEDM_REQUIRE(B >= 1 && (Hin * Win) % 16 == 0 && (Win & (Win - 1)) == 0, "gn_bwd16: bad shape %dx%d", Hin, Win);
   MCEDM_REQUIRE(resample >= 0 && resample <= 2 && add0_mode >= 0 && add0_mode <= 2, "gn_bwd16: resample=%d add0_mode=%d",
                 resample, add0_mode);
-  MCEDM_REQUIRE(dy16 && x16 && meanrstd && red_partial && dgb_partial && kcoef && ticket, "gn_bwd16: missing buffers");
+  MCEDM_REQUIRE(dy16 && x16 && meanrstd && coef_ab && red_partial && dgb_partial && kcoef && ticket,
+                "gn_bwd16: missing buffers");
   GnBwd16Params p;
   memset(&p, 0, sizeof(p));
   p.dy = dy16; p.dy_pitch = dy_pitch; p.dy_blk = dy_blk;
   p.x = x16; p.x_pitch = x_pitch; p.x_blk = x_blk;
   p.fmt = op_fmt ? 1 : 0;
-  p.meanrstd = meanrstd; p.gamma = gamma; p.beta = beta; p.scale_shift = scale_shift;
+  p.meanrstd = meanrstd; p.coef_ab = coef_ab; p.gamma = gamma; p.beta = beta; p.scale_shift = scale_shift;
   p.emb_batch_stride = emb_batch_stride; p.emb_shift_offset = emb_shift_offset;
   p.act = act; p.resample = resample;
   p.B = B; p.Hin = Hin; p.Win = Win;

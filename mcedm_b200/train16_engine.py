@@ -14,10 +14,13 @@ inference data flow (fused_engine.py) for the forward and mirrors it in the back
               saturate instead of overflowing) and the flat gradient buffer is multiplied by 1/S at the end.
               * data gradients of the 3x3 convs = the fused forward kernels on 16-bit gradients (no transform),
                 writing 16-bit;
-              * GroupNorm(+SiLU, scale/shift, resample) backward = mcedm_gn_bwd16: raw fp16 x, 16-bit dy, fp32
-                residual-path gradients (the gradient of the residual stream keeps an fp32 master copy);
-              * weight gradients need the normalised operand: recomputed by one mcedm_gn_apply16 pass right before the
-                launch (4 B per element) instead of stored by the forward;
+              * GroupNorm(+SiLU, scale/shift, resample) backward = mcedm_gn_bwd16: raw fp16 x, 16-bit dy, 16-bit
+                residual-path gradients (GRAD_MASTER_FP32 keeps an fp32 master copy of the residual-stream gradient:
+                measured no accuracy difference, 8 more bytes per element);
+              * weight gradients need the normalised operand: formed from the raw activation inside the weight-gradient
+                kernel (mcedm_conv_wgrad16_fused: the warps that otherwise only run its epilogue transform each row in
+                shared memory), so it is neither stored by the forward nor recomputed through HBM; only the resampled
+                operands of the four up / down blocks are materialised by an mcedm_gn_apply16 pass;
               * 1x1 convolutions on the narrow levels run on the padded-flat position sequence as is.
   Per block: forward 10 B, backward ~40 B per activation element (fp32-stream plan: 28 + ~75).
 
@@ -104,7 +107,7 @@ class Train16Mixin:
             L.check(self.lib.mcedm_conv_flat_fused(L.ptr(src), None, L.ptr(wd), None, B, H, W, 64, L.ptr(out), 0, None, 0,
                                                    0, 0, 0, None, self._fmt, st), "conv_flat_fused")
 
-    def _gn_bwd16(self, ws, dy, dy_lay, x: Act, mr, gamma, beta, ss, act, rs, B, dgamma, dbeta, dss, add0, add0_mode,
+    def _gn_bwd16(self, ws, dy, dy_lay, x: Act, mr, coef, gamma, beta, ss, act, rs, B, dgamma, dbeta, dss, add0, add0_mode,
                   add0_lay, add1, pend, gs, want_dense, st):
         """One GroupNorm(+SiLU, +scale/shift, +resample) backward on raw 16-bit x / 16-bit dy.  `gs` (a _gset16 dict)
         receives dx, or `pend` (a bare tensor in x's layout: fp32 with the master copy, else 16-bit)."""
@@ -112,7 +115,7 @@ class Train16Mixin:
         Hin, Win = x.H, x.W
         n_cta = lib.mcedm_gn_bwd16_ctas_per_img(Hin, Win, B)
         red = self._t(ws, ("gnred", B * n_cta), (B, n_cta, 64, 2), torch.float32)
-        kcoef = self._t(ws, "gnkcoef", (B, 64, 4), torch.float32)
+        kcoef = self._t(ws, "gnkcoef", (B, 192), torch.float32)
         ticket = self._t(ws, "gnticket", (B,), torch.int32, zero=True)
         jid = self._job_id()
         dgb = self._t(ws, ("gndgb", jid), (B, 64, 2), torch.float32)
@@ -127,7 +130,7 @@ class Train16Mixin:
             dx16 = pend
         xl = x.flat if x.flat is not None else (0, 0)
         L.check(lib.mcedm_gn_bwd16(L.ptr(dy), dy_lay[0], dy_lay[1], L.ptr(x.t), xl[0], xl[1], self._fmt, L.ptr(mr),
-                                   L.ptr(gamma), L.ptr(beta), L.ptr(ss), 128, 64, act, rs, B, Hin, Win, L.ptr(red),
+                                   L.ptr(coef), L.ptr(gamma), L.ptr(beta), L.ptr(ss), 128, 64, act, rs, B, Hin, Win, L.ptr(red),
                                    L.ptr(kcoef), L.ptr(ticket), L.ptr(dgb), L.ptr(dss), 128, L.ptr(add0), add0_mode,
                                    add0_lay[0], add0_lay[1], L.ptr(add1), 0 if self.GRAD_MASTER_FP32 else 1,
                                    L.ptr(out_f32), L.ptr(dx16), L.ptr(dense), L.ptr(cs), st), "gn_bwd16")
@@ -181,16 +184,15 @@ class Train16Mixin:
         L.check(lib.mcedm_nchw_to_nhwc_pad16(L.ptr(dF), u.out_channels, None, 0, B, H, W, L.ptr(dFp), 0, S, fmt, st),
                 "pad dF")
         last: Act = T["last"]
-        a_out = recompute(last, T["coef_out"], 1, 0, H, W)
-        self._wgrad(ws, dFp, False, 64, 0, a_out.t, False, B, H, W, 9, G(u.out_conv.weight), 64, 0, st,
-                    co_count=u.out_channels)
+        self._wgrad(ws, dFp, False, 64, 0, last.t, False, B, H, W, 9, G(u.out_conv.weight), 64, 0, st,
+                    co_count=u.out_channels, a_coef=T["coef_out"])
         cs_tmp = self._t(ws, ("cs_tmp", self._job_id()), (csn, 64), torch.float32)
         L.check(lib.mcedm_colsum16(L.ptr(dFp), B * H * W, 64, 0, L.ptr(cs_tmp), csn, fmt, st), "colsum")
         self._reduce_rows(cs_tmp, csn, 64, u.out_channels, 1, G(u.out_conv.bias), st)
         d_a = self._buf16(ws, ("d16", H, W), B, H, W, dev)
         self._dgrad16(ws, dFp, self.wd_out, B, H, W, d_a, st)
         gs = self._gset16(ws, B, H, W, parity, need_dense(last), dev)
-        self._gn_bwd16(ws, d_a, self._lay(ws, H, W), last, T["mr_out"], self.g_out, self.be_out, None, 1, 0, B,
+        self._gn_bwd16(ws, d_a, self._lay(ws, H, W), last, T["mr_out"], T["coef_out"], self.g_out, self.be_out, None, 1, 0, B,
                        G(u.out_norm.weight), G(u.out_norm.bias), None, None, 0, (0, 0), None, None, gs,
                        need_dense(last), st)
         grads = {id(last): gs}
@@ -218,12 +220,10 @@ class Train16Mixin:
                 L.check(lib.mcedm_attention_bwd16(L.ptr(qkv), L.ptr(att), L.ptr(d_att), L.ptr(rec["lse"]), B, Lq,
                                                   L.ptr(dvec), L.ptr(dq), L.ptr(dk), L.ptr(dv), fmt, st), "attention_bwd")
                 L.LAUNCHES[0] += 2
-                a2 = self._fbuf(ws, "att.in", (B, Hb, Wb, 64), self._dt16(), dev)
-                self._fapply16(out, rec["coef2"], 0, 0, B, None, st, dense_out=a2)
                 qb = self._t(ws, ("qkv_bias_tmp", blk.name), (3, 64), torch.float32)
                 for j, dj in enumerate((dq, dk, dv)):
-                    self._wgrad(ws, dj, False, 64, 0, a2, False, B, Hb, Wb, 1, G(m.qkv.weight), 64, 0, st, co_mul=3,
-                                co_add=j)
+                    self._wgrad(ws, dj, False, 64, 0, out.t, is_flat, B, Hb, Wb, 1, G(m.qkv.weight), 64, 0, st, co_mul=3,
+                                co_add=j, a_coef=rec["coef2"], a_act=0)
                     cs_tmp = self._t(ws, ("cs_tmp", self._job_id()), (csn, 64), torch.float32)
                     L.check(lib.mcedm_colsum16(L.ptr(dj), B * Lq, 64, 0, L.ptr(cs_tmp), csn, fmt, st), "colsum")
                     self._reduce_rows(cs_tmp, csn, 64, 64, 1, qb[j], st)
@@ -232,15 +232,15 @@ class Train16Mixin:
                 self._igemm1x1([dq, dk, dv], blk.wdqkv, B, Hb, Wb, 64, d_a2, 1, st)
                 parity ^= 1
                 gs_out = self._gset16(ws, B, Hb, Wb, parity, False, dev)
-                self._gn_bwd16(ws, d_a2, (0, 0), out, rec["mr2"], blk.g2, blk.be2, None, 0, 0, B, G(m.norm2.weight),
+                self._gn_bwd16(ws, d_a2, (0, 0), out, rec["mr2"], rec["coef2"], blk.g2, blk.be2, None, 0, 0, B, G(m.norm2.weight),
                                G(m.norm2.bias), None, gs["f32"] if master else gs["bf"], 0, lay, None, None, gs_out,
                                False, st)
                 gs = gs_out
             # out = conv1(a1) + b1 + skip(x)
             self._bias_grad(gs, B, G(m.conv1.bias), st)
             h: Act = rec["h"]
-            a1 = recompute(h, rec["coef1"], 1, 0, Hb, Wb)
-            self._wgrad(ws, gs["bf"], is_flat, 64, 0, a1.t, is_flat, B, Hb, Wb, 9, G(m.conv1.weight), 64, 0, st)
+            self._wgrad(ws, gs["bf"], is_flat, 64, 0, h.t, is_flat, B, Hb, Wb, 9, G(m.conv1.weight), 64, 0, st,
+                        a_coef=rec["coef1"])
             if blk.skip_conv:
                 self._bias_grad(gs, B, G(m.skip.bias), st)
                 for i, xi in enumerate(rec["inputs"]):
@@ -250,16 +250,20 @@ class Train16Mixin:
             self._dgrad16(ws, gs["bf"], blk.wd1, B, Hb, Wb, d_a1, st)
             d_hb = self._buf16(ws, ("d_h16", Hb, Wb), B, Hb, Wb, dev)
             hset = dict(f32=None, bf=d_hb, dense=None, cs=None, n_cta=lib.mcedm_gn_bwd16_ctas_per_img(Hb, Wb, B))
-            self._gn_bwd16(ws, d_a1, lay, h, rec["mr1"], blk.g1, blk.be1, ss_all[blk.aff_index], 1, 0, B,
+            self._gn_bwd16(ws, d_a1, lay, h, rec["mr1"], rec["coef1"], blk.g1, blk.be1, ss_all[blk.aff_index], 1, 0, B,
                            G(m.norm1.weight), G(m.norm1.bias), dss[blk.aff_index], None, 0, (0, 0), None, None, hset,
                            False, st)
             self._bias_grad(hset, B, G(m.conv0.bias), st)
             parity ^= 1
             for i in reversed(range(blk.n_src)):
                 xi: Act = rec["inputs"][i]
-                a_i = recompute(xi, rec["coef0"][i], 1, rs, Hb, Wb)
-                self._wgrad(ws, d_hb, is_flat, 64, 0, a_i.t, is_flat, B, Hb, Wb, 9, G(m.conv0.weight), 64 * blk.n_src,
-                            64 * i, st)
+                if rs:     # resampled operand: materialised (the in-kernel transform works on same-resolution rows)
+                    a_i = recompute(xi, rec["coef0"][i], 1, rs, Hb, Wb)
+                    self._wgrad(ws, d_hb, is_flat, 64, 0, a_i.t, is_flat, B, Hb, Wb, 9, G(m.conv0.weight),
+                                64 * blk.n_src, 64 * i, st)
+                else:
+                    self._wgrad(ws, d_hb, is_flat, 64, 0, xi.t, is_flat, B, Hb, Wb, 9, G(m.conv0.weight),
+                                64 * blk.n_src, 64 * i, st, a_coef=rec["coef0"][i])
                 d_ai = self._buf16(ws, ("d16", Hb, Wb), B, Hb, Wb, dev)
                 self._dgrad16(ws, d_hb, blk.wd0[i], B, Hb, Wb, d_ai, st)
                 if blk.skip_conv:
@@ -280,13 +284,13 @@ class Train16Mixin:
                 if not first_consumer:
                     # a later consumer (decoder skip connection): keep the partial gradient until the first one runs
                     pend = self._buf16(ws, ("pending", id(xi)), B, xi.H, xi.W, dev, gdt)
-                    self._gn_bwd16(ws, d_ai, lay, xi, rec["mr0"][i], g0, be0, None, 1, rs, B, dg0, db0, None, add0,
+                    self._gn_bwd16(ws, d_ai, lay, xi, rec["mr0"][i], rec["coef0"][i], g0, be0, None, 1, rs, B, dg0, db0, None, add0,
                                    add0_mode, lay, None, pend, None, False, st)
                     pending[id(xi)] = pend
                 else:
                     nd = need_dense(xi)
                     gnext = self._gset16(ws, B, xi.H, xi.W, parity, nd, dev)
-                    self._gn_bwd16(ws, d_ai, lay, xi, rec["mr0"][i], g0, be0, None, 1, rs, B, dg0, db0, None, add0,
+                    self._gn_bwd16(ws, d_ai, lay, xi, rec["mr0"][i], rec["coef0"][i], g0, be0, None, 1, rs, B, dg0, db0, None, add0,
                                    add0_mode, lay, pending.pop(id(xi), None), None, gnext, nd, st)
                     grads[id(xi)] = gnext
 

@@ -314,12 +314,14 @@ class TrainMixin:
         self._conv3x3([src], [], wd, None, B, H, W, 64, out, None, 0, None, st, flat=flat)
 
     def _wgrad(self, tw, dy, dy_flat, dy_ctot, dy_coff, a, a_flat, B, H, W, taps, dw, cin_total, ci_off, st, co_mul=1,
-               co_add=0, co_count=64, ci_count=64):
+               co_add=0, co_count=64, ci_count=64, a_coef=None, a_act=1):
+        """a_coef (fp32 [B][128]): `a` is a raw activation, the kernel forms act(coef.a * a + coef.b) in shared memory."""
         lib = self.lib
         n = lib.mcedm_wgrad_ctas(B, H, W)
         partial = self._t(tw, ("wgpart", self._job_id()), (n * taps * 4096,), torch.float32)
-        L.check(lib.mcedm_conv_wgrad16(L.ptr(dy), 1 if dy_flat else 0, dy_ctot, dy_coff, L.ptr(a), 1 if a_flat else 0, 64,
-                                       0, B, H, W, taps, L.ptr(partial), self._fmt, st), "conv_wgrad")
+        L.check(lib.mcedm_conv_wgrad16_fused(L.ptr(dy), 1 if dy_flat else 0, dy_ctot, dy_coff, L.ptr(a),
+                                             1 if a_flat else 0, 64, 0, L.ptr(a_coef), a_act, B, H, W, taps,
+                                             L.ptr(partial), self._fmt, st), "conv_wgrad")
         self._wjobs.append((partial.data_ptr(), dw.data_ptr(), n, taps, cin_total, ci_off, co_mul, co_add, co_count,
                             ci_count))
         self._job_refs += [partial, dw]

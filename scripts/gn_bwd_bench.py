@@ -33,13 +33,14 @@ for H in (128, 64, 32):
     gamma, beta = torch.randn(64, device=dev), torch.randn(64, device=dev)
     n_cta = lib.mcedm_gn_bwd16_ctas_per_img(H, W, B)
     red = torch.empty(B, n_cta, 64, 2, device=dev)
-    kcoef = torch.empty(B, 64, 4, device=dev)
+    kcoef = torch.empty(B, 192, device=dev)
+    coefab = torch.randn(B, 128, device=dev)
     ticket = torch.zeros(B, device=dev, dtype=torch.int32)
     dgb = torch.empty(B, 64, 2, device=dev)
     cs = torch.empty(B * n_cta, 64, device=dev)
 
     def call(with_add):
-        L.check(lib.mcedm_gn_bwd16(L.ptr(dy), lay[0], lay[1], L.ptr(x), lay[0], lay[1], 1, L.ptr(mr), L.ptr(gamma),
+        L.check(lib.mcedm_gn_bwd16(L.ptr(dy), lay[0], lay[1], L.ptr(x), lay[0], lay[1], 1, L.ptr(mr), L.ptr(coefab), L.ptr(gamma),
                                    L.ptr(beta), None, 128, 64, 1, 0, B, H, W, L.ptr(red), L.ptr(kcoef), L.ptr(ticket),
                                    L.ptr(dgb), None, 128, L.ptr(add0) if with_add else None, 0, lay[0], lay[1], None, 1,
                                    None, L.ptr(dx16), None, L.ptr(cs), L.stream_ptr()))

@@ -100,11 +100,11 @@ def test_gn_bwd16_matches_autograd(L, dev, fmt, add16, B, H, W, rs, act, use_ss,
     dx16 = torch.zeros(n_pos, 64, device=dev, dtype=dt)
     dxd = torch.empty(B, H, W, 64, device=dev, dtype=dt)
     cs = torch.empty(B * n_cta, 64, device=dev)
-    kcoef = torch.empty(B, 64, 4, device=dev)
+    kcoef = torch.empty(B, 192, device=dev)
     ticket = torch.zeros(B, device=dev, dtype=torch.int32)
     for _ in range(2):      # twice: the ticket counters must be back at zero after a launch
         L.check(lib.mcedm_gn_bwd16(L.ptr(dy_buf), dyl[0], dyl[1], L.ptr(x_buf), xl[0], xl[1], fmt, L.ptr(mr),
-                                   L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64, act, rs, B, H, W,
+                                   L.ptr(coef), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64, act, rs, B, H, W,
                                    L.ptr(red), L.ptr(kcoef), L.ptr(ticket), L.ptr(dgb), L.ptr(dss) if use_ss else None,
                                    128, L.ptr(add0_buf), add0_mode or 0, a0l[0], a0l[1], L.ptr(add1_buf), add16,
                                    L.ptr(dx), L.ptr(dx16), L.ptr(dxd), L.ptr(cs), L.stream_ptr()), "gn_bwd16")
@@ -158,6 +158,34 @@ def test_conv_wgrad_fp16_matches_autograd(L, dev, B, H, W, taps, dy_layout, a_la
     w = torch.zeros(64, 64, k, k, device=dev, dtype=torch.float64, requires_grad=True)
     F.conv2d(a.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(dy.double().permute(0, 3, 1, 2))
     assert rel_l2(dw, w.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,taps,dy_layout,a_layout,act", [
+    (2, 128, 128, 9, 0, 0, 1), (3, 64, 64, 9, 1, 1, 1), (5, 32, 32, 1, 0, 1, 0), (37, 32, 32, 9, 1, 1, 1)])
+def test_conv_wgrad_fused_transform_matches_autograd(L, dev, B, H, W, taps, dy_layout, a_layout, act):
+    """mcedm_conv_wgrad16_fused: the operand silu(a*x + b) is formed from the RAW activation inside the kernel."""
+    lib = L.lib()
+    g = torch.Generator().manual_seed(B * 100 + H + taps)
+    dy = torch.randn(B, H, W, 64, generator=g).to(dev).to(torch.float16).contiguous()
+    x = (torch.randn(B, H, W, 64, generator=g) * 1.5 + 0.3).to(dev).to(torch.float16).contiguous()
+    coef = torch.cat([torch.rand(B, 64, generator=g) + 0.5, torch.randn(B, 64, generator=g) * 0.5], 1).to(dev).contiguous()
+    dy_buf = to_flat(L, dy) if dy_layout else dy
+    x_buf = to_flat(L, x) if a_layout else x
+    n = lib.mcedm_wgrad_ctas(B, H, W)
+    partial = torch.full((n, taps, 64, 64), float("nan"), device=dev)
+    L.check(lib.mcedm_conv_wgrad16_fused(L.ptr(dy_buf), dy_layout, 64, 0, L.ptr(x_buf), a_layout, 64, 0, L.ptr(coef), act,
+                                         B, H, W, taps, L.ptr(partial), 1, L.stream_ptr()), "conv_wgrad16_fused")
+    L.check_watchdog()
+    k = 3 if taps == 9 else 1
+    dw = torch.zeros(64, 64, k, k, device=dev)
+    L.check(lib.mcedm_wgrad_reduce(L.ptr(partial), n, taps, L.ptr(dw), 64, 0, 1, 0, 64, 64, 0, L.stream_ptr()))
+    u = x.double() * coef[:, None, None, :64].double() + coef[:, None, None, 64:].double()
+    a = (F.silu(u) if act else u).to(torch.float16)        # the kernel rounds the operand to fp16
+    w = torch.zeros(64, 64, k, k, device=dev, dtype=torch.float64, requires_grad=True)
+    F.conv2d(a.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(dy.double().permute(0, 3, 1, 2))
+    assert rel_l2(dw, w.grad) < 5e-4            # tanh.approx (2^-11) in the SiLU
+    if a_layout:    # the raw activation itself is untouched
+        assert torch.equal(x_buf, to_flat(L, x))
 
 
 def test_attention_bwd_fp16_matches_autograd(L, dev):
