@@ -429,7 +429,7 @@ def test_cond_edm_sampler_and_training_step(dev):
     # 5 chained evaluations on adversarial weights: the trajectories stay close (not a per-step bar)
     assert rel_l2(xs, g["sample"]["xs"]) < 5e-2
     pl._noise_hook, pl._trace = None, None
-    # ---- training step (bf16 training plan; loss within 1e-2 like test_training_step_matches_reference_golden)
+    # ---- training step (fp16 "fused16" training plan; loss within 2e-3)
     pl.train()
     pl.cond_p = 1.0
     nf = NoiseFeed(g["train"]["noise_seed"])
@@ -437,11 +437,11 @@ def test_cond_edm_sampler_and_training_step(dev):
     torch.manual_seed(g["train"]["cpu_seed"])
     grid = torch.zeros(2, 128, 128, 1, device=dev)
     loss = pl.training_step((a, grid, grid, u), 0)
-    assert abs(float(loss) - float(g["train"]["loss"])) < 1e-2 * abs(float(g["train"]["loss"]))
+    assert abs(float(loss) - float(g["train"]["loss"])) < 2e-3 * abs(float(g["train"]["loss"]))
     loss.backward()
     gflat = pl.model.engine().flat_grad()
     gnorm = float(torch.sqrt((gflat.double() ** 2).sum()))
-    assert abs(gnorm - float(g["train"]["grad_norm"])) < 3e-2 * float(g["train"]["grad_norm"])
+    assert abs(gnorm - float(g["train"]["grad_norm"])) < 5e-3 * float(g["train"]["grad_norm"])
 
 
 def test_get_denoised_within_bf16_bar(dev):
@@ -457,14 +457,15 @@ def test_get_denoised_within_bf16_bar(dev):
                                    cond=case["cond"].to(dev), w=0.0)
         assert rel_l2(d, case["D"]) < BF16_TOL and rel_l2(f, case["F"]) < BF16_TOL
         assert rel_l2(f, case["F"]) < 3e-3, "the fp16 inference plan is expected well inside the bar"
-    # the same call in train mode with autograd on goes through the TRAINING forward (bf16 operands: gradients need
-    # the range), which measures 1.0e-2 on these adversarial weights, i.e. AT the bar; pin it loosely so a regression
-    # in the training forward is still caught here
+    # the same call in train mode with autograd on goes through the TRAINING forward: the "fused16" plan runs the
+    # inference data flow in fp16 (train16_engine.py), so it sits in the same 1.4e-3 class, far inside the 1e-2 bar
+    # (the bf16 fp32-stream plan of round 1 measured 1.0e-2 here, AT the bar)
     pl.train()
-    case = g["cases"][1]
-    d, f = pl.get_denoised(pl.ema_model, case["xt"].to(dev), torch.tensor(case["sigma"], dtype=torch.float64),
-                           cond=case["cond"].to(dev), w=0.0)
-    assert rel_l2(f.detach(), case["F"]) < 1.2e-2
+    assert pl.ema_model.ma_model.engine().train_plan == "fused16"
+    for case in g["cases"]:
+        d, f = pl.get_denoised(pl.ema_model, case["xt"].to(dev), torch.tensor(case["sigma"], dtype=torch.float64),
+                               cond=case["cond"].to(dev), w=0.0)
+        assert rel_l2(f.detach(), case["F"]) < 3e-3 and rel_l2(d.detach(), case["D"]) < 3e-3
 
 
 def test_sample_edm_trajectory_parity_with_injected_noise(dev):

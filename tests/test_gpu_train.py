@@ -330,7 +330,9 @@ def _train_batch(g, dev):
 
 def test_training_step_matches_reference_golden(dev):
     """loss, a sample of parameter gradients and the global gradient norm of ONE training step against the fixture
-    produced by the unmodified reference (tests/golden/make_golden.py G4): bf16 tensor-core operands, fp32 accumulate."""
+    produced by the unmodified reference (tests/golden/make_golden.py G4).  Training plan "fused16": fp16 tensor-core
+    operands and activations forward and backward (loss-scaled), fp32 accumulation: every sampled gradient within 5e-3
+    (measured <= 2.8e-3; the bf16 fp32-stream plan of round 1 needed 4e-2)."""
     from common import NoiseFeed, golden, stress_module
 
     g = golden("train_step.pt")
@@ -343,20 +345,21 @@ def test_training_step_matches_reference_golden(dev):
     loss.backward()
     from mcedm_b200 import _lib
     _lib.check_watchdog()
-    assert abs(float(loss) - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+    assert abs(float(loss) - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))
     named = dict(pl.model.named_parameters())
     errs = {k: rel_l2(named[k].grad, v) for k, v in g["grads"].items()}
     print({k: f"{e:.2e}" for k, e in errs.items()})
-    assert max(errs.values()) < 4e-2, errs
+    assert max(errs.values()) < 5e-3, errs
     gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in pl.model.parameters()))
-    assert abs(float(gn) - float(g["grad_norm"])) < 2e-2 * float(g["grad_norm"])
+    assert abs(float(gn) - float(g["grad_norm"])) < 5e-3 * float(g["grad_norm"])
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pl.model.parameters())
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_every_parameter_gradient_matches_oracle_autograd(dev, graph):
+@pytest.mark.parametrize("graph,plan", [(False, "fused16"), (True, "fused16"), (False, "fp32")])
+def test_every_parameter_gradient_matches_oracle_autograd(dev, graph, plan):
     """All 196 parameter gradients against fp32 autograd through the CPU oracle on the same inputs, through the
-    eager autograd bridge and through the CUDA-graph replay (twice: the replay must re-read its static inputs)."""
+    eager autograd bridge and through the CUDA-graph replay (twice: the replay must re-read its static inputs), for
+    the default fp16 "fused16" training plan and for the bf16 fp32-stream plan (kept for other field widths)."""
     from common import NoiseFeed, golden, stress_module
     from oracle import edm_oracle as O
 
@@ -366,6 +369,8 @@ def test_every_parameter_gradient_matches_oracle_autograd(dev, graph):
           for k, v in pl.model.state_dict().items()}
     pl = pl.to(dev).train()
     pl.use_cuda_graph = graph
+    pl.model.engine().train_plan = plan
+    tol = dict(fused16=(2e-3, 4e-3, 6e-3), fp32=(1e-2, 2e-2, 6e-2))[plan]      # loss, global gradient, worst tensor
     h, _, _, u, mask = _train_batch(g, dev)
     x = torch.cat([h, u], -1).permute(0, 3, 1, 2).contiguous()
     mask_c = mask.permute(0, 3, 1, 2).contiguous()
@@ -380,7 +385,7 @@ def test_every_parameter_gradient_matches_oracle_autograd(dev, graph):
     loss.backward()
     ref, _ = O.training_loss(sd, dict(cfg.model.hparams.model), x.cpu(), sigma.cpu(), noise.cpu(), cond.cpu(), mask_c.cpu())
     ref.backward()
-    assert abs(float(loss) - float(ref)) < 1e-2 * abs(float(ref))
+    assert abs(float(loss) - float(ref)) < tol[0] * abs(float(ref))
     worst, flat_a, flat_b = [], [], []
     for k, p in pl.model.named_parameters():
         e = rel_l2(p.grad, sd[k].grad)
@@ -389,8 +394,10 @@ def test_every_parameter_gradient_matches_oracle_autograd(dev, graph):
         flat_b.append(sd[k].grad.flatten())
     worst.sort(reverse=True)
     print([(f"{e:.2e}", k) for e, k in worst[:8]])
-    assert rel_l2(torch.cat(flat_a), torch.cat(flat_b)) < 2e-2
-    assert worst[0][0] < 6e-2, worst[:5]
+    gl = rel_l2(torch.cat(flat_a), torch.cat(flat_b))
+    print(f"global gradient error {gl:.2e}")
+    assert gl < tol[1]                     # north_star bar 1e-2
+    assert worst[0][0] < tol[2], worst[:5]
 
 
 def test_fused_optimizer_step_and_ema_inside_trainer_loop(dev):
