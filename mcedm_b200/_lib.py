@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmcedm_b200.so")
+# MCEDM_LIB: an alternative build of the same library (A/B measurements of build-time knobs, scripts/build_alt.py)
+LIB_PATH = os.environ.get("MCEDM_LIB") or os.path.join(_HERE, "lib", "libmcedm_b200.so")
 
 _vp = C.c_void_p
 _i = C.c_int

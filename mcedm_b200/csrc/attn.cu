@@ -83,6 +83,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   float* xch_m = reinterpret_cast<float*>(ones_smem + 2048 + 256);         // [KS][128 rows] partial row maxima
   float* xch_l = xch_m + 128 * KS;                                         // [KS][128 rows] partial row sums
 
+  pdl_wait();       // (the flag words written below are read by the previous call's fallback launch)
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = L / 128;
   const int p2_start = SINGLE ? 0 : nblk;      // first iteration of the exponentiating pass
@@ -477,26 +479,26 @@ extern "C" int mcedm_attention(const void* qkv_bf16, int B, int L, void* out_bf1
     unsigned int* flags = attn_flags(grid);
     MCEDM_REQUIRE(flags != nullptr, "attention: cannot allocate the overflow flags");
     if (op_fmt && !no_h2 && ks4)
-      attn_kernel<true, true, 4><<<grid, 576, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1,
-                                                          err, flags, (int)grid);
+      MCEDM_CUDA(launch_pdl(attn_kernel<true, true, 4>, dim3(grid), dim3(576), (size_t)smem, st, tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1,
+                                                          err, flags, (int)grid));
     else if (op_fmt && !no_h2 && lmma)
-      attn_kernel<true, true, 2, true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
-                                                                1, err, flags, (int)grid);
+      MCEDM_CUDA(launch_pdl(attn_kernel<true, true, 2, true>, dim3(grid), dim3(320), (size_t)smem, st, tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
+                                                                1, err, flags, (int)grid));
     else if (op_fmt && !no_h2)
-      attn_kernel<true, true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1, err,
-                                                       flags, (int)grid);
+      MCEDM_CUDA(launch_pdl(attn_kernel<true, true>, dim3(grid), dim3(320), (size_t)smem, st, tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr, 1, err,
+                                                       flags, (int)grid));
     else
-      attn_kernel<true><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
-                                                 op_fmt ? 1 : 0, err, flags, (int)grid);
+      MCEDM_CUDA(launch_pdl(attn_kernel<true>, dim3(grid), dim3(320), (size_t)smem, st, tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
+                                                 op_fmt ? 1 : 0, err, flags, (int)grid));
     MCEDM_CUDA(cudaGetLastError());
     const unsigned fb_grid = grid < (unsigned)num_sms() ? grid : (unsigned)num_sms();
-    attn_kernel<false><<<fb_grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
-                                                   op_fmt ? 1 : 0, err, flags, (int)grid);
+    MCEDM_CUDA(launch_pdl(attn_kernel<false>, dim3(fb_grid), dim3(320), (size_t)smem, st, tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), nullptr,
+                                                   op_fmt ? 1 : 0, err, flags, (int)grid));
     MCEDM_CUDA(cudaGetLastError());
     return 0;
   }
-  attn_kernel<false><<<grid, 320, smem, st>>>(tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0,
-                                              err, nullptr, (int)grid);
+  MCEDM_CUDA(launch_pdl(attn_kernel<false>, dim3(grid), dim3(320), (size_t)smem, st, tm, L, reinterpret_cast<__nv_bfloat16*>(out_bf16), lse_out, op_fmt ? 1 : 0,
+                                              err, nullptr, (int)grid));
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

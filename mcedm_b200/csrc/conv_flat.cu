@@ -39,6 +39,13 @@
 #define MCEDM_XF_H2 0   // GroupNorm+SiLU transform in packed half arithmetic (see conv_rows.cu: +2 % speed, 2.5x the error: off)
 #endif
 
+#ifndef MCEDM_FLAT_WG
+#define MCEDM_FLAT_WG 1
+#endif
+#ifndef MCEDM_FLAT_LDG
+#define MCEDM_FLAT_LDG 1   // fused + transform: the transform warps fetch the raw chunk from global memory themselves
+#endif
+
 namespace mcedm {
 
 constexpr int kChunkBytes = 16 * 1024;
@@ -61,6 +68,7 @@ struct FlatParams {
   int res_f32;             // res (mode 1 only) is fp32 padded-flat
   int res_pitch, res_blk;  // layout of the 16-bit residual tensor at ITS resolution: 0,0 dense NHWC, else padded-flat
   int dbg;                 // bring-up switches (MCEDM_DBG): 1 = fp32 transform arithmetic
+  const void* src;         // the padded-flat source itself (the transform warps' direct loads, MCEDM_FLAT_LDG)
 };
 
 template <int N, bool FUSED>
@@ -70,10 +78,19 @@ struct FlatCfg {
   static constexpr int U = 8;
   static constexpr int W_SEG_BYTES = N * 128;
   static constexpr int EPI_WARPS = 4 * NCH;
-  static constexpr int XF_WARPS = FUSED ? 4 : 0;
   static constexpr bool DUAL = FUSED && MCEDM_DUAL;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
-  static constexpr int MMA2_WARP = DUAL ? THREADS / 32 - 1 : -1;
+  // WG (fused): roles laid out on warpgroup boundaries so that setmaxnreg can move registers between them:
+  //   warps 0-3 TMA | MMA | MMA 2 | idle,  warps 4-11 epilogue,  warps 12-19 transform (EIGHT warps: with both MMA warps
+  //   issuing, the four transform warps were this kernel's pacer).  640 threads launch at 96 registers; the transform
+  //   groups drop to 72, the first group to 80, and the two epilogue groups take 128 (what they needed at 480 threads).
+  //   setmaxnreg only moves registers INSIDE the CTA's launch allocation: 4 x 32 x 16 + 8 x 32 x 24 released = 8 x 32 x 32
+  //   acquired, exactly (an inc that outruns the decs never returns).
+  static constexpr bool WG = FUSED && DUAL && MCEDM_FLAT_WG;
+  static constexpr int XF_WARPS = FUSED ? (WG ? 8 : 4) : 0;
+  static constexpr int THREADS = WG ? 640 : 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
+  static constexpr int MMA2_WARP = WG ? 2 : (DUAL ? THREADS / 32 - 1 : -1);
+  static constexpr int EPI_W0 = WG ? 4 : 2;
+  static constexpr int XF_W0 = WG ? 12 : 2 + EPI_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;   // (the 16-bit fast-path epilogue uses half of it)
   static constexpr int ACC_BUFS = 4;
   static constexpr int TMEM_COLS = (ACC_BUFS * N <= 256) ? 256 : 512;
@@ -181,6 +198,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
   const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
   const int n_tiles = (int)(t_end - t_begin);
+  // LDG mode: no TMA for the activation chunks.  The kernel is bounded by shared-memory traffic (operand fetch of the MMAs
+  // + everything the warps move); TMA write + transform read + transform write cost 48 KB per chunk, a direct global load
+  // into registers followed by ONE swizzled store costs 16.
+  const bool xf_ldg = Cfg::WG && MCEDM_FLAT_LDG && FUSED && p.coef != nullptr && !(p.dbg & 16);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_w);
@@ -198,6 +219,9 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     mbar_init(&turn[0], 1);
     mbar_init(&turn[1], 1);
     fence_barrier_init();
+    // weights before pdl_wait (not written by the preceding kernel): the prologue overlaps the previous kernel's tail
+    mbar_expect_tx(w_full, (uint32_t)(9 * Cfg::W_SEG_BYTES));
+    for (int s = 0; s < 9; ++s) tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * N);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -207,14 +231,16 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
+  // (WG: every role branch starts with its warpgroup's setmaxnreg, so that ptxas budgets the branch accordingly)
   if (warp == 0) {
+    if constexpr (Cfg::WG) setmaxnreg_dec<80>();
     // ===================================== TMA producer =====================================
     // local chunk k (0 .. n_tiles+1) = global chunk t_begin - 1 + k; tile j uses chunks j, j+1, j+2
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(9 * Cfg::W_SEG_BYTES));
-      for (int s = 0; s < 9; ++s) tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * N);
-      for (int k = 0; k < n_tiles + 2; ++k) {
+      for (int k = 0; k < (xf_ldg ? 0 : n_tiles + 2); ++k) {
         const uint32_t slot = (uint32_t)k % (uint32_t)S, ph = ((uint32_t)k / (uint32_t)S) & 1u;
         mbar_wait(&c_empty[slot], ph ^ 1u, p.err, 0x3100 + slot);
         const bool mirror = slot < 2 && k >= S;
@@ -225,6 +251,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
     }
   } else if (warp == 1 || warp == Cfg::MMA2_WARP) {
+    if constexpr (Cfg::WG) setmaxnreg_dec<80>();
     // ====================================== MMA issuer ======================================
     // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
     // DUAL (fused kernel): two warps take alternate tiles.  Tiles own separate accumulators, but the chunk ring is
@@ -300,10 +327,11 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         slot = s1;
       }
     }
-  } else if (!FUSED || warp < 2 + Cfg::EPI_WARPS) {
+  } else if (!FUSED || (warp >= Cfg::EPI_W0 && warp < Cfg::EPI_W0 + Cfg::EPI_WARPS)) {
     // ======================================= epilogue =======================================
+    if constexpr (Cfg::WG) setmaxnreg_inc<120>();
     const int q = warp & 3;
-    const int ew = warp - 2;
+    const int ew = warp - Cfg::EPI_W0;
     const int ch = ew >> 2;
     const uint32_t my_stage = smem_u32(stage_smem) + ew * (32 * Cfg::CH * 4);
     const int unit = lane & 7;
@@ -533,20 +561,58 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       __syncwarp();
     }
     }
-  } else if (warp < 2 + Cfg::EPI_WARPS + Cfg::XF_WARPS) {
+  } else if (warp >= Cfg::XF_W0 && warp < Cfg::XF_W0 + Cfg::XF_WARPS) {
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk jc = t & 7 (channels 8jc .. 8jc+7) of positions (t >> 3) + 16 i of every
     // 128-position chunk; physical 16-byte slot = jc ^ (position & 7) (SWIZZLE_128B, 1 KB-aligned chunk slots).
-    const int t = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    if constexpr (Cfg::WG) setmaxnreg_dec<80>();
+    const int t = (int)threadIdx.x - 32 * Cfg::XF_W0;
     const int jc = t & 7;
     const int prow = t >> 3;
+    constexpr int XF_ROWS = FUSED ? 4 * Cfg::XF_WARPS : 16;   // positions covered per pass
+    constexpr int XF_IT = 128 / XF_ROWS;
     int cur_b = -1;
     float ca[8], cb[8];
     uint32_t ca2[4], cb2[4];
+    // LDG mode: chunk k+1 is in flight in registers while chunk k is transformed (a chunk period is ~1.3 us)
+    const uint4* srcp = reinterpret_cast<const uint4*>(p.src);
+    uint4 n0[XF_IT];
+    auto ldg_chunk = [&](int k, uint4 (&dst)[XF_IT]) {
+      const long long g = t_begin - 1 + k;
+      if (k < n_tiles + 2 && g >= 0 && g < p.total_tiles) {
+        const uint4* a = srcp + (g * 128 + prow) * 8 + jc;
+#pragma unroll
+        for (int i = 0; i < XF_IT; ++i) dst[i] = ldg128_stream(a + (long long)i * XF_ROWS * 8);
+      } else {
+#pragma unroll
+        for (int i = 0; i < XF_IT; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (xf_ldg) ldg_chunk(0, n0);
     for (int k = 0; k < n_tiles + 2; ++k) {
       const uint32_t slot = (uint32_t)k % (uint32_t)S, ph = ((uint32_t)k / (uint32_t)S) & 1u;
-      mbar_wait(&c_full[slot], ph, p.err, 0x3600 + slot);
-      const long long g = t_begin - 1 + k;                 // global chunk; outside the tensor = TMA zero fill
+      uint4 v[XF_IT];
+      if (xf_ldg) {
+#pragma unroll
+        for (int i = 0; i < XF_IT; ++i) v[i] = n0[i];
+        ldg_chunk(k + 1, n0);
+        mbar_wait(&c_empty[slot], ph ^ 1u, p.err, 0x3100 + slot);     // the slot's previous chunk has no reader left
+      } else {
+        mbar_wait(&c_full[slot], ph, p.err, 0x3600 + slot);
+      }
+      const long long g = t_begin - 1 + k;                 // global chunk; outside the tensor = zero fill
+      if (xf_ldg && !(g >= 0 && g < p.total_tiles)) {
+        const uint32_t base = smem_u32(ring) + slot * kChunkBytes;
+        const bool mirror = slot < 2 && k >= S;
+#pragma unroll
+        for (int i = 0; i < XF_IT; ++i) {
+          const int pi = prow + XF_ROWS * i;
+          const int off = pi * 128 + ((jc ^ (pi & 7)) << 4);
+          sts128(base + off, make_uint4(0u, 0u, 0u, 0u));
+          if (mirror) sts128(base + S * kChunkBytes + off, make_uint4(0u, 0u, 0u, 0u));
+        }
+        fence_proxy_async_smem();
+      }
       if (g >= 0 && g < p.total_tiles && p.coef != nullptr) {
         const int b = (int)(g / p.tiles_per_img);
         const int base_pos = (int)(g - (long long)b * p.tiles_per_img) * 128;
@@ -569,26 +635,25 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
         const uint32_t base = smem_u32(ring) + slot * kChunkBytes;
         const bool mirror = slot < 2 && k >= S;
-        uint4 v[8];
-        bool ok[8];
-        // (row, column) of this thread's first position; the next ones are 16 positions apart (P >= 17 > 16: at most
-        // one row wrap per step), so one division per chunk instead of eight
+        bool ok[XF_IT];
+        // (row, column) of this thread's first position; the next ones are XF_ROWS positions apart: one division per
+        // chunk instead of one per position
         int row = (base_pos + prow) / p.P;
         int x = (base_pos + prow) - row * p.P;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pi = prow + 16 * i;
+        for (int i = 0; i < XF_IT; ++i) {
+          const int pi = prow + XF_ROWS * i;
           ok[i] = (row >= 1) && (row <= p.H) && (x < p.W);
-          v[i] = lds128(base + pi * 128 + ((jc ^ (pi & 7)) << 4));
-          x += 16;
-          if (x >= p.P) {
+          if (!xf_ldg) v[i] = lds128(base + pi * 128 + ((jc ^ (pi & 7)) << 4));
+          x += XF_ROWS;
+          while (x >= p.P) {
             x -= p.P;
             ++row;
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int pi = prow + 16 * i;
+        for (int i = 0; i < XF_IT; ++i) {
+          const int pi = prow + XF_ROWS * i;
           // branch-free (lanes of a warp sit on different positions): padding positions hold zeros and get them back
           uint4 o;
           if (MCEDM_XF_H2 && fmt == 1 && !(p.dbg & 1)) {        // MCEDM_DBG=1: fp32 transform (A/B switch)
@@ -611,6 +676,8 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
       mbar_arrive_warp(&c_ready[slot]);
     }
+  } else {
+    if constexpr (Cfg::WG) setmaxnreg_dec<80>();    // the idle fourth warp of the first group
   }
 
   tc_fence_before();
@@ -638,6 +705,7 @@ static int launch_flat(FlatParams p, const void* src_flat, const void* w_packed,
   using Cfg = FlatCfg<64, FUSED>;
   const int N = 64;
   p.err = watchdog_ptr();
+  p.src = src_flat;
   MCEDM_REQUIRE(p.err != nullptr, "conv_flat: cannot allocate the watchdog word");
   MCEDM_REQUIRE((long long)B * blk < (1LL << 31), "conv_flat: tensor too large for 32-bit TMA coordinates");
   const int fixed = 1024 + 9 * Cfg::W_SEG_BYTES + Cfg::STAGE_BYTES + 768;
@@ -657,8 +725,7 @@ static int launch_flat(FlatParams p, const void* src_flat, const void* w_packed,
     attr_set = true;
   }
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_flat_kernel<64, FUSED, FM><<<(unsigned)grid, Cfg::THREADS, smem, st>>>(tm_w, tm_a, p);
-  MCEDM_CUDA(cudaGetLastError());
+  MCEDM_CUDA(launch_pdl(conv_flat_kernel<64, FUSED, FM>, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)smem, st, tm_w, tm_a, p));
   return 0;
 }
 }  // namespace mcedm

@@ -113,6 +113,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
       mbar_init(&a_empty[i], 1);
     }
     fence_barrier_init();
+    // weights before pdl_wait (not written by the preceding kernel): the prologue overlaps the previous kernel's tail
+    mbar_expect_tx(w_full, (uint32_t)(p.n_seg * Cfg::W_SEG_BYTES));
+    for (int s = 0; s < p.n_seg; ++s) tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * N);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -122,13 +125,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       const CUtensorMap* maps[4] = {&tm_a0, &tm_a1, &tm_a2, &tm_a3};
-      mbar_expect_tx(w_full, (uint32_t)(p.n_seg * Cfg::W_SEG_BYTES));
-      for (int s = 0; s < p.n_seg; ++s) tma_load_2d(w_smem + s * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * N);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_img;
@@ -187,23 +190,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
     const int unit = lane % Cfg::U;
     const int row_in_it = lane / Cfg::U;
     constexpr int ROWS_PER_IT = 32 / Cfg::U;
-    const int HW = p.H * p.W;
+    const int wshift = __ffs(p.W) - 1;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1u;
       const uint32_t aph = (tcount >> 1) & 1u;
       const long long pix0 = (long long)tile * kTileM + q * 32;
+      // A tile never straddles images (tiles_per_img = H*W / 128) and W is a power of two (it divides 128): one 32-bit
+      // division per tile, shifts per row.  (64-bit divisions per row made this epilogue the pacer of the 1x1 convs:
+      // ~3000 issue cycles per tile.)
+      const int img = tile / p.tiles_per_img;
+      const int rem0 = (tile - img * p.tiles_per_img) * kTileM + q * 32;
       // output / residual pixel index of this lane's rows (dense, or padded-flat for the 16-bit I/O variant)
       long long opix[Cfg::U];
 #pragma unroll
       for (int itr = 0; itr < Cfg::U; ++itr) {
-        const long long pix = pix0 + itr * ROWS_PER_IT + row_in_it;
-        opix[itr] = pix;
+        const int rem = rem0 + itr * ROWS_PER_IT + row_in_it;
+        opix[itr] = pix0 + itr * ROWS_PER_IT + row_in_it;
         if (p.io_pitch > 0) {
-          const int b = (int)(pix / HW);
-          const int rem = (int)(pix - (long long)b * HW);
-          const int y = rem / p.W;
-          opix[itr] = (long long)b * p.io_blk + (long long)(y + 1) * p.io_pitch + (rem - y * p.W);
+          const int y = rem >> wshift;
+          opix[itr] = (long long)img * p.io_blk + (long long)(y + 1) * p.io_pitch + (rem & (p.W - 1));
         }
       }
       // 16-bit residual prefetch (independent of the accumulator); N <= 64 only
@@ -267,9 +273,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constan
               a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
             }
           } else if (p.res_mode != 0) {
-            const int b = (int)(pix / HW);
-            const int rem = (int)(pix - (long long)b * HW);
-            const int y = rem / p.W, x = rem - y * p.W;
+            const int b = img;
+            const int rem = rem0 + row;
+            const int y = rem >> wshift, x = rem & (p.W - 1);
             if (p.res_mode == 2) {
               const int Hs = p.H >> 1, Ws = p.W >> 1;
               const float4 r = *reinterpret_cast<const float4*>(
@@ -351,8 +357,8 @@ static int launch_conv(const CUtensorMap& tm_w, const CUtensorMap* tm_a, const C
     attr_smem = 232448;
   }
   int grid = q.n_tiles < num_sms() ? q.n_tiles : num_sms();
-  conv_igemm_kernel<N><<<grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_a[0], tm_a[1], tm_a[2], tm_a[3], q);
-  MCEDM_CUDA(cudaGetLastError());
+  MCEDM_CUDA(launch_pdl(conv_igemm_kernel<N>, dim3(grid), dim3(Cfg::THREADS), (size_t)smem, stream, tm_w, tm_a[0], tm_a[1], tm_a[2],
+                        tm_a[3], q));
   return 0;
 }
 

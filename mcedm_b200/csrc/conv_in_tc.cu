@@ -51,6 +51,8 @@ conv_in_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const InTcParams p) 
   uint64_t* a_empty = a_ready + kInSlots;  // kInSlots
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kInSlots);
 
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r_begin = p.total_rows * blockIdx.x / gridDim.x;
   const long long r_end = p.total_rows * (blockIdx.x + 1) / gridDim.x;
@@ -278,7 +280,7 @@ extern "C" int mcedm_conv_in_tc16(const float* x, int Cx, const float* cond, int
 #define MCEDM_IN_TC_CASE(C)                                                                                          \
   case C:                                                                                                            \
     MCEDM_CUDA(cudaFuncSetAttribute(conv_in_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
-    conv_in_tc_kernel<C><<<(unsigned)grid, kInThreads, smem, st>>>(tm_w, p);                                         \
+    MCEDM_CUDA(launch_pdl(conv_in_tc_kernel<C>, dim3((unsigned)grid), dim3(kInThreads), (size_t)smem, st, tm_w, p)); \
     break;
   switch (Cx + Cc) {
     MCEDM_IN_TC_CASE(1) MCEDM_IN_TC_CASE(2) MCEDM_IN_TC_CASE(3) MCEDM_IN_TC_CASE(4) MCEDM_IN_TC_CASE(5)

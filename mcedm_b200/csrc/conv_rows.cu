@@ -150,7 +150,7 @@ __device__ __forceinline__ uint32_t xf_pair(uint32_t v, float a0, float b0, floa
 }
 
 // RM: residual mode folded at compile time (fused N = 64 instantiations; -1 = runtime p.res_mode)
-template <int N, bool FUSED, int RM = -1>
+template <int N, bool FUSED, int RM = -1, int EP = 0>
 __global__ void __launch_bounds__(RowsCfg<N, FUSED>::THREADS, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_h0,
                  const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_c0,
@@ -211,6 +211,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     mbar_init(&turn[0], 1);
     mbar_init(&turn[1], 1);
     fence_barrier_init();
+    // the packed weights are not written by the preceding kernel: their load is issued BEFORE pdl_wait, so under a
+    // programmatic dependent launch it (and the whole prologue) overlaps the previous kernel's tail
+    mbar_expect_tx(w_full, (uint32_t)(n_seg * Cfg::W_SEG_BYTES));
+    for (int s = 0; s < n_seg; ++s) {
+      // STACK keeps the taps of one filter column contiguous: slot (kx*3 + ky) holds tap (ky, kx)
+      const int slot = (Cfg::STACK && s < 9) ? (s % 3) * 3 + s / 3 : s;
+      tma_load_2d(w_smem + slot * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * p.w_rows + p.n_off);
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -220,16 +228,12 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(n_seg * Cfg::W_SEG_BYTES));
-      for (int s = 0; s < n_seg; ++s) {
-        // STACK keeps the taps of one filter column contiguous: slot (kx*3 + ky) holds tap (ky, kx)
-        const int slot = (Cfg::STACK && s < 9) ? (s % 3) * 3 + s / 3 : s;
-        tma_load_2d(w_smem + slot * Cfg::W_SEG_BYTES, &tm_w, w_full, 0, s * p.w_rows + p.n_off);
-      }
       uint32_t hl = 0, cl = 0;   // halo rows / centre tiles loaded so far
       long long dbg_w0 = 0;
       const long long dbg_t0 = clock64();
@@ -590,7 +594,129 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int q = warp & 3;                 // TMEM lane quarter
     const int ew = warp - 2;                // 0 .. EPI_WARPS-1
     const int ch = ew >> 2;                 // column chunk drained by this warp
-    if constexpr (Cfg::EPI_H16) {
+    if constexpr (Cfg::EPI_H16 && EP == 1) {
+      // ---------------------------------------------------------------------------------------------------------
+      // Register-direct epilogue (no staging tile).  tcgen05.ld 32x32b hands every thread ONE pixel and 32 consecutive
+      // channels = 64 contiguous bytes of the NHWC output row: bias and residual (two 256-bit loads, requested one tile
+      // ahead) are added in fp32, the result is rounded once and leaves as two 256-bit stores (full 32-byte sectors).
+      // Nothing of the epilogue touches shared memory any more (the 16-bit staging tile cost 16 KB written + 16 KB read
+      // per row of a kernel that is bounded by shared-memory bytes, plus two warp barriers per tile).  GroupNorm sums:
+      // a thread keeps (sum, sum of squares) of its pixel's 8 four-channel groups across the 4 rows of a block, then
+      // ONE transposing butterfly (8+4+2+1+1 shuffles for the 16 values) leaves value i on lanes 2i, 2i+1 - exactly
+      // the order of the record, which 16 lanes write as one 64-byte row.
+      // ---------------------------------------------------------------------------------------------------------
+      const int NT = p.n_total;
+      const int cg = p.n_off + ch * 32;              // first of this thread's 32 channels inside the out / res rows
+      const uint16_t* res16 = reinterpret_cast<const uint16_t*>(p.res);
+      uint16_t* out16p = reinterpret_cast<uint16_t*>(p.out);
+      // bias of the 32 channels: broadcast reads from a 256-byte table in the (otherwise unused) staging area
+      const uint32_t bias_s = smem_u32(stage_smem) + ew * 2048;
+      if (lane < 8) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + cg) + lane);
+        sts128(bias_s + lane * 16, make_uint4(__float_as_uint(bv.x), __float_as_uint(bv.y), __float_as_uint(bv.z),
+                                              __float_as_uint(bv.w)));
+      }
+      __syncwarp();
+      uint32_t rn[16];                               // residual of the NEXT tile (requested one tile ahead)
+      auto load_res = [&](long long r) {
+        if (res_mode == 1) {
+          const uint16_t* a = res16 + (r * 128 + q * 32 + lane) * NT + cg;
+          ldg256(a, rn);
+          ldg256(a + 16, rn + 8);
+        } else if (res_mode == 2) {
+          const int bimg = (int)(r / p.H);
+          const int y = (int)(r - (long long)bimg * p.H);
+          const long long rrow = (p.res_pitch > 0)
+                                     ? ((long long)bimg * p.res_blk + (long long)((y >> 1) + 1) * p.res_pitch) * NT + cg
+                                     : ((long long)bimg * (p.H >> 1) + (y >> 1)) * 64 * NT + cg;
+          const uint16_t* a = res16 + rrow + ((q * 32 + lane) >> 1) * NT;
+          ldg256(a, rn);
+          ldg256(a + 16, rn + 8);
+        }
+      };
+      if (r_begin < r_end) load_res(r_begin);
+      float gs[16];                                  // gs[2g] = sum, gs[2g+1] = sum of squares of group g (4 channels)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+      long long dbg_w3 = 0;
+      const long long dbg_t0 = clock64();
+      uint32_t tcount = 0;
+      for (long long r = r_begin; r < r_end; ++r, ++tcount) {
+        const uint32_t buf = tcount % Cfg::ACC_BUFS, aph = (tcount / Cfg::ACC_BUFS) & 1u;
+        uint32_t rh[16];
+        if (res_mode != 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rh[i] = rn[i];
+          if (r + 1 < r_end) load_res(r + 1);
+        }
+        timed_wait(&acc_full[buf], aph, p.err, 0x2700 + buf, dbg_w3, (p.dbg & 32) != 0);
+        tc_fence_after();
+        uint32_t v[32];
+        const uint32_t acc_col = ((8u - buf) & 7u) * (uint32_t)N;          // STACK: descending tile order
+        tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + ch * 32, v);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive_warp(&acc_empty[buf]);
+        if (p.dbg & 2) continue;                  // bring-up: drain-only epilogue
+        uint32_t o[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {             // group c: channels 4c .. 4c+3
+          const float4 bz = lds128f(bias_s + c * 16);
+          float a0 = __uint_as_float(v[4 * c + 0]) + bz.x, a1 = __uint_as_float(v[4 * c + 1]) + bz.y;
+          float a2 = __uint_as_float(v[4 * c + 2]) + bz.z, a3 = __uint_as_float(v[4 * c + 3]) + bz.w;
+          if (res_mode != 0) {
+            const float2 r0 = unpack_f16x2(rh[2 * c]), r1 = unpack_f16x2(rh[2 * c + 1]);
+            a0 += r0.x; a1 += r0.y; a2 += r1.x; a3 += r1.y;
+          }
+          gs[2 * c] += (a0 + a1) + (a2 + a3);
+          gs[2 * c + 1] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          if (p.dbg & 4) {
+            const float aa[4] = {a0, a1, a2, a3};
+            sat_audit(p.err, aa);
+          }
+          o[2 * c] = pack_f16x2(a0, a1);
+          o[2 * c + 1] = pack_f16x2(a2, a3);
+        }
+        uint16_t* dst = out16p + (r * 128 + q * 32 + lane) * NT + cg;
+        stg256(dst, o);
+        stg256(dst + 16, o + 8);
+        if ((r & 3) == 3) {
+          // end of a 4-row block (ranges are block-aligned and H % 4 == 0, so blocks never straddle images or CTAs)
+          if (p.stats) {
+            float b8[8], c4[4], d2[2], e1;
+            const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float mine = h16 ? gs[8 + k] : gs[k], theirs = h16 ? gs[k] : gs[8 + k];
+              b8[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float mine = h8 ? b8[4 + k] : b8[k], theirs = h8 ? b8[k] : b8[4 + k];
+              c4[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float mine = h4 ? c4[2 + k] : c4[k], theirs = h4 ? c4[k] : c4[2 + k];
+              d2[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, 4);
+            }
+            {
+              const float mine = h2 ? d2[1] : d2[0], theirs = h2 ? d2[0] : d2[1];
+              e1 = mine + __shfl_xor_sync(0xffffffffu, theirs, 2);
+            }
+            e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+            if (!(lane & 1)) p.stats[(((r >> 2) * 4 + q) * (NT / 4) + (cg >> 2)) * 2 + (lane >> 1)] = e1;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gs[i] = 0.f;
+        }
+      }
+      if ((p.dbg & 32) && warp == 2 && lane == 0) {
+        g_rows_dbg[blockIdx.x][3] = dbg_w3;
+        g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
+      }
+    } else if constexpr (Cfg::EPI_H16) {
       // ---------------------------------------------------------------------------------------------------------
       // 16-bit staging.  The kernel is bounded by shared-memory BYTES per row (MMA operand fetch 120 KB + TMA 17 KB +
       // transform 32 KB + epilogue staging; scripts/rows_ablate.py: 9.7 cycles per KB), and the fp32 staging tile
@@ -942,7 +1068,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   }
 }
 
-template <int N, bool FUSED, int RM = -1>
+template <int N, bool FUSED, int RM = -1, int EP = 0>
 static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const CUtensorMap* tm_c, RowsParams p,
                        cudaStream_t stream) {
   using Cfg = RowsCfg<N, FUSED>;
@@ -974,13 +1100,13 @@ static int launch_rows(const CUtensorMap& tm_w, const CUtensorMap* tm_h, const C
   const int smem = fixed + slots * slot_bytes + p.n_cslots * kCtrBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MCEDM_CUDA(cudaFuncSetAttribute(conv_rows_kernel<N, FUSED, RM, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   const long long units = p.total_rows / p.row_align;
   long long grid = units < num_sms() ? units : num_sms();
-  conv_rows_kernel<N, FUSED, RM><<<(unsigned)grid, Cfg::THREADS, smem, stream>>>(tm_w, tm_h[0], tm_h[1], tm_c[0], tm_c[1], p);
-  MCEDM_CUDA(cudaGetLastError());
+  MCEDM_CUDA(launch_pdl(conv_rows_kernel<N, FUSED, RM, EP>, dim3((unsigned)grid), dim3(Cfg::THREADS), (size_t)smem, stream, tm_w,
+                        tm_h[0], tm_h[1], tm_c[0], tm_c[1], p));
   return 0;
 }
 
@@ -1078,6 +1204,11 @@ extern "C" int mcedm_conv_rows_fused(const void* const* halo_src, const float* c
     case 16: return launch_rows<16, true>(tm_w, tm_h, tm_c, p, st);
     case 32: return launch_rows<32, true>(tm_w, tm_h, tm_c, p, st);
     case 64:
+      if ((p.dbg & 128) && !MCEDM_EPI16) {       // MCEDM_DBG=128: register-direct epilogue (A/B: measured 14 % SLOWER, see below)
+        if (res_mode == 0) return launch_rows<64, true, 0, 1>(tm_w, tm_h, tm_c, p, st);
+        if (res_mode == 1) return launch_rows<64, true, 1, 1>(tm_w, tm_h, tm_c, p, st);
+        return launch_rows<64, true, 2, 1>(tm_w, tm_h, tm_c, p, st);
+      }
       if (res_mode == 0) return launch_rows<64, true, 0>(tm_w, tm_h, tm_c, p, st);
       if (res_mode == 1) return launch_rows<64, true, 1>(tm_w, tm_h, tm_c, p, st);
       return launch_rows<64, true, 2>(tm_w, tm_h, tm_c, p, st);

@@ -135,6 +135,8 @@ __device__ __forceinline__ uint4 pack8_rem(const float4 lo, const float4 hi, con
 // grid = B: folds the partial-sum records of image b (fixed order, fp64) into per-channel coefficients.
 // Done once per GroupNorm instead of once per streaming CTA, so the apply pass below is a pure stream.
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnApplyParams p) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sMean[16], sRstd[16];
   const int b = blockIdx.x;
   {
@@ -222,6 +224,8 @@ __device__ __forceinline__ long long gn_in_index(const GnApplyParams& p, int b, 
 
 template <bool X16>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int c8 = threadIdx.x & 7;          // 8-channel slice
   const int ps = threadIdx.x >> 3;         // 0..31
@@ -403,10 +407,8 @@ static int gn_apply_impl(const float* x, const float* partial, const float* gamm
   MCEDM_REQUIRE(work % per == 0, "gn_apply: cannot tile %d pixels", work);
   p.pix_per_cta = per;
   dim3 grid(work / per, B);
-  gn_finalize_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  MCEDM_CUDA(cudaGetLastError());
-  gn_apply_kernel<false><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  MCEDM_CUDA(cudaGetLastError());
+  MCEDM_CUDA(launch_pdl(gn_finalize_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
+  MCEDM_CUDA(launch_pdl(gn_apply_kernel<false>, grid, dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   return 0;
 }
 
@@ -451,8 +453,7 @@ extern "C" int mcedm_gn_coef(const float* partial, int parts_per_img, const floa
   p.Win = Win;
   p.meanrstd_out = meanrstd_out;
   p.coef = coef_out;
-  gn_finalize_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  MCEDM_CUDA(cudaGetLastError());
+  MCEDM_CUDA(launch_pdl(gn_finalize_kernel, dim3(B), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   return 0;
 }
 
@@ -489,7 +490,6 @@ extern "C" int mcedm_gn_apply16(const void* x16, int in_pitch, int in_blk, const
   MCEDM_REQUIRE(work % per == 0, "gn_apply16: cannot tile %d pixels", work);
   p.pix_per_cta = per;
   dim3 grid(work / per, B);
-  gn_apply_kernel<true><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  MCEDM_CUDA(cudaGetLastError());
+  MCEDM_CUDA(launch_pdl(gn_apply_kernel<true>, grid, dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   return 0;
 }

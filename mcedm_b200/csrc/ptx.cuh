@@ -35,6 +35,35 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// Programmatic dependent launch (launch_pdl in runtime.cuh).  pdl_wait: returns once the preceding kernel of the stream
+// has completed and its writes are visible (no-op for a plain launch); everything a kernel reads that an earlier kernel
+// wrote must come after it.  pdl_trigger: lets the NEXT kernel's CTAs become resident as soon as every CTA of this grid
+// has executed it (or exited): their prologue (barrier init, TMEM allocation, weight loads) then overlaps this kernel's
+// tail; placed after pdl_wait, so whatever precedes this kernel is complete by the time a dependent's prologue runs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// register re-allocation between warpgroups (all four warps of an aligned group execute it)
+template <int R>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+// streaming 128-bit global load (read once: do not allocate in L1)
+__device__ __forceinline__ uint4 ldg128_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// 256-bit global accesses (sm_100: LDG/STG.256), 32-byte aligned
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   const uint4 v = lds128(saddr);
   return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));

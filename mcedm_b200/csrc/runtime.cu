@@ -1,4 +1,5 @@
 // Runtime support for libmcedm_b200.so (see runtime.cuh). No torch, no libcuda link dependency.
+#include <cstdlib>
 #include "runtime.cuh"
 #include "../../include/mcedm_b200.h"
 
@@ -50,6 +51,15 @@ int num_sms() {
     g_sms[dev] = n;
   }
   return g_sms[dev];
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MCEDM_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;      // default OFF: measured slower (see runtime.cuh)
+  }
+  return on != 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
