@@ -29,6 +29,7 @@ PlMcedm.training_step (models/mcedm.py:254-281).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -42,6 +43,8 @@ class Train16Mixin:
     # True: the gradient of the residual stream keeps an fp32 master copy next to its 16-bit operand copy (8 more bytes
     # per element in every norm0 backward); False: fp16 only (one 2^-12 rounding per residual hop)
     GRAD_MASTER_FP32 = False
+    # weight-gradient launches on a side stream / parallel graph branch (backward16); MCEDM_WGRAD_SIDE=0 disables
+    WGRAD_SIDE_STREAM = True
 
     # ------------------------------------------------------------------ forward
     def forward_train16(self, x: torch.Tensor, nl: torch.Tensor, cond: Optional[torch.Tensor]) -> torch.Tensor:
@@ -157,6 +160,34 @@ class Train16Mixin:
         dF = dF.contiguous()
         self._jid, self._rjobs, self._wjobs, self._job_refs, self._post_copies = 0, [], [], [], []
 
+        # Weight gradients leave the critical path: the data-gradient chain (dgrad conv -> GroupNorm backward -> next
+        # block) never reads them, so the 3x3 / skip weight-gradient launches go to a SIDE stream (a parallel branch of
+        # the captured graph).  Both branches are grids of persistent one-CTA-per-SM kernels, so nothing runs truly
+        # side by side, but a branch's CTAs start on an SM the moment the other branch's CTA leaves it: launch gaps,
+        # prologues and tails of the short launches at B = 32 (20 - 50 us each) are filled with the other branch's work.
+        # Hazards: a weight-gradient launch only READS (a 16-bit gradient of this block, saved activations) and writes
+        # its own partial buffer; the gradient buffers are rewritten by later blocks, hence join() at every block start
+        # (joining later, just before the first rewrite, measured slower: 5.63 vs 5.48 ms - the lagging branch then
+        # competes with the critical data-gradient chain instead of filling its gaps).
+        main = torch.cuda.current_stream(dev)
+        side_on = self.WGRAD_SIDE_STREAM and os.environ.get("MCEDM_WGRAD_SIDE", "1") != "0"
+        if side_on:
+            s2 = getattr(self, "_side_stream", None)
+            if s2 is None or s2.device != dev:
+                s2 = self._side_stream = torch.cuda.Stream(dev)
+            st2 = s2.cuda_stream
+
+        def wgrad_side(*a, **k):
+            """_wgrad(..., st) on the side stream, ordered after everything enqueued on the main stream so far"""
+            if not side_on:
+                return self._wgrad(*a, **k)
+            s2.wait_stream(main)
+            return self._wgrad(*a[:-1], st2, **k)
+
+        def join():
+            if side_on:
+                main.wait_stream(s2)
+
         consumers: Dict[int, list] = {}
         for rec in tape:
             for i, a in enumerate(rec["inputs"]):
@@ -184,8 +215,8 @@ class Train16Mixin:
         L.check(lib.mcedm_nchw_to_nhwc_pad16(L.ptr(dF), u.out_channels, None, 0, B, H, W, L.ptr(dFp), 0, S, fmt, st),
                 "pad dF")
         last: Act = T["last"]
-        self._wgrad(ws, dFp, False, 64, 0, last.t, False, B, H, W, 9, G(u.out_conv.weight), 64, 0, st,
-                    co_count=u.out_channels, a_coef=T["coef_out"])
+        wgrad_side(ws, dFp, False, 64, 0, last.t, False, B, H, W, 9, G(u.out_conv.weight), 64, 0, st,
+                   co_count=u.out_channels, a_coef=T["coef_out"])
         cs_tmp = self._t(ws, ("cs_tmp", self._job_id()), (csn, 64), torch.float32)
         L.check(lib.mcedm_colsum16(L.ptr(dFp), B * H * W, 64, 0, L.ptr(cs_tmp), csn, fmt, st), "colsum")
         self._reduce_rows(cs_tmp, csn, 64, u.out_channels, 1, G(u.out_conv.bias), st)
@@ -206,6 +237,7 @@ class Train16Mixin:
             is_flat = lay[0] > 0
             gs = grads.pop(id(rec["final"]))
             out: Act = rec["out"]
+            join()
             if blk.attn:
                 # out2 = proj(att) + bproj + out
                 Lq = Hb * Wb
@@ -239,13 +271,13 @@ class Train16Mixin:
             # out = conv1(a1) + b1 + skip(x)
             self._bias_grad(gs, B, G(m.conv1.bias), st)
             h: Act = rec["h"]
-            self._wgrad(ws, gs["bf"], is_flat, 64, 0, h.t, is_flat, B, Hb, Wb, 9, G(m.conv1.weight), 64, 0, st,
-                        a_coef=rec["coef1"])
+            wgrad_side(ws, gs["bf"], is_flat, 64, 0, h.t, is_flat, B, Hb, Wb, 9, G(m.conv1.weight), 64, 0, st,
+                       a_coef=rec["coef1"])
             if blk.skip_conv:
                 self._bias_grad(gs, B, G(m.skip.bias), st)
                 for i, xi in enumerate(rec["inputs"]):
-                    self._wgrad(ws, gs["bf"], is_flat, 64, 0, xi.t, is_flat, B, Hb, Wb, 1, G(m.skip.weight),
-                                64 * blk.n_src, 64 * i, st)
+                    wgrad_side(ws, gs["bf"], is_flat, 64, 0, xi.t, is_flat, B, Hb, Wb, 1, G(m.skip.weight),
+                               64 * blk.n_src, 64 * i, st)
             d_a1 = self._buf16(ws, ("d16", Hb, Wb), B, Hb, Wb, dev)
             self._dgrad16(ws, gs["bf"], blk.wd1, B, Hb, Wb, d_a1, st)
             d_hb = self._buf16(ws, ("d_h16", Hb, Wb), B, Hb, Wb, dev)
@@ -262,8 +294,8 @@ class Train16Mixin:
                     self._wgrad(ws, d_hb, is_flat, 64, 0, a_i.t, is_flat, B, Hb, Wb, 9, G(m.conv0.weight),
                                 64 * blk.n_src, 64 * i, st)
                 else:
-                    self._wgrad(ws, d_hb, is_flat, 64, 0, xi.t, is_flat, B, Hb, Wb, 9, G(m.conv0.weight),
-                                64 * blk.n_src, 64 * i, st, a_coef=rec["coef0"][i])
+                    wgrad_side(ws, d_hb, is_flat, 64, 0, xi.t, is_flat, B, Hb, Wb, 9, G(m.conv0.weight),
+                               64 * blk.n_src, 64 * i, st, a_coef=rec["coef0"][i])
                 d_ai = self._buf16(ws, ("d16", Hb, Wb), B, Hb, Wb, dev)
                 self._dgrad16(ws, d_hb, blk.wd0[i], B, Hb, Wb, d_ai, st)
                 if blk.skip_conv:
@@ -298,8 +330,9 @@ class Train16Mixin:
         gs = grads.pop(id(T["t0"]))
         cin = u.enc[self.conv_in_name]
         self._bias_grad(gs, B, G(cin.bias), st)
-        self._wgrad(ws, gs["bf"], False, 64, 0, ws["xin_pad"], False, B, H, W, 9, G(cin.weight), cin.weight.shape[1], 0,
-                    st, ci_count=cin.weight.shape[1])
+        join()
+        wgrad_side(ws, gs["bf"], False, 64, 0, ws["xin_pad"], False, B, H, W, 9, G(cin.weight), cin.weight.shape[1], 0,
+                   st, ci_count=cin.weight.shape[1])
 
         # ---- embedding MLP and the per-block affine projections
         vec = self._t(ws, "embvec", (B, 320), torch.float32)
@@ -314,6 +347,7 @@ class Train16Mixin:
         torch._foreach_copy_([G(b.mod.affine.weight) for b in blocks], list(d_aff_w.unbind(0)))
         torch._foreach_copy_([G(b.mod.affine.bias) for b in blocks], list(d_aff_b.unbind(0)))
         assert not grads and not pending, (list(grads), list(pending))
+        join()
         self._flush_deferred(ws, st)
         for dst, src in self._post_copies:
             dst.copy_(src.t())
