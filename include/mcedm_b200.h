@@ -250,8 +250,10 @@ MCEDM_API int mcedm_gn_bwd(const float* dy, const float* x, const float* meanrst
  * add0_mode; x, add1, dx, dx16: Hin x Win).  dx16: 16-bit copy in x's layout; dx16_dense: a second, dense copy.
  * add16 != 0: add0 / add1 are 16-bit (op_fmt) too — the gradient of the residual stream without an fp32 master copy.
  * meanrstd / coef_ab: what the forward's mcedm_gn_coef wrote for this GroupNorm ([B][16][2], [B][128]).
- * kcoef: scratch fp32 [B][192]; ticket: uint32 [B], ZERO before the first launch (each launch leaves it zero): the
- * last CTA of a sample to finish pass 1 folds that sample's partials once (fixed order: deterministic).
+ * kcoef: scratch fp32 [B][192]; ticket: uint32 [3][B], ZERO before the first launch (each launch leaves it zero): the
+ * last CTA of a sample to finish pass 1 folds that sample's partials once (fixed order: deterministic).  When the whole
+ * grid is resident at once (ctas_per_img * B <= 2 x SM count) both passes run as ONE kernel: the sample's other CTAs
+ * wait for that fold in the kernel and re-read their slice from L2 (words [B..3B) are the flag and the departure count).
  * Win must be a power of two.  red_partial / dgb_partial / colsum_partial as in mcedm_gn_bwd, sized with
  * mcedm_gn_bwd16_ctas_per_img.
  */

@@ -424,7 +424,9 @@ struct GnBwd16Params {
   int ctas_per_img, pix_per_cta;
   float* red_partial;                          // [B][ctas_per_img][64][2]
   float* kcoef;                                // [B][3][64] = rstd*k | rstd*m1 | rstd*m2 written by the fold
-  unsigned int* ticket;                        // [B], zero before the launch, zero again after it
+  unsigned int* ticket;                        // [3][B], zero before the launch, zero again after it (see the fused kernel)
+  int fused;                                   // both passes in one kernel
+  unsigned int* err;                           // watchdog word
   const void* add0; int add0_mode, add0_pitch, add0_blk;   // at ITS resolution (mode as in GnBwdParams)
   const void* add1;
   int add16;                                   // add0 / add1 are 16-bit (fmt) instead of fp32
@@ -517,11 +519,11 @@ __device__ __forceinline__ void gn16_coef(const GnBwd16Params& p, int b, int oct
 constexpr int kGnNP = 4;    // pass 1: two streams
 constexpr int kGnNPa = 2;   // pass 2: up to four streams + the stores
 
+// pass 1 of one CTA (sums of du and du * xh over its pixels) + the per-sample fold by the last CTA to arrive
 template <bool FAST>
-__global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Params p) {
-  __shared__ float red[32][64][2];
-  __shared__ float sG1[64], sG2[64];
-  __shared__ unsigned int sLast;
+__device__ __forceinline__ void gn16_pass1(const GnBwd16Params& p, float (*red)[64][2], float* sG1, float* sG2,
+                                           unsigned int* sLastp) {
+  unsigned int& sLast = *sLastp;
   const int b = blockIdx.y;
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   Gn16Coef cf;
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Param
   __syncthreads();
   if (threadIdx.x == 0) sLast = (atomicAdd(p.ticket + b, 1u) == (unsigned)p.ctas_per_img - 1u) ? 1u : 0u;
   __syncthreads();
-  if (!sLast) return;
+  if (!sLast) return;            // (warp-uniform: the whole CTA leaves)
   __threadfence();
   float kk = 0.f, rstd_c = 0.f;
   if (threadIdx.x < 64) {
@@ -643,11 +645,25 @@ __global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Param
     kc[128] = rstd_c * m2;
   }
   if (threadIdx.x == 0) p.ticket[b] = 0u;         // ready for the next launch on this stream
+  if (p.fused) {
+    // one-kernel variant: publish "kcoef of sample b is complete" to the sample's other CTAs (spinning in the kernel)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(p.ticket + p.B + b, 1u);
+  }
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Params p) {
-  __shared__ float red[32][64];
+__global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Params p) {
+  __shared__ float red[32][64][2];
+  __shared__ float sG1[64], sG2[64];
+  __shared__ unsigned int sLast;
+  gn16_pass1<FAST>(p, red, sG1, sG2, &sLast);
+}
+
+// pass 2 of one CTA: dx = k0 du - (k1 + xh k2) + residual-path gradients, 16-bit out, column sums
+template <bool FAST>
+__device__ __forceinline__ void gn16_pass2(const GnBwd16Params& p, float (*red)[64]) {
   const int b = blockIdx.y;
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   Gn16Coef cf;
@@ -656,12 +672,12 @@ __global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Par
   float k0[8], cs[8];
   const float* kc = p.kcoef + (long long)b * 192 + oct * 8;
   {
-    const float4 q0 = *reinterpret_cast<const float4*>(kc), q1 = *reinterpret_cast<const float4*>(kc + 4);
+    const float4 q0 = __ldcg(reinterpret_cast<const float4*>(kc)), q1 = __ldcg(reinterpret_cast<const float4*>(kc + 4));
     k0[0] = q0.x; k0[1] = q0.y; k0[2] = q0.z; k0[3] = q0.w; k0[4] = q1.x; k0[5] = q1.y; k0[6] = q1.z; k0[7] = q1.w;
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) cs[k] = 0.f;
-  const float k1a = kc[64], k2a = kc[128], k1b = kc[68], k2b = kc[132];
+  const float k1a = __ldcg(kc + 64), k2a = __ldcg(kc + 128), k1b = __ldcg(kc + 68), k2b = __ldcg(kc + 132);
   const int pix0 = blockIdx.x * p.pix_per_cta;
   if (FAST) {
     // no resampling, residual-path gradients (if any) 16-bit at the same resolution
@@ -769,6 +785,52 @@ __global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Par
 #pragma unroll
       for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
       p.colsum_partial[((long long)b * p.ctas_per_img + blockIdx.x) * 64 + threadIdx.x] = t;
+    }
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, 2) gn_bwd16_apply_kernel(const GnBwd16Params p) {
+  __shared__ float red[32][64];
+  gn16_pass2<FAST>(p, red);
+}
+
+// Both passes in ONE kernel (p.fused).  The grid is about one wave of co-resident CTAs (pick_pix_per_cta16; the launcher
+// checks it against 2 x SM count), a sample's CTAs are neighbours in the launch order: each CTA runs pass 1 on its pixel
+// slice, the last one of the sample folds the partial sums and raises the sample's flag, the others spin on it, then every
+// CTA runs pass 2 on the SAME slice, which it finds in L2 (a sample is 2 x 2 MB at 128 x 128): 3 instead of 5 trips
+// through HBM per element.  ticket[0..B) counts pass-1 arrivals, ticket[B..2B) is the flag, ticket[2B..3B) counts pass-2
+// departures (the last one clears the flag): every word is zero again when the launch ends.  The spin is bounded like the
+// mbarrier waits (a protocol bug must not hang the GPU): on timeout the CTA goes on with whatever kcoef holds and
+// records the tag in *err.
+template <bool FAST1, bool FAST2>
+__global__ void __launch_bounds__(256, 2) gn_bwd16_fused_kernel(const GnBwd16Params p) {
+  __shared__ float red[32][64][2];
+  __shared__ float sG1[64], sG2[64];
+  __shared__ unsigned int sLast;
+  gn16_pass1<FAST1>(p, red, sG1, sG2, &sLast);
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    volatile unsigned int* flag = p.ticket + p.B + b;
+    if (*flag == 0u) {
+      const long long t0 = clock64();
+      while (*flag == 0u) {
+        __nanosleep(64);
+        if (clock64() - t0 > 2000000000LL) {
+          atomicCAS(p.err, 0u, 0xdead7000u);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  gn16_pass2<FAST2>(p, reinterpret_cast<float(*)[64]>(&red[0][0][0]));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(p.ticket + 2 * p.B + b, 1u) == (unsigned)p.ctas_per_img - 1u) {
+      p.ticket[2 * p.B + b] = 0u;
+      p.ticket[p.B + b] = 0u;
     }
   }
 }
@@ -882,6 +944,23 @@ extern "C" int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const 
   p.dss_batch_stride = dss_batch_stride;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(p.ctas_per_img, B);
+  const bool fast2 = resample == 0 && (add0 == nullptr || (add0_mode == 0 && p.add16)) && (add1 == nullptr || p.add16);
+  static int split = -1;
+  if (split < 0) {
+    const char* e = getenv("MCEDM_GNBWD_SPLIT");
+    split = (e && atoi(e)) ? 1 : 0;
+  }
+  // one kernel when every CTA of the grid is resident at once (2 per SM): the in-kernel wait needs the sample's CTAs live
+  if (!split && (long long)p.ctas_per_img * B <= 2LL * num_sms()) {
+    p.fused = 1;
+    p.err = watchdog_ptr();
+    MCEDM_REQUIRE(p.err != nullptr, "gn_bwd16: cannot allocate the watchdog word");
+    if (resample == 0 && fast2) gn_bwd16_fused_kernel<true, true><<<grid, 256, 0, st>>>(p);
+    else if (resample == 0) gn_bwd16_fused_kernel<true, false><<<grid, 256, 0, st>>>(p);
+    else gn_bwd16_fused_kernel<false, false><<<grid, 256, 0, st>>>(p);
+    MCEDM_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (resample == 0) {
     gn_bwd16_reduce_kernel<true><<<grid, 256, 0, st>>>(p);
   } else {

@@ -119,7 +119,7 @@ class Train16Mixin:
         n_cta = lib.mcedm_gn_bwd16_ctas_per_img(Hin, Win, B)
         red = self._t(ws, ("gnred", B * n_cta), (B, n_cta, 64, 2), torch.float32)
         kcoef = self._t(ws, "gnkcoef", (B, 192), torch.float32)
-        ticket = self._t(ws, "gnticket", (B,), torch.int32, zero=True)
+        ticket = self._t(ws, "gnticket", (3 * B,), torch.int32, zero=True)
         jid = self._job_id()
         dgb = self._t(ws, ("gndgb", jid), (B, 64, 2), torch.float32)
         out_f32 = dx16 = dense = cs = None

@@ -35,7 +35,7 @@ for H in (128, 64, 32):
     red = torch.empty(B, n_cta, 64, 2, device=dev)
     kcoef = torch.empty(B, 192, device=dev)
     coefab = torch.randn(B, 128, device=dev)
-    ticket = torch.zeros(B, device=dev, dtype=torch.int32)
+    ticket = torch.zeros(3 * B, device=dev, dtype=torch.int32)
     dgb = torch.empty(B, 64, 2, device=dev)
     cs = torch.empty(B * n_cta, 64, device=dev)
 

@@ -101,7 +101,7 @@ def test_gn_bwd16_matches_autograd(L, dev, fmt, add16, B, H, W, rs, act, use_ss,
     dxd = torch.empty(B, H, W, 64, device=dev, dtype=dt)
     cs = torch.empty(B * n_cta, 64, device=dev)
     kcoef = torch.empty(B, 192, device=dev)
-    ticket = torch.zeros(B, device=dev, dtype=torch.int32)
+    ticket = torch.zeros(3 * B, device=dev, dtype=torch.int32)
     for _ in range(2):      # twice: the ticket counters must be back at zero after a launch
         L.check(lib.mcedm_gn_bwd16(L.ptr(dy_buf), dyl[0], dyl[1], L.ptr(x_buf), xl[0], xl[1], fmt, L.ptr(mr),
                                    L.ptr(coef), L.ptr(gamma), L.ptr(beta), L.ptr(ss) if use_ss else None, 128, 64, act, rs, B, H, W,
