@@ -695,7 +695,11 @@ def measure_training(args, cfg, dev, rank, world, barrier):
     per = ms / args.train_steps
     bytes_in = sum(t.numel() * t.element_size() for t in host)
     return dict(metric="unet_train_samples_per_sec", value=B * world * args.train_steps / (ms / 1e3), unit="samples/s",
-                ms_per_step=per, batch_per_gpu=B, global_batch=B * world, steps=args.train_steps, dtype="bf16",
+                ms_per_step=per, batch_per_gpu=B, global_batch=B * world, steps=args.train_steps,
+                dtype="fp16" if pl.model.engine().train_plan == "fused16" else "bf16",
+                plan=pl.model.engine().train_plan + (": fp16 operands and activations forward and backward, loss-scaled, "
+                                                     "fp32 accumulation / statistics / master weights; weight gradients on a "
+                                                     "parallel graph branch" if pl.model.engine().train_plan == "fused16" else ""),
                 tflops_per_gpu=56.305e9 * B / per / 1e9,
                 e2e=dict(value=B * world * args.train_steps / (ms_e2e / 1e3), unit="samples/s",
                          h2d_bytes_per_step=bytes_in, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.train_steps,
