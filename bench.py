@@ -342,6 +342,9 @@ def run_b200(args):
         roof = dict(bound="tensor", achieved=achieved, peak=pk["tensor_sustained"], unit="TFLOP/s",
                     frac=achieved / pk["tensor_sustained"], frac_burst=achieved / pk["tensor"], peak_burst=pk["tensor"],
                     traffic=traffic,
+                    traffic_note=("dram__bytes_read + dram__bytes_write of ONE launch of the variant with a 16-bit residual "
+                                  "(3 tensor streams of 537 MB at 256 samples = 1.61 GB algorithmic), ncu --set full, "
+                                  "profiles/r2_ncu_conv_rows.md launch 5") if fused and traffic else None,
                     kernel=("conv_rows_kernel<64, fused> (GroupNorm+SiLU-fused 3x3 implicit GEMM at 128x128, 64 input "
                             "channels -> 64 per launch, 16-bit activations)" if fused else
                             "conv_rows_kernel<64> (3x3 implicit GEMM at 128x128, 64->64 channels per launch)"),
