@@ -520,9 +520,16 @@ constexpr int kGnNP = 4;    // pass 1: two streams
 constexpr int kGnNPa = 2;   // pass 2: up to four streams + the stores
 
 // pass 1 of one CTA (sums of du and du * xh over its pixels) + the per-sample fold by the last CTA to arrive
-template <bool FAST>
+// STAGED (one-kernel variant): the loads are per-thread cp.async copies into a 4-deep ring of thread-private shared-memory
+// slots, three batches ahead of the arithmetic.  With register-resident batches a warp alternated a load phase and ~400
+// instructions of arithmetic per thread (2.6 us per iteration at 14 resident warps per SM: 3.3 TB/s of algorithmic traffic);
+// here the memory system always has 3 batches per thread in flight and the registers only hold the pixel being processed.
+constexpr int kGnST = 4;                       // ring depth (batches)
+constexpr int kGnStageBytes = kGnST * 4 * 4096;   // 4 slots of 256 threads x 16 B per batch
+
+template <bool FAST, bool STAGED = false>
 __device__ __forceinline__ void gn16_pass1(const GnBwd16Params& p, float (*red)[64][2], float* sG1, float* sG2,
-                                           unsigned int* sLastp) {
+                                           unsigned int* sLastp, uint32_t stage = 0) {
   unsigned int& sLast = *sLastp;
   const int b = blockIdx.y;
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
@@ -532,7 +539,48 @@ __device__ __forceinline__ void gn16_pass1(const GnBwd16Params& p, float (*red)[
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
   const int pix0 = blockIdx.x * p.pix_per_cta;
-  if (FAST) {
+  if (FAST && STAGED) {
+    constexpr int NPS = 2;                                  // pixels per thread and batch: slots x0 x1 dy0 dy1
+    const int n_it = p.pix_per_cta / (32 * NPS);            // pix_per_cta is a power of two >= 128
+    const uint32_t sb = stage + threadIdx.x * 16;
+    auto issue = [&](int it) {
+      if (it < n_it) {
+        const uint32_t sl = sb + (uint32_t)(it % kGnST) * (4 * 4096);
+#pragma unroll
+        for (int u = 0; u < NPS; ++u) {
+          const int ip = pix0 + pl + 32 * (it * NPS + u);
+          const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+          cp_async16(sl + u * 4096, reinterpret_cast<const uint4*>(p.x) +
+                                        lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win) * 8 + oct);
+          cp_async16(sl + (NPS + u) * 4096, reinterpret_cast<const uint4*>(p.dy) +
+                                                lay_index(p.dy_pitch, p.dy_blk, b, y, x, p.Hin, p.Win) * 8 + oct);
+        }
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    issue(2);
+    for (int it = 0; it < n_it; ++it) {
+      issue(it + 3);
+      cp_async_wait<3>();
+      const uint32_t sl = sb + (uint32_t)(it % kGnST) * (4 * 4096);
+#pragma unroll
+      for (int u = 0; u < NPS; ++u) {
+        float xv[8], d[8];
+        unpack8(lds128(sl + u * 4096), p.fmt, xv);
+        unpack8(lds128(sl + (NPS + u) * 4096), p.fmt, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float dk = d[k];
+          if (p.act) dk *= silu_grad(fmaf(xv[k], cf.a[k], cf.bb[k]));
+          s1[k] += dk;
+          s2[k] += dk * (k < 4 ? fmaf(xv[k], cf.rs0, -cf.mr0) : fmaf(xv[k], cf.rs1, -cf.mr1));
+        }
+      }
+    }
+    cp_async_wait<0>();
+  } else if (FAST) {
     for (int i = pl; i < p.pix_per_cta; i += 32 * kGnNP) {
       uint4 xr[kGnNP], dr[kGnNP];
 #pragma unroll
@@ -662,8 +710,8 @@ __global__ void __launch_bounds__(256) gn_bwd16_reduce_kernel(const GnBwd16Param
 }
 
 // pass 2 of one CTA: dx = k0 du - (k1 + xh k2) + residual-path gradients, 16-bit out, column sums
-template <bool FAST>
-__device__ __forceinline__ void gn16_pass2(const GnBwd16Params& p, float (*red)[64]) {
+template <bool FAST, bool STAGED = false>
+__device__ __forceinline__ void gn16_pass2(const GnBwd16Params& p, float (*red)[64], uint32_t stage = 0) {
   const int b = blockIdx.y;
   const int oct = threadIdx.x & 7, pl = threadIdx.x >> 3;
   Gn16Coef cf;
@@ -679,7 +727,71 @@ __device__ __forceinline__ void gn16_pass2(const GnBwd16Params& p, float (*red)[
   for (int k = 0; k < 8; ++k) cs[k] = 0.f;
   const float k1a = __ldcg(kc + 64), k2a = __ldcg(kc + 128), k1b = __ldcg(kc + 68), k2b = __ldcg(kc + 132);
   const int pix0 = blockIdx.x * p.pix_per_cta;
-  if (FAST) {
+  if (FAST && STAGED) {
+    // one pixel per thread and batch: slots x, dy, add0, add1
+    const int n_it = p.pix_per_cta / 32;
+    const uint32_t sb = stage + threadIdx.x * 16;
+    auto issue = [&](int it) {
+      if (it < n_it) {
+        const uint32_t sl = sb + (uint32_t)(it % kGnST) * (4 * 4096);
+        const int ip = pix0 + pl + 32 * it;
+        const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+        const long long px = lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win);
+        cp_async16(sl, reinterpret_cast<const uint4*>(p.x) + px * 8 + oct);
+        cp_async16(sl + 4096, reinterpret_cast<const uint4*>(p.dy) +
+                                  lay_index(p.dy_pitch, p.dy_blk, b, y, x, p.Hin, p.Win) * 8 + oct);
+        if (p.add0)
+          cp_async16(sl + 2 * 4096, reinterpret_cast<const uint4*>(p.add0) +
+                                        lay_index(p.add0_pitch, p.add0_blk, b, y, x, p.Hin, p.Win) * 8 + oct);
+        if (p.add1) cp_async16(sl + 3 * 4096, reinterpret_cast<const uint4*>(p.add1) + px * 8 + oct);
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    issue(2);
+    for (int it = 0; it < n_it; ++it) {
+      issue(it + 3);
+      cp_async_wait<3>();
+      const uint32_t sl = sb + (uint32_t)(it % kGnST) * (4 * 4096);
+      const int ip = pix0 + pl + 32 * it;
+      const int y = ip >> p.w_shift, x = ip & (p.Win - 1);
+      const long long px = lay_index(p.x_pitch, p.x_blk, b, y, x, p.Hin, p.Win);
+      float xv[8], d[8], o[8];
+      unpack8(lds128(sl), p.fmt, xv);
+      unpack8(lds128(sl + 4096), p.fmt, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dk = d[k];
+        if (p.act) dk *= silu_grad(fmaf(xv[k], cf.a[k], cf.bb[k]));
+        const float t = k < 4 ? fmaf(fmaf(xv[k], cf.rs0, -cf.mr0), k2a, k1a) : fmaf(fmaf(xv[k], cf.rs1, -cf.mr1), k2b, k1b);
+        o[k] = fmaf(k0[k], dk, -t);
+      }
+      if (p.add0) {
+        float r[8];
+        unpack8(lds128(sl + 2 * 4096), p.fmt, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += r[k];
+      }
+      if (p.add1) {
+        float r[8];
+        unpack8(lds128(sl + 3 * 4096), p.fmt, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += r[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] += o[k];
+      if (p.dx) {
+        float4* q = reinterpret_cast<float4*>(p.dx + px * 64 + oct * 8);
+        q[0] = make_float4(o[0], o[1], o[2], o[3]);
+        q[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      const uint4 ov = pack8v(o, p.fmt);
+      if (p.dx16) reinterpret_cast<uint4*>(p.dx16)[px * 8 + oct] = ov;
+      if (p.dx16_dense) reinterpret_cast<uint4*>(p.dx16_dense)[((long long)b * p.Hin * p.Win + ip) * 8 + oct] = ov;
+    }
+    cp_async_wait<0>();
+  } else if (FAST) {
     // no resampling, residual-path gradients (if any) 16-bit at the same resolution
     for (int i = pl; i < p.pix_per_cta; i += 32 * kGnNPa) {
       uint4 xr[kGnNPa], dr[kGnNPa], ar[kGnNPa], br[kGnNPa];
@@ -808,7 +920,9 @@ __global__ void __launch_bounds__(256, 2) gn_bwd16_fused_kernel(const GnBwd16Par
   __shared__ float red[32][64][2];
   __shared__ float sG1[64], sG2[64];
   __shared__ unsigned int sLast;
-  gn16_pass1<FAST1>(p, red, sG1, sG2, &sLast);
+  extern __shared__ uint4 gn_stage[];
+  const uint32_t stage = smem_u32(gn_stage);
+  gn16_pass1<FAST1, FAST1>(p, red, sG1, sG2, &sLast, stage);
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
     volatile unsigned int* flag = p.ticket + p.B + b;
@@ -825,7 +939,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd16_fused_kernel(const GnBwd16Par
     __threadfence();
   }
   __syncthreads();
-  gn16_pass2<FAST2>(p, reinterpret_cast<float(*)[64]>(&red[0][0][0]));
+  gn16_pass2<FAST2, FAST2>(p, reinterpret_cast<float(*)[64]>(&red[0][0][0]), stage);
   __syncthreads();
   if (threadIdx.x == 0) {
     if (atomicAdd(p.ticket + 2 * p.B + b, 1u) == (unsigned)p.ctas_per_img - 1u) {
@@ -951,12 +1065,18 @@ extern "C" int mcedm_gn_bwd16(const void* dy16, int dy_pitch, int dy_blk, const 
     split = (e && atoi(e)) ? 1 : 0;
   }
   // one kernel when every CTA of the grid is resident at once (2 per SM): the in-kernel wait needs the sample's CTAs live
-  if (!split && (long long)p.ctas_per_img * B <= 2LL * num_sms()) {
+  if (!split && (long long)p.ctas_per_img * B <= 2LL * num_sms() && p.pix_per_cta % 64 == 0) {   // (staged batches: 64 pixels)
     p.fused = 1;
     p.err = watchdog_ptr();
     MCEDM_REQUIRE(p.err != nullptr, "gn_bwd16: cannot allocate the watchdog word");
-    if (resample == 0 && fast2) gn_bwd16_fused_kernel<true, true><<<grid, 256, 0, st>>>(p);
-    else if (resample == 0) gn_bwd16_fused_kernel<true, false><<<grid, 256, 0, st>>>(p);
+    static bool attr = false;
+    if (!attr) {
+      MCEDM_CUDA(cudaFuncSetAttribute(gn_bwd16_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnStageBytes));
+      MCEDM_CUDA(cudaFuncSetAttribute(gn_bwd16_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnStageBytes));
+      attr = true;
+    }
+    if (resample == 0 && fast2) gn_bwd16_fused_kernel<true, true><<<grid, 256, kGnStageBytes, st>>>(p);
+    else if (resample == 0) gn_bwd16_fused_kernel<true, false><<<grid, 256, kGnStageBytes, st>>>(p);
     else gn_bwd16_fused_kernel<false, false><<<grid, 256, 0, st>>>(p);
     MCEDM_CUDA(cudaGetLastError());
     return 0;
