@@ -21,7 +21,21 @@ namespace mcedm {
 
 constexpr int kInSlots = 8;                 // ring of operand rows (16 KB each: only bytes [0, 32) of a row are used)
 constexpr int kInTile = 16 * 1024;
-constexpr int kInThreads = 64 + 8 * 32 + 4 * 32;
+// The layer is one MMA per input row and its pacer was the BUILDER: a row's 12-15 scalar loads, the operand store and the
+// hand-over ran back to back, so every input row exposed one full global-memory latency (1.1 us per row: 242 us per launch at
+// 256 samples; doubling the epilogue warps changed nothing).  Two sets of 4 builder warps now take alternate input rows and
+// each thread requests its NEXT row's values before it packs and stores the current one: four rows in flight per CTA.
+#ifndef MCEDM_IN_BSETS
+#define MCEDM_IN_BSETS 2
+#endif
+template <int CIN>
+struct InTcCfg {
+  static constexpr int SETS = 1;                       // epilogue warp sets (alternate output rows): 2 measured slower (184 vs 169 us)
+  static constexpr int EPI_WARPS = 8 * SETS;
+  static constexpr int BSETS = MCEDM_IN_BSETS;         // builder warp sets (alternate input rows)
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + BSETS * 4 * 32;
+  static constexpr int STAGE_BYTES = EPI_WARPS * 4096;
+};
 
 struct InTcParams {
   const float* x;        // [B, Cx, H, 128]
@@ -36,14 +50,15 @@ struct InTcParams {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(kInThreads, 1)
+__global__ void __launch_bounds__(InTcCfg<CIN>::THREADS, 1)
 conv_in_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const InTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem;                                   // 3 x [64 co][64 k] fp16 = 24 KB, ky-major
   uint8_t* a_smem = w_smem + 3 * 8192;                      // kInSlots x 16 KB
   uint8_t* stage_smem = a_smem + kInSlots * kInTile;        // 8 warps x 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + 8 * 4096);
+  using Cfg = InTcCfg<CIN>;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + Cfg::STAGE_BYTES);
   uint64_t* w_full = bars;
   uint64_t* acc_full = bars + 1;           // 8
   uint64_t* acc_empty = acc_full + 8;      // 8
@@ -139,17 +154,17 @@ conv_in_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const InTcParams p) 
       t0 += (uint32_t)R;
       r += R;
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + Cfg::EPI_WARPS) {
     // ======================================= epilogue =======================================
-    const int q = warp & 3, ew = warp - 2, ch = ew >> 2;
+    const int q = warp & 3, ew = warp - 2, ch = (ew & 7) >> 2, set = ew >> 3;
     const uint32_t my_stage = smem_u32(stage_smem) + ew * 4096;
     const int unit = lane & 7, row_in_it = lane >> 3;
     const int c0 = ch * 32 + unit * 4;
     float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) bz = *reinterpret_cast<const float4*>(p.bias + c0);
     uint16_t* o16 = reinterpret_cast<uint16_t*>(p.out);
-    uint32_t tcount = 0;
-    for (long long r = r_begin; r < r_end; ++r, ++tcount) {
+    uint32_t tcount = (uint32_t)set;
+    for (long long r = r_begin + set; r < r_end; r += Cfg::SETS, tcount += Cfg::SETS) {
       const uint32_t buf = tcount & 7u, aph = (tcount >> 3) & 1u;
       const long long pix0 = r * 128 + q * 32;
       mbar_wait(&acc_full[buf], aph, p.err, 0x4700 + buf);
@@ -191,52 +206,69 @@ conv_in_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const InTcParams p) 
     }
   } else {
     // ======================================= builders =======================================
-    const int px = (int)threadIdx.x - 32 * 10;              // this thread's pixel 0..127
+    const int bt = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    const int px = bt & 127;                                 // this thread's pixel 0..127
+    const int bset = bt >> 7;                                // builder set: input rows hl = bset (mod BSETS)
     const uint32_t a_base = smem_u32(a_smem);
     const long long HW = (long long)p.H * 128;
-    uint32_t hs = 0, hph = 0;
+    // cursor over the CTA's input rows in the MMA warp's order: segment (image b, rows y0 .. y0+R-1) -> R + 2 input rows
     long long r = r_begin;
-    while (r < r_end) {
-      const int b = (int)(r / p.H);
-      const int y0 = (int)(r - (long long)b * p.H);
-      const int R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
-      for (int k = 0; k < R + 2; ++k) {
-        const int y = y0 - 1 + k;
-        // operand row of pixel px: value index kx*Cin + c = in[c][y][px + kx - 1]; loads first, then the slot wait
-        float v[16];
+    int b = 0, y0 = 0, R = 0, k = 0;
+    uint32_t hl = 0;
+    bool done = r >= r_end;
+    auto seg = [&]() {
+      b = (int)(r / p.H);
+      y0 = (int)(r - (long long)b * p.H);
+      R = (int)((r_end - r) < (long long)(p.H - y0) ? (r_end - r) : (long long)(p.H - y0));
+      k = 0;
+    };
+    auto advance = [&]() {
+      ++hl;
+      if (++k == R + 2) {
+        r += R;
+        if (r >= r_end) done = true;
+        else seg();
+      }
+    };
+    auto load_row = [&](float (&v)[16]) {
+      // operand row of pixel px: value index kx*Cin + c = in[c][y][px + kx - 1]
+      const int y = y0 - 1 + k;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        if (y >= 0 && y < p.H) {
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      if (y >= 0 && y < p.H) {
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) {
-            {
-              const float* src = (c < p.Cc) ? p.cond + ((long long)b * p.Cc + c) * HW + (long long)y * 128
-                                            : p.x + ((long long)b * p.Cx + (c - p.Cc)) * HW + (long long)y * 128;
+        for (int c = 0; c < CIN; ++c) {
+          const float* src = (c < p.Cc) ? p.cond + ((long long)b * p.Cc + c) * HW + (long long)y * 128
+                                        : p.x + ((long long)b * p.Cx + (c - p.Cc)) * HW + (long long)y * 128;
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const int xx = px + kx - 1;
-                v[kx * CIN + c] = (xx >= 0 && xx < 128) ? __ldg(src + xx) : 0.f;
-              }
-            }
+          for (int kx = 0; kx < 3; ++kx) {
+            const int xx = px + kx - 1;
+            v[kx * CIN + c] = (xx >= 0 && xx < 128) ? __ldg(src + xx) : 0.f;
           }
         }
-        uint4 lo4, hi4;
-        lo4.x = pack_op2(v[0], v[1], p.fmt);   lo4.y = pack_op2(v[2], v[3], p.fmt);
-        lo4.z = pack_op2(v[4], v[5], p.fmt);   lo4.w = pack_op2(v[6], v[7], p.fmt);
-        hi4.x = pack_op2(v[8], v[9], p.fmt);   hi4.y = pack_op2(v[10], v[11], p.fmt);
-        hi4.z = pack_op2(v[12], v[13], p.fmt); hi4.w = pack_op2(v[14], v[15], p.fmt);
-        mbar_wait(&a_empty[hs], hph ^ 1u, p.err, 0x4800 + hs);
-        const uint32_t rowa = a_base + hs * kInTile + px * 128;
-        sts128(rowa + ((0 ^ (px & 7)) << 4), lo4);
-        sts128(rowa + ((1 ^ (px & 7)) << 4), hi4);
-        fence_proxy_async_smem();
-        mbar_arrive_warp(&a_ready[hs]);
-        if (++hs == kInSlots) {
-          hs = 0;
-          hph ^= 1u;
-        }
       }
-      r += R;
+    };
+    if (!done) seg();
+    for (int i = 0; i < bset && !done; ++i) advance();
+    float v[16], vn[16];
+    if (!done) load_row(v);
+    while (!done) {
+      const uint32_t hs = hl % (uint32_t)kInSlots, hph = (hl / (uint32_t)kInSlots) & 1u;
+      for (int i = 0; i < Cfg::BSETS && !done; ++i) advance();
+      if (!done) load_row(vn);                               // the next row's loads fly while this one is stored
+      uint4 lo4, hi4;
+      lo4.x = pack_op2(v[0], v[1], p.fmt);   lo4.y = pack_op2(v[2], v[3], p.fmt);
+      lo4.z = pack_op2(v[4], v[5], p.fmt);   lo4.w = pack_op2(v[6], v[7], p.fmt);
+      hi4.x = pack_op2(v[8], v[9], p.fmt);   hi4.y = pack_op2(v[10], v[11], p.fmt);
+      hi4.z = pack_op2(v[12], v[13], p.fmt); hi4.w = pack_op2(v[14], v[15], p.fmt);
+      mbar_wait(&a_empty[hs], hph ^ 1u, p.err, 0x4800 + hs);
+      const uint32_t rowa = a_base + hs * kInTile + px * 128;
+      sts128(rowa + ((0 ^ (px & 7)) << 4), lo4);
+      sts128(rowa + ((1 ^ (px & 7)) << 4), hi4);
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&a_ready[hs]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = vn[i];
     }
   }
 
@@ -280,7 +312,7 @@ extern "C" int mcedm_conv_in_tc16(const float* x, int Cx, const float* cond, int
 #define MCEDM_IN_TC_CASE(C)                                                                                          \
   case C:                                                                                                            \
     MCEDM_CUDA(cudaFuncSetAttribute(conv_in_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
-    MCEDM_CUDA(launch_pdl(conv_in_tc_kernel<C>, dim3((unsigned)grid), dim3(kInThreads), (size_t)smem, st, tm_w, p)); \
+    MCEDM_CUDA(launch_pdl(conv_in_tc_kernel<C>, dim3((unsigned)grid), dim3(InTcCfg<C>::THREADS), (size_t)smem, st, tm_w, p)); \
     break;
   switch (Cx + Cc) {
     MCEDM_IN_TC_CASE(1) MCEDM_IN_TC_CASE(2) MCEDM_IN_TC_CASE(3) MCEDM_IN_TC_CASE(4) MCEDM_IN_TC_CASE(5)
