@@ -51,6 +51,9 @@
 #ifndef MCEDM_DUAL
 #define MCEDM_DUAL 1   // two MMA-issuing warps taking alternate input rows (stacked kernels), see the MMA issuer
 #endif
+#ifndef MCEDM_XF_SETS
+#define MCEDM_XF_SETS 1   // transform warp SETS taking alternate input rows in the N = 64 kernels (the N = 16 head: always 2)
+#endif
 #ifndef MCEDM_XF_H2
 #define MCEDM_XF_H2 0   // GroupNorm+SiLU transform in packed half arithmetic: 3 instructions per 2 elements instead of 9, but
                         // measured +2 % only (the row is bounded by shared-memory bytes, not by the transform's ALU work) at
@@ -99,6 +102,13 @@ struct RowsCfg {
   // GroupNorm+SiLU transform warps (after the epilogue warps); the 16-wide head conv has a quarter of the MMA / epilogue
   // work per row, so there the transform is the pacer and gets eight
   static constexpr int XF_WARPS = FUSED ? ((N == 16 || (N == 64 && MCEDM_XF8)) ? 8 : 4) : 0;
+  // A row's transform is a latency chain (wait for the TMA, shared-memory load, MUFU, store, proxy fence, hand-over) that
+  // takes ~1300 cycles however many warps share it (head kernel: the same with 8 warps as the N = 64 kernel with 4), and
+  // with all transform warps on the same row nothing overlaps it.  XF_SETS sets take alternate rows instead: the head
+  // (8 warps, the transform is its pacer) goes from 185 to 159 us per launch at 256 samples; the N = 64 kernels lose
+  // (two sets of two warps: 313 vs 302 us, 423 vs 363 with the residual - each thread then carries 16 chunks per row).
+  static constexpr int XF_SETS = FUSED ? (N == 16 ? 2 : MCEDM_XF_SETS) : 1;
+  static constexpr int XF_SET_WARPS = FUSED ? XF_WARPS / XF_SETS : 1;
   // DUAL: a second MMA-issuing warp (the last warp of the CTA) for the stacked kernels
   static constexpr bool DUAL = FUSED && (N == 64 || N == 16) && MCEDM_DUAL;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
@@ -202,7 +212,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     for (int i = 0; i < p.n_slots; ++i) {
       mbar_init(&h_full[i], 1);
       mbar_init(&h_empty[i], 1);
-      mbar_init(&h_ready[i], Cfg::XF_WARPS + (FUSED ? 0 : 1));
+      mbar_init(&h_ready[i], FUSED ? Cfg::XF_SET_WARPS : 1);
     }
     for (int i = 0; i < p.n_cslots; ++i) {
       mbar_init(&c_full[i], 1);
@@ -911,13 +921,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           // output head (adm_blocks.py:403): the TMEM layout (lane = pixel) IS the NCHW order along x, so the first
           // nchw_c accumulator columns go straight to F_x[b, c, y, :] as coalesced 128-byte rows - no staging, no
           // 16-channel NHWC intermediate, no separate head_to_nchw pass
-          const int bimg = (int)(r / p.H);
+          // (one 32-bit division per row; the 16 predicated stores with their own 64-bit address arithmetic and bias
+          // loads cost the epilogue ~1100 cycles per row and made it this kernel's pacer)
+          const int bimg = (int)((unsigned long long)r / (unsigned)p.H);
           const int y = (int)(r - (long long)bimg * p.H);
-          float* F = reinterpret_cast<float*>(p.out);
+          float* F = reinterpret_cast<float*>(p.out) + ((long long)bimg * p.nchw_c * p.H + y) * 128 + q * 32 + lane;
+          const long long cstride = (long long)p.H * 128;
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < p.nchw_c)
-              F[(((long long)bimg * p.nchw_c + c) * p.H + y) * 128 + q * 32 + lane] = __uint_as_float(v[c]) + __ldg(p.bias + c);
+          for (int c = 0; c < 16; ++c) {
+            if (c >= p.nchw_c) break;
+            F[c * cstride] = __uint_as_float(v[c]) + __ldg(p.bias + c);
+          }
           continue;
         }
       }
@@ -982,11 +996,14 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
     // halo row; the chunk's physical position follows SWIZZLE_128B: chunk ^ (pixel row & 7) (slots are 1 KB aligned).
-    const int t = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    const int t0 = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    const int xset = t0 / (32 * Cfg::XF_SET_WARPS);           // this thread's set: input rows hl = xset (mod XF_SETS)
+    const int t = t0 - xset * (32 * Cfg::XF_SET_WARPS);
     const int j = t & 7;
     const int prow = t >> 3;                // 0 .. XF_ROWS-1
-    constexpr int XF_ROWS = FUSED ? 4 * Cfg::XF_WARPS : 16;   // pixels covered per pass by the transform threads
+    constexpr int XF_ROWS = FUSED ? 4 * Cfg::XF_SET_WARPS : 16;   // pixels covered per pass by one set's threads
     constexpr int XF_IT = 128 / XF_ROWS;
+    constexpr int XF_SUB = XF_IT > 8 ? 8 : XF_IT;                 // 16-byte chunks in flight per thread
     uint32_t hl = 0;
     long long dbg_w4 = 0;
     long long r = r_begin;
@@ -1018,6 +1035,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
       }
       for (int k = 0; k < R + 2; ++k, ++hl) {
+        if ((int)(hl % (uint32_t)Cfg::XF_SETS) != xset) continue;
         const uint32_t slot = hl % (uint32_t)p.n_slots, ph = (hl / (uint32_t)p.n_slots) & 1u;
         timed_wait(&h_full[slot], ph, p.err, 0x2800 + slot, dbg_w4, (p.dbg & 32) != 0);
         const int y = y0 - 1 + k;
@@ -1026,15 +1044,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           for (int s = 0; s < 2; ++s) {
             if (s < n_halo) {
               const uint32_t base = smem_u32(h_smem) + slot * slot_bytes + s * kHaloBytes;
-              uint4 v[XF_IT];
 #pragma unroll
-              for (int i = 0; i < XF_IT; ++i) {
-                const int px = 1 + prow + XF_ROWS * i;
+              for (int i0 = 0; i0 < XF_IT; i0 += XF_SUB) {
+              uint4 v[XF_SUB];
+#pragma unroll
+              for (int i = 0; i < XF_SUB; ++i) {
+                const int px = 1 + prow + XF_ROWS * (i0 + i);
                 v[i] = lds128(base + px * 128 + ((j ^ (px & 7)) << 4));
               }
 #pragma unroll
-              for (int i = 0; i < XF_IT; ++i) {
-                const int px = 1 + prow + XF_ROWS * i;
+              for (int i = 0; i < XF_SUB; ++i) {
+                const int px = 1 + prow + XF_ROWS * (i0 + i);
                 uint4 o;
                 if (MCEDM_XF_H2 && fmt == 1 && !(p.dbg & 1)) {      // MCEDM_DBG=1: fp32 transform (A/B switch)
                   o.x = silu_affine_h2(v[i].x, ca2[s][0], cb2[s][0]);
@@ -1048,6 +1068,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
                   o.w = xf_pair(v[i].w, ca[s][6], cb[s][6], ca[s][7], cb[s][7], fmt);
                 }
                 sts128(base + px * 128 + ((j ^ (px & 7)) << 4), o);
+              }
               }
             }
           }
