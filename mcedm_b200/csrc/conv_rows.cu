@@ -728,7 +728,8 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
     } else if constexpr (Cfg::EPI_H16) {
       // ---------------------------------------------------------------------------------------------------------
-      // 16-bit staging.  The kernel is bounded by shared-memory BYTES per row (MMA operand fetch 120 KB + TMA 17 KB +
+      // 16-bit staging.  (Also measured and dropped: the 8 warps as two SETS of 4 on alternate tiles, each warp draining
+      // both 32-column halves of its lane quarter, so that consecutive tiles' latency chains overlap: 317 vs 301 us.)  The kernel is bounded by shared-memory BYTES per row (MMA operand fetch 120 KB + TMA 17 KB +
       // transform 32 KB + epilogue staging; scripts/rows_ablate.py: 9.7 cycles per KB), and the fp32 staging tile
       // (32 KB written + 32 KB read back per row) was the largest item the kernel itself controls.  Now each thread
       // rounds its pixel's 32 accumulators to fp16 FIRST and stages 64 B (4 x 16-byte chunks, XOR-swizzled with
