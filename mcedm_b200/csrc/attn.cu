@@ -93,6 +93,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
   // stand-alone two-pass kernel).  The FALLBACK launch of the two-pass kernel (flags != NULL) runs a small grid whose
   // CTAs stride over the tiles and redo only the flagged ones: with no flag raised — the normal case — it costs a
   // launch and a few flag reads per CTA instead of 2048 empty 180 KB-shared-memory CTAs (17 us).
+  if (!SINGLE && flags != nullptr) {
+    // fallback launch: all of this CTA's flags in ONE round trip (one thread per tile); nothing raised - the normal case -
+    // and the CTA is gone (the loop below would read them one dependent load after the other: ~0.5 us per tile)
+    int any = 0;
+    for (int tile = (int)blockIdx.x + (int)threadIdx.x * (int)gridDim.x; tile < n_tiles; tile += (int)(blockDim.x * gridDim.x))
+      any |= flags[tile] != 0u;
+    if (!__syncthreads_or(any)) return;
+  }
   bool first_tile = true;
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
   if (!SINGLE && flags != nullptr && flags[tile] == 0u) continue;

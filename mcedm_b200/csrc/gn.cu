@@ -139,6 +139,17 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnApplyParams p)
   pdl_trigger();
   __shared__ float sMean[16], sRstd[16];
   const int b = blockIdx.x;
+  // the affine parameters do not depend on the fold: requested first, so their latency overlaps the records'
+  float pg = 0.f, pb = 0.f, psc = 0.f, psh = 0.f;
+  if (threadIdx.x < 64) {
+    pg = __ldg(p.gamma + threadIdx.x);
+    pb = __ldg(p.beta + threadIdx.x);
+    if (p.scale_shift) {
+      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
+      psc = ss[threadIdx.x];
+      psh = ss[p.emb_shift_offset + threadIdx.x];
+    }
+  }
   {
     // fold the partial-sum records of image b: 16 threads per group, fixed order, fp64.
     // Loads are issued 8 at a time before any add so the L2 latency is paid once per batch, not per record.
@@ -178,13 +189,12 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const GnApplyParams p)
   __syncthreads();
   if (threadIdx.x < 64) {
     const int c = threadIdx.x;
-    float a = sRstd[c >> 2] * p.gamma[c];
-    float bb = p.beta[c] - sMean[c >> 2] * a;
+    float a = sRstd[c >> 2] * pg;
+    float bb = pb - sMean[c >> 2] * a;
     if (p.scale_shift) {
-      const float* ss = p.scale_shift + (long long)b * p.emb_batch_stride;
-      const float sc = 1.0f + ss[c];
+      const float sc = 1.0f + psc;
       a *= sc;
-      bb = fmaf(bb, sc, ss[p.emb_shift_offset + c]);
+      bb = fmaf(bb, sc, psh);
     }
     p.coef[(long long)b * 128 + c] = a;
     p.coef[(long long)b * 128 + 64 + c] = bb;
