@@ -42,6 +42,9 @@
 #ifndef MCEDM_FLAT_WG
 #define MCEDM_FLAT_WG 1
 #endif
+#ifndef MCEDM_FLAT_XSETS
+#define MCEDM_FLAT_XSETS 1   // transform warp sets on alternate chunks (WG layout only)
+#endif
 #ifndef MCEDM_FLAT_LDG
 #define MCEDM_FLAT_LDG 1   // fused + transform: the transform warps fetch the raw chunk from global memory themselves
 #endif
@@ -89,6 +92,8 @@ struct FlatCfg {
   static constexpr int XF_WARPS = FUSED ? (WG ? 8 : 4) : 0;
   static constexpr int THREADS = WG ? 640 : 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
   static constexpr int MMA2_WARP = WG ? 2 : (DUAL ? THREADS / 32 - 1 : -1);
+  static constexpr int XF_SETS = WG ? MCEDM_FLAT_XSETS : 1;
+  static constexpr int XF_SET_WARPS = FUSED ? XF_WARPS / XF_SETS : 1;
   static constexpr int EPI_W0 = WG ? 4 : 2;
   static constexpr int XF_W0 = WG ? 12 : 2 + EPI_WARPS;
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * CH * 4;   // (the 16-bit fast-path epilogue uses half of it)
@@ -214,7 +219,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     for (int i = 0; i < S; ++i) {
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 1);
-      mbar_init(&c_ready[i], FUSED ? Cfg::XF_WARPS : 1);
+      mbar_init(&c_ready[i], FUSED ? Cfg::XF_SET_WARPS : 1);
     }
     mbar_init(&turn[0], 1);
     mbar_init(&turn[1], 1);
@@ -566,10 +571,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // thread t owns the logical 16-byte chunk jc = t & 7 (channels 8jc .. 8jc+7) of positions (t >> 3) + 16 i of every
     // 128-position chunk; physical 16-byte slot = jc ^ (position & 7) (SWIZZLE_128B, 1 KB-aligned chunk slots).
     if constexpr (Cfg::WG) setmaxnreg_dec<80>();
-    const int t = (int)threadIdx.x - 32 * Cfg::XF_W0;
+    const int tx = (int)threadIdx.x - 32 * Cfg::XF_W0;
+    const int xset = tx / (32 * Cfg::XF_SET_WARPS);           // this thread's set: chunks k = xset (mod XF_SETS)
+    const int t = tx - xset * (32 * Cfg::XF_SET_WARPS);
     const int jc = t & 7;
     const int prow = t >> 3;
-    constexpr int XF_ROWS = FUSED ? 4 * Cfg::XF_WARPS : 16;   // positions covered per pass
+    constexpr int XF_ROWS = FUSED ? 4 * Cfg::XF_SET_WARPS : 16;   // positions covered per pass
     constexpr int XF_IT = 128 / XF_ROWS;
     int cur_b = -1;
     float ca[8], cb[8];
@@ -588,11 +595,15 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         for (int i = 0; i < XF_IT; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
       }
     };
-    if (xf_ldg) ldg_chunk(0, n0);
+    if (xf_ldg && Cfg::XF_SETS == 1) ldg_chunk(0, n0);
     for (int k = 0; k < n_tiles + 2; ++k) {
+      if (Cfg::XF_SETS > 1 && (k % Cfg::XF_SETS) != xset) continue;
       const uint32_t slot = (uint32_t)k % (uint32_t)S, ph = ((uint32_t)k / (uint32_t)S) & 1u;
       uint4 v[XF_IT];
-      if (xf_ldg) {
+      if (xf_ldg && Cfg::XF_SETS > 1) {
+        ldg_chunk(k, v);           // (the other set's chunk overlaps this load)
+        mbar_wait(&c_empty[slot], ph ^ 1u, p.err, 0x3100 + slot);
+      } else if (xf_ldg) {
 #pragma unroll
         for (int i = 0; i < XF_IT; ++i) v[i] = n0[i];
         ldg_chunk(k + 1, n0);
