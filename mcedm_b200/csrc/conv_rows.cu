@@ -51,6 +51,9 @@
 #ifndef MCEDM_DUAL
 #define MCEDM_DUAL 1   // two MMA-issuing warps taking alternate input rows (stacked kernels), see the MMA issuer
 #endif
+#ifndef MCEDM_ROWS_WG
+#define MCEDM_ROWS_WG 1   // fused N = 64: roles on warpgroup boundaries + setmaxnreg, 8 transform warps (as conv_flat.cu)
+#endif
 #ifndef MCEDM_XF_SETS
 #define MCEDM_XF_SETS 1   // transform warp SETS taking alternate input rows in the N = 64 kernels (the N = 16 head: always 2)
 #endif
@@ -101,7 +104,11 @@ struct RowsCfg {
   static constexpr int EPI_WARPS = 4 * NCH;                 // one warp per (lane quarter, column chunk)
   // GroupNorm+SiLU transform warps (after the epilogue warps); the 16-wide head conv has a quarter of the MMA / epilogue
   // work per row, so there the transform is the pacer and gets eight
-  static constexpr int XF_WARPS = FUSED ? ((N == 16 || (N == 64 && MCEDM_XF8)) ? 8 : 4) : 0;
+  // WG (fused N = 64): warps 0-3 TMA | MMA | MMA 2 | idle, 4-11 epilogue, 12-19 transform; 640 threads launch at 96
+  // registers and setmaxnreg re-balances them (first group stays at 96, epilogue 128, transform 64: releases = acquisitions).
+  // EIGHT transform warps without the spills that the plain 608-thread layout (104 registers for everybody) had.
+  static constexpr bool WG = FUSED && N == 64 && MCEDM_DUAL && MCEDM_ROWS_WG && !MCEDM_EPI16;
+  static constexpr int XF_WARPS = FUSED ? ((N == 16 || WG || (N == 64 && MCEDM_XF8)) ? 8 : 4) : 0;
   // A row's transform is a latency chain (wait for the TMA, shared-memory load, MUFU, store, proxy fence, hand-over) that
   // takes ~1300 cycles however many warps share it (head kernel: the same with 8 warps as the N = 64 kernel with 4), and
   // with all transform warps on the same row nothing overlaps it.  XF_SETS sets take alternate rows instead: the head
@@ -111,8 +118,10 @@ struct RowsCfg {
   static constexpr int XF_SET_WARPS = FUSED ? XF_WARPS / XF_SETS : 1;
   // DUAL: a second MMA-issuing warp (the last warp of the CTA) for the stacked kernels
   static constexpr bool DUAL = FUSED && (N == 64 || N == 16) && MCEDM_DUAL;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
-  static constexpr int MMA2_WARP = DUAL ? THREADS / 32 - 1 : -1;
+  static constexpr int THREADS = WG ? 640 : 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
+  static constexpr int MMA2_WARP = WG ? 2 : (DUAL ? THREADS / 32 - 1 : -1);
+  static constexpr int EPI_W0 = WG ? 4 : 2;                  // first epilogue warp
+  static constexpr int XF_W0 = WG ? 12 : 2 + EPI_WARPS;      // first transform warp
   // fused N = 64: the epilogue transposes through a 16-BIT staging tile (32 pixels x 64 B per warp), see the epilogue
   static constexpr bool EPI_H16 = FUSED && N == 64 && !MCEDM_EPI16;
   static constexpr int STAGE_BYTES = EPI_H16 ? EPI_WARPS * 2048 : EPI_WARPS * 32 * CH * 4;
@@ -599,10 +608,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         r += R;
       }
     }
-  } else if (!FUSED || warp < 2 + Cfg::EPI_WARPS) {
+  } else if (Cfg::WG && warp == 3) {
+    // the idle fourth warp of the first group (TMA | MMA | MMA 2 | idle keep their 96 registers)
+  } else if (!FUSED || (warp >= Cfg::EPI_W0 && warp < Cfg::EPI_W0 + Cfg::EPI_WARPS)) {
+    if constexpr (Cfg::WG) setmaxnreg_inc<128>();
     // ======================================= epilogue =======================================
     const int q = warp & 3;                 // TMEM lane quarter
-    const int ew = warp - 2;                // 0 .. EPI_WARPS-1
+    const int ew = warp - Cfg::EPI_W0;      // 0 .. EPI_WARPS-1
     const int ch = ew >> 2;                 // column chunk drained by this warp
     if constexpr (Cfg::EPI_H16 && EP == 1) {
       // ---------------------------------------------------------------------------------------------------------
@@ -722,7 +734,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           for (int i = 0; i < 16; ++i) gs[i] = 0.f;
         }
       }
-      if ((p.dbg & 32) && warp == 2 && lane == 0) {
+      if ((p.dbg & 32) && warp == Cfg::EPI_W0 && lane == 0) {
         g_rows_dbg[blockIdx.x][3] = dbg_w3;
         g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
       }
@@ -851,7 +863,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
         __syncwarp();                              // the staging tile is rewritten by the next tile
       }
-      if ((p.dbg & 32) && warp == 2 && lane == 0) {
+      if ((p.dbg & 32) && warp == Cfg::EPI_W0 && lane == 0) {
         g_rows_dbg[blockIdx.x][3] = dbg_w3;
         g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
       }
@@ -988,16 +1000,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
       __syncwarp();
     }
-    if ((p.dbg & 32) && warp == 2 && lane == 0) {
+    if ((p.dbg & 32) && warp == Cfg::EPI_W0 && lane == 0) {
       g_rows_dbg[blockIdx.x][3] = dbg_w3;
       g_rows_dbg[blockIdx.x][5] = clock64() - dbg_t0;
     }
     }
-  } else if (warp < 2 + Cfg::EPI_WARPS + Cfg::XF_WARPS) {
+  } else if (warp >= Cfg::XF_W0 && warp < Cfg::XF_W0 + Cfg::XF_WARPS) {
+    if constexpr (Cfg::WG) setmaxnreg_dec<64>();
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk j = t & 7 (channels 8j .. 8j+7) of pixels 1 + (t >> 3) + 16 i of every
     // halo row; the chunk's physical position follows SWIZZLE_128B: chunk ^ (pixel row & 7) (slots are 1 KB aligned).
-    const int t0 = (int)threadIdx.x - 32 * (2 + Cfg::EPI_WARPS);
+    const int t0 = (int)threadIdx.x - 32 * Cfg::XF_W0;
     const int xset = t0 / (32 * Cfg::XF_SET_WARPS);           // this thread's set: input rows hl = xset (mod XF_SETS)
     const int t = t0 - xset * (32 * Cfg::XF_SET_WARPS);
     const int j = t & 7;
