@@ -27,6 +27,8 @@
 #include "../../include/mcedm_b200.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstdio>
 
 namespace mcedm {
 
@@ -42,14 +44,17 @@ struct WgradParams {
   int a_slot_bytes;        // (W + 2) * 128 rounded up to 1024
   float* partial;          // [gridDim.x][taps][64][64]
   uint32_t idesc;          // M = 128, N = 64, A and B both MN-major, operand format of the launch
+  uint32_t idesc192;       // the same with N = 192 (kx-stacked B operand)
   const float* coef;       // NULL, or fp32 [B][128] = (a | b): `a` is a RAW activation and the operand is act(a*x + b),
                            // applied to each row in shared memory by the (otherwise idle) epilogue warps
   int act;                 // 1 SiLU, 0 identity
   int fmt;                 // 0 bf16, 1 fp16
   unsigned int* err;
+  int dbg;                 // bring-up (MCEDM_WG_DBG): 1 skip the epilogue's stores, 2 skip the MMAs
 };
 
-__global__ void __launch_bounds__(192, 1)
+// 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9 two transform / epilogue SETS (alternate a rows; pair A / pair B)
+__global__ void __launch_bounds__(320, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_a,
                   const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -134,6 +139,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     const uint32_t a_base = smem_u32(a_smem);
     const uint32_t lbo = (uint32_t)p.dy_slot_bytes;
     const int kblocks = p.W >> 4;
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO = 1024 | version 1 | SWIZZLE_128B
+    const uint32_t loA = ((lbo >> 4) & 0x3FFFu) << 16;                         // LBO of the dy operand: one slot
+    const uint32_t loB = ((8192u >> 4) & 0x3FFFu) << 16;                       // LBO of the a operand (unused: one MN block)
+    auto mk = [](uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; };
     uint32_t hbase = 0, waited = 0, ac = 0;
     uint32_t first = 1;
     long long r = r_begin;
@@ -153,25 +162,53 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         // window slots w, w+1, w+2 hold dy rows y'-1, y', y'+1 (mirrors keep them contiguous)
         const uint32_t w0 = dy_base + ((hbase + j) % (uint32_t)S) * lbo;
         const uint32_t arow = a_base + as * (uint32_t)p.a_slot_bytes;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const uint64_t adA = umma_desc_mn_sw128(w0 + lbo + kb * 2048, lbo);    // (ky=1 | ky=0)
-          const uint64_t adB = umma_desc_mn_sw128(w0 + kb * 2048, lbo);          // (ky=2 | duplicate)
-          const uint32_t acc = first ? 0u : 1u;
+        // The issuing thread is this kernel's pacer (ncu: the MMA warp never waits, the transform warps wait 40 % of the
+        // time for their TMA, the tensor pipe is active 29 %): ONE election per row, and every descriptor is (a word
+        // formed once per row) + (a small multiple of the loop counters) - the per-tap elections, 64-bit descriptor
+        // builds and reconvergence barriers of the first version cost ~3800 cycles per row for 1536 cycles of MMAs.
+        const uint32_t a1 = loA | (((w0 + lbo) & 0x3FFFFu) >> 4);    // (ky=1 | ky=0), K block 0
+        const uint32_t a2 = loA | ((w0 & 0x3FFFFu) >> 4);            // (ky=2 | duplicate)
+        const uint32_t b0 = loB | ((arow & 0x3FFFFu) >> 4);          // a row, pixel 0 (= kx 0), K block 0
+        if (elect_one() && !(p.dbg & 2)) {
+          uint32_t acc = first ? 0u : 1u;
           if (p.taps == 9) {
+            if (p.dbg & 4) {        // MCEDM_WG_DBG=4: one N = 64 MMA per (pair, kx) - the first version, A/B switch
+#pragma unroll 2
+              for (int kb = 0; kb < kblocks; ++kb) {
+                const uint64_t adA = mk(a1 + (uint32_t)kb * 128u), adB = mk(a2 + (uint32_t)kb * 128u);   // + kb * 2048 B
+                const uint32_t bk = b0 + (uint32_t)kb * 128u;                                              // + 16 pixels
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const uint64_t bd = umma_desc_mn_sw128(arow + (kb * 16 + kx) * 128, 8192);
-              if (elect_one()) {
-                umma_f16(tmem_base + kx * 64, adA, bd, idesc, acc);
-                umma_f16(tmem_base + (3 + kx) * 64, adB, bd, idesc, acc);
+                for (int kx = 0; kx < 3; ++kx) {
+                  const uint64_t bd = mk(bk + (uint32_t)kx * 8u);                                          // + kx pixels
+                  umma_f16(tmem_base + kx * 64, adA, bd, idesc, acc);
+                  umma_f16(tmem_base + (3 + kx) * 64, adB, bd, idesc, acc);
+                }
+                acc = 1u;
+              }
+            } else {
+              // kx-STACKED B operand: N = 192 = three 64-channel MN blocks whose leading-dimension offset is ONE PIXEL
+              // (128 B): block n is the same a row shifted by n pixels, i.e. the tap kx = n (SWIZZLE_128B is a function
+              // of the absolute shared-memory address, so a block that starts 128 B later is the row-shifted view the
+              // single-tap descriptors already used).  Its 192 accumulator columns are the three 64-column accumulators
+              // (kx = 0, 1, 2) of a pair, which already sit next to each other.  2 MMAs per K block instead of 6: an
+              // N = 64 MMA fetched 4 KB of dy for 2 KB of a (48 shared-memory wavefronts for 32 cycles of math).
+              const uint32_t bst = b0 - loB + ((128u >> 4) << 16);
+#pragma unroll 2
+              for (int kb = 0; kb < kblocks; ++kb) {
+                const uint64_t bd = mk(bst + (uint32_t)kb * 128u);
+                umma_f16(tmem_base, mk(a1 + (uint32_t)kb * 128u), bd, p.idesc192, acc);
+                umma_f16(tmem_base + 192, mk(a2 + (uint32_t)kb * 128u), bd, p.idesc192, acc);
+                acc = 1u;
               }
             }
           } else {
-            const uint64_t bd = umma_desc_mn_sw128(arow + (kb * 16 + 1) * 128, 8192);
-            if (elect_one()) umma_f16(tmem_base + 64, adA, bd, idesc, acc);
+            for (int kb = 0; kb < kblocks; ++kb) {
+              umma_f16(tmem_base + 64, mk(a1 + (uint32_t)kb * 128u), mk(b0 + (uint32_t)kb * 128u + 8u), idesc, acc);
+              acc = 1u;
+            }
           }
-          first = 0;
         }
+        first = 0;
         if (elect_one()) {
           umma_commit(&a_empty[as]);
           umma_commit(&dy_empty[(hbase + j) % (uint32_t)S]);
@@ -194,7 +231,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     // row (pixel 0 and pixel W+1 are the zero halo and stay zero); physical chunk = j ^ (pixel & 7) (SWIZZLE_128B,
     // slots are 1 KB aligned) - the scheme of conv_rows.cu's transform warps.
     if (p.coef != nullptr) {
-      const int t = (int)threadIdx.x - 64;
+      const int xset = ((int)threadIdx.x - 64) >> 7;          // transform set: a rows ac = xset (mod 2)
+      const int t = ((int)threadIdx.x - 64) & 127;
       const int j = t & 7, prow = t >> 3;
       uint32_t ac = 0;
       long long r = r_begin;
@@ -217,6 +255,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
           }
         }
         for (int jr = 0; jr < R; ++jr, ++ac) {
+          if ((int)(ac & 1u) != xset) continue;
           const uint32_t as = ac % (uint32_t)SA, aph = (ac / (uint32_t)SA) & 1u;
           mbar_wait(&a_full[as], aph, p.err, 0x4600 + as);
           const uint32_t base = smem_u32(a_smem) + as * (uint32_t)p.a_slot_bytes;
@@ -269,7 +308,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     tc_fence_after();
     float* base = p.partial + (long long)blockIdx.x * p.taps * 4096;
     const bool has_work = r_end > r_begin;
-    for (int i = 0; i < 6; ++i) {
+    const int eset = (warp - 2) >> 2;          // epilogue set: accumulators of pair A (kx 0..2) / pair B
+    for (int i = 3 * eset; i < 3 * eset + 3; ++i) {
       const int pair = i / 3, kx = i - pair * 3;
       int tap;
       if (p.taps == 9) {
@@ -284,7 +324,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         uint32_t v[32];
         tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + i * 64 + c * 32, v);
         tmem_wait_ld();
-        if (tap >= 0) {
+        if (tap >= 0 && !(p.dbg & 1)) {
           float4* dst = reinterpret_cast<float4*>(base + ((long long)tap * 64 + co) * 64 + c * 32);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -419,18 +459,29 @@ extern "C" int mcedm_conv_wgrad16_fused(const void* dy, int dy_layout, int dy_ct
   p.a_slot_bytes = ((W + 2) * 128 + 1023) / 1024 * 1024;
   // ring depths: ~64 KB of dy rows and ~48 KB of a rows in flight (narrow levels have 2-4 KB rows: the
   // producer has to run many rows ahead of the MMA issuer to hide the TMA round trip)
-  p.n_slots = 65536 / p.dy_slot_bytes;
+  // (with 4 dy slots - 3 of them the MMA window - and 3 a slots at W = 128 the kernel ran at one global-memory latency per
+  // row: 60 of its 85 us at 32 samples were spent with the MMAs AND the epilogue switched off.  MCEDM_WG_SLOTS="S,SA")
+  p.n_slots = 98304 / p.dy_slot_bytes;
   if (p.n_slots < 4) p.n_slots = 4;
   if (p.n_slots > 16) p.n_slots = 16;
-  p.n_aslots = 49152 / p.a_slot_bytes;
+  p.n_aslots = 90112 / p.a_slot_bytes;
   if (p.n_aslots < 3) p.n_aslots = 3;
   if (p.n_aslots > 12) p.n_aslots = 12;
+  if (const char* e = getenv("MCEDM_WG_SLOTS")) {
+    int s_ = 0, sa_ = 0;
+    if (sscanf(e, "%d,%d", &s_, &sa_) == 2 && s_ >= 4 && sa_ >= 3) {
+      p.n_slots = s_;
+      p.n_aslots = sa_;
+    }
+  }
   p.partial = partial;
   p.idesc = umma_idesc_16(128, 64, 1, 1, op_fmt ? 1 : 0);
+  p.idesc192 = umma_idesc_16(128, 192, 1, 1, op_fmt ? 1 : 0);
   p.coef = a_coef;
   p.act = a_act ? 1 : 0;
   p.fmt = op_fmt ? 1 : 0;
   p.err = watchdog_ptr();
+  if (const char* e = getenv("MCEDM_WG_DBG")) p.dbg = atoi(e);
   MCEDM_REQUIRE(p.err != nullptr, "conv_wgrad: cannot allocate the watchdog word");
   CUtensorMap tm_dy, tm_a;
   int rc = make_pix_tmap(&tm_dy, dy, dy_layout, dy_ctotal, B, H, W, W, &p.dy_row_off);
@@ -444,7 +495,7 @@ extern "C" int mcedm_conv_wgrad16_fused(const void* dy, int dy_layout, int dy_ct
     attr_set = true;
   }
   const int grid = wgrad_grid(B, H, W);
-  conv_wgrad_kernel<<<grid, 192, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_dy, tm_a, p);
+  conv_wgrad_kernel<<<grid, 320, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_dy, tm_a, p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }
