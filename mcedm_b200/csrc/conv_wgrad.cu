@@ -53,8 +53,9 @@ struct WgradParams {
   int dbg;                 // bring-up (MCEDM_WG_DBG): 1 skip the epilogue's stores, 2 skip the MMAs
 };
 
-// 320 threads: warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9 two transform / epilogue SETS (alternate a rows; pair A / pair B)
-__global__ void __launch_bounds__(320, 1)
+// 352 threads: warp 0 TMA, warps 1 and 10 MMA issuers (alternate rows, issue order handed over as in conv_rows.cu), warps
+// 2-5 and 6-9 two transform / epilogue SETS (alternate a rows; pair A / pair B)
+__global__ void __launch_bounds__(352, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_a,
                   const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -69,7 +70,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
   uint64_t* a_full = dy_empty + S;
   uint64_t* a_empty = a_full + SA;
   uint64_t* a_ready = a_empty + SA;            // row transformed and visible to the async proxy (p.coef only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + SA);
+  uint64_t* turn = a_ready + SA;                // 2: issue-order hand-over between the two MMA warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r_begin = p.total_rows * blockIdx.x / gridDim.x;
@@ -88,6 +90,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
       mbar_init(&a_empty[i], 1);
       mbar_init(&a_ready[i], 4);
     }
+    mbar_init(&turn[0], 1);
+    mbar_init(&turn[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -132,8 +136,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         r += R;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     // ====================================== MMA issuer ======================================
+    // Two issuing warps run the same control flow (every barrier phase is observed by both) and issue alternate rows:
+    // tcgen05.mma queues only ~2 instructions deep, so one issuer's waits, commits and loop control left the tensor pipe
+    // idle ~1000 cycles per row.  All rows accumulate into the same TMEM columns: the issue ORDER is handed over through
+    // turn[] right after a row's last MMA (the pipe executes in issue order), and commits - which track only their own
+    // thread's MMAs - therefore also cover the other warp's earlier rows.
+    const uint32_t my_par = (warp == 1) ? 0u : 1u;
+    uint32_t my_n = 0, last_par = 0;
     const uint32_t idesc = p.idesc;
     const uint32_t dy_base = smem_u32(dy_smem);
     const uint32_t a_base = smem_u32(a_smem);
@@ -169,7 +180,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
         const uint32_t a1 = loA | (((w0 + lbo) & 0x3FFFFu) >> 4);    // (ky=1 | ky=0), K block 0
         const uint32_t a2 = loA | ((w0 & 0x3FFFFu) >> 4);            // (ky=2 | duplicate)
         const uint32_t b0 = loB | ((arow & 0x3FFFFu) >> 4);          // a row, pixel 0 (= kx 0), K block 0
-        if (elect_one() && !(p.dbg & 2)) {
+        const bool mine = (ac & 1u) == my_par;
+        last_par = ac & 1u;
+        if (mine) {
+          if (my_par == 1u) mbar_wait(&turn[1], my_n & 1u, p.err, 0x4a01);
+          else if (my_n > 0) mbar_wait(&turn[0], (my_n - 1u) & 1u, p.err, 0x4a00);
+        }
+        if (mine && elect_one() && !(p.dbg & 2)) {
           uint32_t acc = first ? 0u : 1u;
           if (p.taps == 9) {
             if (p.dbg & 4) {        // MCEDM_WG_DBG=4: one N = 64 MMA per (pair, kx) - the first version, A/B switch
@@ -209,7 +226,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
           }
         }
         first = 0;
-        if (elect_one()) {
+        if (mine && elect_one()) {
+          mbar_arrive(&turn[my_par ^ 1u]);         // row issued: the other warp may issue the next one
           umma_commit(&a_empty[as]);
           umma_commit(&dy_empty[(hbase + j) % (uint32_t)S]);
           if (j == R - 1) {
@@ -218,12 +236,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
           }
         }
         __syncwarp();
+        if (mine) ++my_n;
         ++ac;
       }
       hbase += R + 2;
       r += R;
     }
-    if (elect_one()) umma_commit(acc_full);
+    if ((ac == 0 ? my_par == 0u : last_par == my_par) && elect_one()) umma_commit(acc_full);   // by the last row's issuer
     __syncwarp();
   } else {
     // ============== GroupNorm + SiLU transform of the `a` rows (raw activations), then the epilogue ==============
@@ -495,7 +514,7 @@ extern "C" int mcedm_conv_wgrad16_fused(const void* dy, int dy_layout, int dy_ct
     attr_set = true;
   }
   const int grid = wgrad_grid(B, H, W);
-  conv_wgrad_kernel<<<grid, 320, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_dy, tm_a, p);
+  conv_wgrad_kernel<<<grid, 352, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm_dy, tm_a, p);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }
