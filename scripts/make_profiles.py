@@ -147,7 +147,8 @@ DRAM: {g_read:.0f} MB read per launch = x and dy (67 MB each) TWICE: with all 32
 exceeds what one L2 partition keeps, so pass 2 misses although it re-reads the same slice ~40 us later; what the one-kernel
 form buys is the launch and, with the per-thread cp.async ring (three 64-byte batches per thread in flight, loads no longer
 alternate with ~400 instructions of arithmetic per thread), 14-16 % of the time.  Achieved occupancy stays at 21 % (256 CTAs
-of 256 threads, 2 resident per SM).  Next step: waves of 8 samples so that pass 2 hits L2.
+of 256 threads, 2 resident per SM).  Waves of 8 samples (4 MB each) so that pass 2 hits L2 were tried and measured SLOWER (108.5 vs 88.1 us: four rounds of
+per-sample hand-over and pipeline ramp per CTA cost more than the L2 hits return).
 
 """
 md += summ(f"{O}/r2f_gnbwd.ncu-rep", [1])
