@@ -33,4 +33,12 @@ run $T python scripts/train_bench.py 32 5 > $O/r2f_train_plain.log 2>&1 && \
       python scripts/train_bench.py 32 2 > $O/r2f_train_ncu.log 2>&1
 python scripts/eval_breakdown.py 256 > $O/r2f_eval_breakdown.txt 2>&1
 fi
+if [ "$PART" = 3 ]; then      # training-side refresh only: weight-gradient kernel + the step's launch list
+run $T python scripts/train_breakdown.py 32 fused16 > $O/r2f_tb_fused16.txt 2>&1 && \
+  run $T $NCU -k regex:conv_wgrad --launch-skip 198 -c 8 -f -o $O/r2f_wgrad python scripts/train_breakdown.py 32 fused16 > $O/r2f_wgrad_ncu.log 2>&1
+run $T python scripts/wgrad_bench.py > $O/r2f_wgrad_plain.log 2>&1
+run $T python scripts/train_bench.py 32 5 > $O/r2f_train_plain.log 2>&1 && \
+  run $T ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r2f_launches_train_B32.csv \
+      python scripts/train_bench.py 32 2 > $O/r2f_train_ncu.log 2>&1
+fi
 ls -la $O | grep r2f

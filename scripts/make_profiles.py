@@ -156,10 +156,18 @@ h, u, b = raw(f"{O}/r2f_wgrad.ncu-rep")
 md += f"""
 ## conv_wgrad_kernel (weight gradient with the GroupNorm+SiLU operand formed in shared memory)
 
-Launches 0, 1 = 3x3 at 128x128 (conv1 / conv0 of a 128x128 block, 38.7 GFLOP each: {val(h, b[0], DUR):.0f} / {val(h, b[1], DUR):.0f} us under the
-profiler = ~450 TFLOP/s; tensor pipe {val(h, b[0], TEN):.1f} % active - the six [128 x 64] accumulators per CTA use N = 64 MMAs that re-read a
-4 KB A tile for every 2 KB of B, and pair B = (ky = 2 | duplicate) wastes a quarter of the issued FLOPs); launches 2, 3 = the
-1x1 skip projection's two sources (HBM-bound: 139 MB in {val(h, b[2], DUR):.0f} us).
+Final form: straight-line MMA issue (one election per row, descriptors by 32-bit adds), kx-stacked N = 192 B operand
+(three MN blocks ONE PIXEL = 128 B apart: 2 MMAs per K block instead of 6), two MMA-issuing warps on alternate rows, two
+transform / epilogue warp sets.  Launches 0, 1 = 3x3 at 128x128 (conv1 / conv0 of a 128x128 block, 38.7 GFLOP each):
+{val(h, b[0], DUR):.0f} / {val(h, b[1], DUR):.0f} us under the profiler, tensor pipe {val(h, b[0], TEN):.1f} % active (the first version of this round: 83-87 us, 28.8 % -
+its single issuing thread was the pacer: ~3800 cycles of elections, 64-bit descriptor builds and reconvergence barriers per
+row for 1536 cycles of MMAs, and an N = 64 MMA fetched 48 shared-memory wavefronts for 32 cycles of math); launches 2, 3 =
+the 1x1 skip projection's two sources (HBM-bound: 139 MB in {val(h, b[2], DUR):.0f} us).  CUDA events outside the profiler
+(`scripts/wgrad_bench.py`, `gpurun_out/r2f_wgrad_plain.log`; the first version: 82 / 267 / 54 / 34 / 29 us for the first
+five lines below):
+
+```
+{lines(f'{O}/r2f_wgrad_plain.log', lambda l: l.startswith('B=') and 'xf=1' in l)}```
 
 """
 md += summ(f"{O}/r2f_wgrad.ncu-rep", [0, 2])
@@ -206,8 +214,8 @@ Command (`scripts/capture_profiles.sh 1`): `python scripts/train_bench.py 32 5 >
 branch of the graph and fill the gaps and tails of the data-gradient chain.  Round 1: 9.6 ms per step.
 
 {tr}
-`conv_wgrad_kernel` ~30 % (66 launches: 16 at 128x128 of ~75 us, 50 at 64x64 / 32x32 of ~28 us - fixed-cost bound at
-32 samples), `gn_bwd16` ~22 % (both passes in one kernel; `<0,0>` = the four resampling blocks), the data-gradient convs
+`conv_wgrad_kernel` ~22 % (66 launches: 16 at 128x128 of ~50 us, 50 at 64x64 / 32x32 - fixed-cost bound at
+32 samples; 30 % / ~75 us before the issue-loop rewrite), `gn_bwd16` ~24 % (both passes in one kernel; `<0,0>` = the four resampling blocks), the data-gradient convs
 (`conv_rows<64,1,0,0>` x11, `conv_flat<64,1,0>` x26: the forward kernels on 16-bit gradients) ~11 %, the forward's fused
 convs ~12 %.  Per-call CUDA-event times of the same step run eagerly (`scripts/train_breakdown.py 32 fused16`):
 
