@@ -357,3 +357,52 @@ def test_fp16_activation_storage_at_range_and_saturation_audit(L, dev):
         else:
             os.environ["MCEDM_DBG"] = old
     L.check_watchdog()
+
+
+def _with_env(name, value, fn):
+    import os
+
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("H,W,res", [(64, 64, False), (32, 32, True)])
+def test_conv_flat_fused_direct_load_path_is_bit_identical_to_the_tma_path(L, dev, H, W, res):
+    """conv_flat_fused's transform warps either rewrite a TMA-loaded chunk in place (MCEDM_DBG=16) or load the raw chunk
+    from global memory themselves (default): same arithmetic, so outputs and GroupNorm records must be bit-identical."""
+    lib = L.lib()
+    B = 5
+    pitch, blk = C.c_int(0), C.c_int(0)
+    L.check(lib.mcedm_flat_geometry(H, W, C.byref(pitch), C.byref(blk)))
+    P, blk = pitch.value, blk.value
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.zeros(B, blk, 64)
+    img = torch.randn(B, H, W, 64, generator=g)
+    for y in range(H):
+        x[:, (y + 1) * P:(y + 1) * P + W] = img[:, y]
+    x = x.reshape(B * blk, 64).to(dev).half()
+    r = x.clone() if res else None
+    coef = torch.cat([torch.rand(B, 64, generator=g) + 0.5, torch.randn(B, 64, generator=g) * 0.3], 1).to(dev).contiguous()
+    w = pack_conv3x3((torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev), dtype=torch.float16)
+    bias = torch.randn(64, generator=g).to(dev)
+
+    def run():
+        out = torch.zeros(B * blk, 64, device=dev, dtype=torch.float16)
+        st = torch.zeros(B * blk // 128, 4, 16, 2, device=dev)
+        L.check(lib.mcedm_conv_flat_fused(L.ptr(x), L.ptr(coef), L.ptr(w), L.ptr(bias), B, H, W, 64, L.ptr(out), 0, L.ptr(r),
+                                          1 if res else 0, 0, 0, 0, L.ptr(st), 1, L.stream_ptr()), "conv_flat_fused")
+        torch.cuda.synchronize()
+        L.check_watchdog()
+        return out, st
+
+    o_ldg, s_ldg = run()
+    o_tma, s_tma = _with_env("MCEDM_DBG", "16", run)
+    assert torch.equal(o_ldg, o_tma) and torch.equal(s_ldg, s_tma)
+    assert float(o_ldg.float().abs().mean()) > 0.05

@@ -227,3 +227,41 @@ def test_pad16_and_colsum16(L, dev):
         part = torch.empty(7, 64, device=dev)
         L.check(lib.mcedm_colsum16(L.ptr(pad), B * H * W, 64, 0, L.ptr(part), 7, fmt, L.stream_ptr()))
         assert rel_l2(part.sum(0)[:4], ref.float().sum((0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("H,W,taps", [(128, 128, 9), (32, 32, 9), (64, 64, 1)])
+def test_wgrad_kx_stacked_operand_is_bit_identical_to_one_mma_per_tap(dev, H, W, taps):
+    """conv_wgrad16_fused issues one N = 192 MMA per K block whose B operand is three 64-channel blocks ONE PIXEL apart
+    (leading-dimension offset 128 B: the kx taps); MCEDM_WG_DBG=4 issues the three N = 64 MMAs separately.  Same products
+    in the same order per accumulator column: the per-CTA partial sums must be bit-identical."""
+    import os
+
+    from mcedm_b200 import _lib as L
+    lib = L.lib()
+    B = 3
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dy = (torch.randn(B, H, W, 64, generator=g) * 0.1).to(dev).half()
+    a = torch.randn(B, H, W, 64, generator=g).to(dev).half()
+    coef = torch.cat([torch.rand(B, 64, generator=g) + 0.5, torch.randn(B, 64, generator=g) * 0.3], 1).to(dev).contiguous()
+    nc = lib.mcedm_wgrad_ctas(B, H, W)
+
+    def run():
+        part = torch.zeros(nc * taps * 4096, device=dev)
+        L.check(lib.mcedm_conv_wgrad16_fused(L.ptr(dy), 0, 64, 0, L.ptr(a), 0, 64, 0, L.ptr(coef), 1, B, H, W, taps, L.ptr(part),
+                                             1, L.stream_ptr()), "conv_wgrad")
+        torch.cuda.synchronize()
+        L.check_watchdog()
+        return part
+
+    p_stacked = run()
+    old = os.environ.get("MCEDM_WG_DBG")
+    os.environ["MCEDM_WG_DBG"] = "4"
+    try:
+        p_single = run()
+    finally:
+        if old is None:
+            os.environ.pop("MCEDM_WG_DBG", None)
+        else:
+            os.environ["MCEDM_WG_DBG"] = old
+    assert torch.equal(p_stacked, p_single)
+    assert float(p_stacked.abs().sum()) > 0
