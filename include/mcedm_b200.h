@@ -567,29 +567,16 @@ MCEDM_API int mcedm_corr_minmax(const double* pred, const float* target, int b, 
                                 double* min_bc, double* max_bc, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
-/* bring-up / checker kernels (tests only; not on the product path)                              */
+/* bring-up instrumentation of the product kernels (the checker / probe kernels live in their own   */
+/* library: include/mcedm_b200_check.h, libmcedm_b200_check.so)                                     */
 /* -------------------------------------------------------------------------------------------- */
-/* tensor-pipe + shared-memory operand-fetch ceiling: every SM issues n_tiles x 36 tcgen05.mma (M=128, N, K=16, the conv
- * kernels' descriptor pattern) and nothing else; cycles_per_cta[sm] = clock64 ticks (DEVICE int64 [#SMs]). */
 /* Saturation audit of the fp16 activation storage: with MCEDM_DBG=4 in the environment the fused 16-bit convolution
  * epilogues (conv_rows_fused N=64, conv_flat_fused fast paths) count every accumulator / output value whose magnitude
  * exceeds 65504 (clamped by the saturating conversion) or is NaN; *host_out receives the count since the last reset. */
 MCEDM_API int mcedm_saturation_count(long long* host_out, int reset, void* stream);
-MCEDM_API int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_cta, void* stream);
-/* issue-queue depth of tcgen05.mma: per iteration n_mma x (M=128, N=192, K=16) + one commit, then `idle` cycles of
- * nothing on the issuing warp; out3_per_cta[sm] = {total, issue, commit} clock64 ticks (DEVICE int64 [#SMs][3]). */
-MCEDM_API int mcedm_probe_mma_queue(int iters, int n_mma, int idle, long long* out3_per_cta, void* stream);
 /* bring-up: per-CTA cycles spent in each role's barrier waits by the last fused conv_rows launch run with MCEDM_DBG=32
  * (HOST int64 [160][8]: h_empty, acc_empty, h_ready, acc_full, h_full waits; epilogue, MMA, producer role totals) */
 MCEDM_API int mcedm_debug_rows(long long* host_out);
-MCEDM_API int mcedm_probe_umma(const void* a, int a_rows, const void* bm, int row_shift, int base_offset, int b_mn_major,
-                     float* out, void* stream);
-/* seg_dev: DEVICE int array [n_seg][3] = (src, dy, dx). Same math as mcedm_conv_igemm on CUDA cores. */
-MCEDM_API int mcedm_conv_direct_ref(const void* const* src, int n_src, const int* seg_dev, int n_seg, const void* w_packed,
-                          const float* bias, int B, int H, int W, int N, float* out, const float* res, int res_mode,
-                          void* stream);
-/* fp32 CUDA-core attention on the same bf16 qkv (out fp32 [B,L,64]) */
-MCEDM_API int mcedm_attention_ref(const void* qkv_bf16, int B, int L, float* out_f32, void* stream);
 
 #ifdef __cplusplus
 }

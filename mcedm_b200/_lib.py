@@ -72,7 +72,6 @@ _PROTOTYPES = {
     "mcedm_attention": [_vp, _i, _i, _vp, _vp, _i, _vp],
     "mcedm_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mcedm_attention_bwd16": [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
-    "mcedm_attention_ref": [_vp, _i, _i, _vp, _vp],
     "mcedm_emb_mlp": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "mcedm_conv_in": [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mcedm_head_to_nchw": [_vp, _i, _i, _i, _i, _i, _vp, _vp],
@@ -102,13 +101,18 @@ _PROTOTYPES = {
                               _vp, _vp],
     "mcedm_corr_minmax": [_vp, _vp, _i, C.c_longlong, _i, _vp, _vp, _vp, _vp],
     "mcedm_saturation_count": [_llp, _i, _vp],
-    "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
-    "mcedm_probe_mma_queue": [_i, _i, _i, _vp, _vp],
     "mcedm_debug_rows": [_vp],
-    "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
-    "mcedm_conv_direct_ref": [_vpp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
 }
 _RESTYPES = {"mcedm_last_error": C.c_char_p}
+# checker / probe kernels: libmcedm_b200_check.so (include/mcedm_b200_check.h), loaded by tests and scripts only
+_CHECK_PROTOTYPES = {
+    "mcedm_probe_mma_rate": [_i, _i, _vp, _vp],
+    "mcedm_probe_mma_queue": [_i, _i, _i, _vp, _vp],
+    "mcedm_probe_umma": [_vp, _i, _vp, _i, _i, _i, _vp, _vp],
+    "mcedm_conv_direct_ref": [_vpp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp],
+    "mcedm_attention_ref": [_vp, _i, _i, _vp, _vp],
+}
+CHECK_LIB_PATH = os.path.join(_HERE, "lib", "libmcedm_b200_check.so")
 
 _lib = None
 # number of kernel launches issued through the C ABI by this process (every successful call below launches
@@ -147,10 +151,35 @@ def lib():
     return _lib
 
 
-def check(rc: int, what: str = ""):
+_check_lib = None
+
+
+def check_exported_names():
+    """Every symbol include/mcedm_b200_check.h declares."""
+    return sorted(_CHECK_PROTOTYPES)
+
+
+def check_lib():
+    """The checker / probe library (test infrastructure): not needed, and never loaded, by the product path."""
+    global _check_lib
+    if _check_lib is None:
+        if not os.path.exists(CHECK_LIB_PATH):
+            raise McedmError(f"{CHECK_LIB_PATH} is missing: build it with `python -m mcedm_b200.build`")
+        l = C.CDLL(CHECK_LIB_PATH)
+        for name, args in _CHECK_PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        l.mcedm_last_error.argtypes = []
+        l.mcedm_last_error.restype = C.c_char_p
+        _check_lib = l
+    return _check_lib
+
+
+def check(rc: int, what: str = "", lib_=None):
     LAUNCHES[0] += 1
     if rc != 0:
-        msg = lib().mcedm_last_error()
+        msg = (lib_ or lib()).mcedm_last_error()
         raise McedmError(f"{what or 'mcedm call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
 
 

@@ -17,6 +17,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmcedm_b200.so")
+# checker / probe kernels (tests and scripts only): their own library, linked with a private copy of the runtime
+CHECK_LIB = os.path.join(LIBDIR, "libmcedm_b200_check.so")
+CHECK_SOURCES = ("probe.cu",)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -74,13 +77,16 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
                 sys.stderr.write(f"[mcedm_b200.build] {name}\n{r.stdout}{r.stderr}\n")
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {name}")
-    relink = bool(jobs) or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
-    if relink:
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("link of libmcedm_b200.so failed")
+    check_objs = [o for o in objs if os.path.basename(o)[:-2] + ".cu" in CHECK_SOURCES]
+    prod_objs = [o for o in objs if o not in check_objs]
+    for lib, members in ((LIB, prod_objs), (CHECK_LIB, check_objs + [os.path.join(OBJ, "runtime.o")])):
+        relink = bool(jobs) or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in members)
+        if relink:
+            cmd = [nvcc, "-shared", "-o", lib, *members, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"link of {os.path.basename(lib)} failed")
     return LIB
 
 

@@ -7,7 +7,7 @@
 //                             mcedm_conv_igemm, used by the GPU tests as an on-device cross-check.
 #include "ptx.cuh"
 #include "runtime.cuh"
-#include "../../include/mcedm_b200.h"
+#include "../../include/mcedm_b200_check.h"
 
 #include <cuda_bf16.h>
 
@@ -177,6 +177,39 @@ __global__ void __launch_bounds__(64, 1) probe_mma_rate_kernel(int n_tiles, long
     tmem_dealloc(tmem_base, 256);
   }
 }
+// CUDA-core fp32 checker (tests only): one warp per query.
+__global__ void attn_ref_kernel(const __nv_bfloat16* __restrict__ qkv, int L, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (qi >= L) return;
+  const __nv_bfloat16* base = qkv + (long long)b * L * 192;
+  float qv[64];
+  for (int c = 0; c < 64; ++c) qv[c] = __bfloat162float(base[(long long)qi * 192 + c]);
+  float m = -INFINITY;
+  for (int j = lane; j < L; j += 32) {
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s += qv[c] * __bfloat162float(base[(long long)j * 192 + 64 + c]);
+    m = fmaxf(m, s * 0.125f);
+  }
+  for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float l = 0.f, acc[64];
+  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+  for (int j = lane; j < L; j += 32) {
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s += qv[c] * __bfloat162float(base[(long long)j * 192 + 64 + c]);
+    const float p = expf(s * 0.125f - m);
+    l += p;
+    for (int c = 0; c < 64; ++c) acc[c] += p * __bfloat162float(base[(long long)j * 192 + 128 + c]);
+  }
+  for (int off = 16; off; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+  for (int c = 0; c < 64; ++c) {
+    float a = acc[c];
+    for (int off = 16; off; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) out[((long long)b * L + qi) * 64 + c] = a / l;
+  }
+}
+
 }  // namespace mcedm
 
 extern "C" int mcedm_probe_mma_rate(int N, int n_tiles, long long* cycles_per_cta, void* stream) {
@@ -319,6 +352,15 @@ extern "C" int mcedm_conv_direct_ref(const void* const* src, int n_src, const in
   conv_direct_ref_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       s[0], s[1], s[2], s[3], seg_dev, n_seg, reinterpret_cast<const __nv_bfloat16*>(w_packed), bias, B, H, W, N, out,
       res, res_mode);
+  MCEDM_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mcedm_attention_ref(const void* qkv_bf16, int B, int L, float* out_f32, void* stream) {
+  using namespace mcedm;
+  dim3 grid((L + 3) / 4, B);
+  attn_ref_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), L, out_f32);
   MCEDM_CUDA(cudaGetLastError());
   return 0;
 }

@@ -11,7 +11,7 @@ for n_mma in (12, 24):
     for idle in (0, 100, 200, 400, 800, 1200, 1600):
         out = torch.zeros(n_sm, 3, dtype=torch.int64, device=dev)
         for _ in range(2):
-            L.check(lib.mcedm_probe_mma_queue(iters, n_mma, idle, L.ptr(out), L.stream_ptr()))
+            L.check(L.check_lib().mcedm_probe_mma_queue(iters, n_mma, idle, L.ptr(out), L.stream_ptr()))
         torch.cuda.synchronize()
         L.check_watchdog()
         m = out.double().mean(0) / iters

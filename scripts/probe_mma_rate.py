@@ -9,10 +9,10 @@ n_sm = torch.cuda.get_device_properties(0).multi_processor_count
 for N in (64, 128):
     for tiles in (110, 1100):
         cyc = torch.zeros(n_sm, dtype=torch.int64, device=dev)
-        L.check(lib.mcedm_probe_mma_rate(N, tiles, L.ptr(cyc), L.stream_ptr()))
+        L.check(L.check_lib().mcedm_probe_mma_rate(N, tiles, L.ptr(cyc), L.stream_ptr()))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        L.check(lib.mcedm_probe_mma_rate(N, tiles, L.ptr(cyc), L.stream_ptr()))
+        L.check(L.check_lib().mcedm_probe_mma_rate(N, tiles, L.ptr(cyc), L.stream_ptr()))
         e1.record()
         torch.cuda.synchronize()
         L.check_watchdog()

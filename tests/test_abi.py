@@ -42,6 +42,21 @@ def test_python_binding_covers_the_header(libpath):
     _lib.lib()
 
 
+def test_checker_library_is_separate_from_the_product_library(libpath):
+    """Probe / checker kernels (test infrastructure) live in libmcedm_b200_check.so with their own header; the product
+    library exports none of them."""
+    from mcedm_b200 import _lib, build
+
+    src = open(os.path.join(ROOT, "include", "mcedm_b200_check.h")).read()
+    declared = sorted(set(re.findall(r"MCEDM_API\s+(?:const\s+)?\w+\*?\s+(mcedm_\w+)\s*\(", src)))
+    assert declared == _lib.check_exported_names() and len(declared) == 5
+    chk = ctypes.CDLL(build.CHECK_LIB)
+    prod = ctypes.CDLL(libpath)
+    for name in declared:
+        assert hasattr(chk, name), name
+        assert not hasattr(prod, name), f"{name} must not ship in the product library"
+
+
 def test_sass_contains_blackwell_tensor_and_tma_instructions(libpath):
     import shutil
     import subprocess

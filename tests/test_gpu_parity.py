@@ -153,7 +153,7 @@ def test_umma_row_shifted_descriptor(L, dev):
     for b_mn in (0, 1):
         for shift in (0, 1, 2, 7, 9, 16):
             out = torch.full((128, 64), float("nan"), device=dev)
-            L.check(lib.mcedm_probe_umma(L.ptr(a), 144, L.ptr(bm), shift, 0, b_mn, L.ptr(out), L.stream_ptr()))
+            L.check(L.check_lib().mcedm_probe_umma(L.ptr(a), 144, L.ptr(bm), shift, 0, b_mn, L.ptr(out), L.stream_ptr()))
             L.check_watchdog()
             ref = a[shift:shift + 128].float() @ (bm.float() if b_mn else bm.float().t())
             assert (out - ref).abs().max().item() < 1e-4
@@ -195,7 +195,7 @@ def test_attention_matches_fp32_softmax(L, dev, B, Lq, scale):
     ref = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=2) @ v
     assert rel_l2(out.float(), ref) < 5e-3                         # bf16 P and bf16 output rounding
     chk = torch.empty(B, Lq, 64, device=dev)
-    L.check(lib.mcedm_attention_ref(L.ptr(qkv), B, Lq, L.ptr(chk), L.stream_ptr()))
+    L.check(L.check_lib().mcedm_attention_ref(L.ptr(qkv), B, Lq, L.ptr(chk), L.stream_ptr()))
     assert rel_l2(chk, ref) < 1e-5
 
 
