@@ -85,9 +85,12 @@ struct FlatCfg {
   // WG (fused): roles laid out on warpgroup boundaries so that setmaxnreg can move registers between them:
   //   warps 0-3 TMA | MMA | MMA 2 | idle,  warps 4-11 epilogue,  warps 12-19 transform (EIGHT warps: with both MMA warps
   //   issuing, the four transform warps were this kernel's pacer).  640 threads launch at 96 registers; the transform
-  //   groups drop to 72, the first group to 80, and the two epilogue groups take 128 (what they needed at 480 threads).
-  //   setmaxnreg only moves registers INSIDE the CTA's launch allocation: 4 x 32 x 16 + 8 x 32 x 24 released = 8 x 32 x 32
-  //   acquired, exactly (an inc that outruns the decs never returns).
+  //   groups and the first group drop to 80, the two epilogue groups take 120 (what they needed at 480 threads).
+  //   setmaxnreg only moves registers INSIDE the CTA's launch allocation: 4 x 32 x 16 + 8 x 32 x 16 released = 8 x 32 x 24
+  //   acquired (an inc that outruns the decs never returns).  `.aligned` means every warp of a warpgroup executes the SAME
+  //   setmaxnreg instruction: each group has exactly one site (a dec per role branch of the first group - three
+  //   different instructions - is undefined behaviour; it ran, and is the suspect of one launch failure in 8 x 99 x 8
+  //   evaluations of an 8-GPU run).
   static constexpr bool WG = FUSED && DUAL && MCEDM_FLAT_WG;
   static constexpr int XF_WARPS = FUSED ? (WG ? 8 : 4) : 0;
   static constexpr int THREADS = WG ? 640 : 64 + 32 * EPI_WARPS + 32 * XF_WARPS + (DUAL ? 32 : 0);
@@ -239,9 +242,12 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   pdl_wait();
   pdl_trigger();
 
-  // (WG: every role branch starts with its warpgroup's setmaxnreg, so that ptxas budgets the branch accordingly)
+  // (WG: every warpgroup has exactly ONE setmaxnreg site, and it dominates the group's role code so that ptxas budgets that
+  // code accordingly: the first group's three roles therefore sit inside one block)
+  const bool wg0 = Cfg::WG ? (warp < 4) : (warp == 0 || warp == 1 || warp == Cfg::MMA2_WARP);
+  if (wg0) {
+  if constexpr (Cfg::WG) setmaxnreg_dec<80>();
   if (warp == 0) {
-    if constexpr (Cfg::WG) setmaxnreg_dec<80>();
     // ===================================== TMA producer =====================================
     // local chunk k (0 .. n_tiles+1) = global chunk t_begin - 1 + k; tile j uses chunks j, j+1, j+2
     if (lane == 0) {
@@ -256,7 +262,6 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
     }
   } else if (warp == 1 || warp == Cfg::MMA2_WARP) {
-    if constexpr (Cfg::WG) setmaxnreg_dec<80>();
     // ====================================== MMA issuer ======================================
     // warp-uniform control flow, one elected lane issues (see conv_rows.cu)
     // DUAL (fused kernel): two warps take alternate tiles.  Tiles own separate accumulators, but the chunk ring is
@@ -332,9 +337,10 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         slot = s1;
       }
     }
+  }
   } else if (!FUSED || (warp >= Cfg::EPI_W0 && warp < Cfg::EPI_W0 + Cfg::EPI_WARPS)) {
     // ======================================= epilogue =======================================
-    if constexpr (Cfg::WG) setmaxnreg_inc<120>();
+    if constexpr (Cfg::WG) setmaxnreg_inc<120>();     // (the ONE setmaxnreg instruction of the two epilogue warpgroups)
     const int q = warp & 3;
     const int ew = warp - Cfg::EPI_W0;
     const int ch = ew >> 2;
@@ -570,7 +576,7 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // ============================ GroupNorm + SiLU transform (FUSED) ============================
     // thread t owns the logical 16-byte chunk jc = t & 7 (channels 8jc .. 8jc+7) of positions (t >> 3) + 16 i of every
     // 128-position chunk; physical 16-byte slot = jc ^ (position & 7) (SWIZZLE_128B, 1 KB-aligned chunk slots).
-    if constexpr (Cfg::WG) setmaxnreg_dec<80>();
+    if constexpr (Cfg::WG) setmaxnreg_dec<80>();      // (the ONE setmaxnreg instruction of the two transform warpgroups)
     const int tx = (int)threadIdx.x - 32 * Cfg::XF_W0;
     const int xset = tx / (32 * Cfg::XF_SET_WARPS);           // this thread's set: chunks k = xset (mod XF_SETS)
     const int t = tx - xset * (32 * Cfg::XF_SET_WARPS);
@@ -687,8 +693,6 @@ conv_flat_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       }
       mbar_arrive_warp(&c_ready[slot]);
     }
-  } else {
-    if constexpr (Cfg::WG) setmaxnreg_dec<80>();    // the idle fourth warp of the first group
   }
 
   tc_fence_before();
