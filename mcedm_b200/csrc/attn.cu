@@ -101,6 +101,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       any |= flags[tile] != 0u;
     if (!__syncthreads_or(any)) return;
   }
+  // TMEM is allocated ONCE per CTA: tcgen05.relinquish_alloc_permit gives the right to allocate up for the rest of the
+  // CTA's life, so a second allocation by a fallback CTA that redoes more than one flagged tile is a device exception
+  // ("unspecified launch failure": seen at 256 samples per call, where a CTA strides over 14 tiles, as soon as one CTA had
+  // two flagged tiles; the 2-sample test gave every CTA at most one).
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
   bool first_tile = true;
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x) {
   if (!SINGLE && flags != nullptr && flags[tile] == 0u) continue;
@@ -126,10 +134,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
       mbar_init(&kv_empty[i], 1);
     }
     fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
   }
   if (H2 && warp >= 2 && warp < 10) {
     // all-ones tile (uniform, so the 128-byte swizzle does not matter), made visible to the async proxy
@@ -384,13 +388,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tm_qkv, int L, __nv_bfloat16* __
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+  tc_fence_after();
   first_tile = false;
-  __syncthreads();
   }   // tile loop
+  if (warp == 1) tmem_dealloc(*tmem_slot, 512);
 }
 
 }  // namespace mcedm

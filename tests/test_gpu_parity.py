@@ -233,6 +233,34 @@ def test_attention_single_pass_overflow_falls_back_to_two_pass(L, dev, fmt):
     assert rel_l2(out[1].float(), out2[1].float()) < tol
 
 
+def test_attention_overflow_fallback_redoes_several_tiles_per_cta(L, dev):
+    """The fallback launch is a 148-CTA grid striding over the tiles: at the sampler's batch sizes a CTA redoes MORE THAN
+    ONE flagged tile (here tiles 0-7 of sample 0 and tiles 296-303 = 0-7 + 2 x 148 of sample 37 land on the same CTAs).
+    Regression test: the kernel used to allocate TMEM per tile after relinquishing its allocation permit - a device
+    exception on a CTA's second tile, first seen on one rank of an 8-GPU sampling run."""
+    lib = L.lib()
+    B, Lq = 40, 1024
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(B, Lq, 64, generator=g) * 1.5
+    k = torch.randn(B, Lq, 64, generator=g)
+    v = torch.randn(B, Lq, 64, generator=g)
+    hot = [0, 20, 37]
+    for s in hot:
+        k[s] = k[s] * 0.05
+        k[s, 896:] = q[s, :128] * 1.2
+    qkv = torch.cat([q, k, v], dim=2).to(dev).half().contiguous()
+    out = torch.full((B, Lq, 64), float("nan"), device=dev, dtype=torch.float16)
+    for _ in range(2):
+        L.check(lib.mcedm_attention(L.ptr(qkv), B, Lq, L.ptr(out), None, 1, L.stream_ptr()), "attention")
+        torch.cuda.synchronize()
+        L.check_watchdog()
+    assert torch.isfinite(out.float()).all()
+    for s in hot + [1, 39]:
+        qd, kd, vd = qkv[s].double().split(64, dim=1)
+        ref = torch.softmax(qd @ kd.t() / 8.0, dim=1) @ vd
+        assert rel_l2(out[s].float(), ref) < 2e-3, s
+
+
 # ----------------------------------------------------------------------------------------------- K5
 def test_sampler_updates_bit_exact_against_torch_fp64(L, dev):
     lib = L.lib()
