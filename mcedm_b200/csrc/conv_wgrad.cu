@@ -418,7 +418,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_batched_kernel(const mcedm_w
 }
 
 static int wgrad_grid(int B, int H, int W) {
-  long long g = (long long)B * H * W / 512;
+  // pixels per CTA >= 256 (was 512: at 32x32 and 32 samples only 64 of the 148 SMs had work)
+  static int div = 0;
+  if (!div) {
+    const char* e = getenv("MCEDM_WG_DIV");
+    div = e ? atoi(e) : 256;
+    if (div < 128) div = 128;
+  }
+  long long g = (long long)B * H * W / div;
   if (g < 1) g = 1;
   if (g > num_sms()) g = num_sms();
   if (g > (long long)B * H) g = (long long)B * H;
